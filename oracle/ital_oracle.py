@@ -1,0 +1,360 @@
+"""CPU float64 restatement of ITAL's batch-selection hot path -- ORACLE (test infrastructure only).
+
+This file restates, in numpy, what the reference computes on the path
+``ITAL.fetch_unlabelled`` -> ``AppendedMutualInformation`` -> ``MutualInformation`` -> ``GaussianProcess``
+(/root/reference/ital/ital.py:84-134, 183-224, 278-383, 432-481, 485-586; /root/reference/ital/gp.py:8-87,
+141-261, 295-344, 390-416; /root/reference/ital/retrieval_base.py:34-194).  It is NOT the product: only
+tests/, ``__graft_entry__.smoke()`` and bench.py's ``cpu_baseline`` / ``--impl reference`` legs import it,
+as the checker.  The product path (ital_b200/) never touches it and has no CPU fallback.
+
+Differences from the reference that are deliberate and documented in DESIGN.md:
+
+* The reference materialises the n-by-n kernel matrix ``K_all`` (gp.py:128).  Every ``K_all[np.ix_(..)]``
+  gather is restated here as a Gram of data rows against the few rows involved (columns on demand), which is
+  the same arithmetic (gp.py:414-416) evaluated only where it is used.
+* Orthant probabilities of two or more variables come from ``oracle/orthant.py`` (fixed-node rule) instead
+  of the randomised third-party ``MVNDST``.  Pinning: one variable is the reference's closed form; two
+  variables agree with Genz's BVU to ~1e-12; three and more are checked against the reference code driven
+  through an accurate ``mvndst`` stand-in (tests/golden/make_golden.py).  Against the historical Fortran
+  routine (1e-4 noise) parity for three or more variables is **unpinned**.
+* Monte-Carlo modes, ``clip_cov`` grouping and ``change_estimation_subset`` (ital.py:227-275, 293-297,
+  386-429) are not restated: none of the named configurations uses them.
+"""
+
+import itertools
+
+import numpy as np
+import scipy.linalg.lapack
+
+from .orthant import orthant_prob_all, safe_cholesky, snq_joint, snq_order
+
+EPS = 1e-12   # MutualInformation.__init__ default (ital.py:144)
+
+
+def invh(M):
+    """Cholesky inverse via dpotrf/dpotri, symmetrised (gp.py:8-37)."""
+    zz, _ = scipy.linalg.lapack.dpotrf(M, False, False)
+    inv_M, _ = scipy.linalg.lapack.dpotri(zz)
+    i, j = np.triu_indices_from(inv_M, k=1)
+    inv_M[j, i] = inv_M[i, j]
+    return inv_M
+
+
+class OracleGP(object):
+    """GaussianProcess (gp.py:91-436) without the n-by-n matrix."""
+
+    def __init__(self, data, length_scale, var=1.0, noise=1e-6):
+        self.X = np.array(data, dtype=np.float64)
+        self.length_scale = length_scale
+        self.length_scale_sq = length_scale * length_scale
+        self.var = var
+        self.noise = noise
+        self.sqnorm = np.sum(self.X ** 2, axis=-1)          # gp.py:411
+        self.reset()
+
+    def reset(self):                                           # gp.py:132-138
+        self.ind = []
+        self.y = self.K = self.K_inv = self.w = None
+        self._cols = {}
+
+    def kernel(self, a, b):                                    # gp.py:390-416
+        a = np.atleast_2d(np.asarray(a, dtype=np.float64))
+        b = np.atleast_2d(np.asarray(b, dtype=np.float64))
+        a_norm = np.sum(a ** 2, axis=-1)
+        b_norm = np.sum(b ** 2, axis=-1)
+        s = -2 * self.length_scale_sq
+        return self.var * np.exp((a_norm[:, None] + b_norm[None, :] - 2 * np.dot(a, b.T)) / s)
+
+    def col(self, i):
+        """K_all[:, i] on demand (one column of gp.py:128)."""
+        i = int(i)
+        if i not in self._cols:
+            s = -2 * self.length_scale_sq
+            self._cols[i] = self.var * np.exp((self.sqnorm + self.sqnorm[i] - 2 * (self.X @ self.X[i])) / s)
+        return self._cols[i]
+
+    def cols(self, ind):
+        """K_all[:, ind] as an N-by-len(ind) array."""
+        if len(ind) == 0:
+            return np.zeros((len(self.X), 0))
+        return np.stack([self.col(i) for i in ind], axis=1)
+
+    def block(self, a, b):
+        """K_all[np.ix_(a, b)]."""
+        return self.cols(b)[np.asarray(a, dtype=np.int64)] if len(a) else np.zeros((0, len(b)))
+
+    def fit(self, ind, y):                                     # gp.py:141-161
+        self.ind = [int(i) for i in ind]
+        self.y = np.array(y, dtype=np.float64)
+        self.K = self.block(self.ind, self.ind) + self.noise * np.eye(len(self.ind))
+        self.K_inv = invh(self.K)
+        self.w = np.dot(self.K_inv, self.y)
+        return self
+
+    def update(self, ind, y):                                  # gp.py:164-200
+        if len(self.ind) == 0:
+            return self.fit(ind, y)
+        ind = [int(i) for i in ind]
+        y = np.asarray(y, dtype=np.float64)
+        K_old_new = self.block(self.ind, ind)
+        K_new = self.block(ind, ind) + self.noise * np.eye(len(ind))
+        self.ind += ind
+        self.y = np.concatenate((self.y, y))
+        self.K = np.vstack((np.hstack((self.K, K_old_new)), np.hstack((K_old_new.T, K_new))))
+        self.K_inv = invh(self.K)
+        self.w = np.dot(self.K_inv, self.y)
+        return self
+
+    def predict_stored(self, ind=None, cov_mode=None):         # gp.py:203-232
+        k_test = self.cols(self.ind).T if ind is None else self.block(self.ind, ind)
+        pred_mean = np.dot(self.w.T, k_test)
+        if cov_mode == 'full':
+            if ind is None:
+                raise ValueError('full covariance over all samples is the n-by-n matrix this oracle avoids')
+            return pred_mean, self.block(ind, ind) - np.dot(k_test.T, np.dot(self.K_inv, k_test))
+        elif cov_mode == 'diag':
+            return pred_mean, np.maximum(0, self.var - np.sum(k_test * np.dot(self.K_inv, k_test), axis=0))
+        return pred_mean
+
+    def predict_cov_parts(self, base_ind):
+        """The three ingredients of predict_cov_batch (gp.py:250-256) for ind = all rows."""
+        base_ind = [int(i) for i in base_ind]
+        k_base = self.block(self.ind, base_ind)
+        cov_base = self.block(base_ind, base_ind) - np.dot(k_base.T, np.dot(self.K_inv, k_base))
+        k_test = self.cols(self.ind).T
+        var_test = self.var - np.sum(k_test * np.dot(self.K_inv, k_test), axis=0)
+        cov_base_test = self.cols(base_ind).T - np.dot(k_base.T, np.dot(self.K_inv, k_test))
+        return cov_base, var_test, cov_base_test
+
+    def predict(self, X, cov_mode=None):                       # gp.py:264-292
+        k_test = self.kernel(self.X[self.ind], X)
+        pred_mean = np.dot(self.w.T, k_test)
+        if cov_mode == 'full':
+            return pred_mean, self.kernel(X, X) - np.dot(k_test.T, np.dot(self.K_inv, k_test))
+        elif cov_mode == 'diag':
+            return pred_mean, np.maximum(0, self.var - np.sum(k_test * np.dot(self.K_inv, k_test), axis=0))
+        return pred_mean
+
+
+def entropy_terms(p, p_upd=1.0, eps=EPS):
+    """p * (log(p' + eps) - log(p + eps)), the summand of ital.py:207-219 ('mean' estimation)."""
+    return p * (np.log(p_upd + eps) - np.log(p + eps))
+
+
+def mi_perfect_user(m_base, cov_base, m_c, var_c, cov_base_c, q=None):
+    """MI of ``ret + [i]`` for every candidate i under the perfect-user model, vectorised.
+
+    With label_prob >= 1 and mistake_prob <= 0 there is one feedback configuration per relevance
+    configuration (ital.py:313-315) and the updated orthant probability is 1 to double precision whenever
+    the posterior variances are large against the label noise, so
+    ``MI = sum_r p_r * (log(1 + eps) - log(p_r + eps))``.  Returns (scores, p_plus, p_base,
+    flagged) where ``flagged`` marks candidates whose conditional variance is too small for that shortcut.
+    """
+    t = len(m_base)
+    m_c = np.asarray(m_c, dtype=np.float64)
+    if t == 0:
+        sd = np.sqrt(np.maximum(var_c, 0.0))
+        with np.errstate(divide='ignore', invalid='ignore'):
+            z = np.where(sd > 0, m_c / np.where(sd > 0, sd, 1.0), np.where(m_c > 0, np.inf, -np.inf))
+        from scipy.special import ndtr
+        p1 = ndtr(z)
+        p0 = ndtr(-z)
+        return entropy_terms(p0) + entropy_terms(p1), p1[:, None], np.ones(1), sd
+    L = safe_cholesky(cov_base)
+    l = scipy.linalg.solve_triangular(L, cov_base_c, lower=True).T        # (N, t)
+    s2 = var_c - np.sum(l * l, axis=1)
+    s = np.sqrt(np.maximum(s2, 0.0))
+    p_plus, p_base = snq_joint(m_base, L, m_c, l, s, q)
+    p_minus = np.maximum(p_base[None, :] - p_plus, 0.0)
+    scores = entropy_terms(p_plus).sum(axis=1) + entropy_terms(p_minus).sum(axis=1)
+    return scores, p_plus, p_base, s
+
+
+class OracleITAL(object):
+    """ITAL + ActiveRetrievalBase (ital.py:12-134, retrieval_base.py:7-194) over OracleGP."""
+
+    def __init__(self, data=None, queries=[], length_scale=0.1, var=1.0, noise=1e-6,
+                 label_prob=1.0, mistake_prob=0.0, top_candidates=None, change_estimation_subset=0,
+                 clip_cov=0, label_estimation='mean', monte_carlo_num_rel=None, monte_carlo_num_fb=None,
+                 parallelized=True, force_general=False):
+        self.length_scale, self.var, self.noise = length_scale, var, noise
+        self.label_prob, self.mistake_prob = label_prob, mistake_prob
+        self.top_candidates = top_candidates
+        self.label_estimation = label_estimation
+        self.parallelized = parallelized
+        self.force_general = force_general
+        if change_estimation_subset != 0 or clip_cov != 0 or monte_carlo_num_rel is not None \
+                or monte_carlo_num_fb is not None:
+            raise NotImplementedError('oracle restates the enumeration path only (see module docstring)')
+        self.fit(data, queries)
+
+    # ---- retrieval_base.py ---------------------------------------------------------------------------
+    def fit(self, data, queries=[]):                                            # retrieval_base.py:34-45
+        self.data = data
+        self.queries = queries
+        if self.data is not None:
+            X = np.concatenate((self.data, self.queries)) if len(self.queries) > 0 else self.data
+            self.gp = OracleGP(X, self.length_scale, self.var, self.noise)
+            self.reset()
+        else:
+            self.gp = None
+
+    def reset(self):                                                            # retrieval_base.py:48-61
+        self.rounds = 0
+        self.relevant_ids, self.irrelevant_ids, self.unnameable_ids = set(), set(), set()
+        if len(self.queries) > 0:
+            n = len(self.data)
+            self.gp.fit(np.arange(n, n + len(self.queries)), [1] * len(self.queries))
+            self.rel_mean = self.gp.predict_stored()[:n]
+        else:
+            self.gp.reset()
+            self.rel_mean = None
+
+    def top_results(self, k=None):                                              # retrieval_base.py:64-75
+        ind = np.argsort(self.rel_mean)[::-1]
+        return ind[:k] if k is not None else ind
+
+    def get_unseen(self):                                                       # retrieval_base.py:78-87
+        seen = self.relevant_ids | self.irrelevant_ids | self.unnameable_ids
+        return [i for i in range(len(self.data)) if i not in seen]
+
+    def partition_feedback(self, feedback):                                     # retrieval_base.py:167-194
+        rel, irr, unnameable = [], [], []
+        for i, fb in feedback.items():
+            if fb > 0:
+                if i in self.irrelevant_ids:
+                    raise RuntimeError('Cannot change feedback once given.')
+                elif i not in self.relevant_ids:
+                    rel.append(i)
+            elif fb < 0:
+                if i in self.relevant_ids:
+                    raise RuntimeError('Cannot change feedback once given.')
+                elif i not in self.irrelevant_ids:
+                    irr.append(i)
+            else:
+                unnameable.append(i)
+        return rel, irr, unnameable
+
+    def update(self, feedback):                                                 # retrieval_base.py:105-126
+        rel, irr, unnameable = self.partition_feedback(feedback)
+        if len(rel) + len(irr) > 0:
+            self.gp.update(rel + irr, np.concatenate((np.ones(len(rel)), -1 * np.ones(len(irr)))))
+            self.rel_mean = self.gp.predict_stored()[:len(self.data)]
+            self.relevant_ids.update(rel)
+            self.irrelevant_ids.update(irr)
+            self.rounds += 1
+        self.unnameable_ids.update(unnameable)
+
+    # ---- ital.py -------------------------------------------------------------------------------------
+    def _perfect_user(self):
+        return (self.label_prob >= 1) and (self.mistake_prob <= 0)            # ital.py:313
+
+    def fetch_unlabelled(self, k, show_progress=False, forced=None):            # ital.py:84-134
+        """``forced`` (test hook): follow these choices instead of the argmax so that a recorded greedy path
+        can be re-scored step by step even where the maximum is an exact tie."""
+        candidates = self.get_unseen()
+        if len(candidates) < k:
+            k = len(candidates)
+        if self.top_candidates is not None:                                     # ital.py:111-117
+            top = self.top_candidates
+            if isinstance(top, float):
+                top = min(len(candidates), int(top * (len(self.queries) + len(self.relevant_ids)
+                                                      + len(self.irrelevant_ids))))
+            if (top > 0) and (top < len(candidates)):
+                top_ind = np.argpartition(self.rel_mean[candidates], -top)[-top:]
+                candidates = [candidates[i] for i in top_ind]
+        n = len(self.data)
+        ret = []
+        self.trace = []          # per greedy step: dict(candidates, scores, ...) for the parity tests
+        var0 = self.gp.predict_stored(cov_mode='diag')[1]                       # ital.py:557-558 (clamped)
+        for it in range(k):
+            cand = np.asarray(candidates, dtype=np.int64)
+            if len(ret) == 0:
+                cov_base, var_test, cov_base_test = np.zeros((0, 0)), var0, np.zeros((0, len(var0)))
+            else:
+                cov_base, var_test, cov_base_test = self.gp.predict_cov_parts(ret)   # ital.py:586
+            m_base = self.rel_mean[ret] if len(ret) else np.zeros(0)
+            if self._perfect_user() and self.label_estimation == 'mean' and not self.force_general:
+                scores, p_plus, p_base, s = mi_perfect_user(
+                    m_base, cov_base, self.rel_mean[cand], var_test[cand], cov_base_test[:, cand])
+                extra = dict(p_plus=p_plus, p_base=p_base, s=s)
+            else:
+                scores = np.array([self._mi_general(ret + [int(i)], m_base, cov_base, self.rel_mean[i],
+                                                    var_test[i], cov_base_test[:, i]) for i in cand])
+                extra = {}
+            max_ind = int(np.argmax(scores))                                    # ital.py:130 (first maximum)
+            if forced is not None:
+                max_ind = candidates.index(int(forced[it]))
+            self.trace.append(dict(candidates=cand, scores=scores, mean=self.rel_mean[cand].copy(),
+                                   var=var_test[cand].copy(), cov_base=cov_base.copy(),
+                                   cov_base_test=cov_base_test[:, cand].copy(), chosen=int(cand[max_ind]),
+                                   argmax=int(cand[int(np.argmax(scores))]), **extra))
+            ret.append(int(cand[max_ind]))
+            del candidates[max_ind]
+        return ret
+
+    # General feedback model: literal restatement of _call_iter_all for one candidate (ital.py:183-224).
+    def _mi_general(self, ids, m_base, cov_base, m_c, var_c, cov_base_c):
+        D = len(ids)
+        mean = np.concatenate((m_base, [m_c]))
+        cov = np.empty((D, D))
+        cov[:D - 1, :D - 1] = cov_base
+        cov[:D - 1, D - 1] = cov[D - 1, :D - 1] = cov_base_c
+        cov[D - 1, D - 1] = var_c
+        p_all = orthant_prob_all(mean, cov, snq_order(D - 1))
+        order = np.argsort(ids, kind='stable')                 # updated_prob_rel sorts by index (ital.py:448)
+        mi = 0.0
+        for reli in itertools.product([False, True], repeat=D):                # ital.py:295
+            pr = p_all[sum(int(r) << j for j, r in enumerate(reli))]
+            log_pr = np.log(pr + EPS)
+            for fbi in self._fb_iter(reli):                                     # ital.py:300-342
+                if not any(fb != 0 for fb in fbi):
+                    continue
+                pr_upd = self._updated_prob_rel(reli, fbi, mean, cov, order)
+                cur = np.log(pr_upd + EPS) - log_pr
+                cur *= 1.0 if self._perfect_user() else self._likelihood(fbi, reli)   # ital.py:208
+                if self.label_estimation == 'optimistic':                       # ital.py:210-219
+                    if cur > mi:
+                        mi = cur
+                elif self.label_estimation == 'pessimistic':
+                    if (mi == 0) or (cur < mi):
+                        mi = cur
+                else:
+                    mi += cur * pr
+        return mi
+
+    def _fb_iter(self, reli):
+        if self._perfect_user():
+            return [[1 if r else -1 for r in reli]]
+        elif self.label_prob >= 1:
+            return itertools.product([-1, 1], repeat=len(reli))
+        return itertools.product([-1, 0, 1], repeat=len(reli))
+
+    def _likelihood(self, fbi, reli):                                           # ital.py:453-481
+        prob = 1.0
+        for fb, r in zip(fbi, reli):
+            if fb == 0:
+                prob *= 1.0 - self.label_prob
+            elif fb == 2 * r - 1:
+                prob *= self.label_prob * (1.0 - self.mistake_prob)
+            else:
+                prob *= self.label_prob * self.mistake_prob
+        return prob
+
+    def _updated_prob_rel(self, reli, fbi, mean, cov, order):
+        """P(R = r | F = f) on the block (ital.py:432-450 -> retrieval_base.py:129-164 -> gp.py:295-344).
+
+        The reference extends K^-1 by the annotated samples (extend_inv, gp.py:40-87) and predicts the block;
+        that equals conditioning the block's current posterior N(mean, cov) on noisy observations of the
+        annotated members, which is what is evaluated here.
+        """
+        fbi = np.asarray(fbi, dtype=np.float64)
+        obs = np.nonzero(fbi != 0)[0]
+        A = cov[np.ix_(obs, obs)] + self.noise * np.eye(len(obs))
+        G = np.linalg.solve(A, cov[obs, :])                                      # (|O|, D)
+        mean_u = mean + G.T @ (fbi[obs] - mean[obs])
+        cov_u = cov - cov[:, obs] @ G
+        mean_u, cov_u = mean_u[order], cov_u[np.ix_(order, order)]
+        rel_sorted = np.asarray(reli)[order]
+        p = orthant_prob_all(mean_u, cov_u, snq_order(len(mean) - 1))
+        return p[sum(int(r) << j for j, r in enumerate(rel_sorted))]

@@ -1,0 +1,75 @@
+"""The oracle against the goldens recorded from the reference itself (tests/golden/make_golden.py).
+
+Tolerances: selected indices identical; rel_mean / variances within 1e-6 relative
+(absolute floor 1e-9 * var); MI scores within 1e-6 relative + 1e-9 absolute where one or two variables
+are involved (closed form / Genz BVU in the reference), and within 2e-6 absolute from three variables on,
+where the oracle's fixed 16/12-node panels are compared with the converged stand-in the goldens used.
+General feedback models (mistake_prob > 0 or label_prob < 1): 1e-4 relative, see the comment below.
+"""
+import numpy as np
+
+from conftest import drive
+from oracle.ital_oracle import OracleITAL
+
+
+def _tol(step):
+    return (1e-6, 1e-9) if step <= 1 else (1e-6, 2e-6)
+
+
+def check_choice(scores, candidates, chosen, rtol=1e-9):
+    """Index identity, or an exact-tie equivalent: the recorded choice scores within rtol of the maximum."""
+    best = int(candidates[int(np.argmax(scores))])
+    if best == chosen:
+        return 'identical'
+    pos = int(np.nonzero(candidates == chosen)[0][0])
+    assert scores[pos] >= scores.max() - rtol * abs(scores.max()), (best, chosen, scores.max(), scores[pos])
+    return 'tie'
+
+
+def test_oracle_reproduces_reference(golden):
+    name, g = golden
+    ora = drive(OracleITAL(g['X'], queries=list(g['queries']), **g['learner_kw']), g)
+    np.testing.assert_allclose(ora.rel_mean, g['rel_mean'], rtol=1e-6, atol=1e-9)
+    var = ora.gp.predict_stored(cov_mode='diag')[1][:len(g['X'])]
+    np.testing.assert_allclose(var, g['var_diag'], rtol=1e-6, atol=1e-9 * float(g['var']))
+    # follow the recorded greedy path so that every step is compared even after an exact tie
+    ora.fetch_unlabelled(int(g['k']), forced=g['ret'].tolist())
+    general = not (float(g['label_prob']) >= 1 and float(g['mistake_prob']) <= 0)
+    for t, (tr, st) in enumerate(zip(ora.trace, g['steps'])):
+        assert tr['candidates'].tolist() == st['candidates'].tolist()
+        rtol, atol = _tol(t)
+        atol = np.full(len(st['mi']), atol)
+        if general:
+            # scores are sums of log(p' + 1e-12) with p' ~ 0: round-off in p' at the 1e-13 level moves them
+            # by ~1e-5 relative (the reference's own MVNDST noise of 1e-4 moves them by O(1))
+            rtol, atol = 1e-4, np.full(len(st['mi']), 1e-5)
+            if str(g['label_estimation']) != 'mean':
+                # 'optimistic' / 'pessimistic' return the single largest / smallest log-ratio, which is set by
+                # the RELATIVE accuracy of probabilities far below MVNDST's own 1e-4 absolute tolerance:
+                # ill-conditioned in the reference itself, compared loosely and never used by a named config
+                rtol = 1e-2
+        elif t >= 2:
+            # candidates strongly tied to the base (|l|/s > 1, i.e. R^2 > 0.5) make Phi(./s) a near-step that
+            # the fixed panels resolve less well (SURVEY.md A.3 caveat); they carry low MI and never win
+            l = np.linalg.solve(np.linalg.cholesky(tr['cov_base']), tr['cov_base_test'])
+            beta = np.sqrt((l * l).sum(axis=0)) / np.maximum(tr['s'], 1e-300)
+            atol = np.where(beta > 2, 2e-3, np.where(beta > 1, 1e-4, atol))
+        err = np.abs(tr['scores'] - st['mi'])
+        assert np.all(err <= atol + rtol * np.abs(st['mi'])), '%s step %d: max err %g' % (name, t, err.max())
+        if not (general and str(g['label_estimation']) != 'mean'):
+            check_choice(tr['scores'], tr['candidates'], st['chosen'],
+                         rtol=1e-4 if general else 1e-9)
+
+
+def test_perfect_user_shortcut_equals_general_formula():
+    """mi_perfect_user (p' = 1) against the literal double loop of ital.py:183-224 on a small pool."""
+    rng = np.random.default_rng(5)
+    X = rng.uniform(size=(60, 3))
+    fast = OracleITAL(X, length_scale=0.4)
+    slow = OracleITAL(X, length_scale=0.4, force_general=True)
+    for L in (fast, slow):
+        L.update({2: 1})
+        L.update({7: -1, 21: 1, 40: -1})
+    assert fast.fetch_unlabelled(3) == slow.fetch_unlabelled(3)
+    for a, b in zip(fast.trace, slow.trace):
+        np.testing.assert_allclose(a['scores'], b['scores'], rtol=1e-6, atol=1e-7)
