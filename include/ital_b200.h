@@ -1,0 +1,125 @@
+/*
+ * ital_b200 -- C ABI of the B200-native ITAL batch-selection path.
+ *
+ * One `ital_shard` owns a contiguous block of rows of the pool on one GPU and everything the greedy
+ * batch construction needs about those rows (posterior moments, Cholesky projections, candidate mask).
+ * A single-GPU learner is one shard holding all rows; a multi-GPU learner is one shard per process, and the
+ * host moves the small fixed-size "point records" between them (one per greedy step).
+ *
+ * The reference is pure Python; there is no FFI in it.  Each entry point below names the reference code it
+ * replaces (paths relative to /root/reference).  Plain pointers and sizes only; no torch types.  Every
+ * function returns 0 on success and a negative ITAL_E* code on failure; ital_last_error() gives the text.
+ * Calls on one shard must be serialised by the caller.  Host arrays are only read/written during the call.
+ */
+#ifndef ITAL_B200_H
+#define ITAL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ital_shard ital_shard;
+
+enum { ITAL_OK = 0, ITAL_EINVAL = -1, ITAL_ECUDA = -2, ITAL_ESTATE = -3, ITAL_ENOMEM = -4 };
+enum { ITAL_F32 = 0, ITAL_F64 = 1 };
+
+/* Number of doubles in the header of a point record: [0] global row index, [1] score, [2] posterior mean,
+ * [3] variance conditional on labelled + already selected points, [4] squared norm of the row,
+ * [5] posterior variance given the labelled set, [6] gain (score - H(base)), [7] reserved.
+ * The header is followed by `ital_width_cap()` projection entries and the row itself as `d` doubles. */
+#define ITAL_RECORD_HEADER 8
+
+const char* ital_last_error(void);
+int ital_version(void);
+
+/* GaussianProcess.__init__ (ital/gp.py:103-129) + ActiveRetrievalBase.fit (ital/retrieval_base.py:34-45),
+ * without the n-by-n matrix: uploads rows [row_offset, row_offset + n_local) of the (data ++ queries) matrix,
+ * computes their squared norms and resets the model.  `n_data` is the global number of pool rows; rows with a
+ * global index >= n_data are query rows and never candidates.  `x_dtype` is the dtype of X AND of the copy
+ * kept in HBM (ITAL_F32 halves the streamed bytes; use it only if the data is float32-representable). */
+int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_t n_local, int64_t d,
+                int64_t row_offset, int64_t n_data, double length_scale, double var, double noise);
+int ital_destroy(ital_shard* s);
+
+/* Use this CUDA stream (a cudaStream_t) for all work of the shard; NULL = the legacy default stream. */
+int ital_set_stream(ital_shard* s, void* cuda_stream);
+
+/* GaussianProcess.reset (ital/gp.py:132-138) + ActiveRetrievalBase.reset (ital/retrieval_base.py:48-61):
+ * forget all labels and all "seen" marks. */
+int ital_reset(ital_shard* s);
+
+/* Size in doubles of one point record in the shard's current state, and the projection capacity in it. */
+int64_t ital_record_doubles(const ital_shard* s);
+int64_t ital_width_cap(const ital_shard* s);
+int64_t ital_width(const ital_shard* s);          /* labelled points currently in the model */
+
+/* Fill host `records` (q records) for the given global rows.  Rows not owned by this shard give an all-zero
+ * record, so that summing the buffers of all shards yields the complete records. */
+int ital_export_points(ital_shard* s, int q, const int64_t* global_idx, double* records);
+
+/* GaussianProcess.fit / update (ital/gp.py:141-200) + the predict_stored() that follows it
+ * (ital/retrieval_base.py:58,120): add ONE labelled point (complete record, target y) to the model by a
+ * rank-1 Cholesky extension and update posterior mean and variance of every local row in one pass over X.
+ * Also marks the point as seen.  Points are appended in the order given (relevant first, irrelevant after,
+ * as ActiveRetrievalBase.update does). */
+int ital_add_labelled(ital_shard* s, const double* record, double y);
+
+/* ActiveRetrievalBase.update's unnameable_ids / get_unseen (ital/retrieval_base.py:78-87,126):
+ * mark rows as seen (never candidates again until reset).  Non-local indices are ignored. */
+int ital_mark_seen(ital_shard* s, int64_t m, const int64_t* global_idx);
+
+/* ITAL.fetch_unlabelled's top_candidates restriction (ital/ital.py:111-117): candidates are the unseen rows
+ * whose global index is in `global_idx` (m entries; m < 0 lifts the restriction). */
+int ital_restrict_candidates(ital_shard* s, int64_t m, const int64_t* global_idx);
+
+/* ---- greedy batch construction (ITAL.fetch_unlabelled, ital/ital.py:119-134) ---------------------------
+ * ital_fetch_begin:   AppendedMutualInformation.__init__/set_ret([]) (ital/ital.py:491-558).
+ * ital_fetch_propose: scores the local candidates of the current greedy step given the batch so far
+ *                     (MutualInformation._call_iter_all, prob_rel; ital/ital.py:183-224, 345-383, with
+ *                     predict_cov_batch, ital/gp.py:235-261, maintained incrementally) and writes the record
+ *                     of the local best candidate (score desc, index asc; record[1] = -inf if none).
+ *                     `floor_score`: a score some other shard already reached this step (or -inf).
+ *                     `exhaustive` != 0 scores every candidate instead of pruning with the lazy-greedy
+ *                     bound (same winner; used by tests and to report unpruned throughput).
+ * ital_fetch_commit:  np.argmax + AppendedMutualInformation.append (ital/ital.py:130-132, 561-586) for the
+ *                     globally best record: extends every local row's projection by the chosen point.
+ * ital_fetch_end:     drops the batch-conditional state (the selected rows stay unseen until update()).
+ * ital_fetch:         the whole loop for a single-shard learner; returns the number selected. */
+int ital_fetch_begin(ital_shard* s, double label_prob, double mistake_prob);
+int ital_fetch_propose(ital_shard* s, double floor_score, int exhaustive, double* record);
+int ital_fetch_commit(ital_shard* s, const double* record);
+int ital_fetch_end(ital_shard* s);
+int ital_fetch(ital_shard* s, int k, double label_prob, double mistake_prob, int exhaustive,
+               int64_t* out_idx, double* out_scores);
+
+/* Per-step diagnostics of the last propose: [0] candidates considered, [1] candidates scored exactly,
+ * [2] quadrature nodes, [3] H(base), [4] flagged (conditional variance < 100 * noise), [5..7] reserved. */
+int ital_fetch_stats(const ital_shard* s, double* out8);
+
+/* Scores of the last propose for all local rows (NaN where not scored this step). */
+int ital_last_scores(ital_shard* s, double* out_n_local);
+
+/* rel_mean = gp.predict_stored()[:n] (ital/retrieval_base.py:58,120; ital/gp.py:221-222) and the posterior
+ * variance of predict_stored(cov_mode='diag') before clamping (ital/gp.py:229), for the local rows. */
+int ital_rel_mean(ital_shard* s, double* out_n_local);
+int ital_rel_var(ital_shard* s, double* out_n_local);
+
+/* GaussianProcess.predict (ital/gp.py:264-292): mean (and, if out_var != NULL, the 'diag' variance clamped at
+ * 0) for m arbitrary rows of float64 features.  Uses the labelled rows held by this shard's model, so it is
+ * valid on any shard (the labelled points are replicated). */
+int ital_predict(ital_shard* s, const double* Xt, int64_t m, double* out_mean, double* out_var);
+
+/* Host-side pieces exposed for CPU-only tests (no GPU needed) ------------------------------------------- */
+/* Shared quadrature nodes of one greedy step (see oracle/orthant.py for the rule): base mean m[t], lower
+ * Cholesky factor L[t*t] (row-major).  Returns the node count N = (2q)^t; if eta != NULL fills eta[t*N]
+ * (dimension-major), w[N], orth[N], sorted by orthant, and masses[2^t]. */
+int64_t ital_snq_nodes(int t, const double* m, const double* L, double* eta, double* w, int32_t* orth,
+                       double* masses);
+int ital_snq_order(int t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

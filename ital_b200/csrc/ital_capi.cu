@@ -1,0 +1,777 @@
+// C ABI of the ITAL batch-selection path (include/ital_b200.h): shard state, launch sequencing, small
+// host-side linear algebra (the |L| x |L| Cholesky factor grows by one row per labelled point and stays on the
+// host; everything that scales with the pool runs in the kernels of ital_kernels.cuh).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/ital_b200.h"
+#include "ital_kernels.cuh"
+#include "snq_host.h"
+
+using namespace italk;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(ITAL_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr uint8_t kSeen = 1, kSelected = 2, kNotCandidate = 4, kRestricted = 8;
+constexpr double kPruneMargin = 1e-6;   // slack of the lazy-greedy bound against quadrature round-off
+constexpr int kArgmaxBlocks = 592;      // 4 x 148 SMs
+
+}  // namespace
+
+struct ital_shard {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int x_dtype = ITAL_F32;
+    int64_t n = 0, d = 0, d_pad = 0, row_offset = 0, n_data = 0, ldu = 0;
+    double ls = 0, var = 1, noise = 1e-6;
+    int num_sms = 148;
+
+    void* X = nullptr;
+    double *sqn = nullptr, *m = nullptr, *v = nullptr, *U = nullptr, *gain = nullptr, *score = nullptr;
+    uint8_t* mask = nullptr;
+    int* worklist = nullptr;
+    int* counters = nullptr;         // [0] worklist size, [1] flagged
+    Best* block_best = nullptr;      // kArgmaxBlocks
+    Best* best = nullptr;            // [0] step winner, [1] most promising candidate
+    ExtendParams* ext = nullptr;
+    void* z_dev = nullptr;           // d_pad elements of the storage type
+    double* ur_dev = nullptr;        // w_cap
+    double* rec_dev = nullptr;       // record staging
+    double* rec_host = nullptr;      // pinned
+    int64_t rec_cap = 0;
+    int64_t* idx_dev = nullptr;      // scratch for index lists
+    int64_t idx_cap = 0;
+    // quadrature nodes of the current step
+    double *eta_dev = nullptr, *w_dev = nullptr, *masses_dev = nullptr;
+    int* group_dev = nullptr;
+    int64_t nodes_cap = 0;
+    int64_t n_nodes = 0;
+    double h_base = 0.0;
+
+    int w_cap = 0;                   // allocated projection columns
+    int W = 0;                       // labelled points in the model
+    int t = 0;                       // points selected in the running fetch
+    bool fetching = false;
+    double label_prob = 1.0, mistake_prob = 0.0;
+
+    // host copy of the small model
+    std::vector<std::vector<double>> LK;     // row a of the Cholesky factor of K_LL + noise I (a+1 entries)
+    std::vector<double> beta;                // L_K^-1 y
+    std::vector<double> lab_x;               // labelled rows, W x d doubles
+    std::vector<double> lab_sqn, lab_y;
+    std::vector<int64_t> lab_idx;
+    std::vector<double> base_m;              // means of the points selected in this fetch
+    std::vector<std::vector<double>> base_L; // rows of the Cholesky factor of their posterior covariance
+    std::vector<int64_t> selected;           // global indices selected in this fetch
+    std::vector<int64_t> restricted;         // local rows carrying kRestricted
+
+    // predict() scratch
+    double *lab_x_dev = nullptr, *lab_sqn_dev = nullptr, *w_vec_dev = nullptr, *LK_dev = nullptr;
+    int lab_dev_cap = 0;
+    bool lab_dev_valid = false;
+
+    double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double log1p_eps = std::log(1.0 + 1e-12);
+};
+
+namespace {
+
+int64_t record_doubles(const ital_shard* s) { return ITAL_RECORD_HEADER + s->w_cap + s->d; }
+
+int grid_for(const ital_shard* s, int64_t work_items, int per_block, int max_waves = 8) {
+    int64_t blocks = (work_items + per_block - 1) / per_block;
+    int64_t cap = (int64_t)s->num_sms * max_waves;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+int ensure_record_buffers(ital_shard* s, int q) {
+    const int64_t need = record_doubles(s) * q;
+    if (need <= s->rec_cap) return ITAL_OK;
+    if (s->rec_dev) CU(cudaFree(s->rec_dev));
+    if (s->rec_host) CU(cudaFreeHost(s->rec_host));
+    s->rec_dev = nullptr;
+    s->rec_host = nullptr;
+    CU(cudaMalloc(&s->rec_dev, need * sizeof(double)));
+    CU(cudaMallocHost(&s->rec_host, need * sizeof(double)));
+    s->rec_cap = need;
+    return ITAL_OK;
+}
+
+int ensure_idx(ital_shard* s, int64_t m) {
+    if (m <= s->idx_cap) return ITAL_OK;
+    if (s->idx_dev) CU(cudaFree(s->idx_dev));
+    s->idx_dev = nullptr;
+    CU(cudaMalloc(&s->idx_dev, m * sizeof(int64_t)));
+    s->idx_cap = m;
+    return ITAL_OK;
+}
+
+// grow U to hold at least `cols` projection columns
+int ensure_width(ital_shard* s, int cols) {
+    if (cols <= s->w_cap) return ITAL_OK;
+    int new_cap = std::max(32, s->w_cap);
+    while (new_cap < cols) new_cap *= 2;
+    double* nu = nullptr;
+    CU(cudaMalloc(&nu, (size_t)new_cap * s->ldu * sizeof(double)));
+    if (s->U) {
+        CU(cudaMemcpyAsync(nu, s->U, (size_t)s->w_cap * s->ldu * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        CU(cudaFree(s->U));
+    }
+    s->U = nu;
+    if (s->ur_dev) CU(cudaFree(s->ur_dev));
+    s->ur_dev = nullptr;
+    CU(cudaMalloc(&s->ur_dev, (size_t)new_cap * sizeof(double)));
+    s->w_cap = new_cap;
+    // records change size with the capacity
+    s->rec_cap = 0;
+    return ensure_record_buffers(s, 1);
+}
+
+template <typename XT>
+int launch_extend_t(ital_shard* s, int W_used, int labelled) {
+    constexpr int VN = Vec<XT>::N;
+    const int nchunks = (int)(s->d_pad / (32 * VN));
+    const int threads = 256, warps = threads / 32;
+    const bool fixed = (nchunks == 1 || nchunks == 2 || nchunks == 4);
+    size_t smem = ((size_t)warps * 32 * 33 + ((W_used + 1) & ~1) + (fixed ? 0 : s->d_pad)) * sizeof(double);
+    const int64_t units = (s->n + 31) / 32;
+    int blocks = (int)std::min<int64_t>((units + warps - 1) / warps, (int64_t)s->num_sms * 2);
+    if (blocks < 1) blocks = 1;
+    const double neg2ls2 = -2.0 * (s->ls * s->ls);
+#define ITAL_LAUNCH_EXT(NCV)                                                                                   \
+    do {                                                                                                       \
+        CU(cudaFuncSetAttribute(k_extend<XT, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        k_extend<XT, NCV><<<blocks, threads, smem, s->stream>>>(                                                \
+            (const XT*)s->X, s->n, (int)s->d_pad, (const XT*)s->z_dev, s->ext, s->ur_dev, W_used, s->sqn, s->U, \
+            s->ldu, s->m, s->v, labelled, s->var, neg2ls2);                                                     \
+    } while (0)
+    if (nchunks == 4) ITAL_LAUNCH_EXT(4);
+    else if (nchunks == 2) ITAL_LAUNCH_EXT(2);
+    else if (nchunks == 1) ITAL_LAUNCH_EXT(1);
+    else ITAL_LAUNCH_EXT(0);
+#undef ITAL_LAUNCH_EXT
+    CU(cudaGetLastError());
+    return ITAL_OK;
+}
+
+// One streaming pass: extend every local row's projection by the point described by `rec` (host record).
+// Writes column `col`; uses the first `col` entries of the record's projection.
+int extend_with_record(ital_shard* s, const double* rec, int col, double piv, double beta, int labelled) {
+    int rc = ensure_width(s, col + 1);
+    if (rc) return rc;
+    const double* ru = rec + ITAL_RECORD_HEADER;
+    const double* rx = rec + ITAL_RECORD_HEADER + s->w_cap;
+    // staging through the pinned record buffer keeps the copies asynchronous
+    ExtendParams prm{rec[4], piv, beta, 0.0};
+    CU(cudaMemcpyAsync(s->ext, &prm, sizeof prm, cudaMemcpyHostToDevice, s->stream));
+    if (col > 0) CU(cudaMemcpyAsync(s->ur_dev, ru, (size_t)col * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    std::vector<char> zbuf((size_t)s->d_pad * (s->x_dtype == ITAL_F32 ? 4 : 8), 0);
+    if (s->x_dtype == ITAL_F32) {
+        float* zf = (float*)zbuf.data();
+        for (int64_t j = 0; j < s->d; ++j) zf[j] = (float)rx[j];
+    } else {
+        memcpy(zbuf.data(), rx, (size_t)s->d * sizeof(double));
+    }
+    CU(cudaMemcpyAsync(s->z_dev, zbuf.data(), zbuf.size(), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));   // zbuf / prm are pageable host memory
+    if (s->x_dtype == ITAL_F32) return launch_extend_t<float>(s, col, labelled);
+    return launch_extend_t<double>(s, col, labelled);
+}
+
+int make_record(ital_shard* s, long long local_row, double* dst_dev) {
+    if (s->x_dtype == ITAL_F32)
+        k_record<float><<<1, 256, 0, s->stream>>>(local_row, s->best, s->row_offset, (const float*)s->X, (int)s->d,
+                                                  (int)s->d_pad, s->sqn, s->m, s->v, s->U, s->ldu, s->W,
+                                                  s->W + s->t, s->w_cap, s->gain, dst_dev);
+    else
+        k_record<double><<<1, 256, 0, s->stream>>>(local_row, s->best, s->row_offset, (const double*)s->X,
+                                                   (int)s->d, (int)s->d_pad, s->sqn, s->m, s->v, s->U, s->ldu,
+                                                   s->W, s->W + s->t, s->w_cap, s->gain, dst_dev);
+    CU(cudaGetLastError());
+    return ITAL_OK;
+}
+
+int upload_nodes(ital_shard* s, const snq::Nodes& nd) {
+    const int nb = 1 << nd.t;
+    if (nd.n > s->nodes_cap) {
+        if (s->eta_dev) CU(cudaFree(s->eta_dev));
+        if (s->w_dev) CU(cudaFree(s->w_dev));
+        s->eta_dev = s->w_dev = nullptr;
+        CU(cudaMalloc(&s->eta_dev, (size_t)nd.n * 10 * sizeof(double)));
+        CU(cudaMalloc(&s->w_dev, (size_t)nd.n * sizeof(double)));
+        s->nodes_cap = nd.n;
+    }
+    if (!s->masses_dev) CU(cudaMalloc(&s->masses_dev, 1024 * sizeof(double)));
+    if (!s->group_dev) CU(cudaMalloc(&s->group_dev, 1025 * sizeof(int)));
+    CU(cudaMemcpyAsync(s->eta_dev, nd.eta.data(), nd.eta.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->w_dev, nd.w.data(), nd.w.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->masses_dev, nd.masses.data(), nb * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->group_dev, nd.group_begin.data(), (nb + 1) * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));   // nd lives in pageable host memory
+    s->n_nodes = nd.n;
+    s->h_base = nd.entropy;
+    return ITAL_OK;
+}
+
+int launch_eval(ital_shard* s, int max_items_hint) {
+    const int t = s->t;
+    const int threads = 256;
+    int blocks = grid_for(s, std::max(1, max_items_hint), threads / 32, 8);
+    const double flag_var = 100.0 * s->noise;
+#define ITAL_EVAL_ARGS                                                                                      \
+    s->counters, s->worklist, t, s->m, s->v, s->U, s->ldu, s->W, s->eta_dev, s->w_dev, s->n_nodes, s->group_dev, \
+        s->masses_dev, s->h_base, s->log1p_eps, flag_var, s->score, s->gain, s->counters + 1
+    if (t == 1) k_eval<1><<<blocks, threads, 0, s->stream>>>(ITAL_EVAL_ARGS);
+    else if (t == 2) k_eval<2><<<blocks, threads, 0, s->stream>>>(ITAL_EVAL_ARGS);
+    else if (t == 3) k_eval<3><<<blocks, threads, 0, s->stream>>>(ITAL_EVAL_ARGS);
+    else k_eval<0><<<blocks, threads, 0, s->stream>>>(ITAL_EVAL_ARGS);
+#undef ITAL_EVAL_ARGS
+    CU(cudaGetLastError());
+    return ITAL_OK;
+}
+
+void free_all(ital_shard* s) {
+    cudaSetDevice(s->device);
+    void* ptrs[] = {s->X, s->sqn, s->m, s->v, s->U, s->gain, s->score, s->mask, s->worklist, s->counters,
+                    s->block_best, s->best, s->ext, s->z_dev, s->ur_dev, s->rec_dev, s->idx_dev, s->eta_dev,
+                    s->w_dev, s->masses_dev, s->group_dev, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (s->rec_host) cudaFreeHost(s->rec_host);
+}
+
+int reset_model(ital_shard* s) {
+    s->W = 0;
+    s->t = 0;
+    s->fetching = false;
+    s->LK.clear();
+    s->beta.clear();
+    s->lab_x.clear();
+    s->lab_sqn.clear();
+    s->lab_y.clear();
+    s->lab_idx.clear();
+    s->base_m.clear();
+    s->base_L.clear();
+    s->selected.clear();
+    s->restricted.clear();
+    s->lab_dev_valid = false;
+    const int blocks = grid_for(s, s->n, 256);
+    k_fill<<<blocks, 256, 0, s->stream>>>(s->m, s->n, 0.0);
+    k_fill<<<blocks, 256, 0, s->stream>>>(s->v, s->n, s->var);
+    CU(cudaGetLastError());
+    // candidates are the pool rows only (queries sit behind them, retrieval_base.py:40,84)
+    std::vector<uint8_t> mk((size_t)s->n, 0);
+    for (int64_t i = 0; i < s->n; ++i)
+        if (s->row_offset + i >= s->n_data) mk[i] = kNotCandidate;
+    CU(cudaMemcpyAsync(s->mask, mk.data(), (size_t)s->n, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return ITAL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ital_last_error(void) { return g_err.c_str(); }
+int ital_version(void) { return 100; }
+
+int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_t n_local, int64_t d,
+                int64_t row_offset, int64_t n_data, double length_scale, double var, double noise) {
+    if (!out || !X || n_local <= 0 || d <= 0 || (x_dtype != ITAL_F32 && x_dtype != ITAL_F64))
+        return fail(ITAL_EINVAL, "ital_create: bad arguments");
+    if (n_local >= (int64_t)1 << 31) return fail(ITAL_EINVAL, "ital_create: at most 2^31-1 rows per shard");
+    if (!(length_scale > 0)) return fail(ITAL_EINVAL, "ital_create: length_scale must be positive");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(ITAL_ECUDA, "ital_create: no CUDA device (%s); this path has no CPU fallback",
+                    cudaGetErrorString(e));
+    CU(cudaSetDevice(device));
+    ital_shard* s = new ital_shard();
+    s->device = device;
+    s->x_dtype = x_dtype;
+    s->n = n_local;
+    s->d = d;
+    const int64_t esize = x_dtype == ITAL_F32 ? 4 : 8;
+    const int64_t row_elems = 512 / esize;                       // rows padded to a multiple of 512 bytes
+    s->d_pad = (d + row_elems - 1) / row_elems * row_elems;
+    s->row_offset = row_offset;
+    s->n_data = n_data;
+    s->ldu = (n_local + 31) / 32 * 32;
+    s->ls = length_scale;
+    s->var = var;
+    s->noise = noise;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    s->num_sms = prop.multiProcessorCount;
+    int rc = ITAL_OK;
+    auto body = [&]() -> int {
+        CU(cudaMalloc(&s->X, (size_t)s->n * s->d_pad * esize));
+        if (s->d_pad == d) {
+            CU(cudaMemcpy(s->X, X, (size_t)s->n * d * esize, cudaMemcpyHostToDevice));
+        } else {
+            CU(cudaMemset(s->X, 0, (size_t)s->n * s->d_pad * esize));
+            CU(cudaMemcpy2D(s->X, (size_t)s->d_pad * esize, X, (size_t)d * esize, (size_t)d * esize, (size_t)s->n,
+                            cudaMemcpyHostToDevice));
+        }
+        CU(cudaMalloc(&s->sqn, (size_t)s->n * sizeof(double)));
+        CU(cudaMalloc(&s->m, (size_t)s->n * sizeof(double)));
+        CU(cudaMalloc(&s->v, (size_t)s->n * sizeof(double)));
+        CU(cudaMalloc(&s->gain, (size_t)s->n * sizeof(double)));
+        CU(cudaMalloc(&s->score, (size_t)s->n * sizeof(double)));
+        CU(cudaMalloc(&s->mask, (size_t)s->n));
+        CU(cudaMalloc(&s->worklist, (size_t)s->n * sizeof(int)));
+        CU(cudaMalloc(&s->counters, 4 * sizeof(int)));
+        CU(cudaMalloc(&s->block_best, kArgmaxBlocks * sizeof(Best)));
+        CU(cudaMalloc(&s->best, 2 * sizeof(Best)));
+        CU(cudaMalloc(&s->ext, sizeof(ExtendParams)));
+        CU(cudaMalloc(&s->z_dev, (size_t)s->d_pad * esize));
+        int r = ensure_width(s, 32);
+        if (r) return r;
+        const int blocks = grid_for(s, s->n, 8);
+        if (x_dtype == ITAL_F32)
+            k_sqnorm<float><<<blocks, 256, 0, s->stream>>>((const float*)s->X, s->n, (int)s->d_pad, s->sqn);
+        else
+            k_sqnorm<double><<<blocks, 256, 0, s->stream>>>((const double*)s->X, s->n, (int)s->d_pad, s->sqn);
+        CU(cudaGetLastError());
+        return reset_model(s);
+    };
+    rc = body();
+    if (rc != ITAL_OK) {
+        free_all(s);
+        delete s;
+        return rc;
+    }
+    *out = s;
+    return ITAL_OK;
+}
+
+int ital_destroy(ital_shard* s) {
+    if (!s) return ITAL_OK;
+    free_all(s);
+    delete s;
+    return ITAL_OK;
+}
+
+int ital_set_stream(ital_shard* s, void* cuda_stream) {
+    if (!s) return fail(ITAL_EINVAL, "null shard");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    s->stream = (cudaStream_t)cuda_stream;
+    return ITAL_OK;
+}
+
+int ital_reset(ital_shard* s) {
+    if (!s) return fail(ITAL_EINVAL, "null shard");
+    CU(cudaSetDevice(s->device));
+    return reset_model(s);
+}
+
+int64_t ital_record_doubles(const ital_shard* s) { return s ? record_doubles(s) : 0; }
+int64_t ital_width_cap(const ital_shard* s) { return s ? s->w_cap : 0; }
+int64_t ital_width(const ital_shard* s) { return s ? s->W : 0; }
+
+int ital_export_points(ital_shard* s, int q, const int64_t* global_idx, double* records) {
+    if (!s || q < 0 || (q > 0 && (!global_idx || !records))) return fail(ITAL_EINVAL, "ital_export_points: bad arguments");
+    CU(cudaSetDevice(s->device));
+    int rc = ensure_record_buffers(s, std::max(q, 1));
+    if (rc) return rc;
+    const int64_t rl = record_doubles(s);
+    bool any = false;
+    for (int a = 0; a < q; ++a) {
+        const int64_t loc = global_idx[a] - s->row_offset;
+        if (loc >= 0 && loc < s->n) {
+            rc = make_record(s, loc, s->rec_dev + a * rl);
+            if (rc) return rc;
+            any = true;
+        }
+    }
+    if (any) {
+        CU(cudaMemcpyAsync(s->rec_host, s->rec_dev, (size_t)q * rl * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    for (int a = 0; a < q; ++a) {
+        const int64_t loc = global_idx[a] - s->row_offset;
+        if (loc >= 0 && loc < s->n) memcpy(records + a * rl, s->rec_host + a * rl, (size_t)rl * sizeof(double));
+        else memset(records + a * rl, 0, (size_t)rl * sizeof(double));
+    }
+    return ITAL_OK;
+}
+
+int ital_add_labelled(ital_shard* s, const double* record, double y) {
+    if (!s || !record) return fail(ITAL_EINVAL, "ital_add_labelled: bad arguments");
+    if (s->fetching) return fail(ITAL_ESTATE, "ital_add_labelled: a fetch is in progress");
+    CU(cudaSetDevice(s->device));
+    // the capacity (and with it the record layout) may have to grow first: copy the record out
+    const int64_t old_cap = s->w_cap;
+    std::vector<double> u(record + ITAL_RECORD_HEADER, record + ITAL_RECORD_HEADER + s->W);
+    std::vector<double> x(record + ITAL_RECORD_HEADER + old_cap, record + ITAL_RECORD_HEADER + old_cap + s->d);
+    double hdr[ITAL_RECORD_HEADER];
+    memcpy(hdr, record, sizeof hdr);
+    int rc = ensure_width(s, s->W + 1);
+    if (rc) return rc;
+    std::vector<double> rec((size_t)record_doubles(s), 0.0);
+    memcpy(rec.data(), hdr, sizeof hdr);
+    std::copy(u.begin(), u.end(), rec.begin() + ITAL_RECORD_HEADER);
+    std::copy(x.begin(), x.end(), rec.begin() + ITAL_RECORD_HEADER + s->w_cap);
+    // rank-1 extension of the Cholesky factor of K_LL + noise I (replaces the full re-inversion of gp.py:194)
+    const double v_r = hdr[5];
+    double piv2 = v_r + s->noise;
+    if (!(piv2 > 0)) piv2 = std::numeric_limits<double>::min();
+    const double piv = std::sqrt(piv2);
+    const double beta = (y - hdr[2]) / piv;
+    rc = extend_with_record(s, rec.data(), s->W, piv, beta, 1);
+    if (rc) return rc;
+    std::vector<double> row(u);
+    row.push_back(piv);
+    s->LK.push_back(row);
+    s->beta.push_back(beta);
+    s->lab_x.insert(s->lab_x.end(), x.begin(), x.end());
+    s->lab_sqn.push_back(hdr[4]);
+    s->lab_y.push_back(y);
+    s->lab_idx.push_back((int64_t)hdr[0]);
+    s->lab_dev_valid = false;
+    s->W += 1;
+    int64_t g = (int64_t)hdr[0];
+    return ital_mark_seen(s, 1, &g);
+}
+
+int ital_mark_seen(ital_shard* s, int64_t m, const int64_t* global_idx) {
+    if (!s || m < 0 || (m > 0 && !global_idx)) return fail(ITAL_EINVAL, "ital_mark_seen: bad arguments");
+    CU(cudaSetDevice(s->device));
+    std::vector<int64_t> loc;
+    for (int64_t k = 0; k < m; ++k) {
+        const int64_t l = global_idx[k] - s->row_offset;
+        if (l >= 0 && l < s->n) loc.push_back(l);
+    }
+    if (loc.empty()) return ITAL_OK;
+    int rc = ensure_idx(s, (int64_t)loc.size());
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(s->idx_dev, loc.data(), loc.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream));
+    k_mask_rows<<<grid_for(s, (int64_t)loc.size(), 256), 256, 0, s->stream>>>(s->mask, s->idx_dev, (int64_t)loc.size(), kSeen);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s->stream));
+    return ITAL_OK;
+}
+
+int ital_restrict_candidates(ital_shard* s, int64_t m, const int64_t* global_idx) {
+    if (!s || (m > 0 && !global_idx)) return fail(ITAL_EINVAL, "ital_restrict_candidates: bad arguments");
+    CU(cudaSetDevice(s->device));
+    const int blocks = grid_for(s, s->n, 256);
+    if (m < 0) {
+        k_mask_all<<<blocks, 256, 0, s->stream>>>(s->mask, s->n, (uint8_t)~kRestricted, 0);
+        CU(cudaGetLastError());
+        return ITAL_OK;
+    }
+    // everything restricted, then the listed rows released
+    k_mask_all<<<blocks, 256, 0, s->stream>>>(s->mask, s->n, 0xff, kRestricted);
+    CU(cudaGetLastError());
+    std::vector<int64_t> loc;
+    for (int64_t k = 0; k < m; ++k) {
+        const int64_t l = global_idx[k] - s->row_offset;
+        if (l >= 0 && l < s->n) loc.push_back(l);
+    }
+    if (!loc.empty()) {
+        int rc = ensure_idx(s, (int64_t)loc.size());
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(s->idx_dev, loc.data(), loc.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream));
+        k_mask_clear_rows<<<grid_for(s, (int64_t)loc.size(), 256), 256, 0, s->stream>>>(s->mask, s->idx_dev,
+                                                                                       (int64_t)loc.size(), kRestricted);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    return ITAL_OK;
+}
+
+int ital_fetch_begin(ital_shard* s, double label_prob, double mistake_prob) {
+    if (!s) return fail(ITAL_EINVAL, "null shard");
+    if (s->W == 0) return fail(ITAL_ESTATE, "fetch before any labelled point or query (the reference fails here too: gp.K_inv is None)");
+    if (!(label_prob >= 1.0 && mistake_prob <= 0.0))
+        return fail(ITAL_EINVAL, "only the perfect-user feedback model (label_prob >= 1, mistake_prob <= 0) is implemented on the GPU path");
+    CU(cudaSetDevice(s->device));
+    if (s->fetching) {
+        int rc = ital_fetch_end(s);
+        if (rc) return rc;
+    }
+    s->fetching = true;
+    s->t = 0;
+    s->base_m.clear();
+    s->base_L.clear();
+    s->selected.clear();
+    s->label_prob = label_prob;
+    s->mistake_prob = mistake_prob;
+    return ITAL_OK;
+}
+
+int ital_fetch_propose(ital_shard* s, double floor_score, int exhaustive, double* record) {
+    if (!s || !record) return fail(ITAL_EINVAL, "ital_fetch_propose: bad arguments");
+    if (!s->fetching) return fail(ITAL_ESTATE, "ital_fetch_propose outside a fetch");
+    CU(cudaSetDevice(s->device));
+    int rc = ensure_record_buffers(s, 1);
+    if (rc) return rc;
+    const int blocks = std::min(kArgmaxBlocks, grid_for(s, s->n, 256));
+    CU(cudaMemsetAsync(s->counters, 0, 4 * sizeof(int), s->stream));
+    for (double& x : s->stats) x = 0.0;
+    if (s->t == 0) {
+        k_score0<<<blocks, 256, 0, s->stream>>>(s->n, s->m, s->v, s->mask, s->score, s->gain, s->block_best, s->log1p_eps);
+        k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, blocks, s->best);
+        CU(cudaGetLastError());
+        s->h_base = 0.0;
+        s->n_nodes = 1;
+    } else {
+        if (s->t > 10) return fail(ITAL_EINVAL, "batches of more than 11 samples are not supported");
+        // shared nodes of this step from the base selected so far
+        std::vector<double> Lb((size_t)s->t * s->t, 0.0);
+        for (int a = 0; a < s->t; ++a)
+            for (int b = 0; b <= a; ++b) Lb[(size_t)a * s->t + b] = s->base_L[a][b];
+        snq::Nodes nd = snq::generate(s->t, s->base_m.data(), Lb.data());
+        rc = upload_nodes(s, nd);
+        if (rc) return rc;
+        k_fill<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->score, s->n, std::numeric_limits<double>::quiet_NaN());
+        if (!exhaustive) {
+            // most promising candidate first: its exact score is the pruning threshold
+            k_argmax_rows<<<blocks, 256, 0, s->stream>>>(s->n, s->gain, s->mask, s->block_best);
+            k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, blocks, s->best + 1);
+            k_list_from_best<<<1, 1, 0, s->stream>>>(s->best + 1, s->counters, s->worklist);
+            CU(cudaGetLastError());
+            rc = launch_eval(s, 1);
+            if (rc) return rc;
+            k_argmax_list<<<1, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->block_best);
+            k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, 1, s->best + 1);
+            CU(cudaMemsetAsync(s->counters, 0, 2 * sizeof(int), s->stream));
+        }
+        k_worklist<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->n, s->mask, s->gain, s->h_base, s->best + 1,
+                                                                    floor_score, kPruneMargin, exhaustive,
+                                                                    s->counters, s->worklist);
+        CU(cudaGetLastError());
+        rc = launch_eval(s, exhaustive ? (int)std::min<int64_t>(s->n, 1 << 30) : 1 << 16);
+        if (rc) return rc;
+        const int lb = std::min(kArgmaxBlocks, grid_for(s, exhaustive ? s->n : 1 << 16, 256));
+        k_argmax_list<<<lb, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->block_best);
+        k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, lb, s->best);
+        CU(cudaGetLastError());
+    }
+    rc = make_record(s, -1, s->rec_dev);
+    if (rc) return rc;
+    int cnt[4] = {0, 0, 0, 0};
+    const int64_t rl = record_doubles(s);
+    CU(cudaMemcpyAsync(s->rec_host, s->rec_dev, (size_t)rl * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(cnt, s->counters, sizeof cnt, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    memcpy(record, s->rec_host, (size_t)rl * sizeof(double));
+    s->stats[1] = s->t == 0 ? -1.0 : (double)cnt[0] + (exhaustive ? 0.0 : 1.0);
+    s->stats[2] = (double)s->n_nodes;
+    s->stats[3] = s->h_base;
+    s->stats[4] = (double)cnt[1];
+    return ITAL_OK;
+}
+
+int ital_fetch_commit(ital_shard* s, const double* record) {
+    if (!s || !record) return fail(ITAL_EINVAL, "ital_fetch_commit: bad arguments");
+    if (!s->fetching) return fail(ITAL_ESTATE, "ital_fetch_commit outside a fetch");
+    if (record[0] < 0) return fail(ITAL_EINVAL, "ital_fetch_commit: empty record");
+    CU(cudaSetDevice(s->device));
+    const int64_t g = (int64_t)record[0];
+    const int col = s->W + s->t;
+    const int64_t old_cap = s->w_cap;
+    std::vector<double> u(record + ITAL_RECORD_HEADER, record + ITAL_RECORD_HEADER + col);
+    std::vector<double> x(record + ITAL_RECORD_HEADER + old_cap, record + ITAL_RECORD_HEADER + old_cap + s->d);
+    double hdr[ITAL_RECORD_HEADER];
+    memcpy(hdr, record, sizeof hdr);
+    int rc = ensure_width(s, col + 1);
+    if (rc) return rc;
+    std::vector<double> rec((size_t)record_doubles(s), 0.0);
+    memcpy(rec.data(), hdr, sizeof hdr);
+    std::copy(u.begin(), u.end(), rec.begin() + ITAL_RECORD_HEADER);
+    std::copy(x.begin(), x.end(), rec.begin() + ITAL_RECORD_HEADER + s->w_cap);
+    // new row of the Cholesky factor of the batch's posterior covariance: [l_0 .. l_{t-1}, sqrt(cond. var)]
+    double cv = hdr[3];
+    if (!(cv > 1e-300)) cv = 1e-300;
+    const double piv = std::sqrt(cv);
+    std::vector<double> row(u.begin() + s->W, u.end());
+    row.push_back(piv);
+    const int64_t loc = g - s->row_offset;
+    if (loc >= 0 && loc < s->n) {
+        rc = ensure_idx(s, 1);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(s->idx_dev, &loc, sizeof loc, cudaMemcpyHostToDevice, s->stream));
+        k_mask_rows<<<1, 32, 0, s->stream>>>(s->mask, s->idx_dev, 1, kSelected);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    rc = extend_with_record(s, rec.data(), col, piv, 0.0, 0);
+    if (rc) return rc;
+    s->base_m.push_back(hdr[2]);
+    s->base_L.push_back(row);
+    s->selected.push_back(g);
+    s->t += 1;
+    return ITAL_OK;
+}
+
+int ital_fetch_end(ital_shard* s) {
+    if (!s) return fail(ITAL_EINVAL, "null shard");
+    CU(cudaSetDevice(s->device));
+    if (s->fetching) {
+        k_mask_all<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->mask, s->n, (uint8_t)~kSelected, 0);
+        CU(cudaGetLastError());
+    }
+    s->fetching = false;
+    s->t = 0;
+    s->base_m.clear();
+    s->base_L.clear();
+    return ITAL_OK;
+}
+
+int ital_fetch(ital_shard* s, int k, double label_prob, double mistake_prob, int exhaustive, int64_t* out_idx,
+               double* out_scores) {
+    if (!s || k < 0 || (k > 0 && !out_idx)) return fail(ITAL_EINVAL, "ital_fetch: bad arguments");
+    int rc = ital_fetch_begin(s, label_prob, mistake_prob);
+    if (rc) return rc;
+    std::vector<double> rec;
+    int got = 0;
+    for (int it = 0; it < k; ++it) {
+        rec.assign((size_t)record_doubles(s), 0.0);
+        rc = ital_fetch_propose(s, -std::numeric_limits<double>::infinity(), exhaustive, rec.data());
+        if (rc) break;
+        if (rec[0] < 0) break;   // no candidates left (k is clamped to the number of unseen rows, ital.py:99-100)
+        out_idx[got] = (int64_t)rec[0];
+        if (out_scores) out_scores[got] = rec[1];
+        ++got;
+        if (it + 1 < k) {
+            rc = ital_fetch_commit(s, rec.data());
+            if (rc) break;
+        }
+    }
+    int rc2 = ital_fetch_end(s);
+    if (rc) return rc;
+    if (rc2) return rc2;
+    return got;
+}
+
+int ital_fetch_stats(const ital_shard* s, double* out8) {
+    if (!s || !out8) return fail(ITAL_EINVAL, "ital_fetch_stats: bad arguments");
+    memcpy(out8, s->stats, sizeof s->stats);
+    return ITAL_OK;
+}
+
+static int copy_vec(ital_shard* s, const double* dev, double* out) {
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpyAsync(out, dev, (size_t)s->n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return ITAL_OK;
+}
+
+int ital_last_scores(ital_shard* s, double* out) {
+    if (!s || !out) return fail(ITAL_EINVAL, "bad arguments");
+    return copy_vec(s, s->score, out);
+}
+int ital_rel_mean(ital_shard* s, double* out) {
+    if (!s || !out) return fail(ITAL_EINVAL, "bad arguments");
+    return copy_vec(s, s->m, out);
+}
+int ital_rel_var(ital_shard* s, double* out) {
+    if (!s || !out) return fail(ITAL_EINVAL, "bad arguments");
+    return copy_vec(s, s->v, out);
+}
+
+int ital_predict(ital_shard* s, const double* Xt, int64_t mrows, double* out_mean, double* out_var) {
+    if (!s || !Xt || mrows < 0 || !out_mean) return fail(ITAL_EINVAL, "ital_predict: bad arguments");
+    if (s->W == 0) return fail(ITAL_ESTATE, "ital_predict before any labelled point");
+    if (mrows == 0) return ITAL_OK;
+    CU(cudaSetDevice(s->device));
+    const int nl = s->W;
+    if (!s->lab_dev_valid) {
+        if (nl > s->lab_dev_cap) {
+            for (double** p : {&s->lab_x_dev, &s->lab_sqn_dev, &s->w_vec_dev, &s->LK_dev})
+                if (*p) { CU(cudaFree(*p)); *p = nullptr; }
+            const int cap = std::max(64, 2 * nl);
+            CU(cudaMalloc(&s->lab_x_dev, (size_t)cap * s->d * sizeof(double)));
+            CU(cudaMalloc(&s->lab_sqn_dev, (size_t)cap * sizeof(double)));
+            CU(cudaMalloc(&s->w_vec_dev, (size_t)cap * sizeof(double)));
+            CU(cudaMalloc(&s->LK_dev, (size_t)cap * cap * sizeof(double)));
+            s->lab_dev_cap = cap;
+        }
+        // w = K^-1 y = L^-T (L^-1 y)  (gp.py:158,196)
+        std::vector<double> w(s->beta);
+        for (int a = nl - 1; a >= 0; --a) {
+            double acc = w[a];
+            for (int b = a + 1; b < nl; ++b) acc -= s->LK[b][a] * w[b];
+            w[a] = acc / s->LK[a][a];
+        }
+        std::vector<double> LKd((size_t)nl * nl, 0.0);
+        for (int a = 0; a < nl; ++a)
+            for (int b = 0; b <= a; ++b) LKd[(size_t)a * nl + b] = s->LK[a][b];
+        CU(cudaMemcpy(s->lab_x_dev, s->lab_x.data(), (size_t)nl * s->d * sizeof(double), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(s->lab_sqn_dev, s->lab_sqn.data(), (size_t)nl * sizeof(double), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(s->w_vec_dev, w.data(), (size_t)nl * sizeof(double), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(s->LK_dev, LKd.data(), (size_t)nl * nl * sizeof(double), cudaMemcpyHostToDevice));
+        s->lab_dev_valid = true;
+    }
+    double *xt_dev = nullptr, *mean_dev = nullptr, *var_dev = nullptr;
+    CU(cudaMalloc(&xt_dev, (size_t)mrows * s->d * sizeof(double)));
+    CU(cudaMalloc(&mean_dev, (size_t)mrows * sizeof(double)));
+    if (out_var) CU(cudaMalloc(&var_dev, (size_t)mrows * sizeof(double)));
+    CU(cudaMemcpyAsync(xt_dev, Xt, (size_t)mrows * s->d * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    const int threads = 128, wpb = threads / 32;
+    const size_t smem = (size_t)wpb * nl * sizeof(double);
+    k_predict<<<(unsigned)((mrows + wpb - 1) / wpb), threads, smem, s->stream>>>(
+        xt_dev, mrows, (int)s->d, s->lab_x_dev, s->lab_sqn_dev, nl, s->w_vec_dev, s->LK_dev, s->var,
+        -2.0 * s->ls * s->ls, mean_dev, var_dev);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_mean, mean_dev, (size_t)mrows * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (out_var) CU(cudaMemcpyAsync(out_var, var_dev, (size_t)mrows * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaFree(xt_dev));
+    CU(cudaFree(mean_dev));
+    if (var_dev) CU(cudaFree(var_dev));
+    return ITAL_OK;
+}
+
+int64_t ital_snq_nodes(int t, const double* m, const double* L, double* eta, double* w, int32_t* orth, double* masses) {
+    if (t < 1 || t > 10 || !m || !L) return fail(ITAL_EINVAL, "ital_snq_nodes: bad arguments");
+    if (!eta) {
+        int64_t n = 1;
+        for (int j = 0; j < t; ++j) n *= 2 * snq::order_for(t);
+        return n;
+    }
+    snq::Nodes nd = snq::generate(t, m, L);
+    memcpy(eta, nd.eta.data(), nd.eta.size() * sizeof(double));
+    if (w) memcpy(w, nd.w.data(), nd.w.size() * sizeof(double));
+    if (orth) memcpy(orth, nd.orth.data(), nd.orth.size() * sizeof(int32_t));
+    if (masses) memcpy(masses, nd.masses.data(), nd.masses.size() * sizeof(double));
+    return nd.n;
+}
+
+int ital_snq_order(int t) { return snq::order_for(t); }
+
+}  // extern "C"

@@ -1,0 +1,544 @@
+// Device kernels of the ITAL batch-selection path for sm_100a (B200).
+//
+// Memory layout in HBM (per shard, n = local rows, ldu = n rounded up to 32):
+//   X      [n][d_pad]  float or double, row-major, rows zero-padded to a multiple of 512 bytes
+//   sqn    [n]         double  |x_i|^2                                  (ital/gp.py:411,414-415)
+//   m, v   [n]         double  posterior mean / variance given the labelled set (ital/gp.py:221-229)
+//   U      [w_cap][ldu] double, COLUMN-major per projection: U[j][i] is entry j of L_K^-1 k(X_L, x_i),
+//                      continued past the labelled set by the points already selected in the running batch
+//                      (those extra columns are the l_i of SURVEY.md A.3)
+//   gain   [n]         double  last exactly evaluated MI gain of row i in this fetch (lazy-greedy bound)
+//   score  [n]         double  score of the last propose (NaN if not scored)
+//   mask   [n]         uint8   1 seen, 2 selected in this fetch, 4 not a candidate
+//
+// Kernels:
+//   k_sqnorm     one pass over X, |x_i|^2 in float64
+//   k_extend     THE streaming pass: X row . z in float64, RBF value, projection against the new Cholesky
+//                column, optional posterior mean/variance update.  HBM-bound: reads d_pad*sizeof(x) + 8*W + 8
+//                bytes and writes 8 bytes per row (plus 32 bytes of m, v read-modify-write when labelling).
+//   k_score0     closed-form first greedy step (one variable): binary entropy of Phi(m / sqrt(v))
+//   k_eval       exact MI of the worklist candidates with the step's shared quadrature nodes, one warp each
+//   k_argmax*    (score desc, index asc) reductions
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace italk {
+
+constexpr int kWarp = 32;
+constexpr double kEps = 1e-12;           // MutualInformation eps (ital/ital.py:144)
+
+struct Best {                            // result of an argmax reduction
+    double score;
+    long long idx;                       // local row, -1 if none
+};
+
+struct ExtendParams {                    // lives in device memory, written by the host before k_extend
+    double zn;                           // |z|^2
+    double piv;                          // pivot of the new Cholesky column
+    double beta;                         // new entry of L_K^-1 y (0 for a batch extension)
+    double pad;
+};
+
+__device__ __forceinline__ bool better(double sa, long long ia, double sb, long long ib) {
+    // NaN never wins; ties go to the lower index (np.argmax on the ascending candidate list, ital.py:98,130)
+    if (ib < 0) return ia >= 0;
+    if (ia < 0) return false;
+    if (sa != sa) return false;
+    if (sb != sb) return true;
+    return sa > sb || (sa == sb && ia < ib);
+}
+
+__device__ __forceinline__ double phi_cdf(double x) { return 0.5 * erfc(-x * 0.70710678118654752440); }
+
+__device__ __forceinline__ double mi_term(double p, double log1p_eps) {
+    // p * (log(p' + eps) - log(p + eps)) with p' = 1 (perfect user; ital.py:205-219)
+    return p * (log1p_eps - log(p + kEps));
+}
+
+template <typename XT> struct Vec;
+template <> struct Vec<float> {
+    static constexpr int N = 4;
+    float4 v;
+    __device__ __forceinline__ void load(const float* p) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    }
+    __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ __forceinline__ double get(int e) const {
+        return (double)(e == 0 ? v.x : e == 1 ? v.y : e == 2 ? v.z : v.w);
+    }
+};
+template <> struct Vec<double> {
+    static constexpr int N = 2;
+    double2 v;
+    __device__ __forceinline__ void load(const double* p) {
+        asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    }
+    __device__ __forceinline__ void zero() { v = make_double2(0.0, 0.0); }
+    __device__ __forceinline__ double get(int e) const { return e == 0 ? v.x : v.y; }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+template <typename XT>
+__global__ void __launch_bounds__(256) k_sqnorm(const XT* __restrict__ X, int64_t n, int d_pad,
+                                                double* __restrict__ sqn) {
+    constexpr int VN = Vec<XT>::N;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int nchunks = d_pad / (32 * VN);
+    for (int64_t row = warp; row < n; row += nwarps) {
+        const XT* p = X + row * (int64_t)d_pad;
+        double acc = 0.0;
+        for (int c = 0; c < nchunks; ++c) {
+            Vec<XT> x;
+            x.load(p + (c * 32 + lane) * VN);
+#pragma unroll
+            for (int e = 0; e < VN; ++e) acc = fma(x.get(e), x.get(e), acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) sqn[row] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The streaming pass.  One warp owns a unit of 32 consecutive rows: phase 1 streams the rows with coalesced
+// 16-byte loads (lane l holds columns (c*32 + l)*VN .. +VN of every row, the matching slice of z stays in
+// registers) and leaves 32 partial sums per row in shared memory; phase 2 turns the warp by 90 degrees --
+// lane l finishes row l -- so that the exp, the W-long projection and the stores run with all lanes busy and
+// coalesced against the column-major U.
+template <typename XT, int NC>   // NC: 16-byte chunks per lane and row (d_pad = NC * 32 * VN); 0 = run time
+__global__ void __launch_bounds__(256, 2)
+k_extend(const XT* __restrict__ X, int64_t n, int d_pad, const XT* __restrict__ z,
+         const ExtendParams* __restrict__ prm, const double* __restrict__ ur, int W,
+         const double* __restrict__ sqn, double* __restrict__ U, int64_t ldu,
+         double* __restrict__ m, double* __restrict__ v, int labelled, double var, double neg2ls2) {
+    constexpr int VN = Vec<XT>::N;
+    constexpr int RB = 4;                               // rows in flight per warp
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int nwarp_blk = blockDim.x >> 5;
+    double* part = smem + (size_t)wib * 32 * 33;        // [32 rows][33]
+    double* ur_s = smem + (size_t)nwarp_blk * 32 * 33;  // [W]
+    double* z_s = ur_s + ((W + 1) & ~1);                // [d_pad] only when NC == 0
+    for (int j = threadIdx.x; j < W; j += blockDim.x) ur_s[j] = ur[j];
+    const int nchunks = NC > 0 ? NC : d_pad / (32 * VN);
+    double zr[(NC > 0 ? NC : 1) * VN];
+    if (NC > 0) {
+#pragma unroll
+        for (int c = 0; c < (NC > 0 ? NC : 1); ++c)
+#pragma unroll
+            for (int e = 0; e < VN; ++e) zr[c * VN + e] = (double)z[(c * 32 + lane) * VN + e];
+    } else {
+        for (int j = threadIdx.x; j < d_pad; j += blockDim.x) z_s[j] = (double)z[j];
+    }
+    __syncthreads();
+    const double zn = prm->zn, piv = prm->piv, beta = prm->beta;
+
+    const int64_t n_units = (n + 31) >> 5;
+    const int64_t warp_global = (int64_t)blockIdx.x * nwarp_blk + wib;
+    const int64_t warps_total = (int64_t)gridDim.x * nwarp_blk;
+    for (int64_t unit = warp_global; unit < n_units; unit += warps_total) {
+        const int64_t row0 = unit << 5;
+        // ---- phase 1: 32 partial dot products per row ----
+        if (NC > 0) {
+#pragma unroll 1
+            for (int r = 0; r < 32; r += RB) {
+                Vec<XT> x[RB][NC > 0 ? NC : 1];
+#pragma unroll
+                for (int rr = 0; rr < RB; ++rr) {
+                    const int64_t row = row0 + r + rr;
+                    const XT* p = X + row * (int64_t)d_pad + lane * VN;
+#pragma unroll
+                    for (int c = 0; c < (NC > 0 ? NC : 1); ++c) {
+                        if (row < n) x[rr][c].load(p + c * 32 * VN); else x[rr][c].zero();
+                    }
+                }
+#pragma unroll
+                for (int rr = 0; rr < RB; ++rr) {
+                    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                    for (int c = 0; c < (NC > 0 ? NC : 1); ++c)
+#pragma unroll
+                        for (int e = 0; e < VN; e += 2) {
+                            a0 = fma(x[rr][c].get(e), zr[c * VN + e], a0);
+                            a1 = fma(x[rr][c].get(e + 1), zr[c * VN + e + 1], a1);
+                        }
+                    part[(r + rr) * 33 + lane] = a0 + a1;
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int r = 0; r < 32; r += RB) {
+                double acc[RB];
+#pragma unroll
+                for (int rr = 0; rr < RB; ++rr) acc[rr] = 0.0;
+                for (int c = 0; c < nchunks; ++c) {
+                    Vec<XT> x[RB];
+#pragma unroll
+                    for (int rr = 0; rr < RB; ++rr) {
+                        const int64_t row = row0 + r + rr;
+                        if (row < n) x[rr].load(X + row * (int64_t)d_pad + (c * 32 + lane) * VN);
+                        else x[rr].zero();
+                    }
+                    const double* zz = z_s + (c * 32 + lane) * VN;
+#pragma unroll
+                    for (int rr = 0; rr < RB; ++rr)
+#pragma unroll
+                        for (int e = 0; e < VN; ++e) acc[rr] = fma(x[rr].get(e), zz[e], acc[rr]);
+                }
+#pragma unroll
+                for (int rr = 0; rr < RB; ++rr) part[(r + rr) * 33 + lane] = acc[rr];
+            }
+        }
+        __syncwarp();
+        // ---- phase 2: lane l finishes row row0 + l ----
+        const int64_t i = row0 + lane;
+        if (i < n) {
+            double dot = 0.0;
+#pragma unroll
+            for (int l = 0; l < 32; ++l) dot += part[lane * 33 + l];
+            // v * exp((A + B - 2 * C) / s), s = -2 * sigma^2   (ital/gp.py:416)
+            const double kv = var * exp((sqn[i] + zn - 2.0 * dot) / neg2ls2);
+            double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+            const double* u = U + i;
+            int j = 0;
+            for (; j + 4 <= W; j += 4) {
+                p0 = fma(u[(int64_t)(j + 0) * ldu], ur_s[j + 0], p0);
+                p1 = fma(u[(int64_t)(j + 1) * ldu], ur_s[j + 1], p1);
+                p2 = fma(u[(int64_t)(j + 2) * ldu], ur_s[j + 2], p2);
+                p3 = fma(u[(int64_t)(j + 3) * ldu], ur_s[j + 3], p3);
+            }
+            for (; j < W; ++j) p0 = fma(u[(int64_t)j * ldu], ur_s[j], p0);
+            const double e = (kv - ((p0 + p1) + (p2 + p3))) / piv;
+            U[(int64_t)W * ldu + i] = e;
+            if (labelled) {
+                m[i] = fma(e, beta, m[i]);
+                v[i] = fma(-e, e, v[i]);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// First greedy step: one variable, closed form (ital/ital.py:364-369 and 183-224 with one configuration).
+// Also seeds the lazy-greedy bound: gain = score.
+__global__ void __launch_bounds__(256) k_score0(int64_t n, const double* __restrict__ m,
+                                                const double* __restrict__ v, const uint8_t* __restrict__ mask,
+                                                double* __restrict__ score, double* __restrict__ gain,
+                                                Best* __restrict__ block_best, double log1p_eps) {
+    double bs = 0.0;
+    long long bi = -1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = nan("");
+        if (mask[i] == 0) {
+            const double var_i = fmax(v[i], 0.0);        // predict_stored(cov_mode='diag') clamps (gp.py:229)
+            const double sd = sqrt(var_i);
+            double p1, p0;
+            if (sd > 0.0) {
+                const double zz = m[i] / sd;
+                p1 = phi_cdf(zz);
+                p0 = phi_cdf(-zz);
+            } else {
+                p1 = m[i] > 0.0 ? 1.0 : 0.0;
+                p0 = 1.0 - p1;
+            }
+            s = mi_term(p0, log1p_eps) + mi_term(p1, log1p_eps);
+            gain[i] = s;
+            if (better(s, i, bs, bi)) { bs = s; bi = i; }
+        }
+        score[i] = s;
+    }
+    // block reduction
+    __shared__ double ss[8];
+    __shared__ long long si[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(os, oi, bs, bi)) { bs = os; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = bs; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            if (better(ss[w], si[w], bs, bi)) { bs = ss[w]; bi = si[w]; }
+        block_best[blockIdx.x].score = bs;
+        block_best[blockIdx.x].idx = bi;
+    }
+}
+
+// argmax of `values` over candidate rows (mask == 0); stage 1 of 2
+__global__ void __launch_bounds__(256) k_argmax_rows(int64_t n, const double* __restrict__ values,
+                                                     const uint8_t* __restrict__ mask,
+                                                     Best* __restrict__ block_best) {
+    double bs = 0.0;
+    long long bi = -1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (mask[i] == 0 && better(values[i], i, bs, bi)) { bs = values[i]; bi = i; }
+    __shared__ double ss[8];
+    __shared__ long long si[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(os, oi, bs, bi)) { bs = os; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = bs; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            if (better(ss[w], si[w], bs, bi)) { bs = ss[w]; bi = si[w]; }
+        block_best[blockIdx.x].score = bs;
+        block_best[blockIdx.x].idx = bi;
+    }
+}
+
+// argmax of score[] over the rows listed in the worklist; stage 1 of 2
+__global__ void __launch_bounds__(256) k_argmax_list(const int* __restrict__ count,
+                                                     const int* __restrict__ list,
+                                                     const double* __restrict__ score,
+                                                     Best* __restrict__ block_best) {
+    const int n = *count;
+    double bs = 0.0;
+    long long bi = -1;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const long long i = list[k];
+        if (better(score[i], i, bs, bi)) { bs = score[i]; bi = i; }
+    }
+    __shared__ double ss[8];
+    __shared__ long long si[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(os, oi, bs, bi)) { bs = os; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = bs; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            if (better(ss[w], si[w], bs, bi)) { bs = ss[w]; bi = si[w]; }
+        block_best[blockIdx.x].score = bs;
+        block_best[blockIdx.x].idx = bi;
+    }
+}
+
+// stage 2: one block reduces the per-block results into out[0]
+__global__ void __launch_bounds__(256) k_argmax_final(const Best* __restrict__ block_best, int nblocks,
+                                                      Best* __restrict__ out) {
+    double bs = 0.0;
+    long long bi = -1;
+    for (int k = threadIdx.x; k < nblocks; k += blockDim.x)
+        if (better(block_best[k].score, block_best[k].idx, bs, bi)) { bs = block_best[k].score; bi = block_best[k].idx; }
+    __shared__ double ss[8];
+    __shared__ long long si[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(os, oi, bs, bi)) { bs = os; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = bs; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            if (better(ss[w], si[w], bs, bi)) { bs = ss[w]; bi = si[w]; }
+        out->score = bs;
+        out->idx = bi;
+    }
+}
+
+// worklist[0] = the row found by an argmax (used to score the most promising candidate first)
+__global__ void k_list_from_best(const Best* __restrict__ best, int* __restrict__ count, int* __restrict__ list) {
+    if (best->idx >= 0) { list[0] = (int)best->idx; *count = 1; } else { *count = 0; }
+}
+
+// Lazy-greedy worklist: rows whose upper bound gain + H(base) can still reach the score already achieved.
+// thr_src: score of the most promising candidate (device), floor_score: from other shards, margin: slack for
+// quadrature round-off between steps.  exhaustive: every candidate.
+__global__ void __launch_bounds__(256) k_worklist(int64_t n, const uint8_t* __restrict__ mask,
+                                                  const double* __restrict__ gain, double h_base,
+                                                  const Best* __restrict__ thr_src, double floor_score,
+                                                  double margin, int exhaustive, int* __restrict__ count,
+                                                  int* __restrict__ list) {
+    double thr = -1e300;
+    if (!exhaustive) {
+        thr = floor_score;
+        if (thr_src->idx >= 0 && thr_src->score == thr_src->score) thr = fmax(thr, thr_src->score);
+        thr -= margin;
+    }
+    const int lane = threadIdx.x & 31;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n;
+         i0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = i0 + lane;
+        const bool take = i < n && mask[i] == 0 && (exhaustive || gain[i] + h_base >= thr);
+        const unsigned ballot = __ballot_sync(0xffffffffu, take);
+        if (ballot != 0) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(count, __popc(ballot));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (take) list[base + __popc(ballot & ((1u << lane) - 1))] = (int)i;
+        }
+    }
+}
+
+// Exact MI of one candidate per warp with the shared nodes of the step (t >= 1 base variables):
+//   P(r_base, +) = sum_{q in group r_base} w_q * Phi((m_i + l_i . eta_q) / s_i),  P(r_base, -) = P(r_base) - P(+)
+//   score = sum_r p_r * (log(1 + eps) - log(p_r + eps))
+// Replaces 2^(t+1) calls of prob_rel + updated_prob_rel per candidate (ital/ital.py:193-219).
+template <int T>   // T = t if 1..3 (unrolled), 0 = run time
+__global__ void __launch_bounds__(256) k_eval(const int* __restrict__ count, const int* __restrict__ list, int t_rt,
+                                              const double* __restrict__ m, const double* __restrict__ v,
+                                              const double* __restrict__ U, int64_t ldu, int W0,
+                                              const double* __restrict__ eta, const double* __restrict__ w,
+                                              int64_t n_nodes, const int* __restrict__ group_begin,
+                                              const double* __restrict__ masses, double h_base,
+                                              double log1p_eps, double flag_var,
+                                              double* __restrict__ score, double* __restrict__ gain,
+                                              int* __restrict__ n_flagged) {
+    const int t = T > 0 ? T : t_rt;
+    const int lane = threadIdx.x & 31;
+    const int n_items = *count;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int warps_total = (gridDim.x * blockDim.x) >> 5;
+    for (int item = warp_global; item < n_items; item += warps_total) {
+        const int64_t i = list[item];
+        double l[T > 0 ? T : 10];
+        double s2 = v[i];
+        for (int j = 0; j < t; ++j) {
+            l[j] = U[(int64_t)(W0 + j) * ldu + i];
+            s2 = fma(-l[j], l[j], s2);
+        }
+        const double mi = m[i];
+        const double s = s2 > 0.0 ? sqrt(s2) : 0.0;
+        double sc = 0.0;
+        const int nb = 1 << t;
+        for (int b = 0; b < nb; ++b) {
+            double acc = 0.0;
+            const int g0 = group_begin[b], g1 = group_begin[b + 1];
+            for (int q = g0 + lane; q < g1; q += 32) {
+                double num = mi;
+#pragma unroll
+                for (int j = 0; j < (T > 0 ? T : 10); ++j)
+                    if (j < t) num = fma(l[j], eta[(int64_t)j * n_nodes + q], num);
+                const double cdf = s > 0.0 ? phi_cdf(num / s) : (num > 0.0 ? 1.0 : 0.0);
+                acc = fma(w[q], cdf, acc);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            const double p_plus = acc;
+            const double p_minus = fmax(masses[b] - acc, 0.0);
+            sc += mi_term(p_plus, log1p_eps) + mi_term(p_minus, log1p_eps);
+        }
+        if (lane == 0) {
+            score[i] = sc;
+            gain[i] = sc - h_base;
+            if (s2 < flag_var) atomicAdd(n_flagged, 1);
+        }
+    }
+}
+
+__global__ void k_fill(double* __restrict__ p, int64_t n, double value) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = value;
+}
+
+// mask[i] = (mask[i] & ~clear) | set for the listed local rows
+__global__ void k_mask_rows(uint8_t* __restrict__ mask, const int64_t* __restrict__ rows, int64_t m,
+                            uint8_t set_bits) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += (int64_t)gridDim.x * blockDim.x)
+        mask[rows[k]] |= set_bits;
+}
+
+__global__ void k_mask_all(uint8_t* __restrict__ mask, int64_t n, uint8_t and_bits, uint8_t or_bits) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        mask[i] = (mask[i] & and_bits) | or_bits;
+}
+
+__global__ void k_mask_clear_rows(uint8_t* __restrict__ mask, const int64_t* __restrict__ rows, int64_t m,
+                                  uint8_t clear_bits) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += (int64_t)gridDim.x * blockDim.x)
+        mask[rows[k]] &= (uint8_t)~clear_bits;
+}
+
+// Point record of local row `row` (or of best->idx when row < 0); see ITAL_RECORD_HEADER in ital_b200.h.
+template <typename XT>
+__global__ void __launch_bounds__(256) k_record(long long row, const Best* __restrict__ best, int64_t row_offset,
+                                                const XT* __restrict__ X, int d, int d_pad,
+                                                const double* __restrict__ sqn, const double* __restrict__ m,
+                                                const double* __restrict__ v, const double* __restrict__ U,
+                                                int64_t ldu, int W_lab, int W_tot, int w_cap,
+                                                const double* __restrict__ gain, double* __restrict__ rec) {
+    double score = 0.0;
+    if (row < 0) { row = best->idx; score = best->score; }
+    const int rec_len = 8 + w_cap + d;
+    if (row < 0) {
+        for (int k = threadIdx.x; k < rec_len; k += blockDim.x) rec[k] = k == 0 ? -1.0 : (k == 1 ? -INFINITY : 0.0);
+        return;
+    }
+    for (int j = threadIdx.x; j < w_cap; j += blockDim.x) rec[8 + j] = j < W_tot ? U[(int64_t)j * ldu + row] : 0.0;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) rec[8 + w_cap + j] = (double)X[row * (int64_t)d_pad + j];
+    if (threadIdx.x == 0) {
+        double cv = v[row];
+        for (int j = W_lab; j < W_tot; ++j) { const double e = U[(int64_t)j * ldu + row]; cv = fma(-e, e, cv); }
+        rec[0] = (double)(row_offset + row);
+        rec[1] = score;
+        rec[2] = m[row];
+        rec[3] = cv;
+        rec[4] = sqn[row];
+        rec[5] = v[row];
+        rec[6] = gain[row];
+        rec[7] = 0.0;
+    }
+}
+
+// GaussianProcess.predict (ital/gp.py:264-292) for arbitrary rows: one warp per test row.
+//   k_l = var * exp((|x|^2 + |x_l|^2 - 2 x . x_l) / s);  mean = w . k;  var = max(0, var - |L_K^-1 k|^2)
+__global__ void __launch_bounds__(128) k_predict(const double* __restrict__ Xt, int64_t mrows, int d,
+                                                 const double* __restrict__ Xl, const double* __restrict__ sqn_l,
+                                                 int nl, const double* __restrict__ wvec,
+                                                 const double* __restrict__ LK, double var, double neg2ls2,
+                                                 double* __restrict__ out_mean, double* __restrict__ out_var) {
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double* kbuf = sm + (size_t)wib * nl;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (row >= mrows) return;
+    const double* x = Xt + row * (int64_t)d;
+    double xn = 0.0;
+    for (int j = lane; j < d; j += 32) xn = fma(x[j], x[j], xn);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) xn += __shfl_xor_sync(0xffffffffu, xn, o);
+    for (int l = 0; l < nl; ++l) {
+        double acc = 0.0;
+        const double* xl = Xl + (int64_t)l * d;
+        for (int j = lane; j < d; j += 32) acc = fma(x[j], xl[j], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) kbuf[l] = var * exp((sqn_l[l] + xn - 2.0 * acc) / neg2ls2);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        double mean = 0.0;
+        for (int l = 0; l < nl; ++l) mean = fma(wvec[l], kbuf[l], mean);
+        out_mean[row] = mean;
+        if (out_var != nullptr) {
+            double q = 0.0;
+            for (int a = 0; a < nl; ++a) {               // forward substitution with the Cholesky factor
+                double u = kbuf[a];
+                for (int b = 0; b < a; ++b) u = fma(-LK[(int64_t)a * nl + b], kbuf[b], u);
+                u /= LK[(int64_t)a * nl + a];
+                kbuf[a] = u;
+                q = fma(u, u, q);
+            }
+            out_var[row] = fmax(0.0, var - q);
+        }
+    }
+}
+
+}  // namespace italk

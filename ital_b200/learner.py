@@ -1,0 +1,376 @@
+"""`ITAL` learner with the reference's public interface over the CUDA library (include/ital_b200.h).
+
+Mirrors /root/reference/ital/ital.py:12-134 (ITAL) and /root/reference/ital/retrieval_base.py:7-194
+(ActiveRetrievalBase): same constructor keywords, same methods, same attributes read by the reference's
+`run_experiment.py` / `utils.LEARNERS`, same exceptions.  Everything that scales with the pool runs on the
+GPU; there is no CPU fallback (a missing library or device raises).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _capi
+from .dist import LocalComm, TorchComm, partition_rows, pick_winner
+
+
+class _Shard(object):
+    """Thin owner of one `ital_shard*`."""
+
+    def __init__(self, X, dtype_code, row_offset, n_data, length_scale, var, noise, device):
+        self.lib = _capi.load()
+        self.handle = ctypes.c_void_p()
+        self.n_local, self.d = X.shape
+        self._keepalive = X
+        _capi.check(self.lib.ital_create(ctypes.byref(self.handle), int(device), X.ctypes.data_as(ctypes.c_void_p),
+                                         dtype_code, self.n_local, self.d, int(row_offset), int(n_data),
+                                         float(length_scale), float(var), float(noise)))
+        self._keepalive = None
+
+    def close(self):
+        if self.handle:
+            self.lib.ital_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    __del__ = close
+
+    def record_doubles(self):
+        return int(self.lib.ital_record_doubles(self.handle))
+
+    def reset(self):
+        _capi.check(self.lib.ital_reset(self.handle))
+
+    def set_stream(self, stream_ptr):
+        _capi.check(self.lib.ital_set_stream(self.handle, ctypes.c_void_p(stream_ptr)))
+
+    def export_points(self, idx):
+        idx = _capi.as_i64(idx)
+        rec = np.zeros((len(idx), self.record_doubles()))
+        _capi.check(self.lib.ital_export_points(self.handle, len(idx), _capi.i64ptr(idx), _capi.dptr(rec)))
+        return rec
+
+    def add_labelled(self, record, y):
+        record = _capi.as_f64(record)
+        _capi.check(self.lib.ital_add_labelled(self.handle, _capi.dptr(record), float(y)))
+
+    def mark_seen(self, idx):
+        idx = _capi.as_i64(idx)
+        if len(idx):
+            _capi.check(self.lib.ital_mark_seen(self.handle, len(idx), _capi.i64ptr(idx)))
+
+    def restrict_candidates(self, idx):
+        if idx is None:
+            _capi.check(self.lib.ital_restrict_candidates(self.handle, -1, None))
+        else:
+            idx = _capi.as_i64(idx)
+            _capi.check(self.lib.ital_restrict_candidates(self.handle, len(idx), _capi.i64ptr(idx)))
+
+    def fetch_begin(self, label_prob, mistake_prob):
+        _capi.check(self.lib.ital_fetch_begin(self.handle, float(label_prob), float(mistake_prob)))
+
+    def fetch_propose(self, floor_score, exhaustive):
+        rec = np.zeros(self.record_doubles())
+        _capi.check(self.lib.ital_fetch_propose(self.handle, float(floor_score), int(bool(exhaustive)),
+                                                _capi.dptr(rec)))
+        return rec
+
+    def fetch_commit(self, record):
+        record = _capi.as_f64(record)
+        _capi.check(self.lib.ital_fetch_commit(self.handle, _capi.dptr(record)))
+
+    def fetch_end(self):
+        _capi.check(self.lib.ital_fetch_end(self.handle))
+
+    def fetch(self, k, label_prob, mistake_prob, exhaustive):
+        idx = np.zeros(max(k, 1), dtype=np.int64)
+        scores = np.zeros(max(k, 1))
+        got = _capi.check(self.lib.ital_fetch(self.handle, int(k), float(label_prob), float(mistake_prob),
+                                              int(bool(exhaustive)), _capi.i64ptr(idx), _capi.dptr(scores)))
+        return idx[:got], scores[:got]
+
+    def stats(self):
+        out = np.zeros(8)
+        _capi.check(self.lib.ital_fetch_stats(self.handle, _capi.dptr(out)))
+        return out
+
+    def _vec(self, fn):
+        out = np.zeros(self.n_local)
+        _capi.check(fn(self.handle, _capi.dptr(out)))
+        return out
+
+    def last_scores(self):
+        return self._vec(self.lib.ital_last_scores)
+
+    def rel_mean(self):
+        return self._vec(self.lib.ital_rel_mean)
+
+    def rel_var(self):
+        return self._vec(self.lib.ital_rel_var)
+
+    def predict(self, X, want_var):
+        X = _capi.as_f64(X)
+        mean = np.zeros(len(X))
+        var = np.zeros(len(X)) if want_var else None
+        _capi.check(self.lib.ital_predict(self.handle, _capi.dptr(X), len(X), _capi.dptr(mean),
+                                          _capi.dptr(var) if want_var else None))
+        return mean, var
+
+
+class _GPView(object):
+    """What the reference's callers read from `learner.gp` (run_experiment.py:153,166; viz_utils.py:153,177)."""
+
+    def __init__(self, learner):
+        self._l = learner
+
+    @property
+    def ind(self):
+        return list(self._l._labelled_idx)
+
+    @property
+    def y(self):
+        return np.array(self._l._labelled_y, dtype=np.float64)
+
+    @property
+    def noise(self):
+        return self._l.noise
+
+    @property
+    def var(self):
+        return self._l.var
+
+    @property
+    def length_scale(self):
+        return self._l.length_scale
+
+    def predict(self, X, cov_mode=None):
+        """GaussianProcess.predict (ital/gp.py:264-292); cov_mode None or 'diag'."""
+        X = np.asarray(X, dtype=np.float64)
+        if X.ndim == 1:
+            X = X[None, :]
+        if cov_mode == 'full':
+            raise NotImplementedError("cov_mode='full' is not on the accelerated path")
+        mean, var = self._l._shard.predict(X, cov_mode == 'diag')
+        return (mean, var) if cov_mode == 'diag' else mean
+
+    def predict_stored(self, ind=None, cov_mode=None):
+        """GaussianProcess.predict_stored (ital/gp.py:203-232) for the pool rows; cov_mode None or 'diag'."""
+        if cov_mode == 'full':
+            raise NotImplementedError("cov_mode='full' is not on the accelerated path")
+        mean = self._l._all_rows(self._l._shard.rel_mean())
+        sel = slice(None) if ind is None else np.asarray(ind, dtype=np.int64)
+        if cov_mode == 'diag':
+            return mean[sel], np.maximum(0, self._l._all_rows(self._l._shard.rel_var()))[sel]
+        return mean[sel]
+
+    def __getattr__(self, name):
+        if name in ('K_all', 'K_inv', 'K', 'w'):
+            raise AttributeError("gp.%s does not exist here: the n-by-n kernel matrix of ital/gp.py:128 is never "
+                                 "formed and the model is kept as a Cholesky factor" % name)
+        raise AttributeError(name)
+
+
+class ITAL(object):
+    """Information-theoretic Active Learning; drop-in for `ital.ITAL` (ital/ital.py:12-134).
+
+    Extra keywords (all optional): `device` CUDA ordinal; `storage` 'auto' | 'float32' | 'float64' for the copy
+    of the data kept in HBM ('auto' picks float32 only if that is lossless); `process_group` a
+    torch.distributed group (or True for the default group) to shard the rows over one GPU per process;
+    `exhaustive` scores every candidate each step instead of pruning with the lazy-greedy bound.
+    """
+
+    def __init__(self, data=None, queries=[], length_scale=0.1, var=1.0, noise=1e-6,
+                 label_prob=1.0, mistake_prob=0.0, top_candidates=None, change_estimation_subset=0,
+                 clip_cov=0, label_estimation='mean', monte_carlo_num_rel=None, monte_carlo_num_fb=None,
+                 parallelized=True, device=None, storage='auto', process_group=None, exhaustive=False):
+        self.length_scale, self.var, self.noise = length_scale, var, noise
+        self.label_prob, self.mistake_prob = label_prob, mistake_prob
+        self.top_candidates = top_candidates
+        self.change_estimation_subset = change_estimation_subset
+        self.clip_cov = clip_cov
+        self.label_estimation = label_estimation
+        self.monte_carlo_num_rel, self.monte_carlo_num_fb = monte_carlo_num_rel, monte_carlo_num_fb
+        self.parallelized = parallelized            # accepted for compatibility; the GPU is the parallelism
+        self.exhaustive = exhaustive
+        self._storage = storage
+        self._device = device
+        self._comm = LocalComm() if process_group is None else \
+            TorchComm(None if process_group is True else process_group, device)
+        self._shard = None
+        self.last_fetch_stats = []
+        self.fit(data, queries)
+
+    # ---- ActiveRetrievalBase ---------------------------------------------------------------------------
+    def fit(self, data, queries=[]):                                            # retrieval_base.py:34-45
+        self.data = data
+        self.queries = queries
+        if self._shard is not None:
+            self._shard.close()
+            self._shard = None
+        if self.data is None:
+            self.gp = None
+            return
+        X = np.asarray(self.data, dtype=np.float64)
+        if len(self.queries) > 0:
+            X = np.concatenate((X, np.asarray(self.queries, dtype=np.float64).reshape(len(self.queries), -1)))
+        self._n = len(self.data)
+        storage = self._storage
+        if storage == 'auto':
+            storage = 'float32' if np.array_equal(X.astype(np.float32).astype(np.float64), X) else 'float64'
+        if storage not in ('float32', 'float64'):
+            raise ValueError("storage must be 'auto', 'float32' or 'float64'")
+        self.storage = storage
+        self._offsets = partition_rows(len(X), self._comm.world_size)
+        lo, hi = int(self._offsets[self._comm.rank]), int(self._offsets[self._comm.rank + 1])
+        if hi <= lo:
+            raise ValueError('more processes than rows')
+        Xl = np.ascontiguousarray(X[lo:hi], dtype=np.float32 if storage == 'float32' else np.float64)
+        device = self._device
+        if device is None:
+            device = getattr(self._comm, 'device', None)
+            device = device.index if device is not None and getattr(device, 'type', 'cpu') == 'cuda' else 0
+        self._shard = _Shard(Xl, _capi.ITAL_F32 if storage == 'float32' else _capi.ITAL_F64, lo, self._n,
+                             self.length_scale, self.var, self.noise, device)
+        self.gp = _GPView(self)
+        self.reset()
+
+    def reset(self):                                                            # retrieval_base.py:48-61
+        self.rounds = 0
+        self.relevant_ids, self.irrelevant_ids, self.unnameable_ids = set(), set(), set()
+        self._labelled_idx, self._labelled_y = [], []
+        self._rel_mean = None
+        self._shard.reset()
+        if len(self.queries) > 0:
+            self._add_labelled(list(range(self._n, self._n + len(self.queries))), [1.0] * len(self.queries))
+
+    @property
+    def rel_mean(self):
+        """gp.predict_stored()[:n] (retrieval_base.py:58,120); None before the first label."""
+        if len(self._labelled_idx) == 0:
+            return None
+        if self._rel_mean is None:
+            self._rel_mean = self._all_rows(self._shard.rel_mean())[:self._n]
+        return self._rel_mean
+
+    def _all_rows(self, local):
+        return self._comm.gather_rows(local, self._offsets)
+
+    def top_results(self, k=None):                                              # retrieval_base.py:64-75
+        ind = np.argsort(self.rel_mean)[::-1]
+        return ind[:k] if k is not None else ind
+
+    def _seen_mask(self):
+        seen = np.zeros(self._n, dtype=bool)
+        for ids in (self.relevant_ids, self.irrelevant_ids, self.unnameable_ids):
+            if ids:
+                seen[np.fromiter(ids, dtype=np.int64, count=len(ids))] = True
+        return seen
+
+    def get_unseen(self):                                                       # retrieval_base.py:78-87
+        return np.nonzero(~self._seen_mask())[0].tolist()
+
+    def partition_feedback(self, feedback):                                     # retrieval_base.py:167-194
+        rel, irr, unnameable = [], [], []
+        for i, fb in feedback.items():
+            if fb > 0:
+                if i in self.irrelevant_ids:
+                    raise RuntimeError('Cannot change feedback once given.')
+                elif i not in self.relevant_ids:
+                    rel.append(i)
+            elif fb < 0:
+                if i in self.relevant_ids:
+                    raise RuntimeError('Cannot change feedback once given.')
+                elif i not in self.irrelevant_ids:
+                    irr.append(i)
+            else:
+                unnameable.append(i)
+        return rel, irr, unnameable
+
+    def _add_labelled(self, idx, y):
+        for i, yi in zip(idx, y):       # one rank-1 extension and one pass over the pool per labelled point
+            rec = self._comm.sum_records(self._shard.export_points([int(i)]))[0]
+            self._shard.add_labelled(rec, yi)
+            self._labelled_idx.append(int(i))
+            self._labelled_y.append(float(yi))
+        self._rel_mean = None
+
+    def update(self, feedback):                                                 # retrieval_base.py:105-126
+        rel, irr, unnameable = self.partition_feedback(feedback)
+        if len(rel) + len(irr) > 0:
+            self._add_labelled(rel + irr, [1.0] * len(rel) + [-1.0] * len(irr))
+            self.relevant_ids.update(rel)
+            self.irrelevant_ids.update(irr)
+            self.rounds += 1
+        if len(unnameable):
+            self._shard.mark_seen([int(i) for i in unnameable])
+        self.unnameable_ids.update(unnameable)
+
+    def updated_prediction(self, feedback, test_ind, cov_mode='full'):          # retrieval_base.py:129-164
+        raise NotImplementedError('updated_prediction is folded into the GPU scoring kernels; the standalone '
+                                  'method is not part of the accelerated path')
+
+    # ---- ITAL ------------------------------------------------------------------------------------------
+    def _check_supported(self):
+        if not (self.label_prob >= 1 and self.mistake_prob <= 0):
+            raise NotImplementedError('GPU path implements the perfect-user model of the named configurations '
+                                      '(label_prob >= 1, mistake_prob <= 0); general feedback models are not '
+                                      'available yet and there is deliberately no CPU fallback')
+        if self.label_estimation != 'mean':
+            raise NotImplementedError("label_estimation must be 'mean' on the GPU path")
+        if self.change_estimation_subset != 0 or (self.clip_cov and 0 < self.clip_cov < 1) \
+                or self.monte_carlo_num_rel is not None or self.monte_carlo_num_fb is not None:
+            raise NotImplementedError('change_estimation_subset, clip_cov and the Monte-Carlo modes are outside the '
+                                      'accelerated path (no named configuration uses them)')
+
+    def fetch_unlabelled(self, k, show_progress=False):                         # ital.py:84-134
+        """Greedy batch of k unlabelled samples maximising mutual information; list of row indices."""
+        self._check_supported()
+        if len(self._labelled_idx) == 0:
+            raise RuntimeError('fetch_unlabelled() needs at least one query or labelled sample '
+                               '(the reference fails here with gp.K_inv = None)')
+        n_unseen = self._n - len(self.relevant_ids | self.irrelevant_ids | self.unnameable_ids)
+        k = min(int(k), n_unseen)                                               # ital.py:99-100
+        restricted = False
+        if self.top_candidates is not None:                                     # ital.py:111-117
+            top = self.top_candidates
+            if isinstance(top, float):
+                top = min(n_unseen, int(top * (len(self.queries) + len(self.relevant_ids) + len(self.irrelevant_ids))))
+            if 0 < top < n_unseen:
+                cand = np.nonzero(~self._seen_mask())[0]
+                top_ind = np.argpartition(self.rel_mean[cand], -top)[-top:]
+                self._shard.restrict_candidates(cand[top_ind])
+                restricted = True
+        self.last_fetch_stats = []
+        try:
+            if self._comm.world_size == 1 and not show_progress:
+                idx, scores = self._shard.fetch(k, self.label_prob, self.mistake_prob, self.exhaustive)
+                self.last_fetch_scores = scores
+                return [int(i) for i in idx]
+            return self._fetch_stepwise(k, show_progress)
+        finally:
+            if restricted:
+                self._shard.restrict_candidates(None)
+
+    def _fetch_stepwise(self, k, show_progress=False, keep_scores=False):
+        """The greedy loop with the per-step exchange made explicit (multi-GPU, progress bars, tests)."""
+        steps = range(k)
+        if show_progress:
+            from tqdm import trange
+            steps = trange(k)
+        ret, self.last_fetch_scores, self.last_step_scores = [], [], []
+        self._shard.fetch_begin(self.label_prob, self.mistake_prob)
+        try:
+            for it in steps:
+                rec = self._shard.fetch_propose(-np.inf, self.exhaustive)
+                self.last_fetch_stats.append(self._shard.stats())
+                if keep_scores:
+                    self.last_step_scores.append(self._all_rows(self._shard.last_scores())[:self._n])
+                allrec = self._comm.gather_records(rec)
+                win = pick_winner(allrec)
+                if win < 0:
+                    break
+                ret.append(int(allrec[win][0]))
+                self.last_fetch_scores.append(float(allrec[win][1]))
+                if it + 1 < k:
+                    self._shard.fetch_commit(allrec[win])
+        finally:
+            self._shard.fetch_end()
+        return ret
