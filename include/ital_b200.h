@@ -111,6 +111,14 @@ int ital_rel_var(ital_shard* s, double* out_n_local);
  * valid on any shard (the labelled points are replicated). */
 int ital_predict(ital_shard* s, const double* Xt, int64_t m, double* out_mean, double* out_var);
 
+/* Measurement hooks (bench.py): with profiling on, every launch of the streaming kernel (k_extend) is bracketed
+ * by CUDA events on the shard's stream.  ital_profile_read synchronises, returns the accumulated kernel time in
+ * milliseconds, the number of launches and the algorithmic bytes they moved, and clears the accumulators.
+ * ital_launch_count: kernels launched by this shard since creation (all kernels, profiling on or off). */
+int ital_profile_enable(ital_shard* s, int on);
+int ital_profile_read(ital_shard* s, double* ms_total, int64_t* launches, double* algorithmic_bytes);
+int64_t ital_launch_count(const ital_shard* s);
+
 /* Host-side pieces exposed for CPU-only tests (no GPU needed) ------------------------------------------- */
 /* Shared quadrature nodes of one greedy step (see oracle/orthant.py for the rule): base mean m[t], lower
  * Cholesky factor L[t*t] (row-major).  Returns the node count N = (2q)^t; if eta != NULL fills eta[t*N]

@@ -43,6 +43,9 @@ SIGNATURES = {
     'ital_rel_mean': (ctypes.c_int, [_shard_p, _c_double_p]),
     'ital_rel_var': (ctypes.c_int, [_shard_p, _c_double_p]),
     'ital_predict': (ctypes.c_int, [_shard_p, _c_double_p, ctypes.c_int64, _c_double_p, _c_double_p]),
+    'ital_profile_enable': (ctypes.c_int, [_shard_p, ctypes.c_int]),
+    'ital_profile_read': (ctypes.c_int, [_shard_p, _c_double_p, _c_int64_p, _c_double_p]),
+    'ital_launch_count': (ctypes.c_int64, [_shard_p]),
     'ital_snq_nodes': (ctypes.c_int64, [ctypes.c_int, _c_double_p, _c_double_p, _c_double_p, _c_double_p,
                                         _c_int32_p, _c_double_p]),
     'ital_snq_order': (ctypes.c_int, [ctypes.c_int]),

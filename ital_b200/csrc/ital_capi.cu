@@ -98,6 +98,11 @@ struct ital_shard {
     bool lab_dev_valid = false;
 
     double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // measurement
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    double prof_bytes = 0.0;
+    int64_t launches = 0;
     double log1p_eps = std::log(1.0 + 1e-12);
 };
 
@@ -168,6 +173,12 @@ int launch_extend_t(ital_shard* s, int W_used, int labelled) {
     int blocks = (int)std::min<int64_t>((units + warps - 1) / warps, (int64_t)s->num_sms * 2);
     if (blocks < 1) blocks = 1;
     const double neg2ls2 = -2.0 * (s->ls * s->ls);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (s->profiling) {
+        CU(cudaEventCreate(&ev0));
+        CU(cudaEventCreate(&ev1));
+        CU(cudaEventRecord(ev0, s->stream));
+    }
 #define ITAL_LAUNCH_EXT(NCV)                                                                                   \
     do {                                                                                                       \
         CU(cudaFuncSetAttribute(k_extend<XT, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
@@ -180,7 +191,15 @@ int launch_extend_t(ital_shard* s, int W_used, int labelled) {
     else if (nchunks == 1) ITAL_LAUNCH_EXT(1);
     else ITAL_LAUNCH_EXT(0);
 #undef ITAL_LAUNCH_EXT
+    s->launches++;
     CU(cudaGetLastError());
+    if (s->profiling) {
+        CU(cudaEventRecord(ev1, s->stream));
+        s->prof_events.emplace_back(ev0, ev1);
+        // algorithmic bytes of one pass: the row, |x|^2, W projections in, one out; m and v
+        // read-modify-write when a labelled point is added
+        s->prof_bytes += (double)s->n * ((double)s->d * sizeof(XT) + 8.0 + 8.0 * W_used + 8.0 + (labelled ? 32.0 : 0.0));
+    }
     return ITAL_OK;
 }
 
@@ -216,7 +235,7 @@ int make_record(ital_shard* s, long long local_row, double* dst_dev) {
     else
         k_record<double><<<1, 256, 0, s->stream>>>(local_row, s->best, s->row_offset, (const double*)s->X,
                                                    (int)s->d, (int)s->d_pad, s->sqn, s->m, s->v, s->U, s->ldu,
-                                                   s->W, s->W + s->t, s->w_cap, s->gain, dst_dev);
+                                                   s->W, s->W + s->t, s->w_cap, s->gain, dst_dev); s->launches++;
     CU(cudaGetLastError());
     return ITAL_OK;
 }
@@ -256,6 +275,7 @@ int launch_eval(ital_shard* s, int max_items_hint) {
     else if (t == 3) k_eval<3><<<blocks, threads, 0, s->stream>>>(ITAL_EVAL_ARGS);
     else k_eval<0><<<blocks, threads, 0, s->stream>>>(ITAL_EVAL_ARGS);
 #undef ITAL_EVAL_ARGS
+    s->launches++;
     CU(cudaGetLastError());
     return ITAL_OK;
 }
@@ -286,8 +306,8 @@ int reset_model(ital_shard* s) {
     s->restricted.clear();
     s->lab_dev_valid = false;
     const int blocks = grid_for(s, s->n, 256);
-    k_fill<<<blocks, 256, 0, s->stream>>>(s->m, s->n, 0.0);
-    k_fill<<<blocks, 256, 0, s->stream>>>(s->v, s->n, s->var);
+    k_fill<<<blocks, 256, 0, s->stream>>>(s->m, s->n, 0.0); s->launches++;
+    k_fill<<<blocks, 256, 0, s->stream>>>(s->v, s->n, s->var); s->launches++;
     CU(cudaGetLastError());
     // candidates are the pool rows only (queries sit behind them, retrieval_base.py:40,84)
     std::vector<uint8_t> mk((size_t)s->n, 0);
@@ -362,7 +382,7 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
         if (x_dtype == ITAL_F32)
             k_sqnorm<float><<<blocks, 256, 0, s->stream>>>((const float*)s->X, s->n, (int)s->d_pad, s->sqn);
         else
-            k_sqnorm<double><<<blocks, 256, 0, s->stream>>>((const double*)s->X, s->n, (int)s->d_pad, s->sqn);
+            k_sqnorm<double><<<blocks, 256, 0, s->stream>>>((const double*)s->X, s->n, (int)s->d_pad, s->sqn); s->launches++;
         CU(cudaGetLastError());
         return reset_model(s);
     };
@@ -478,7 +498,7 @@ int ital_mark_seen(ital_shard* s, int64_t m, const int64_t* global_idx) {
     int rc = ensure_idx(s, (int64_t)loc.size());
     if (rc) return rc;
     CU(cudaMemcpyAsync(s->idx_dev, loc.data(), loc.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream));
-    k_mask_rows<<<grid_for(s, (int64_t)loc.size(), 256), 256, 0, s->stream>>>(s->mask, s->idx_dev, (int64_t)loc.size(), kSeen);
+    k_mask_rows<<<grid_for(s, (int64_t)loc.size(), 256), 256, 0, s->stream>>>(s->mask, s->idx_dev, (int64_t)loc.size(), kSeen); s->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s->stream));
     return ITAL_OK;
@@ -489,12 +509,12 @@ int ital_restrict_candidates(ital_shard* s, int64_t m, const int64_t* global_idx
     CU(cudaSetDevice(s->device));
     const int blocks = grid_for(s, s->n, 256);
     if (m < 0) {
-        k_mask_all<<<blocks, 256, 0, s->stream>>>(s->mask, s->n, (uint8_t)~kRestricted, 0);
+        k_mask_all<<<blocks, 256, 0, s->stream>>>(s->mask, s->n, (uint8_t)~kRestricted, 0); s->launches++;
         CU(cudaGetLastError());
         return ITAL_OK;
     }
     // everything restricted, then the listed rows released
-    k_mask_all<<<blocks, 256, 0, s->stream>>>(s->mask, s->n, 0xff, kRestricted);
+    k_mask_all<<<blocks, 256, 0, s->stream>>>(s->mask, s->n, 0xff, kRestricted); s->launches++;
     CU(cudaGetLastError());
     std::vector<int64_t> loc;
     for (int64_t k = 0; k < m; ++k) {
@@ -506,7 +526,7 @@ int ital_restrict_candidates(ital_shard* s, int64_t m, const int64_t* global_idx
         if (rc) return rc;
         CU(cudaMemcpyAsync(s->idx_dev, loc.data(), loc.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream));
         k_mask_clear_rows<<<grid_for(s, (int64_t)loc.size(), 256), 256, 0, s->stream>>>(s->mask, s->idx_dev,
-                                                                                       (int64_t)loc.size(), kRestricted);
+                                                                                       (int64_t)loc.size(), kRestricted); s->launches++;
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(s->stream));
     }
@@ -543,8 +563,8 @@ int ital_fetch_propose(ital_shard* s, double floor_score, int exhaustive, double
     CU(cudaMemsetAsync(s->counters, 0, 4 * sizeof(int), s->stream));
     for (double& x : s->stats) x = 0.0;
     if (s->t == 0) {
-        k_score0<<<blocks, 256, 0, s->stream>>>(s->n, s->m, s->v, s->mask, s->score, s->gain, s->block_best, s->log1p_eps);
-        k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, blocks, s->best);
+        k_score0<<<blocks, 256, 0, s->stream>>>(s->n, s->m, s->v, s->mask, s->score, s->gain, s->block_best, s->log1p_eps); s->launches++;
+        k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, blocks, s->best); s->launches++;
         CU(cudaGetLastError());
         s->h_base = 0.0;
         s->n_nodes = 1;
@@ -557,28 +577,28 @@ int ital_fetch_propose(ital_shard* s, double floor_score, int exhaustive, double
         snq::Nodes nd = snq::generate(s->t, s->base_m.data(), Lb.data());
         rc = upload_nodes(s, nd);
         if (rc) return rc;
-        k_fill<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->score, s->n, std::numeric_limits<double>::quiet_NaN());
+        k_fill<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->score, s->n, std::numeric_limits<double>::quiet_NaN()); s->launches++;
         if (!exhaustive) {
             // most promising candidate first: its exact score is the pruning threshold
-            k_argmax_rows<<<blocks, 256, 0, s->stream>>>(s->n, s->gain, s->mask, s->block_best);
-            k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, blocks, s->best + 1);
-            k_list_from_best<<<1, 1, 0, s->stream>>>(s->best + 1, s->counters, s->worklist);
+            k_argmax_rows<<<blocks, 256, 0, s->stream>>>(s->n, s->gain, s->mask, s->block_best); s->launches++;
+            k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, blocks, s->best + 1); s->launches++;
+            k_list_from_best<<<1, 1, 0, s->stream>>>(s->best + 1, s->counters, s->worklist); s->launches++;
             CU(cudaGetLastError());
             rc = launch_eval(s, 1);
             if (rc) return rc;
-            k_argmax_list<<<1, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->block_best);
-            k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, 1, s->best + 1);
+            k_argmax_list<<<1, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->block_best); s->launches++;
+            k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, 1, s->best + 1); s->launches++;
             CU(cudaMemsetAsync(s->counters, 0, 2 * sizeof(int), s->stream));
         }
         k_worklist<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->n, s->mask, s->gain, s->h_base, s->best + 1,
                                                                     floor_score, kPruneMargin, exhaustive,
-                                                                    s->counters, s->worklist);
+                                                                    s->counters, s->worklist); s->launches++;
         CU(cudaGetLastError());
         rc = launch_eval(s, exhaustive ? (int)std::min<int64_t>(s->n, 1 << 30) : 1 << 16);
         if (rc) return rc;
         const int lb = std::min(kArgmaxBlocks, grid_for(s, exhaustive ? s->n : 1 << 16, 256));
-        k_argmax_list<<<lb, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->block_best);
-        k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, lb, s->best);
+        k_argmax_list<<<lb, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->block_best); s->launches++;
+        k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, lb, s->best); s->launches++;
         CU(cudaGetLastError());
     }
     rc = make_record(s, -1, s->rec_dev);
@@ -625,7 +645,7 @@ int ital_fetch_commit(ital_shard* s, const double* record) {
         rc = ensure_idx(s, 1);
         if (rc) return rc;
         CU(cudaMemcpyAsync(s->idx_dev, &loc, sizeof loc, cudaMemcpyHostToDevice, s->stream));
-        k_mask_rows<<<1, 32, 0, s->stream>>>(s->mask, s->idx_dev, 1, kSelected);
+        k_mask_rows<<<1, 32, 0, s->stream>>>(s->mask, s->idx_dev, 1, kSelected); s->launches++;
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(s->stream));
     }
@@ -642,7 +662,7 @@ int ital_fetch_end(ital_shard* s) {
     if (!s) return fail(ITAL_EINVAL, "null shard");
     CU(cudaSetDevice(s->device));
     if (s->fetching) {
-        k_mask_all<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->mask, s->n, (uint8_t)~kSelected, 0);
+        k_mask_all<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->mask, s->n, (uint8_t)~kSelected, 0); s->launches++;
         CU(cudaGetLastError());
     }
     s->fetching = false;
@@ -746,7 +766,7 @@ int ital_predict(ital_shard* s, const double* Xt, int64_t mrows, double* out_mea
     const size_t smem = (size_t)wpb * nl * sizeof(double);
     k_predict<<<(unsigned)((mrows + wpb - 1) / wpb), threads, smem, s->stream>>>(
         xt_dev, mrows, (int)s->d, s->lab_x_dev, s->lab_sqn_dev, nl, s->w_vec_dev, s->LK_dev, s->var,
-        -2.0 * s->ls * s->ls, mean_dev, var_dev);
+        -2.0 * s->ls * s->ls, mean_dev, var_dev); s->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out_mean, mean_dev, (size_t)mrows * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     if (out_var) CU(cudaMemcpyAsync(out_var, var_dev, (size_t)mrows * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
@@ -756,6 +776,34 @@ int ital_predict(ital_shard* s, const double* Xt, int64_t mrows, double* out_mea
     if (var_dev) CU(cudaFree(var_dev));
     return ITAL_OK;
 }
+
+int ital_profile_enable(ital_shard* s, int on) {
+    if (!s) return fail(ITAL_EINVAL, "null shard");
+    s->profiling = on != 0;
+    return ITAL_OK;
+}
+
+int ital_profile_read(ital_shard* s, double* ms_total, int64_t* launches, double* algorithmic_bytes) {
+    if (!s) return fail(ITAL_EINVAL, "null shard");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    double total = 0.0;
+    for (auto& pr : s->prof_events) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        total += ms;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    if (ms_total) *ms_total = total;
+    if (launches) *launches = (int64_t)s->prof_events.size();
+    if (algorithmic_bytes) *algorithmic_bytes = s->prof_bytes;
+    s->prof_events.clear();
+    s->prof_bytes = 0.0;
+    return ITAL_OK;
+}
+
+int64_t ital_launch_count(const ital_shard* s) { return s ? s->launches : 0; }
 
 int64_t ital_snq_nodes(int t, const double* m, const double* L, double* eta, double* w, int32_t* orth, double* masses) {
     if (t < 1 || t > 10 || !m || !L) return fail(ITAL_EINVAL, "ital_snq_nodes: bad arguments");

@@ -174,13 +174,16 @@ class ITAL(object):
     Extra keywords (all optional): `device` CUDA ordinal; `storage` 'auto' | 'float32' | 'float64' for the copy
     of the data kept in HBM ('auto' picks float32 only if that is lossless); `process_group` a
     torch.distributed group (or True for the default group) to shard the rows over one GPU per process;
-    `exhaustive` scores every candidate each step instead of pruning with the lazy-greedy bound.
+    `exhaustive` scores every candidate each step instead of pruning with the lazy-greedy bound;
+    `local_rows=(first_row, n_total)` declares that `data` holds only this process's contiguous block of a
+    pool of n_total rows (for pools too large to replicate on every host process; no `queries` then).
     """
 
     def __init__(self, data=None, queries=[], length_scale=0.1, var=1.0, noise=1e-6,
                  label_prob=1.0, mistake_prob=0.0, top_candidates=None, change_estimation_subset=0,
                  clip_cov=0, label_estimation='mean', monte_carlo_num_rel=None, monte_carlo_num_fb=None,
-                 parallelized=True, device=None, storage='auto', process_group=None, exhaustive=False):
+                 parallelized=True, device=None, storage='auto', process_group=None, exhaustive=False,
+                 local_rows=None):
         self.length_scale, self.var, self.noise = length_scale, var, noise
         self.label_prob, self.mistake_prob = label_prob, mistake_prob
         self.top_candidates = top_candidates
@@ -192,6 +195,7 @@ class ITAL(object):
         self.exhaustive = exhaustive
         self._storage = storage
         self._device = device
+        self._local_rows = local_rows
         self._comm = LocalComm() if process_group is None else \
             TorchComm(None if process_group is True else process_group, device)
         self._shard = None
@@ -208,21 +212,34 @@ class ITAL(object):
         if self.data is None:
             self.gp = None
             return
-        X = np.asarray(self.data, dtype=np.float64)
+        X = np.asarray(self.data)
+        if X.dtype not in (np.float32, np.float64):
+            X = X.astype(np.float64)
         if len(self.queries) > 0:
             X = np.concatenate((X, np.asarray(self.queries, dtype=np.float64).reshape(len(self.queries), -1)))
-        self._n = len(self.data)
+        self._n = len(self.data) if self._local_rows is None else int(self._local_rows[1])
+        if self._local_rows is not None and len(self.queries) > 0:
+            raise ValueError('local_rows and queries cannot be combined')
         storage = self._storage
         if storage == 'auto':
-            storage = 'float32' if np.array_equal(X.astype(np.float32).astype(np.float64), X) else 'float64'
+            storage = 'float32' if X.dtype == np.float32 or np.array_equal(X.astype(np.float32), X) else 'float64'
         if storage not in ('float32', 'float64'):
             raise ValueError("storage must be 'auto', 'float32' or 'float64'")
         self.storage = storage
-        self._offsets = partition_rows(len(X), self._comm.world_size)
-        lo, hi = int(self._offsets[self._comm.rank]), int(self._offsets[self._comm.rank + 1])
-        if hi <= lo:
-            raise ValueError('more processes than rows')
-        Xl = np.ascontiguousarray(X[lo:hi], dtype=np.float32 if storage == 'float32' else np.float64)
+        if self._local_rows is None:
+            self._offsets = partition_rows(len(X), self._comm.world_size)
+            lo, hi = int(self._offsets[self._comm.rank]), int(self._offsets[self._comm.rank + 1])
+            if hi <= lo:
+                raise ValueError('more processes than rows')
+            Xl = X[lo:hi]
+        else:
+            lo = int(self._local_rows[0])
+            firsts = self._comm.gather_records(np.array([float(lo)]))[:, 0].astype(np.int64)
+            self._offsets = np.concatenate((firsts, [self._n])).astype(np.int64)
+            if np.any(np.diff(self._offsets) <= 0) or self._offsets[self._comm.rank + 1] - lo != len(X):
+                raise ValueError('local_rows blocks must be contiguous, ordered by rank and cover the pool')
+            Xl = X
+        Xl = np.ascontiguousarray(Xl, dtype=np.float32 if storage == 'float32' else np.float64)
         device = self._device
         if device is None:
             device = getattr(self._comm, 'device', None)

@@ -141,7 +141,7 @@ def entropy_terms(p, p_upd=1.0, eps=EPS):
     return p * (np.log(p_upd + eps) - np.log(p + eps))
 
 
-def mi_perfect_user(m_base, cov_base, m_c, var_c, cov_base_c, q=None):
+def mi_perfect_user(m_base, cov_base, m_c, var_c, cov_base_c, q=None, pool=None):
     """MI of ``ret + [i]`` for every candidate i under the perfect-user model, vectorised.
 
     With label_prob >= 1 and mistake_prob <= 0 there is one feedback configuration per relevance
@@ -164,7 +164,7 @@ def mi_perfect_user(m_base, cov_base, m_c, var_c, cov_base_c, q=None):
     l = scipy.linalg.solve_triangular(L, cov_base_c, lower=True).T        # (N, t)
     s2 = var_c - np.sum(l * l, axis=1)
     s = np.sqrt(np.maximum(s2, 0.0))
-    p_plus, p_base = snq_joint(m_base, L, m_c, l, s, q)
+    p_plus, p_base = snq_joint(m_base, L, m_c, l, s, q, pool=pool)
     p_minus = np.maximum(p_base[None, :] - p_plus, 0.0)
     scores = entropy_terms(p_plus).sum(axis=1) + entropy_terms(p_minus).sum(axis=1)
     return scores, p_plus, p_base, s
@@ -249,9 +249,10 @@ class OracleITAL(object):
     def _perfect_user(self):
         return (self.label_prob >= 1) and (self.mistake_prob <= 0)            # ital.py:313
 
-    def fetch_unlabelled(self, k, show_progress=False, forced=None):            # ital.py:84-134
+    def fetch_unlabelled(self, k, show_progress=False, forced=None, pool=None):   # ital.py:84-134
         """``forced`` (test hook): follow these choices instead of the argmax so that a recorded greedy path
-        can be re-scored step by step even where the maximum is an exact tie."""
+        can be re-scored step by step even where the maximum is an exact tie.  ``pool``: multiprocessing pool over
+        which the candidates of every step are spread (the reference's ``parallelized=True``, ital.py:124-126)."""
         candidates = self.get_unseen()
         if len(candidates) < k:
             k = len(candidates)
@@ -276,7 +277,7 @@ class OracleITAL(object):
             m_base = self.rel_mean[ret] if len(ret) else np.zeros(0)
             if self._perfect_user() and self.label_estimation == 'mean' and not self.force_general:
                 scores, p_plus, p_base, s = mi_perfect_user(
-                    m_base, cov_base, self.rel_mean[cand], var_test[cand], cov_base_test[:, cand])
+                    m_base, cov_base, self.rel_mean[cand], var_test[cand], cov_base_test[:, cand], pool=pool)
                 extra = dict(p_plus=p_plus, p_base=p_base, s=s)
             else:
                 scores = np.array([self._mi_general(ret + [int(i)], m_base, cov_base, self.rel_mean[i],

@@ -17,8 +17,9 @@ analytically,
 
 and the expectation over ``eta`` is a nested Gauss-Legendre rule applied *directly in eta*: dimension j is
 split at the orthant boundary ``a_j(eta_<j) = -(m_j + sum_{i<j} L_ji eta_i) / L_jj`` into the two panels
-``[-R, c]`` and ``[c, R]`` with ``c = clip(a_j, -R, R)``, each carrying Q Gauss-Legendre nodes whose weights
-are multiplied by the standard normal density.  The node set depends only on the base variables, so one set
+``[-R, c]`` and ``[c, R]`` with ``c = clip(a_j, -R, R)``; the 2Q Gauss-Legendre nodes of the dimension are
+shared out between the panels in proportion to their widths (``snq_split``; at least ``SNQ_QMIN`` each) and the
+weights are multiplied by the standard normal density.  The node set depends only on the base variables, so one set
 serves every candidate of a greedy step.  ``R = SNQ_R`` and ``Q = snq_order(t)``.
 
 Nothing here is imported by the product path (ital_b200/); only tests/, bench.py's cpu_baseline /
@@ -116,10 +117,18 @@ def base_masses(w, orth, t):
     return np.bincount(orth, weights=w, minlength=1 << t)
 
 
-def snq_joint(m_base, L_base, m_c, l_c, s_c, q=None, R=SNQ_R, chunk=None):
+def _joint_rows(args):
+    """Worker of snq_joint: candidates [lo, hi) against the (sorted) shared nodes."""
+    m_c, l_c, s_c, eta, w, bounds, chunk = args
+    return _joint_block(m_c, l_c, s_c, eta, w, bounds, chunk)
+
+
+def snq_joint(m_base, L_base, m_c, l_c, s_c, q=None, R=SNQ_R, chunk=None, pool=None, pool_tasks=64):
     """P(r_base, candidate > 0) and P(r_base) for many candidates sharing one base.
 
     m_c (n,), l_c (n, t), s_c (n,)  ->  p_plus (n, 2^t), p_base (2^t,).  ``s_c <= 0`` turns Phi into a step.
+    ``pool``: a multiprocessing pool to spread the candidates over host cores -- the counterpart of the
+    reference's ``parallelized=True`` ``Pool.map`` over candidates (ital/ital.py:124-126).
     """
     m_c = np.atleast_1d(np.asarray(m_c, dtype=np.float64))
     l_c = np.asarray(l_c, dtype=np.float64).reshape(len(m_c), -1)
@@ -129,12 +138,22 @@ def snq_joint(m_base, L_base, m_c, l_c, s_c, q=None, R=SNQ_R, chunk=None):
     nb = 1 << t
     p_base = base_masses(w, orth, t)
     n = len(m_c)
-    p_plus = np.empty((n, nb))
     if chunk is None:
         chunk = max(1, int(4e6 // max(1, len(w))))
     order = np.argsort(orth, kind='stable')
     eta, w, orth = eta[order], w[order], orth[order]
     bounds = np.searchsorted(orth, np.arange(nb + 1))
+    if pool is not None and n > 1:
+        cuts = np.linspace(0, n, min(pool_tasks, n) + 1).astype(np.int64)
+        parts = pool.map(_joint_rows, [(m_c[a:b], l_c[a:b], s_c[a:b], eta, w, bounds, chunk)
+                                       for a, b in zip(cuts[:-1], cuts[1:]) if b > a])
+        return np.concatenate(parts, axis=0), p_base
+    return _joint_block(m_c, l_c, s_c, eta, w, bounds, chunk), p_base
+
+
+def _joint_block(m_c, l_c, s_c, eta, w, bounds, chunk):
+    n, nb = len(m_c), len(bounds) - 1
+    p_plus = np.empty((n, nb))
     for lo in range(0, n, chunk):
         hi = min(n, lo + chunk)
         num = m_c[lo:hi, None] + l_c[lo:hi] @ eta.T
@@ -146,7 +165,7 @@ def snq_joint(m_base, L_base, m_c, l_c, s_c, q=None, R=SNQ_R, chunk=None):
         cdf = ndtr(arg) * w[None, :]
         for b in range(nb):
             p_plus[lo:hi, b] = cdf[:, bounds[b]:bounds[b + 1]].sum(axis=1)
-    return p_plus, p_base
+    return p_plus
 
 
 def orthant_prob_all(mean, cov, q=None, R=SNQ_R):

@@ -75,7 +75,8 @@ def test_golden_parity(name):
         # lazy-greedy pruning must not change the batch
         gpu.exhaustive = False
         assert gpu.fetch_unlabelled(int(g['k'])) == ret
-        assert gpu._fetch_stepwise(int(g['k'])) == ret
+        if kw.get('top_candidates') is None:      # (the restriction is applied by fetch_unlabelled itself)
+            assert gpu._fetch_stepwise(int(g['k'])) == ret
 
 
 def _syn(n, d, seed=0, centres=50):
