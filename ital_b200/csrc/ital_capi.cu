@@ -57,15 +57,16 @@ struct ital_shard {
     double *sqn = nullptr, *m = nullptr, *v = nullptr, *U = nullptr, *gain = nullptr, *score = nullptr;
     uint8_t* mask = nullptr;
     int* worklist = nullptr;
-    int* counters = nullptr;         // [0] worklist size, [1] flagged
+    int* counters = nullptr;         // [0] worklist size, [1] flagged, [2] scored exactly
     Best* block_best = nullptr;      // kArgmaxBlocks
     Best* best = nullptr;            // [0] step winner, [1] most promising candidate
-    ExtendParams* ext = nullptr;
-    void* z_dev = nullptr;           // d_pad elements of the storage type
-    double* ur_dev = nullptr;        // w_cap
-    double* rec_dev = nullptr;       // record staging
-    double* rec_host = nullptr;      // pinned
+    double* rec_dev = nullptr;       // records produced on the device (propose / export)
+    double* rec_host = nullptr;      // pinned mirror of rec_dev
+    double* rec_in_dev = nullptr;    // the record k_extend reads (one record)
+    double* rec_in_host = nullptr;   // pinned staging of rec_in_dev
     int64_t rec_cap = 0;
+    char* nodes_host = nullptr;      // pinned staging of the quadrature nodes
+    size_t nodes_host_cap = 0;
     int64_t* idx_dev = nullptr;      // scratch for index lists
     int64_t idx_cap = 0;
     // quadrature nodes of the current step
@@ -121,12 +122,16 @@ int grid_for(const ital_shard* s, int64_t work_items, int per_block, int max_wav
 int ensure_record_buffers(ital_shard* s, int q) {
     const int64_t need = record_doubles(s) * q;
     if (need <= s->rec_cap) return ITAL_OK;
+    CU(cudaStreamSynchronize(s->stream));
     if (s->rec_dev) CU(cudaFree(s->rec_dev));
     if (s->rec_host) CU(cudaFreeHost(s->rec_host));
-    s->rec_dev = nullptr;
-    s->rec_host = nullptr;
+    if (s->rec_in_dev) CU(cudaFree(s->rec_in_dev));
+    if (s->rec_in_host) CU(cudaFreeHost(s->rec_in_host));
+    s->rec_dev = s->rec_host = s->rec_in_dev = s->rec_in_host = nullptr;
     CU(cudaMalloc(&s->rec_dev, need * sizeof(double)));
     CU(cudaMallocHost(&s->rec_host, need * sizeof(double)));
+    CU(cudaMalloc(&s->rec_in_dev, record_doubles(s) * sizeof(double)));
+    CU(cudaMallocHost(&s->rec_in_host, record_doubles(s) * sizeof(double)));
     s->rec_cap = need;
     return ITAL_OK;
 }
@@ -153,9 +158,6 @@ int ensure_width(ital_shard* s, int cols) {
         CU(cudaFree(s->U));
     }
     s->U = nu;
-    if (s->ur_dev) CU(cudaFree(s->ur_dev));
-    s->ur_dev = nullptr;
-    CU(cudaMalloc(&s->ur_dev, (size_t)new_cap * sizeof(double)));
     s->w_cap = new_cap;
     // records change size with the capacity
     s->rec_cap = 0;
@@ -163,7 +165,7 @@ int ensure_width(ital_shard* s, int cols) {
 }
 
 template <typename XT>
-int launch_extend_t(ital_shard* s, int W_used, int labelled) {
+int launch_extend_t(ital_shard* s, int W_used, int labelled, double y) {
     constexpr int VN = Vec<XT>::N;
     const int nchunks = (int)(s->d_pad / (32 * VN));
     const int threads = 256, warps = threads / 32;
@@ -183,8 +185,8 @@ int launch_extend_t(ital_shard* s, int W_used, int labelled) {
     do {                                                                                                       \
         CU(cudaFuncSetAttribute(k_extend<XT, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
         k_extend<XT, NCV><<<blocks, threads, smem, s->stream>>>(                                                \
-            (const XT*)s->X, s->n, (int)s->d_pad, (const XT*)s->z_dev, s->ext, s->ur_dev, W_used, s->sqn, s->U, \
-            s->ldu, s->m, s->v, labelled, s->var, neg2ls2);                                                     \
+            (const XT*)s->X, s->n, (int)s->d, (int)s->d_pad, s->rec_in_dev, s->w_cap, W_used, s->sqn, s->U,     \
+            s->ldu, s->m, s->v, labelled, y, s->noise, s->var, neg2ls2);                                        \
     } while (0)
     if (nchunks == 4) ITAL_LAUNCH_EXT(4);
     else if (nchunks == 2) ITAL_LAUNCH_EXT(2);
@@ -203,28 +205,21 @@ int launch_extend_t(ital_shard* s, int W_used, int labelled) {
     return ITAL_OK;
 }
 
-// One streaming pass: extend every local row's projection by the point described by `rec` (host record).
-// Writes column `col`; uses the first `col` entries of the record's projection.
-int extend_with_record(ital_shard* s, const double* rec, int col, double piv, double beta, int labelled) {
+// One streaming pass: extend every local row's projection by the point described by the host record `rec`
+// (current layout).  Writes column `col`, using the first `col` entries of the record's projection.  The record
+// goes through pinned staging, so nothing here waits for the device.
+int extend_with_record(ital_shard* s, const double* rec, int col, int labelled, double y, bool mark_selected) {
     int rc = ensure_width(s, col + 1);
     if (rc) return rc;
-    const double* ru = rec + ITAL_RECORD_HEADER;
-    const double* rx = rec + ITAL_RECORD_HEADER + s->w_cap;
-    // staging through the pinned record buffer keeps the copies asynchronous
-    ExtendParams prm{rec[4], piv, beta, 0.0};
-    CU(cudaMemcpyAsync(s->ext, &prm, sizeof prm, cudaMemcpyHostToDevice, s->stream));
-    if (col > 0) CU(cudaMemcpyAsync(s->ur_dev, ru, (size_t)col * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    std::vector<char> zbuf((size_t)s->d_pad * (s->x_dtype == ITAL_F32 ? 4 : 8), 0);
-    if (s->x_dtype == ITAL_F32) {
-        float* zf = (float*)zbuf.data();
-        for (int64_t j = 0; j < s->d; ++j) zf[j] = (float)rx[j];
-    } else {
-        memcpy(zbuf.data(), rx, (size_t)s->d * sizeof(double));
+    const int64_t rl = record_doubles(s);
+    memcpy(s->rec_in_host, rec, (size_t)rl * sizeof(double));
+    CU(cudaMemcpyAsync(s->rec_in_dev, s->rec_in_host, (size_t)rl * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    if (mark_selected) {
+        k_mask_record<<<1, 32, 0, s->stream>>>(s->mask, s->rec_in_dev, s->row_offset, s->n, kSelected); s->launches++;
+        CU(cudaGetLastError());
     }
-    CU(cudaMemcpyAsync(s->z_dev, zbuf.data(), zbuf.size(), cudaMemcpyHostToDevice, s->stream));
-    CU(cudaStreamSynchronize(s->stream));   // zbuf / prm are pageable host memory
-    if (s->x_dtype == ITAL_F32) return launch_extend_t<float>(s, col, labelled);
-    return launch_extend_t<double>(s, col, labelled);
+    if (s->x_dtype == ITAL_F32) return launch_extend_t<float>(s, col, labelled, y);
+    return launch_extend_t<double>(s, col, labelled, y);
 }
 
 int make_record(ital_shard* s, long long local_row, double* dst_dev) {
@@ -243,6 +238,7 @@ int make_record(ital_shard* s, long long local_row, double* dst_dev) {
 int upload_nodes(ital_shard* s, const snq::Nodes& nd) {
     const int nb = 1 << nd.t;
     if (nd.n > s->nodes_cap) {
+        CU(cudaStreamSynchronize(s->stream));
         if (s->eta_dev) CU(cudaFree(s->eta_dev));
         if (s->w_dev) CU(cudaFree(s->w_dev));
         s->eta_dev = s->w_dev = nullptr;
@@ -252,24 +248,44 @@ int upload_nodes(ital_shard* s, const snq::Nodes& nd) {
     }
     if (!s->masses_dev) CU(cudaMalloc(&s->masses_dev, 1024 * sizeof(double)));
     if (!s->group_dev) CU(cudaMalloc(&s->group_dev, 1025 * sizeof(int)));
-    CU(cudaMemcpyAsync(s->eta_dev, nd.eta.data(), nd.eta.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    CU(cudaMemcpyAsync(s->w_dev, nd.w.data(), nd.w.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    CU(cudaMemcpyAsync(s->masses_dev, nd.masses.data(), nb * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    CU(cudaMemcpyAsync(s->group_dev, nd.group_begin.data(), (nb + 1) * sizeof(int), cudaMemcpyHostToDevice, s->stream));
-    CU(cudaStreamSynchronize(s->stream));   // nd lives in pageable host memory
+    // pinned staging: the copies are asynchronous; the buffer is rewritten only after the next propose has
+    // synchronised on its result
+    const size_t b_eta = nd.eta.size() * sizeof(double), b_w = nd.w.size() * sizeof(double);
+    const size_t b_m = nb * sizeof(double), b_g = (nb + 1) * sizeof(int);
+    const size_t need = b_eta + b_w + b_m + b_g;
+    if (need > s->nodes_host_cap) {
+        CU(cudaStreamSynchronize(s->stream));
+        if (s->nodes_host) CU(cudaFreeHost(s->nodes_host));
+        s->nodes_host = nullptr;
+        CU(cudaMallocHost(&s->nodes_host, need));
+        s->nodes_host_cap = need;
+    }
+    char* p = s->nodes_host;
+    memcpy(p, nd.eta.data(), b_eta);
+    memcpy(p + b_eta, nd.w.data(), b_w);
+    memcpy(p + b_eta + b_w, nd.masses.data(), b_m);
+    memcpy(p + b_eta + b_w + b_m, nd.group_begin.data(), b_g);
+    CU(cudaMemcpyAsync(s->eta_dev, p, b_eta, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->w_dev, p + b_eta, b_w, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->masses_dev, p + b_eta + b_w, b_m, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->group_dev, p + b_eta + b_w + b_m, b_g, cudaMemcpyHostToDevice, s->stream));
     s->n_nodes = nd.n;
     s->h_base = nd.entropy;
     return ITAL_OK;
 }
 
-int launch_eval(ital_shard* s, int max_items_hint) {
+// Score the rows in the worklist.  `items_hint` bounds the number of items (the true count is on the device);
+// few items -> one 256-thread block per candidate (latency), many -> one warp per candidate (throughput).
+int launch_eval(ital_shard* s, int64_t items_hint, bool block_per_candidate) {
     const int t = s->t;
     const int threads = 256;
-    int blocks = grid_for(s, std::max(1, max_items_hint), threads / 32, 8);
+    int blocks = grid_for(s, std::max<int64_t>(1, items_hint), block_per_candidate ? 1 : threads / 32, 8);
     const double flag_var = 100.0 * s->noise;
+    const int force_block = block_per_candidate ? 1 : 0;
 #define ITAL_EVAL_ARGS                                                                                      \
     s->counters, s->worklist, t, s->m, s->v, s->U, s->ldu, s->W, s->eta_dev, s->w_dev, s->n_nodes, s->group_dev, \
-        s->masses_dev, s->h_base, s->log1p_eps, flag_var, s->score, s->gain, s->counters + 1
+        s->masses_dev, s->h_base, s->log1p_eps, flag_var, s->score, s->gain, s->counters + 1, s->counters + 2,  \
+        force_block
     if (t == 1) k_eval<1><<<blocks, threads, 0, s->stream>>>(ITAL_EVAL_ARGS);
     else if (t == 2) k_eval<2><<<blocks, threads, 0, s->stream>>>(ITAL_EVAL_ARGS);
     else if (t == 3) k_eval<3><<<blocks, threads, 0, s->stream>>>(ITAL_EVAL_ARGS);
@@ -283,11 +299,13 @@ int launch_eval(ital_shard* s, int max_items_hint) {
 void free_all(ital_shard* s) {
     cudaSetDevice(s->device);
     void* ptrs[] = {s->X, s->sqn, s->m, s->v, s->U, s->gain, s->score, s->mask, s->worklist, s->counters,
-                    s->block_best, s->best, s->ext, s->z_dev, s->ur_dev, s->rec_dev, s->idx_dev, s->eta_dev,
+                    s->block_best, s->best, s->rec_dev, s->rec_in_dev, s->idx_dev, s->eta_dev,
                     s->w_dev, s->masses_dev, s->group_dev, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->rec_host) cudaFreeHost(s->rec_host);
+    if (s->rec_in_host) cudaFreeHost(s->rec_in_host);
+    if (s->nodes_host) cudaFreeHost(s->nodes_host);
 }
 
 int reset_model(ital_shard* s) {
@@ -374,8 +392,6 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
         CU(cudaMalloc(&s->counters, 4 * sizeof(int)));
         CU(cudaMalloc(&s->block_best, kArgmaxBlocks * sizeof(Best)));
         CU(cudaMalloc(&s->best, 2 * sizeof(Best)));
-        CU(cudaMalloc(&s->ext, sizeof(ExtendParams)));
-        CU(cudaMalloc(&s->z_dev, (size_t)s->d_pad * esize));
         int r = ensure_width(s, 32);
         if (r) return r;
         const int blocks = grid_for(s, s->n, 8);
@@ -465,12 +481,11 @@ int ital_add_labelled(ital_shard* s, const double* record, double y) {
     std::copy(u.begin(), u.end(), rec.begin() + ITAL_RECORD_HEADER);
     std::copy(x.begin(), x.end(), rec.begin() + ITAL_RECORD_HEADER + s->w_cap);
     // rank-1 extension of the Cholesky factor of K_LL + noise I (replaces the full re-inversion of gp.py:194)
+    // (the kernel derives the same pivot and beta from the record header)
     const double v_r = hdr[5];
-    double piv2 = v_r + s->noise;
-    if (!(piv2 > 0)) piv2 = std::numeric_limits<double>::min();
-    const double piv = std::sqrt(piv2);
+    const double piv = std::sqrt(std::max(v_r + s->noise, 2.3e-308));
     const double beta = (y - hdr[2]) / piv;
-    rc = extend_with_record(s, rec.data(), s->W, piv, beta, 1);
+    rc = extend_with_record(s, rec.data(), s->W, 1, y, false);
     if (rc) return rc;
     std::vector<double> row(u);
     row.push_back(piv);
@@ -579,22 +594,24 @@ int ital_fetch_propose(ital_shard* s, double floor_score, int exhaustive, double
         if (rc) return rc;
         k_fill<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->score, s->n, std::numeric_limits<double>::quiet_NaN()); s->launches++;
         if (!exhaustive) {
-            // most promising candidate first: its exact score is the pruning threshold
-            k_argmax_rows<<<blocks, 256, 0, s->stream>>>(s->n, s->gain, s->mask, s->block_best); s->launches++;
-            k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, blocks, s->best + 1); s->launches++;
-            k_list_from_best<<<1, 1, 0, s->stream>>>(s->best + 1, s->counters, s->worklist); s->launches++;
+            // stage A: the most promising candidates (the per-block maxima of the bound) are scored first, one
+            // block each; the best exact score among them is the pruning threshold
+            const int ba = std::min(kArgmaxBlocks, std::min(blocks, 2 * s->num_sms));
+            k_argmax_rows<<<ba, 256, 0, s->stream>>>(s->n, s->gain, s->mask, s->block_best); s->launches++;
+            k_list_from_blocks<<<1, 32, 0, s->stream>>>(s->block_best, ba, s->counters, s->worklist); s->launches++;
             CU(cudaGetLastError());
-            rc = launch_eval(s, 1);
+            rc = launch_eval(s, ba, true);
             if (rc) return rc;
             k_argmax_list<<<1, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->block_best); s->launches++;
             k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, 1, s->best + 1); s->launches++;
-            CU(cudaMemsetAsync(s->counters, 0, 2 * sizeof(int), s->stream));
+            CU(cudaMemsetAsync(s->counters, 0, sizeof(int), s->stream));
         }
+        // stage B: every row whose bound still reaches the threshold (all rows when exhaustive)
         k_worklist<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->n, s->mask, s->gain, s->h_base, s->best + 1,
                                                                     floor_score, kPruneMargin, exhaustive,
                                                                     s->counters, s->worklist); s->launches++;
         CU(cudaGetLastError());
-        rc = launch_eval(s, exhaustive ? (int)std::min<int64_t>(s->n, 1 << 30) : 1 << 16);
+        rc = launch_eval(s, exhaustive ? s->n : (int64_t)s->num_sms * 16, false);
         if (rc) return rc;
         const int lb = std::min(kArgmaxBlocks, grid_for(s, exhaustive ? s->n : 1 << 16, 256));
         k_argmax_list<<<lb, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->block_best); s->launches++;
@@ -609,7 +626,8 @@ int ital_fetch_propose(ital_shard* s, double floor_score, int exhaustive, double
     CU(cudaMemcpyAsync(cnt, s->counters, sizeof cnt, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     memcpy(record, s->rec_host, (size_t)rl * sizeof(double));
-    s->stats[1] = s->t == 0 ? -1.0 : (double)cnt[0] + (exhaustive ? 0.0 : 1.0);
+    s->stats[0] = (double)cnt[0];                       // rows in the final worklist
+    s->stats[1] = s->t == 0 ? -1.0 : (double)cnt[2];    // rows scored by quadrature (-1: closed form for all)
     s->stats[2] = (double)s->n_nodes;
     s->stats[3] = s->h_base;
     s->stats[4] = (double)cnt[1];
@@ -640,16 +658,7 @@ int ital_fetch_commit(ital_shard* s, const double* record) {
     const double piv = std::sqrt(cv);
     std::vector<double> row(u.begin() + s->W, u.end());
     row.push_back(piv);
-    const int64_t loc = g - s->row_offset;
-    if (loc >= 0 && loc < s->n) {
-        rc = ensure_idx(s, 1);
-        if (rc) return rc;
-        CU(cudaMemcpyAsync(s->idx_dev, &loc, sizeof loc, cudaMemcpyHostToDevice, s->stream));
-        k_mask_rows<<<1, 32, 0, s->stream>>>(s->mask, s->idx_dev, 1, kSelected); s->launches++;
-        CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(s->stream));
-    }
-    rc = extend_with_record(s, rec.data(), col, piv, 0.0, 0);
+    rc = extend_with_record(s, rec.data(), col, 0, 0.0, true);
     if (rc) return rc;
     s->base_m.push_back(hdr[2]);
     s->base_L.push_back(row);

@@ -33,13 +33,6 @@ struct Best {                            // result of an argmax reduction
     long long idx;                       // local row, -1 if none
 };
 
-struct ExtendParams {                    // lives in device memory, written by the host before k_extend
-    double zn;                           // |z|^2
-    double piv;                          // pivot of the new Cholesky column
-    double beta;                         // new entry of L_K^-1 y (0 for a batch extension)
-    double pad;
-};
-
 __device__ __forceinline__ bool better(double sa, long long ia, double sb, long long ib) {
     // NaN never wins; ties go to the lower index (np.argmax on the ascending candidate list, ital.py:98,130)
     if (ib < 0) return ia >= 0;
@@ -111,10 +104,10 @@ __global__ void __launch_bounds__(256) k_sqnorm(const XT* __restrict__ X, int64_
 // coalesced against the column-major U.
 template <typename XT, int NC>   // NC: 16-byte chunks per lane and row (d_pad = NC * 32 * VN); 0 = run time
 __global__ void __launch_bounds__(256, 2)
-k_extend(const XT* __restrict__ X, int64_t n, int d_pad, const XT* __restrict__ z,
-         const ExtendParams* __restrict__ prm, const double* __restrict__ ur, int W,
+k_extend(const XT* __restrict__ X, int64_t n, int d, int d_pad, const double* __restrict__ rec, int w_cap, int W,
          const double* __restrict__ sqn, double* __restrict__ U, int64_t ldu,
-         double* __restrict__ m, double* __restrict__ v, int labelled, double var, double neg2ls2) {
+         double* __restrict__ m, double* __restrict__ v, int labelled, double y, double noise, double var,
+         double neg2ls2) {
     constexpr int VN = Vec<XT>::N;
     constexpr int RB = 4;                               // rows in flight per warp
     extern __shared__ double smem[];
@@ -124,6 +117,9 @@ k_extend(const XT* __restrict__ X, int64_t n, int d_pad, const XT* __restrict__ 
     double* part = smem + (size_t)wib * 32 * 33;        // [32 rows][33]
     double* ur_s = smem + (size_t)nwarp_blk * 32 * 33;  // [W]
     double* z_s = ur_s + ((W + 1) & ~1);                // [d_pad] only when NC == 0
+    // the new point comes as a device-resident point record (header, projection, row as float64)
+    const double* ur = rec + 8;
+    const double* z = rec + 8 + w_cap;
     for (int j = threadIdx.x; j < W; j += blockDim.x) ur_s[j] = ur[j];
     const int nchunks = NC > 0 ? NC : d_pad / (32 * VN);
     double zr[(NC > 0 ? NC : 1) * VN];
@@ -131,12 +127,18 @@ k_extend(const XT* __restrict__ X, int64_t n, int d_pad, const XT* __restrict__ 
 #pragma unroll
         for (int c = 0; c < (NC > 0 ? NC : 1); ++c)
 #pragma unroll
-            for (int e = 0; e < VN; ++e) zr[c * VN + e] = (double)z[(c * 32 + lane) * VN + e];
+            for (int e = 0; e < VN; ++e) {
+                const int col = (c * 32 + lane) * VN + e;
+                zr[c * VN + e] = col < d ? z[col] : 0.0;
+            }
     } else {
-        for (int j = threadIdx.x; j < d_pad; j += blockDim.x) z_s[j] = (double)z[j];
+        for (int j = threadIdx.x; j < d_pad; j += blockDim.x) z_s[j] = j < d ? z[j] : 0.0;
     }
     __syncthreads();
-    const double zn = prm->zn, piv = prm->piv, beta = prm->beta;
+    const double zn = rec[4];
+    // labelled point: pivot of K_LL + noise I and the new entry of L_K^-1 y; batch point: noise-free pivot
+    const double piv = labelled ? sqrt(fmax(rec[5] + noise, 2.3e-308)) : sqrt(fmax(rec[3], 1e-300));
+    const double beta = labelled ? (y - rec[2]) / piv : 0.0;
 
     const int64_t n_units = (n + 31) >> 5;
     const int64_t warp_global = (int64_t)blockIdx.x * nwarp_blk + wib;
@@ -353,11 +355,6 @@ __global__ void __launch_bounds__(256) k_argmax_final(const Best* __restrict__ b
     }
 }
 
-// worklist[0] = the row found by an argmax (used to score the most promising candidate first)
-__global__ void k_list_from_best(const Best* __restrict__ best, int* __restrict__ count, int* __restrict__ list) {
-    if (best->idx >= 0) { list[0] = (int)best->idx; *count = 1; } else { *count = 0; }
-}
-
 // Lazy-greedy worklist: rows whose upper bound gain + H(base) can still reach the score already achieved.
 // thr_src: score of the most promising candidate (device), floor_score: from other shards, margin: slack for
 // quadrature round-off between steps.  exhaustive: every candidate.
@@ -387,10 +384,12 @@ __global__ void __launch_bounds__(256) k_worklist(int64_t n, const uint8_t* __re
     }
 }
 
-// Exact MI of one candidate per warp with the shared nodes of the step (t >= 1 base variables):
+// Exact MI of one candidate per team of threads (a warp, or the whole 256-thread block when few
+// candidates are left and latency matters) with the shared nodes of the step (t >= 1 base variables):
 //   P(r_base, +) = sum_{q in group r_base} w_q * Phi((m_i + l_i . eta_q) / s_i),  P(r_base, -) = P(r_base) - P(+)
 //   score = sum_r p_r * (log(1 + eps) - log(p_r + eps))
-// Replaces 2^(t+1) calls of prob_rel + updated_prob_rel per candidate (ital/ital.py:193-219).
+// Replaces 2^(t+1) calls of prob_rel + updated_prob_rel per candidate (ital/ital.py:193-219).  The reduction
+// order is fixed, so identical rows get bit-identical scores.  Rows already scored in this step are skipped.
 template <int T>   // T = t if 1..3 (unrolled), 0 = run time
 __global__ void __launch_bounds__(256) k_eval(const int* __restrict__ count, const int* __restrict__ list, int t_rt,
                                               const double* __restrict__ m, const double* __restrict__ v,
@@ -400,19 +399,31 @@ __global__ void __launch_bounds__(256) k_eval(const int* __restrict__ count, con
                                               const double* __restrict__ masses, double h_base,
                                               double log1p_eps, double flag_var,
                                               double* __restrict__ score, double* __restrict__ gain,
-                                              int* __restrict__ n_flagged) {
+                                              int* __restrict__ n_flagged, int* __restrict__ n_scored,
+                                              int force_block) {
+    constexpr int MAXT = T > 0 ? T : 10;
     const int t = T > 0 ? T : t_rt;
     const int lane = threadIdx.x & 31;
     const int n_items = *count;
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int warps_total = (gridDim.x * blockDim.x) >> 5;
-    for (int item = warp_global; item < n_items; item += warps_total) {
+    // team size: a warp per candidate when there are enough candidates to keep every warp busy, otherwise the
+    // whole block works on one candidate (the node loop is latency-bound for a lone warp)
+    const int TPC = (force_block || n_items < (int)(gridDim.x * (blockDim.x >> 5))) ? (int)blockDim.x : 32;
+    const int tid_team = threadIdx.x % TPC;
+    const int team_global = (blockIdx.x * blockDim.x + threadIdx.x) / TPC;
+    const int teams_total = (gridDim.x * blockDim.x) / TPC;
+    __shared__ double red[8];
+    for (int item = team_global; item < n_items; item += teams_total) {
         const int64_t i = list[item];
-        double l[T > 0 ? T : 10];
+        if (score[i] == score[i]) continue;             // scored earlier in this step (team-uniform)
+        double l[MAXT];
         double s2 = v[i];
-        for (int j = 0; j < t; ++j) {
-            l[j] = U[(int64_t)(W0 + j) * ldu + i];
-            s2 = fma(-l[j], l[j], s2);
+#pragma unroll
+        for (int j = 0; j < MAXT; ++j) {
+            l[j] = 0.0;
+            if (j < t) {
+                l[j] = U[(int64_t)(W0 + j) * ldu + i];
+                s2 = fma(-l[j], l[j], s2);
+            }
         }
         const double mi = m[i];
         const double s = s2 > 0.0 ? sqrt(s2) : 0.0;
@@ -421,25 +432,45 @@ __global__ void __launch_bounds__(256) k_eval(const int* __restrict__ count, con
         for (int b = 0; b < nb; ++b) {
             double acc = 0.0;
             const int g0 = group_begin[b], g1 = group_begin[b + 1];
-            for (int q = g0 + lane; q < g1; q += 32) {
+            for (int q = g0 + tid_team; q < g1; q += TPC) {
                 double num = mi;
 #pragma unroll
-                for (int j = 0; j < (T > 0 ? T : 10); ++j)
+                for (int j = 0; j < MAXT; ++j)
                     if (j < t) num = fma(l[j], eta[(int64_t)j * n_nodes + q], num);
                 const double cdf = s > 0.0 ? phi_cdf(num / s) : (num > 0.0 ? 1.0 : 0.0);
                 acc = fma(w[q], cdf, acc);
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (TPC > 32) {
+                __syncthreads();
+                if (lane == 0) red[threadIdx.x >> 5] = acc;
+                __syncthreads();
+                acc = 0.0;
+                for (int k = 0; k < TPC / 32; ++k) acc += red[k];
+            }
             const double p_plus = acc;
             const double p_minus = fmax(masses[b] - acc, 0.0);
             sc += mi_term(p_plus, log1p_eps) + mi_term(p_minus, log1p_eps);
         }
-        if (lane == 0) {
+        if (TPC > 32) __syncthreads();                  // every thread has read score[i] before it is written
+        if (tid_team == 0) {
             score[i] = sc;
             gain[i] = sc - h_base;
+            atomicAdd(n_scored, 1);
             if (s2 < flag_var) atomicAdd(n_flagged, 1);
         }
+    }
+}
+
+// worklist = the per-block winners of an argmax stage (the most promising candidates, scored first)
+__global__ void k_list_from_blocks(const Best* __restrict__ block_best, int nblocks, int* __restrict__ count,
+                                   int* __restrict__ list) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int c = 0;
+        for (int k = 0; k < nblocks; ++k)
+            if (block_best[k].idx >= 0) list[c++] = (int)block_best[k].idx;
+        *count = c;
     }
 }
 
@@ -453,6 +484,13 @@ __global__ void k_mask_rows(uint8_t* __restrict__ mask, const int64_t* __restric
                             uint8_t set_bits) {
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += (int64_t)gridDim.x * blockDim.x)
         mask[rows[k]] |= set_bits;
+}
+
+// mark the row of a device-resident point record (if it is local)
+__global__ void k_mask_record(uint8_t* __restrict__ mask, const double* __restrict__ rec, int64_t row_offset,
+                              int64_t n, uint8_t set_bits) {
+    const long long loc = (long long)rec[0] - row_offset;
+    if (threadIdx.x == 0 && blockIdx.x == 0 && loc >= 0 && loc < n) mask[loc] |= set_bits;
 }
 
 __global__ void k_mask_all(uint8_t* __restrict__ mask, int64_t n, uint8_t and_bits, uint8_t or_bits) {

@@ -141,7 +141,7 @@ def test_repeated_rounds_track_the_oracle():
 
 
 def test_interface_edge_cases():
-    X, assign = _syn(40, 8, seed=3, centres=4)
+    X, assign = _syn(12, 8, seed=3, centres=4)
     gpu = _gpu_learner(X, length_scale=1.0)
     assert gpu.rel_mean is None
     with pytest.raises(RuntimeError):
@@ -155,11 +155,11 @@ def test_interface_edge_cases():
     gpu.update({11: 0})                               # only unnameable: no round counted
     assert gpu.rounds == 1
     ret = gpu.fetch_unlabelled(100)                   # k clamped to the unseen rows (ital.py:99-100)
-    assert sorted(ret) == sorted(set(range(40)) - {3, 5, 9, 11})
-    assert gpu.get_unseen() == sorted(set(range(40)) - {3, 5, 9, 11})
+    assert sorted(ret) == sorted(set(range(12)) - {3, 5, 9, 11})
+    assert gpu.get_unseen() == sorted(set(range(12)) - {3, 5, 9, 11})
     assert gpu.fetch_unlabelled(0) == []
     gpu.reset()
-    assert gpu.rel_mean is None and gpu.rounds == 0 and gpu.get_unseen() == list(range(40))
+    assert gpu.rel_mean is None and gpu.rounds == 0 and gpu.get_unseen() == list(range(12))
     for kw in (dict(mistake_prob=0.2), dict(label_prob=0.5), dict(label_estimation='optimistic'),
                dict(monte_carlo_num_rel=3)):
         bad = _gpu_learner(X, length_scale=1.0, **kw)
