@@ -89,7 +89,7 @@ class ClockSampler(object):
         self.proc = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
         except OSError:
             pass
@@ -179,7 +179,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--rows', type=int, default=1000000, help='pool rows per GPU')
@@ -255,6 +255,9 @@ def main():
             dist.barrier()
         return dev, wall, ret
 
+    # clocks are sampled from the warm-up on: the timed region itself can be shorter than one nvidia-smi period
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.3 if rank == 0 else 0.0)
     # warm-up (also grows every buffer to its steady-state size)
     timed(args.warmup, False)
     # X per GPU (2 GB at 1M x 512 x 4 B) is far larger than the 126 MB L2: no L2 flush needed between steps
@@ -262,7 +265,6 @@ def main():
     lib.ital_profile_enable(shard.handle, 1)
     lib.ital_profile_read(shard.handle, None, None, None)
     launches0 = int(lib.ital_launch_count(shard.handle))
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     dev, wall, ret = timed(args.steps, False)
     clocks = sampler.stop() if sampler else None
     launches = int(lib.ital_launch_count(shard.handle)) - launches0

