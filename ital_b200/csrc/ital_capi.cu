@@ -165,7 +165,7 @@ int ensure_width(ital_shard* s, int cols) {
 }
 
 template <typename XT>
-int launch_extend_t(ital_shard* s, int W_used, int labelled, double y) {
+int launch_extend_t(ital_shard* s, int W_used, int labelled, double y, uint8_t mark_bits) {
     constexpr int VN = Vec<XT>::N;
     const int nchunks = (int)(s->d_pad / (32 * VN));
     const int threads = 256, warps = threads / 32;
@@ -186,7 +186,7 @@ int launch_extend_t(ital_shard* s, int W_used, int labelled, double y) {
         CU(cudaFuncSetAttribute(k_extend<XT, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
         k_extend<XT, NCV><<<blocks, threads, smem, s->stream>>>(                                                \
             (const XT*)s->X, s->n, (int)s->d, (int)s->d_pad, s->rec_in_dev, s->w_cap, W_used, s->sqn, s->U,     \
-            s->ldu, s->m, s->v, labelled, y, s->noise, s->var, neg2ls2);                                        \
+            s->ldu, s->m, s->v, labelled, y, s->noise, s->var, neg2ls2, s->mask, s->row_offset, mark_bits);     \
     } while (0)
     if (nchunks == 4) ITAL_LAUNCH_EXT(4);
     else if (nchunks == 2) ITAL_LAUNCH_EXT(2);
@@ -214,12 +214,9 @@ int extend_with_record(ital_shard* s, const double* rec, int col, int labelled, 
     const int64_t rl = record_doubles(s);
     memcpy(s->rec_in_host, rec, (size_t)rl * sizeof(double));
     CU(cudaMemcpyAsync(s->rec_in_dev, s->rec_in_host, (size_t)rl * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    if (mark_selected) {
-        k_mask_record<<<1, 32, 0, s->stream>>>(s->mask, s->rec_in_dev, s->row_offset, s->n, kSelected); s->launches++;
-        CU(cudaGetLastError());
-    }
-    if (s->x_dtype == ITAL_F32) return launch_extend_t<float>(s, col, labelled, y);
-    return launch_extend_t<double>(s, col, labelled, y);
+    const uint8_t mark = mark_selected ? kSelected : (uint8_t)0;
+    if (s->x_dtype == ITAL_F32) return launch_extend_t<float>(s, col, labelled, y, mark);
+    return launch_extend_t<double>(s, col, labelled, y, mark);
 }
 
 int make_record(ital_shard* s, long long local_row, double* dst_dev) {
@@ -592,18 +589,18 @@ int ital_fetch_propose(ital_shard* s, double floor_score, int exhaustive, double
         snq::Nodes nd = snq::generate(s->t, s->base_m.data(), Lb.data());
         rc = upload_nodes(s, nd);
         if (rc) return rc;
-        k_fill<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->score, s->n, std::numeric_limits<double>::quiet_NaN()); s->launches++;
-        if (!exhaustive) {
+        if (exhaustive) {
+            k_fill<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->score, s->n, std::numeric_limits<double>::quiet_NaN()); s->launches++;
+        } else {
             // stage A: the most promising candidates (the per-block maxima of the bound) are scored first, one
             // block each; the best exact score among them is the pruning threshold
             const int ba = std::min(kArgmaxBlocks, std::min(blocks, 2 * s->num_sms));
-            k_argmax_rows<<<ba, 256, 0, s->stream>>>(s->n, s->gain, s->mask, s->block_best); s->launches++;
-            k_list_from_blocks<<<1, 32, 0, s->stream>>>(s->block_best, ba, s->counters, s->worklist); s->launches++;
+            k_argmax_rows<<<ba, 256, 0, s->stream>>>(s->n, s->gain, s->mask, s->block_best, s->score); s->launches++;
+            k_list_from_blocks<<<1, 512, 0, s->stream>>>(s->block_best, ba, s->counters, s->worklist); s->launches++;
             CU(cudaGetLastError());
             rc = launch_eval(s, ba, true);
             if (rc) return rc;
-            k_argmax_list<<<1, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->block_best); s->launches++;
-            k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, 1, s->best + 1); s->launches++;
+            k_argmax_list<<<1, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->best + 1); s->launches++;
             CU(cudaMemsetAsync(s->counters, 0, sizeof(int), s->stream));
         }
         // stage B: every row whose bound still reaches the threshold (all rows when exhaustive)
@@ -613,9 +610,13 @@ int ital_fetch_propose(ital_shard* s, double floor_score, int exhaustive, double
         CU(cudaGetLastError());
         rc = launch_eval(s, exhaustive ? s->n : (int64_t)s->num_sms * 16, false);
         if (rc) return rc;
-        const int lb = std::min(kArgmaxBlocks, grid_for(s, exhaustive ? s->n : 1 << 16, 256));
-        k_argmax_list<<<lb, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->block_best); s->launches++;
-        k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, lb, s->best); s->launches++;
+        if (exhaustive) {
+            const int lb = std::min(kArgmaxBlocks, grid_for(s, s->n, 256));
+            k_argmax_list<<<lb, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->block_best); s->launches++;
+            k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, lb, s->best); s->launches++;
+        } else {        // short list: one block writes the result directly
+            k_argmax_list<<<1, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->best); s->launches++;
+        }
         CU(cudaGetLastError());
     }
     rc = make_record(s, -1, s->rec_dev);

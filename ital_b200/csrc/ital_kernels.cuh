@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256, 2)
 k_extend(const XT* __restrict__ X, int64_t n, int d, int d_pad, const double* __restrict__ rec, int w_cap, int W,
          const double* __restrict__ sqn, double* __restrict__ U, int64_t ldu,
          double* __restrict__ m, double* __restrict__ v, int labelled, double y, double noise, double var,
-         double neg2ls2) {
+         double neg2ls2, uint8_t* __restrict__ mask, int64_t row_offset, uint8_t mark_bits) {
     constexpr int VN = Vec<XT>::N;
     constexpr int RB = 4;                               // rows in flight per warp
     extern __shared__ double smem[];
@@ -120,6 +120,10 @@ k_extend(const XT* __restrict__ X, int64_t n, int d, int d_pad, const double* __
     // the new point comes as a device-resident point record (header, projection, row as float64)
     const double* ur = rec + 8;
     const double* z = rec + 8 + w_cap;
+    if (mark_bits != 0 && blockIdx.x == 0 && threadIdx.x == 0) {    // the chosen row leaves the candidate set
+        const long long loc = (long long)rec[0] - row_offset;
+        if (loc >= 0 && loc < n) mask[loc] |= mark_bits;
+    }
     for (int j = threadIdx.x; j < W; j += blockDim.x) ur_s[j] = ur[j];
     const int nchunks = NC > 0 ? NC : d_pad / (32 * VN);
     double zr[(NC > 0 ? NC : 1) * VN];
@@ -277,11 +281,15 @@ __global__ void __launch_bounds__(256) k_score0(int64_t n, const double* __restr
 // argmax of `values` over candidate rows (mask == 0); stage 1 of 2
 __global__ void __launch_bounds__(256) k_argmax_rows(int64_t n, const double* __restrict__ values,
                                                      const uint8_t* __restrict__ mask,
-                                                     Best* __restrict__ block_best) {
+                                                     Best* __restrict__ block_best,
+                                                     double* __restrict__ clear_score) {
     double bs = 0.0;
     long long bi = -1;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    const double qnan = nan("");
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         if (mask[i] == 0 && better(values[i], i, bs, bi)) { bs = values[i]; bi = i; }
+        if (clear_score != nullptr) clear_score[i] = qnan;      // "not scored in this step"
+    }
     __shared__ double ss[8];
     __shared__ long long si[8];
 #pragma unroll
@@ -427,19 +435,35 @@ __global__ void __launch_bounds__(256) k_eval(const int* __restrict__ count, con
         }
         const double mi = m[i];
         const double s = s2 > 0.0 ? sqrt(s2) : 0.0;
+        const double inv_s = s > 0.0 ? 1.0 / s : 0.0;
         double sc = 0.0;
         const int nb = 1 << t;
         for (int b = 0; b < nb; ++b) {
-            double acc = 0.0;
             const int g0 = group_begin[b], g1 = group_begin[b + 1];
-            for (int q = g0 + tid_team; q < g1; q += TPC) {
-                double num = mi;
+            // four nodes per thread and trip: independent erfc chains hide the FP64 latency
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            for (int q = g0 + tid_team; q < g1; q += 4 * TPC) {
+                double num[4], ww[4];
 #pragma unroll
-                for (int j = 0; j < MAXT; ++j)
-                    if (j < t) num = fma(l[j], eta[(int64_t)j * n_nodes + q], num);
-                const double cdf = s > 0.0 ? phi_cdf(num / s) : (num > 0.0 ? 1.0 : 0.0);
-                acc = fma(w[q], cdf, acc);
+                for (int u = 0; u < 4; ++u) {
+                    const int qq = q + u * TPC;
+                    const bool ok = qq < g1;
+                    ww[u] = ok ? w[qq] : 0.0;
+                    num[u] = mi;
+#pragma unroll
+                    for (int j = 0; j < MAXT; ++j)
+                        if (j < t) num[u] = fma(l[j], ok ? eta[(int64_t)j * n_nodes + qq] : 0.0, num[u]);
+                }
+                double cdf[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    cdf[u] = s > 0.0 ? phi_cdf(num[u] * inv_s) : (num[u] > 0.0 ? 1.0 : 0.0);
+                a0 = fma(ww[0], cdf[0], a0);
+                a1 = fma(ww[1], cdf[1], a1);
+                a2 = fma(ww[2], cdf[2], a2);
+                a3 = fma(ww[3], cdf[3], a3);
             }
+            double acc = (a0 + a1) + (a2 + a3);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (TPC > 32) {
@@ -466,12 +490,9 @@ __global__ void __launch_bounds__(256) k_eval(const int* __restrict__ count, con
 // worklist = the per-block winners of an argmax stage (the most promising candidates, scored first)
 __global__ void k_list_from_blocks(const Best* __restrict__ block_best, int nblocks, int* __restrict__ count,
                                    int* __restrict__ list) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        int c = 0;
-        for (int k = 0; k < nblocks; ++k)
-            if (block_best[k].idx >= 0) list[c++] = (int)block_best[k].idx;
-        *count = c;
-    }
+    // one block; *count must be 0 on entry
+    for (int k = threadIdx.x; k < nblocks; k += blockDim.x)
+        if (block_best[k].idx >= 0) list[atomicAdd(count, 1)] = (int)block_best[k].idx;
 }
 
 __global__ void k_fill(double* __restrict__ p, int64_t n, double value) {

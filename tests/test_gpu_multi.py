@@ -1,0 +1,87 @@
+"""Two-GPU run of the sharded learner over NCCL against the single-GPU learner and the oracle."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _syn(n, d, seed, centres=20):
+    rng = np.random.default_rng(seed)
+    C = rng.standard_normal((centres, d))
+    assign = rng.integers(0, centres, n)
+    X = C[assign] + 0.6 * rng.standard_normal((n, d))
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    return X.astype(np.float32).astype(np.float64), assign
+
+
+def _rounds(learner, y, rounds=3):
+    learner.update({0: 1})
+    out = []
+    for _ in range(rounds):
+        ret = learner.fetch_unlabelled(4)
+        out.append(ret)
+        learner.update({i: int(y[i]) for i in ret})
+    return out, np.array(learner.rel_mean)
+
+
+def _worker(rank, world, port, q, local_rows):
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        from ital_b200 import ITAL
+        X, assign = _syn(5003, 96, seed=5)
+        y = np.where(assign == assign[0], 1, -1)
+        if local_rows:
+            from ital_b200.dist import partition_rows
+            off = partition_rows(len(X), world)
+            learner = ITAL(X[off[rank]:off[rank + 1]], length_scale=1.0, device=rank, process_group=True,
+                           local_rows=(int(off[rank]), len(X)))
+        else:
+            learner = ITAL(X, length_scale=1.0, device=rank, process_group=True)
+        batches, rel_mean = _rounds(learner, y)
+        q.put((rank, batches, rel_mean))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('local_rows', [False, True])
+def test_two_gpus_match_one_gpu_and_oracle(local_rows):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    from ital_b200 import ITAL
+    from oracle.ital_oracle import OracleITAL
+    X, assign = _syn(5003, 96, seed=5)
+    y = np.where(assign == assign[0], 1, -1)
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, local_rows)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=300) for _ in procs), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    one_batches, one_mean = _rounds(ITAL(X, length_scale=1.0, device=0), y)
+    ora_batches, ora_mean = _rounds(OracleITAL(X, length_scale=1.0), y)
+    for rank, batches, rel_mean in res:
+        assert batches == one_batches == ora_batches
+        np.testing.assert_allclose(rel_mean, one_mean, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(rel_mean, ora_mean, rtol=1e-6, atol=1e-9)
