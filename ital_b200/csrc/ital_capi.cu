@@ -42,6 +42,7 @@ int fail(int code, const char* fmt, ...) {
 constexpr uint8_t kSeen = 1, kSelected = 2, kNotCandidate = 4, kRestricted = 8;
 constexpr double kPruneMargin = 1e-6;   // slack of the lazy-greedy bound against quadrature round-off
 constexpr int kArgmaxBlocks = 592;      // 4 x 148 SMs
+constexpr int kStageA = 48;             // rows scored ahead of the pruning threshold
 
 }  // namespace
 
@@ -59,7 +60,8 @@ struct ital_shard {
     int* worklist = nullptr;
     int* counters = nullptr;         // [0] worklist size, [1] flagged, [2] scored exactly
     Best* block_best = nullptr;      // kArgmaxBlocks
-    Best* best = nullptr;            // [0] step winner, [1] most promising candidate
+    Best* best = nullptr;            // [0] step winner, [1] best of stage A
+    double* thr_dev = nullptr;       // worklist threshold (device scalar)
     double* rec_dev = nullptr;       // records produced on the device (propose / export)
     double* rec_host = nullptr;      // pinned mirror of rec_dev
     double* rec_in_dev = nullptr;    // the record k_extend reads (one record)
@@ -296,7 +298,7 @@ int launch_eval(ital_shard* s, int64_t items_hint, bool block_per_candidate) {
 void free_all(ital_shard* s) {
     cudaSetDevice(s->device);
     void* ptrs[] = {s->X, s->sqn, s->m, s->v, s->U, s->gain, s->score, s->mask, s->worklist, s->counters,
-                    s->block_best, s->best, s->rec_dev, s->rec_in_dev, s->idx_dev, s->eta_dev,
+                    s->block_best, s->best, s->thr_dev, s->rec_dev, s->rec_in_dev, s->idx_dev, s->eta_dev,
                     s->w_dev, s->masses_dev, s->group_dev, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -389,6 +391,7 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
         CU(cudaMalloc(&s->counters, 4 * sizeof(int)));
         CU(cudaMalloc(&s->block_best, kArgmaxBlocks * sizeof(Best)));
         CU(cudaMalloc(&s->best, 2 * sizeof(Best)));
+        CU(cudaMalloc(&s->thr_dev, sizeof(double)));
         int r = ensure_width(s, 32);
         if (r) return r;
         const int blocks = grid_for(s, s->n, 8);
@@ -591,30 +594,34 @@ int ital_fetch_propose(ital_shard* s, double floor_score, int exhaustive, double
         if (rc) return rc;
         if (exhaustive) {
             k_fill<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->score, s->n, std::numeric_limits<double>::quiet_NaN()); s->launches++;
-        } else {
-            // stage A: the most promising candidates (the per-block maxima of the bound) are scored first, one
-            // block each; the best exact score among them is the pruning threshold
-            const int ba = std::min(kArgmaxBlocks, std::min(blocks, 2 * s->num_sms));
-            k_argmax_rows<<<ba, 256, 0, s->stream>>>(s->n, s->gain, s->mask, s->block_best, s->score); s->launches++;
-            k_list_from_blocks<<<1, 512, 0, s->stream>>>(s->block_best, ba, s->counters, s->worklist); s->launches++;
+            k_worklist<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->n, s->mask, s->gain, s->thr_dev, 1,
+                                                                        s->counters, s->worklist); s->launches++;
             CU(cudaGetLastError());
-            rc = launch_eval(s, ba, true);
+            rc = launch_eval(s, s->n, false);
             if (rc) return rc;
-            k_argmax_list<<<1, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->best + 1); s->launches++;
-            CU(cudaMemsetAsync(s->counters, 0, sizeof(int), s->stream));
-        }
-        // stage B: every row whose bound still reaches the threshold (all rows when exhaustive)
-        k_worklist<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->n, s->mask, s->gain, s->h_base, s->best + 1,
-                                                                    floor_score, kPruneMargin, exhaustive,
-                                                                    s->counters, s->worklist); s->launches++;
-        CU(cudaGetLastError());
-        rc = launch_eval(s, exhaustive ? s->n : (int64_t)s->num_sms * 16, false);
-        if (rc) return rc;
-        if (exhaustive) {
             const int lb = std::min(kArgmaxBlocks, grid_for(s, s->n, 256));
             k_argmax_list<<<lb, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->block_best); s->launches++;
             k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, lb, s->best); s->launches++;
-        } else {        // short list: one block writes the result directly
+        } else {
+            // stage A: score the rows with the largest bounds first (block per row); the bound cutoff is the
+            // kStageA-th largest per-block maximum, so the list holds the global top rows by bound
+            const int ba = std::min(kArgmaxBlocks, blocks);
+            k_argmax_rows<<<ba, 256, 0, s->stream>>>(s->n, s->gain, s->mask, s->block_best, s->score); s->launches++;
+            k_cutoff_from_blocks<<<1, 1024, 0, s->stream>>>(s->block_best, ba, kStageA, s->thr_dev); s->launches++;
+            k_worklist<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->n, s->mask, s->gain, s->thr_dev, 0,
+                                                                        s->counters, s->worklist); s->launches++;
+            CU(cudaGetLastError());
+            rc = launch_eval(s, 4 * kStageA, true);
+            if (rc) return rc;
+            k_argmax_list<<<1, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->best + 1); s->launches++;
+            // stage B: every row whose bound still reaches the best exact score of stage A
+            CU(cudaMemsetAsync(s->counters, 0, sizeof(int), s->stream));
+            k_threshold_from_best<<<1, 1, 0, s->stream>>>(s->best + 1, s->h_base, floor_score, kPruneMargin, s->thr_dev); s->launches++;
+            k_worklist<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->n, s->mask, s->gain, s->thr_dev, 0,
+                                                                        s->counters, s->worklist); s->launches++;
+            CU(cudaGetLastError());
+            rc = launch_eval(s, (int64_t)s->num_sms * 16, false);
+            if (rc) return rc;
             k_argmax_list<<<1, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->best); s->launches++;
         }
         CU(cudaGetLastError());

@@ -363,25 +363,42 @@ __global__ void __launch_bounds__(256) k_argmax_final(const Best* __restrict__ b
     }
 }
 
-// Lazy-greedy worklist: rows whose upper bound gain + H(base) can still reach the score already achieved.
-// thr_src: score of the most promising candidate (device), floor_score: from other shards, margin: slack for
-// quadrature round-off between steps.  exhaustive: every candidate.
-__global__ void __launch_bounds__(256) k_worklist(int64_t n, const uint8_t* __restrict__ mask,
-                                                  const double* __restrict__ gain, double h_base,
-                                                  const Best* __restrict__ thr_src, double floor_score,
-                                                  double margin, int exhaustive, int* __restrict__ count,
-                                                  int* __restrict__ list) {
-    double thr = -1e300;
-    if (!exhaustive) {
-        thr = floor_score;
-        if (thr_src->idx >= 0 && thr_src->score == thr_src->score) thr = fmax(thr, thr_src->score);
-        thr -= margin;
+// Stage A cutoff: the K-th largest of the per-block maxima of the bound.  At least K rows reach it, and they
+// are the rows with the globally largest bounds (one block; nblocks <= 1024).
+__global__ void __launch_bounds__(1024) k_cutoff_from_blocks(const Best* __restrict__ block_best, int nblocks, int K,
+                                                             double* __restrict__ thr_gain) {
+    __shared__ double v[1024];
+    const int k = threadIdx.x;
+    v[k] = (k < nblocks && block_best[k].idx >= 0) ? block_best[k].score : -1e300;
+    __syncthreads();
+    if (k < nblocks) {
+        int rank = 0;                                   // number of entries strictly ahead of v[k]
+        for (int j = 0; j < nblocks; ++j) rank += (v[j] > v[k]) || (v[j] == v[k] && j < k);
+        if (rank == min(K, nblocks) - 1) *thr_gain = v[k];
     }
+}
+
+// Stage B threshold: a row can still win only if gain_i + H(base) >= best exact score so far - margin.
+__global__ void k_threshold_from_best(const Best* __restrict__ best, double h_base, double floor_score,
+                                      double margin, double* __restrict__ thr_gain) {
+    double thr = floor_score;
+    if (best->idx >= 0 && best->score == best->score) thr = fmax(thr, best->score);
+    *thr_gain = thr - margin - h_base;
+}
+
+// Lazy-greedy worklist: candidate rows whose upper bound gain_i reaches *thr_gain (a device scalar prepared by
+// k_cutoff_from_blocks or k_threshold_from_best); every candidate when exhaustive.  Rows already scored in this
+// step are left out unless `keep_scored` (the final list must contain them for the argmax).
+__global__ void __launch_bounds__(256) k_worklist(int64_t n, const uint8_t* __restrict__ mask,
+                                                  const double* __restrict__ gain,
+                                                  const double* __restrict__ thr_gain, int exhaustive,
+                                                  int* __restrict__ count, int* __restrict__ list) {
+    const double thr = exhaustive ? -1e300 : *thr_gain;
     const int lane = threadIdx.x & 31;
     for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n;
          i0 += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = i0 + lane;
-        const bool take = i < n && mask[i] == 0 && (exhaustive || gain[i] + h_base >= thr);
+        const bool take = i < n && mask[i] == 0 && gain[i] >= thr;
         const unsigned ballot = __ballot_sync(0xffffffffu, take);
         if (ballot != 0) {
             int base = 0;
