@@ -363,21 +363,6 @@ __global__ void __launch_bounds__(256) k_argmax_final(const Best* __restrict__ b
     }
 }
 
-// Stage A cutoff: the K-th largest of the per-block maxima of the bound.  At least K rows reach it, and they
-// are the rows with the globally largest bounds (one block; nblocks <= 1024).
-__global__ void __launch_bounds__(1024) k_cutoff_from_blocks(const Best* __restrict__ block_best, int nblocks, int K,
-                                                             double* __restrict__ thr_gain) {
-    __shared__ double v[1024];
-    const int k = threadIdx.x;
-    v[k] = (k < nblocks && block_best[k].idx >= 0) ? block_best[k].score : -1e300;
-    __syncthreads();
-    if (k < nblocks) {
-        int rank = 0;                                   // number of entries strictly ahead of v[k]
-        for (int j = 0; j < nblocks; ++j) rank += (v[j] > v[k]) || (v[j] == v[k] && j < k);
-        if (rank == min(K, nblocks) - 1) *thr_gain = v[k];
-    }
-}
-
 // Stage B threshold: a row can still win only if gain_i + H(base) >= best exact score so far - margin.
 __global__ void k_threshold_from_best(const Best* __restrict__ best, double h_base, double floor_score,
                                       double margin, double* __restrict__ thr_gain) {
@@ -387,7 +372,7 @@ __global__ void k_threshold_from_best(const Best* __restrict__ best, double h_ba
 }
 
 // Lazy-greedy worklist: candidate rows whose upper bound gain_i reaches *thr_gain (a device scalar prepared by
-// k_cutoff_from_blocks or k_threshold_from_best); every candidate when exhaustive.  Rows already scored in this
+// k_threshold_from_best); every candidate when exhaustive.  Rows already scored in this
 // step are left out unless `keep_scored` (the final list must contain them for the argmax).
 __global__ void __launch_bounds__(256) k_worklist(int64_t n, const uint8_t* __restrict__ mask,
                                                   const double* __restrict__ gain,
