@@ -87,6 +87,15 @@ int ital_restrict_candidates(ital_shard* s, int64_t m, const int64_t* global_idx
  *                     globally best record: extends every local row's projection by the chosen point.
  * ital_fetch_end:     drops the batch-conditional state (the selected rows stay unseen until update()).
  * ital_fetch:         the whole loop for a single-shard learner; returns the number selected. */
+/* Device-resident variants (what the multi-GPU host loop uses; nothing in them waits for the GPU):
+ * ital_fetch_propose_dev writes the local best record to DEVICE memory (ital_record_doubles() doubles);
+ * ital_fetch_commit_dev picks the best of `n_records` consecutive records in DEVICE memory (e.g. the output of
+ * an NCCL all-gather of every shard's proposal) with the rule above, appends it to the batch and, if `extend`
+ * is non-zero, runs the streaming pass (pass 0 for the last sample of the batch: nothing follows it);
+ * ital_fetch_result synchronises and returns the (global row, score) of the samples committed so far. */
+int ital_fetch_propose_dev(ital_shard* s, double floor_score, int exhaustive, double* record_dev);
+int ital_fetch_commit_dev(ital_shard* s, const double* records_dev, int n_records, int extend);
+int ital_fetch_result(ital_shard* s, int max_out, int64_t* out_idx, double* out_scores);
 int ital_fetch_begin(ital_shard* s, double label_prob, double mistake_prob);
 int ital_fetch_propose(ital_shard* s, double floor_score, int exhaustive, double* record);
 int ital_fetch_commit(ital_shard* s, const double* record);

@@ -32,6 +32,9 @@ SIGNATURES = {
     'ital_add_labelled': (ctypes.c_int, [_shard_p, _c_double_p, ctypes.c_double]),
     'ital_mark_seen': (ctypes.c_int, [_shard_p, ctypes.c_int64, _c_int64_p]),
     'ital_restrict_candidates': (ctypes.c_int, [_shard_p, ctypes.c_int64, _c_int64_p]),
+    'ital_fetch_propose_dev': (ctypes.c_int, [_shard_p, ctypes.c_double, ctypes.c_int, ctypes.c_void_p]),
+    'ital_fetch_commit_dev': (ctypes.c_int, [_shard_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    'ital_fetch_result': (ctypes.c_int, [_shard_p, ctypes.c_int, _c_int64_p, _c_double_p]),
     'ital_fetch_begin': (ctypes.c_int, [_shard_p, ctypes.c_double, ctypes.c_double]),
     'ital_fetch_propose': (ctypes.c_int, [_shard_p, ctypes.c_double, ctypes.c_int, _c_double_p]),
     'ital_fetch_commit': (ctypes.c_int, [_shard_p, _c_double_p]),

@@ -72,10 +72,16 @@ struct ital_shard {
     int64_t idx_cap = 0;
     // quadrature nodes of the current step
     double *eta_dev = nullptr, *w_dev = nullptr, *masses_dev = nullptr;
-    int* group_dev = nullptr;
+    int *group_dev = nullptr, *orth_dev = nullptr;
     int64_t nodes_cap = 0;
     int64_t n_nodes = 0;
-    double h_base = 0.0;
+    double* gl_dev = nullptr;        // Gauss-Legendre tables: x[65][64] then w[65][64]
+    // batch state on the device: means and Cholesky rows of the selected points, selection list, H(base)
+    double *base_m_dev = nullptr, *base_L_dev = nullptr, *sel_dev = nullptr, *hbase_dev = nullptr;
+    double* sel_host = nullptr;      // pinned mirror of sel_dev: (global row, score) per step
+    int* stats_dev = nullptr;        // per step: worklist size, flagged, scored, -
+    int* stats_host = nullptr;       // pinned
+    int proposals = 0;               // propose calls in the running fetch
 
     int w_cap = 0;                   // allocated projection columns
     int W = 0;                       // labelled points in the model
@@ -89,8 +95,6 @@ struct ital_shard {
     std::vector<double> lab_x;               // labelled rows, W x d doubles
     std::vector<double> lab_sqn, lab_y;
     std::vector<int64_t> lab_idx;
-    std::vector<double> base_m;              // means of the points selected in this fetch
-    std::vector<std::vector<double>> base_L; // rows of the Cholesky factor of their posterior covariance
     std::vector<int64_t> selected;           // global indices selected in this fetch
     std::vector<int64_t> restricted;         // local rows carrying kRestricted
 
@@ -100,6 +104,7 @@ struct ital_shard {
     bool lab_dev_valid = false;
 
     double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double step_nodes[16] = {0};
     // measurement
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -233,64 +238,171 @@ int make_record(ital_shard* s, long long local_row, double* dst_dev) {
     return ITAL_OK;
 }
 
-int upload_nodes(ital_shard* s, const snq::Nodes& nd) {
-    const int nb = 1 << nd.t;
-    if (nd.n > s->nodes_cap) {
-        CU(cudaStreamSynchronize(s->stream));
-        if (s->eta_dev) CU(cudaFree(s->eta_dev));
-        if (s->w_dev) CU(cudaFree(s->w_dev));
-        s->eta_dev = s->w_dev = nullptr;
-        CU(cudaMalloc(&s->eta_dev, (size_t)nd.n * 10 * sizeof(double)));
-        CU(cudaMalloc(&s->w_dev, (size_t)nd.n * sizeof(double)));
-        s->nodes_cap = nd.n;
+constexpr int kMaxBatch = 11;            // greedy steps per fetch (t <= 10 base variables)
+
+int ensure_nodes(ital_shard* s, int64_t n_nodes) {
+    if (n_nodes <= s->nodes_cap) return ITAL_OK;
+    CU(cudaStreamSynchronize(s->stream));
+    for (void* p : {(void*)s->eta_dev, (void*)s->w_dev, (void*)s->orth_dev})
+        if (p) CU(cudaFree(p));
+    s->eta_dev = s->w_dev = nullptr;
+    s->orth_dev = nullptr;
+    CU(cudaMalloc(&s->eta_dev, (size_t)n_nodes * 10 * sizeof(double)));
+    CU(cudaMalloc(&s->w_dev, (size_t)n_nodes * sizeof(double)));
+    CU(cudaMalloc(&s->orth_dev, (size_t)n_nodes * sizeof(int)));
+    s->nodes_cap = n_nodes;
+    return ITAL_OK;
+}
+
+// Quadrature nodes of the step from the batch state.  t <= 3: generated on the device from the device-resident
+// state, nothing waits.  t >= 4 (batches of more than 4): generated and sorted on the host (csrc/snq_host.h),
+// which costs one device-to-host round trip for the batch state.
+int prepare_nodes(ital_shard* s) {
+    const int t = s->t;
+    const int q = snq::order_for(t);
+    int64_t N = 1;
+    for (int j = 0; j < t; ++j) N *= 2 * q;
+    int rc = ensure_nodes(s, N);
+    if (rc) return rc;
+    s->n_nodes = N;
+    if (t <= 3) {
+        const int blocks = (int)((N + 255) / 256);
+        const double* glx = s->gl_dev;
+        const double* glw = s->gl_dev + (snq::kMaxOrder + 1) * 64;
+#define ITAL_GEN(TV) k_snq_generate<TV><<<blocks, 256, 0, s->stream>>>(q, snq::kR, snq::kQMin, s->base_m_dev, s->base_L_dev, \
+                                                              glx, glw, N, s->eta_dev, s->w_dev, s->orth_dev)
+        if (t == 1) ITAL_GEN(1);
+        else if (t == 2) ITAL_GEN(2);
+        else ITAL_GEN(3);
+#undef ITAL_GEN
+        s->launches++;
+        k_snq_masses<<<1, 1024, 0, s->stream>>>(t, N, s->w_dev, s->orth_dev, s->log1p_eps, s->masses_dev, s->hbase_dev); s->launches++;
+        CU(cudaGetLastError());
+        return ITAL_OK;
     }
-    if (!s->masses_dev) CU(cudaMalloc(&s->masses_dev, 1024 * sizeof(double)));
-    if (!s->group_dev) CU(cudaMalloc(&s->group_dev, 1025 * sizeof(int)));
-    // pinned staging: the copies are asynchronous; the buffer is rewritten only after the next propose has
-    // synchronised on its result
-    const size_t b_eta = nd.eta.size() * sizeof(double), b_w = nd.w.size() * sizeof(double);
-    const size_t b_m = nb * sizeof(double), b_g = (nb + 1) * sizeof(int);
-    const size_t need = b_eta + b_w + b_m + b_g;
-    if (need > s->nodes_host_cap) {
-        CU(cudaStreamSynchronize(s->stream));
-        if (s->nodes_host) CU(cudaFreeHost(s->nodes_host));
-        s->nodes_host = nullptr;
-        CU(cudaMallocHost(&s->nodes_host, need));
-        s->nodes_host_cap = need;
-    }
-    char* p = s->nodes_host;
-    memcpy(p, nd.eta.data(), b_eta);
-    memcpy(p + b_eta, nd.w.data(), b_w);
-    memcpy(p + b_eta + b_w, nd.masses.data(), b_m);
-    memcpy(p + b_eta + b_w + b_m, nd.group_begin.data(), b_g);
-    CU(cudaMemcpyAsync(s->eta_dev, p, b_eta, cudaMemcpyHostToDevice, s->stream));
-    CU(cudaMemcpyAsync(s->w_dev, p + b_eta, b_w, cudaMemcpyHostToDevice, s->stream));
-    CU(cudaMemcpyAsync(s->masses_dev, p + b_eta + b_w, b_m, cudaMemcpyHostToDevice, s->stream));
-    CU(cudaMemcpyAsync(s->group_dev, p + b_eta + b_w + b_m, b_g, cudaMemcpyHostToDevice, s->stream));
-    s->n_nodes = nd.n;
-    s->h_base = nd.entropy;
+    // host path
+    std::vector<double> bm(16), bL(16 * 16);
+    CU(cudaMemcpyAsync(bm.data(), s->base_m_dev, 16 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(bL.data(), s->base_L_dev, 256 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    std::vector<double> Lb((size_t)t * t, 0.0);
+    for (int a = 0; a < t; ++a)
+        for (int b = 0; b <= a; ++b) Lb[(size_t)a * t + b] = bL[(size_t)a * kBaseStride + b];
+    snq::Nodes nd = snq::generate(t, bm.data(), Lb.data());
+    const int nb = 1 << t;
+    CU(cudaMemcpyAsync(s->eta_dev, nd.eta.data(), nd.eta.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->w_dev, nd.w.data(), nd.w.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->masses_dev, nd.masses.data(), nb * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->group_dev, nd.group_begin.data(), (nb + 1) * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->hbase_dev, &nd.entropy, sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));   // nd lives in pageable host memory
     return ITAL_OK;
 }
 
 // Score the rows in the worklist.  `items_hint` bounds the number of items (the true count is on the device);
 // few items -> one 256-thread block per candidate (latency), many -> one warp per candidate (throughput).
 int launch_eval(ital_shard* s, int64_t items_hint, bool block_per_candidate) {
-    const int t = s->t;
     const int threads = 256;
-    int blocks = grid_for(s, std::max<int64_t>(1, items_hint), block_per_candidate ? 1 : threads / 32, 8);
-    const double flag_var = 100.0 * s->noise;
-    const int force_block = block_per_candidate ? 1 : 0;
-#define ITAL_EVAL_ARGS                                                                                      \
-    s->counters, s->worklist, t, s->m, s->v, s->U, s->ldu, s->W, s->eta_dev, s->w_dev, s->n_nodes, s->group_dev, \
-        s->masses_dev, s->h_base, s->log1p_eps, flag_var, s->score, s->gain, s->counters + 1, s->counters + 2,  \
-        force_block
-    if (t == 1) k_eval<1><<<blocks, threads, 0, s->stream>>>(ITAL_EVAL_ARGS);
-    else if (t == 2) k_eval<2><<<blocks, threads, 0, s->stream>>>(ITAL_EVAL_ARGS);
-    else if (t == 3) k_eval<3><<<blocks, threads, 0, s->stream>>>(ITAL_EVAL_ARGS);
-    else k_eval<0><<<blocks, threads, 0, s->stream>>>(ITAL_EVAL_ARGS);
-#undef ITAL_EVAL_ARGS
+    const int blocks = grid_for(s, std::max<int64_t>(1, items_hint), block_per_candidate ? 1 : threads / 32, 8);
+    EvalArgs a;
+    a.count = s->counters;
+    a.list = s->worklist;
+    a.m = s->m;
+    a.v = s->v;
+    a.U = s->U;
+    a.ldu = s->ldu;
+    a.W0 = s->W;
+    a.eta = s->eta_dev;
+    a.w = s->w_dev;
+    a.orth = s->orth_dev;
+    a.group_begin = s->group_dev;
+    a.n_nodes = s->n_nodes;
+    a.masses = s->masses_dev;
+    a.h_base = s->hbase_dev;
+    a.log1p_eps = s->log1p_eps;
+    a.flag_var = 100.0 * s->noise;
+    a.score = s->score;
+    a.gain = s->gain;
+    a.n_flagged = s->counters + 1;
+    a.n_scored = s->counters + 2;
+    a.force_block = block_per_candidate ? 1 : 0;
+    a.t = s->t;
+    if (s->t == 1) k_eval<1><<<blocks, threads, 0, s->stream>>>(a);
+    else if (s->t == 2) k_eval<2><<<blocks, threads, 0, s->stream>>>(a);
+    else if (s->t == 3) k_eval<3><<<blocks, threads, 0, s->stream>>>(a);
+    else k_eval_sorted<<<blocks, threads, 0, s->stream>>>(a);
     s->launches++;
     CU(cudaGetLastError());
+    return ITAL_OK;
+}
+
+// The local candidates of the current greedy step -> record of the local best in DEVICE memory `rec_out`.
+// Nothing here waits for the GPU (t <= 3).
+int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_out) {
+    if (s->t >= kMaxBatch) return fail(ITAL_EINVAL, "batches of more than %d samples are not supported", kMaxBatch);
+    const int blocks = std::min(kArgmaxBlocks, grid_for(s, s->n, 256));
+    CU(cudaMemsetAsync(s->counters, 0, 4 * sizeof(int), s->stream));
+    if (s->t == 0) {
+        k_score0<<<blocks, 256, 0, s->stream>>>(s->n, s->m, s->v, s->mask, s->score, s->gain, s->block_best, s->log1p_eps); s->launches++;
+        k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, blocks, s->best); s->launches++;
+        CU(cudaGetLastError());
+        s->n_nodes = 1;
+    } else {
+        int rc = prepare_nodes(s);
+        if (rc) return rc;
+        if (exhaustive) {
+            k_fill<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->score, s->n, std::numeric_limits<double>::quiet_NaN()); s->launches++;
+            k_worklist<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->n, s->mask, s->gain, s->thr_dev, 1,
+                                                                        s->counters, s->worklist); s->launches++;
+            CU(cudaGetLastError());
+            rc = launch_eval(s, s->n, false);
+            if (rc) return rc;
+            const int lb = std::min(kArgmaxBlocks, grid_for(s, s->n, 256));
+            k_argmax_list<<<lb, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->block_best); s->launches++;
+            k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, lb, s->best); s->launches++;
+        } else {
+            // stage A: a spread sample of the most promising rows -- the maximum of the bound within each of
+            // 2 x #SM strided subsets of the pool -- is scored first, one block per row.  (Taking the global
+            // top rows by bound instead is worse: they cluster around the previous pick, whose neighbours have
+            // just lost their gain; measured 882 vs 399 rows left for stage B at t = 3 on SYN-1M.)
+            const int ba = std::min(kArgmaxBlocks, std::min(blocks, 2 * s->num_sms));
+            k_argmax_rows<<<ba, 256, 0, s->stream>>>(s->n, s->gain, s->mask, s->block_best, s->score); s->launches++;
+            k_list_from_blocks<<<1, 512, 0, s->stream>>>(s->block_best, ba, s->counters, s->worklist); s->launches++;
+            CU(cudaGetLastError());
+            rc = launch_eval(s, ba, true);
+            if (rc) return rc;
+            k_argmax_list<<<1, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->best + 1); s->launches++;
+            // stage B: every row whose bound still reaches the best exact score of stage A
+            CU(cudaMemsetAsync(s->counters, 0, sizeof(int), s->stream));
+            k_threshold_from_best<<<1, 1, 0, s->stream>>>(s->best + 1, s->hbase_dev, floor_score, kPruneMargin, s->thr_dev); s->launches++;
+            k_worklist<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->n, s->mask, s->gain, s->thr_dev, 0,
+                                                                        s->counters, s->worklist); s->launches++;
+            CU(cudaGetLastError());
+            rc = launch_eval(s, (int64_t)s->num_sms * 16, false);
+            if (rc) return rc;
+            k_argmax_list<<<1, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->best); s->launches++;
+        }
+        CU(cudaGetLastError());
+    }
+    k_save_counters<<<1, 32, 0, s->stream>>>(s->counters, s->stats_dev + 4 * s->t); s->launches++;
+    s->step_nodes[s->t] = (double)s->n_nodes;
+    s->proposals = s->t + 1;
+    return make_record(s, -1, rec_out);
+}
+
+// np.argmax over `n_records` proposals in device memory + append; with `extend` the streaming pass follows.
+int commit_dev(ital_shard* s, const double* recs_dev, int n_records, int extend) {
+    if (s->t >= kMaxBatch) return fail(ITAL_EINVAL, "batches of more than %d samples are not supported", kMaxBatch);
+    k_pick_winner<<<1, 256, 0, s->stream>>>(recs_dev, n_records, record_doubles(s), s->t, s->W, s->rec_in_dev,
+                                            s->base_m_dev, s->base_L_dev, s->sel_dev); s->launches++;
+    CU(cudaGetLastError());
+    if (extend) {
+        const int col = s->W + s->t;
+        int rc = s->x_dtype == ITAL_F32 ? launch_extend_t<float>(s, col, 0, 0.0, kSelected)
+                                        : launch_extend_t<double>(s, col, 0, 0.0, kSelected);
+        if (rc) return rc;
+    }
+    s->t += 1;
     return ITAL_OK;
 }
 
@@ -298,12 +410,15 @@ void free_all(ital_shard* s) {
     cudaSetDevice(s->device);
     void* ptrs[] = {s->X, s->sqn, s->m, s->v, s->U, s->gain, s->score, s->mask, s->worklist, s->counters,
                     s->block_best, s->best, s->thr_dev, s->rec_dev, s->rec_in_dev, s->idx_dev, s->eta_dev,
-                    s->w_dev, s->masses_dev, s->group_dev, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev};
+                    s->w_dev, s->masses_dev, s->group_dev, s->orth_dev, s->gl_dev, s->base_m_dev, s->base_L_dev, s->sel_dev,
+                    s->hbase_dev, s->stats_dev, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->rec_host) cudaFreeHost(s->rec_host);
     if (s->rec_in_host) cudaFreeHost(s->rec_in_host);
     if (s->nodes_host) cudaFreeHost(s->nodes_host);
+    if (s->sel_host) cudaFreeHost(s->sel_host);
+    if (s->stats_host) cudaFreeHost(s->stats_host);
 }
 
 int reset_model(ital_shard* s) {
@@ -316,8 +431,6 @@ int reset_model(ital_shard* s) {
     s->lab_sqn.clear();
     s->lab_y.clear();
     s->lab_idx.clear();
-    s->base_m.clear();
-    s->base_L.clear();
     s->selected.clear();
     s->restricted.clear();
     s->lab_dev_valid = false;
@@ -391,6 +504,27 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
         CU(cudaMalloc(&s->block_best, kArgmaxBlocks * sizeof(Best)));
         CU(cudaMalloc(&s->best, 2 * sizeof(Best)));
         CU(cudaMalloc(&s->thr_dev, sizeof(double)));
+        CU(cudaMalloc(&s->base_m_dev, 16 * sizeof(double)));
+        CU(cudaMalloc(&s->base_L_dev, 16 * 16 * sizeof(double)));
+        CU(cudaMalloc(&s->sel_dev, 32 * sizeof(double)));
+        CU(cudaMalloc(&s->hbase_dev, sizeof(double)));
+        CU(cudaMemset(s->hbase_dev, 0, sizeof(double)));
+        CU(cudaMalloc(&s->masses_dev, 1024 * sizeof(double)));
+        CU(cudaMalloc(&s->group_dev, 1025 * sizeof(int)));
+        CU(cudaMalloc(&s->stats_dev, 16 * 4 * sizeof(int)));
+        CU(cudaMallocHost(&s->sel_host, 32 * sizeof(double)));
+        CU(cudaMallocHost(&s->stats_host, 16 * 4 * sizeof(int)));
+        {   // Gauss-Legendre tables for every order the panel split can ask for
+            const snq::GaussLegendre& G = snq::gl();
+            std::vector<double> tab((size_t)2 * (snq::kMaxOrder + 1) * 64, 0.0);
+            for (int nn = 1; nn <= snq::kMaxOrder; ++nn)
+                for (int i = 0; i < nn; ++i) {
+                    tab[(size_t)nn * 64 + i] = G.x[nn][i];
+                    tab[(size_t)(snq::kMaxOrder + 1) * 64 + (size_t)nn * 64 + i] = G.w[nn][i];
+                }
+            CU(cudaMalloc(&s->gl_dev, tab.size() * sizeof(double)));
+            CU(cudaMemcpy(s->gl_dev, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
         int r = ensure_width(s, 32);
         if (r) return r;
         const int blocks = grid_for(s, s->n, 8);
@@ -557,13 +691,42 @@ int ital_fetch_begin(ital_shard* s, double label_prob, double mistake_prob) {
         int rc = ital_fetch_end(s);
         if (rc) return rc;
     }
+    // room for the batch's projection columns up front: the record layout stays fixed during the fetch
+    int rc = ensure_width(s, s->W + kMaxBatch + 1);
+    if (rc) return rc;
+    rc = ensure_record_buffers(s, 1);
+    if (rc) return rc;
     s->fetching = true;
     s->t = 0;
-    s->base_m.clear();
-    s->base_L.clear();
+    s->proposals = 0;
     s->selected.clear();
     s->label_prob = label_prob;
     s->mistake_prob = mistake_prob;
+    return ITAL_OK;
+}
+
+int ital_fetch_propose_dev(ital_shard* s, double floor_score, int exhaustive, double* record_dev) {
+    if (!s || !record_dev) return fail(ITAL_EINVAL, "ital_fetch_propose_dev: bad arguments");
+    if (!s->fetching) return fail(ITAL_ESTATE, "ital_fetch_propose_dev outside a fetch");
+    CU(cudaSetDevice(s->device));
+    return propose_dev(s, floor_score, exhaustive, record_dev);
+}
+
+int ital_fetch_commit_dev(ital_shard* s, const double* records_dev, int n_records, int extend) {
+    if (!s || !records_dev || n_records < 1) return fail(ITAL_EINVAL, "ital_fetch_commit_dev: bad arguments");
+    if (!s->fetching) return fail(ITAL_ESTATE, "ital_fetch_commit_dev outside a fetch");
+    CU(cudaSetDevice(s->device));
+    return commit_dev(s, records_dev, n_records, extend);
+}
+
+static int read_step_stats(ital_shard* s, int step) {
+    // (after a synchronisation) diagnostics of propose number `step`
+    const int* c = s->stats_host + 4 * step;
+    for (double& x : s->stats) x = 0.0;
+    s->stats[0] = (double)c[0];                         // rows in the final worklist
+    s->stats[1] = step == 0 ? -1.0 : (double)c[2];      // rows scored by quadrature (-1: closed form for all)
+    s->stats[2] = s->step_nodes[step];
+    s->stats[4] = (double)c[1];
     return ITAL_OK;
 }
 
@@ -571,73 +734,18 @@ int ital_fetch_propose(ital_shard* s, double floor_score, int exhaustive, double
     if (!s || !record) return fail(ITAL_EINVAL, "ital_fetch_propose: bad arguments");
     if (!s->fetching) return fail(ITAL_ESTATE, "ital_fetch_propose outside a fetch");
     CU(cudaSetDevice(s->device));
-    int rc = ensure_record_buffers(s, 1);
+    const int step = s->t;
+    int rc = propose_dev(s, floor_score, exhaustive, s->rec_dev);
     if (rc) return rc;
-    const int blocks = std::min(kArgmaxBlocks, grid_for(s, s->n, 256));
-    CU(cudaMemsetAsync(s->counters, 0, 4 * sizeof(int), s->stream));
-    for (double& x : s->stats) x = 0.0;
-    if (s->t == 0) {
-        k_score0<<<blocks, 256, 0, s->stream>>>(s->n, s->m, s->v, s->mask, s->score, s->gain, s->block_best, s->log1p_eps); s->launches++;
-        k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, blocks, s->best); s->launches++;
-        CU(cudaGetLastError());
-        s->h_base = 0.0;
-        s->n_nodes = 1;
-    } else {
-        if (s->t > 10) return fail(ITAL_EINVAL, "batches of more than 11 samples are not supported");
-        // shared nodes of this step from the base selected so far
-        std::vector<double> Lb((size_t)s->t * s->t, 0.0);
-        for (int a = 0; a < s->t; ++a)
-            for (int b = 0; b <= a; ++b) Lb[(size_t)a * s->t + b] = s->base_L[a][b];
-        snq::Nodes nd = snq::generate(s->t, s->base_m.data(), Lb.data());
-        rc = upload_nodes(s, nd);
-        if (rc) return rc;
-        if (exhaustive) {
-            k_fill<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->score, s->n, std::numeric_limits<double>::quiet_NaN()); s->launches++;
-            k_worklist<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->n, s->mask, s->gain, s->thr_dev, 1,
-                                                                        s->counters, s->worklist); s->launches++;
-            CU(cudaGetLastError());
-            rc = launch_eval(s, s->n, false);
-            if (rc) return rc;
-            const int lb = std::min(kArgmaxBlocks, grid_for(s, s->n, 256));
-            k_argmax_list<<<lb, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->block_best); s->launches++;
-            k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, lb, s->best); s->launches++;
-        } else {
-            // stage A: a spread sample of the most promising rows -- the maximum of the bound within each of
-            // 2 x #SM strided subsets of the pool -- is scored first, one block per row.  (Taking the global
-            // top rows by bound instead is worse: they cluster around the previous pick, whose neighbours have
-            // just lost their gain; measured 882 vs 399 rows left for stage B at t = 3 on SYN-1M.)
-            const int ba = std::min(kArgmaxBlocks, std::min(blocks, 2 * s->num_sms));
-            k_argmax_rows<<<ba, 256, 0, s->stream>>>(s->n, s->gain, s->mask, s->block_best, s->score); s->launches++;
-            k_list_from_blocks<<<1, 512, 0, s->stream>>>(s->block_best, ba, s->counters, s->worklist); s->launches++;
-            CU(cudaGetLastError());
-            rc = launch_eval(s, ba, true);
-            if (rc) return rc;
-            k_argmax_list<<<1, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->best + 1); s->launches++;
-            // stage B: every row whose bound still reaches the best exact score of stage A
-            CU(cudaMemsetAsync(s->counters, 0, sizeof(int), s->stream));
-            k_threshold_from_best<<<1, 1, 0, s->stream>>>(s->best + 1, s->h_base, floor_score, kPruneMargin, s->thr_dev); s->launches++;
-            k_worklist<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->n, s->mask, s->gain, s->thr_dev, 0,
-                                                                        s->counters, s->worklist); s->launches++;
-            CU(cudaGetLastError());
-            rc = launch_eval(s, (int64_t)s->num_sms * 16, false);
-            if (rc) return rc;
-            k_argmax_list<<<1, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->best); s->launches++;
-        }
-        CU(cudaGetLastError());
-    }
-    rc = make_record(s, -1, s->rec_dev);
-    if (rc) return rc;
-    int cnt[4] = {0, 0, 0, 0};
     const int64_t rl = record_doubles(s);
+    double hb = 0.0;
     CU(cudaMemcpyAsync(s->rec_host, s->rec_dev, (size_t)rl * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(cnt, s->counters, sizeof cnt, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(s->stats_host, s->stats_dev, 16 * 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(&hb, s->hbase_dev, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     memcpy(record, s->rec_host, (size_t)rl * sizeof(double));
-    s->stats[0] = (double)cnt[0];                       // rows in the final worklist
-    s->stats[1] = s->t == 0 ? -1.0 : (double)cnt[2];    // rows scored by quadrature (-1: closed form for all)
-    s->stats[2] = (double)s->n_nodes;
-    s->stats[3] = s->h_base;
-    s->stats[4] = (double)cnt[1];
+    read_step_stats(s, step);
+    s->stats[3] = step == 0 ? 0.0 : hb;
     return ITAL_OK;
 }
 
@@ -646,32 +754,28 @@ int ital_fetch_commit(ital_shard* s, const double* record) {
     if (!s->fetching) return fail(ITAL_ESTATE, "ital_fetch_commit outside a fetch");
     if (record[0] < 0) return fail(ITAL_EINVAL, "ital_fetch_commit: empty record");
     CU(cudaSetDevice(s->device));
-    const int64_t g = (int64_t)record[0];
-    const int col = s->W + s->t;
-    const int64_t old_cap = s->w_cap;
-    std::vector<double> u(record + ITAL_RECORD_HEADER, record + ITAL_RECORD_HEADER + col);
-    std::vector<double> x(record + ITAL_RECORD_HEADER + old_cap, record + ITAL_RECORD_HEADER + old_cap + s->d);
-    double hdr[ITAL_RECORD_HEADER];
-    memcpy(hdr, record, sizeof hdr);
-    int rc = ensure_width(s, col + 1);
-    if (rc) return rc;
-    std::vector<double> rec((size_t)record_doubles(s), 0.0);
-    memcpy(rec.data(), hdr, sizeof hdr);
-    std::copy(u.begin(), u.end(), rec.begin() + ITAL_RECORD_HEADER);
-    std::copy(x.begin(), x.end(), rec.begin() + ITAL_RECORD_HEADER + s->w_cap);
-    // new row of the Cholesky factor of the batch's posterior covariance: [l_0 .. l_{t-1}, sqrt(cond. var)]
-    double cv = hdr[3];
-    if (!(cv > 1e-300)) cv = 1e-300;
-    const double piv = std::sqrt(cv);
-    std::vector<double> row(u.begin() + s->W, u.end());
-    row.push_back(piv);
-    rc = extend_with_record(s, rec.data(), col, 0, 0.0, true);
-    if (rc) return rc;
-    s->base_m.push_back(hdr[2]);
-    s->base_L.push_back(row);
-    s->selected.push_back(g);
-    s->t += 1;
-    return ITAL_OK;
+    // through pinned staging into the device buffer the winner is picked from (a list of one)
+    const int64_t rl = record_doubles(s);
+    memcpy(s->rec_in_host, record, (size_t)rl * sizeof(double));
+    CU(cudaMemcpyAsync(s->rec_dev, s->rec_in_host, (size_t)rl * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    return commit_dev(s, s->rec_dev, 1, 1);
+}
+
+int ital_fetch_result(ital_shard* s, int max_out, int64_t* out_idx, double* out_scores) {
+    if (!s || max_out < 0 || (max_out > 0 && !out_idx)) return fail(ITAL_EINVAL, "ital_fetch_result: bad arguments");
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpyAsync(s->sel_host, s->sel_dev, 32 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(s->stats_host, s->stats_dev, 16 * 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    int got = 0;
+    for (int k = 0; k < s->t && k < max_out; ++k) {
+        if (s->sel_host[2 * k] < 0) break;      // no candidate was left at that step
+        out_idx[got] = (int64_t)s->sel_host[2 * k];
+        if (out_scores) out_scores[got] = s->sel_host[2 * k + 1];
+        ++got;
+    }
+    if (s->proposals > 0) read_step_stats(s, s->proposals - 1);
+    return got;
 }
 
 int ital_fetch_end(ital_shard* s) {
@@ -683,30 +787,24 @@ int ital_fetch_end(ital_shard* s) {
     }
     s->fetching = false;
     s->t = 0;
-    s->base_m.clear();
-    s->base_L.clear();
     return ITAL_OK;
 }
 
 int ital_fetch(ital_shard* s, int k, double label_prob, double mistake_prob, int exhaustive, int64_t* out_idx,
                double* out_scores) {
     if (!s || k < 0 || (k > 0 && !out_idx)) return fail(ITAL_EINVAL, "ital_fetch: bad arguments");
+    if (k > kMaxBatch) return fail(ITAL_EINVAL, "batches of more than %d samples are not supported", kMaxBatch);
     int rc = ital_fetch_begin(s, label_prob, mistake_prob);
     if (rc) return rc;
-    std::vector<double> rec;
+    // the whole greedy loop is enqueued without waiting for the GPU; one read-back at the end
+    for (int it = 0; it < k && rc == ITAL_OK; ++it) {
+        rc = propose_dev(s, -std::numeric_limits<double>::infinity(), exhaustive, s->rec_dev);
+        if (rc == ITAL_OK) rc = commit_dev(s, s->rec_dev, 1, it + 1 < k);
+    }
     int got = 0;
-    for (int it = 0; it < k; ++it) {
-        rec.assign((size_t)record_doubles(s), 0.0);
-        rc = ital_fetch_propose(s, -std::numeric_limits<double>::infinity(), exhaustive, rec.data());
-        if (rc) break;
-        if (rec[0] < 0) break;   // no candidates left (k is clamped to the number of unseen rows, ital.py:99-100)
-        out_idx[got] = (int64_t)rec[0];
-        if (out_scores) out_scores[got] = rec[1];
-        ++got;
-        if (it + 1 < k) {
-            rc = ital_fetch_commit(s, rec.data());
-            if (rc) break;
-        }
+    if (rc == ITAL_OK) {
+        got = ital_fetch_result(s, k, out_idx, out_scores);
+        if (got < 0) rc = got;
     }
     int rc2 = ital_fetch_end(s);
     if (rc) return rc;

@@ -118,6 +118,7 @@ k_extend(const XT* __restrict__ X, int64_t n, int d, int d_pad, const double* __
     double* ur_s = smem + (size_t)nwarp_blk * 32 * 33;  // [W]
     double* z_s = ur_s + ((W + 1) & ~1);                // [d_pad] only when NC == 0
     // the new point comes as a device-resident point record (header, projection, row as float64)
+    if (rec[0] < 0.0) return;                           // empty record (no candidate was left): nothing to extend
     const double* ur = rec + 8;
     const double* z = rec + 8 + w_cap;
     if (mark_bits != 0 && blockIdx.x == 0 && threadIdx.x == 0) {    // the chosen row leaves the candidate set
@@ -364,11 +365,11 @@ __global__ void __launch_bounds__(256) k_argmax_final(const Best* __restrict__ b
 }
 
 // Stage B threshold: a row can still win only if gain_i + H(base) >= best exact score so far - margin.
-__global__ void k_threshold_from_best(const Best* __restrict__ best, double h_base, double floor_score,
-                                      double margin, double* __restrict__ thr_gain) {
+__global__ void k_threshold_from_best(const Best* __restrict__ best, const double* __restrict__ h_base,
+                                      double floor_score, double margin, double* __restrict__ thr_gain) {
     double thr = floor_score;
     if (best->idx >= 0 && best->score == best->score) thr = fmax(thr, best->score);
-    *thr_gain = thr - margin - h_base;
+    *thr_gain = thr - margin - *h_base;
 }
 
 // Lazy-greedy worklist: candidate rows whose upper bound gain_i reaches *thr_gain (a device scalar prepared by
@@ -394,99 +395,306 @@ __global__ void __launch_bounds__(256) k_worklist(int64_t n, const uint8_t* __re
     }
 }
 
-// Exact MI of one candidate per team of threads (a warp, or the whole 256-thread block when few
-// candidates are left and latency matters) with the shared nodes of the step (t >= 1 base variables):
-//   P(r_base, +) = sum_{q in group r_base} w_q * Phi((m_i + l_i . eta_q) / s_i),  P(r_base, -) = P(r_base) - P(+)
+// Exact MI of one candidate per team of threads (a warp, or the whole 256-thread block when few candidates are
+// left and latency matters) with the shared nodes of the step (t >= 1 base variables):
+//   P(r_base, +) = sum_{q in orthant r_base} w_q * Phi((m_i + l_i . eta_q) / s_i),  P(r_base, -) = P(r_base) - P(+)
 //   score = sum_r p_r * (log(1 + eps) - log(p_r + eps))
 // Replaces 2^(t+1) calls of prob_rel + updated_prob_rel per candidate (ital/ital.py:193-219).  The reduction
 // order is fixed, so identical rows get bit-identical scores.  Rows already scored in this step are skipped.
-template <int T>   // T = t if 1..3 (unrolled), 0 = run time
-__global__ void __launch_bounds__(256) k_eval(const int* __restrict__ count, const int* __restrict__ list, int t_rt,
-                                              const double* __restrict__ m, const double* __restrict__ v,
-                                              const double* __restrict__ U, int64_t ldu, int W0,
-                                              const double* __restrict__ eta, const double* __restrict__ w,
-                                              int64_t n_nodes, const int* __restrict__ group_begin,
-                                              const double* __restrict__ masses, double h_base,
-                                              double log1p_eps, double flag_var,
-                                              double* __restrict__ score, double* __restrict__ gain,
-                                              int* __restrict__ n_flagged, int* __restrict__ n_scored,
-                                              int force_block) {
-    constexpr int MAXT = T > 0 ? T : 10;
-    const int t = T > 0 ? T : t_rt;
-    const int lane = threadIdx.x & 31;
-    const int n_items = *count;
-    // team size: a warp per candidate when there are enough candidates to keep every warp busy, otherwise the
-    // whole block works on one candidate (the node loop is latency-bound for a lone warp)
-    const int TPC = (force_block || n_items < (int)(gridDim.x * (blockDim.x >> 5))) ? (int)blockDim.x : 32;
+//
+// k_eval<T>, T = 1..3: nodes in generation order with their orthant id (k_snq_generate), 2^T accumulators per
+// thread.  k_eval_sorted: any t, nodes sorted by orthant on the host (t >= 4).
+struct EvalArgs {
+    const int* count;
+    const int* list;
+    const double* m;
+    const double* v;
+    const double* U;
+    int64_t ldu;
+    int W0;
+    const double* eta;          // [t][n_nodes]
+    const double* w;
+    const int* orth;            // k_eval<T>: orthant id per node
+    const int* group_begin;     // k_eval_sorted: 2^t + 1 offsets
+    int64_t n_nodes;
+    const double* masses;       // 2^t base orthant probabilities (device)
+    const double* h_base;       // score of the base alone (device scalar)
+    double log1p_eps;
+    double flag_var;
+    double* score;
+    double* gain;
+    int* n_flagged;
+    int* n_scored;
+    int force_block;
+    int t;
+};
+
+__device__ __forceinline__ int eval_team_size(int n_items, int force_block) {
+    // a warp per candidate when there are enough candidates to keep every warp busy, otherwise the whole block
+    // works on one candidate (the node loop is latency-bound for a lone warp)
+    return (force_block || n_items < (int)(gridDim.x * (blockDim.x >> 5))) ? (int)blockDim.x : 32;
+}
+
+__device__ __forceinline__ double team_sum(double acc, int TPC, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (TPC > 32) {
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        acc = 0.0;
+        for (int k = 0; k < TPC / 32; ++k) acc += red[k];
+    }
+    return acc;
+}
+
+template <int T>
+__global__ void __launch_bounds__(256) k_eval(EvalArgs a) {
+    constexpr int NB = 1 << T;
+    const int n_items = *a.count;
+    const int TPC = eval_team_size(n_items, a.force_block);
     const int tid_team = threadIdx.x % TPC;
     const int team_global = (blockIdx.x * blockDim.x + threadIdx.x) / TPC;
     const int teams_total = (gridDim.x * blockDim.x) / TPC;
+    const int64_t N = a.n_nodes;
     __shared__ double red[8];
     for (int item = team_global; item < n_items; item += teams_total) {
-        const int64_t i = list[item];
-        if (score[i] == score[i]) continue;             // scored earlier in this step (team-uniform)
+        const int64_t i = a.list[item];
+        if (a.score[i] == a.score[i]) continue;         // scored earlier in this step (team-uniform)
+        double l[T];
+        double s2 = a.v[i];
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+            l[j] = a.U[(int64_t)(a.W0 + j) * a.ldu + i];
+            s2 = fma(-l[j], l[j], s2);
+        }
+        const double mi = a.m[i];
+        const double s = s2 > 0.0 ? sqrt(s2) : 0.0;
+        const double inv_s = s > 0.0 ? 1.0 / s : 0.0;
+        double acc[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) acc[b] = 0.0;
+        // four nodes per thread and trip: independent erfc chains hide the FP64 latency
+        for (int64_t q = tid_team; q < N; q += 4 * TPC) {
+            double num[4], ww[4];
+            int ob[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t qq = q + (int64_t)u * TPC;
+                const bool ok = qq < N;
+                ww[u] = ok ? a.w[qq] : 0.0;
+                ob[u] = ok ? a.orth[qq] : 0;
+                num[u] = mi;
+#pragma unroll
+                for (int j = 0; j < T; ++j) num[u] = fma(l[j], ok ? a.eta[(int64_t)j * N + qq] : 0.0, num[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double cdf = s > 0.0 ? phi_cdf(num[u] * inv_s) : (num[u] > 0.0 ? 1.0 : 0.0);
+                const double term = ww[u] * cdf;
+#pragma unroll
+                for (int b = 0; b < NB; ++b) acc[b] += (ob[u] == b) ? term : 0.0;
+            }
+        }
+        double sc = 0.0;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const double p_plus = team_sum(acc[b], TPC, red);
+            const double p_minus = fmax(a.masses[b] - p_plus, 0.0);
+            sc += mi_term(p_plus, a.log1p_eps) + mi_term(p_minus, a.log1p_eps);
+        }
+        if (TPC > 32) __syncthreads();                  // every thread has read score[i] before it is written
+        if (tid_team == 0) {
+            a.score[i] = sc;
+            a.gain[i] = sc - *a.h_base;
+            atomicAdd(a.n_scored, 1);
+            if (s2 < a.flag_var) atomicAdd(a.n_flagged, 1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_eval_sorted(EvalArgs a) {
+    constexpr int MAXT = 10;
+    const int t = a.t;
+    const int n_items = *a.count;
+    const int TPC = eval_team_size(n_items, a.force_block);
+    const int tid_team = threadIdx.x % TPC;
+    const int team_global = (blockIdx.x * blockDim.x + threadIdx.x) / TPC;
+    const int teams_total = (gridDim.x * blockDim.x) / TPC;
+    const int64_t N = a.n_nodes;
+    __shared__ double red[8];
+    for (int item = team_global; item < n_items; item += teams_total) {
+        const int64_t i = a.list[item];
+        if (a.score[i] == a.score[i]) continue;
         double l[MAXT];
-        double s2 = v[i];
+        double s2 = a.v[i];
 #pragma unroll
         for (int j = 0; j < MAXT; ++j) {
             l[j] = 0.0;
             if (j < t) {
-                l[j] = U[(int64_t)(W0 + j) * ldu + i];
+                l[j] = a.U[(int64_t)(a.W0 + j) * a.ldu + i];
                 s2 = fma(-l[j], l[j], s2);
             }
         }
-        const double mi = m[i];
+        const double mi = a.m[i];
         const double s = s2 > 0.0 ? sqrt(s2) : 0.0;
         const double inv_s = s > 0.0 ? 1.0 / s : 0.0;
         double sc = 0.0;
         const int nb = 1 << t;
         for (int b = 0; b < nb; ++b) {
-            const int g0 = group_begin[b], g1 = group_begin[b + 1];
-            // four nodes per thread and trip: independent erfc chains hide the FP64 latency
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            for (int q = g0 + tid_team; q < g1; q += 4 * TPC) {
-                double num[4], ww[4];
+            const int g0 = a.group_begin[b], g1 = a.group_begin[b + 1];
+            double acc = 0.0;
+            for (int q = g0 + tid_team; q < g1; q += TPC) {
+                double num = mi;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int qq = q + u * TPC;
-                    const bool ok = qq < g1;
-                    ww[u] = ok ? w[qq] : 0.0;
-                    num[u] = mi;
-#pragma unroll
-                    for (int j = 0; j < MAXT; ++j)
-                        if (j < t) num[u] = fma(l[j], ok ? eta[(int64_t)j * n_nodes + qq] : 0.0, num[u]);
-                }
-                double cdf[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    cdf[u] = s > 0.0 ? phi_cdf(num[u] * inv_s) : (num[u] > 0.0 ? 1.0 : 0.0);
-                a0 = fma(ww[0], cdf[0], a0);
-                a1 = fma(ww[1], cdf[1], a1);
-                a2 = fma(ww[2], cdf[2], a2);
-                a3 = fma(ww[3], cdf[3], a3);
+                for (int j = 0; j < MAXT; ++j)
+                    if (j < t) num = fma(l[j], a.eta[(int64_t)j * N + q], num);
+                const double cdf = s > 0.0 ? phi_cdf(num * inv_s) : (num > 0.0 ? 1.0 : 0.0);
+                acc = fma(a.w[q], cdf, acc);
             }
-            double acc = (a0 + a1) + (a2 + a3);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (TPC > 32) {
-                __syncthreads();
-                if (lane == 0) red[threadIdx.x >> 5] = acc;
-                __syncthreads();
-                acc = 0.0;
-                for (int k = 0; k < TPC / 32; ++k) acc += red[k];
-            }
-            const double p_plus = acc;
-            const double p_minus = fmax(masses[b] - acc, 0.0);
-            sc += mi_term(p_plus, log1p_eps) + mi_term(p_minus, log1p_eps);
+            const double p_plus = team_sum(acc, TPC, red);
+            const double p_minus = fmax(a.masses[b] - p_plus, 0.0);
+            sc += mi_term(p_plus, a.log1p_eps) + mi_term(p_minus, a.log1p_eps);
         }
-        if (TPC > 32) __syncthreads();                  // every thread has read score[i] before it is written
+        if (TPC > 32) __syncthreads();
         if (tid_team == 0) {
-            score[i] = sc;
-            gain[i] = sc - h_base;
-            atomicAdd(n_scored, 1);
-            if (s2 < flag_var) atomicAdd(n_flagged, 1);
+            a.score[i] = sc;
+            a.gain[i] = sc - *a.h_base;
+            atomicAdd(a.n_scored, 1);
+            if (s2 < a.flag_var) atomicAdd(a.n_flagged, 1);
         }
     }
+}
+
+// ---- shared quadrature nodes on the device (same rule as csrc/snq_host.h / oracle/orthant.py) ----------------
+constexpr int kBaseStride = 16;          // row stride of the batch's Cholesky factor in device memory
+constexpr int kGlStride = 64;            // Gauss-Legendre tables: rule n at [n * 64 .. n * 64 + n)
+
+// One thread per node; node index = sum_j digit_j (2q)^(t-1-j).  Every thread recomputes the boundary of each
+// dimension from its own prefix of coordinates (a handful of flops) instead of communicating.
+template <int T>
+__global__ void __launch_bounds__(256) k_snq_generate(int q, double R, int q_min, const double* __restrict__ base_m,
+                                                      const double* __restrict__ base_L,
+                                                      const double* __restrict__ gl_x, const double* __restrict__ gl_w,
+                                                      int64_t N, double* __restrict__ eta, double* __restrict__ w,
+                                                      int* __restrict__ orth) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    const int two_q = 2 * q;
+    double e[T];
+    double wt = 1.0;
+    int ob = 0;
+    int64_t rem = k, stride = N;
+#pragma unroll
+    for (int j = 0; j < T; ++j) {
+        stride /= two_q;
+        const int g = (int)(rem / stride);
+        rem -= (int64_t)g * stride;
+        double acc = base_m[j];
+#pragma unroll
+        for (int i = 0; i < T; ++i)
+            if (i < j) acc += e[i] * base_L[j * kBaseStride + i];
+        const double av = -acc / base_L[j * kBaseStride + j];
+        const double c = av < -R ? -R : (av > R ? R : av);
+        int n_lo = (int)floor(two_q * (c + R) / (2.0 * R) + 0.5);
+        n_lo = max(q_min, min(two_q - q_min, n_lo));
+        const int n_hi = two_q - n_lo;
+        double x, wg;
+        if (g < n_lo) {
+            const double half = 0.5 * (c + R);
+            x = -R + half * (1.0 + gl_x[n_lo * kGlStride + g]);
+            wg = half * gl_w[n_lo * kGlStride + g];
+        } else {
+            const double half = 0.5 * (R - c);
+            x = c + half * (1.0 + gl_x[n_hi * kGlStride + (g - n_lo)]);
+            wg = half * gl_w[n_hi * kGlStride + (g - n_lo)];
+            ob |= 1 << j;
+        }
+        wg *= exp(-0.5 * x * x) / 2.50662827463100050242;      // standard normal density
+        e[j] = x;
+        wt *= wg;
+        eta[(int64_t)j * N + k] = x;
+    }
+    w[k] = wt;
+    orth[k] = ob;
+}
+
+// Base orthant probabilities P_b = sum of the weights per orthant, and the score of the base alone
+// (one block, fixed summation order).
+__global__ void __launch_bounds__(1024) k_snq_masses(int t, int64_t N, const double* __restrict__ w,
+                                                     const int* __restrict__ orth, double log1p_eps,
+                                                     double* __restrict__ masses, double* __restrict__ h_base) {
+    __shared__ double part[32][8];
+    const int nb = 1 << t;                              // t <= 3 here
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t k = threadIdx.x; k < N; k += blockDim.x) {
+        const int ob = orth[k];
+        const double wk = w[k];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[b] += (ob == b) ? wk : 0.0;
+    }
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], o);
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5][b] = acc[b];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double h = 0.0;
+        for (int b = 0; b < nb; ++b) {
+            double p = 0.0;
+            for (int k = 0; k < (int)(blockDim.x >> 5); ++k) p += part[k][b];
+            masses[b] = p;
+            h += mi_term(p, log1p_eps);
+        }
+        *h_base = h;
+    }
+}
+
+// np.argmax over the shards' proposals + AppendedMutualInformation.append (ital/ital.py:130-131, 561-568): choose
+// the best of G point records (score desc, global row asc), make it the record k_extend will read, and append it
+// to the batch state kept on the device (mean, Cholesky row of the batch's posterior covariance, selection list).
+__global__ void __launch_bounds__(256) k_pick_winner(const double* __restrict__ recs, int G, int64_t rec_len, int t,
+                                                     int W, double* __restrict__ rec_in, double* __restrict__ base_m,
+                                                     double* __restrict__ base_L, double* __restrict__ sel) {
+    __shared__ int win_s;
+    if (threadIdx.x == 0) {
+        int win = -1;
+        for (int g = 0; g < G; ++g) {
+            const double idx = recs[g * rec_len], sc = recs[g * rec_len + 1];
+            if (idx < 0.0 || sc != sc) continue;
+            if (win < 0 || sc > recs[win * rec_len + 1] ||
+                (sc == recs[win * rec_len + 1] && idx < recs[win * rec_len]))
+                win = g;
+        }
+        win_s = win;
+    }
+    __syncthreads();
+    const int win = win_s;
+    if (win < 0) {
+        if (threadIdx.x == 0) {
+            rec_in[0] = -1.0;
+            rec_in[1] = -INFINITY;
+            sel[2 * t] = -1.0;
+            sel[2 * t + 1] = -INFINITY;
+        }
+        return;
+    }
+    const double* r = recs + (int64_t)win * rec_len;
+    for (int64_t k = threadIdx.x; k < rec_len; k += blockDim.x) rec_in[k] = r[k];
+    if (threadIdx.x == 0) {
+        base_m[t] = r[2];
+        for (int j = 0; j < t; ++j) base_L[t * kBaseStride + j] = r[8 + W + j];
+        base_L[t * kBaseStride + t] = sqrt(fmax(r[3], 1e-300));
+        sel[2 * t] = r[0];
+        sel[2 * t + 1] = r[1];
+    }
+}
+
+// keep the per-step counters for ital_fetch_stats
+__global__ void k_save_counters(const int* __restrict__ counters, int* __restrict__ dst) {
+    if (threadIdx.x < 4) dst[threadIdx.x] = counters[threadIdx.x];
 }
 
 // worklist = the per-block winners of an argmax stage (the most promising candidates, scored first)

@@ -55,6 +55,21 @@ class TorchComm(object):
         backend = dist.get_backend(group)
         self.device = torch.device('cuda', device if device is not None else torch.cuda.current_device()) \
             if backend == 'nccl' else torch.device('cpu')
+        self.on_device = self.device.type == 'cuda'
+        self._bufs = {}
+
+    def device_buffers(self, rec_len):
+        """(one record, world_size records) as float64 CUDA tensors, reused across fetches."""
+        if rec_len not in self._bufs:
+            self._bufs[rec_len] = (self._torch.zeros(rec_len, dtype=self._torch.float64, device=self.device),
+                                   self._torch.zeros(rec_len * self.world_size, dtype=self._torch.float64,
+                                                     device=self.device))
+        return self._bufs[rec_len]
+
+    def all_gather_device(self, out, rec):
+        """NCCL all-gather of device-resident records, ordered after the kernels that wrote `rec` and before
+        the kernels that read `out` (same CUDA stream semantics as any torch collective)."""
+        self._dist.all_gather_into_tensor(out, rec, group=self.group)
 
     def _t(self, a):
         return self._torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)

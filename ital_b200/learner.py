@@ -80,6 +80,20 @@ class _Shard(object):
     def fetch_end(self):
         _capi.check(self.lib.ital_fetch_end(self.handle))
 
+    def fetch_propose_dev(self, floor_score, exhaustive, dev_ptr):
+        _capi.check(self.lib.ital_fetch_propose_dev(self.handle, float(floor_score), int(bool(exhaustive)),
+                                                    ctypes.c_void_p(dev_ptr)))
+
+    def fetch_commit_dev(self, dev_ptr, n_records, extend):
+        _capi.check(self.lib.ital_fetch_commit_dev(self.handle, ctypes.c_void_p(dev_ptr), int(n_records),
+                                                   int(bool(extend))))
+
+    def fetch_result(self, k):
+        idx = np.zeros(max(k, 1), dtype=np.int64)
+        scores = np.zeros(max(k, 1))
+        got = _capi.check(self.lib.ital_fetch_result(self.handle, int(k), _capi.i64ptr(idx), _capi.dptr(scores)))
+        return idx[:got], scores[:got]
+
     def fetch(self, k, label_prob, mistake_prob, exhaustive):
         idx = np.zeros(max(k, 1), dtype=np.int64)
         scores = np.zeros(max(k, 1))
@@ -361,10 +375,31 @@ class ITAL(object):
                 idx, scores = self._shard.fetch(k, self.label_prob, self.mistake_prob, self.exhaustive)
                 self.last_fetch_scores = scores
                 return [int(i) for i in idx]
+            if getattr(self._comm, 'on_device', False) and not show_progress:
+                return self._fetch_device_loop(k)
             return self._fetch_stepwise(k, show_progress)
         finally:
             if restricted:
                 self._shard.restrict_candidates(None)
+
+    def _fetch_device_loop(self, k):
+        """Multi-GPU greedy loop with the records staying on the GPUs: per step one enqueue of the local
+        scoring, one NCCL all-gather of the shards' best records, one enqueue of winner pick + streaming pass.
+        The host never waits inside the loop; one read-back at the end."""
+        comm = self._comm
+        self._shard.fetch_begin(self.label_prob, self.mistake_prob)
+        try:
+            rl = self._shard.record_doubles()
+            rec, allrec = comm.device_buffers(rl)
+            for it in range(k):
+                self._shard.fetch_propose_dev(-np.inf, self.exhaustive, rec.data_ptr())
+                comm.all_gather_device(allrec, rec)
+                self._shard.fetch_commit_dev(allrec.data_ptr(), comm.world_size, it + 1 < k)
+            idx, scores = self._shard.fetch_result(k)
+        finally:
+            self._shard.fetch_end()
+        self.last_fetch_scores = scores
+        return [int(i) for i in idx]
 
     def _fetch_stepwise(self, k, show_progress=False, keep_scores=False):
         """The greedy loop with the per-step exchange made explicit (multi-GPU, progress bars, tests)."""
