@@ -65,10 +65,11 @@ def load():
     """dlopen the in-tree library and type its entry points.  Fails loudly when it has not been built."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get('ITAL_B200_LIB', LIB_PATH)     # (override: tuning experiments with variant builds)
+        if not os.path.exists(path):
             raise ItalError('%s is missing: build it with `python -m ital_b200.build` '
-                            '(or __graft_entry__.build()); this package has no CPU fallback' % LIB_PATH)
-        lib = ctypes.CDLL(LIB_PATH)
+                            '(or __graft_entry__.build()); this package has no CPU fallback' % path)
+        lib = ctypes.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)          # AttributeError if the library does not export the symbol
             fn.restype = res

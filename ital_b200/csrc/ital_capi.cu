@@ -178,7 +178,7 @@ int launch_extend_t(ital_shard* s, int W_used, int labelled, double y, uint8_t m
     const bool fixed = (nchunks == 1 || nchunks == 2 || nchunks == 4);
     size_t smem = ((size_t)warps * 32 * 33 + ((W_used + 1) & ~1) + (fixed ? 0 : s->d_pad)) * sizeof(double);
     const int64_t units = (s->n + 31) / 32;
-    int blocks = (int)std::min<int64_t>((units + warps - 1) / warps, (int64_t)s->num_sms * 2);
+    int blocks = (int)std::min<int64_t>((units + warps - 1) / warps, (int64_t)s->num_sms * ITAL_EXTEND_MINB);
     if (blocks < 1) blocks = 1;
     const double neg2ls2 = -2.0 * (s->ls * s->ls);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -23,6 +23,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// tuning knobs of the streaming pass (see profiles/: chosen by measurement on B200)
+#ifndef ITAL_EXTEND_RB
+#define ITAL_EXTEND_RB 4
+#endif
+#ifndef ITAL_EXTEND_MINB
+#define ITAL_EXTEND_MINB 2
+#endif
+
 namespace italk {
 
 constexpr int kWarp = 32;
@@ -103,13 +111,13 @@ __global__ void __launch_bounds__(256) k_sqnorm(const XT* __restrict__ X, int64_
 // lane l finishes row l -- so that the exp, the W-long projection and the stores run with all lanes busy and
 // coalesced against the column-major U.
 template <typename XT, int NC>   // NC: 16-byte chunks per lane and row (d_pad = NC * 32 * VN); 0 = run time
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, ITAL_EXTEND_MINB)
 k_extend(const XT* __restrict__ X, int64_t n, int d, int d_pad, const double* __restrict__ rec, int w_cap, int W,
          const double* __restrict__ sqn, double* __restrict__ U, int64_t ldu,
          double* __restrict__ m, double* __restrict__ v, int labelled, double y, double noise, double var,
          double neg2ls2, uint8_t* __restrict__ mask, int64_t row_offset, uint8_t mark_bits) {
     constexpr int VN = Vec<XT>::N;
-    constexpr int RB = 4;                               // rows in flight per warp
+    constexpr int RB = ITAL_EXTEND_RB;                  // rows in flight per warp
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
