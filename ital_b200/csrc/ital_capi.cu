@@ -225,15 +225,26 @@ int extend_with_record(ital_shard* s, const double* rec, int col, int labelled, 
     return launch_extend_t<double>(s, col, labelled, y, mark);
 }
 
+// additive constant of the scores of the running step for a user who mislabels with probability mistake_prob and
+// always answers (label_prob >= 1): every relevance configuration r keeps log(1 + eps) with probability
+// (1 - mp)^(t+1) and gets log(eps) otherwise (the updated orthant probability is 0 after a contradicting label), so
+// score = perfect-user score + (1 - (1 - mp)^(t+1)) * (log eps - log(1 + eps)) * sum_r p_r.
+double step_shift_coef(const ital_shard* s) {
+    if (!(s->mistake_prob > 0.0)) return 0.0;
+    const double c = std::pow(1.0 - s->mistake_prob, (double)(s->t + 1));
+    return (1.0 - c) * (std::log(1e-12) - s->log1p_eps);
+}
+
 int make_record(ital_shard* s, long long local_row, double* dst_dev) {
+    const double shift = local_row < 0 ? step_shift_coef(s) : 0.0;
     if (s->x_dtype == ITAL_F32)
         k_record<float><<<1, 256, 0, s->stream>>>(local_row, s->best, s->row_offset, (const float*)s->X, (int)s->d,
                                                   (int)s->d_pad, s->sqn, s->m, s->v, s->U, s->ldu, s->W,
-                                                  s->W + s->t, s->w_cap, s->gain, dst_dev);
+                                                  s->W + s->t, s->w_cap, s->gain, dst_dev, shift, s->hbase_dev);
     else
         k_record<double><<<1, 256, 0, s->stream>>>(local_row, s->best, s->row_offset, (const double*)s->X,
                                                    (int)s->d, (int)s->d_pad, s->sqn, s->m, s->v, s->U, s->ldu,
-                                                   s->W, s->W + s->t, s->w_cap, s->gain, dst_dev); s->launches++;
+                                                   s->W, s->W + s->t, s->w_cap, s->gain, dst_dev, shift, s->hbase_dev); s->launches++;
     CU(cudaGetLastError());
     return ITAL_OK;
 }
@@ -294,7 +305,9 @@ int prepare_nodes(ital_shard* s) {
     CU(cudaMemcpyAsync(s->w_dev, nd.w.data(), nd.w.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     CU(cudaMemcpyAsync(s->masses_dev, nd.masses.data(), nb * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     CU(cudaMemcpyAsync(s->group_dev, nd.group_begin.data(), (nb + 1) * sizeof(int), cudaMemcpyHostToDevice, s->stream));
-    CU(cudaMemcpyAsync(s->hbase_dev, &nd.entropy, sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    double hb[2] = {nd.entropy, 0.0};
+    for (double mval : nd.masses) hb[1] += mval;
+    CU(cudaMemcpyAsync(s->hbase_dev, hb, sizeof hb, cudaMemcpyHostToDevice, s->stream));
     CU(cudaStreamSynchronize(s->stream));   // nd lives in pageable host memory
     return ITAL_OK;
 }
@@ -507,8 +520,8 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
         CU(cudaMalloc(&s->base_m_dev, 16 * sizeof(double)));
         CU(cudaMalloc(&s->base_L_dev, 16 * 16 * sizeof(double)));
         CU(cudaMalloc(&s->sel_dev, 32 * sizeof(double)));
-        CU(cudaMalloc(&s->hbase_dev, sizeof(double)));
-        CU(cudaMemset(s->hbase_dev, 0, sizeof(double)));
+        CU(cudaMalloc(&s->hbase_dev, 2 * sizeof(double)));      // [0] H(base), [1] total quadrature mass
+        CU(cudaMemset(s->hbase_dev, 0, 2 * sizeof(double)));
         CU(cudaMalloc(&s->masses_dev, 1024 * sizeof(double)));
         CU(cudaMalloc(&s->group_dev, 1025 * sizeof(int)));
         CU(cudaMalloc(&s->stats_dev, 16 * 4 * sizeof(int)));
@@ -684,8 +697,9 @@ int ital_restrict_candidates(ital_shard* s, int64_t m, const int64_t* global_idx
 int ital_fetch_begin(ital_shard* s, double label_prob, double mistake_prob) {
     if (!s) return fail(ITAL_EINVAL, "null shard");
     if (s->W == 0) return fail(ITAL_ESTATE, "fetch before any labelled point or query (the reference fails here too: gp.K_inv is None)");
-    if (!(label_prob >= 1.0 && mistake_prob <= 0.0))
-        return fail(ITAL_EINVAL, "only the perfect-user feedback model (label_prob >= 1, mistake_prob <= 0) is implemented on the GPU path");
+    if (!(label_prob >= 1.0))
+        return fail(ITAL_EINVAL, "label_prob < 1 (users who skip samples) is not implemented on the GPU path");
+    if (!(mistake_prob >= 0.0 && mistake_prob <= 1.0)) return fail(ITAL_EINVAL, "mistake_prob must be in [0, 1]");
     CU(cudaSetDevice(s->device));
     if (s->fetching) {
         int rc = ital_fetch_end(s);
@@ -696,6 +710,9 @@ int ital_fetch_begin(ital_shard* s, double label_prob, double mistake_prob) {
     if (rc) return rc;
     rc = ensure_record_buffers(s, 1);
     if (rc) return rc;
+    const double hb0[2] = {0.0, 1.0};                   // first step: no base, total mass 1
+    memcpy(s->sel_host + 30, hb0, sizeof hb0);          // (pinned scratch at the tail of the selection mirror)
+    CU(cudaMemcpyAsync(s->hbase_dev, s->sel_host + 30, sizeof hb0, cudaMemcpyHostToDevice, s->stream));
     s->fetching = true;
     s->t = 0;
     s->proposals = 0;
@@ -741,7 +758,7 @@ int ital_fetch_propose(ital_shard* s, double floor_score, int exhaustive, double
     double hb = 0.0;
     CU(cudaMemcpyAsync(s->rec_host, s->rec_dev, (size_t)rl * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaMemcpyAsync(s->stats_host, s->stats_dev, 16 * 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(&hb, s->hbase_dev, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(&hb, s->hbase_dev, sizeof(double), cudaMemcpyDeviceToHost, s->stream));   // pageable: synchronous
     CU(cudaStreamSynchronize(s->stream));
     memcpy(record, s->rec_host, (size_t)rl * sizeof(double));
     read_step_stats(s, step);
@@ -827,7 +844,19 @@ static int copy_vec(ital_shard* s, const double* dev, double* out) {
 
 int ital_last_scores(ital_shard* s, double* out) {
     if (!s || !out) return fail(ITAL_EINVAL, "bad arguments");
-    return copy_vec(s, s->score, out);
+    int rc = copy_vec(s, s->score, out);
+    if (rc) return rc;
+    if (s->mistake_prob > 0.0 && s->proposals > 0) {    // same additive constant as the records carry
+        double hb[2];
+        CU(cudaMemcpy(hb, s->hbase_dev, sizeof hb, cudaMemcpyDeviceToHost));
+        const int t_saved = s->t;
+        s->t = s->proposals - 1;
+        const double shift = step_shift_coef(s) * hb[1];
+        s->t = t_saved;
+        for (int64_t i = 0; i < s->n; ++i)
+            if (out[i] == out[i]) out[i] += shift;
+    }
+    return ITAL_OK;
 }
 int ital_rel_mean(ital_shard* s, double* out) {
     if (!s || !out) return fail(ITAL_EINVAL, "bad arguments");

@@ -649,14 +649,16 @@ __global__ void __launch_bounds__(1024) k_snq_masses(int t, int64_t N, const dou
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double h = 0.0;
+        double h = 0.0, tot = 0.0;
         for (int b = 0; b < nb; ++b) {
             double p = 0.0;
             for (int k = 0; k < (int)(blockDim.x >> 5); ++k) p += part[k][b];
             masses[b] = p;
             h += mi_term(p, log1p_eps);
+            tot += p;
         }
-        *h_base = h;
+        h_base[0] = h;
+        h_base[1] = tot;                                // total mass (1 up to quadrature error)
     }
 }
 
@@ -750,9 +752,12 @@ __global__ void __launch_bounds__(256) k_record(long long row, const Best* __res
                                                 const double* __restrict__ sqn, const double* __restrict__ m,
                                                 const double* __restrict__ v, const double* __restrict__ U,
                                                 int64_t ldu, int W_lab, int W_tot, int w_cap,
-                                                const double* __restrict__ gain, double* __restrict__ rec) {
+                                                const double* __restrict__ gain, double* __restrict__ rec,
+                                                double shift_coef, const double* __restrict__ h_base) {
+    // shift_coef * (total mass): what a user who mislabels with probability mistake_prob adds to every score of
+    // the step (DESIGN.md "mistake_prob"); 0 for the perfect user
     double score = 0.0;
-    if (row < 0) { row = best->idx; score = best->score; }
+    if (row < 0) { row = best->idx; score = best->score + shift_coef * h_base[1]; }
     const int rec_len = 8 + w_cap + d;
     if (row < 0) {
         for (int k = threadIdx.x; k < rec_len; k += blockDim.x) rec[k] = k == 0 ? -1.0 : (k == 1 ? -INFINITY : 0.0);

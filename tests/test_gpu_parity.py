@@ -79,6 +79,26 @@ def test_golden_parity(name):
             assert gpu._fetch_stepwise(int(g['k'])) == ret
 
 
+def test_mistaken_user_golden_and_oracle():
+    """label_prob = 1, mistake_prob = 0.5 (configs/butterflies-aggressive.conf): the scores are the perfect-user
+    scores plus a per-step constant; compared with the reference golden and the oracle's literal double loop
+    at 1e-4 relative (both carry log(p' + 1e-12) terms with p' at round-off level, see tests/test_oracle_golden)."""
+    from oracle.ital_oracle import OracleITAL
+    g = load_golden('butterflies_aggressive_k3')
+    kw = dict(g['learner_kw'])
+    gpu = drive(_gpu_learner(g['X'], exhaustive=True, **kw), g)
+    ora = drive(OracleITAL(g['X'], **kw), g)
+    ret = gpu._fetch_stepwise(int(g['k']), keep_scores=True)
+    assert ret == g['ret'].tolist()
+    ora.fetch_unlabelled(int(g['k']), forced=ret)
+    for t, (sc, tr, st) in enumerate(zip(gpu.last_step_scores, ora.trace, g['steps'])):
+        np.testing.assert_allclose(sc[tr['candidates']], tr['scores'], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(sc[st['candidates']], st['mi'], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(gpu.last_fetch_scores, [st['mi'].max() for st in g['steps']], rtol=1e-4)
+    gpu.exhaustive = False
+    assert gpu.fetch_unlabelled(int(g['k'])) == ret
+
+
 def _syn(n, d, seed=0, centres=50):
     rng = np.random.default_rng(seed)
     C = rng.standard_normal((centres, d))
@@ -162,7 +182,7 @@ def test_interface_edge_cases():
     assert gpu.fetch_unlabelled(0) == []
     gpu.reset()
     assert gpu.rel_mean is None and gpu.rounds == 0 and gpu.get_unseen() == list(range(12))
-    for kw in (dict(mistake_prob=0.2), dict(label_prob=0.5), dict(label_estimation='optimistic'),
+    for kw in (dict(label_prob=0.5), dict(label_prob=0.5, mistake_prob=0.2), dict(label_estimation='optimistic'),
                dict(monte_carlo_num_rel=3)):
         bad = _gpu_learner(X, length_scale=1.0, **kw)
         bad.update({0: 1})
