@@ -135,6 +135,12 @@ int64_t ital_launch_count(const ital_shard* s);
 int64_t ital_snq_nodes(int t, const double* m, const double* L, double* eta, double* w, int32_t* orth,
                        double* masses);
 int ital_snq_order(int t);
+/* Conditional node sets of the general feedback model (label_prob < 1; csrc/snq_host.h generate_general).
+ * sizes[4] = {n_nodes, n_groups, n_sets, lut entries}; call with eta == NULL to get the sizes only.  eta[t*n_nodes]
+ * dimension-major, w[n_nodes], group_begin[n_groups+1], group_mass[n_groups], set_group0[n_sets+1],
+ * lut[3 * 4^(t+1)] = {group, set, flags} per (relevance configuration, labelled subset). */
+int ital_snq_general(int t, const double* m, const double* L, double noise, int64_t* sizes, double* eta, double* w,
+                     int32_t* group_begin, double* group_mass, int32_t* set_group0, int32_t* lut);
 
 #ifdef __cplusplus
 }

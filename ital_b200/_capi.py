@@ -52,6 +52,8 @@ SIGNATURES = {
     'ital_snq_nodes': (ctypes.c_int64, [ctypes.c_int, _c_double_p, _c_double_p, _c_double_p, _c_double_p,
                                         _c_int32_p, _c_double_p]),
     'ital_snq_order': (ctypes.c_int, [ctypes.c_int]),
+    'ital_snq_general': (ctypes.c_int, [ctypes.c_int, _c_double_p, _c_double_p, ctypes.c_double, _c_int64_p,
+                                        _c_double_p, _c_double_p, _c_int32_p, _c_double_p, _c_int32_p, _c_int32_p]),
 }
 
 _lib = None

@@ -82,6 +82,10 @@ struct ital_shard {
     int* stats_dev = nullptr;        // per step: worklist size, flagged, scored, -
     int* stats_host = nullptr;       // pinned
     int proposals = 0;               // propose calls in the running fetch
+    // general feedback model (label_prob < 1): conditional node sets of the running step
+    double *g_eta = nullptr, *g_w = nullptr, *g_mass = nullptr;
+    int *g_begin = nullptr, *g_set0 = nullptr, *g_lut = nullptr;
+    size_t g_cap_nodes = 0, g_cap_groups = 0, g_cap_sets = 0, g_cap_lut = 0;
 
     int w_cap = 0;                   // allocated projection columns
     int W = 0;                       // labelled points in the model
@@ -230,7 +234,7 @@ int extend_with_record(ital_shard* s, const double* rec, int col, int labelled, 
 // (1 - mp)^(t+1) and gets log(eps) otherwise (the updated orthant probability is 0 after a contradicting label), so
 // score = perfect-user score + (1 - (1 - mp)^(t+1)) * (log eps - log(1 + eps)) * sum_r p_r.
 double step_shift_coef(const ital_shard* s) {
-    if (!(s->mistake_prob > 0.0)) return 0.0;
+    if (!(s->mistake_prob > 0.0) || s->label_prob < 1.0) return 0.0;
     const double c = std::pow(1.0 - s->mistake_prob, (double)(s->t + 1));
     return (1.0 - c) * (std::log(1e-12) - s->log1p_eps);
 }
@@ -349,6 +353,81 @@ int launch_eval(ital_shard* s, int64_t items_hint, bool block_per_candidate) {
     return ITAL_OK;
 }
 
+// General feedback model, steps t >= 1: every candidate is scored (the lazy-greedy bound is only proven for users
+// who label every sample); the conditional node sets come from the host, which costs one round trip per step.
+int propose_general(ital_shard* s) {
+    const int t = s->t;
+    if (t > 4) return fail(ITAL_EINVAL, "label_prob < 1 supports batches of at most 5 samples");
+    std::vector<double> bm(16), bL(16 * 16);
+    CU(cudaMemcpyAsync(bm.data(), s->base_m_dev, 16 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(bL.data(), s->base_L_dev, 256 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    std::vector<double> Lb((size_t)t * t, 0.0);
+    for (int a = 0; a < t; ++a)
+        for (int b = 0; b <= a; ++b) Lb[(size_t)a * t + b] = bL[(size_t)a * kBaseStride + b];
+    snq::GeneralSets gs = snq::generate_general(t, bm.data(), Lb.data(), s->noise);
+    auto grow = [&](void** p, size_t* cap, size_t need, size_t esize) -> int {
+        if (need <= *cap) return ITAL_OK;
+        if (*p) CU(cudaFree(*p));
+        *p = nullptr;
+        CU(cudaMalloc(p, need * esize));
+        *cap = need;
+        return ITAL_OK;
+    };
+    int rc;
+    size_t cap_w = s->g_cap_nodes;
+    if ((rc = grow((void**)&s->g_eta, &s->g_cap_nodes, (size_t)gs.n_nodes * 4, sizeof(double)))) return rc;
+    if ((rc = grow((void**)&s->g_w, &cap_w, (size_t)gs.n_nodes * 4, sizeof(double)))) return rc;
+    size_t cap_b = s->g_cap_groups;
+    if ((rc = grow((void**)&s->g_mass, &s->g_cap_groups, (size_t)gs.n_groups + 1, sizeof(double)))) return rc;
+    if ((rc = grow((void**)&s->g_begin, &cap_b, (size_t)gs.n_groups + 1, sizeof(int)))) return rc;
+    if ((rc = grow((void**)&s->g_set0, &s->g_cap_sets, (size_t)gs.n_sets + 1, sizeof(int)))) return rc;
+    if ((rc = grow((void**)&s->g_lut, &s->g_cap_lut, gs.lut.size(), sizeof(int)))) return rc;
+    CU(cudaMemcpyAsync(s->g_eta, gs.eta.data(), gs.eta.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->g_w, gs.w.data(), gs.w.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->g_mass, gs.group_mass.data(), gs.group_mass.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->g_begin, gs.group_begin.data(), gs.group_begin.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->g_set0, gs.set_group0.data(), gs.set_group0.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->g_lut, gs.lut.data(), gs.lut.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));       // gs lives in pageable host memory
+    s->n_nodes = gs.n_nodes;
+    k_fill<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->score, s->n, std::numeric_limits<double>::quiet_NaN()); s->launches++;
+    k_worklist<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->n, s->mask, s->gain, s->thr_dev, 1, s->counters, s->worklist); s->launches++;
+    GeneralArgs a;
+    a.count = s->counters;
+    a.list = s->worklist;
+    a.m = s->m;
+    a.v = s->v;
+    a.U = s->U;
+    a.ldu = s->ldu;
+    a.W0 = s->W;
+    a.t = t;
+    a.eta = s->g_eta;
+    a.w = s->g_w;
+    a.n_nodes = gs.n_nodes;
+    a.group_begin = s->g_begin;
+    a.group_mass = s->g_mass;
+    a.set_group0 = s->g_set0;
+    a.lut = s->g_lut;
+    a.n_groups = gs.n_groups;
+    a.n_sets = gs.n_sets;
+    a.lp = s->label_prob;
+    a.mp = s->mistake_prob;
+    a.noise = s->noise;
+    a.score = s->score;
+    a.gain = s->gain;
+    a.n_scored = s->counters + 2;
+    const size_t smem = ((size_t)3 * gs.n_groups + 2 * gs.n_sets + (size_t)gs.n_groups * 24 + 8) * sizeof(double);
+    CU(cudaFuncSetAttribute(k_eval_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int blocks = grid_for(s, s->n, 1, 8);
+    k_eval_general<<<blocks, 256, smem, s->stream>>>(a); s->launches++;
+    const int lb = std::min(kArgmaxBlocks, grid_for(s, s->n, 256));
+    k_argmax_list<<<lb, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->block_best); s->launches++;
+    k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, lb, s->best); s->launches++;
+    CU(cudaGetLastError());
+    return ITAL_OK;
+}
+
 // The local candidates of the current greedy step -> record of the local best in DEVICE memory `rec_out`.
 // Nothing here waits for the GPU (t <= 3).
 int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_out) {
@@ -356,10 +435,16 @@ int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_o
     const int blocks = std::min(kArgmaxBlocks, grid_for(s, s->n, 256));
     CU(cudaMemsetAsync(s->counters, 0, 4 * sizeof(int), s->stream));
     if (s->t == 0) {
-        k_score0<<<blocks, 256, 0, s->stream>>>(s->n, s->m, s->v, s->mask, s->score, s->gain, s->block_best, s->log1p_eps); s->launches++;
+        const bool general = s->label_prob < 1.0;
+        const double lc = general ? (1.0 - s->mistake_prob) * s->log1p_eps + s->mistake_prob * std::log(1e-12) : s->log1p_eps;
+        k_score0<<<blocks, 256, 0, s->stream>>>(s->n, s->m, s->v, s->mask, s->score, s->gain, s->block_best, lc,
+                                                general ? s->label_prob : 1.0); s->launches++;
         k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, blocks, s->best); s->launches++;
         CU(cudaGetLastError());
         s->n_nodes = 1;
+    } else if (s->label_prob < 1.0) {
+        int rc = propose_general(s);
+        if (rc) return rc;
     } else {
         int rc = prepare_nodes(s);
         if (rc) return rc;
@@ -424,7 +509,7 @@ void free_all(ital_shard* s) {
     void* ptrs[] = {s->X, s->sqn, s->m, s->v, s->U, s->gain, s->score, s->mask, s->worklist, s->counters,
                     s->block_best, s->best, s->thr_dev, s->rec_dev, s->rec_in_dev, s->idx_dev, s->eta_dev,
                     s->w_dev, s->masses_dev, s->group_dev, s->orth_dev, s->gl_dev, s->base_m_dev, s->base_L_dev, s->sel_dev,
-                    s->hbase_dev, s->stats_dev, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev};
+                    s->hbase_dev, s->stats_dev, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->rec_host) cudaFreeHost(s->rec_host);
@@ -697,8 +782,7 @@ int ital_restrict_candidates(ital_shard* s, int64_t m, const int64_t* global_idx
 int ital_fetch_begin(ital_shard* s, double label_prob, double mistake_prob) {
     if (!s) return fail(ITAL_EINVAL, "null shard");
     if (s->W == 0) return fail(ITAL_ESTATE, "fetch before any labelled point or query (the reference fails here too: gp.K_inv is None)");
-    if (!(label_prob >= 1.0))
-        return fail(ITAL_EINVAL, "label_prob < 1 (users who skip samples) is not implemented on the GPU path");
+    if (!(label_prob > 0.0)) return fail(ITAL_EINVAL, "label_prob must be positive");
     if (!(mistake_prob >= 0.0 && mistake_prob <= 1.0)) return fail(ITAL_EINVAL, "mistake_prob must be in [0, 1]");
     CU(cudaSetDevice(s->device));
     if (s->fetching) {
@@ -964,5 +1048,23 @@ int64_t ital_snq_nodes(int t, const double* m, const double* L, double* eta, dou
 }
 
 int ital_snq_order(int t) { return snq::order_for(t); }
+
+int ital_snq_general(int t, const double* m, const double* L, double noise, int64_t* sizes, double* eta, double* w,
+                     int32_t* group_begin, double* group_mass, int32_t* set_group0, int32_t* lut) {
+    if (t < 1 || t > 4 || !m || !L || !sizes) return fail(ITAL_EINVAL, "ital_snq_general: bad arguments");
+    snq::GeneralSets gs = snq::generate_general(t, m, L, noise);
+    sizes[0] = gs.n_nodes;
+    sizes[1] = gs.n_groups;
+    sizes[2] = gs.n_sets;
+    sizes[3] = (int64_t)gs.lut.size();
+    if (!eta) return ITAL_OK;
+    memcpy(eta, gs.eta.data(), gs.eta.size() * sizeof(double));
+    memcpy(w, gs.w.data(), gs.w.size() * sizeof(double));
+    memcpy(group_begin, gs.group_begin.data(), gs.group_begin.size() * sizeof(int32_t));
+    memcpy(group_mass, gs.group_mass.data(), gs.group_mass.size() * sizeof(double));
+    memcpy(set_group0, gs.set_group0.data(), gs.set_group0.size() * sizeof(int32_t));
+    memcpy(lut, gs.lut.data(), gs.lut.size() * sizeof(int32_t));
+    return ITAL_OK;
+}
 
 }  // extern "C"

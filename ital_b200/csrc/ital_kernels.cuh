@@ -245,7 +245,9 @@ k_extend(const XT* __restrict__ X, int64_t n, int d, int d_pad, const double* __
 __global__ void __launch_bounds__(256) k_score0(int64_t n, const double* __restrict__ m,
                                                 const double* __restrict__ v, const uint8_t* __restrict__ mask,
                                                 double* __restrict__ score, double* __restrict__ gain,
-                                                Best* __restrict__ block_best, double log1p_eps) {
+                                                Best* __restrict__ block_best, double log1p_eps, double scale) {
+    // perfect / mistaken user: scale = 1, log1p_eps = log(1 + eps) (a mistaken user adds a constant later);
+    // general model (label_prob < 1): scale = label_prob, log1p_eps = (1-mp) log(1+eps) + mp log(eps)
     double bs = 0.0;
     long long bi = -1;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(256) k_score0(int64_t n, const double* __restr
                 p1 = m[i] > 0.0 ? 1.0 : 0.0;
                 p0 = 1.0 - p1;
             }
-            s = mi_term(p0, log1p_eps) + mi_term(p1, log1p_eps);
+            s = scale * (mi_term(p0, log1p_eps) + mi_term(p1, log1p_eps));
             gain[i] = s;
             if (better(s, i, bs, bi)) { bs = s; bi = i; }
         }
@@ -571,6 +573,155 @@ __global__ void __launch_bounds__(256) k_eval_sorted(EvalArgs a) {
             atomicAdd(a.n_scored, 1);
             if (s2 < a.flag_var) atomicAdd(a.n_flagged, 1);
         }
+    }
+}
+
+// General feedback model (label_prob < 1): MI of one candidate per block from the conditional node sets of
+// csrc/snq_host.h (generate_general).  For every (set, orthant of the unlabelled base variables) it accumulates
+//   A  = sum w Phi((m_i + l_i.eta)/s_i)                        candidate unlabelled, relevant
+//   B+ = sum w exp(-((+1 - m_i - l_i.eta)/s~_i)^2 / 2)          candidate labelled relevant   (s~^2 = s^2 + noise)
+//   B- = sum w exp(-((-1 - m_i - l_i.eta)/s~_i)^2 / 2)          candidate labelled irrelevant
+// and then assembles  MI = sum_r p_r { sum_{O != 0} (1-lp)^(D-|O|) lp^|O| [ (1-mp)^|O| log(q_{r,O} + eps)
+//                                      + (1 - (1-mp)^|O|) log eps ] - (1 - (1-lp)^D) log(p_r + eps) }
+// (MutualInformation._call_iter_all with fb_iter's general case, ital/ital.py:183-224, 330-342, 453-481; q_{r,O} is
+// updated_prob_rel, ital/ital.py:432-450, with the labelled samples pinned -- DESIGN.md "general feedback model").
+struct GeneralArgs {
+    const int* count;
+    const int* list;
+    const double* m;
+    const double* v;
+    const double* U;
+    int64_t ldu;
+    int W0;
+    int t;
+    const double* eta;
+    const double* w;
+    int64_t n_nodes;
+    const int* group_begin;
+    const double* group_mass;
+    const int* set_group0;
+    const int* lut;
+    int n_groups;
+    int n_sets;
+    double lp, mp, noise;
+    double* score;
+    double* gain;
+    int* n_scored;
+};
+
+__global__ void __launch_bounds__(256) k_eval_general(GeneralArgs a) {
+    extern __shared__ double gsm[];
+    const int G = a.n_groups, NS = a.n_sets, t = a.t, D = a.t + 1;
+    double* A = gsm;                    // [G]
+    double* Bp = A + G;                 // [G]
+    double* Bm = Bp + G;                // [G]
+    double* sBp = Bm + G;               // [NS]
+    double* sBm = sBp + NS;             // [NS]
+    double* red = sBm + NS;             // [G][8][3] per-warp partials, later [8] for the final sum
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_items = *a.count;
+    const int64_t N = a.n_nodes;
+    const double log_eps = log(kEps), log1p_eps = log(1.0 + kEps);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int64_t i = a.list[item];
+        double l[4];
+        double s2 = a.v[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            l[j] = 0.0;
+            if (j < t) {
+                l[j] = a.U[(int64_t)(a.W0 + j) * a.ldu + i];
+                s2 = fma(-l[j], l[j], s2);
+            }
+        }
+        const double mi = a.m[i];
+        const double s = s2 > 0.0 ? sqrt(s2) : 0.0;
+        const double inv_s = s > 0.0 ? 1.0 / s : 0.0;
+        const double inv_st = 1.0 / sqrt(fmax(s2, 0.0) + a.noise);
+        for (int g = 0; g < G; ++g) {
+            double xa = 0.0, xp = 0.0, xm = 0.0;
+            for (int q = a.group_begin[g] + threadIdx.x; q < a.group_begin[g + 1]; q += blockDim.x) {
+                double num = mi;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j < t) num = fma(l[j], a.eta[(int64_t)j * N + q], num);
+                const double wq = a.w[q];
+                const double cdf = s > 0.0 ? phi_cdf(num * inv_s) : (num > 0.0 ? 1.0 : 0.0);
+                const double dp = (1.0 - num) * inv_st, dm = (-1.0 - num) * inv_st;
+                xa = fma(wq, cdf, xa);
+                xp = fma(wq, exp(-0.5 * dp * dp), xp);
+                xm = fma(wq, exp(-0.5 * dm * dm), xm);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                xa += __shfl_xor_sync(0xffffffffu, xa, o);
+                xp += __shfl_xor_sync(0xffffffffu, xp, o);
+                xm += __shfl_xor_sync(0xffffffffu, xm, o);
+            }
+            if (lane == 0) {
+                red[(g * 8 + warp) * 3 + 0] = xa;
+                red[(g * 8 + warp) * 3 + 1] = xp;
+                red[(g * 8 + warp) * 3 + 2] = xm;
+            }
+        }
+        __syncthreads();
+        for (int g = threadIdx.x; g < G; g += blockDim.x) {
+            double xa = 0.0, xp = 0.0, xm = 0.0;
+            for (int k = 0; k < 8; ++k) {
+                xa += red[(g * 8 + k) * 3 + 0];
+                xp += red[(g * 8 + k) * 3 + 1];
+                xm += red[(g * 8 + k) * 3 + 2];
+            }
+            A[g] = xa;
+            Bp[g] = xp;
+            Bm[g] = xm;
+        }
+        __syncthreads();
+        for (int sidx = threadIdx.x; sidx < NS; sidx += blockDim.x) {
+            double xp = 0.0, xm = 0.0;
+            for (int g = a.set_group0[sidx]; g < a.set_group0[sidx + 1]; ++g) { xp += Bp[g]; xm += Bm[g]; }
+            sBp[sidx] = xp;
+            sBm[sidx] = xm;
+        }
+        __syncthreads();
+        // assembly over (r, O); O = 0 stands for the -log p_r term
+        double part = 0.0;
+        const int nr = 1 << D;
+        for (int pidx = threadIdx.x; pidx < nr * nr; pidx += blockDim.x) {
+            const int r = pidx >> D, Om = pidx & (nr - 1);
+            const int g0 = r & ((1 << t) - 1), rc = r >> t;
+            const double p_r = fmax(rc ? A[g0] : a.group_mass[g0] - A[g0], 0.0);
+            double term;
+            if (Om == 0) {
+                term = -(1.0 - pow(1.0 - a.lp, (double)D)) * log(p_r + kEps);
+            } else {
+                const int k = __popc(Om);
+                const double lam = pow(1.0 - a.lp, (double)(D - k)) * pow(a.lp, (double)k);
+                const double c1 = pow(1.0 - a.mp, (double)k);
+                const int* e = a.lut + ((size_t)r * nr + Om) * 3;
+                double q;
+                if (e[2] & 2) q = 1.0;
+                else if (e[2] & 1) q = (rc ? Bp[e[0]] : Bm[e[0]]) / fmax(rc ? sBp[e[1]] : sBm[e[1]], 1e-300);
+                else q = rc ? A[e[0]] : a.group_mass[e[0]] - A[e[0]];
+                q = fmin(fmax(q, 0.0), 1.0);
+                term = lam * (c1 * log(q + kEps) + (1.0 - c1) * log_eps);
+            }
+            part = fma(p_r, term, part);
+        }
+        (void)log1p_eps;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        __syncthreads();                                 // red is reused below
+        if (lane == 0) red[warp] = part;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+            for (int k = 0; k < 8; ++k) tot += red[k];
+            a.score[i] = tot;
+            a.gain[i] = tot;
+            atomicAdd(a.n_scored, 1);
+        }
+        __syncthreads();
     }
 }
 

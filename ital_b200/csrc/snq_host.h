@@ -160,3 +160,209 @@ inline Nodes generate(int t, const double* m, const double* L, int q = 0, double
 }
 
 }  // namespace snq
+
+// ---------------------------------------------------------------------------------------------------------------
+// Node sets of the GENERAL feedback model (label_prob < 1): the user may skip samples, so the score of a candidate
+// needs, besides P(r), the orthant probabilities of the unobserved samples conditional on pinned (labelled) ones
+// (MutualInformation.updated_prob_rel, /root/reference/ital/ital.py:432-450, via gp.updated_prediction,
+// /root/reference/ital/gp.py:295-344).  For every subset O of the batch's base that is labelled and every sign
+// pattern f of those labels, the whitened coordinates eta of the base are Gaussian with
+//     mu = A^T (A A^T + noise I)^-1 (f - m_O),   Sigma = I - A^T (A A^T + noise I)^-1 A,   A = L[O, :],
+// and the unlabelled base variables z_U = m_U + L[U, :] eta get their own SNQ nodes zeta; eta = mu + G zeta with
+// G = Sigma L[U,:]^T Lc^-T, Lc Lc^T = L[U,:] Sigma L[U,:]^T.  Every set is a list of (eta, weight, orthant of z_U)
+// shared by all candidates, exactly like the unconditional nodes (set 0).  See DESIGN.md "general feedback model"
+// and tools/proto_general.py (numpy prototype checked against the oracle and the reference goldens).
+namespace snq {
+
+struct GeneralSets {
+    int t = 0;
+    int n_sets = 0;
+    int n_groups = 0;                  // total number of (set, orthant of U) accumulators
+    int64_t n_nodes = 0;
+    std::vector<double> eta;           // dimension-major [t][n_nodes]
+    std::vector<double> w;
+    std::vector<int32_t> group_begin;  // n_groups + 1 node offsets (nodes sorted by global group)
+    std::vector<double> group_mass;    // n_groups: sum of the weights of the group
+    std::vector<int32_t> set_group0;   // n_sets + 1: first global group of each set
+    // lut[r * 2^D + Omask] for r in [0, 2^D), Omask in [1, 2^D): {global group, set, flags}; D = t + 1, the
+    // candidate is variable t.  flags: 1 = candidate labelled (use the density sums), 2 = every sample labelled.
+    std::vector<int32_t> lut;
+};
+
+inline void chol_inplace(std::vector<double>& C, int n, double floor = 1e-300) {
+    for (int j = 0; j < n; ++j) {
+        double d = C[j * n + j];
+        for (int k = 0; k < j; ++k) d -= C[j * n + k] * C[j * n + k];
+        const double p = std::sqrt(d > floor ? d : floor);
+        C[j * n + j] = p;
+        for (int i = j + 1; i < n; ++i) {
+            double v = C[i * n + j];
+            for (int k = 0; k < j; ++k) v -= C[i * n + k] * C[j * n + k];
+            C[i * n + j] = v / p;
+        }
+        for (int i = 0; i < j; ++i) C[i * n + j] = 0.0;
+    }
+}
+
+// m[t], L[t*t] row-major lower triangular, label noise sigma^2
+inline GeneralSets generate_general(int t, const double* m, const double* L, double noise) {
+    GeneralSets out;
+    out.t = t;
+    const int D = t + 1;
+    std::vector<std::vector<double>> eta_sets, w_sets;
+    std::vector<std::vector<int32_t>> gb_sets;
+    std::vector<int> set_Omask, set_fbits, set_nU;
+    // set index by (Omask over base, sign bits compacted over O)
+    std::vector<std::vector<int>> set_of(1 << t);
+    for (int Omask = 0; Omask < (1 << t); ++Omask) {
+        std::vector<int> O, U;
+        for (int j = 0; j < t; ++j) ((Omask >> j) & 1 ? O : U).push_back(j);
+        const int k = (int)O.size(), u = (int)U.size();
+        set_of[Omask].assign(1 << k, -1);
+        // pieces that do not depend on the signs
+        std::vector<double> A((size_t)k * t), X((size_t)k * t, 0.0), Sig((size_t)t * t, 0.0);
+        for (int a = 0; a < k; ++a)
+            for (int c = 0; c < t; ++c) A[a * t + c] = L[O[a] * t + c];
+        std::vector<double> S((size_t)k * k);
+        for (int a = 0; a < k; ++a)
+            for (int b = 0; b < k; ++b) {
+                double acc = (a == b) ? noise : 0.0;
+                for (int c = 0; c < t; ++c) acc += A[a * t + c] * A[b * t + c];
+                S[a * k + b] = acc;
+            }
+        if (k > 0) {
+            chol_inplace(S, k);
+            // X = S^-1 A by two triangular solves per column
+            for (int c = 0; c < t; ++c) {
+                std::vector<double> y(k);
+                for (int a = 0; a < k; ++a) {
+                    double v = A[a * t + c];
+                    for (int b = 0; b < a; ++b) v -= S[a * k + b] * y[b];
+                    y[a] = v / S[a * k + a];
+                }
+                for (int a = k - 1; a >= 0; --a) {
+                    double v = y[a];
+                    for (int b = a + 1; b < k; ++b) v -= S[b * k + a] * X[b * t + c];
+                    X[a * t + c] = v / S[a * k + a];
+                }
+            }
+        }
+        for (int r = 0; r < t; ++r)
+            for (int c = 0; c < t; ++c) {
+                double acc = (r == c) ? 1.0 : 0.0;
+                for (int a = 0; a < k; ++a) acc -= A[a * t + r] * X[a * t + c];
+                Sig[r * t + c] = acc;
+            }
+        // B = L[U,:], CU = B Sig B^T, Lc = chol(CU), G = Sig B^T Lc^-T
+        std::vector<double> B((size_t)u * t), SB((size_t)t * u), CU((size_t)u * u), G((size_t)t * u);
+        for (int a = 0; a < u; ++a)
+            for (int c = 0; c < t; ++c) B[a * t + c] = L[U[a] * t + c];
+        for (int r = 0; r < t; ++r)
+            for (int a = 0; a < u; ++a) {
+                double acc = 0.0;
+                for (int c = 0; c < t; ++c) acc += Sig[r * t + c] * B[a * t + c];
+                SB[r * u + a] = acc;
+            }
+        for (int a = 0; a < u; ++a)
+            for (int b = 0; b < u; ++b) {
+                double acc = 0.0;
+                for (int c = 0; c < t; ++c) acc += B[a * t + c] * SB[c * u + b];
+                CU[a * u + b] = acc;
+            }
+        std::vector<double> Lc(CU);
+        if (u > 0) chol_inplace(Lc, u);
+        for (int r = 0; r < t; ++r)       // row r of G solves Lc x = (SB row r)
+            for (int a = 0; a < u; ++a) {
+                double v = SB[r * u + a];
+                for (int b = 0; b < a; ++b) v -= Lc[a * u + b] * G[r * u + b];
+                G[r * u + a] = v / Lc[a * u + a];
+            }
+        for (int fb = 0; fb < (1 << k); ++fb) {
+            std::vector<double> mu(t, 0.0), resid(k);
+            for (int a = 0; a < k; ++a) resid[a] = (((fb >> a) & 1) ? 1.0 : -1.0) - m[O[a]];
+            for (int c = 0; c < t; ++c)
+                for (int a = 0; a < k; ++a) mu[c] += X[a * t + c] * resid[a];
+            std::vector<double> eta, w;
+            std::vector<int32_t> gb;
+            if (u == 0) {
+                eta = mu;                  // a single node
+                w.assign(1, 1.0);
+                gb = {0, 1};
+            } else {
+                std::vector<double> mU(u);
+                for (int a = 0; a < u; ++a) {
+                    double acc = m[U[a]];
+                    for (int c = 0; c < t; ++c) acc += B[a * t + c] * mu[c];
+                    mU[a] = acc;
+                }
+                Nodes nd = generate(u, mU.data(), Lc.data());
+                eta.assign((size_t)t * nd.n, 0.0);
+                for (int64_t q = 0; q < nd.n; ++q)
+                    for (int r = 0; r < t; ++r) {
+                        double acc = mu[r];
+                        for (int a = 0; a < u; ++a) acc += G[r * u + a] * nd.eta[(size_t)a * nd.n + q];
+                        eta[(size_t)r * nd.n + q] = acc;
+                    }
+                w = nd.w;
+                gb = nd.group_begin;
+            }
+            set_of[Omask][fb] = (int)eta_sets.size();
+            eta_sets.push_back(eta);
+            w_sets.push_back(w);
+            gb_sets.push_back(gb);
+            set_Omask.push_back(Omask);
+            set_fbits.push_back(fb);
+            set_nU.push_back(u);
+        }
+    }
+    // flatten
+    out.n_sets = (int)eta_sets.size();
+    out.set_group0.assign(out.n_sets + 1, 0);
+    int64_t total = 0;
+    for (int s = 0; s < out.n_sets; ++s) {
+        out.set_group0[s + 1] = out.set_group0[s] + (1 << set_nU[s]);
+        total += (int64_t)w_sets[s].size();
+    }
+    out.n_groups = out.set_group0[out.n_sets];
+    out.n_nodes = total;
+    out.eta.assign((size_t)t * total, 0.0);
+    out.w.resize(total);
+    out.group_begin.assign(out.n_groups + 1, 0);
+    out.group_mass.assign(out.n_groups, 0.0);
+    int64_t pos = 0;
+    for (int s = 0; s < out.n_sets; ++s) {
+        const int64_t ns = (int64_t)w_sets[s].size();
+        for (int r = 0; r < t; ++r)
+            for (int64_t q = 0; q < ns; ++q) out.eta[(size_t)r * total + pos + q] = eta_sets[s][(size_t)r * ns + q];
+        for (int64_t q = 0; q < ns; ++q) out.w[pos + q] = w_sets[s][q];
+        for (int g = 0; g < (1 << set_nU[s]); ++g) {
+            const int gg = out.set_group0[s] + g;
+            out.group_begin[gg] = (int32_t)(pos + gb_sets[s][g]);
+            double acc = 0.0;
+            for (int32_t q = gb_sets[s][g]; q < gb_sets[s][g + 1]; ++q) acc += w_sets[s][q];
+            out.group_mass[gg] = acc;
+        }
+        pos += ns;
+    }
+    out.group_begin[out.n_groups] = (int32_t)total;
+    // lookup: (relevance configuration r of base + candidate, labelled subset O) -> accumulator
+    out.lut.assign((size_t)3 << (2 * D), 0);
+    for (int r = 0; r < (1 << D); ++r)
+        for (int Om = 1; Om < (1 << D); ++Om) {
+            const int Ob = Om & ((1 << t) - 1);
+            const bool c_in = (Om >> t) & 1;
+            int fb = 0, kk = 0, g = 0, uu = 0;
+            for (int j = 0; j < t; ++j) {
+                if ((Ob >> j) & 1) { fb |= ((r >> j) & 1) << kk; ++kk; }
+                else { g |= ((r >> j) & 1) << uu; ++uu; }
+            }
+            const int s = set_of[Ob][fb];
+            int32_t* e = &out.lut[((size_t)r * (1 << D) + Om) * 3];
+            e[0] = out.set_group0[s] + g;
+            e[1] = s;
+            e[2] = (c_in ? 1 : 0) | (Om == (1 << D) - 1 ? 2 : 0);
+        }
+    return out;
+}
+
+}  // namespace snq

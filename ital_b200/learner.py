@@ -340,10 +340,6 @@ class ITAL(object):
 
     # ---- ITAL ------------------------------------------------------------------------------------------
     def _check_supported(self):
-        if not (self.label_prob >= 1):
-            raise NotImplementedError('GPU path implements users who label every sample (label_prob >= 1, any '
-                                      'mistake_prob); label_prob < 1 is not available yet and there is '
-                                      'deliberately no CPU fallback')
         if self.label_estimation != 'mean':
             raise NotImplementedError("label_estimation must be 'mean' on the GPU path")
         if self.change_estimation_subset != 0 or (self.clip_cov and 0 < self.clip_cov < 1) \

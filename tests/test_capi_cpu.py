@@ -73,3 +73,77 @@ def test_snq_nodes_match_oracle(lib, t):
 def test_snq_order_matches_oracle(lib):
     for t in range(1, 11):
         assert lib.ital_snq_order(t) == orthant.snq_order(t)
+
+
+def _general_mi_from_c_arrays(lib, m_b, L, m_c, l_c, s_c, lp, mp, noise):
+    """The assembly of k_eval_general restated in numpy on the node sets the C library generates."""
+    from scipy.special import ndtr
+    t = len(m_b)
+    D = t + 1
+    sizes = np.zeros(4, dtype=np.int64)
+    Lc = np.ascontiguousarray(L)
+    i32 = ctypes.POINTER(ctypes.c_int32)
+    assert lib.ital_snq_general(t, _capi.dptr(m_b), _capi.dptr(Lc), noise, _capi.i64ptr(sizes),
+                                None, None, None, None, None, None) == 0
+    N, G, NS, nl = [int(x) for x in sizes]
+    eta, w = np.zeros((t, N)), np.zeros(N)
+    gb, gm = np.zeros(G + 1, dtype=np.int32), np.zeros(G)
+    s0, lut = np.zeros(NS + 1, dtype=np.int32), np.zeros(nl, dtype=np.int32)
+    assert lib.ital_snq_general(t, _capi.dptr(m_b), _capi.dptr(Lc), noise, _capi.i64ptr(sizes), _capi.dptr(eta),
+                                _capi.dptr(w), gb.ctypes.data_as(i32), _capi.dptr(gm), s0.ctypes.data_as(i32),
+                                lut.ctypes.data_as(i32)) == 0
+    lut = lut.reshape(1 << D, 1 << D, 3)
+    arg = m_c[:, None] + l_c @ eta
+    st = np.sqrt(s_c ** 2 + noise)
+    cdf = ndtr(arg / s_c[:, None]) * w
+    bp = np.exp(-0.5 * ((1 - arg) / st[:, None]) ** 2) * w
+    bm = np.exp(-0.5 * ((-1 - arg) / st[:, None]) ** 2) * w
+    A = np.stack([cdf[:, gb[g]:gb[g + 1]].sum(axis=1) for g in range(G)], axis=1)
+    Bp = np.stack([bp[:, gb[g]:gb[g + 1]].sum(axis=1) for g in range(G)], axis=1)
+    Bm = np.stack([bm[:, gb[g]:gb[g + 1]].sum(axis=1) for g in range(G)], axis=1)
+    sBp = np.stack([Bp[:, s0[k]:s0[k + 1]].sum(axis=1) for k in range(NS)], axis=1)
+    sBm = np.stack([Bm[:, s0[k]:s0[k + 1]].sum(axis=1) for k in range(NS)], axis=1)
+    eps = 1e-12
+    mi = np.zeros(len(m_c))
+    for r in range(1 << D):
+        g0, rc = r & ((1 << t) - 1), r >> t
+        p_r = np.maximum(A[:, g0] if rc else gm[g0] - A[:, g0], 0)
+        inner = -(1 - (1 - lp) ** D) * np.log(p_r + eps)
+        for Om in range(1, 1 << D):
+            k = bin(Om).count('1')
+            g, sidx, flags = lut[r, Om]
+            if flags & 2:
+                q = np.ones(len(m_c))
+            elif flags & 1:
+                q = (Bp[:, g] / np.maximum(sBp[:, sidx], 1e-300)) if rc else (Bm[:, g] / np.maximum(sBm[:, sidx], 1e-300))
+            else:
+                q = A[:, g] if rc else gm[g] - A[:, g]
+            q = np.clip(q, 0, 1)
+            inner = inner + (1 - lp) ** (D - k) * lp ** k * ((1 - mp) ** k * np.log(q + eps) + (1 - (1 - mp) ** k) * np.log(eps))
+        mi += p_r * inner
+    return mi
+
+
+@pytest.mark.parametrize('t,lp,mp', [(1, 0.75, 0.2), (2, 0.25, 0.0), (3, 0.6, 0.1)])
+def test_general_feedback_node_sets_match_oracle(lib, t, lp, mp):
+    """Host-side conditional node sets + lookup table of the general feedback model against the oracle's literal
+    enumeration of relevance and feedback configurations (ital.py:183-224) on random blocks."""
+    from oracle.ital_oracle import OracleITAL
+    rng = np.random.default_rng(10 * t)
+    D = t + 1
+    n = 6
+    ora = OracleITAL.__new__(OracleITAL)
+    ora.label_prob, ora.mistake_prob, ora.label_estimation, ora.noise = lp, mp, 'mean', 1e-6
+    A = rng.normal(size=(t, t + 2))
+    C = A @ A.T / (t + 2) * 0.5
+    L = np.linalg.cholesky(C)
+    m_b = rng.normal(size=t) * 0.4
+    l_c = rng.normal(size=(n, t)) * 0.3
+    s_c = rng.uniform(0.3, 0.8, size=n)
+    m_c = rng.normal(size=n) * 0.5
+    got = _general_mi_from_c_arrays(lib, m_b, L, m_c, l_c, s_c, lp, mp, 1e-6)
+    for i in range(n):
+        cbc = L @ l_c[i]
+        var_c = s_c[i] ** 2 + l_c[i] @ l_c[i]
+        want = ora._mi_general(list(range(D)), m_b, C, m_c[i], var_c, cbc)
+        assert abs(got[i] - want) <= 1e-4 * abs(want) + 1e-6, (i, got[i], want)

@@ -99,6 +99,30 @@ def test_mistaken_user_golden_and_oracle():
     assert gpu.fetch_unlabelled(int(g['k'])) == ret
 
 
+@pytest.mark.parametrize('name', ['toy_mistakes_k3', 'butterflies_conservative_k3'])
+def test_general_feedback_model_golden_and_oracle(name):
+    """label_prob < 1 (configs/toy-mistakes.conf, configs/butterflies-conservative.conf): conditional node sets,
+    every candidate scored.  1e-4 relative against the reference golden and the oracle's literal enumeration."""
+    from oracle.ital_oracle import OracleITAL
+    g = load_golden(name)
+    kw = dict(g['learner_kw'])
+    gpu = drive(_gpu_learner(g['X'], **kw), g)
+    ora = drive(OracleITAL(g['X'], **kw), g)
+    ret = gpu._fetch_stepwise(int(g['k']), keep_scores=True)
+    ora.fetch_unlabelled(int(g['k']), forced=ret)
+    for t, (sc, tr) in enumerate(zip(gpu.last_step_scores, ora.trace)):
+        np.testing.assert_allclose(sc[tr['candidates']], tr['scores'], rtol=1e-4, atol=1e-6, err_msg='step %d' % t)
+        pos = int(np.nonzero(tr['candidates'] == ret[t])[0][0])
+        assert tr['scores'][pos] >= tr['scores'].max() - 1e-4 * abs(tr['scores'].max())
+    for t, st in enumerate(g['steps']):          # the reference's own record, as far as the paths coincide
+        if ret[t] != st['chosen']:
+            pos = int(np.nonzero(st['candidates'] == ret[t])[0][0])
+            assert st['mi'][pos] >= st['mi'].max() - 1e-4 * abs(st['mi'].max())
+            break
+        np.testing.assert_allclose(gpu.last_step_scores[t][st['candidates']], st['mi'], rtol=1e-4, atol=1e-6)
+    assert gpu.fetch_unlabelled(int(g['k'])) == ret
+
+
 def _syn(n, d, seed=0, centres=50):
     rng = np.random.default_rng(seed)
     C = rng.standard_normal((centres, d))
@@ -182,7 +206,7 @@ def test_interface_edge_cases():
     assert gpu.fetch_unlabelled(0) == []
     gpu.reset()
     assert gpu.rel_mean is None and gpu.rounds == 0 and gpu.get_unseen() == list(range(12))
-    for kw in (dict(label_prob=0.5), dict(label_prob=0.5, mistake_prob=0.2), dict(label_estimation='optimistic'),
+    for kw in (dict(label_estimation='pessimistic'), dict(clip_cov=0.5), dict(label_estimation='optimistic'),
                dict(monte_carlo_num_rel=3)):
         bad = _gpu_learner(X, length_scale=1.0, **kw)
         bad.update({0: 1})
