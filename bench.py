@@ -188,6 +188,7 @@ def main():
     ap.add_argument('--cpu-rows', type=int, default=0, help='rows of the CPU baseline sample (0 = default)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--exhaustive-steps', type=int, default=1)
+    ap.add_argument('--lazy-steps', type=int, default=50)
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -297,6 +298,17 @@ def main():
                'note': 'every candidate scored by quadrature at every greedy step (no lazy-greedy bound)'}
         learner.exhaustive = False
 
+    lazy = None
+    if args.lazy_steps > 0:
+        learner.lazy_rows = True
+        timed(3, False)
+        ldev, lwall, lret = timed(args.lazy_steps, False)
+        lazy = {'value': ranked * args.lazy_steps / ldev, 'unit': UNIT, 'ms_per_step': ldev / args.lazy_steps * 1e3,
+                'e2e_ms_per_step': lwall / args.lazy_steps * 1e3, 'steps': args.lazy_steps, 'same_batch': lret == ret,
+                'note': 'lazy_rows=True: batch-conditional projections extended on demand for the scored rows only '
+                        '(k_catchup) instead of one streaming pass over the pool per greedy step (k_extend)'}
+        learner.lazy_rows = False
+
     if rank != 0:
         dist.destroy_process_group()
         return
@@ -324,6 +336,7 @@ def main():
                      'algorithmic_bytes_per_launch': nbytes.value / max(1, nl.value),
                      'share_of_step': ms.value / 1e3 / dev},
         'exhaustive': exh,
+        'lazy_rows': lazy,
         'fetch_stats_per_step': stats,
         'setup': {'generate_s': t_gen, 'fit_s': t_fit, 'update_9_labels_s': t_update},
     }

@@ -103,6 +103,13 @@ int ital_fetch_end(ital_shard* s);
 int ital_fetch(ital_shard* s, int k, double label_prob, double mistake_prob, int exhaustive,
                int64_t* out_idx, double* out_scores);
 
+/* Lazy rows (off by default).  Off: every greedy step streams the whole pool once to extend every row's
+ * batch-conditional projection (k_extend; HBM-bound, what predict_cov_batch does for all rows, ital/gp.py:235-261).
+ * On: the projection is extended only for the rows that are actually scored, on demand, from the stored records of
+ * the selected points (k_catchup); same entries bit for bit, same batch, far less traffic when the lazy-greedy bound
+ * prunes most rows. */
+int ital_set_lazy_rows(ital_shard* s, int on);
+
 /* Per-step diagnostics of the last propose: [0] candidates considered, [1] candidates scored exactly,
  * [2] quadrature nodes, [3] H(base), [4] flagged (conditional variance < 100 * noise), [5..7] reserved. */
 int ital_fetch_stats(const ital_shard* s, double* out8);

@@ -82,6 +82,10 @@ struct ital_shard {
     int* stats_dev = nullptr;        // per step: worklist size, flagged, scored, -
     int* stats_host = nullptr;       // pinned
     int proposals = 0;               // propose calls in the running fetch
+    bool lazy_rows = false;          // batch projections only for the rows that get scored (k_catchup)
+    uint8_t* ncol = nullptr;         // lazy rows: batch columns valid per row
+    double* rec_hist = nullptr;      // records of the points selected in the running fetch
+    int64_t rec_hist_cap = 0;
     // general feedback model (label_prob < 1): conditional node sets of the running step
     double *g_eta = nullptr, *g_w = nullptr, *g_mass = nullptr;
     int *g_begin = nullptr, *g_set0 = nullptr, *g_lut = nullptr;
@@ -316,9 +320,31 @@ int prepare_nodes(ital_shard* s) {
     return ITAL_OK;
 }
 
+// lazy rows: make the listed rows' batch projections current before they are scored
+int launch_catchup(ital_shard* s, int64_t items_hint) {
+    if (!s->lazy_rows || s->t == 0) return ITAL_OK;
+    const int threads = 256, warps = threads / 32;
+    const int blocks = grid_for(s, std::max<int64_t>(1, items_hint), warps, 8);
+    const size_t smem = (size_t)warps * (32 + s->w_cap) * sizeof(double);
+    const double neg2ls2 = -2.0 * (s->ls * s->ls);
+    if (s->x_dtype == ITAL_F32)
+        k_catchup<float><<<blocks, threads, smem, s->stream>>>(s->counters, s->worklist, (const float*)s->X, (int)s->d,
+                                                               (int)s->d_pad, s->rec_hist, record_doubles(s), s->w_cap,
+                                                               s->W, s->t, s->sqn, s->U, s->ldu, s->ncol, s->var, neg2ls2);
+    else
+        k_catchup<double><<<blocks, threads, smem, s->stream>>>(s->counters, s->worklist, (const double*)s->X, (int)s->d,
+                                                                (int)s->d_pad, s->rec_hist, record_doubles(s), s->w_cap,
+                                                                s->W, s->t, s->sqn, s->U, s->ldu, s->ncol, s->var, neg2ls2);
+    s->launches++;
+    CU(cudaGetLastError());
+    return ITAL_OK;
+}
+
 // Score the rows in the worklist.  `items_hint` bounds the number of items (the true count is on the device);
 // few items -> one 256-thread block per candidate (latency), many -> one warp per candidate (throughput).
 int launch_eval(ital_shard* s, int64_t items_hint, bool block_per_candidate) {
+    int rc_c = launch_catchup(s, items_hint);
+    if (rc_c) return rc_c;
     const int threads = 256;
     const int blocks = grid_for(s, std::max<int64_t>(1, items_hint), block_per_candidate ? 1 : threads / 32, 8);
     EvalArgs a;
@@ -417,6 +443,7 @@ int propose_general(ital_shard* s) {
     a.score = s->score;
     a.gain = s->gain;
     a.n_scored = s->counters + 2;
+    if ((rc = launch_catchup(s, s->n))) return rc;
     const size_t smem = ((size_t)3 * gs.n_groups + 2 * gs.n_sets + (size_t)gs.n_groups * 24 + 8) * sizeof(double);
     CU(cudaFuncSetAttribute(k_eval_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int blocks = grid_for(s, s->n, 1, 8);
@@ -492,12 +519,13 @@ int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_o
 int commit_dev(ital_shard* s, const double* recs_dev, int n_records, int extend) {
     if (s->t >= kMaxBatch) return fail(ITAL_EINVAL, "batches of more than %d samples are not supported", kMaxBatch);
     k_pick_winner<<<1, 256, 0, s->stream>>>(recs_dev, n_records, record_doubles(s), s->t, s->W, s->rec_in_dev,
-                                            s->base_m_dev, s->base_L_dev, s->sel_dev); s->launches++;
+                                            s->base_m_dev, s->base_L_dev, s->sel_dev, s->rec_hist, s->mask,
+                                            s->row_offset, s->n, kSelected); s->launches++;
     CU(cudaGetLastError());
-    if (extend) {
+    if (extend && !s->lazy_rows) {      // lazy rows: the projection is extended on demand by k_catchup instead
         const int col = s->W + s->t;
-        int rc = s->x_dtype == ITAL_F32 ? launch_extend_t<float>(s, col, 0, 0.0, kSelected)
-                                        : launch_extend_t<double>(s, col, 0, 0.0, kSelected);
+        int rc = s->x_dtype == ITAL_F32 ? launch_extend_t<float>(s, col, 0, 0.0, 0)
+                                        : launch_extend_t<double>(s, col, 0, 0.0, 0);
         if (rc) return rc;
     }
     s->t += 1;
@@ -509,7 +537,7 @@ void free_all(ital_shard* s) {
     void* ptrs[] = {s->X, s->sqn, s->m, s->v, s->U, s->gain, s->score, s->mask, s->worklist, s->counters,
                     s->block_best, s->best, s->thr_dev, s->rec_dev, s->rec_in_dev, s->idx_dev, s->eta_dev,
                     s->w_dev, s->masses_dev, s->group_dev, s->orth_dev, s->gl_dev, s->base_m_dev, s->base_L_dev, s->sel_dev,
-                    s->hbase_dev, s->stats_dev, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev};
+                    s->hbase_dev, s->stats_dev, s->ncol, s->rec_hist, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->rec_host) cudaFreeHost(s->rec_host);
@@ -597,6 +625,7 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
         CU(cudaMalloc(&s->gain, (size_t)s->n * sizeof(double)));
         CU(cudaMalloc(&s->score, (size_t)s->n * sizeof(double)));
         CU(cudaMalloc(&s->mask, (size_t)s->n));
+        CU(cudaMalloc(&s->ncol, (size_t)s->n));
         CU(cudaMalloc(&s->worklist, (size_t)s->n * sizeof(int)));
         CU(cudaMalloc(&s->counters, 4 * sizeof(int)));
         CU(cudaMalloc(&s->block_best, kArgmaxBlocks * sizeof(Best)));
@@ -794,6 +823,15 @@ int ital_fetch_begin(ital_shard* s, double label_prob, double mistake_prob) {
     if (rc) return rc;
     rc = ensure_record_buffers(s, 1);
     if (rc) return rc;
+    const int64_t hist_need = record_doubles(s) * (kMaxBatch + 1);
+    if (hist_need > s->rec_hist_cap) {
+        CU(cudaStreamSynchronize(s->stream));
+        if (s->rec_hist) CU(cudaFree(s->rec_hist));
+        s->rec_hist = nullptr;
+        CU(cudaMalloc(&s->rec_hist, (size_t)hist_need * sizeof(double)));
+        s->rec_hist_cap = hist_need;
+    }
+    if (s->lazy_rows) CU(cudaMemsetAsync(s->ncol, 0, (size_t)s->n, s->stream));
     const double hb0[2] = {0.0, 1.0};                   // first step: no base, total mass 1
     memcpy(s->sel_host + 30, hb0, sizeof hb0);          // (pinned scratch at the tail of the selection mirror)
     CU(cudaMemcpyAsync(s->hbase_dev, s->sel_host + 30, sizeof hb0, cudaMemcpyHostToDevice, s->stream));
@@ -1001,6 +1039,13 @@ int ital_predict(ital_shard* s, const double* Xt, int64_t mrows, double* out_mea
     CU(cudaFree(xt_dev));
     CU(cudaFree(mean_dev));
     if (var_dev) CU(cudaFree(var_dev));
+    return ITAL_OK;
+}
+
+int ital_set_lazy_rows(ital_shard* s, int on) {
+    if (!s) return fail(ITAL_EINVAL, "null shard");
+    if (s->fetching) return fail(ITAL_ESTATE, "ital_set_lazy_rows during a fetch");
+    s->lazy_rows = on != 0;
     return ITAL_OK;
 }
 

@@ -240,6 +240,84 @@ k_extend(const XT* __restrict__ X, int64_t n, int d, int d_pad, const double* __
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Lazy rows: bring the batch-conditional projection of the LISTED rows up to date (columns ncol[i] .. t-1) from
+// the stored records of the points selected so far, instead of streaming the whole pool once per greedy step
+// (k_extend).  One warp per row; the arithmetic (per-lane partial sums, order of the lane sum, fma chains of the
+// projection) is the same as in k_extend, so a row gets bit-identical entries either way.
+template <typename XT>
+__global__ void __launch_bounds__(256) k_catchup(const int* __restrict__ count, const int* __restrict__ list,
+                                                 const XT* __restrict__ X, int d, int d_pad,
+                                                 const double* __restrict__ rec_hist, int64_t rec_len, int w_cap,
+                                                 int W, int t, const double* __restrict__ sqn,
+                                                 double* __restrict__ U, int64_t ldu, uint8_t* __restrict__ ncol,
+                                                 double var, double neg2ls2) {
+    constexpr int VN = Vec<XT>::N;
+    extern __shared__ double csm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarp_blk = blockDim.x >> 5;
+    double* part = csm + (size_t)wib * (32 + w_cap);   // [32]
+    double* uv = part + 32;                             // [w_cap] projection entries of the row
+    const int nchunks = d_pad / (32 * VN);
+    const bool fixed = nchunks == 1 || nchunks == 2 || nchunks == 4;    // k_extend<XT, NC> vs k_extend<XT, 0>
+    const int n_items = *count;
+    for (int item = blockIdx.x * nwarp_blk + wib; item < n_items; item += gridDim.x * nwarp_blk) {
+        const int64_t i = list[item];
+        const int c0 = ncol[i];
+        if (c0 >= t) continue;
+        for (int j = lane; j < W + c0; j += 32) uv[j] = U[(int64_t)j * ldu + i];
+        const XT* xrow = X + i * (int64_t)d_pad;
+        const double sq = sqn[i];
+        for (int col = c0; col < t; ++col) {
+            const double* rec = rec_hist + (int64_t)col * rec_len;
+            const double* z = rec + 8 + w_cap;
+            double a0 = 0.0, a1 = 0.0;
+            for (int c = 0; c < nchunks; ++c) {
+                Vec<XT> x;
+                x.load(xrow + (c * 32 + lane) * VN);
+#pragma unroll
+                for (int e = 0; e < VN; e += 2) {
+                    const int cc = (c * 32 + lane) * VN + e;
+                    const double z0 = cc < d ? z[cc] : 0.0, z1 = cc + 1 < d ? z[cc + 1] : 0.0;
+                    if (fixed) {
+                        a0 = fma(x.get(e), z0, a0);
+                        a1 = fma(x.get(e + 1), z1, a1);
+                    } else {
+                        a0 = fma(x.get(e), z0, a0);
+                        a0 = fma(x.get(e + 1), z1, a0);
+                    }
+                }
+            }
+            __syncwarp();
+            part[lane] = fixed ? a0 + a1 : a0;
+            __syncwarp();
+            double e_new = 0.0;
+            if (lane == 0) {
+                double dot = 0.0;
+                for (int l = 0; l < 32; ++l) dot += part[l];
+                const double kv = var * exp((sq + rec[4] - 2.0 * dot) / neg2ls2);
+                const double* ur = rec + 8;
+                const int Wc = W + col;
+                double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+                int j = 0;
+                for (; j + 4 <= Wc; j += 4) {
+                    p0 = fma(uv[j + 0], ur[j + 0], p0);
+                    p1 = fma(uv[j + 1], ur[j + 1], p1);
+                    p2 = fma(uv[j + 2], ur[j + 2], p2);
+                    p3 = fma(uv[j + 3], ur[j + 3], p3);
+                }
+                for (; j < Wc; ++j) p0 = fma(uv[j], ur[j], p0);
+                const double piv = sqrt(fmax(rec[3], 1e-300));
+                e_new = (kv - ((p0 + p1) + (p2 + p3))) / piv;
+                uv[Wc] = e_new;
+                U[(int64_t)Wc * ldu + i] = e_new;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) ncol[i] = (uint8_t)t;
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // First greedy step: one variable, closed form (ital/ital.py:364-369 and 183-224 with one configuration).
 // Also seeds the lazy-greedy bound: gain = score.
 __global__ void __launch_bounds__(256) k_score0(int64_t n, const double* __restrict__ m,
@@ -818,7 +896,9 @@ __global__ void __launch_bounds__(1024) k_snq_masses(int t, int64_t N, const dou
 // to the batch state kept on the device (mean, Cholesky row of the batch's posterior covariance, selection list).
 __global__ void __launch_bounds__(256) k_pick_winner(const double* __restrict__ recs, int G, int64_t rec_len, int t,
                                                      int W, double* __restrict__ rec_in, double* __restrict__ base_m,
-                                                     double* __restrict__ base_L, double* __restrict__ sel) {
+                                                     double* __restrict__ base_L, double* __restrict__ sel,
+                                                     double* __restrict__ rec_hist, uint8_t* __restrict__ mask,
+                                                     int64_t row_offset, int64_t n, uint8_t mark_bits) {
     __shared__ int win_s;
     if (threadIdx.x == 0) {
         int win = -1;
@@ -843,8 +923,13 @@ __global__ void __launch_bounds__(256) k_pick_winner(const double* __restrict__ 
         return;
     }
     const double* r = recs + (int64_t)win * rec_len;
-    for (int64_t k = threadIdx.x; k < rec_len; k += blockDim.x) rec_in[k] = r[k];
+    for (int64_t k = threadIdx.x; k < rec_len; k += blockDim.x) {
+        rec_in[k] = r[k];
+        rec_hist[(int64_t)t * rec_len + k] = r[k];      // kept for rows that catch up later (k_catchup)
+    }
     if (threadIdx.x == 0) {
+        const long long loc = (long long)r[0] - row_offset;
+        if (loc >= 0 && loc < n) mask[loc] |= mark_bits;    // the chosen row leaves the candidate set
         base_m[t] = r[2];
         for (int j = 0; j < t; ++j) base_L[t * kBaseStride + j] = r[8 + W + j];
         base_L[t * kBaseStride + t] = sqrt(fmax(r[3], 1e-300));

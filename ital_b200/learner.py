@@ -190,14 +190,16 @@ class ITAL(object):
     torch.distributed group (or True for the default group) to shard the rows over one GPU per process;
     `exhaustive` scores every candidate each step instead of pruning with the lazy-greedy bound;
     `local_rows=(first_row, n_total)` declares that `data` holds only this process's contiguous block of a
-    pool of n_total rows (for pools too large to replicate on every host process; no `queries` then).
+    pool of n_total rows (for pools too large to replicate on every host process; no `queries` then);
+    `lazy_rows` extends the batch-conditional projections only for the rows that get scored instead of streaming
+    the whole pool once per greedy step (same batch, same scores bit for bit; see include/ital_b200.h).
     """
 
     def __init__(self, data=None, queries=[], length_scale=0.1, var=1.0, noise=1e-6,
                  label_prob=1.0, mistake_prob=0.0, top_candidates=None, change_estimation_subset=0,
                  clip_cov=0, label_estimation='mean', monte_carlo_num_rel=None, monte_carlo_num_fb=None,
                  parallelized=True, device=None, storage='auto', process_group=None, exhaustive=False,
-                 local_rows=None):
+                 local_rows=None, lazy_rows=False):
         self.length_scale, self.var, self.noise = length_scale, var, noise
         self.label_prob, self.mistake_prob = label_prob, mistake_prob
         self.top_candidates = top_candidates
@@ -207,6 +209,7 @@ class ITAL(object):
         self.monte_carlo_num_rel, self.monte_carlo_num_fb = monte_carlo_num_rel, monte_carlo_num_fb
         self.parallelized = parallelized            # accepted for compatibility; the GPU is the parallelism
         self.exhaustive = exhaustive
+        self._lazy_rows = bool(lazy_rows)
         self._storage = storage
         self._device = device
         self._local_rows = local_rows
@@ -215,6 +218,16 @@ class ITAL(object):
         self._shard = None
         self.last_fetch_stats = []
         self.fit(data, queries)
+
+    @property
+    def lazy_rows(self):
+        return self._lazy_rows
+
+    @lazy_rows.setter
+    def lazy_rows(self, on):
+        self._lazy_rows = bool(on)
+        if self._shard is not None:
+            _capi.check(self._shard.lib.ital_set_lazy_rows(self._shard.handle, int(self._lazy_rows)))
 
     # ---- ActiveRetrievalBase ---------------------------------------------------------------------------
     def fit(self, data, queries=[]):                                            # retrieval_base.py:34-45
@@ -261,6 +274,7 @@ class ITAL(object):
         self._shard = _Shard(Xl, _capi.ITAL_F32 if storage == 'float32' else _capi.ITAL_F64, lo, self._n,
                              self.length_scale, self.var, self.noise, device)
         self.gp = _GPView(self)
+        self.lazy_rows = self._lazy_rows
         self.reset()
 
     def reset(self):                                                            # retrieval_base.py:48-61

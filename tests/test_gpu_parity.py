@@ -156,6 +156,18 @@ def test_synthetic_parity_exhaustive_and_pruned(n, d, storage):
     gpu.exhaustive = False
     assert gpu.fetch_unlabelled(4) == ret
     stats = gpu._fetch_stepwise(4) and gpu.last_fetch_stats
+    # lazy rows: projections extended on demand for the scored rows only -- same batch, same scores bit for bit
+    stream_scores = np.array(gpu.last_fetch_scores)
+    gpu.lazy_rows = True
+    assert gpu.fetch_unlabelled(4) == ret
+    assert np.array_equal(np.array(gpu.last_fetch_scores), stream_scores)
+    gpu.exhaustive = True
+    assert gpu._fetch_stepwise(4, keep_scores=True) == ret
+    ora.fetch_unlabelled(4, forced=ret)
+    for sc, tr in zip(gpu.last_step_scores, ora.trace):
+        np.testing.assert_allclose(sc[tr['candidates']], tr['scores'], rtol=SCORE_RTOL, atol=SCORE_ATOL)
+    gpu.exhaustive = False
+    gpu.lazy_rows = False
     # [0] rows in the final worklist, [1] rows scored by quadrature (-1: closed form), [2] nodes
     assert stats[0][1] == -1 and all(0 < s[1] <= n + 2 * 148 for s in stats[1:]), stats
     assert [int(s[2]) for s in stats] == [1, 64, 1024, 13824]
@@ -171,6 +183,7 @@ def test_repeated_rounds_track_the_oracle():
     for L in (gpu, ora):
         L.update({0: 1})
     for rnd in range(5):
+        gpu.lazy_rows = bool(rnd % 2)                 # alternate streaming and on-demand projections
         a, b = gpu.fetch_unlabelled(4), ora.fetch_unlabelled(4)
         assert a == b, rnd
         fb = {i: int(y[i]) for i in a}
