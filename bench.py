@@ -118,11 +118,38 @@ class ClockSampler(object):
                 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
+def ncu_traffic():
+    """DRAM bytes per k_extend launch from the committed `ncu --set full` capture (profiles/), or None."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_k_extend_full.txt')))
+    if not files:
+        return None, None
+    rd = wr = None
+    for line in open(files[-1]):
+        f = line.split()
+        if line.startswith('dram__bytes_read.sum'):
+            rd = np.mean([float(x) for x in f[2:]]) * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}[f[1]]
+        if line.startswith('dram__bytes_write.sum'):
+            wr = np.mean([float(x) for x in f[2:]]) * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}[f[1]]
+    if rd is None or wr is None:
+        return None, None
+    return float(rd + wr), os.path.relpath(files[-1], ROOT)
+
+
 def measured_peak():
     try:
         return float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs'
     except Exception:
         return 6650.0, 'fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)'
+
+
+def _one_blas_thread():
+    """Pool workers run one BLAS thread each (README.md:78-87 of the reference: MKL/OMP/OPENBLAS_NUM_THREADS=1 when
+    parallelized=True); the limiter object has to stay alive for the life of the worker."""
+    global _BLAS_LIMIT
+    from threadpoolctl import threadpool_limits
+    _BLAS_LIMIT = threadpool_limits(limits=1)
 
 
 def oracle_fetch_rate(rows, d, batch, procs, steps=1, warmup=0, budget_s=None):
@@ -133,7 +160,7 @@ def oracle_fetch_rate(rows, d, batch, procs, steps=1, warmup=0, budget_s=None):
     ora = OracleITAL(X.astype(np.float64), length_scale=1.0)
     for fb in labelled_state(assign[:65536]):
         ora.update(fb)
-    pool = mp.get_context('fork').Pool(procs) if procs > 1 else None
+    pool = mp.get_context('fork').Pool(procs, initializer=_one_blas_thread) if procs > 1 else None
     try:
         times = []
         for it in range(warmup + steps):
@@ -283,12 +310,13 @@ def main():
     value = ranked * args.steps / dev
     peak, peak_src = measured_peak()
     achieved = (nbytes.value / 1e9) / (ms.value / 1e3) if ms.value > 0 else 0.0
-    # host<->device bytes of one fetch through the public API: per committed step a point record down and the
-    # quadrature nodes + the extension parameters up (counted from the buffers the library copies)
-    rec_bytes = shard.record_doubles() * 8
-    node_bytes = sum((2 * q) ** t * (t + 1) * 8 + (2 ** t) * 12 for t, q in ((1, 32), (2, 16), (3, 12))[:args.batch - 1])
-    h2d = node_bytes + (args.batch - 1) * (32 + rec_bytes)
-    d2h = args.batch * (rec_bytes + 16)
+    traffic, traffic_src = ncu_traffic()
+    # host<->device bytes of one fetch through the public API (counted from the buffers the library copies): the
+    # greedy loop is device-resident (nodes, winner records and the batch state never leave the GPU), so a call
+    # uploads 16 bytes of step-0 constants and reads back the selection list and the per-step counters.  With more
+    # than one GPU the records cross NVLink inside the NCCL all-gather, not the host.
+    h2d = 16
+    d2h = 32 * 8 + 16 * 4 * 4
 
     exh = None
     if args.exhaustive_steps > 0:
@@ -330,7 +358,8 @@ def main():
         'gpu_launches': launches,
         'clocks': clocks,
         'roofline': {'bound': 'hbm', 'kernel': 'k_extend (streaming pass: row . z in f64, RBF, projection)',
-                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+                     'traffic_source': traffic_src,
                      'peak_source': peak_src, 'launches': int(nl.value),
                      'avg_launch_ms': ms.value / max(1, nl.value),
                      'algorithmic_bytes_per_launch': nbytes.value / max(1, nl.value),
