@@ -248,11 +248,13 @@ int make_record(ital_shard* s, long long local_row, double* dst_dev) {
     if (s->x_dtype == ITAL_F32)
         k_record<float><<<1, 256, 0, s->stream>>>(local_row, s->best, s->row_offset, (const float*)s->X, (int)s->d,
                                                   (int)s->d_pad, s->sqn, s->m, s->v, s->U, s->ldu, s->W,
-                                                  s->W + s->t, s->w_cap, s->gain, dst_dev, shift, s->hbase_dev);
+                                                  s->W + s->t, s->w_cap, s->gain, dst_dev, shift, s->hbase_dev,
+                                                  s->counters, local_row < 0 ? s->stats_dev + 4 * s->t : nullptr);
     else
         k_record<double><<<1, 256, 0, s->stream>>>(local_row, s->best, s->row_offset, (const double*)s->X,
                                                    (int)s->d, (int)s->d_pad, s->sqn, s->m, s->v, s->U, s->ldu,
-                                                   s->W, s->W + s->t, s->w_cap, s->gain, dst_dev, shift, s->hbase_dev); s->launches++;
+                                                   s->W, s->W + s->t, s->w_cap, s->gain, dst_dev, shift, s->hbase_dev,
+                                                   s->counters, local_row < 0 ? s->stats_dev + 4 * s->t : nullptr); s->launches++;
     CU(cudaGetLastError());
     return ITAL_OK;
 }
@@ -491,15 +493,15 @@ int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_o
             // top rows by bound instead is worse: they cluster around the previous pick, whose neighbours have
             // just lost their gain; measured 882 vs 399 rows left for stage B at t = 3 on SYN-1M.)
             const int ba = std::min(kArgmaxBlocks, std::min(blocks, 2 * s->num_sms));
-            k_argmax_rows<<<ba, 256, 0, s->stream>>>(s->n, s->gain, s->mask, s->block_best, s->score); s->launches++;
+            k_argmax_rows<<<ba, 1024, 0, s->stream>>>(s->n, s->gain, s->mask, s->block_best, s->score); s->launches++;
             k_list_from_blocks<<<1, 512, 0, s->stream>>>(s->block_best, ba, s->counters, s->worklist); s->launches++;
             CU(cudaGetLastError());
             rc = launch_eval(s, ba, true);
             if (rc) return rc;
-            k_argmax_list<<<1, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->best + 1); s->launches++;
-            // stage B: every row whose bound still reaches the best exact score of stage A
-            CU(cudaMemsetAsync(s->counters, 0, sizeof(int), s->stream));
-            k_threshold_from_best<<<1, 1, 0, s->stream>>>(s->best + 1, s->hbase_dev, floor_score, kPruneMargin, s->thr_dev); s->launches++;
+            // best of stage A and, in the same kernel, the threshold of stage B: every row whose bound still
+            // reaches the best exact score found so far
+            k_argmax_list<<<1, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->best + 1, s->hbase_dev,
+                                                    floor_score, kPruneMargin, s->thr_dev, s->counters); s->launches++;
             k_worklist<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->n, s->mask, s->gain, s->thr_dev, 0,
                                                                         s->counters, s->worklist); s->launches++;
             CU(cudaGetLastError());
@@ -509,7 +511,6 @@ int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_o
         }
         CU(cudaGetLastError());
     }
-    k_save_counters<<<1, 32, 0, s->stream>>>(s->counters, s->stats_dev + 4 * s->t); s->launches++;
     s->step_nodes[s->t] = (double)s->n_nodes;
     s->proposals = s->t + 1;
     return make_record(s, -1, rec_out);

@@ -349,8 +349,8 @@ __global__ void __launch_bounds__(256) k_score0(int64_t n, const double* __restr
         score[i] = s;
     }
     // block reduction
-    __shared__ double ss[8];
-    __shared__ long long si[8];
+    __shared__ double ss[32];
+    __shared__ long long si[32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double os = __shfl_xor_sync(0xffffffffu, bs, o);
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(256) k_score0(int64_t n, const double* __restr
 }
 
 // argmax of `values` over candidate rows (mask == 0); stage 1 of 2
-__global__ void __launch_bounds__(256) k_argmax_rows(int64_t n, const double* __restrict__ values,
+__global__ void __launch_bounds__(1024) k_argmax_rows(int64_t n, const double* __restrict__ values,
                                                      const uint8_t* __restrict__ mask,
                                                      Best* __restrict__ block_best,
                                                      double* __restrict__ clear_score) {
@@ -379,8 +379,8 @@ __global__ void __launch_bounds__(256) k_argmax_rows(int64_t n, const double* __
         if (mask[i] == 0 && better(values[i], i, bs, bi)) { bs = values[i]; bi = i; }
         if (clear_score != nullptr) clear_score[i] = qnan;      // "not scored in this step"
     }
-    __shared__ double ss[8];
-    __shared__ long long si[8];
+    __shared__ double ss[32];
+    __shared__ long long si[32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double os = __shfl_xor_sync(0xffffffffu, bs, o);
@@ -401,7 +401,11 @@ __global__ void __launch_bounds__(256) k_argmax_rows(int64_t n, const double* __
 __global__ void __launch_bounds__(256) k_argmax_list(const int* __restrict__ count,
                                                      const int* __restrict__ list,
                                                      const double* __restrict__ score,
-                                                     Best* __restrict__ block_best) {
+                                                     Best* __restrict__ block_best,     // gridDim.x == 1: final
+                                                     const double* __restrict__ h_base = nullptr,
+                                                     double floor_score = 0.0, double margin = 0.0,
+                                                     double* __restrict__ thr_gain = nullptr,
+                                                     int* __restrict__ reset_count = nullptr) {
     const int n = *count;
     double bs = 0.0;
     long long bi = -1;
@@ -409,8 +413,8 @@ __global__ void __launch_bounds__(256) k_argmax_list(const int* __restrict__ cou
         const long long i = list[k];
         if (better(score[i], i, bs, bi)) { bs = score[i]; bi = i; }
     }
-    __shared__ double ss[8];
-    __shared__ long long si[8];
+    __shared__ double ss[32];
+    __shared__ long long si[32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double os = __shfl_xor_sync(0xffffffffu, bs, o);
@@ -424,6 +428,12 @@ __global__ void __launch_bounds__(256) k_argmax_list(const int* __restrict__ cou
             if (better(ss[w], si[w], bs, bi)) { bs = ss[w]; bi = si[w]; }
         block_best[blockIdx.x].score = bs;
         block_best[blockIdx.x].idx = bi;
+        if (thr_gain != nullptr) {      // stage B threshold: a row can still win only if its bound reaches this
+            double thr = floor_score;
+            if (bi >= 0 && bs == bs) thr = fmax(thr, bs);
+            *thr_gain = thr - margin - *h_base;
+            *reset_count = 0;           // the worklist is rebuilt next
+        }
     }
 }
 
@@ -434,8 +444,8 @@ __global__ void __launch_bounds__(256) k_argmax_final(const Best* __restrict__ b
     long long bi = -1;
     for (int k = threadIdx.x; k < nblocks; k += blockDim.x)
         if (better(block_best[k].score, block_best[k].idx, bs, bi)) { bs = block_best[k].score; bi = block_best[k].idx; }
-    __shared__ double ss[8];
-    __shared__ long long si[8];
+    __shared__ double ss[32];
+    __shared__ long long si[32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double os = __shfl_xor_sync(0xffffffffu, bs, o);
@@ -989,7 +999,10 @@ __global__ void __launch_bounds__(256) k_record(long long row, const Best* __res
                                                 const double* __restrict__ v, const double* __restrict__ U,
                                                 int64_t ldu, int W_lab, int W_tot, int w_cap,
                                                 const double* __restrict__ gain, double* __restrict__ rec,
-                                                double shift_coef, const double* __restrict__ h_base) {
+                                                double shift_coef, const double* __restrict__ h_base,
+                                                const int* __restrict__ counters = nullptr,
+                                                int* __restrict__ counters_dst = nullptr) {
+    if (counters_dst != nullptr && threadIdx.x < 4) counters_dst[threadIdx.x] = counters[threadIdx.x];
     // shift_coef * (total mass): what a user who mislabels with probability mistake_prob adds to every score of
     // the step (DESIGN.md "mistake_prob"); 0 for the perfect user
     double score = 0.0;
