@@ -66,8 +66,6 @@ struct ital_shard {
     double* rec_in_dev = nullptr;    // the record k_extend reads (one record)
     double* rec_in_host = nullptr;   // pinned staging of rec_in_dev
     int64_t rec_cap = 0;
-    char* nodes_host = nullptr;      // pinned staging of the quadrature nodes
-    size_t nodes_host_cap = 0;
     int64_t* idx_dev = nullptr;      // scratch for index lists
     int64_t idx_cap = 0;
     // quadrature nodes of the current step
@@ -104,7 +102,6 @@ struct ital_shard {
     std::vector<double> lab_sqn, lab_y;
     std::vector<int64_t> lab_idx;
     std::vector<int64_t> selected;           // global indices selected in this fetch
-    std::vector<int64_t> restricted;         // local rows carrying kRestricted
 
     // predict() scratch
     double *lab_x_dev = nullptr, *lab_sqn_dev = nullptr, *w_vec_dev = nullptr, *LK_dev = nullptr;
@@ -543,7 +540,6 @@ void free_all(ital_shard* s) {
         if (p) cudaFree(p);
     if (s->rec_host) cudaFreeHost(s->rec_host);
     if (s->rec_in_host) cudaFreeHost(s->rec_in_host);
-    if (s->nodes_host) cudaFreeHost(s->nodes_host);
     if (s->sel_host) cudaFreeHost(s->sel_host);
     if (s->stats_host) cudaFreeHost(s->stats_host);
 }
@@ -559,7 +555,6 @@ int reset_model(ital_shard* s) {
     s->lab_y.clear();
     s->lab_idx.clear();
     s->selected.clear();
-    s->restricted.clear();
     s->lab_dev_valid = false;
     const int blocks = grid_for(s, s->n, 256);
     k_fill<<<blocks, 256, 0, s->stream>>>(s->m, s->n, 0.0); s->launches++;

@@ -462,16 +462,8 @@ __global__ void __launch_bounds__(256) k_argmax_final(const Best* __restrict__ b
     }
 }
 
-// Stage B threshold: a row can still win only if gain_i + H(base) >= best exact score so far - margin.
-__global__ void k_threshold_from_best(const Best* __restrict__ best, const double* __restrict__ h_base,
-                                      double floor_score, double margin, double* __restrict__ thr_gain) {
-    double thr = floor_score;
-    if (best->idx >= 0 && best->score == best->score) thr = fmax(thr, best->score);
-    *thr_gain = thr - margin - *h_base;
-}
-
-// Lazy-greedy worklist: candidate rows whose upper bound gain_i reaches *thr_gain (a device scalar prepared by
-// k_threshold_from_best); every candidate when exhaustive.  Rows already scored in this
+// Lazy-greedy worklist: candidate rows whose upper bound gain_i reaches *thr_gain (a device scalar written by
+// k_argmax_list at the end of stage A); every candidate when exhaustive.  Rows already scored in this
 // step are left out unless `keep_scored` (the final list must contain them for the argmax).
 __global__ void __launch_bounds__(256) k_worklist(int64_t n, const uint8_t* __restrict__ mask,
                                                   const double* __restrict__ gain,
@@ -948,11 +940,6 @@ __global__ void __launch_bounds__(256) k_pick_winner(const double* __restrict__ 
     }
 }
 
-// keep the per-step counters for ital_fetch_stats
-__global__ void k_save_counters(const int* __restrict__ counters, int* __restrict__ dst) {
-    if (threadIdx.x < 4) dst[threadIdx.x] = counters[threadIdx.x];
-}
-
 // worklist = the per-block winners of an argmax stage (the most promising candidates, scored first)
 __global__ void k_list_from_blocks(const Best* __restrict__ block_best, int nblocks, int* __restrict__ count,
                                    int* __restrict__ list) {
@@ -971,13 +958,6 @@ __global__ void k_mask_rows(uint8_t* __restrict__ mask, const int64_t* __restric
                             uint8_t set_bits) {
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += (int64_t)gridDim.x * blockDim.x)
         mask[rows[k]] |= set_bits;
-}
-
-// mark the row of a device-resident point record (if it is local)
-__global__ void k_mask_record(uint8_t* __restrict__ mask, const double* __restrict__ rec, int64_t row_offset,
-                              int64_t n, uint8_t set_bits) {
-    const long long loc = (long long)rec[0] - row_offset;
-    if (threadIdx.x == 0 && blockIdx.x == 0 && loc >= 0 && loc < n) mask[loc] |= set_bits;
 }
 
 __global__ void k_mask_all(uint8_t* __restrict__ mask, int64_t n, uint8_t and_bits, uint8_t or_bits) {
