@@ -110,6 +110,11 @@ int ital_fetch(ital_shard* s, int k, double label_prob, double mistake_prob, int
  * prunes most rows. */
 int ital_set_lazy_rows(ital_shard* s, int on);
 
+/* Streaming pass variant (on by default): stage the rows through shared memory with the bulk-copy engine (TMA,
+ * cp.async.bulk + mbarrier; k_extend_bulk) where the tuned shape applies (2 KB rows, e.g. d = 512 float32), else
+ * coalesced register loads (k_extend).  Same results bit for bit either way. */
+int ital_set_bulk_stream(ital_shard* s, int on);
+
 /* Per-step diagnostics of the last propose: [0] candidates considered, [1] candidates scored exactly,
  * [2] quadrature nodes, [3] H(base), [4] flagged (conditional variance < 100 * noise), [5..7] reserved. */
 int ital_fetch_stats(const ital_shard* s, double* out8);
@@ -137,8 +142,9 @@ int64_t ital_launch_count(const ital_shard* s);
 
 /* Host-side pieces exposed for CPU-only tests (no GPU needed) ------------------------------------------- */
 /* Shared quadrature nodes of one greedy step (see oracle/orthant.py for the rule): base mean m[t], lower
- * Cholesky factor L[t*t] (row-major).  Returns the node count N = (2q)^t; if eta != NULL fills eta[t*N]
- * (dimension-major), w[N], orth[N], sorted by orthant, and masses[2^t]. */
+ * Cholesky factor L[t*t] (row-major).  With eta == NULL returns the capacity (2q)^t; otherwise fills eta[t*N]
+ * (dimension-major, stride N), w[N], orth[N], sorted by orthant, and masses[2^t], and returns N, the number of
+ * nodes kept (nodes lighter than 1e-13 are dropped). */
 int64_t ital_snq_nodes(int t, const double* m, const double* L, double* eta, double* w, int32_t* orth,
                        double* masses);
 int ital_snq_order(int t);

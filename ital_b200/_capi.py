@@ -42,6 +42,7 @@ SIGNATURES = {
     'ital_fetch': (ctypes.c_int, [_shard_p, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                   _c_int64_p, _c_double_p]),
     'ital_set_lazy_rows': (ctypes.c_int, [_shard_p, ctypes.c_int]),
+    'ital_set_bulk_stream': (ctypes.c_int, [_shard_p, ctypes.c_int]),
     'ital_fetch_stats': (ctypes.c_int, [_shard_p, _c_double_p]),
     'ital_last_scores': (ctypes.c_int, [_shard_p, _c_double_p]),
     'ital_rel_mean': (ctypes.c_int, [_shard_p, _c_double_p]),

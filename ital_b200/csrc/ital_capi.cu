@@ -81,6 +81,7 @@ struct ital_shard {
     int* stats_host = nullptr;       // pinned
     int proposals = 0;               // propose calls in the running fetch
     bool lazy_rows = false;          // batch projections only for the rows that get scored (k_catchup)
+    bool bulk_stream = true;         // X stream staged by the bulk-copy engine (k_extend_bulk) where it applies
     uint8_t* ncol = nullptr;         // lazy rows: batch columns valid per row
     double* rec_hist = nullptr;      // records of the points selected in the running fetch
     int64_t rec_hist_cap = 0;
@@ -192,6 +193,25 @@ int launch_extend_t(ital_shard* s, int W_used, int labelled, double y, uint8_t m
         CU(cudaEventCreate(&ev1));
         CU(cudaEventRecord(ev0, s->stream));
     }
+    if (s->bulk_stream && nchunks == 4 && s->d_pad * sizeof(XT) == 2048) {    // 2 KB rows: the tuned shape
+        // TMA-staged variant: one CTA per SM, every warp with a private ring of slots
+        const int bthreads = kBulkThreads, bwarps = bthreads / 32;
+        const size_t ring = (size_t)bwarps * kBulkSlots * kBulkRows * s->d_pad * sizeof(XT);
+        const size_t bsmem = ring + ((size_t)bwarps * 32 * 33 + ((W_used + 1) & ~1)) * sizeof(double) +
+                             (size_t)bwarps * kBulkSlots * sizeof(uint64_t);
+        const int bblocks = (int)std::min<int64_t>((units + bwarps - 1) / bwarps, (int64_t)s->num_sms);
+#define ITAL_LAUNCH_BULK(NCV)                                                                                     \
+    do {                                                                                                          \
+        CU(cudaFuncSetAttribute(k_extend_bulk<XT, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem)); \
+        k_extend_bulk<XT, NCV><<<bblocks, bthreads, bsmem, s->stream>>>(                                           \
+            (const XT*)s->X, s->n, (int)s->d, (int)s->d_pad, s->rec_in_dev, s->w_cap, W_used, s->sqn, s->U,       \
+            s->ldu, s->m, s->v, labelled, y, s->noise, s->var, neg2ls2);                                          \
+    } while (0)
+        if (nchunks == 4) ITAL_LAUNCH_BULK(4);
+        else if (nchunks == 2) ITAL_LAUNCH_BULK(2);
+        else ITAL_LAUNCH_BULK(1);
+#undef ITAL_LAUNCH_BULK
+    } else {
 #define ITAL_LAUNCH_EXT(NCV)                                                                                   \
     do {                                                                                                       \
         CU(cudaFuncSetAttribute(k_extend<XT, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
@@ -204,6 +224,7 @@ int launch_extend_t(ital_shard* s, int W_used, int labelled, double y, uint8_t m
     else if (nchunks == 1) ITAL_LAUNCH_EXT(1);
     else ITAL_LAUNCH_EXT(0);
 #undef ITAL_LAUNCH_EXT
+    }
     s->launches++;
     CU(cudaGetLastError());
     if (s->profiling) {
@@ -294,7 +315,8 @@ int prepare_nodes(ital_shard* s) {
         else ITAL_GEN(3);
 #undef ITAL_GEN
         s->launches++;
-        k_snq_masses<<<1, 1024, 0, s->stream>>>(t, N, s->w_dev, s->orth_dev, s->log1p_eps, s->masses_dev, s->hbase_dev); s->launches++;
+        k_snq_finalize<<<1, 1024, 0, s->stream>>>(t, N, snq::kWMin, s->eta_dev, s->w_dev, s->orth_dev, s->log1p_eps, s->masses_dev,
+                                                  s->hbase_dev, s->counters + 3); s->launches++;
         CU(cudaGetLastError());
         return ITAL_OK;
     }
@@ -359,6 +381,7 @@ int launch_eval(ital_shard* s, int64_t items_hint, bool block_per_candidate) {
     a.orth = s->orth_dev;
     a.group_begin = s->group_dev;
     a.n_nodes = s->n_nodes;
+    a.n_kept = s->counters + 3;
     a.masses = s->masses_dev;
     a.h_base = s->hbase_dev;
     a.log1p_eps = s->log1p_eps;
@@ -1042,6 +1065,12 @@ int ital_set_lazy_rows(ital_shard* s, int on) {
     if (!s) return fail(ITAL_EINVAL, "null shard");
     if (s->fetching) return fail(ITAL_ESTATE, "ital_set_lazy_rows during a fetch");
     s->lazy_rows = on != 0;
+    return ITAL_OK;
+}
+
+int ital_set_bulk_stream(ital_shard* s, int on) {
+    if (!s) return fail(ITAL_EINVAL, "null shard");
+    s->bulk_stream = on != 0;
     return ITAL_OK;
 }
 

@@ -65,6 +65,7 @@ template <> struct Vec<float> {
         asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     }
+    __device__ __forceinline__ void lds(const float* p) { v = *reinterpret_cast<const float4*>(p); }
     __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
     __device__ __forceinline__ double get(int e) const {
         return (double)(e == 0 ? v.x : e == 1 ? v.y : e == 2 ? v.z : v.w);
@@ -76,6 +77,7 @@ template <> struct Vec<double> {
     __device__ __forceinline__ void load(const double* p) {
         asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
     }
+    __device__ __forceinline__ void lds(const double* p) { v = *reinterpret_cast<const double2*>(p); }
     __device__ __forceinline__ void zero() { v = make_double2(0.0, 0.0); }
     __device__ __forceinline__ double get(int e) const { return e == 0 ? v.x : v.y; }
 };
@@ -217,6 +219,161 @@ k_extend(const XT* __restrict__ X, int64_t n, int d, int d_pad, const double* __
 #pragma unroll
             for (int l = 0; l < 32; ++l) dot += part[lane * 33 + l];
             // v * exp((A + B - 2 * C) / s), s = -2 * sigma^2   (ital/gp.py:416)
+            const double kv = var * exp((sqn[i] + zn - 2.0 * dot) / neg2ls2);
+            double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+            const double* u = U + i;
+            int j = 0;
+            for (; j + 4 <= W; j += 4) {
+                p0 = fma(u[(int64_t)(j + 0) * ldu], ur_s[j + 0], p0);
+                p1 = fma(u[(int64_t)(j + 1) * ldu], ur_s[j + 1], p1);
+                p2 = fma(u[(int64_t)(j + 2) * ldu], ur_s[j + 2], p2);
+                p3 = fma(u[(int64_t)(j + 3) * ldu], ur_s[j + 3], p3);
+            }
+            for (; j < W; ++j) p0 = fma(u[(int64_t)j * ldu], ur_s[j], p0);
+            const double e = (kv - ((p0 + p1) + (p2 + p3))) / piv;
+            U[(int64_t)W * ldu + i] = e;
+            if (labelled) {
+                m[i] = fma(e, beta, m[i]);
+                v[i] = fma(-e, e, v[i]);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The streaming pass with the X stream staged through shared memory by the bulk-copy engine (TMA, 1-D
+// cp.async.bulk + mbarrier): every warp owns a private ring of kBulkSlots slots of kBulkRows rows (4 KB at
+// d = 512 float32); lane 0 issues one bulk copy per slot (the rows of a slot are contiguous in HBM) and the whole
+// warp waits on the slot's mbarrier, so the loads need no registers and keep flowing while the warp is in its
+// epilogue.  Arithmetic and its order are those of k_extend (bit-identical results).  NC > 0 only.
+#ifndef ITAL_BULK_ROWS
+#define ITAL_BULK_ROWS 1
+#endif
+#ifndef ITAL_BULK_SLOTS
+#define ITAL_BULK_SLOTS 4
+#endif
+#ifndef ITAL_BULK_THREADS
+#define ITAL_BULK_THREADS 384
+#endif
+constexpr int kBulkRows = ITAL_BULK_ROWS;
+constexpr int kBulkSlots = ITAL_BULK_SLOTS;
+constexpr int kBulkThreads = ITAL_BULK_THREADS;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bulk_issue(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template <typename XT, int NC>
+__global__ void __launch_bounds__(kBulkThreads, 1)
+k_extend_bulk(const XT* __restrict__ X, int64_t n, int d, int d_pad, const double* __restrict__ rec, int w_cap, int W,
+              const double* __restrict__ sqn, double* __restrict__ U, int64_t ldu,
+              double* __restrict__ m, double* __restrict__ v, int labelled, double y, double noise, double var,
+              double neg2ls2) {
+    constexpr int VN = Vec<XT>::N;
+    extern __shared__ __align__(128) unsigned char bsm_raw[];
+    if (rec[0] < 0.0) return;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarp_blk = blockDim.x >> 5;
+    const uint32_t row_bytes = (uint32_t)d_pad * sizeof(XT);
+    const uint32_t slot_bytes = kBulkRows * row_bytes;
+    // layout: [ring of every warp][part of every warp][ur][barriers]
+    unsigned char* ring = bsm_raw + (size_t)wib * kBulkSlots * slot_bytes;
+    double* part = (double*)(bsm_raw + (size_t)nwarp_blk * kBulkSlots * slot_bytes) + (size_t)wib * 32 * 33;
+    double* ur_s = (double*)(bsm_raw + (size_t)nwarp_blk * kBulkSlots * slot_bytes) + (size_t)nwarp_blk * 32 * 33;
+    uint64_t* bars = (uint64_t*)(ur_s + ((W + 1) & ~1)) + wib * kBulkSlots;
+    const double* ur = rec + 8;
+    const double* z = rec + 8 + w_cap;
+    for (int j = threadIdx.x; j < W; j += blockDim.x) ur_s[j] = ur[j];
+    double zr[NC * VN];
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+            const int col = (c * 32 + lane) * VN + e;
+            zr[c * VN + e] = col < d ? z[col] : 0.0;
+        }
+    if (lane == 0) {
+        for (int k = 0; k < kBulkSlots; ++k)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + k)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const double zn = rec[4];
+    const double piv = labelled ? sqrt(fmax(rec[5] + noise, 2.3e-308)) : sqrt(fmax(rec[3], 1e-300));
+    const double beta = labelled ? (y - rec[2]) / piv : 0.0;
+
+    const int64_t n_units = (n + 31) >> 5;
+    const int64_t warp_global = (int64_t)blockIdx.x * nwarp_blk + wib;
+    const int64_t warps_total = (int64_t)gridDim.x * nwarp_blk;
+    constexpr int kSubPerUnit = 32 / kBulkRows;
+    // this warp's sequence of sub-tiles: (unit index in its own list) * kSubPerUnit + sub
+    const int64_t my_units = warp_global < n_units ? (n_units - 1 - warp_global) / warps_total + 1 : 0;
+    const int64_t total_sub = my_units * kSubPerUnit;
+    auto issue = [&](int64_t sidx) {
+        const int64_t unit = warp_global + (sidx / kSubPerUnit) * warps_total;
+        const int64_t row = (unit << 5) + (sidx % kSubPerUnit) * kBulkRows;
+        int64_t rows = n - row;
+        if (rows > kBulkRows) rows = kBulkRows;
+        const int slot = (int)(sidx % kBulkSlots);
+        if (rows > 0)
+            bulk_issue(ring + (size_t)slot * slot_bytes, X + row * (int64_t)d_pad, (uint32_t)rows * row_bytes, bars + slot);
+        else    // nothing to load: complete the phase so that the waiters do not hang
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bars + slot)) : "memory");
+    };
+    if (lane == 0)
+        for (int64_t k = 0; k < kBulkSlots && k < total_sub; ++k) issue(k);
+    int64_t sidx = 0;
+    for (int64_t unit = warp_global; unit < n_units; unit += warps_total) {
+        const int64_t row0 = unit << 5;
+#pragma unroll 1
+        for (int sub = 0; sub < kSubPerUnit; ++sub, ++sidx) {
+            const int slot = (int)(sidx % kBulkSlots);
+            bar_wait(bars + slot, (uint32_t)((sidx / kBulkSlots) & 1));
+            const unsigned char* sp = ring + (size_t)slot * slot_bytes;
+#pragma unroll
+            for (int rr = 0; rr < kBulkRows; ++rr) {
+                const XT* xr = (const XT*)(sp + (size_t)rr * row_bytes) + lane * VN;
+                double a0 = 0.0, a1 = 0.0;
+                if (row0 + sub * kBulkRows + rr < n) {
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        Vec<XT> x;
+                        x.lds(xr + c * 32 * VN);
+#pragma unroll
+                        for (int e = 0; e < VN; e += 2) {
+                            a0 = fma(x.get(e), zr[c * VN + e], a0);
+                            a1 = fma(x.get(e + 1), zr[c * VN + e + 1], a1);
+                        }
+                    }
+                }
+                part[(sub * kBulkRows + rr) * 33 + lane] = a0 + a1;
+            }
+            __syncwarp();                                   // every lane is done with the slot
+            if (lane == 0 && sidx + kBulkSlots < total_sub) issue(sidx + kBulkSlots);
+        }
+        __syncwarp();
+        const int64_t i = row0 + lane;
+        if (i < n) {
+            double dot = 0.0;
+#pragma unroll
+            for (int l = 0; l < 32; ++l) dot += part[lane * 33 + l];
             const double kv = var * exp((sqn[i] + zn - 2.0 * dot) / neg2ls2);
             double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
             const double* u = U + i;
@@ -506,7 +663,8 @@ struct EvalArgs {
     const double* w;
     const int* orth;            // k_eval<T>: orthant id per node
     const int* group_begin;     // k_eval_sorted: 2^t + 1 offsets
-    int64_t n_nodes;
+    int64_t n_nodes;            // stride of eta (nodes generated)
+    const int* n_kept;          // nodes kept after dropping negligible weights (device; k_eval<T>)
     const double* masses;       // 2^t base orthant probabilities (device)
     const double* h_base;       // score of the base alone (device scalar)
     double log1p_eps;
@@ -547,6 +705,7 @@ __global__ void __launch_bounds__(256) k_eval(EvalArgs a) {
     const int team_global = (blockIdx.x * blockDim.x + threadIdx.x) / TPC;
     const int teams_total = (gridDim.x * blockDim.x) / TPC;
     const int64_t N = a.n_nodes;
+    const int64_t NK = *a.n_kept;
     __shared__ double red[8];
     for (int item = team_global; item < n_items; item += teams_total) {
         const int64_t i = a.list[item];
@@ -565,13 +724,13 @@ __global__ void __launch_bounds__(256) k_eval(EvalArgs a) {
 #pragma unroll
         for (int b = 0; b < NB; ++b) acc[b] = 0.0;
         // four nodes per thread and trip: independent erfc chains hide the FP64 latency
-        for (int64_t q = tid_team; q < N; q += 4 * TPC) {
+        for (int64_t q = tid_team; q < NK; q += 4 * TPC) {
             double num[4], ww[4];
             int ob[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int64_t qq = q + (int64_t)u * TPC;
-                const bool ok = qq < N;
+                const bool ok = qq < NK;
                 ww[u] = ok ? a.w[qq] : 0.0;
                 ob[u] = ok ? a.orth[qq] : 0;
                 num[u] = mi;
@@ -858,15 +1017,53 @@ __global__ void __launch_bounds__(256) k_snq_generate(int q, double R, int q_min
     orth[k] = ob;
 }
 
-// Base orthant probabilities P_b = sum of the weights per orthant, and the score of the base alone
-// (one block, fixed summation order).
-__global__ void __launch_bounds__(1024) k_snq_masses(int t, int64_t N, const double* __restrict__ w,
-                                                     const int* __restrict__ orth, double log1p_eps,
-                                                     double* __restrict__ masses, double* __restrict__ h_base) {
+// Drops the nodes whose weight is below w_min (stable, in place: about half of the nodes at t = 3 carry a total
+// mass of ~1e-11), then sums the base orthant probabilities P_b = sum of the kept weights per orthant and the
+// score of the base alone.  One block, fixed order throughout.
+__global__ void __launch_bounds__(1024) k_snq_finalize(int t, int64_t N, double w_min, double* __restrict__ eta,
+                                                       double* __restrict__ w, int* __restrict__ orth,
+                                                       double log1p_eps, double* __restrict__ masses,
+                                                       double* __restrict__ h_base, int* __restrict__ n_kept) {
+    __shared__ int warp_cnt[32];
+    __shared__ int base_s;
     __shared__ double part[32][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base_s = 0;
+    __syncthreads();
+    for (int64_t c0 = 0; c0 < N; c0 += blockDim.x) {
+        const int64_t k = c0 + threadIdx.x;
+        double wk = 0.0, e[3] = {0.0, 0.0, 0.0};
+        int ob = 0;
+        if (k < N) {
+            wk = w[k];
+            ob = orth[k];
+            for (int j = 0; j < t; ++j) e[j] = eta[(int64_t)j * N + k];
+        }
+        const bool keep = k < N && wk >= w_min;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();                                // every element of the chunk is in registers
+        int off = base_s;
+        for (int ww = 0; ww < warp; ++ww) off += warp_cnt[ww];
+        off += __popc(bal & ((1u << lane) - 1));
+        if (keep) {
+            w[off] = wk;
+            orth[off] = ob;
+            for (int j = 0; j < t; ++j) eta[(int64_t)j * N + off] = e[j];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int ww = 0; ww < (int)(blockDim.x >> 5); ++ww) tot += warp_cnt[ww];
+            base_s += tot;
+        }
+        __syncthreads();
+    }
+    const int kept = base_s;
+    if (threadIdx.x == 0) *n_kept = kept;
     const int nb = 1 << t;                              // t <= 3 here
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int64_t k = threadIdx.x; k < N; k += blockDim.x) {
+    for (int k = threadIdx.x; k < kept; k += blockDim.x) {
         const int ob = orth[k];
         const double wk = w[k];
 #pragma unroll
@@ -876,7 +1073,7 @@ __global__ void __launch_bounds__(1024) k_snq_masses(int t, int64_t N, const dou
     for (int b = 0; b < 8; ++b) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], o);
-        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5][b] = acc[b];
+        if (lane == 0) part[warp][b] = acc[b];
     }
     __syncthreads();
     if (threadIdx.x == 0) {

@@ -17,6 +17,7 @@ namespace snq {
 constexpr double kR = 7.0;
 constexpr int kQMin = 2;
 constexpr int kMaxOrder = 64;
+constexpr double kWMin = 1e-13;   // nodes lighter than this are dropped (about half of them at t = 3, mass ~1e-11)
 
 inline int order_for(int t) {
     if (t <= 1) return 32;
@@ -129,6 +130,25 @@ inline Nodes generate(int t, const double* m, const double* L, int q = 0, double
         w.swap(w_new);
         orth.swap(orth_new);
         n = n_new;
+    }
+    // drop the nodes whose weight is negligible (keeps the generation order)
+    if (t > 0) {
+        int64_t kept = 0;
+        for (int64_t k = 0; k < n; ++k) {
+            if (w[k] < kWMin) continue;
+            for (int i = 0; i < t; ++i) eta[(size_t)i * n + kept] = eta[(size_t)i * n + k];
+            w[kept] = w[k];
+            orth[kept] = orth[k];
+            ++kept;
+        }
+        // re-pack the dimension-major coordinates to the new stride
+        std::vector<double> eta2((size_t)t * kept);
+        for (int i = 0; i < t; ++i)
+            for (int64_t k = 0; k < kept; ++k) eta2[(size_t)i * kept + k] = eta[(size_t)i * n + k];
+        eta.swap(eta2);
+        w.resize(kept);
+        orth.resize(kept);
+        n = kept;
     }
     // stable counting sort by orthant
     const int nb = 1 << t;

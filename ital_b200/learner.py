@@ -192,14 +192,16 @@ class ITAL(object):
     `local_rows=(first_row, n_total)` declares that `data` holds only this process's contiguous block of a
     pool of n_total rows (for pools too large to replicate on every host process; no `queries` then);
     `lazy_rows` extends the batch-conditional projections only for the rows that get scored instead of streaming
-    the whole pool once per greedy step (same batch, same scores bit for bit; see include/ital_b200.h).
+    the whole pool once per greedy step (same batch, same scores bit for bit; see include/ital_b200.h);
+    `bulk_stream` (default on; environment ITAL_B200_BULK=0 turns it off) stages the streaming pass through shared
+    memory with the bulk-copy engine where the tuned shape applies (2 KB rows), else coalesced register loads.
     """
 
     def __init__(self, data=None, queries=[], length_scale=0.1, var=1.0, noise=1e-6,
                  label_prob=1.0, mistake_prob=0.0, top_candidates=None, change_estimation_subset=0,
                  clip_cov=0, label_estimation='mean', monte_carlo_num_rel=None, monte_carlo_num_fb=None,
                  parallelized=True, device=None, storage='auto', process_group=None, exhaustive=False,
-                 local_rows=None, lazy_rows=False):
+                 local_rows=None, lazy_rows=False, bulk_stream=None):
         self.length_scale, self.var, self.noise = length_scale, var, noise
         self.label_prob, self.mistake_prob = label_prob, mistake_prob
         self.top_candidates = top_candidates
@@ -210,6 +212,8 @@ class ITAL(object):
         self.parallelized = parallelized            # accepted for compatibility; the GPU is the parallelism
         self.exhaustive = exhaustive
         self._lazy_rows = bool(lazy_rows)
+        import os
+        self._bulk_stream = os.environ.get('ITAL_B200_BULK', '1') == '1' if bulk_stream is None else bool(bulk_stream)
         self._storage = storage
         self._device = device
         self._local_rows = local_rows
@@ -228,6 +232,16 @@ class ITAL(object):
         self._lazy_rows = bool(on)
         if self._shard is not None:
             _capi.check(self._shard.lib.ital_set_lazy_rows(self._shard.handle, int(self._lazy_rows)))
+
+    @property
+    def bulk_stream(self):
+        return self._bulk_stream
+
+    @bulk_stream.setter
+    def bulk_stream(self, on):
+        self._bulk_stream = bool(on)
+        if self._shard is not None:
+            _capi.check(self._shard.lib.ital_set_bulk_stream(self._shard.handle, int(self._bulk_stream)))
 
     # ---- ActiveRetrievalBase ---------------------------------------------------------------------------
     def fit(self, data, queries=[]):                                            # retrieval_base.py:34-45
@@ -275,6 +289,7 @@ class ITAL(object):
                              self.length_scale, self.var, self.noise, device)
         self.gp = _GPView(self)
         self.lazy_rows = self._lazy_rows
+        self.bulk_stream = self._bulk_stream
         self.reset()
 
     def reset(self):                                                            # retrieval_base.py:48-61

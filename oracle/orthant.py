@@ -31,6 +31,7 @@ from scipy.special import ndtr
 
 SNQ_R = 7.0
 SNQ_QMIN = 2
+SNQ_WMIN = 1e-13      # nodes lighter than this are dropped (about half of them at t = 3, total mass ~1e-11)
 _SQRT_2PI = np.sqrt(2.0 * np.pi)
 _GL_CACHE = {}
 
@@ -68,10 +69,11 @@ def snq_split(c, q, R=SNQ_R, q_min=SNQ_QMIN):
     return np.clip(n_lo, q_min, 2 * q - q_min)
 
 
-def snq_nodes(m_base, L_base, q=None, R=SNQ_R):
+def snq_nodes(m_base, L_base, q=None, R=SNQ_R, w_min=SNQ_WMIN):
     """Shared nodes for a base N(m_base, L L^T).
 
-    Returns ``eta`` (N, t), ``w`` (N,), ``orth`` (N,) with ``N = (2q)^t``.  Bit j of ``orth`` is 1 where
+    Returns ``eta`` (N, t), ``w`` (N,), ``orth`` (N,) with ``N <= (2q)^t`` (nodes whose weight is below ``w_min``
+    are dropped after the full product rule has been formed).  Bit j of ``orth`` is 1 where
     ``z_j > 0``.  Node index = sum_j digit_j * (2q)^(t-1-j), digit_j in [0, 2q): the first n_lo digits
     of a dimension are the lower panel (z_j < 0), the rest the upper one; n_lo = snq_split(c).
     """
@@ -109,6 +111,9 @@ def snq_nodes(m_base, L_base, q=None, R=SNQ_R):
         eta = np.concatenate((np.repeat(eta, 2 * q, axis=0), x.reshape(-1, 1)), axis=1)
         w = (w[:, None] * ww).reshape(-1)
         orth = (orth[:, None] + (bit << j)).reshape(-1)
+    if w_min > 0 and t > 0:
+        keep = w >= w_min
+        eta, w, orth = eta[keep], w[keep], orth[keep]
     return eta, w, orth
 
 

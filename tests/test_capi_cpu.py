@@ -54,15 +54,17 @@ def test_snq_nodes_match_oracle(lib, t):
         m = rng.normal(size=t) * (0.1 if trial < 2 else 1.5)
         eta_o, w_o, orth_o = orthant.snq_nodes(m, L)
         order = np.argsort(orth_o, kind='stable')
-        n = lib.ital_snq_nodes(t, _capi.dptr(m), _capi.dptr(np.ascontiguousarray(L)), None, None, None, None)
-        assert n == len(w_o) == (2 * lib.ital_snq_order(t)) ** t
-        eta = np.zeros((t, n))
-        w = np.zeros(n)
-        orth = np.zeros(n, dtype=np.int32)
+        cap = lib.ital_snq_nodes(t, _capi.dptr(m), _capi.dptr(np.ascontiguousarray(L)), None, None, None, None)
+        assert cap == (2 * lib.ital_snq_order(t)) ** t >= len(w_o)
+        eta_buf = np.zeros(t * cap)
+        w = np.zeros(cap)
+        orth = np.zeros(cap, dtype=np.int32)
         masses = np.zeros(1 << t)
         Lc = np.ascontiguousarray(L)
-        assert lib.ital_snq_nodes(t, _capi.dptr(m), _capi.dptr(Lc), _capi.dptr(eta), _capi.dptr(w),
-                                  orth.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _capi.dptr(masses)) == n
+        n = lib.ital_snq_nodes(t, _capi.dptr(m), _capi.dptr(Lc), _capi.dptr(eta_buf), _capi.dptr(w),
+                               orth.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _capi.dptr(masses))
+        assert n == len(w_o)        # both drop the nodes lighter than 1e-13
+        eta, w, orth = eta_buf[:t * n].reshape(t, n), w[:n], orth[:n]
         assert np.array_equal(orth, orth_o[order])
         np.testing.assert_allclose(eta.T, eta_o[order], rtol=0, atol=2e-13)
         np.testing.assert_allclose(w, w_o[order], rtol=1e-12, atol=1e-300)

@@ -173,6 +173,18 @@ def test_synthetic_parity_exhaustive_and_pruned(n, d, storage):
     assert [int(s[2]) for s in stats] == [1, 64, 1024, 13824]
 
 
+def test_bulk_staged_stream_is_bit_identical():
+    """k_extend_bulk (TMA-staged rows) against k_extend (register loads): same bits in rel_mean and scores."""
+    X, assign = _syn(20011, 512, seed=4)
+    out = {}
+    for bulk in (False, True):
+        gpu = _gpu_learner(X, length_scale=1.0, bulk_stream=bulk)
+        _label_syn(gpu, assign)
+        out[bulk] = (gpu.fetch_unlabelled(4), np.array(gpu.last_fetch_scores), gpu.rel_mean.copy())
+    assert out[False][0] == out[True][0]
+    assert np.array_equal(out[False][1], out[True][1]) and np.array_equal(out[False][2], out[True][2])
+
+
 def test_repeated_rounds_track_the_oracle():
     """Several update/fetch rounds like run_experiment.py:160-164, incremental model on the GPU."""
     from oracle.ital_oracle import OracleITAL
