@@ -122,7 +122,8 @@ def ncu_traffic():
     """DRAM bytes per k_extend launch from the committed `ncu --set full` capture (profiles/), or None."""
     import glob
     import re
-    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_k_extend_full.txt')))
+    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_k_extend_bulk_full.txt'))) or \
+        sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_k_extend*_full.txt')))
     if not files:
         return None, None
     rd = wr = None
@@ -357,7 +358,7 @@ def main():
                         'itself is resident (uploaded once by fit: %.0f ms, %.2f GB)' % (t_fit * 1e3, X.nbytes / 1e9)},
         'gpu_launches': launches,
         'clocks': clocks,
-        'roofline': {'bound': 'hbm', 'kernel': 'k_extend (streaming pass: row . z in f64, RBF, projection)',
+        'roofline': {'bound': 'hbm', 'kernel': 'k_extend_bulk / k_extend (streaming pass: row . z in f64, RBF, projection)',
                      'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
                      'traffic_source': traffic_src,
                      'peak_source': peak_src, 'launches': int(nl.value),

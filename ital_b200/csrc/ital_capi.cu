@@ -71,6 +71,8 @@ struct ital_shard {
     // quadrature nodes of the current step
     double *eta_dev = nullptr, *w_dev = nullptr, *masses_dev = nullptr;
     int *group_dev = nullptr, *orth_dev = nullptr;
+    double *eta_raw = nullptr, *w_raw = nullptr;     // nodes as generated, before the negligible ones are dropped
+    int* orth_raw = nullptr;
     int64_t nodes_cap = 0;
     int64_t n_nodes = 0;
     double* gl_dev = nullptr;        // Gauss-Legendre tables: x[65][64] then w[65][64]
@@ -282,10 +284,14 @@ constexpr int kMaxBatch = 11;            // greedy steps per fetch (t <= 10 base
 int ensure_nodes(ital_shard* s, int64_t n_nodes) {
     if (n_nodes <= s->nodes_cap) return ITAL_OK;
     CU(cudaStreamSynchronize(s->stream));
-    for (void* p : {(void*)s->eta_dev, (void*)s->w_dev, (void*)s->orth_dev})
+    for (void* p : {(void*)s->eta_dev, (void*)s->w_dev, (void*)s->orth_dev, (void*)s->eta_raw, (void*)s->w_raw,
+                    (void*)s->orth_raw})
         if (p) CU(cudaFree(p));
-    s->eta_dev = s->w_dev = nullptr;
-    s->orth_dev = nullptr;
+    s->eta_dev = s->w_dev = s->eta_raw = s->w_raw = nullptr;
+    s->orth_dev = s->orth_raw = nullptr;
+    CU(cudaMalloc(&s->eta_raw, (size_t)n_nodes * 3 * sizeof(double)));
+    CU(cudaMalloc(&s->w_raw, (size_t)n_nodes * sizeof(double)));
+    CU(cudaMalloc(&s->orth_raw, (size_t)n_nodes * sizeof(int)));
     CU(cudaMalloc(&s->eta_dev, (size_t)n_nodes * 10 * sizeof(double)));
     CU(cudaMalloc(&s->w_dev, (size_t)n_nodes * sizeof(double)));
     CU(cudaMalloc(&s->orth_dev, (size_t)n_nodes * sizeof(int)));
@@ -309,14 +315,14 @@ int prepare_nodes(ital_shard* s) {
         const double* glx = s->gl_dev;
         const double* glw = s->gl_dev + (snq::kMaxOrder + 1) * 64;
 #define ITAL_GEN(TV) k_snq_generate<TV><<<blocks, 256, 0, s->stream>>>(q, snq::kR, snq::kQMin, s->base_m_dev, s->base_L_dev, \
-                                                              glx, glw, N, s->eta_dev, s->w_dev, s->orth_dev)
+                                                              glx, glw, N, s->eta_raw, s->w_raw, s->orth_raw)
         if (t == 1) ITAL_GEN(1);
         else if (t == 2) ITAL_GEN(2);
         else ITAL_GEN(3);
 #undef ITAL_GEN
         s->launches++;
-        k_snq_finalize<<<1, 1024, 0, s->stream>>>(t, N, snq::kWMin, s->eta_dev, s->w_dev, s->orth_dev, s->log1p_eps, s->masses_dev,
-                                                  s->hbase_dev, s->counters + 3); s->launches++;
+        k_snq_finalize<<<1, 1024, 0, s->stream>>>(t, N, snq::kWMin, s->eta_raw, s->w_raw, s->orth_raw, s->eta_dev, s->w_dev,
+                                                  s->orth_dev, s->log1p_eps, s->masses_dev, s->hbase_dev, s->counters + 3); s->launches++;
         CU(cudaGetLastError());
         return ITAL_OK;
     }
@@ -557,7 +563,7 @@ void free_all(ital_shard* s) {
     cudaSetDevice(s->device);
     void* ptrs[] = {s->X, s->sqn, s->m, s->v, s->U, s->gain, s->score, s->mask, s->worklist, s->counters,
                     s->block_best, s->best, s->thr_dev, s->rec_dev, s->rec_in_dev, s->idx_dev, s->eta_dev,
-                    s->w_dev, s->masses_dev, s->group_dev, s->orth_dev, s->gl_dev, s->base_m_dev, s->base_L_dev, s->sel_dev,
+                    s->w_dev, s->masses_dev, s->group_dev, s->orth_dev, s->eta_raw, s->w_raw, s->orth_raw, s->gl_dev, s->base_m_dev, s->base_L_dev, s->sel_dev,
                     s->hbase_dev, s->stats_dev, s->ncol, s->rec_hist, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev};
     for (void* p : ptrs)
         if (p) cudaFree(p);

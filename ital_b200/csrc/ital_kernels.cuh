@@ -1017,50 +1017,47 @@ __global__ void __launch_bounds__(256) k_snq_generate(int q, double R, int q_min
     orth[k] = ob;
 }
 
-// Drops the nodes whose weight is below w_min (stable, in place: about half of the nodes at t = 3 carry a total
-// mass of ~1e-11), then sums the base orthant probabilities P_b = sum of the kept weights per orthant and the
-// score of the base alone.  One block, fixed order throughout.
-__global__ void __launch_bounds__(1024) k_snq_finalize(int t, int64_t N, double w_min, double* __restrict__ eta,
+// Drops the nodes whose weight is below w_min (stable, out of place: about half of the nodes at t = 3 carry a
+// total mass of ~1e-11), then sums the base orthant probabilities P_b = sum of the kept weights per orthant and
+// the score of the base alone.  One block; every thread owns a contiguous range of nodes, one block-wide scan of
+// the kept counts gives the output offsets; fixed order throughout.
+__global__ void __launch_bounds__(1024) k_snq_finalize(int t, int64_t N, double w_min,
+                                                       const double* __restrict__ eta_in, const double* __restrict__ w_in,
+                                                       const int* __restrict__ orth_in, double* __restrict__ eta,
                                                        double* __restrict__ w, int* __restrict__ orth,
                                                        double log1p_eps, double* __restrict__ masses,
                                                        double* __restrict__ h_base, int* __restrict__ n_kept) {
-    __shared__ int warp_cnt[32];
-    __shared__ int base_s;
+    __shared__ int warp_tot[32];
     __shared__ double part[32][8];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) base_s = 0;
-    __syncthreads();
-    for (int64_t c0 = 0; c0 < N; c0 += blockDim.x) {
-        const int64_t k = c0 + threadIdx.x;
-        double wk = 0.0, e[3] = {0.0, 0.0, 0.0};
-        int ob = 0;
-        if (k < N) {
-            wk = w[k];
-            ob = orth[k];
-            for (int j = 0; j < t; ++j) e[j] = eta[(int64_t)j * N + k];
-        }
-        const bool keep = k < N && wk >= w_min;
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) warp_cnt[warp] = __popc(bal);
-        __syncthreads();                                // every element of the chunk is in registers
-        int off = base_s;
-        for (int ww = 0; ww < warp; ++ww) off += warp_cnt[ww];
-        off += __popc(bal & ((1u << lane) - 1));
-        if (keep) {
-            w[off] = wk;
-            orth[off] = ob;
-            for (int j = 0; j < t; ++j) eta[(int64_t)j * N + off] = e[j];
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int tot = 0;
-            for (int ww = 0; ww < (int)(blockDim.x >> 5); ++ww) tot += warp_cnt[ww];
-            base_s += tot;
-        }
-        __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int64_t per = (N + blockDim.x - 1) / blockDim.x;
+    const int64_t k0 = min(N, (int64_t)threadIdx.x * per), k1 = min(N, k0 + per);
+    int cnt = 0;
+    for (int64_t k = k0; k < k1; ++k) cnt += w_in[k] >= w_min;
+    // exclusive scan of cnt over the block
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
     }
-    const int kept = base_s;
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int off = incl - cnt;
+    for (int ww = 0; ww < warp; ++ww) off += warp_tot[ww];
+    int kept = 0;
+    for (int ww = 0; ww < nwarps; ++ww) kept += warp_tot[ww];
+    for (int64_t k = k0; k < k1; ++k) {
+        const double wk = w_in[k];
+        if (wk >= w_min) {
+            w[off] = wk;
+            orth[off] = orth_in[k];
+            for (int j = 0; j < t; ++j) eta[(int64_t)j * N + off] = eta_in[(int64_t)j * N + k];
+            ++off;
+        }
+    }
     if (threadIdx.x == 0) *n_kept = kept;
+    __syncthreads();
     const int nb = 1 << t;                              // t <= 3 here
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int k = threadIdx.x; k < kept; k += blockDim.x) {
@@ -1080,7 +1077,7 @@ __global__ void __launch_bounds__(1024) k_snq_finalize(int t, int64_t N, double 
         double h = 0.0, tot = 0.0;
         for (int b = 0; b < nb; ++b) {
             double p = 0.0;
-            for (int k = 0; k < (int)(blockDim.x >> 5); ++k) p += part[k][b];
+            for (int k = 0; k < nwarps; ++k) p += part[k][b];
             masses[b] = p;
             h += mi_term(p, log1p_eps);
             tot += p;
