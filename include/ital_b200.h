@@ -65,6 +65,10 @@ int ital_export_points(ital_shard* s, int q, const int64_t* global_idx, double* 
  * Also marks the point as seen.  Points are appended in the order given (relevant first, irrelevant after,
  * as ActiveRetrievalBase.update does). */
 int ital_add_labelled(ital_shard* s, const double* record, double y);
+/* The same for q <= 4 points with ONE pass over X (block Cholesky extension; GaussianProcess.update with several
+ * samples, ital/gp.py:164-200).  All q records must have been exported in the current state of the model, i.e.
+ * before any of them is added. */
+int ital_add_labelled_many(ital_shard* s, int q, const double* records, const double* y);
 
 /* ActiveRetrievalBase.update's unnameable_ids / get_unseen (ital/retrieval_base.py:78-87,126):
  * mark rows as seen (never candidates again until reset).  Non-local indices are ignored. */

@@ -86,6 +86,9 @@ struct ital_shard {
     bool bulk_stream = true;         // X stream staged by the bulk-copy engine (k_extend_bulk) where it applies
     uint8_t* ncol = nullptr;         // lazy rows: batch columns valid per row
     double* rec_hist = nullptr;      // records of the points selected in the running fetch
+    double* mext_dev = nullptr;      // block of the multi-column labelled extension (MultiExt + z + ur)
+    double* mext_host = nullptr;     // pinned
+    size_t mext_cap = 0;
     int64_t rec_hist_cap = 0;
     // general feedback model (label_prob < 1): conditional node sets of the running step
     double *g_eta = nullptr, *g_w = nullptr, *g_mass = nullptr;
@@ -251,6 +254,41 @@ int extend_with_record(ital_shard* s, const double* rec, int col, int labelled, 
     const uint8_t mark = mark_selected ? kSelected : (uint8_t)0;
     if (s->x_dtype == ITAL_F32) return launch_extend_t<float>(s, col, labelled, y, mark);
     return launch_extend_t<double>(s, col, labelled, y, mark);
+}
+
+template <typename XT>
+int launch_extend_multi(ital_shard* s, int q, int W_used) {
+    const int threads = 256, warps = threads / 32;
+    const size_t smem = ((size_t)q * s->d_pad + (size_t)q * W_used) * sizeof(double);
+    const int64_t units = (s->n + 31) / 32;
+    int blocks = (int)std::min<int64_t>((units + warps - 1) / warps, (int64_t)s->num_sms * 2);
+    if (blocks < 1) blocks = 1;
+    const double neg2ls2 = -2.0 * (s->ls * s->ls);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (s->profiling) {
+        CU(cudaEventCreate(&ev0));
+        CU(cudaEventCreate(&ev1));
+        CU(cudaEventRecord(ev0, s->stream));
+    }
+#define ITAL_LAUNCH_MULTI(QV)                                                                                     \
+    do {                                                                                                          \
+        CU(cudaFuncSetAttribute(k_extend_multi<XT, QV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_extend_multi<XT, QV><<<blocks, threads, smem, s->stream>>>((const XT*)s->X, s->n, (int)s->d_pad,       \
+                                                                      s->mext_dev, W_used, s->sqn, s->U, s->ldu,  \
+                                                                      s->m, s->v, s->var, neg2ls2);               \
+    } while (0)
+    if (q == 2) ITAL_LAUNCH_MULTI(2);
+    else if (q == 3) ITAL_LAUNCH_MULTI(3);
+    else ITAL_LAUNCH_MULTI(4);
+#undef ITAL_LAUNCH_MULTI
+    s->launches++;
+    CU(cudaGetLastError());
+    if (s->profiling) {
+        CU(cudaEventRecord(ev1, s->stream));
+        s->prof_events.emplace_back(ev0, ev1);
+        s->prof_bytes += (double)s->n * ((double)s->d * sizeof(XT) + 8.0 + 8.0 * W_used + 8.0 * q + 32.0);
+    }
+    return ITAL_OK;
 }
 
 // additive constant of the scores of the running step for a user who mislabels with probability mistake_prob and
@@ -564,12 +602,13 @@ void free_all(ital_shard* s) {
     void* ptrs[] = {s->X, s->sqn, s->m, s->v, s->U, s->gain, s->score, s->mask, s->worklist, s->counters,
                     s->block_best, s->best, s->thr_dev, s->rec_dev, s->rec_in_dev, s->idx_dev, s->eta_dev,
                     s->w_dev, s->masses_dev, s->group_dev, s->orth_dev, s->eta_raw, s->w_raw, s->orth_raw, s->gl_dev, s->base_m_dev, s->base_L_dev, s->sel_dev,
-                    s->hbase_dev, s->stats_dev, s->ncol, s->rec_hist, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev};
+                    s->hbase_dev, s->stats_dev, s->ncol, s->rec_hist, s->mext_dev, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->rec_host) cudaFreeHost(s->rec_host);
     if (s->rec_in_host) cudaFreeHost(s->rec_in_host);
     if (s->sel_host) cudaFreeHost(s->sel_host);
+    if (s->mext_host) cudaFreeHost(s->mext_host);
     if (s->stats_host) cudaFreeHost(s->stats_host);
 }
 
@@ -784,6 +823,93 @@ int ital_add_labelled(ital_shard* s, const double* record, double y) {
     s->W += 1;
     int64_t g = (int64_t)hdr[0];
     return ital_mark_seen(s, 1, &g);
+}
+
+// GaussianProcess.update with several samples (ital/gp.py:164-200): q <= 4 labelled points, whose records were all
+// exported in the CURRENT state of the model, enter with ONE pass over the pool.  The q x q triangle of the block
+// Cholesky extension among the new points is computed here on the host from the records.
+int ital_add_labelled_many(ital_shard* s, int q, const double* records, const double* y) {
+    if (!s || q < 1 || !records || !y) return fail(ITAL_EINVAL, "ital_add_labelled_many: bad arguments");
+    if (s->fetching) return fail(ITAL_ESTATE, "ital_add_labelled_many: a fetch is in progress");
+    if (q == 1) return ital_add_labelled(s, records, y[0]);
+    if (q > 4) return fail(ITAL_EINVAL, "ital_add_labelled_many: at most 4 points per pass");
+    CU(cudaSetDevice(s->device));
+    const int W = s->W;
+    const int64_t old_cap = s->w_cap, old_rl = record_doubles(s);
+    const int64_t d = s->d;
+    std::vector<std::vector<double>> u(q), x(q);
+    std::vector<double> hm(q), hv(q), hsq(q), hidx(q);
+    for (int a = 0; a < q; ++a) {
+        const double* r = records + (int64_t)a * old_rl;
+        hidx[a] = r[0]; hm[a] = r[2]; hsq[a] = r[4]; hv[a] = r[5];
+        u[a].assign(r + ITAL_RECORD_HEADER, r + ITAL_RECORD_HEADER + W);
+        x[a].assign(r + ITAL_RECORD_HEADER + old_cap, r + ITAL_RECORD_HEADER + old_cap + d);
+    }
+    int rc = ensure_width(s, W + q);
+    if (rc) return rc;
+    // block Cholesky extension among the new points
+    const double neg2ls2 = -2.0 * (s->ls * s->ls);
+    double tri[16] = {0}, piv[4] = {0}, beta[4] = {0};
+    for (int a = 0; a < q; ++a) {
+        double cv = hv[a], ma = hm[a];
+        for (int b = 0; b < a; ++b) {
+            double dot = 0.0;
+            for (int64_t j = 0; j < d; ++j) dot += x[a][j] * x[b][j];
+            double num = s->var * std::exp((hsq[a] + hsq[b] - 2.0 * dot) / neg2ls2);
+            for (int j = 0; j < W; ++j) num -= u[a][j] * u[b][j];
+            for (int c = 0; c < b; ++c) num -= tri[a * 4 + c] * tri[b * 4 + c];
+            const double e = num / piv[b];
+            tri[a * 4 + b] = e;
+            cv -= e * e;
+            ma += e * beta[b];
+        }
+        piv[a] = std::sqrt(std::max(cv + s->noise, 2.3e-308));
+        beta[a] = (y[a] - ma) / piv[a];
+    }
+    // device block: MultiExt header, z[q][d_pad] (zero padded), ur[q][W]
+    const size_t hdr_d = sizeof(MultiExt) / sizeof(double);
+    const size_t need = hdr_d + (size_t)q * s->d_pad + (size_t)q * W;
+    if (need > s->mext_cap) {
+        CU(cudaStreamSynchronize(s->stream));
+        if (s->mext_dev) CU(cudaFree(s->mext_dev));
+        if (s->mext_host) CU(cudaFreeHost(s->mext_host));
+        s->mext_dev = s->mext_host = nullptr;
+        const size_t cap = need * 2;
+        CU(cudaMalloc(&s->mext_dev, cap * sizeof(double)));
+        CU(cudaMallocHost(&s->mext_host, cap * sizeof(double)));
+        s->mext_cap = cap;
+    }
+    CU(cudaStreamSynchronize(s->stream));               // the pinned block may still feed the previous pass
+    MultiExt* h = reinterpret_cast<MultiExt*>(s->mext_host);
+    memset(s->mext_host, 0, need * sizeof(double));
+    for (int a = 0; a < q; ++a) {
+        h->zn[a] = hsq[a];
+        h->piv[a] = piv[a];
+        h->beta[a] = beta[a];
+        memcpy(s->mext_host + hdr_d + (size_t)a * s->d_pad, x[a].data(), (size_t)d * sizeof(double));
+        memcpy(s->mext_host + hdr_d + (size_t)q * s->d_pad + (size_t)a * W, u[a].data(), (size_t)W * sizeof(double));
+    }
+    memcpy(h->tri, tri, sizeof tri);
+    CU(cudaMemcpyAsync(s->mext_dev, s->mext_host, need * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    rc = s->x_dtype == ITAL_F32 ? launch_extend_multi<float>(s, q, W) : launch_extend_multi<double>(s, q, W);
+    if (rc) return rc;
+    // host copy of the model: Cholesky rows, beta, labelled rows (for predict)
+    std::vector<int64_t> gidx(q);
+    for (int a = 0; a < q; ++a) {
+        std::vector<double> row(u[a]);
+        for (int b = 0; b < a; ++b) row.push_back(tri[a * 4 + b]);
+        row.push_back(piv[a]);
+        s->LK.push_back(row);
+        s->beta.push_back(beta[a]);
+        s->lab_x.insert(s->lab_x.end(), x[a].begin(), x[a].end());
+        s->lab_sqn.push_back(hsq[a]);
+        s->lab_y.push_back(y[a]);
+        s->lab_idx.push_back((int64_t)hidx[a]);
+        gidx[a] = (int64_t)hidx[a];
+    }
+    s->lab_dev_valid = false;
+    s->W += q;
+    return ital_mark_seen(s, q, gidx.data());
 }
 
 int ital_mark_seen(ital_shard* s, int64_t m, const int64_t* global_idx) {

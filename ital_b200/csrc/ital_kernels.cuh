@@ -242,6 +242,113 @@ k_extend(const XT* __restrict__ X, int64_t n, int d, int d_pad, const double* __
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Streaming pass for Q labelled points at once (GaussianProcess.update with several samples, ital/gp.py:164-200):
+// one read of X serves Q kernel columns -- the block-Cholesky extension of every row,
+//   e_a = (k(x_i, z_a) - u_i . u_a - sum_{b<a} e_b T[a][b]) / piv_a,   a = 0..Q-1,
+// with T the Q x Q triangle among the new points (computed on the host from their records), followed by
+// m_i += sum_a e_a beta_a, v_i -= sum_a e_a^2.  The new rows sit in shared memory as float64; two rows of X are in
+// flight per warp so that every shared-memory read of z is used twice.
+struct MultiExt {                 // device block written by the host: header, then z[Q][d_pad], then ur[Q][W]
+    double zn[4];
+    double piv[4];
+    double beta[4];
+    double tri[16];               // tri[a * 4 + b], b < a
+};
+
+template <typename XT, int Q>
+__global__ void __launch_bounds__(256, 2)
+k_extend_multi(const XT* __restrict__ X, int64_t n, int d_pad, const double* __restrict__ ext, int W,
+               const double* __restrict__ sqn, double* __restrict__ U, int64_t ldu, double* __restrict__ m,
+               double* __restrict__ v, double var, double neg2ls2) {
+    constexpr int VN = Vec<XT>::N;
+    extern __shared__ double msm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarp_blk = blockDim.x >> 5;
+    const MultiExt* hdr = reinterpret_cast<const MultiExt*>(ext);
+    const double* z_g = ext + sizeof(MultiExt) / sizeof(double);
+    const double* ur_g = z_g + (size_t)Q * d_pad;
+    double* z_s = msm;                                  // [Q][d_pad]
+    double* ur_s = z_s + (size_t)Q * d_pad;             // [Q][W]
+    for (int j = threadIdx.x; j < Q * d_pad; j += blockDim.x) z_s[j] = z_g[j];
+    for (int j = threadIdx.x; j < Q * W; j += blockDim.x) ur_s[j] = ur_g[j];
+    __syncthreads();
+    const int nchunks = d_pad / (32 * VN);
+    const int64_t n_units = (n + 31) >> 5;
+    const int64_t warp_global = (int64_t)blockIdx.x * nwarp_blk + wib;
+    const int64_t warps_total = (int64_t)gridDim.x * nwarp_blk;
+    for (int64_t unit = warp_global; unit < n_units; unit += warps_total) {
+        const int64_t row0 = unit << 5;
+        double dot[Q];
+#pragma unroll
+        for (int a = 0; a < Q; ++a) dot[a] = 0.0;
+#pragma unroll 1
+        for (int r = 0; r < 32; r += 2) {
+            double acc0[Q], acc1[Q];
+#pragma unroll
+            for (int a = 0; a < Q; ++a) { acc0[a] = 0.0; acc1[a] = 0.0; }
+            const int64_t ra = row0 + r, rb = row0 + r + 1;
+            for (int c = 0; c < nchunks; ++c) {
+                Vec<XT> x0, x1;
+                if (ra < n) x0.load(X + ra * (int64_t)d_pad + (c * 32 + lane) * VN); else x0.zero();
+                if (rb < n) x1.load(X + rb * (int64_t)d_pad + (c * 32 + lane) * VN); else x1.zero();
+                double xd0[VN], xd1[VN];
+#pragma unroll
+                for (int e = 0; e < VN; ++e) { xd0[e] = x0.get(e); xd1[e] = x1.get(e); }
+#pragma unroll
+                for (int a = 0; a < Q; ++a) {
+                    const double* zz = z_s + (size_t)a * d_pad + (c * 32 + lane) * VN;
+#pragma unroll
+                    for (int e = 0; e < VN; ++e) {
+                        const double zv = zz[e];
+                        acc0[a] = fma(xd0[e], zv, acc0[a]);
+                        acc1[a] = fma(xd1[e], zv, acc1[a]);
+                    }
+                }
+            }
+            // lane sums by xor butterfly; lane r (r + 1) keeps the totals of its row
+#pragma unroll
+            for (int a = 0; a < Q; ++a) {
+                double s0 = acc0[a], s1 = acc1[a];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                }
+                if (lane == r) dot[a] = s0;
+                if (lane == r + 1) dot[a] = s1;
+            }
+        }
+        const int64_t i = row0 + lane;
+        if (i < n) {
+            double proj[Q];
+#pragma unroll
+            for (int a = 0; a < Q; ++a) proj[a] = 0.0;
+            const double* u = U + i;
+            for (int j = 0; j < W; ++j) {
+                const double uj = u[(int64_t)j * ldu];
+#pragma unroll
+                for (int a = 0; a < Q; ++a) proj[a] = fma(uj, ur_s[a * W + j], proj[a]);
+            }
+            const double sq = sqn[i];
+            double e[Q];
+            double dm = 0.0, dv = 0.0;
+#pragma unroll
+            for (int a = 0; a < Q; ++a) {
+                double num = var * exp((sq + hdr->zn[a] - 2.0 * dot[a]) / neg2ls2) - proj[a];
+#pragma unroll
+                for (int b = 0; b < Q; ++b)
+                    if (b < a) num = fma(-e[b], hdr->tri[a * 4 + b], num);
+                e[a] = num / hdr->piv[a];
+                U[(int64_t)(W + a) * ldu + i] = e[a];
+                dm = fma(e[a], hdr->beta[a], dm);
+                dv = fma(e[a], e[a], dv);
+            }
+            m[i] += dm;
+            v[i] -= dv;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // The streaming pass with the X stream staged through shared memory by the bulk-copy engine (TMA, 1-D
 // cp.async.bulk + mbarrier): every warp owns a private ring of kBulkSlots slots of kBulkRows rows (4 KB at
 // d = 512 float32); lane 0 issues one bulk copy per slot (the rows of a slot are contiguous in HBM) and the whole

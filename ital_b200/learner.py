@@ -52,6 +52,10 @@ class _Shard(object):
         record = _capi.as_f64(record)
         _capi.check(self.lib.ital_add_labelled(self.handle, _capi.dptr(record), float(y)))
 
+    def add_labelled_many(self, records, y):
+        records, y = _capi.as_f64(records), _capi.as_f64(y)
+        _capi.check(self.lib.ital_add_labelled_many(self.handle, len(y), _capi.dptr(records), _capi.dptr(y)))
+
     def mark_seen(self, idx):
         idx = _capi.as_i64(idx)
         if len(idx):
@@ -345,11 +349,14 @@ class ITAL(object):
         return rel, irr, unnameable
 
     def _add_labelled(self, idx, y):
-        for i, yi in zip(idx, y):       # one rank-1 extension and one pass over the pool per labelled point
-            rec = self._comm.sum_records(self._shard.export_points([int(i)]))[0]
-            self._shard.add_labelled(rec, yi)
-            self._labelled_idx.append(int(i))
-            self._labelled_y.append(float(yi))
+        """gp.fit / gp.update (ital/gp.py:141-200): up to four labelled points per pass over the pool."""
+        idx, y = [int(i) for i in idx], [float(v) for v in y]
+        for lo in range(0, len(idx), 4):
+            chunk = idx[lo:lo + 4]
+            recs = self._comm.sum_records(self._shard.export_points(chunk))     # all in the current state
+            self._shard.add_labelled_many(recs, y[lo:lo + 4])
+            self._labelled_idx.extend(chunk)
+            self._labelled_y.extend(y[lo:lo + 4])
         self._rel_mean = None
 
     def update(self, feedback):                                                 # retrieval_base.py:105-126
