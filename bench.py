@@ -217,6 +217,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--exhaustive-steps', type=int, default=1)
     ap.add_argument('--lazy-steps', type=int, default=50)
+    ap.add_argument('--rounds', type=int, default=5, help='full fetch+update rounds timed at the end')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -338,6 +339,35 @@ def main():
                         '(k_catchup) instead of one streaming pass over the pool per greedy step (k_extend)'}
         learner.lazy_rows = False
 
+    # a few full active-learning rounds (fetch 4, label them, update) for orientation: the update is the other
+    # user of the streaming pass (one pass per <= 4 labels); this changes the model, so it runs last
+    rounds = None
+    if args.rounds > 0:
+        c0 = head[0]
+        barrier()
+        tf = tu = 0.0
+        for _ in range(args.rounds):
+            w0 = time.perf_counter()
+            batch = learner.fetch_unlabelled(args.batch)
+            w1 = time.perf_counter()
+            lab = {}
+            for i in batch:        # simulated user: relevance = membership in the query's cluster
+                owner = i // args.rows
+                ci = assign[i - first] if owner == rank else -1
+                if world > 1:
+                    tt = torch.tensor([ci], device='cuda')
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    ci = int(tt[0])
+                lab[i] = 1 if ci == c0 else -1
+            learner.update(lab)
+            torch.cuda.synchronize()
+            w2 = time.perf_counter()
+            tf += w1 - w0
+            tu += w2 - w1
+        rounds = {'rounds': args.rounds, 'fetch_ms': tf / args.rounds * 1e3, 'update_ms': tu / args.rounds * 1e3,
+                  'labelled_after': n_lab + args.rounds * args.batch,
+                  'note': 'wall clock; update(%d labels) = one multi-column streaming pass + host bookkeeping' % args.batch}
+
     if rank != 0:
         dist.destroy_process_group()
         return
@@ -367,6 +397,7 @@ def main():
                      'share_of_step': ms.value / 1e3 / dev},
         'exhaustive': exh,
         'lazy_rows': lazy,
+        'al_rounds': rounds,
         'fetch_stats_per_step': stats,
         'setup': {'generate_s': t_gen, 'fit_s': t_fit, 'update_9_labels_s': t_update},
     }

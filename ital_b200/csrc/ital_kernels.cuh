@@ -286,21 +286,32 @@ k_extend_multi(const XT* __restrict__ X, int64_t n, int d_pad, const double* __r
 #pragma unroll
             for (int a = 0; a < Q; ++a) { acc0[a] = 0.0; acc1[a] = 0.0; }
             const int64_t ra = row0 + r, rb = row0 + r + 1;
-            for (int c = 0; c < nchunks; ++c) {
-                Vec<XT> x0, x1;
-                if (ra < n) x0.load(X + ra * (int64_t)d_pad + (c * 32 + lane) * VN); else x0.zero();
-                if (rb < n) x1.load(X + rb * (int64_t)d_pad + (c * 32 + lane) * VN); else x1.zero();
-                double xd0[VN], xd1[VN];
+            // chunks in groups of four: all eight 16-byte loads of a group are issued before any is used
+            for (int c0 = 0; c0 < nchunks; c0 += 4) {
+                Vec<XT> x0[4], x1[4];
 #pragma unroll
-                for (int e = 0; e < VN; ++e) { xd0[e] = x0.get(e); xd1[e] = x1.get(e); }
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int c = c0 + cc;
+                    if (c < nchunks && ra < n) x0[cc].load(X + ra * (int64_t)d_pad + (c * 32 + lane) * VN); else x0[cc].zero();
+                    if (c < nchunks && rb < n) x1[cc].load(X + rb * (int64_t)d_pad + (c * 32 + lane) * VN); else x1[cc].zero();
+                }
 #pragma unroll
-                for (int a = 0; a < Q; ++a) {
-                    const double* zz = z_s + (size_t)a * d_pad + (c * 32 + lane) * VN;
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int c = c0 + cc;
+                    if (c < nchunks) {
+                        double xd0[VN], xd1[VN];
 #pragma unroll
-                    for (int e = 0; e < VN; ++e) {
-                        const double zv = zz[e];
-                        acc0[a] = fma(xd0[e], zv, acc0[a]);
-                        acc1[a] = fma(xd1[e], zv, acc1[a]);
+                        for (int e = 0; e < VN; ++e) { xd0[e] = x0[cc].get(e); xd1[e] = x1[cc].get(e); }
+#pragma unroll
+                        for (int a = 0; a < Q; ++a) {
+                            const double* zz = z_s + (size_t)a * d_pad + (c * 32 + lane) * VN;
+#pragma unroll
+                            for (int e = 0; e < VN; ++e) {
+                                const double zv = zz[e];
+                                acc0[a] = fma(xd0[e], zv, acc0[a]);
+                                acc1[a] = fma(xd1[e], zv, acc1[a]);
+                            }
+                        }
                     }
                 }
             }
