@@ -146,7 +146,8 @@ int64_t ital_launch_count(const ital_shard* s);
 
 /* Host-side pieces exposed for CPU-only tests (no GPU needed) ------------------------------------------- */
 /* Shared quadrature nodes of one greedy step (see oracle/orthant.py for the rule): base mean m[t], lower
- * Cholesky factor L[t*t] (row-major).  With eta == NULL returns the capacity (2q)^t; otherwise fills eta[t*N]
+ * Cholesky factor L[t*t] (row-major).  With eta == NULL returns the capacity ((2q)^t, or 65536 quasi-Monte-Carlo
+ * nodes from t = 4 on); otherwise fills eta[t*N]
  * (dimension-major, stride N), w[N], orth[N], sorted by orthant, and masses[2^t], and returns N, the number of
  * nodes kept (nodes lighter than 1e-13 are dropped). */
 int64_t ital_snq_nodes(int t, const double* m, const double* L, double* eta, double* w, int32_t* orth,

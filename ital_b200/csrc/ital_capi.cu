@@ -343,8 +343,7 @@ int ensure_nodes(ital_shard* s, int64_t n_nodes) {
 int prepare_nodes(ital_shard* s) {
     const int t = s->t;
     const int q = snq::order_for(t);
-    int64_t N = 1;
-    for (int j = 0; j < t; ++j) N *= 2 * q;
+    const int64_t N = snq::capacity_for(t);
     int rc = ensure_nodes(s, N);
     if (rc) return rc;
     s->n_nodes = N;
@@ -374,6 +373,7 @@ int prepare_nodes(ital_shard* s) {
         for (int b = 0; b <= a; ++b) Lb[(size_t)a * t + b] = bL[(size_t)a * kBaseStride + b];
     snq::Nodes nd = snq::generate(t, bm.data(), Lb.data());
     const int nb = 1 << t;
+    s->n_nodes = nd.n;                      // stride of the dimension-major coordinates
     CU(cudaMemcpyAsync(s->eta_dev, nd.eta.data(), nd.eta.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     CU(cudaMemcpyAsync(s->w_dev, nd.w.data(), nd.w.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     CU(cudaMemcpyAsync(s->masses_dev, nd.masses.data(), nb * sizeof(double), cudaMemcpyHostToDevice, s->stream));
@@ -1236,11 +1236,7 @@ int64_t ital_launch_count(const ital_shard* s) { return s ? s->launches : 0; }
 
 int64_t ital_snq_nodes(int t, const double* m, const double* L, double* eta, double* w, int32_t* orth, double* masses) {
     if (t < 1 || t > 10 || !m || !L) return fail(ITAL_EINVAL, "ital_snq_nodes: bad arguments");
-    if (!eta) {
-        int64_t n = 1;
-        for (int j = 0; j < t; ++j) n *= 2 * snq::order_for(t);
-        return n;
-    }
+    if (!eta) return snq::capacity_for(t);
     snq::Nodes nd = snq::generate(t, m, L);
     memcpy(eta, nd.eta.data(), nd.eta.size() * sizeof(double));
     if (w) memcpy(w, nd.w.data(), nd.w.size() * sizeof(double));

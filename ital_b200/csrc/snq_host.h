@@ -19,12 +19,40 @@ constexpr int kQMin = 2;
 constexpr int kMaxOrder = 64;
 constexpr double kWMin = 1e-13;   // nodes lighter than this are dropped (about half of them at t = 3, mass ~1e-11)
 
-inline int order_for(int t) {
+constexpr int kQmcFrom = 4;        // bases of this many variables or more use the quasi-Monte-Carlo node set
+constexpr int64_t kQmcN = 65536;
+
+inline int order_for(int t) {      // Gauss-Legendre nodes per panel, t <= 3 (0: quasi-Monte-Carlo nodes instead)
     if (t <= 1) return 32;
     if (t == 2) return 16;
     if (t == 3) return 12;
-    if (t == 4) return 6;
-    return t == 5 ? 4 : 2;
+    return 0;
+}
+
+inline int64_t capacity_for(int t) {
+    if (t >= kQmcFrom) return kQmcN;
+    int64_t n = 1;
+    for (int j = 0; j < t; ++j) n *= 2 * order_for(t);
+    return n;
+}
+
+// inverse of the standard normal CDF: Abramowitz-Stegun 26.2.23 start, Halley steps on 0.5 erfc(-x / sqrt 2)
+inline double ndtri(double p) {
+    const bool lower = p < 0.5;
+    const double pp = lower ? p : 1.0 - p;
+    const double tt = std::sqrt(-2.0 * std::log(pp));
+    double x = tt - (2.515517 + 0.802853 * tt + 0.010328 * tt * tt) /
+                        (1.0 + 1.432788 * tt + 0.189269 * tt * tt + 0.001308 * tt * tt * tt);
+    x = lower ? -x : x;
+    for (int it = 0; it < 6; ++it) {
+        const double cdf = 0.5 * std::erfc(-x * 0.70710678118654752440);
+        const double pdf = std::exp(-0.5 * x * x) * 0.39894228040143267794;
+        const double f = cdf - p;
+        const double dx = f / (pdf + 0.5 * x * f);        // Halley: f / (f' - f f'' / (2 f')), f'' = -x f'
+        x -= dx;
+        if (std::fabs(dx) < 1e-15 * (1.0 + std::fabs(x))) break;
+    }
+    return x;
 }
 
 struct GaussLegendre {
@@ -87,13 +115,43 @@ struct Nodes {
 inline Nodes generate(int t, const double* m, const double* L, int q = 0, double R = kR) {
     Nodes out;
     out.t = t;
+    const bool qmc = q <= 0 && t >= kQmcFrom;
     if (q <= 0) q = order_for(t);
     const int two_q = 2 * q;
     int64_t n = 1;
     std::vector<double> eta(0), w(1, 1.0);
     std::vector<int32_t> orth(1, 0);
     const GaussLegendre& G = gl();
-    for (int j = 0; j < t; ++j) {
+    if (qmc) {
+        // Kronecker sequence frac((k + 1/2) sqrt(p_j)), tent map, inverse normal CDF; equal weights
+        // (oracle/orthant.py qmc_nodes); accuracy class of the reference's mvndst(maxpts=100*dim)
+        static const int primes[10] = {2, 3, 5, 7, 11, 13, 17, 19, 23, 29};
+        n = kQmcN;
+        eta.assign((size_t)t * n, 0.0);
+        w.assign(n, 1.0 / (double)n);
+        orth.assign(n, 0);
+        for (int j = 0; j < t; ++j) {
+            double a = std::sqrt((double)primes[j]);
+            a -= std::floor(a);
+            for (int64_t k = 0; k < n; ++k) {
+                double u = ((double)k + 0.5) * a;
+                u -= std::floor(u);
+                u = 1.0 - std::fabs(2.0 * u - 1.0);
+                u = u < 1e-16 ? 1e-16 : (u > 1.0 - 1e-16 ? 1.0 - 1e-16 : u);
+                eta[(size_t)j * n + k] = ndtri(u);
+            }
+        }
+        for (int64_t k = 0; k < n; ++k) {
+            int ob = 0;
+            for (int j = 0; j < t; ++j) {
+                double z = m[j];
+                for (int i = 0; i <= j; ++i) z += L[j * t + i] * eta[(size_t)i * n + k];
+                ob |= (z > 0.0 ? 1 : 0) << j;
+            }
+            orth[k] = ob;
+        }
+    }
+    for (int j = 0; j < (qmc ? 0 : t); ++j) {
         const int64_t n_new = n * two_q;
         std::vector<double> eta_new((size_t)(j + 1) * n_new), w_new(n_new);
         std::vector<int32_t> orth_new(n_new);
@@ -132,7 +190,7 @@ inline Nodes generate(int t, const double* m, const double* L, int q = 0, double
         n = n_new;
     }
     // drop the nodes whose weight is negligible (keeps the generation order)
-    if (t > 0) {
+    if (t > 0 && !qmc) {
         int64_t kept = 0;
         for (int64_t k = 0; k < n; ++k) {
             if (w[k] < kWMin) continue;

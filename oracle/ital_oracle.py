@@ -302,7 +302,7 @@ class OracleITAL(object):
         cov[:D - 1, :D - 1] = cov_base
         cov[:D - 1, D - 1] = cov[D - 1, :D - 1] = cov_base_c
         cov[D - 1, D - 1] = var_c
-        p_all = orthant_prob_all(mean, cov, snq_order(D - 1))
+        p_all = orthant_prob_all(mean, cov, snq_order(D - 1) or None)
         order = np.argsort(ids, kind='stable')                 # updated_prob_rel sorts by index (ital.py:448)
         mi = 0.0
         for reli in itertools.product([False, True], repeat=D):                # ital.py:295
@@ -357,5 +357,5 @@ class OracleITAL(object):
         cov_u = cov - cov[:, obs] @ G
         mean_u, cov_u = mean_u[order], cov_u[np.ix_(order, order)]
         rel_sorted = np.asarray(reli)[order]
-        p = orthant_prob_all(mean_u, cov_u, snq_order(len(mean) - 1))
+        p = orthant_prob_all(mean_u, cov_u, snq_order(len(mean) - 1) or None)
         return p[sum(int(r) << j for j, r in enumerate(rel_sorted))]

@@ -55,7 +55,7 @@ def test_snq_nodes_match_oracle(lib, t):
         eta_o, w_o, orth_o = orthant.snq_nodes(m, L)
         order = np.argsort(orth_o, kind='stable')
         cap = lib.ital_snq_nodes(t, _capi.dptr(m), _capi.dptr(np.ascontiguousarray(L)), None, None, None, None)
-        assert cap == (2 * lib.ital_snq_order(t)) ** t >= len(w_o)
+        assert cap == ((2 * lib.ital_snq_order(t)) ** t if t <= 3 else orthant.SNQ_QMC_N) >= len(w_o)
         eta_buf = np.zeros(t * cap)
         w = np.zeros(cap)
         orth = np.zeros(cap, dtype=np.int32)
@@ -66,10 +66,11 @@ def test_snq_nodes_match_oracle(lib, t):
         assert n == len(w_o)        # both drop the nodes lighter than 1e-13
         eta, w, orth = eta_buf[:t * n].reshape(t, n), w[:n], orth[:n]
         assert np.array_equal(orth, orth_o[order])
-        np.testing.assert_allclose(eta.T, eta_o[order], rtol=0, atol=2e-13)
+        # (t >= 4: inverse normal CDF of Kronecker points; the few points with u ~ 1e-10 are ill-conditioned)
+        np.testing.assert_allclose(eta.T, eta_o[order], rtol=0, atol=2e-13 if t <= 3 else 1e-10)
         np.testing.assert_allclose(w, w_o[order], rtol=1e-12, atol=1e-300)
         np.testing.assert_allclose(masses, orthant.base_masses(w_o, orth_o, t), rtol=1e-12)
-        assert abs(masses.sum() - 1.0) < {1: 1e-11, 2: 1e-8, 3: 1e-6, 4: 1e-1}[t]   # t >= 4: coarse panels, see DESIGN.md (batches > 4)
+        assert abs(masses.sum() - 1.0) < {1: 1e-11, 2: 1e-8, 3: 1e-6, 4: 1e-12}[t]   # t >= 4: equal-weight QMC nodes
 
 
 def test_snq_order_matches_oracle(lib):

@@ -185,6 +185,21 @@ def test_bulk_staged_stream_is_bit_identical():
     assert np.array_equal(out[False][1], out[True][1]) and np.array_equal(out[False][2], out[True][2])
 
 
+def test_batches_beyond_four_track_the_oracle():
+    """Greedy steps with 4 and more base variables switch from the tensor rule to 65 536 quasi-Monte-Carlo nodes
+    (oracle/orthant.py qmc_nodes, csrc/snq_host.h); same nodes on both sides, so scores agree to round-off."""
+    from oracle.ital_oracle import OracleITAL
+    X, assign = _syn(500, 48, seed=21, centres=8)
+    gpu = _gpu_learner(X, length_scale=1.0, exhaustive=True)
+    ora = OracleITAL(X, length_scale=1.0)
+    _label_syn(gpu, assign)
+    _label_syn(ora, assign)
+    ret, kinds = _compare_steps(gpu, ora, 7)
+    assert len(ret) == 7 and len(set(ret)) == 7
+    gpu.exhaustive = False
+    assert gpu.fetch_unlabelled(7) == ret
+
+
 def test_repeated_rounds_track_the_oracle():
     """Several update/fetch rounds like run_experiment.py:160-164, incremental model on the GPU."""
     from oracle.ital_oracle import OracleITAL
