@@ -202,7 +202,7 @@ int launch_extend_t(ital_shard* s, int W_used, int labelled, double y, uint8_t m
         // TMA-staged variant: one CTA per SM, every warp with a private ring of slots
         const int bthreads = kBulkThreads, bwarps = bthreads / 32;
         const size_t ring = (size_t)bwarps * kBulkSlots * kBulkRows * s->d_pad * sizeof(XT);
-        const size_t bsmem = ring + ((size_t)bwarps * 32 * 33 + ((W_used + 1) & ~1)) * sizeof(double) +
+        const size_t bsmem = ring + (size_t)((W_used + 1) & ~1) * sizeof(double) +
                              (size_t)bwarps * kBulkSlots * sizeof(uint64_t);
         const int bblocks = (int)std::min<int64_t>((units + bwarps - 1) / bwarps, (int64_t)s->num_sms);
 #define ITAL_LAUNCH_BULK(NCV)                                                                                     \

@@ -57,6 +57,28 @@ __device__ __forceinline__ double mi_term(double p, double log1p_eps) {
     return p * (log1p_eps - log(p + kEps));
 }
 
+// Sum of 32 lane partials in the order of an xor butterfly (1, 2, 4, 8, 16): ((p0+p1)+(p2+p3))+...  Every kernel
+// that sums lane partials of a row uses this association, whether the partials sit in shared memory (k_extend),
+// travel through shuffles (k_catchup) or are transposed on the fly (k_extend_bulk), so the three agree bit for bit.
+__device__ __forceinline__ double tree_sum32(const double* p) {
+    double a[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = p[2 * k] + p[2 * k + 1];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = a[2 * k] + a[2 * k + 1];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a[k] = a[2 * k] + a[2 * k + 1];
+    return (a[0] + a[1]) + (a[2] + a[3]);
+}
+
+// One level of the on-the-fly transposition: `lo` belongs to the row group whose bit `o` is 0, `hi` to the one whose
+// bit is 1.  Each lane hands the value of the other group to its partner (lane ^ o) and keeps the sum for its own.
+__device__ __forceinline__ double tree_combine(double lo, double hi, int o, int lane) {
+    const bool up = (lane & o) != 0;
+    const double recv = __shfl_xor_sync(0xffffffffu, up ? lo : hi, o);
+    return (up ? hi : lo) + recv;
+}
+
 template <typename XT> struct Vec;
 template <> struct Vec<float> {
     static constexpr int N = 4;
@@ -215,9 +237,7 @@ k_extend(const XT* __restrict__ X, int64_t n, int d, int d_pad, const double* __
         // ---- phase 2: lane l finishes row row0 + l ----
         const int64_t i = row0 + lane;
         if (i < n) {
-            double dot = 0.0;
-#pragma unroll
-            for (int l = 0; l < 32; ++l) dot += part[lane * 33 + l];
+            const double dot = tree_sum32(part + lane * 33);
             // v * exp((A + B - 2 * C) / s), s = -2 * sigma^2   (ital/gp.py:416)
             const double kv = var * exp((sqn[i] + zn - 2.0 * dot) / neg2ls2);
             double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
@@ -372,7 +392,7 @@ k_extend_multi(const XT* __restrict__ X, int64_t n, int d_pad, const double* __r
 #define ITAL_BULK_SLOTS 4
 #endif
 #ifndef ITAL_BULK_THREADS
-#define ITAL_BULK_THREADS 384
+#define ITAL_BULK_THREADS 512
 #endif
 constexpr int kBulkRows = ITAL_BULK_ROWS;
 constexpr int kBulkSlots = ITAL_BULK_SLOTS;
@@ -410,10 +430,9 @@ k_extend_bulk(const XT* __restrict__ X, int64_t n, int d, int d_pad, const doubl
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarp_blk = blockDim.x >> 5;
     const uint32_t row_bytes = (uint32_t)d_pad * sizeof(XT);
     const uint32_t slot_bytes = kBulkRows * row_bytes;
-    // layout: [ring of every warp][part of every warp][ur][barriers]
+    // layout: [ring of every warp][ur][barriers]
     unsigned char* ring = bsm_raw + (size_t)wib * kBulkSlots * slot_bytes;
-    double* part = (double*)(bsm_raw + (size_t)nwarp_blk * kBulkSlots * slot_bytes) + (size_t)wib * 32 * 33;
-    double* ur_s = (double*)(bsm_raw + (size_t)nwarp_blk * kBulkSlots * slot_bytes) + (size_t)nwarp_blk * 32 * 33;
+    double* ur_s = (double*)(bsm_raw + (size_t)nwarp_blk * kBulkSlots * slot_bytes);
     uint64_t* bars = (uint64_t*)(ur_s + ((W + 1) & ~1)) + wib * kBulkSlots;
     const double* ur = rec + 8;
     const double* z = rec + 8 + w_cap;
@@ -460,16 +479,22 @@ k_extend_bulk(const XT* __restrict__ X, int64_t n, int d, int d_pad, const doubl
     int64_t sidx = 0;
     for (int64_t unit = warp_global; unit < n_units; unit += warps_total) {
         const int64_t row0 = unit << 5;
-#pragma unroll 1
+        // Phase 1 with the 90-degree turn folded in: the lane partials of the 32 rows are transposed on the fly by a
+        // binary tree of shuffles (pairs of rows, then pairs of pairs, ...), so that lane l ends up with the full
+        // dot product of row l and no shared-memory tile is needed.  lv[k] holds the pending value of level k.
+        double lv[5];
+        double dot = 0.0;
+#pragma unroll
         for (int sub = 0; sub < kSubPerUnit; ++sub, ++sidx) {
             const int slot = (int)(sidx % kBulkSlots);
             bar_wait(bars + slot, (uint32_t)((sidx / kBulkSlots) & 1));
             const unsigned char* sp = ring + (size_t)slot * slot_bytes;
 #pragma unroll
             for (int rr = 0; rr < kBulkRows; ++rr) {
+                const int r = sub * kBulkRows + rr;             // compile-time after unrolling
                 const XT* xr = (const XT*)(sp + (size_t)rr * row_bytes) + lane * VN;
                 double a0 = 0.0, a1 = 0.0;
-                if (row0 + sub * kBulkRows + rr < n) {
+                if (row0 + r < n) {
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
                         Vec<XT> x;
@@ -481,17 +506,19 @@ k_extend_bulk(const XT* __restrict__ X, int64_t n, int d, int d_pad, const doubl
                         }
                     }
                 }
-                part[(sub * kBulkRows + rr) * 33 + lane] = a0 + a1;
+                double val = a0 + a1;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    if (((r >> k) & 1) == 0) { lv[k] = val; break; }
+                    val = tree_combine(lv[k], val, 1 << k, lane);
+                    if (k == 4) dot = val;
+                }
             }
             __syncwarp();                                   // every lane is done with the slot
             if (lane == 0 && sidx + kBulkSlots < total_sub) issue(sidx + kBulkSlots);
         }
-        __syncwarp();
         const int64_t i = row0 + lane;
         if (i < n) {
-            double dot = 0.0;
-#pragma unroll
-            for (int l = 0; l < 32; ++l) dot += part[lane * 33 + l];
             const double kv = var * exp((sqn[i] + zn - 2.0 * dot) / neg2ls2);
             double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
             const double* u = U + i;
@@ -510,7 +537,6 @@ k_extend_bulk(const XT* __restrict__ X, int64_t n, int d, int d_pad, const doubl
                 v[i] = fma(-e, e, v[i]);
             }
         }
-        __syncwarp();
     }
 }
 
@@ -539,6 +565,7 @@ __global__ void __launch_bounds__(256) k_catchup(const int* __restrict__ count, 
         const int c0 = ncol[i];
         if (c0 >= t) continue;
         for (int j = lane; j < W + c0; j += 32) uv[j] = U[(int64_t)j * ldu + i];
+        __syncwarp();
         const XT* xrow = X + i * (int64_t)d_pad;
         const double sq = sqn[i];
         for (int col = c0; col < t; ++col) {
@@ -561,13 +588,11 @@ __global__ void __launch_bounds__(256) k_catchup(const int* __restrict__ count, 
                     }
                 }
             }
-            __syncwarp();
-            part[lane] = fixed ? a0 + a1 : a0;
-            __syncwarp();
+            double dot = fixed ? a0 + a1 : a0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);   // = tree_sum32 order
             double e_new = 0.0;
             if (lane == 0) {
-                double dot = 0.0;
-                for (int l = 0; l < 32; ++l) dot += part[l];
                 const double kv = var * exp((sq + rec[4] - 2.0 * dot) / neg2ls2);
                 const double* ur = rec + 8;
                 const int Wc = W + col;
