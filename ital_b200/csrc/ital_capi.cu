@@ -76,6 +76,7 @@ struct ital_shard {
     int64_t nodes_cap = 0;
     int64_t n_nodes = 0;
     double* gl_dev = nullptr;        // Gauss-Legendre tables: x[65][64] then w[65][64]
+    double2* phi_dev = nullptr;      // (Phi, phi) on the grid of phi_tab
     // batch state on the device: means and Cholesky rows of the selected points, selection list, H(base)
     double *base_m_dev = nullptr, *base_L_dev = nullptr, *sel_dev = nullptr, *hbase_dev = nullptr;
     double* sel_host = nullptr;      // pinned mirror of sel_dev: (global row, score) per step
@@ -423,6 +424,7 @@ int launch_eval(ital_shard* s, int64_t items_hint, bool block_per_candidate) {
     a.eta = s->eta_dev;
     a.w = s->w_dev;
     a.orth = s->orth_dev;
+    a.phi = s->phi_dev;
     a.group_begin = s->group_dev;
     a.n_nodes = s->n_nodes;
     a.n_kept = s->counters + 3;
@@ -506,6 +508,7 @@ int propose_general(ital_shard* s) {
     a.lp = s->label_prob;
     a.mp = s->mistake_prob;
     a.noise = s->noise;
+    a.phi = s->phi_dev;
     a.score = s->score;
     a.gain = s->gain;
     a.n_scored = s->counters + 2;
@@ -531,7 +534,7 @@ int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_o
         const bool general = s->label_prob < 1.0;
         const double lc = general ? (1.0 - s->mistake_prob) * s->log1p_eps + s->mistake_prob * std::log(1e-12) : s->log1p_eps;
         k_score0<<<blocks, 256, 0, s->stream>>>(s->n, s->m, s->v, s->mask, s->score, s->gain, s->block_best, lc,
-                                                general ? s->label_prob : 1.0); s->launches++;
+                                                general ? s->label_prob : 1.0, s->phi_dev); s->launches++;
         k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, blocks, s->best); s->launches++;
         CU(cudaGetLastError());
         s->n_nodes = 1;
@@ -601,7 +604,7 @@ void free_all(ital_shard* s) {
     cudaSetDevice(s->device);
     void* ptrs[] = {s->X, s->sqn, s->m, s->v, s->U, s->gain, s->score, s->mask, s->worklist, s->counters,
                     s->block_best, s->best, s->thr_dev, s->rec_dev, s->rec_in_dev, s->idx_dev, s->eta_dev,
-                    s->w_dev, s->masses_dev, s->group_dev, s->orth_dev, s->eta_raw, s->w_raw, s->orth_raw, s->gl_dev, s->base_m_dev, s->base_L_dev, s->sel_dev,
+                    s->w_dev, s->masses_dev, s->group_dev, s->orth_dev, s->eta_raw, s->w_raw, s->orth_raw, s->gl_dev, s->phi_dev, s->base_m_dev, s->base_L_dev, s->sel_dev,
                     s->hbase_dev, s->stats_dev, s->ncol, s->rec_hist, s->mext_dev, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -705,6 +708,16 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
         CU(cudaMalloc(&s->stats_dev, 16 * 4 * sizeof(int)));
         CU(cudaMallocHost(&s->sel_host, 32 * sizeof(double)));
         CU(cudaMallocHost(&s->stats_host, 16 * 4 * sizeof(int)));
+        {   // table of the standard normal CDF / density for phi_tab
+            std::vector<double2> tab(kPhiTableLen);
+            for (int k = 0; k < kPhiTableLen; ++k) {
+                const double xk = -kPhiXMax + (double)k / kPhiPerUnit;
+                tab[k].x = 0.5 * std::erfc(-xk * 0.70710678118654752440);
+                tab[k].y = std::exp(-0.5 * xk * xk) * 0.39894228040143267794;
+            }
+            CU(cudaMalloc(&s->phi_dev, tab.size() * sizeof(double2)));
+            CU(cudaMemcpy(s->phi_dev, tab.data(), tab.size() * sizeof(double2), cudaMemcpyHostToDevice));
+        }
         {   // Gauss-Legendre tables for every order the panel split can ask for
             const snq::GaussLegendre& G = snq::gl();
             std::vector<double> tab((size_t)2 * (snq::kMaxOrder + 1) * 64, 0.0);
