@@ -86,6 +86,7 @@ struct ital_shard {
     bool lazy_rows = false;          // batch projections only for the rows that get scored (k_catchup)
     bool bulk_stream = true;         // X stream staged by the bulk-copy engine (k_extend_bulk) where it applies
     uint8_t* ncol = nullptr;         // lazy rows: batch columns valid per row
+    uint8_t* stamp = nullptr;        // greedy step in which the row was last scored (this fetch)
     double* rec_hist = nullptr;      // records of the points selected in the running fetch
     double* mext_dev = nullptr;      // block of the multi-column labelled extension (MultiExt + z + ur)
     double* mext_host = nullptr;     // pinned
@@ -434,6 +435,7 @@ int launch_eval(ital_shard* s, int64_t items_hint, bool block_per_candidate) {
     a.flag_var = 100.0 * s->noise;
     a.score = s->score;
     a.gain = s->gain;
+    a.stamp = s->stamp;
     a.n_flagged = s->counters + 1;
     a.n_scored = s->counters + 2;
     a.force_block = block_per_candidate ? 1 : 0;
@@ -485,7 +487,6 @@ int propose_general(ital_shard* s) {
     CU(cudaMemcpyAsync(s->g_lut, gs.lut.data(), gs.lut.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
     CU(cudaStreamSynchronize(s->stream));       // gs lives in pageable host memory
     s->n_nodes = gs.n_nodes;
-    k_fill<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->score, s->n, std::numeric_limits<double>::quiet_NaN()); s->launches++;
     k_worklist<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->n, s->mask, s->gain, s->thr_dev, 1, s->counters, s->worklist); s->launches++;
     GeneralArgs a;
     a.count = s->counters;
@@ -511,6 +512,7 @@ int propose_general(ital_shard* s) {
     a.phi = s->phi_dev;
     a.score = s->score;
     a.gain = s->gain;
+    a.stamp = s->stamp;
     a.n_scored = s->counters + 2;
     if ((rc = launch_catchup(s, s->n))) return rc;
     const size_t smem = ((size_t)3 * gs.n_groups + 2 * gs.n_sets + (size_t)gs.n_groups * 24 + 8) * sizeof(double);
@@ -545,7 +547,6 @@ int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_o
         int rc = prepare_nodes(s);
         if (rc) return rc;
         if (exhaustive) {
-            k_fill<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->score, s->n, std::numeric_limits<double>::quiet_NaN()); s->launches++;
             k_worklist<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->n, s->mask, s->gain, s->thr_dev, 1,
                                                                         s->counters, s->worklist); s->launches++;
             CU(cudaGetLastError());
@@ -560,8 +561,8 @@ int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_o
             // top rows by bound instead is worse: they cluster around the previous pick, whose neighbours have
             // just lost their gain; measured 882 vs 399 rows left for stage B at t = 3 on SYN-1M.)
             const int ba = std::min(kArgmaxBlocks, std::min(blocks, 2 * s->num_sms));
-            k_argmax_rows<<<ba, 1024, 0, s->stream>>>(s->n, s->gain, s->mask, s->block_best, s->score); s->launches++;
-            k_list_from_blocks<<<1, 512, 0, s->stream>>>(s->block_best, ba, s->counters, s->worklist); s->launches++;
+            k_argmax_rows<<<ba, 1024, 0, s->stream>>>(s->n, s->gain, s->mask, s->block_best, s->counters + 4, s->counters,
+                                                      s->worklist); s->launches++;
             CU(cudaGetLastError());
             rc = launch_eval(s, ba, true);
             if (rc) return rc;
@@ -605,7 +606,7 @@ void free_all(ital_shard* s) {
     void* ptrs[] = {s->X, s->sqn, s->m, s->v, s->U, s->gain, s->score, s->mask, s->worklist, s->counters,
                     s->block_best, s->best, s->thr_dev, s->rec_dev, s->rec_in_dev, s->idx_dev, s->eta_dev,
                     s->w_dev, s->masses_dev, s->group_dev, s->orth_dev, s->eta_raw, s->w_raw, s->orth_raw, s->gl_dev, s->phi_dev, s->base_m_dev, s->base_L_dev, s->sel_dev,
-                    s->hbase_dev, s->stats_dev, s->ncol, s->rec_hist, s->mext_dev, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev};
+                    s->hbase_dev, s->stats_dev, s->ncol, s->stamp, s->rec_hist, s->mext_dev, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->rec_host) cudaFreeHost(s->rec_host);
@@ -693,8 +694,10 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
         CU(cudaMalloc(&s->score, (size_t)s->n * sizeof(double)));
         CU(cudaMalloc(&s->mask, (size_t)s->n));
         CU(cudaMalloc(&s->ncol, (size_t)s->n));
+        CU(cudaMalloc(&s->stamp, (size_t)s->n));
         CU(cudaMalloc(&s->worklist, (size_t)s->n * sizeof(int)));
-        CU(cudaMalloc(&s->counters, 4 * sizeof(int)));
+        CU(cudaMalloc(&s->counters, 8 * sizeof(int)));     // [4] ticket of k_argmax_rows
+        CU(cudaMemset(s->counters, 0, 8 * sizeof(int)));
         CU(cudaMalloc(&s->block_best, kArgmaxBlocks * sizeof(Best)));
         CU(cudaMalloc(&s->best, 2 * sizeof(Best)));
         CU(cudaMalloc(&s->thr_dev, sizeof(double)));
@@ -996,6 +999,7 @@ int ital_fetch_begin(ital_shard* s, double label_prob, double mistake_prob) {
         s->rec_hist_cap = hist_need;
     }
     if (s->lazy_rows) CU(cudaMemsetAsync(s->ncol, 0, (size_t)s->n, s->stream));
+    CU(cudaMemsetAsync(s->stamp, 0, (size_t)s->n, s->stream));
     const double hb0[2] = {0.0, 1.0};                   // first step: no base, total mass 1
     memcpy(s->sel_host + 30, hb0, sizeof hb0);          // (pinned scratch at the tail of the selection mirror)
     CU(cudaMemcpyAsync(s->hbase_dev, s->sel_host + 30, sizeof hb0, cudaMemcpyHostToDevice, s->stream));
@@ -1132,6 +1136,13 @@ int ital_last_scores(ital_shard* s, double* out) {
     if (!s || !out) return fail(ITAL_EINVAL, "bad arguments");
     int rc = copy_vec(s, s->score, out);
     if (rc) return rc;
+    if (s->proposals > 1) {      // steps after the first: only rows stamped with the step were scored in it
+        std::vector<uint8_t> st((size_t)s->n);
+        CU(cudaMemcpy(st.data(), s->stamp, (size_t)s->n, cudaMemcpyDeviceToHost));
+        const uint8_t want = (uint8_t)(s->proposals - 1);
+        for (int64_t i = 0; i < s->n; ++i)
+            if (st[i] != want) out[i] = std::numeric_limits<double>::quiet_NaN();
+    }
     if (s->mistake_prob > 0.0 && s->proposals > 0) {    // same additive constant as the records carry
         double hb[2];
         CU(cudaMemcpy(hb, s->hbase_dev, sizeof hb, cudaMemcpyDeviceToHost));

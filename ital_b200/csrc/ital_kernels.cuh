@@ -694,18 +694,16 @@ __global__ void __launch_bounds__(256) k_score0(int64_t n, const double* __restr
 
 // argmax of `values` over candidate rows (mask == 0); stage 1 of 2
 __global__ void __launch_bounds__(1024) k_argmax_rows(int64_t n, const double* __restrict__ values,
-                                                     const uint8_t* __restrict__ mask,
-                                                     Best* __restrict__ block_best,
-                                                     double* __restrict__ clear_score) {
+                                                      const uint8_t* __restrict__ mask,
+                                                      Best* __restrict__ block_best, int* __restrict__ done,
+                                                      int* __restrict__ count, int* __restrict__ list) {
     double bs = 0.0;
     long long bi = -1;
-    const double qnan = nan("");
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         if (mask[i] == 0 && better(values[i], i, bs, bi)) { bs = values[i]; bi = i; }
-        if (clear_score != nullptr) clear_score[i] = qnan;      // "not scored in this step"
-    }
     __shared__ double ss[32];
     __shared__ long long si[32];
+    __shared__ int last_s;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double os = __shfl_xor_sync(0xffffffffu, bs, o);
@@ -719,6 +717,20 @@ __global__ void __launch_bounds__(1024) k_argmax_rows(int64_t n, const double* _
             if (better(ss[w], si[w], bs, bi)) { bs = ss[w]; bi = si[w]; }
         block_best[blockIdx.x].score = bs;
         block_best[blockIdx.x].idx = bi;
+        // the last block to finish turns the per-block winners into the stage-A worklist (fixed order)
+        __threadfence();
+        last_s = (list != nullptr && atomicAdd(done, 1) == (int)gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (last_s) {
+        __threadfence();
+        if (threadIdx.x == 0) {
+            int c = 0;
+            for (int k = 0; k < (int)gridDim.x; ++k)
+                if (block_best[k].idx >= 0) list[c++] = (int)block_best[k].idx;
+            *count = c;
+            *done = 0;
+        }
     }
 }
 
@@ -840,6 +852,7 @@ struct EvalArgs {
     double flag_var;
     double* score;
     double* gain;
+    uint8_t* stamp;             // stamp[i] == t: row i has been scored in this greedy step
     int* n_flagged;
     int* n_scored;
     int force_block;
@@ -878,7 +891,7 @@ __global__ void __launch_bounds__(256) k_eval(EvalArgs a) {
     __shared__ double red[8];
     for (int item = team_global; item < n_items; item += teams_total) {
         const int64_t i = a.list[item];
-        if (a.score[i] == a.score[i]) continue;         // scored earlier in this step (team-uniform)
+        if (a.stamp[i] == (uint8_t)a.t) continue;       // scored earlier in this step (team-uniform)
         double l[T];
         double s2 = a.v[i];
 #pragma unroll
@@ -921,8 +934,9 @@ __global__ void __launch_bounds__(256) k_eval(EvalArgs a) {
             const double p_minus = fmax(a.masses[b] - p_plus, 0.0);
             sc += mi_term(p_plus, a.log1p_eps) + mi_term(p_minus, a.log1p_eps);
         }
-        if (TPC > 32) __syncthreads();                  // every thread has read score[i] before it is written
+        if (TPC > 32) __syncthreads();                  // every thread has read stamp[i] before it is written
         if (tid_team == 0) {
+            a.stamp[i] = (uint8_t)a.t;
             a.score[i] = sc;
             a.gain[i] = sc - *a.h_base;
             atomicAdd(a.n_scored, 1);
@@ -943,7 +957,7 @@ __global__ void __launch_bounds__(256) k_eval_sorted(EvalArgs a) {
     __shared__ double red[8];
     for (int item = team_global; item < n_items; item += teams_total) {
         const int64_t i = a.list[item];
-        if (a.score[i] == a.score[i]) continue;
+        if (a.stamp[i] == (uint8_t)a.t) continue;
         double l[MAXT];
         double s2 = a.v[i];
 #pragma unroll
@@ -976,6 +990,7 @@ __global__ void __launch_bounds__(256) k_eval_sorted(EvalArgs a) {
         }
         if (TPC > 32) __syncthreads();
         if (tid_team == 0) {
+            a.stamp[i] = (uint8_t)a.t;
             a.score[i] = sc;
             a.gain[i] = sc - *a.h_base;
             atomicAdd(a.n_scored, 1);
@@ -1015,6 +1030,7 @@ struct GeneralArgs {
     const double2* phi;
     double* score;
     double* gain;
+    uint8_t* stamp;
     int* n_scored;
 };
 
@@ -1126,6 +1142,7 @@ __global__ void __launch_bounds__(256) k_eval_general(GeneralArgs a) {
         if (threadIdx.x == 0) {
             double tot = 0.0;
             for (int k = 0; k < 8; ++k) tot += red[k];
+            a.stamp[i] = (uint8_t)a.t;
             a.score[i] = tot;
             a.gain[i] = tot;
             atomicAdd(a.n_scored, 1);
@@ -1302,14 +1319,6 @@ __global__ void __launch_bounds__(256) k_pick_winner(const double* __restrict__ 
         sel[2 * t] = r[0];
         sel[2 * t + 1] = r[1];
     }
-}
-
-// worklist = the per-block winners of an argmax stage (the most promising candidates, scored first)
-__global__ void k_list_from_blocks(const Best* __restrict__ block_best, int nblocks, int* __restrict__ count,
-                                   int* __restrict__ list) {
-    // one block; *count must be 0 on entry
-    for (int k = threadIdx.x; k < nblocks; k += blockDim.x)
-        if (block_best[k].idx >= 0) list[atomicAdd(count, 1)] = (int)block_best[k].idx;
 }
 
 __global__ void k_fill(double* __restrict__ p, int64_t n, double value) {
