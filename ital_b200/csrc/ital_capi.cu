@@ -109,7 +109,6 @@ struct ital_shard {
     std::vector<double> lab_x;               // labelled rows, W x d doubles
     std::vector<double> lab_sqn, lab_y;
     std::vector<int64_t> lab_idx;
-    std::vector<int64_t> selected;           // global indices selected in this fetch
 
     // predict() scratch
     double *lab_x_dev = nullptr, *lab_sqn_dev = nullptr, *w_vec_dev = nullptr, *LK_dev = nullptr;
@@ -626,7 +625,6 @@ int reset_model(ital_shard* s) {
     s->lab_sqn.clear();
     s->lab_y.clear();
     s->lab_idx.clear();
-    s->selected.clear();
     s->lab_dev_valid = false;
     const int blocks = grid_for(s, s->n, 256);
     k_fill<<<blocks, 256, 0, s->stream>>>(s->m, s->n, 0.0); s->launches++;
@@ -1006,7 +1004,6 @@ int ital_fetch_begin(ital_shard* s, double label_prob, double mistake_prob) {
     s->fetching = true;
     s->t = 0;
     s->proposals = 0;
-    s->selected.clear();
     s->label_prob = label_prob;
     s->mistake_prob = mistake_prob;
     return ITAL_OK;

@@ -722,15 +722,13 @@ __global__ void __launch_bounds__(1024) k_argmax_rows(int64_t n, const double* _
         last_s = (list != nullptr && atomicAdd(done, 1) == (int)gridDim.x - 1) ? 1 : 0;
     }
     __syncthreads();
-    if (last_s) {
+    if (last_s) {                                       // (*count is 0 on entry; the order of the list is immaterial)
         __threadfence();
-        if (threadIdx.x == 0) {
-            int c = 0;
-            for (int k = 0; k < (int)gridDim.x; ++k)
-                if (block_best[k].idx >= 0) list[c++] = (int)block_best[k].idx;
-            *count = c;
-            *done = 0;
+        for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) {
+            const long long idx = block_best[k].idx;
+            if (idx >= 0) list[atomicAdd(count, 1)] = (int)idx;
         }
+        if (threadIdx.x == 0) *done = 0;
     }
 }
 
@@ -1217,31 +1215,33 @@ __global__ void __launch_bounds__(1024) k_snq_finalize(int t, int64_t N, double 
     __shared__ int warp_tot[32];
     __shared__ double part[32][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int64_t per = (N + blockDim.x - 1) / blockDim.x;
-    const int64_t k0 = min(N, (int64_t)threadIdx.x * per), k1 = min(N, k0 + per);
+    // every warp owns a contiguous range of nodes and walks it 32 at a time (coalesced); ballots give the stable
+    // order inside the warp, one scan over the warp totals the offsets between warps
+    const int64_t per = ((N + nwarps - 1) / nwarps + 31) / 32 * 32;
+    const int64_t k0 = min(N, (int64_t)warp * per), k1 = min(N, k0 + per);
     int cnt = 0;
-    for (int64_t k = k0; k < k1; ++k) cnt += w_in[k] >= w_min;
-    // exclusive scan of cnt over the block
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int up = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += up;
+    for (int64_t k = k0 + lane; k < k1 + 31 - (k1 - k0 + 31) % 32; k += 32) {
+        const bool keep = k < k1 && w_in[k] >= w_min;
+        cnt += __popc(__ballot_sync(0xffffffffu, keep));
     }
-    if (lane == 31) warp_tot[warp] = incl;
+    if (lane == 0) warp_tot[warp] = cnt;
     __syncthreads();
-    int off = incl - cnt;
-    for (int ww = 0; ww < warp; ++ww) off += warp_tot[ww];
-    int kept = 0;
-    for (int ww = 0; ww < nwarps; ++ww) kept += warp_tot[ww];
-    for (int64_t k = k0; k < k1; ++k) {
-        const double wk = w_in[k];
-        if (wk >= w_min) {
-            w[off] = wk;
-            orth[off] = orth_in[k];
-            for (int j = 0; j < t; ++j) eta[(int64_t)j * N + off] = eta_in[(int64_t)j * N + k];
-            ++off;
+    int off = 0, kept = 0;
+    for (int ww = 0; ww < nwarps; ++ww) {
+        if (ww < warp) off += warp_tot[ww];
+        kept += warp_tot[ww];
+    }
+    for (int64_t k = k0 + lane; k < k1 + 31 - (k1 - k0 + 31) % 32; k += 32) {
+        const double wk = k < k1 ? w_in[k] : 0.0;
+        const bool keep = k < k1 && wk >= w_min;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int dst = off + __popc(bal & ((1u << lane) - 1));
+            w[dst] = wk;
+            orth[dst] = orth_in[k];
+            for (int j = 0; j < t; ++j) eta[(int64_t)j * N + dst] = eta_in[(int64_t)j * N + k];
         }
+        off += __popc(bal);
     }
     if (threadIdx.x == 0) *n_kept = kept;
     __syncthreads();

@@ -318,8 +318,14 @@ class ITAL(object):
         return self._comm.gather_rows(local, self._offsets)
 
     def top_results(self, k=None):                                              # retrieval_base.py:64-75
-        ind = np.argsort(self.rel_mean)[::-1]
-        return ind[:k] if k is not None else ind
+        """np.argsort(rel_mean)[::-1][:k]; for k far below n only the top slice is sorted (same result up to the
+        order of exactly tied scores, which the reference's unstable sort does not define either)."""
+        rel_mean = self.rel_mean
+        if k is None or k <= 0 or 4 * k >= len(rel_mean):
+            ind = np.argsort(rel_mean)[::-1]
+            return ind[:k] if k is not None else ind
+        top = np.argpartition(rel_mean, -k)[-k:]
+        return top[np.argsort(rel_mean[top])[::-1]]
 
     def _seen_mask(self):
         seen = np.zeros(self._n, dtype=bool)
