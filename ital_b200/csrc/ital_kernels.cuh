@@ -1216,13 +1216,25 @@ __global__ void __launch_bounds__(1024) k_snq_finalize(int t, int64_t N, double 
     __shared__ double part[32][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     // every warp owns a contiguous range of nodes and walks it 32 at a time (coalesced); ballots give the stable
-    // order inside the warp, one scan over the warp totals the offsets between warps
+    // order inside the warp, one scan over the warp totals the offsets between warps.  All loads of a pass are
+    // issued before any is used (N <= 13824 = 32 warps x kIt x 32 nodes).
+    constexpr int kIt = 14;
     const int64_t per = ((N + nwarps - 1) / nwarps + 31) / 32 * 32;
     const int64_t k0 = min(N, (int64_t)warp * per), k1 = min(N, k0 + per);
+    double wv[kIt];
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+        const int64_t k = k0 + it * 32 + lane;
+        wv[it] = k < k1 ? w_in[k] : 0.0;
+    }
+    int dst[kIt];                                       // position inside the warp's output, -1 = dropped
     int cnt = 0;
-    for (int64_t k = k0 + lane; k < k1 + 31 - (k1 - k0 + 31) % 32; k += 32) {
-        const bool keep = k < k1 && w_in[k] >= w_min;
-        cnt += __popc(__ballot_sync(0xffffffffu, keep));
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+        const bool keep = wv[it] >= w_min && k0 + it * 32 + lane < k1;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        dst[it] = keep ? cnt + __popc(bal & ((1u << lane) - 1)) : -1;
+        cnt += __popc(bal);
     }
     if (lane == 0) warp_tot[warp] = cnt;
     __syncthreads();
@@ -1231,17 +1243,30 @@ __global__ void __launch_bounds__(1024) k_snq_finalize(int t, int64_t N, double 
         if (ww < warp) off += warp_tot[ww];
         kept += warp_tot[ww];
     }
-    for (int64_t k = k0 + lane; k < k1 + 31 - (k1 - k0 + 31) % 32; k += 32) {
-        const double wk = k < k1 ? w_in[k] : 0.0;
-        const bool keep = k < k1 && wk >= w_min;
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-            const int dst = off + __popc(bal & ((1u << lane) - 1));
-            w[dst] = wk;
-            orth[dst] = orth_in[k];
-            for (int j = 0; j < t; ++j) eta[(int64_t)j * N + dst] = eta_in[(int64_t)j * N + k];
+#pragma unroll
+    for (int it = 0; it < kIt; ++it)
+        if (dst[it] >= 0) w[off + dst[it]] = wv[it];
+    {
+        int ov[kIt];
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+            const int64_t k = k0 + it * 32 + lane;
+            ov[it] = k < k1 ? orth_in[k] : 0;
         }
-        off += __popc(bal);
+#pragma unroll
+        for (int it = 0; it < kIt; ++it)
+            if (dst[it] >= 0) orth[off + dst[it]] = ov[it];
+    }
+    for (int j = 0; j < t; ++j) {
+        double ev[kIt];
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+            const int64_t k = k0 + it * 32 + lane;
+            ev[it] = k < k1 ? eta_in[(int64_t)j * N + k] : 0.0;
+        }
+#pragma unroll
+        for (int it = 0; it < kIt; ++it)
+            if (dst[it] >= 0) eta[(int64_t)j * N + off + dst[it]] = ev[it];
     }
     if (threadIdx.x == 0) *n_kept = kept;
     __syncthreads();
