@@ -464,3 +464,16 @@ class ITAL(object):
         finally:
             self._shard.fetch_end()
         return ret
+
+
+class EntropySampling(ITAL):
+    """Greedy maximum joint-entropy batches; drop-in for `ital.baseline_methods.EntropySampling`
+    (ital/baseline_methods.py:229-287), which scores a batch by the entropy of the sign pattern of its joint GP
+    posterior.  That is ITAL's mutual information under the perfect-user model, so the same kernels
+    serve it; the scores differ from the reference's only in its clamps (probabilities clipped to [1e-8, 1 - 1e-8]
+    for one sample, terms below 1e-12 dropped for several), i.e. by less than 1e-7."""
+
+    def __init__(self, data=None, queries=[], length_scale=0.1, var=1.0, noise=1e-6, **kwargs):
+        for name in ('label_prob', 'mistake_prob', 'label_estimation'):
+            kwargs.pop(name, None)
+        ITAL.__init__(self, data, queries, length_scale, var, noise, label_prob=1.0, mistake_prob=0.0, **kwargs)

@@ -200,6 +200,17 @@ def test_batches_beyond_four_track_the_oracle():
     assert gpu.fetch_unlabelled(7) == ret
 
 
+def test_entropy_sampling_shares_the_kernels():
+    """EntropySampling (ital/baseline_methods.py:229-287): joint entropy of the batch = perfect-user ITAL."""
+    from ital_b200 import EntropySampling
+    X, assign = _syn(2000, 64, seed=17, centres=10)
+    a, b = EntropySampling(X, length_scale=1.0, mistake_prob=0.3), _gpu_learner(X, length_scale=1.0)
+    for L in (a, b):
+        _label_syn(L, assign)
+    assert a.fetch_unlabelled(4) == b.fetch_unlabelled(4)
+    assert np.array_equal(a.last_fetch_scores, b.last_fetch_scores)
+
+
 def test_repeated_rounds_track_the_oracle():
     """Several update/fetch rounds like run_experiment.py:160-164, incremental model on the GPU."""
     from oracle.ital_oracle import OracleITAL
