@@ -200,6 +200,24 @@ def test_batches_beyond_four_track_the_oracle():
     assert gpu.fetch_unlabelled(7) == ret
 
 
+@pytest.mark.parametrize('var,noise,ls', [(2.5, 1e-4, 0.7), (0.3, 1e-6, 2.0), (1.0, 1e-2, 1.0)])
+def test_kernel_hyperparameters(var, noise, ls):
+    """var, sigma_noise and length_scale away from the defaults (ital/gp.py:100: k = var exp(-d^2 / 2 sigma^2))."""
+    from oracle.ital_oracle import OracleITAL
+    X, assign = _syn(1500, 40, seed=31, centres=9)
+    kw = dict(length_scale=ls, var=var, noise=noise)
+    gpu, ora = _gpu_learner(X, exhaustive=True, **kw), OracleITAL(X, **kw)
+    for L in (gpu, ora):
+        _label_syn(L, assign)
+    np.testing.assert_allclose(gpu.rel_mean, ora.rel_mean, rtol=1e-6, atol=1e-9)
+    v = gpu.gp.predict_stored(cov_mode='diag')[1]
+    np.testing.assert_allclose(v, ora.gp.predict_stored(cov_mode='diag')[1], rtol=1e-6, atol=1e-9 * var)
+    ret, kinds = _compare_steps(gpu, ora, 4)
+    assert ret == ora.fetch_unlabelled(4)
+    Xt = X[:64] * 1.01
+    np.testing.assert_allclose(gpu.gp.predict(Xt), ora.gp.predict(Xt), rtol=1e-6, atol=1e-9)
+
+
 def test_entropy_sampling_shares_the_kernels():
     """EntropySampling (ital/baseline_methods.py:229-287): joint entropy of the batch = perfect-user ITAL."""
     from ital_b200 import EntropySampling
