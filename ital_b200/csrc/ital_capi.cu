@@ -560,7 +560,7 @@ int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_o
             // top rows by bound instead is worse: they cluster around the previous pick, whose neighbours have
             // just lost their gain; measured 882 vs 399 rows left for stage B at t = 3 on SYN-1M.)
             const int ba = std::min(kArgmaxBlocks, std::min(blocks, 2 * s->num_sms));
-            k_argmax_rows<<<ba, 1024, 0, s->stream>>>(s->n, s->gain, s->mask, s->block_best, s->counters + 4, s->counters,
+            k_argmax_rows<<<ba, 512, 0, s->stream>>>(s->n, s->gain, s->mask, s->block_best, s->counters + 4, s->counters,
                                                       s->worklist); s->launches++;
             CU(cudaGetLastError());
             rc = launch_eval(s, ba, true);
