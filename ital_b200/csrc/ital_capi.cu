@@ -572,7 +572,7 @@ int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_o
             k_worklist<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->n, s->mask, s->gain, s->thr_dev, 0,
                                                                         s->counters, s->worklist); s->launches++;
             CU(cudaGetLastError());
-            rc = launch_eval(s, (int64_t)s->num_sms * 16, false);
+            rc = launch_eval(s, (int64_t)s->num_sms * 24, false);    // 3 resident blocks per SM (80 registers)
             if (rc) return rc;
             k_argmax_list<<<1, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->best); s->launches++;
         }
