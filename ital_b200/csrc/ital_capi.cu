@@ -271,6 +271,26 @@ int launch_extend_multi(ital_shard* s, int q, int W_used) {
         CU(cudaEventCreate(&ev1));
         CU(cudaEventRecord(ev0, s->stream));
     }
+    constexpr int VN = Vec<XT>::N;
+    const int bwarps = kMultiThreads / 32;
+    const size_t bsmem = (size_t)bwarps * kMultiSlots * 2 * s->d_pad * sizeof(XT) +
+                         ((size_t)q * s->d_pad + (size_t)((q * W_used + 1) & ~1)) * sizeof(double) +
+                         (size_t)bwarps * kMultiSlots * sizeof(uint64_t);
+    if (s->bulk_stream && s->d_pad * sizeof(XT) == 2048 && s->d_pad / (32 * VN) == 4 && bsmem <= 227 * 1024) {
+        // 2 KB rows: the TMA-staged variant, one CTA per SM
+        const int bblocks = (int)std::max<int64_t>(1, std::min<int64_t>((units + bwarps - 1) / bwarps, (int64_t)s->num_sms));
+#define ITAL_LAUNCH_BMULTI(QV)                                                                                        \
+    do {                                                                                                              \
+        CU(cudaFuncSetAttribute(k_extend_bulk_multi<XT, 4, QV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem)); \
+        k_extend_bulk_multi<XT, 4, QV><<<bblocks, kMultiThreads, bsmem, s->stream>>>(                                  \
+            (const XT*)s->X, s->n, (int)s->d_pad, s->mext_dev, W_used, s->sqn, s->U, s->ldu, s->m, s->v, s->var,      \
+            neg2ls2);                                                                                                 \
+    } while (0)
+        if (q == 2) ITAL_LAUNCH_BMULTI(2);
+        else if (q == 3) ITAL_LAUNCH_BMULTI(3);
+        else ITAL_LAUNCH_BMULTI(4);
+#undef ITAL_LAUNCH_BMULTI
+    } else {
 #define ITAL_LAUNCH_MULTI(QV)                                                                                     \
     do {                                                                                                          \
         CU(cudaFuncSetAttribute(k_extend_multi<XT, QV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -282,6 +302,7 @@ int launch_extend_multi(ital_shard* s, int q, int W_used) {
     else if (q == 3) ITAL_LAUNCH_MULTI(3);
     else ITAL_LAUNCH_MULTI(4);
 #undef ITAL_LAUNCH_MULTI
+    }
     s->launches++;
     CU(cudaGetLastError());
     if (s->profiling) {
@@ -302,18 +323,31 @@ double step_shift_coef(const ital_shard* s) {
     return (1.0 - c) * (std::log(1e-12) - s->log1p_eps);
 }
 
-int make_record(ital_shard* s, long long local_row, double* dst_dev) {
+int make_record(ital_shard* s, long long local_row, double* dst_dev, bool commit_here = false) {
     const double shift = local_row < 0 ? step_shift_coef(s) : 0.0;
+    CommitTargets ct;
+    if (commit_here) {
+        ct.rec_in = s->rec_in_dev;
+        ct.rec_hist_t = s->rec_hist + (int64_t)s->t * record_doubles(s);
+        ct.base_m = s->base_m_dev;
+        ct.base_L = s->base_L_dev;
+        ct.sel = s->sel_dev;
+        ct.mask = s->mask;
+        ct.n = s->n;
+        ct.t = s->t;
+        ct.mark_bits = kSelected;
+        ct.enabled = 1;
+    }
     if (s->x_dtype == ITAL_F32)
         k_record<float><<<1, 256, 0, s->stream>>>(local_row, s->best, s->row_offset, (const float*)s->X, (int)s->d,
                                                   (int)s->d_pad, s->sqn, s->m, s->v, s->U, s->ldu, s->W,
                                                   s->W + s->t, s->w_cap, s->gain, dst_dev, shift, s->hbase_dev,
-                                                  s->counters, local_row < 0 ? s->stats_dev + 4 * s->t : nullptr);
+                                                  s->counters, local_row < 0 ? s->stats_dev + 4 * s->t : nullptr, ct);
     else
         k_record<double><<<1, 256, 0, s->stream>>>(local_row, s->best, s->row_offset, (const double*)s->X,
                                                    (int)s->d, (int)s->d_pad, s->sqn, s->m, s->v, s->U, s->ldu,
                                                    s->W, s->W + s->t, s->w_cap, s->gain, dst_dev, shift, s->hbase_dev,
-                                                   s->counters, local_row < 0 ? s->stats_dev + 4 * s->t : nullptr); s->launches++;
+                                                   s->counters, local_row < 0 ? s->stats_dev + 4 * s->t : nullptr, ct); s->launches++;
     CU(cudaGetLastError());
     return ITAL_OK;
 }
@@ -527,7 +561,7 @@ int propose_general(ital_shard* s) {
 
 // The local candidates of the current greedy step -> record of the local best in DEVICE memory `rec_out`.
 // Nothing here waits for the GPU (t <= 3).
-int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_out) {
+int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_out, bool commit_here = false) {
     if (s->t >= kMaxBatch) return fail(ITAL_EINVAL, "batches of more than %d samples are not supported", kMaxBatch);
     const int blocks = std::min(kArgmaxBlocks, grid_for(s, s->n, 256));
     CU(cudaMemsetAsync(s->counters, 0, 4 * sizeof(int), s->stream));
@@ -580,16 +614,18 @@ int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_o
     }
     s->step_nodes[s->t] = (double)s->n_nodes;
     s->proposals = s->t + 1;
-    return make_record(s, -1, rec_out);
+    return make_record(s, -1, rec_out, commit_here);
 }
 
 // np.argmax over `n_records` proposals in device memory + append; with `extend` the streaming pass follows.
-int commit_dev(ital_shard* s, const double* recs_dev, int n_records, int extend) {
+int commit_dev(ital_shard* s, const double* recs_dev, int n_records, int extend, bool picked = false) {
     if (s->t >= kMaxBatch) return fail(ITAL_EINVAL, "batches of more than %d samples are not supported", kMaxBatch);
+    if (!picked) {
     k_pick_winner<<<1, 256, 0, s->stream>>>(recs_dev, n_records, record_doubles(s), s->t, s->W, s->rec_in_dev,
                                             s->base_m_dev, s->base_L_dev, s->sel_dev, s->rec_hist, s->mask,
                                             s->row_offset, s->n, kSelected); s->launches++;
     CU(cudaGetLastError());
+    }
     if (extend && !s->lazy_rows) {      // lazy rows: the projection is extended on demand by k_catchup instead
         const int col = s->W + s->t;
         int rc = s->x_dtype == ITAL_F32 ? launch_extend_t<float>(s, col, 0, 0.0, 0)
@@ -1102,8 +1138,9 @@ int ital_fetch(ital_shard* s, int k, double label_prob, double mistake_prob, int
     if (rc) return rc;
     // the whole greedy loop is enqueued without waiting for the GPU; one read-back at the end
     for (int it = 0; it < k && rc == ITAL_OK; ++it) {
-        rc = propose_dev(s, -std::numeric_limits<double>::infinity(), exhaustive, s->rec_dev);
-        if (rc == ITAL_OK) rc = commit_dev(s, s->rec_dev, 1, it + 1 < k);
+        // single shard: the record kernel commits the winner itself (no separate pick)
+        rc = propose_dev(s, -std::numeric_limits<double>::infinity(), exhaustive, s->rec_dev, true);
+        if (rc == ITAL_OK) rc = commit_dev(s, s->rec_dev, 1, it + 1 < k, true);
     }
     int got = 0;
     if (rc == ITAL_OK) {

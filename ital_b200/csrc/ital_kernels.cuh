@@ -41,6 +41,21 @@ struct Best {                            // result of an argmax reduction
     long long idx;                       // local row, -1 if none
 };
 
+constexpr int kBaseStride = 16;          // row stride of the batch's Cholesky factor in device memory
+
+struct CommitTargets {                   // where a single-shard step commits its winner (see k_pick_winner)
+    double* rec_in = nullptr;
+    double* rec_hist_t = nullptr;
+    double* base_m = nullptr;
+    double* base_L = nullptr;
+    double* sel = nullptr;
+    uint8_t* mask = nullptr;
+    long long n = 0;
+    int t = 0;
+    int mark_bits = 0;
+    int enabled = 0;
+};
+
 __device__ __forceinline__ bool better(double sa, long long ia, double sb, long long ib) {
     // NaN never wins; ties go to the lower index (np.argmax on the ascending candidate list, ital.py:98,130)
     if (ib < 0) return ia >= 0;
@@ -560,6 +575,151 @@ k_extend_bulk(const XT* __restrict__ X, int64_t n, int d, int d_pad, const doubl
                 m[i] = fma(e, beta, m[i]);
                 v[i] = fma(-e, e, v[i]);
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_extend_multi on the bulk-copy ring (2 KB rows): Q labelled points enter with one pass over the pool at the
+// speed of the single-column pass.  Slots hold TWO consecutive rows (one 4 KB bulk copy), so every shared-memory
+// read of a new point's coordinates serves two rows; the new points sit in shared memory as float64, laid out so
+// that the 32 lanes of a 16-byte read touch consecutive 16-byte words (no bank conflicts):
+//   z_s[((a * NC + c) * (VN / 2) + h) * 64 + lane * 2 + e]  =  z_a[(c * 32 + lane) * VN + 2 h + e].
+// The lane partials are transposed by the same shuffle tree as in k_extend_bulk (level 0 joins the two rows of a
+// slot).  8 warps per CTA, one CTA per SM; the ring keeps 8 warps x kMultiSlots x 4 KB in flight.
+constexpr int kMultiThreads = 256;
+constexpr int kMultiSlots = 4;
+
+template <typename XT, int NC, int Q>
+__global__ void __launch_bounds__(kMultiThreads, 1)
+k_extend_bulk_multi(const XT* __restrict__ X, int64_t n, int d_pad, const double* __restrict__ ext, int W,
+                    const double* __restrict__ sqn, double* __restrict__ U, int64_t ldu, double* __restrict__ m,
+                    double* __restrict__ v, double var, double neg2ls2) {
+    constexpr int VN = Vec<XT>::N;
+    constexpr int H = VN / 2;
+    extern __shared__ __align__(128) unsigned char bmm_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarp_blk = blockDim.x >> 5;
+    const uint32_t row_bytes = (uint32_t)d_pad * sizeof(XT);
+    const uint32_t slot_bytes = 2 * row_bytes;
+    // layout: [ring of every warp][z_s][ur][barriers]
+    unsigned char* ring = bmm_raw + (size_t)wib * kMultiSlots * slot_bytes;
+    double* z_s = (double*)(bmm_raw + (size_t)nwarp_blk * kMultiSlots * slot_bytes);
+    double* ur_s = z_s + (size_t)Q * d_pad;
+    uint64_t* bars = (uint64_t*)(ur_s + ((Q * W + 1) & ~1)) + wib * kMultiSlots;
+    const MultiExt* hdr = reinterpret_cast<const MultiExt*>(ext);
+    const double* z_g = ext + sizeof(MultiExt) / sizeof(double);
+    const double* ur_g = z_g + (size_t)Q * d_pad;
+    for (int j = threadIdx.x; j < Q * d_pad; j += blockDim.x) {
+        const int a = j / d_pad, col = j - a * d_pad;
+        const int e = col % VN, ln = (col / VN) & 31, c = col / (VN * 32);
+        z_s[((a * NC + c) * H + (e >> 1)) * 64 + ln * 2 + (e & 1)] = z_g[j];
+    }
+    for (int j = threadIdx.x; j < Q * W; j += blockDim.x) ur_s[j] = ur_g[j];
+    if (lane == 0) {
+        for (int k = 0; k < kMultiSlots; ++k)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + k)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int64_t n_units = (n + 31) >> 5;
+    const int64_t warp_global = (int64_t)blockIdx.x * nwarp_blk + wib;
+    const int64_t warps_total = (int64_t)gridDim.x * nwarp_blk;
+    const int64_t my_units = warp_global < n_units ? (n_units - 1 - warp_global) / warps_total + 1 : 0;
+    const int64_t total_sub = my_units * 16;            // 16 two-row slots per unit of 32 rows
+    auto issue = [&](int64_t sidx) {
+        const int64_t unit = warp_global + (sidx >> 4) * warps_total;
+        const int64_t row = (unit << 5) + (sidx & 15) * 2;
+        int64_t rows = n - row;
+        if (rows > 2) rows = 2;
+        const int slot = (int)(sidx % kMultiSlots);
+        if (rows > 0)
+            bulk_issue(ring + (size_t)slot * slot_bytes, X + row * (int64_t)d_pad, (uint32_t)rows * row_bytes, bars + slot);
+        else
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bars + slot)) : "memory");
+    };
+    if (lane == 0)
+        for (int64_t k = 0; k < kMultiSlots && k < total_sub; ++k) issue(k);
+    const double2* z2 = reinterpret_cast<const double2*>(z_s) + lane;
+    int64_t sidx = 0;
+    for (int64_t unit = warp_global; unit < n_units; unit += warps_total) {
+        const int64_t row0 = unit << 5;
+        double lv[Q][4];
+        double dot[Q];
+#pragma unroll
+        for (int a = 0; a < Q; ++a) dot[a] = 0.0;
+#pragma unroll
+        for (int sub = 0; sub < 16; ++sub, ++sidx) {
+            const int slot = (int)(sidx % kMultiSlots);
+            bar_wait(bars + slot, (uint32_t)((sidx / kMultiSlots) & 1));
+            const XT* xr0 = (const XT*)(ring + (size_t)slot * slot_bytes) + lane * VN;
+            const XT* xr1 = xr0 + d_pad;
+            double acc0[Q], acc1[Q];
+#pragma unroll
+            for (int a = 0; a < Q; ++a) { acc0[a] = 0.0; acc1[a] = 0.0; }
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                Vec<XT> x0, x1;
+                x0.lds(xr0 + c * 32 * VN);
+                x1.lds(xr1 + c * 32 * VN);
+                double xd0[VN], xd1[VN];
+#pragma unroll
+                for (int e = 0; e < VN; ++e) { xd0[e] = x0.get(e); xd1[e] = x1.get(e); }
+#pragma unroll
+                for (int a = 0; a < Q; ++a) {
+#pragma unroll
+                    for (int h = 0; h < H; ++h) {
+                        const double2 zz = z2[((a * NC + c) * H + h) * 32];
+                        acc0[a] = fma(xd0[2 * h], zz.x, acc0[a]);
+                        acc1[a] = fma(xd1[2 * h], zz.x, acc1[a]);
+                        acc0[a] = fma(xd0[2 * h + 1], zz.y, acc0[a]);
+                        acc1[a] = fma(xd1[2 * h + 1], zz.y, acc1[a]);
+                    }
+                }
+            }
+            const bool valid1 = row0 + 2 * sub + 1 < n;      // a slot may hold one row only at the end of the pool
+            const bool valid0 = row0 + 2 * sub < n;
+#pragma unroll
+            for (int a = 0; a < Q; ++a) {
+                double val = tree_combine(valid0 ? acc0[a] : 0.0, valid1 ? acc1[a] : 0.0, 1, lane);
+#pragma unroll
+                for (int k = 1; k < 5; ++k) {
+                    if (((sub >> (k - 1)) & 1) == 0) { lv[a][k - 1] = val; break; }
+                    val = tree_combine(lv[a][k - 1], val, 1 << k, lane);
+                    if (k == 4) dot[a] = val;
+                }
+            }
+            __syncwarp();                                   // every lane is done with the slot
+            if (lane == 0 && sidx + kMultiSlots < total_sub) issue(sidx + kMultiSlots);
+        }
+        const int64_t i = row0 + lane;
+        if (i < n) {
+            double proj[Q];
+#pragma unroll
+            for (int a = 0; a < Q; ++a) proj[a] = 0.0;
+            const double* u = U + i;
+            for (int j = 0; j < W; ++j) {
+                const double uj = u[(int64_t)j * ldu];
+#pragma unroll
+                for (int a = 0; a < Q; ++a) proj[a] = fma(uj, ur_s[a * W + j], proj[a]);
+            }
+            const double sq = sqn[i];
+            double e[Q];
+            double dm = 0.0, dv = 0.0;
+#pragma unroll
+            for (int a = 0; a < Q; ++a) {
+                double num = var * exp((sq + hdr->zn[a] - 2.0 * dot[a]) / neg2ls2) - proj[a];
+#pragma unroll
+                for (int b = 0; b < Q; ++b)
+                    if (b < a) num = fma(-e[b], hdr->tri[a * 4 + b], num);
+                e[a] = num / hdr->piv[a];
+                U[(int64_t)(W + a) * ldu + i] = e[a];
+                dm = fma(e[a], hdr->beta[a], dm);
+                dv = fma(e[a], e[a], dv);
+            }
+            m[i] += dm;
+            v[i] -= dv;
         }
     }
 }
@@ -1150,7 +1310,6 @@ __global__ void __launch_bounds__(256) k_eval_general(GeneralArgs a) {
 }
 
 // ---- shared quadrature nodes on the device (same rule as csrc/snq_host.h / oracle/orthant.py) ----------------
-constexpr int kBaseStride = 16;          // row stride of the batch's Cholesky factor in device memory
 constexpr int kGlStride = 64;            // Gauss-Legendre tables: rule n at [n * 64 .. n * 64 + n)
 
 // One thread per node; node index = sum_j digit_j (2q)^(t-1-j).  Every thread recomputes the boundary of each
@@ -1379,15 +1538,23 @@ __global__ void __launch_bounds__(256) k_record(long long row, const Best* __res
                                                 const double* __restrict__ gain, double* __restrict__ rec,
                                                 double shift_coef, const double* __restrict__ h_base,
                                                 const int* __restrict__ counters = nullptr,
-                                                int* __restrict__ counters_dst = nullptr) {
+                                                int* __restrict__ counters_dst = nullptr,
+                                                CommitTargets ct = CommitTargets()) {
     if (counters_dst != nullptr && threadIdx.x < 4) counters_dst[threadIdx.x] = counters[threadIdx.x];
     // shift_coef * (total mass): what a user who mislabels with probability mistake_prob adds to every score of
     // the step (DESIGN.md "mistake_prob"); 0 for the perfect user
     double score = 0.0;
     if (row < 0) { row = best->idx; score = best->score + shift_coef * h_base[1]; }
+    if (ct.enabled && score != score) row = -1;      // a NaN score never wins (k_pick_winner)
     const int rec_len = 8 + w_cap + d;
     if (row < 0) {
         for (int k = threadIdx.x; k < rec_len; k += blockDim.x) rec[k] = k == 0 ? -1.0 : (k == 1 ? -INFINITY : 0.0);
+        if (ct.enabled && threadIdx.x == 0) {
+            ct.rec_in[0] = -1.0;
+            ct.rec_in[1] = -INFINITY;
+            ct.sel[2 * ct.t] = -1.0;
+            ct.sel[2 * ct.t + 1] = -INFINITY;
+        }
         return;
     }
     for (int j = threadIdx.x; j < w_cap; j += blockDim.x) rec[8 + j] = j < W_tot ? U[(int64_t)j * ldu + row] : 0.0;
@@ -1403,6 +1570,21 @@ __global__ void __launch_bounds__(256) k_record(long long row, const Best* __res
         rec[5] = v[row];
         rec[6] = gain[row];
         rec[7] = 0.0;
+    }
+    if (ct.enabled) {       // single shard: this record is the step's winner -- commit it here (k_pick_winner, G = 1)
+        __syncthreads();
+        for (int k = threadIdx.x; k < rec_len; k += blockDim.x) {
+            ct.rec_in[k] = rec[k];
+            ct.rec_hist_t[k] = rec[k];
+        }
+        if (threadIdx.x == 0) {
+            if (row < ct.n) ct.mask[row] |= ct.mark_bits;
+            ct.base_m[ct.t] = rec[2];
+            for (int j = 0; j < ct.t; ++j) ct.base_L[ct.t * kBaseStride + j] = rec[8 + W_lab + j];
+            ct.base_L[ct.t * kBaseStride + ct.t] = sqrt(fmax(rec[3], 1e-300));
+            ct.sel[2 * ct.t] = rec[0];
+            ct.sel[2 * ct.t + 1] = rec[1];
+        }
     }
 }
 
