@@ -345,7 +345,8 @@ def main():
     if args.rounds > 0:
         c0 = head[0]
         barrier()
-        tf = tu = 0.0
+        tf = tu = tt_top = 0.0
+        upd_ms, upd_gbs, fetch_each = [], [], []
         for _ in range(args.rounds):
             w0 = time.perf_counter()
             batch = learner.fetch_unlabelled(args.batch)
@@ -359,14 +360,34 @@ def main():
                     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
                     ci = int(tt[0])
                 lab[i] = 1 if ci == c0 else -1
+            lib.ital_profile_enable(shard.handle, 1)
             learner.update(lab)
             torch.cuda.synchronize()
             w2 = time.perf_counter()
+            ums, unl, unb = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
+            lib.ital_profile_read(shard.handle, ctypes.byref(ums), ctypes.byref(unl), ctypes.byref(unb))
+            lib.ital_profile_enable(shard.handle, 0)
+            upd_ms.append(ums.value / max(1, unl.value))
+            upd_gbs.append(unb.value / 1e9 / (ums.value / 1e3) if ums.value > 0 else 0.0)
+            fetch_each.append((w1 - w0) * 1e3)
+            w3 = w2
             tf += w1 - w0
             tu += w2 - w1
+            tt_top += w3 - w2
+        learner.top_results(100)                      # first call allocates the sort buffers
+        tops = []
+        for _ in range(10):
+            w0 = time.perf_counter()
+            learner.top_results(100)
+            tops.append(time.perf_counter() - w0)
+        tt_top = float(np.median(tops)) * args.rounds
         rounds = {'rounds': args.rounds, 'fetch_ms': tf / args.rounds * 1e3, 'update_ms': tu / args.rounds * 1e3,
+                  'top_results_100_ms': tt_top / args.rounds * 1e3,
+                  'fetch_ms_each': fetch_each,
+                  'update_pass_ms': float(np.median(upd_ms)), 'update_pass_GBs': float(np.median(upd_gbs)),
                   'labelled_after': n_lab + args.rounds * args.batch,
-                  'note': 'wall clock; update(%d labels) = one multi-column streaming pass + host bookkeeping' % args.batch}
+                  'note': 'wall clock; update(%d labels) = one multi-column streaming pass + host bookkeeping; '
+                          'top_results(100) = device radix sort of the local means, 100 indices read back' % args.batch}
 
     if rank != 0:
         dist.destroy_process_group()

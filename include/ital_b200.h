@@ -131,6 +131,13 @@ int ital_last_scores(ital_shard* s, double* out_n_local);
 int ital_rel_mean(ital_shard* s, double* out_n_local);
 int ital_rel_var(ital_shard* s, double* out_n_local);
 
+/* ActiveRetrievalBase.top_results (ital/retrieval_base.py:64-75): np.argsort(rel_mean)[::-1][:k] over the local pool
+ * rows, sorted on the device (stable radix sort; exactly tied means keep ascending row order, which the reference's
+ * unstable argsort leaves undefined).  k < 0 = all local pool rows.  Writes global row indices (and, if out_val is
+ * not NULL, their means) in descending order of the mean and returns how many were written; a multi-shard learner
+ * merges the shards' lists on the host. */
+int64_t ital_top_results(ital_shard* s, int64_t k, int64_t* out_idx, double* out_val);
+
 /* GaussianProcess.predict (ital/gp.py:264-292): mean (and, if out_var != NULL, the 'diag' variance clamped at
  * 0) for m arbitrary rows of float64 features.  Uses the labelled rows held by this shard's model, so it is
  * valid on any shard (the labelled points are replicated). */

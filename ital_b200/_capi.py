@@ -48,6 +48,7 @@ SIGNATURES = {
     'ital_last_scores': (ctypes.c_int, [_shard_p, _c_double_p]),
     'ital_rel_mean': (ctypes.c_int, [_shard_p, _c_double_p]),
     'ital_rel_var': (ctypes.c_int, [_shard_p, _c_double_p]),
+    'ital_top_results': (ctypes.c_int64, [_shard_p, ctypes.c_int64, _c_int64_p, _c_double_p]),
     'ital_predict': (ctypes.c_int, [_shard_p, _c_double_p, ctypes.c_int64, _c_double_p, _c_double_p]),
     'ital_profile_enable': (ctypes.c_int, [_shard_p, ctypes.c_int]),
     'ital_profile_read': (ctypes.c_int, [_shard_p, _c_double_p, _c_int64_p, _c_double_p]),

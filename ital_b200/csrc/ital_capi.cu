@@ -7,9 +7,11 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/ital_b200.h"
@@ -88,6 +90,12 @@ struct ital_shard {
     uint8_t* ncol = nullptr;         // lazy rows: batch columns valid per row
     uint8_t* stamp = nullptr;        // greedy step in which the row was last scored (this fetch)
     double* rec_hist = nullptr;      // records of the points selected in the running fetch
+    uint64_t* sort_keys = nullptr;   // top_results: two key and two row buffers (ping-pong), tile histograms
+    uint32_t* sort_rows = nullptr;
+    uint32_t* sort_hist = nullptr;
+    int64_t* sort_out_idx = nullptr;
+    double* sort_out_val = nullptr;
+    int64_t sort_cap = 0;
     double* mext_dev = nullptr;      // block of the multi-column labelled extension (MultiExt + z + ur)
     double* mext_host = nullptr;     // pinned
     size_t mext_cap = 0;
@@ -273,7 +281,7 @@ int launch_extend_multi(ital_shard* s, int q, int W_used) {
     }
     constexpr int VN = Vec<XT>::N;
     const int bwarps = kMultiThreads / 32;
-    const size_t bsmem = (size_t)bwarps * kMultiSlots * 2 * s->d_pad * sizeof(XT) +
+    const size_t bsmem = (size_t)bwarps * kMultiSlots * kMultiRows * s->d_pad * sizeof(XT) +
                          ((size_t)q * s->d_pad + (size_t)((q * W_used + 1) & ~1)) * sizeof(double) +
                          (size_t)bwarps * kMultiSlots * sizeof(uint64_t);
     if (s->bulk_stream && s->d_pad * sizeof(XT) == 2048 && s->d_pad / (32 * VN) == 4 && bsmem <= 227 * 1024) {
@@ -641,7 +649,8 @@ void free_all(ital_shard* s) {
     void* ptrs[] = {s->X, s->sqn, s->m, s->v, s->U, s->gain, s->score, s->mask, s->worklist, s->counters,
                     s->block_best, s->best, s->thr_dev, s->rec_dev, s->rec_in_dev, s->idx_dev, s->eta_dev,
                     s->w_dev, s->masses_dev, s->group_dev, s->orth_dev, s->eta_raw, s->w_raw, s->orth_raw, s->gl_dev, s->phi_dev, s->base_m_dev, s->base_L_dev, s->sel_dev,
-                    s->hbase_dev, s->stats_dev, s->ncol, s->stamp, s->rec_hist, s->mext_dev, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev};
+                    s->hbase_dev, s->stats_dev, s->ncol, s->stamp, s->rec_hist, s->mext_dev, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev,
+                    s->sort_keys, s->sort_rows, s->sort_hist, s->sort_out_idx, s->sort_out_val};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->rec_host) cudaFreeHost(s->rec_host);
@@ -1196,6 +1205,49 @@ int ital_rel_mean(ital_shard* s, double* out) {
 int ital_rel_var(ital_shard* s, double* out) {
     if (!s || !out) return fail(ITAL_EINVAL, "bad arguments");
     return copy_vec(s, s->v, out);
+}
+
+int64_t ital_top_results(ital_shard* s, int64_t k, int64_t* out_idx, double* out_val) {
+    if (!s || !out_idx) return fail(ITAL_EINVAL, "ital_top_results: bad arguments");
+    if (s->W == 0) return fail(ITAL_ESTATE, "ital_top_results before any labelled point");
+    CU(cudaSetDevice(s->device));
+    // pool rows only: query rows (global index >= n_data) are the last local rows of the last shard
+    const int64_t np = std::max<int64_t>(0, std::min<int64_t>(s->n, s->n_data - s->row_offset));
+    if (k < 0 || k > np) k = np;
+    if (k == 0) return 0;
+    if (np >= ((int64_t)1 << 32)) return fail(ITAL_EINVAL, "ital_top_results: more than 2^32 rows in one shard");
+    const int tiles = (int)((np + kSortTile - 1) / kSortTile);
+    if (np > s->sort_cap) {
+        for (void** p : {(void**)&s->sort_keys, (void**)&s->sort_rows, (void**)&s->sort_hist, (void**)&s->sort_out_idx,
+                         (void**)&s->sort_out_val})
+            if (*p) { CU(cudaFree(*p)); *p = nullptr; }
+        s->sort_cap = 0;
+        CU(cudaMalloc(&s->sort_keys, 2 * (size_t)np * sizeof(uint64_t)));
+        CU(cudaMalloc(&s->sort_rows, 2 * (size_t)np * sizeof(uint32_t)));
+        CU(cudaMalloc(&s->sort_hist, ((size_t)256 * tiles + 256) * sizeof(uint32_t)));
+        CU(cudaMalloc(&s->sort_out_idx, (size_t)np * sizeof(int64_t)));
+        CU(cudaMalloc(&s->sort_out_val, (size_t)np * sizeof(double)));
+        s->sort_cap = np;
+    }
+    uint64_t* kb[2] = {s->sort_keys, s->sort_keys + np};
+    uint32_t* rb[2] = {s->sort_rows, s->sort_rows + np};
+    uint32_t* totals = s->sort_hist + (size_t)256 * tiles;
+    k_sort_init<<<grid_for(s, np, 256), 256, 0, s->stream>>>(s->m, np, kb[0], rb[0]); s->launches++;
+    for (int pass = 0; pass < 8; ++pass) {
+        const int a = pass & 1, b = a ^ 1;
+        k_sort_hist<<<tiles, kSortThreads, 0, s->stream>>>(kb[a], np, 8 * pass, s->sort_hist);
+        k_sort_scan<<<256, 256, 0, s->stream>>>(s->sort_hist, tiles, totals);
+        k_sort_scatter<<<tiles, kSortThreads, 0, s->stream>>>(kb[a], rb[a], np, 8 * pass, s->sort_hist, totals, kb[b], rb[b]);
+        s->launches += 3;
+    }
+    k_sort_gather<<<grid_for(s, k, 256), 256, 0, s->stream>>>(rb[0], k, s->row_offset, s->m, s->sort_out_idx,
+                                                             s->sort_out_val); s->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_idx, s->sort_out_idx, (size_t)k * sizeof(int64_t), cudaMemcpyDeviceToHost, s->stream));
+    if (out_val)
+        CU(cudaMemcpyAsync(out_val, s->sort_out_val, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return k;
 }
 
 int ital_predict(ital_shard* s, const double* Xt, int64_t mrows, double* out_mean, double* out_var) {

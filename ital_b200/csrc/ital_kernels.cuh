@@ -580,15 +580,26 @@ k_extend_bulk(const XT* __restrict__ X, int64_t n, int d, int d_pad, const doubl
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// k_extend_multi on the bulk-copy ring (2 KB rows): Q labelled points enter with one pass over the pool at the
-// speed of the single-column pass.  Slots hold TWO consecutive rows (one 4 KB bulk copy), so every shared-memory
-// read of a new point's coordinates serves two rows; the new points sit in shared memory as float64, laid out so
-// that the 32 lanes of a 16-byte read touch consecutive 16-byte words (no bank conflicts):
+// k_extend_multi on the bulk-copy ring (2 KB rows): Q labelled points enter with one pass over the pool at close to
+// the speed of the single-column pass.  Slots hold kMultiRows consecutive rows (one 8 KB bulk copy), so every
+// shared-memory read of a new point's coordinates serves four rows (shared-memory bandwidth, not HBM, limits a
+// two-row version); the new points sit in shared memory as float64, laid out so that the 32 lanes of a 16-byte
+// read touch consecutive 16-byte words (no bank conflicts):
 //   z_s[((a * NC + c) * (VN / 2) + h) * 64 + lane * 2 + e]  =  z_a[(c * 32 + lane) * VN + 2 h + e].
-// The lane partials are transposed by the same shuffle tree as in k_extend_bulk (level 0 joins the two rows of a
-// slot).  8 warps per CTA, one CTA per SM; the ring keeps 8 warps x kMultiSlots x 4 KB in flight.
-constexpr int kMultiThreads = 256;
-constexpr int kMultiSlots = 4;
+// The lane partials are transposed by the same shuffle tree as in k_extend_bulk.  8 warps per CTA, one CTA per SM;
+// the ring keeps 8 warps x kMultiSlots x 8 KB in flight.
+#ifndef ITAL_MULTI_THREADS
+#define ITAL_MULTI_THREADS 256
+#endif
+#ifndef ITAL_MULTI_SLOTS
+#define ITAL_MULTI_SLOTS 3
+#endif
+#ifndef ITAL_MULTI_ROWS
+#define ITAL_MULTI_ROWS 4
+#endif
+constexpr int kMultiThreads = ITAL_MULTI_THREADS;
+constexpr int kMultiSlots = ITAL_MULTI_SLOTS;
+constexpr int kMultiRows = ITAL_MULTI_ROWS;
 
 template <typename XT, int NC, int Q>
 __global__ void __launch_bounds__(kMultiThreads, 1)
@@ -597,10 +608,12 @@ k_extend_bulk_multi(const XT* __restrict__ X, int64_t n, int d_pad, const double
                     double* __restrict__ v, double var, double neg2ls2) {
     constexpr int VN = Vec<XT>::N;
     constexpr int H = VN / 2;
+    constexpr int R = kMultiRows;
+    constexpr int kSubs = 32 / R;
     extern __shared__ __align__(128) unsigned char bmm_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarp_blk = blockDim.x >> 5;
     const uint32_t row_bytes = (uint32_t)d_pad * sizeof(XT);
-    const uint32_t slot_bytes = 2 * row_bytes;
+    const uint32_t slot_bytes = R * row_bytes;
     // layout: [ring of every warp][z_s][ur][barriers]
     unsigned char* ring = bmm_raw + (size_t)wib * kMultiSlots * slot_bytes;
     double* z_s = (double*)(bmm_raw + (size_t)nwarp_blk * kMultiSlots * slot_bytes);
@@ -627,12 +640,12 @@ k_extend_bulk_multi(const XT* __restrict__ X, int64_t n, int d_pad, const double
     const int64_t warp_global = (int64_t)blockIdx.x * nwarp_blk + wib;
     const int64_t warps_total = (int64_t)gridDim.x * nwarp_blk;
     const int64_t my_units = warp_global < n_units ? (n_units - 1 - warp_global) / warps_total + 1 : 0;
-    const int64_t total_sub = my_units * 16;            // 16 two-row slots per unit of 32 rows
+    const int64_t total_sub = my_units * kSubs;
     auto issue = [&](int64_t sidx) {
-        const int64_t unit = warp_global + (sidx >> 4) * warps_total;
-        const int64_t row = (unit << 5) + (sidx & 15) * 2;
+        const int64_t unit = warp_global + (sidx / kSubs) * warps_total;
+        const int64_t row = (unit << 5) + (sidx % kSubs) * R;
         int64_t rows = n - row;
-        if (rows > 2) rows = 2;
+        if (rows > R) rows = R;
         const int slot = (int)(sidx % kMultiSlots);
         if (rows > 0)
             bulk_issue(ring + (size_t)slot * slot_bytes, X + row * (int64_t)d_pad, (uint32_t)rows * row_bytes, bars + slot);
@@ -645,64 +658,90 @@ k_extend_bulk_multi(const XT* __restrict__ X, int64_t n, int d_pad, const double
     int64_t sidx = 0;
     for (int64_t unit = warp_global; unit < n_units; unit += warps_total) {
         const int64_t row0 = unit << 5;
-        double lv[Q][4];
-        double dot[Q];
+        double lv[Q][5];
+        double dot[Q], proj[Q];
 #pragma unroll
-        for (int a = 0; a < Q; ++a) dot[a] = 0.0;
+        for (int a = 0; a < Q; ++a) { dot[a] = 0.0; proj[a] = 0.0; }
+        const int64_t i = row0 + lane;
+        const double* u = U + i;
 #pragma unroll
-        for (int sub = 0; sub < 16; ++sub, ++sidx) {
+        for (int sub = 0; sub < kSubs; ++sub, ++sidx) {
+            // the projection of this lane's row against the new points is folded into the main loop, four columns
+            // of U per slot: the loads are issued here and used after the slot's arithmetic, so their latency is
+            // covered (8 warps per SM cannot hide it in a separate epilogue)
+            double up[4];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const int col = sub * 4 + q4;
+                up[q4] = (i < n && col < W) ? u[(int64_t)col * ldu] : 0.0;
+            }
             const int slot = (int)(sidx % kMultiSlots);
             bar_wait(bars + slot, (uint32_t)((sidx / kMultiSlots) & 1));
-            const XT* xr0 = (const XT*)(ring + (size_t)slot * slot_bytes) + lane * VN;
-            const XT* xr1 = xr0 + d_pad;
-            double acc0[Q], acc1[Q];
+            const XT* xr = (const XT*)(ring + (size_t)slot * slot_bytes) + lane * VN;
+            double acc[R][Q];
 #pragma unroll
-            for (int a = 0; a < Q; ++a) { acc0[a] = 0.0; acc1[a] = 0.0; }
+            for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+                for (int a = 0; a < Q; ++a) acc[rr][a] = 0.0;
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
-                Vec<XT> x0, x1;
-                x0.lds(xr0 + c * 32 * VN);
-                x1.lds(xr1 + c * 32 * VN);
-                double xd0[VN], xd1[VN];
+                double xd[R][VN];
 #pragma unroll
-                for (int e = 0; e < VN; ++e) { xd0[e] = x0.get(e); xd1[e] = x1.get(e); }
+                for (int rr = 0; rr < R; ++rr) {
+                    Vec<XT> x;
+                    x.lds(xr + (size_t)rr * d_pad + c * 32 * VN);
+#pragma unroll
+                    for (int e = 0; e < VN; ++e) xd[rr][e] = x.get(e);
+                }
 #pragma unroll
                 for (int a = 0; a < Q; ++a) {
 #pragma unroll
                     for (int h = 0; h < H; ++h) {
                         const double2 zz = z2[((a * NC + c) * H + h) * 32];
-                        acc0[a] = fma(xd0[2 * h], zz.x, acc0[a]);
-                        acc1[a] = fma(xd1[2 * h], zz.x, acc1[a]);
-                        acc0[a] = fma(xd0[2 * h + 1], zz.y, acc0[a]);
-                        acc1[a] = fma(xd1[2 * h + 1], zz.y, acc1[a]);
+#pragma unroll
+                        for (int rr = 0; rr < R; ++rr) acc[rr][a] = fma(xd[rr][2 * h], zz.x, acc[rr][a]);
+#pragma unroll
+                        for (int rr = 0; rr < R; ++rr) acc[rr][a] = fma(xd[rr][2 * h + 1], zz.y, acc[rr][a]);
                     }
                 }
             }
-            const bool valid1 = row0 + 2 * sub + 1 < n;      // a slot may hold one row only at the end of the pool
-            const bool valid0 = row0 + 2 * sub < n;
 #pragma unroll
-            for (int a = 0; a < Q; ++a) {
-                double val = tree_combine(valid0 ? acc0[a] : 0.0, valid1 ? acc1[a] : 0.0, 1, lane);
+            for (int rr = 0; rr < R; ++rr) {
+                const int r = sub * R + rr;                     // compile-time after unrolling
+                const bool valid = row0 + r < n;                // a slot may be partly filled at the end of the pool
 #pragma unroll
-                for (int k = 1; k < 5; ++k) {
-                    if (((sub >> (k - 1)) & 1) == 0) { lv[a][k - 1] = val; break; }
-                    val = tree_combine(lv[a][k - 1], val, 1 << k, lane);
-                    if (k == 4) dot[a] = val;
+                for (int a = 0; a < Q; ++a) {
+                    double val = valid ? acc[rr][a] : 0.0;
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        if (((r >> k) & 1) == 0) { lv[a][k] = val; break; }
+                        val = tree_combine(lv[a][k], val, 1 << k, lane);
+                        if (k == 4) dot[a] = val;
+                    }
                 }
             }
             __syncwarp();                                   // every lane is done with the slot
             if (lane == 0 && sidx + kMultiSlots < total_sub) issue(sidx + kMultiSlots);
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const int col = sub * 4 + q4;
+                if (col < W) {
+#pragma unroll
+                    for (int a = 0; a < Q; ++a) proj[a] = fma(up[q4], ur_s[a * W + col], proj[a]);
+                }
+            }
         }
-        const int64_t i = row0 + lane;
         if (i < n) {
-            double proj[Q];
+            for (int j0 = 4 * kSubs; j0 < W; j0 += 8) {    // columns beyond the 32 covered above, eight loads in flight
+                double ub[8];
 #pragma unroll
-            for (int a = 0; a < Q; ++a) proj[a] = 0.0;
-            const double* u = U + i;
-            for (int j = 0; j < W; ++j) {
-                const double uj = u[(int64_t)j * ldu];
+                for (int q8 = 0; q8 < 8; ++q8) ub[q8] = j0 + q8 < W ? u[(int64_t)(j0 + q8) * ldu] : 0.0;
 #pragma unroll
-                for (int a = 0; a < Q; ++a) proj[a] = fma(uj, ur_s[a * W + j], proj[a]);
+                for (int q8 = 0; q8 < 8; ++q8)
+                    if (j0 + q8 < W) {
+#pragma unroll
+                        for (int a = 0; a < Q; ++a) proj[a] = fma(ub[q8], ur_s[a * W + j0 + q8], proj[a]);
+                    }
             }
             const double sq = sqn[i];
             double e[Q];
@@ -813,25 +852,41 @@ __global__ void __launch_bounds__(256) k_score0(int64_t n, const double* __restr
     // general model (label_prob < 1): scale = label_prob, log1p_eps = (1-mp) log(1+eps) + mp log(eps)
     double bs = 0.0;
     long long bi = -1;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        double s = nan("");
-        if (mask[i] == 0) {
-            const double var_i = fmax(v[i], 0.0);        // predict_stored(cov_mode='diag') clamps (gp.py:229)
-            const double sd = sqrt(var_i);
-            double p1, p0;
-            if (sd > 0.0) {
-                const double zz = m[i] / sd;
-                p1 = phi_tab(phi, zz);
-                p0 = phi_tab(phi, -zz);
-            } else {
-                p1 = m[i] > 0.0 ? 1.0 : 0.0;
-                p0 = 1.0 - p1;
-            }
-            s = scale * (mi_term(p0, log1p_eps) + mi_term(p1, log1p_eps));
-            gain[i] = s;
-            if (better(s, i, bs, bi)) { bs = s; bi = i; }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 2 * stride) {
+        // the loads of two rows are issued before the arithmetic of either
+        uint8_t mk[2];
+        double mm[2], vv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int64_t i = i0 + u * stride;
+            mk[u] = i < n ? __ldg(mask + i) : (uint8_t)1;
+            mm[u] = i < n ? __ldg(m + i) : 0.0;
+            vv[u] = i < n ? __ldg(v + i) : 0.0;
         }
-        score[i] = s;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i >= n) break;
+            double s = nan("");
+            if (mk[u] == 0) {
+                const double var_i = fmax(vv[u], 0.0);   // predict_stored(cov_mode='diag') clamps (gp.py:229)
+                const double sd = sqrt(var_i);
+                double p1, p0;
+                if (sd > 0.0) {
+                    const double zz = mm[u] / sd;
+                    p1 = phi_tab(phi, zz);
+                    p0 = phi_tab(phi, -zz);
+                } else {
+                    p1 = mm[u] > 0.0 ? 1.0 : 0.0;
+                    p0 = 1.0 - p1;
+                }
+                s = scale * (mi_term(p0, log1p_eps) + mi_term(p1, log1p_eps));
+                gain[i] = s;
+                if (better(s, i, bs, bi)) { bs = s; bi = i; }
+            }
+            score[i] = s;
+        }
     }
     // block reduction
     __shared__ double ss[32];
@@ -859,8 +914,23 @@ __global__ void __launch_bounds__(1024) k_argmax_rows(int64_t n, const double* _
                                                       int* __restrict__ count, int* __restrict__ list) {
     double bs = 0.0;
     long long bi = -1;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        if (mask[i] == 0 && better(values[i], i, bs, bi)) { bs = values[i]; bi = i; }
+    // four independent (mask, value) loads in flight per thread: the pass is latency-bound, not bandwidth-bound
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        uint8_t mk[4];
+        double val[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + u * stride;
+            mk[u] = i < n ? __ldg(mask + i) : (uint8_t)1;
+            val[u] = i < n ? __ldg(values + i) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (mk[u] == 0 && better(val[u], i, bs, bi)) { bs = val[u]; bi = i; }
+        }
+    }
     __shared__ double ss[32];
     __shared__ long long si[32];
     __shared__ int last_s;
@@ -969,7 +1039,9 @@ __global__ void __launch_bounds__(256) k_worklist(int64_t n, const uint8_t* __re
     for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n;
          i0 += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = i0 + lane;
-        const bool take = i < n && mask[i] == 0 && gain[i] >= thr;
+        const uint8_t mk = i < n ? __ldg(mask + i) : (uint8_t)1;      // both loads issued before either is used
+        const double gv = i < n ? __ldg(gain + i) : 0.0;
+        const bool take = mk == 0 && gv >= thr;
         const unsigned ballot = __ballot_sync(0xffffffffu, take);
         if (ballot != 0) {
             int base = 0;
@@ -1629,6 +1701,144 @@ __global__ void __launch_bounds__(128) k_predict(const double* __restrict__ Xt, 
             }
             out_var[row] = fmax(0.0, var - q);
         }
+    }
+}
+
+// ---- ActiveRetrievalBase.top_results (ital/retrieval_base.py:64-75): np.argsort(rel_mean)[::-1] on the device ----
+// Stable LSD radix sort of (key, row) pairs, 8 bits per pass, keys = posterior means mapped to unsigned integers
+// whose ascending order is the descending order of the means (exact ties keep ascending row order).  Per pass:
+// k_sort_hist (digit histogram of every tile), k_sort_scan (per digit: exclusive scan over the tiles + digit total),
+// k_sort_scatter (stable ranks inside a tile by warp match + per-warp counters).
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;                                   // keys per thread
+constexpr int kSortTile = kSortThreads * kSortItems;             // 4096 keys per block
+
+__device__ __forceinline__ uint64_t desc_key(double x) {
+    const uint64_t b = (uint64_t)__double_as_longlong(x);
+    const uint64_t asc = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+    return ~asc;
+}
+
+__global__ void __launch_bounds__(256) k_sort_init(const double* __restrict__ m, int64_t n, uint64_t* __restrict__ keys,
+                                                   uint32_t* __restrict__ rows) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        keys[i] = desc_key(m[i]);
+        rows[i] = (uint32_t)i;
+    }
+}
+
+// item (w, j, lane) of a tile: tile_base + w * (32 * kSortItems) + j * 32 + lane -- the order that defines stability
+__global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint64_t* __restrict__ keys, int64_t n, int shift,
+                                                            uint32_t* __restrict__ hist) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kSortTile;
+#pragma unroll 4
+    for (int j = 0; j < kSortItems; ++j) {
+        const int64_t i = base + (int64_t)j * kSortThreads + threadIdx.x;
+        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];
+}
+
+// One block per digit: exclusive scan of the digit's tile counts in place, digit total to totals[digit].
+__global__ void __launch_bounds__(256) k_sort_scan(uint32_t* __restrict__ hist, int tiles, uint32_t* __restrict__ totals) {
+    __shared__ uint32_t wsum[8];
+    uint32_t* h = hist + (size_t)blockIdx.x * tiles;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t carry = 0;
+    for (int base = 0; base < tiles; base += 256) {
+        const int i = base + threadIdx.x;
+        const uint32_t c = i < tiles ? h[i] : 0u;
+        uint32_t inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += up;
+        }
+        if (lane == 31) wsum[w] = inc;
+        __syncthreads();
+        uint32_t before = carry, all = 0;
+#pragma unroll
+        for (int ww = 0; ww < 8; ++ww) {
+            if (ww < w) before += wsum[ww];
+            all += wsum[ww];
+        }
+        if (i < tiles) h[i] = before + inc - c;
+        carry += all;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) totals[blockIdx.x] = carry;
+}
+
+__global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint64_t* __restrict__ keys_in,
+                                                               const uint32_t* __restrict__ rows_in, int64_t n,
+                                                               int shift, const uint32_t* __restrict__ offs,
+                                                               const uint32_t* __restrict__ totals,
+                                                               uint64_t* __restrict__ keys_out,
+                                                               uint32_t* __restrict__ rows_out) {
+    constexpr int kWarps = kSortThreads / 32;
+    __shared__ uint32_t cnt[kWarps][256];
+    __shared__ uint32_t dsum[kWarps];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int k = threadIdx.x; k < kWarps * 256; k += kSortThreads) (&cnt[0][0])[k] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kSortTile + (int64_t)w * 32 * kSortItems;
+    uint64_t key[kSortItems];
+    uint32_t rank[kSortItems];
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int j = 0; j < kSortItems; ++j) {
+        const int64_t i = base + j * 32 + lane;
+        const bool ok = i < n;
+        key[j] = ok ? keys_in[i] : ~0ull;
+        const uint32_t dgt = ok ? (uint32_t)((key[j] >> shift) & 255u) : 256u;       // 256: not an item
+        const uint32_t peers = __match_any_sync(0xffffffffu, dgt);
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (ok && lane == leader) { old = cnt[w][dgt]; cnt[w][dgt] = old + __popc(peers); }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[j] = old + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // thread = digit: exclusive scan over the warps of the tile, on top of the tile's global offset
+        // (keys with smaller digits anywhere + keys with this digit in earlier tiles)
+        const uint32_t tot = totals[threadIdx.x];
+        uint32_t inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += up;
+        }
+        if (lane == 31) dsum[w] = inc;
+        __syncthreads();
+        uint32_t run = inc - tot + offs[(size_t)threadIdx.x * gridDim.x + blockIdx.x];
+        for (int ww = 0; ww < w; ++ww) run += dsum[ww];
+#pragma unroll
+        for (int ww = 0; ww < kWarps; ++ww) { const uint32_t c = cnt[ww][threadIdx.x]; cnt[ww][threadIdx.x] = run; run += c; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kSortItems; ++j) {
+        const int64_t i = base + j * 32 + lane;
+        if (i < n) {
+            const uint32_t pos = cnt[w][(key[j] >> shift) & 255u] + rank[j];
+            keys_out[pos] = key[j];
+            rows_out[pos] = rows_in[i];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sort_gather(const uint32_t* __restrict__ rows, int64_t k, int64_t row_offset,
+                                                     const double* __restrict__ m, int64_t* __restrict__ out_idx,
+                                                     double* __restrict__ out_val) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < k; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = rows[i];
+        out_idx[i] = row_offset + (int64_t)r;
+        out_val[i] = m[r];
     }
 }
 

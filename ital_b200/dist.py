@@ -29,6 +29,21 @@ def pick_winner(records):
     return best
 
 
+def merge_top(comm, idx, val, width, want):
+    """Merge the shards' descending (row, mean) lists into the global top list: mean descending, ties by ascending
+    row (ActiveRetrievalBase.top_results, ital/retrieval_base.py:64-75).  `width` = longest local list any shard may
+    send, `want` = entries wanted (None = all)."""
+    pad = np.full((2, width), -1.0)
+    pad[0, :len(idx)] = idx
+    pad[1, :len(idx)] = val
+    allv = comm.gather_records(pad)
+    gi, gv = allv[:, 0, :].reshape(-1), allv[:, 1, :].reshape(-1)
+    keep = gi >= 0
+    gi, gv = gi[keep].astype(np.int64), gv[keep]
+    order = np.lexsort((gi, -gv))
+    return gi[order] if want is None else gi[order[:want]]
+
+
 class LocalComm(object):
     """Single process: collectives are identities."""
     rank, world_size = 0, 1

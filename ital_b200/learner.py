@@ -10,7 +10,7 @@ import ctypes
 import numpy as np
 
 from . import _capi
-from .dist import LocalComm, TorchComm, partition_rows, pick_winner
+from .dist import LocalComm, TorchComm, merge_top, partition_rows, pick_winner
 
 
 class _Shard(object):
@@ -124,6 +124,14 @@ class _Shard(object):
     def rel_var(self):
         return self._vec(self.lib.ital_rel_var)
 
+    def top_results(self, k):
+        cap = self.n_local if k is None or k < 0 else min(int(k), self.n_local)
+        idx = np.zeros(max(cap, 1), dtype=np.int64)
+        val = np.zeros(max(cap, 1))
+        got = _capi.check(self.lib.ital_top_results(self.handle, -1 if k is None else int(k), _capi.i64ptr(idx),
+                                                    _capi.dptr(val)))
+        return idx[:got], val[:got]
+
     def predict(self, X, want_var):
         X = _capi.as_f64(X)
         mean = np.zeros(len(X))
@@ -172,7 +180,9 @@ class _GPView(object):
     def predict_stored(self, ind=None, cov_mode=None):
         """GaussianProcess.predict_stored (ital/gp.py:203-232) for the pool rows; cov_mode None or 'diag'."""
         if cov_mode == 'full':
-            raise NotImplementedError("cov_mode='full' is not on the accelerated path")
+            if ind is None:
+                raise NotImplementedError("cov_mode='full' over all rows is the n-by-n matrix this path never forms")
+            return self._l._posterior_block(ind)
         mean = self._l._all_rows(self._l._shard.rel_mean())
         sel = slice(None) if ind is None else np.asarray(ind, dtype=np.int64)
         if cov_mode == 'diag':
@@ -318,14 +328,19 @@ class ITAL(object):
         return self._comm.gather_rows(local, self._offsets)
 
     def top_results(self, k=None):                                              # retrieval_base.py:64-75
-        """np.argsort(rel_mean)[::-1][:k]; for k far below n only the top slice is sorted (same result up to the
-        order of exactly tied scores, which the reference's unstable sort does not define either)."""
-        rel_mean = self.rel_mean
-        if k is None or k <= 0 or 4 * k >= len(rel_mean):
-            ind = np.argsort(rel_mean)[::-1]
-            return ind[:k] if k is not None else ind
-        top = np.argpartition(rel_mean, -k)[-k:]
-        return top[np.argsort(rel_mean[top])[::-1]]
+        """np.argsort(rel_mean)[::-1][:k], sorted on the GPU (ital_top_results): only the k indices come back to the
+        host.  Exactly tied means come in ascending row order (the reference's unstable sort leaves that open)."""
+        if len(self._labelled_idx) == 0:
+            raise RuntimeError('top_results() needs at least one query or labelled sample')
+        want = None if k is None else (max(0, self._n + int(k)) if k < 0 else min(int(k), self._n))   # ind[:k]
+        if want == 0:
+            return np.zeros(0, dtype=np.int64)
+        idx, val = self._shard.top_results(want)
+        if self._comm.world_size == 1:
+            return idx
+        # every shard contributes its own top list; merge by (mean desc, row asc)
+        widest = int(np.max(np.diff(self._offsets)))
+        return merge_top(self._comm, idx, val, widest if want is None else min(want, widest), want)
 
     def _seen_mask(self):
         seen = np.zeros(self._n, dtype=bool)
@@ -376,9 +391,46 @@ class ITAL(object):
             self._shard.mark_seen([int(i) for i in unnameable])
         self.unnameable_ids.update(unnameable)
 
+    def _posterior_block(self, rows):
+        """Posterior means and full covariance of a small set of rows from their point records (one k_record launch
+        per row): c_ij = k(x_i, x_j) - u_i . u_j with u the projections on the labelled set's Cholesky factor."""
+        rows = [int(i) for i in rows]
+        recs = []
+        for lo in range(0, len(rows), 64):
+            recs.append(self._comm.sum_records(self._shard.export_points(rows[lo:lo + 64])))
+        recs = np.concatenate(recs) if recs else np.zeros((0, self._shard.record_doubles()))
+        W = int(self._shard.lib.ital_width(self._shard.handle))
+        cap = int(self._shard.lib.ital_width_cap(self._shard.handle))
+        h = _capi.RECORD_HEADER
+        u, x = recs[:, h:h + W], recs[:, h + cap:h + cap + self._shard.d]
+        sq = recs[:, 4]
+        kxx = self.var * np.exp((sq[:, None] + sq[None, :] - 2.0 * (x @ x.T)) / (-2.0 * self.length_scale ** 2))
+        return recs[:, 2].copy(), kxx - u @ u.T
+
     def updated_prediction(self, feedback, test_ind, cov_mode='full'):          # retrieval_base.py:129-164
-        raise NotImplementedError('updated_prediction is folded into the GPU scoring kernels; the standalone '
-                                  'method is not part of the accelerated path')
+        """Prediction for `test_ind` after hypothetically adding `feedback` (gp.py:295-344), without changing the
+        model.  Meant for the handful of rows the reference calls it with (a batch and its candidates): the
+        posterior block of the rows involved is assembled from their point records and conditioned on the
+        annotated ones (mean' = m_T + C_TO (C_OO + noise I)^-1 (y - m_O), cov' = C_TT - C_TO (C_OO + noise I)^-1 C_OT),
+        which equals the reference's extended inverse (extend_inv, gp.py:40-87)."""
+        if cov_mode not in (None, 'diag', 'full'):
+            raise ValueError('cov_mode must be None, "diag" or "full"')
+        rel, irr, _ = self.partition_feedback(feedback)
+        test_ind = [int(i) for i in test_ind]
+        obs = sorted(rel) + sorted(irr)
+        y = np.concatenate((np.ones(len(rel)), -np.ones(len(irr))))
+        mean, cov = self._posterior_block(test_ind + obs)
+        T, O = slice(0, len(test_ind)), slice(len(test_ind), len(test_ind) + len(obs))
+        mean_t, cov_t = mean[T], cov[T, T]
+        if len(obs):
+            G = np.linalg.solve(cov[O, O] + self.noise * np.eye(len(obs)), cov[O, T])
+            mean_t = mean_t + G.T @ (y - mean[O])
+            cov_t = cov_t - cov[T, O] @ G
+        if cov_mode == 'full':
+            return mean_t, cov_t
+        if cov_mode == 'diag':
+            return mean_t, np.maximum(0, np.diag(cov_t))
+        return mean_t
 
     # ---- ITAL ------------------------------------------------------------------------------------------
     def _check_supported(self):

@@ -116,6 +116,26 @@ class OracleGP(object):
             return pred_mean, np.maximum(0, self.var - np.sum(k_test * np.dot(self.K_inv, k_test), axis=0))
         return pred_mean
 
+    def updated_prediction(self, ind, y, pred_ind, cov_mode=None):     # gp.py:295-344
+        """Prediction for rows `pred_ind` after hypothetically adding (ind, y); the model itself is unchanged.
+        The reference extends K^-1 by a Woodbury identity (extend_inv, gp.py:40-87); the same extended inverse is
+        formed here from the Schur complement of the new block."""
+        ind = [int(i) for i in ind]
+        pred_ind = [int(i) for i in pred_ind]
+        B = self.block(self.ind, ind)                                   # old x new
+        D = self.block(ind, ind) + self.noise * np.eye(len(ind))
+        KiB = np.dot(self.K_inv, B)
+        S_inv = np.linalg.inv(D - np.dot(B.T, KiB))
+        K_inv = np.vstack((np.hstack((self.K_inv + KiB @ S_inv @ KiB.T, -KiB @ S_inv)),
+                           np.hstack((-S_inv @ KiB.T, S_inv))))
+        k_test = self.block(self.ind + ind, pred_ind)
+        pred_mean = np.dot(np.dot(K_inv, np.concatenate((self.y, np.asarray(y, dtype=np.float64)))).T, k_test)
+        if cov_mode == 'full':
+            return pred_mean, self.block(pred_ind, pred_ind) - np.dot(k_test.T, np.dot(K_inv, k_test))
+        elif cov_mode == 'diag':
+            return pred_mean, np.maximum(0, self.var - np.sum(k_test * np.dot(K_inv, k_test), axis=0))
+        return pred_mean
+
     def predict_cov_parts(self, base_ind):
         """The three ingredients of predict_cov_batch (gp.py:250-256) for ind = all rows."""
         base_ind = [int(i) for i in base_ind]
@@ -246,6 +266,15 @@ class OracleITAL(object):
         self.unnameable_ids.update(unnameable)
 
     # ---- ital.py -------------------------------------------------------------------------------------
+    def updated_prediction(self, feedback, test_ind, cov_mode='full'):          # retrieval_base.py:129-164
+        rel, irr, _ = self.partition_feedback(feedback)
+        if len(rel) + len(irr) == 0:
+            return self.gp.predict_stored(test_ind, cov_mode=cov_mode)
+        rel.sort()
+        irr.sort()
+        return self.gp.updated_prediction(rel + irr, np.concatenate((np.ones(len(rel)), -np.ones(len(irr)))),
+                                          test_ind, cov_mode=cov_mode)
+
     def _perfect_user(self):
         return (self.label_prob >= 1) and (self.mistake_prob <= 0)            # ital.py:313
 

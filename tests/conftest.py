@@ -16,8 +16,29 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
 
 
-def golden_names():
+def _npz_names():
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
+
+
+def golden_names():
+    """Fetch goldens (every greedy step of a fetch_unlabelled of the reference)."""
+    return [n for n in _npz_names() if not n.startswith('updpred_')]
+
+
+def updpred_names():
+    """updated_prediction goldens (make_golden.py run_updated_prediction)."""
+    return [n for n in _npz_names() if n.startswith('updpred_')]
+
+
+def load_updpred(name):
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + '.npz'), allow_pickle=False))
+    g['updates'] = [dict(zip(g['upd%d_idx' % u].tolist(), g['upd%d_val' % u].tolist()))
+                    for u in range(int(g['n_updates']))]
+    g['probes'] = [dict(feedback=dict(zip(g['probe%d_fb_idx' % p].tolist(), g['probe%d_fb_val' % p].tolist())),
+                        test=g['probe%d_test' % p].tolist(), mean=g['probe%d_mean' % p], var=g['probe%d_var' % p],
+                        cov=g['probe%d_cov' % p]) for p in range(int(g['n_probes']))]
+    g['learner_kw'] = dict(length_scale=float(g['length_scale']), var=float(g['var']), noise=float(g['noise']))
+    return g
 
 
 def load_golden(name):

@@ -118,6 +118,33 @@ def run_case(name, X, updates, k, learner_kw, unnameable=(), queries=()):
           flush=True)
 
 
+def run_updated_prediction(name, X, updates, learner_kw, probes, queries=()):
+    """ActiveRetrievalBase.updated_prediction (retrieval_base.py:129-164 -> gp.py:295-344) of the unmodified
+    reference for a few (feedback, test_ind) probes, all three cov_modes."""
+    learner = ital.ITAL(X, queries=list(queries), parallelized=False, **learner_kw)
+    for fb in updates:
+        learner.update(fb)
+    out = dict(X=X, n_updates=len(updates), n_probes=len(probes),
+               queries=np.array(queries, dtype=np.float64).reshape(len(queries), X.shape[1]))
+    for key in ('length_scale', 'var', 'noise'):
+        out[key] = float(learner_kw.get(key, dict(length_scale=0.1, var=1.0, noise=1e-6)[key]))
+    for u, fb in enumerate(updates):
+        out['upd%d_idx' % u] = np.array(list(fb.keys()), dtype=np.int64)
+        out['upd%d_val' % u] = np.array(list(fb.values()), dtype=np.float64)
+    for p, (fb, test_ind) in enumerate(probes):
+        out['probe%d_fb_idx' % p] = np.array(list(fb.keys()), dtype=np.int64)
+        out['probe%d_fb_val' % p] = np.array(list(fb.values()), dtype=np.float64)
+        out['probe%d_test' % p] = np.array(test_ind, dtype=np.int64)
+        out['probe%d_mean' % p] = np.array(learner.updated_prediction(fb, test_ind, cov_mode=None))
+        m, v = learner.updated_prediction(fb, test_ind, cov_mode='diag')
+        out['probe%d_var' % p] = np.array(v)
+        m, c = learner.updated_prediction(fb, test_ind, cov_mode='full')
+        out['probe%d_cov' % p] = np.array(c)
+        assert np.allclose(m, out['probe%d_mean' % p])
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+    print('%-28s n=%d probes=%d' % (name, X.shape[0], len(probes)), flush=True)
+
+
 def labelled_rounds(y, positive, rng, rounds=2, per_round=4):
     """A query plus a few feedback rounds, like run_experiment.py:142-164 (simulated perfect feedback)."""
     pos = np.nonzero(y == positive)[0]
@@ -174,8 +201,31 @@ def cases():
                         dict(length_scale=1.0)), {}
 
 
+def updated_prediction_cases():
+    rng = np.random.default_rng(20181010)
+    Xt, yt = toy_data()
+    upd_t = labelled_rounds(yt, 1, rng, rounds=1)
+    seen = set(i for fb in upd_t for i in fb)
+    free = [i for i in range(len(Xt)) if i not in seen]
+    probes = [({free[0]: 1}, [free[0], free[1]]),
+              ({free[3]: -1, free[2]: 1, free[5]: 0}, [free[2], free[3], free[5], free[7]]),
+              ({free[4]: 0}, [free[4], free[6], free[8]]),                       # nothing annotated: predict_stored
+              ({free[10]: 1, free[9]: 1, free[12]: -1, free[11]: -1}, [free[9], free[10], free[11], free[12]])]
+    yield 'updpred_toy', (Xt, upd_t, dict(length_scale=0.1), probes), {}
+    Xs, assign = syn_pool(300, d=64, centres=10)
+    upd_s = [{0: 1}, {3: -1, 9: -1, 11: 1 if assign[11] == assign[0] else -1, 20: -1}]
+    probes = [({50: 1, 40: -1}, [40, 50, 60, 299]), ({100: -1}, [100]), ({7: 1, 8: 1, 12: -1}, [7, 8, 12, 13, 14])]
+    yield 'updpred_syn300', (Xs, upd_s, dict(length_scale=1.0), probes), dict(queries=[Xs[150] + 0.01])
+
+
 if __name__ == '__main__':
     want = set(sys.argv[1:])
+    for name, args, kw in updated_prediction_cases():
+        if want and name not in want:
+            continue
+        run_updated_prediction(name, *args, **kw)
+    if want and all(w.startswith('updpred') for w in want):
+        sys.exit(0)
     for name, args, kw in cases():
         if want and name not in want:
             continue

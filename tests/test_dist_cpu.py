@@ -6,7 +6,7 @@ import socket
 import numpy as np
 import pytest
 
-from ital_b200.dist import LocalComm, partition_rows, pick_winner
+from ital_b200.dist import LocalComm, merge_top, partition_rows, pick_winner
 
 
 def test_partition_rows_contiguous_and_balanced():
@@ -60,7 +60,13 @@ def _worker(rank, world, port, out):
         mine[1] = 0.25 if rank == 0 else 0.75
         allrec = comm.gather_records(mine)
         rows = comm.gather_rows(np.arange(lo, hi, dtype=np.float64), off)
-        out.put((rank, summed.tolist(), pick_winner(allrec), rows.tolist()))
+        # top_results: every shard sends its own descending list, everyone merges to the same global list
+        means = np.array([0.5, -1.0, 0.5, 2.0, 0.0, 2.0, -3.0, 0.25, 0.5, 1.0, -0.5])
+        loc = np.arange(lo, hi)
+        order = np.lexsort((loc, -means[lo:hi]))
+        top_all = merge_top(comm, loc[order], means[lo:hi][order], int(np.max(np.diff(off))), None)
+        top4 = merge_top(comm, loc[order][:4], means[lo:hi][order][:4], 4, 4)
+        out.put((rank, summed.tolist(), pick_winner(allrec), rows.tolist(), top_all.tolist(), top4.tolist()))
     finally:
         dist.destroy_process_group()
 
@@ -77,7 +83,10 @@ def test_record_exchange_over_gloo_world2():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, summed, win, rows in res:
+    means = np.array([0.5, -1.0, 0.5, 2.0, 0.0, 2.0, -3.0, 0.25, 0.5, 1.0, -0.5])
+    want = np.lexsort((np.arange(11), -means)).tolist()
+    for rank, summed, win, rows, top_all, top4 in res:
+        assert top_all == want and top4 == want[:4]
         assert summed[0] == (np.arange(9) + 300).tolist() and summed[1] == (np.arange(9) + 900).tolist()
         assert win == 1
         assert rows == list(range(11))

@@ -32,7 +32,7 @@ def _rounds(learner, y, rounds=3):
         ret = learner.fetch_unlabelled(4)
         out.append(ret)
         learner.update({i: int(y[i]) for i in ret})
-    return out, np.array(learner.rel_mean)
+    return out, np.array(learner.rel_mean), (learner.top_results(), learner.top_results(25))
 
 
 def _worker(rank, world, port, q, local_rows):
@@ -53,8 +53,8 @@ def _worker(rank, world, port, q, local_rows):
                            local_rows=(int(off[rank]), len(X)))
         else:
             learner = ITAL(X, length_scale=1.0, device=rank, process_group=True)
-        batches, rel_mean = _rounds(learner, y)
-        q.put((rank, batches, rel_mean))
+        batches, rel_mean, tops = _rounds(learner, y)
+        q.put((rank, batches, rel_mean, tops))
     finally:
         dist.destroy_process_group()
 
@@ -79,9 +79,12 @@ def test_two_gpus_match_one_gpu_and_oracle(local_rows):
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    one_batches, one_mean = _rounds(ITAL(X, length_scale=1.0, device=0), y)
-    ora_batches, ora_mean = _rounds(OracleITAL(X, length_scale=1.0), y)
-    for rank, batches, rel_mean in res:
+    one_batches, one_mean, one_tops = _rounds(ITAL(X, length_scale=1.0, device=0), y)
+    ora_batches, ora_mean, _ = _rounds(OracleITAL(X, length_scale=1.0), y)
+    for rank, batches, rel_mean, tops in res:
+        want = np.lexsort((np.arange(len(rel_mean)), -rel_mean))
+        assert np.array_equal(tops[0], want) and np.array_equal(tops[1], want[:25])
+        assert np.array_equal(one_tops[1], np.lexsort((np.arange(len(one_mean)), -one_mean))[:25])
         assert batches == one_batches == ora_batches
         np.testing.assert_allclose(rel_mean, one_mean, rtol=1e-9, atol=1e-12)
         np.testing.assert_allclose(rel_mean, ora_mean, rtol=1e-6, atol=1e-9)

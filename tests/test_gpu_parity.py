@@ -8,7 +8,7 @@ oracle (absolute floor 1e-9 for moments, 1e-12 = the reference's eps for scores)
 import numpy as np
 import pytest
 
-from conftest import drive, golden_names, load_golden
+from conftest import drive, golden_names, load_golden, load_updpred, updpred_names
 
 pytestmark = pytest.mark.gpu
 
@@ -294,3 +294,74 @@ def test_duplicate_rows_tie_to_lowest_index():
     a, b = gpu.fetch_unlabelled(4), ora.fetch_unlabelled(4)
     assert a == b
     assert not ({200, 250} & set(a)) or 17 in a
+
+
+@pytest.mark.parametrize('n', [1, 31, 4096, 4097, 70001])
+def test_top_results_sorted_on_the_device(n):
+    """retrieval_base.py:64-75: np.argsort(rel_mean)[::-1][:k]; ties (duplicate rows) in ascending row order;
+    tile boundaries of the radix sort (4096 keys per block); query rows are never returned."""
+    X, assign = _syn(n, 16, seed=n, centres=5)
+    if n > 40:
+        X[n // 2] = X[3]
+        X[n - 1] = X[3]                               # exact ties
+    queries = [X[0] + 0.01, X[n // 3] - 0.01]
+    gpu = _gpu_learner(X, queries=queries, length_scale=1.0)
+    if n > 2:
+        gpu.update({1: -1, 2: 1})
+    rm = np.array(gpu.rel_mean)
+    assert len(rm) == n
+    want = np.lexsort((np.arange(n), -rm))
+    assert np.array_equal(gpu.top_results(), want)
+    for k in (1, 7, n // 2, n, n + 5):
+        got = gpu.top_results(k)
+        assert got.dtype == np.int64 and np.array_equal(got, want[:k])
+    assert len(gpu.top_results(0)) == 0
+    assert np.all(np.diff(rm[gpu.top_results()]) <= 0)
+    assert np.array_equal(np.sort(rm)[::-1], rm[gpu.top_results()])       # same values as the reference's argsort
+
+
+@pytest.mark.parametrize('name', updpred_names())
+def test_updated_prediction_matches_reference(name):
+    """ActiveRetrievalBase.updated_prediction (retrieval_base.py:129-164, gp.py:295-344) against the outputs of the
+    unmodified reference: mean, 'diag' variance and 'full' covariance; the model itself must not change."""
+    g = load_updpred(name)
+    gpu = _gpu_learner(g['X'], queries=list(g['queries']), **g['learner_kw'])
+    for fb in g['updates']:
+        gpu.update(fb)
+    before = np.array(gpu.rel_mean)
+    for pr in g['probes']:
+        np.testing.assert_allclose(gpu.updated_prediction(pr['feedback'], pr['test'], cov_mode=None), pr['mean'],
+                                   rtol=1e-6, atol=1e-9)
+        m, v = gpu.updated_prediction(pr['feedback'], pr['test'], cov_mode='diag')
+        np.testing.assert_allclose(v, pr['var'], rtol=1e-6, atol=1e-9)
+        m, c = gpu.updated_prediction(pr['feedback'], pr['test'])
+        np.testing.assert_allclose(m, pr['mean'], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(c, pr['cov'], rtol=1e-6, atol=1e-9)
+    m, c = gpu.gp.predict_stored(g['probes'][0]['test'], cov_mode='full')
+    m2, c2 = gpu.updated_prediction({}, g['probes'][0]['test'])
+    assert np.array_equal(m, m2) and np.array_equal(c, c2)
+    assert np.array_equal(before, gpu.rel_mean)
+    with pytest.raises(RuntimeError, match='Cannot change feedback once given.'):
+        first = next(iter(g['updates'][0].items()))
+        gpu.updated_prediction({first[0]: -first[1]}, g['probes'][0]['test'])
+
+
+@pytest.mark.parametrize('n,d', [(2053, 512), (999, 400), (64, 512)])
+def test_multi_label_update_on_2kb_rows(n, d):
+    """GaussianProcess.update with 2, 3 and 4 samples at once (gp.py:164-200) on float32 rows of 2 KB, where the
+    pass runs on the bulk-copy ring with four-row slots (k_extend_bulk_multi); ragged tails (n not a multiple of 4)."""
+    from oracle.ital_oracle import OracleITAL
+    X, assign = _syn(n, d, seed=n + d, centres=9)
+    y = np.where(assign == assign[0], 1, -1)
+    gpu = _gpu_learner(X, length_scale=1.0, storage='float32')
+    ora = OracleITAL(X, length_scale=1.0)
+    nxt = 0
+    for q in (1, 2, 3, 4, 4, 3):
+        fb = {i: int(y[i]) for i in range(nxt, nxt + q)}
+        nxt += q
+        gpu.update(fb)
+        ora.update(fb)
+        np.testing.assert_allclose(gpu.rel_mean, ora.rel_mean, rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(gpu.gp.predict_stored(cov_mode='diag')[1],
+                                   ora.gp.predict_stored(cov_mode='diag')[1][:n], rtol=1e-6, atol=1e-9)
+    assert gpu.fetch_unlabelled(3) == ora.fetch_unlabelled(3)

@@ -8,7 +8,9 @@ General feedback models (mistake_prob > 0 or label_prob < 1): 1e-4 relative, see
 """
 import numpy as np
 
-from conftest import drive
+import pytest
+
+from conftest import drive, load_updpred, updpred_names
 from oracle.ital_oracle import OracleITAL
 
 
@@ -73,3 +75,20 @@ def test_perfect_user_shortcut_equals_general_formula():
     assert fast.fetch_unlabelled(3) == slow.fetch_unlabelled(3)
     for a, b in zip(fast.trace, slow.trace):
         np.testing.assert_allclose(a['scores'], b['scores'], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize('name', updpred_names())
+def test_oracle_updated_prediction_matches_reference(name):
+    """retrieval_base.py:129-164 / gp.py:295-344 (extend_inv) of the unmodified reference, all cov_modes."""
+    g = load_updpred(name)
+    ora = OracleITAL(g['X'], queries=list(g['queries']), **g['learner_kw'])
+    for fb in g['updates']:
+        ora.update(fb)
+    for pr in g['probes']:
+        np.testing.assert_allclose(ora.updated_prediction(pr['feedback'], pr['test'], cov_mode=None), pr['mean'],
+                                   rtol=1e-6, atol=1e-9)
+        m, v = ora.updated_prediction(pr['feedback'], pr['test'], cov_mode='diag')
+        np.testing.assert_allclose(v, pr['var'], rtol=1e-6, atol=1e-9)
+        m, c = ora.updated_prediction(pr['feedback'], pr['test'], cov_mode='full')
+        np.testing.assert_allclose(m, pr['mean'], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(c, pr['cov'], rtol=1e-6, atol=1e-9)
