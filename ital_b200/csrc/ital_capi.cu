@@ -12,6 +12,7 @@
 #include <limits>
 #include <string>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "../../include/ital_b200.h"
@@ -86,6 +87,7 @@ struct ital_shard {
     int* stats_host = nullptr;       // pinned
     int proposals = 0;               // propose calls in the running fetch
     bool lazy_rows = false;          // batch projections only for the rows that get scored (k_catchup)
+    bool pdl = true;                 // programmatic dependent launch between the kernels of a stream (ITAL_B200_PDL=0: off)
     bool bulk_stream = true;         // X stream staged by the bulk-copy engine (k_extend_bulk) where it applies
     uint8_t* ncol = nullptr;         // lazy rows: batch columns valid per row
     uint8_t* stamp = nullptr;        // greedy step in which the row was last scored (this fetch)
@@ -136,6 +138,38 @@ struct ital_shard {
 namespace {
 
 int64_t record_doubles(const ital_shard* s) { return ITAL_RECORD_HEADER + s->w_cap + s->d; }
+
+// Kernel launch with programmatic stream serialization (see pdl_enter in ital_kernels.cuh): the kernel may start
+// launching while its predecessor in the stream drains; it waits for the predecessor's completion itself.  All
+// arguments are given explicitly (default arguments do not exist behind a function pointer).
+template <typename... KArgs>
+struct PdlLaunch {
+    void (*kernel)(KArgs...);
+    dim3 grid, block;
+    size_t smem;
+    cudaStream_t stream;
+    bool programmatic;
+    template <typename... Args>
+    void operator()(Args&&... args) const {
+        static_assert(sizeof...(Args) == sizeof...(KArgs), "pass every kernel argument explicitly");
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = block;
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = programmatic ? 1 : 0;
+        cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);   // errors: cudaGetLastError
+    }
+};
+
+template <typename... KArgs>
+PdlLaunch<KArgs...> pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, const ital_shard* s) {
+    return PdlLaunch<KArgs...>{kernel, grid, block, smem, s->stream, s->pdl};
+}
 
 int grid_for(const ital_shard* s, int64_t work_items, int per_block, int max_waves = 8) {
     int64_t blocks = (work_items + per_block - 1) / per_block;
@@ -217,7 +251,7 @@ int launch_extend_t(ital_shard* s, int W_used, int labelled, double y, uint8_t m
 #define ITAL_LAUNCH_BULK(NCV)                                                                                     \
     do {                                                                                                          \
         CU(cudaFuncSetAttribute(k_extend_bulk<XT, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem)); \
-        k_extend_bulk<XT, NCV><<<bblocks, bthreads, bsmem, s->stream>>>(                                           \
+        pdl(k_extend_bulk<XT, NCV>, bblocks, bthreads, bsmem, s)(                                           \
             (const XT*)s->X, s->n, (int)s->d, (int)s->d_pad, s->rec_in_dev, s->w_cap, W_used, s->sqn, s->U,       \
             s->ldu, s->m, s->v, labelled, y, s->noise, s->var, neg2ls2);                                          \
     } while (0)
@@ -229,7 +263,7 @@ int launch_extend_t(ital_shard* s, int W_used, int labelled, double y, uint8_t m
 #define ITAL_LAUNCH_EXT(NCV)                                                                                   \
     do {                                                                                                       \
         CU(cudaFuncSetAttribute(k_extend<XT, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-        k_extend<XT, NCV><<<blocks, threads, smem, s->stream>>>(                                                \
+        pdl(k_extend<XT, NCV>, blocks, threads, smem, s)(                                                \
             (const XT*)s->X, s->n, (int)s->d, (int)s->d_pad, s->rec_in_dev, s->w_cap, W_used, s->sqn, s->U,     \
             s->ldu, s->m, s->v, labelled, y, s->noise, s->var, neg2ls2, s->mask, s->row_offset, mark_bits);     \
     } while (0)
@@ -290,7 +324,7 @@ int launch_extend_multi(ital_shard* s, int q, int W_used) {
 #define ITAL_LAUNCH_BMULTI(QV)                                                                                        \
     do {                                                                                                              \
         CU(cudaFuncSetAttribute(k_extend_bulk_multi<XT, 4, QV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem)); \
-        k_extend_bulk_multi<XT, 4, QV><<<bblocks, kMultiThreads, bsmem, s->stream>>>(                                  \
+        pdl(k_extend_bulk_multi<XT, 4, QV>, bblocks, kMultiThreads, bsmem, s)(                                  \
             (const XT*)s->X, s->n, (int)s->d_pad, s->mext_dev, W_used, s->sqn, s->U, s->ldu, s->m, s->v, s->var,      \
             neg2ls2);                                                                                                 \
     } while (0)
@@ -302,7 +336,7 @@ int launch_extend_multi(ital_shard* s, int q, int W_used) {
 #define ITAL_LAUNCH_MULTI(QV)                                                                                     \
     do {                                                                                                          \
         CU(cudaFuncSetAttribute(k_extend_multi<XT, QV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_extend_multi<XT, QV><<<blocks, threads, smem, s->stream>>>((const XT*)s->X, s->n, (int)s->d_pad,       \
+        pdl(k_extend_multi<XT, QV>, blocks, threads, smem, s)((const XT*)s->X, s->n, (int)s->d_pad,       \
                                                                       s->mext_dev, W_used, s->sqn, s->U, s->ldu,  \
                                                                       s->m, s->v, s->var, neg2ls2);               \
     } while (0)
@@ -347,12 +381,12 @@ int make_record(ital_shard* s, long long local_row, double* dst_dev, bool commit
         ct.enabled = 1;
     }
     if (s->x_dtype == ITAL_F32)
-        k_record<float><<<1, 256, 0, s->stream>>>(local_row, s->best, s->row_offset, (const float*)s->X, (int)s->d,
+        pdl(k_record<float>, 1, 256, 0, s)(local_row, s->best, s->row_offset, (const float*)s->X, (int)s->d,
                                                   (int)s->d_pad, s->sqn, s->m, s->v, s->U, s->ldu, s->W,
                                                   s->W + s->t, s->w_cap, s->gain, dst_dev, shift, s->hbase_dev,
                                                   s->counters, local_row < 0 ? s->stats_dev + 4 * s->t : nullptr, ct);
     else
-        k_record<double><<<1, 256, 0, s->stream>>>(local_row, s->best, s->row_offset, (const double*)s->X,
+        pdl(k_record<double>, 1, 256, 0, s)(local_row, s->best, s->row_offset, (const double*)s->X,
                                                    (int)s->d, (int)s->d_pad, s->sqn, s->m, s->v, s->U, s->ldu,
                                                    s->W, s->W + s->t, s->w_cap, s->gain, dst_dev, shift, s->hbase_dev,
                                                    s->counters, local_row < 0 ? s->stats_dev + 4 * s->t : nullptr, ct); s->launches++;
@@ -394,14 +428,14 @@ int prepare_nodes(ital_shard* s) {
         const int blocks = (int)((N + 255) / 256);
         const double* glx = s->gl_dev;
         const double* glw = s->gl_dev + (snq::kMaxOrder + 1) * 64;
-#define ITAL_GEN(TV) k_snq_generate<TV><<<blocks, 256, 0, s->stream>>>(q, snq::kR, snq::kQMin, s->base_m_dev, s->base_L_dev, \
+#define ITAL_GEN(TV) pdl(k_snq_generate<TV>, blocks, 256, 0, s)(q, snq::kR, snq::kQMin, s->base_m_dev, s->base_L_dev, \
                                                               glx, glw, N, s->eta_raw, s->w_raw, s->orth_raw)
         if (t == 1) ITAL_GEN(1);
         else if (t == 2) ITAL_GEN(2);
         else ITAL_GEN(3);
 #undef ITAL_GEN
         s->launches++;
-        k_snq_finalize<<<1, 1024, 0, s->stream>>>(t, N, snq::kWMin, s->eta_raw, s->w_raw, s->orth_raw, s->eta_dev, s->w_dev,
+        pdl(k_snq_finalize, 1, 1024, 0, s)(t, N, snq::kWMin, s->eta_raw, s->w_raw, s->orth_raw, s->eta_dev, s->w_dev,
                                                   s->orth_dev, s->log1p_eps, s->masses_dev, s->hbase_dev, s->counters + 3); s->launches++;
         CU(cudaGetLastError());
         return ITAL_OK;
@@ -436,11 +470,11 @@ int launch_catchup(ital_shard* s, int64_t items_hint) {
     const size_t smem = (size_t)warps * (32 + s->w_cap) * sizeof(double);
     const double neg2ls2 = -2.0 * (s->ls * s->ls);
     if (s->x_dtype == ITAL_F32)
-        k_catchup<float><<<blocks, threads, smem, s->stream>>>(s->counters, s->worklist, (const float*)s->X, (int)s->d,
+        pdl(k_catchup<float>, blocks, threads, smem, s)(s->counters, s->worklist, (const float*)s->X, (int)s->d,
                                                                (int)s->d_pad, s->rec_hist, record_doubles(s), s->w_cap,
                                                                s->W, s->t, s->sqn, s->U, s->ldu, s->ncol, s->var, neg2ls2);
     else
-        k_catchup<double><<<blocks, threads, smem, s->stream>>>(s->counters, s->worklist, (const double*)s->X, (int)s->d,
+        pdl(k_catchup<double>, blocks, threads, smem, s)(s->counters, s->worklist, (const double*)s->X, (int)s->d,
                                                                 (int)s->d_pad, s->rec_hist, record_doubles(s), s->w_cap,
                                                                 s->W, s->t, s->sqn, s->U, s->ldu, s->ncol, s->var, neg2ls2);
     s->launches++;
@@ -481,10 +515,10 @@ int launch_eval(ital_shard* s, int64_t items_hint, bool block_per_candidate) {
     a.n_scored = s->counters + 2;
     a.force_block = block_per_candidate ? 1 : 0;
     a.t = s->t;
-    if (s->t == 1) k_eval<1><<<blocks, threads, 0, s->stream>>>(a);
-    else if (s->t == 2) k_eval<2><<<blocks, threads, 0, s->stream>>>(a);
-    else if (s->t == 3) k_eval<3><<<blocks, threads, 0, s->stream>>>(a);
-    else k_eval_sorted<<<blocks, threads, 0, s->stream>>>(a);
+    if (s->t == 1) pdl(k_eval<1>, blocks, threads, 0, s)(a);
+    else if (s->t == 2) pdl(k_eval<2>, blocks, threads, 0, s)(a);
+    else if (s->t == 3) pdl(k_eval<3>, blocks, threads, 0, s)(a);
+    else pdl(k_eval_sorted, blocks, threads, 0, s)(a);
     s->launches++;
     CU(cudaGetLastError());
     return ITAL_OK;
@@ -528,7 +562,7 @@ int propose_general(ital_shard* s) {
     CU(cudaMemcpyAsync(s->g_lut, gs.lut.data(), gs.lut.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
     CU(cudaStreamSynchronize(s->stream));       // gs lives in pageable host memory
     s->n_nodes = gs.n_nodes;
-    k_worklist<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->n, s->mask, s->gain, s->thr_dev, 1, s->counters, s->worklist); s->launches++;
+    pdl(k_worklist, grid_for(s, s->n, 256), 256, 0, s)(s->n, s->mask, s->gain, s->thr_dev, 1, s->counters, s->worklist); s->launches++;
     GeneralArgs a;
     a.count = s->counters;
     a.list = s->worklist;
@@ -559,10 +593,10 @@ int propose_general(ital_shard* s) {
     const size_t smem = ((size_t)3 * gs.n_groups + 2 * gs.n_sets + (size_t)gs.n_groups * 24 + 8) * sizeof(double);
     CU(cudaFuncSetAttribute(k_eval_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int blocks = grid_for(s, s->n, 1, 8);
-    k_eval_general<<<blocks, 256, smem, s->stream>>>(a); s->launches++;
+    pdl(k_eval_general, blocks, 256, smem, s)(a); s->launches++;
     const int lb = std::min(kArgmaxBlocks, grid_for(s, s->n, 256));
-    k_argmax_list<<<lb, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->block_best); s->launches++;
-    k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, lb, s->best); s->launches++;
+    pdl(k_argmax_list, lb, 256, 0, s)(s->counters, s->worklist, s->score, s->block_best, nullptr, 0.0, 0.0, nullptr, nullptr); s->launches++;
+    pdl(k_argmax_final, 1, 256, 0, s)(s->block_best, lb, s->best); s->launches++;
     CU(cudaGetLastError());
     return ITAL_OK;
 }
@@ -572,13 +606,14 @@ int propose_general(ital_shard* s) {
 int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_out, bool commit_here = false) {
     if (s->t >= kMaxBatch) return fail(ITAL_EINVAL, "batches of more than %d samples are not supported", kMaxBatch);
     const int blocks = std::min(kArgmaxBlocks, grid_for(s, s->n, 256));
-    CU(cudaMemsetAsync(s->counters, 0, 4 * sizeof(int), s->stream));
+    // counters [0..2] are zero here: k_record re-arms them at the end of every step, ital_fetch_begin before the first
+    if (s->t == 0) CU(cudaMemsetAsync(s->counters, 0, 4 * sizeof(int), s->stream));
     if (s->t == 0) {
         const bool general = s->label_prob < 1.0;
         const double lc = general ? (1.0 - s->mistake_prob) * s->log1p_eps + s->mistake_prob * std::log(1e-12) : s->log1p_eps;
-        k_score0<<<blocks, 256, 0, s->stream>>>(s->n, s->m, s->v, s->mask, s->score, s->gain, s->block_best, lc,
+        pdl(k_score0, blocks, 256, 0, s)(s->n, s->m, s->v, s->mask, s->score, s->gain, s->block_best, lc,
                                                 general ? s->label_prob : 1.0, s->phi_dev); s->launches++;
-        k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, blocks, s->best); s->launches++;
+        pdl(k_argmax_final, 1, 256, 0, s)(s->block_best, blocks, s->best); s->launches++;
         CU(cudaGetLastError());
         s->n_nodes = 1;
     } else if (s->label_prob < 1.0) {
@@ -588,35 +623,35 @@ int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_o
         int rc = prepare_nodes(s);
         if (rc) return rc;
         if (exhaustive) {
-            k_worklist<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->n, s->mask, s->gain, s->thr_dev, 1,
+            pdl(k_worklist, grid_for(s, s->n, 256), 256, 0, s)(s->n, s->mask, s->gain, s->thr_dev, 1,
                                                                         s->counters, s->worklist); s->launches++;
             CU(cudaGetLastError());
             rc = launch_eval(s, s->n, false);
             if (rc) return rc;
             const int lb = std::min(kArgmaxBlocks, grid_for(s, s->n, 256));
-            k_argmax_list<<<lb, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->block_best); s->launches++;
-            k_argmax_final<<<1, 256, 0, s->stream>>>(s->block_best, lb, s->best); s->launches++;
+            pdl(k_argmax_list, lb, 256, 0, s)(s->counters, s->worklist, s->score, s->block_best, nullptr, 0.0, 0.0, nullptr, nullptr); s->launches++;
+            pdl(k_argmax_final, 1, 256, 0, s)(s->block_best, lb, s->best); s->launches++;
         } else {
             // stage A: a spread sample of the most promising rows -- the maximum of the bound within each of
             // 2 x #SM strided subsets of the pool -- is scored first, one block per row.  (Taking the global
             // top rows by bound instead is worse: they cluster around the previous pick, whose neighbours have
             // just lost their gain; measured 882 vs 399 rows left for stage B at t = 3 on SYN-1M.)
             const int ba = std::min(kArgmaxBlocks, std::min(blocks, 2 * s->num_sms));
-            k_argmax_rows<<<ba, 512, 0, s->stream>>>(s->n, s->gain, s->mask, s->block_best, s->counters + 4, s->counters,
+            pdl(k_argmax_rows, ba, 512, 0, s)(s->n, s->gain, s->mask, s->block_best, s->counters + 4, s->counters,
                                                       s->worklist); s->launches++;
             CU(cudaGetLastError());
             rc = launch_eval(s, ba, true);
             if (rc) return rc;
             // best of stage A and, in the same kernel, the threshold of stage B: every row whose bound still
             // reaches the best exact score found so far
-            k_argmax_list<<<1, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->best + 1, s->hbase_dev,
+            pdl(k_argmax_list, 1, 256, 0, s)(s->counters, s->worklist, s->score, s->best + 1, s->hbase_dev,
                                                     floor_score, kPruneMargin, s->thr_dev, s->counters); s->launches++;
-            k_worklist<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->n, s->mask, s->gain, s->thr_dev, 0,
+            pdl(k_worklist, grid_for(s, s->n, 256), 256, 0, s)(s->n, s->mask, s->gain, s->thr_dev, 0,
                                                                         s->counters, s->worklist); s->launches++;
             CU(cudaGetLastError());
             rc = launch_eval(s, (int64_t)s->num_sms * 24, false);    // 3 resident blocks per SM (80 registers)
             if (rc) return rc;
-            k_argmax_list<<<1, 256, 0, s->stream>>>(s->counters, s->worklist, s->score, s->best); s->launches++;
+            pdl(k_argmax_list, 1, 256, 0, s)(s->counters, s->worklist, s->score, s->best, nullptr, 0.0, 0.0, nullptr, nullptr); s->launches++;
         }
         CU(cudaGetLastError());
     }
@@ -629,7 +664,7 @@ int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_o
 int commit_dev(ital_shard* s, const double* recs_dev, int n_records, int extend, bool picked = false) {
     if (s->t >= kMaxBatch) return fail(ITAL_EINVAL, "batches of more than %d samples are not supported", kMaxBatch);
     if (!picked) {
-    k_pick_winner<<<1, 256, 0, s->stream>>>(recs_dev, n_records, record_doubles(s), s->t, s->W, s->rec_in_dev,
+    pdl(k_pick_winner, 1, 256, 0, s)(recs_dev, n_records, record_doubles(s), s->t, s->W, s->rec_in_dev,
                                             s->base_m_dev, s->base_L_dev, s->sel_dev, s->rec_hist, s->mask,
                                             s->row_offset, s->n, kSelected); s->launches++;
     CU(cudaGetLastError());
@@ -672,8 +707,8 @@ int reset_model(ital_shard* s) {
     s->lab_idx.clear();
     s->lab_dev_valid = false;
     const int blocks = grid_for(s, s->n, 256);
-    k_fill<<<blocks, 256, 0, s->stream>>>(s->m, s->n, 0.0); s->launches++;
-    k_fill<<<blocks, 256, 0, s->stream>>>(s->v, s->n, s->var); s->launches++;
+    pdl(k_fill, blocks, 256, 0, s)(s->m, s->n, 0.0); s->launches++;
+    pdl(k_fill, blocks, 256, 0, s)(s->v, s->n, s->var); s->launches++;
     CU(cudaGetLastError());
     // candidates are the pool rows only (queries sit behind them, retrieval_base.py:40,84)
     std::vector<uint8_t> mk((size_t)s->n, 0);
@@ -713,6 +748,7 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
     s->d_pad = (d + row_elems - 1) / row_elems * row_elems;
     s->row_offset = row_offset;
     s->n_data = n_data;
+    if (const char* env = std::getenv("ITAL_B200_PDL")) s->pdl = env[0] != '0';    // (A/B comparisons)
     s->ldu = (n_local + 31) / 32 * 32;
     s->ls = length_scale;
     s->var = var;
@@ -779,9 +815,9 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
         if (r) return r;
         const int blocks = grid_for(s, s->n, 8);
         if (x_dtype == ITAL_F32)
-            k_sqnorm<float><<<blocks, 256, 0, s->stream>>>((const float*)s->X, s->n, (int)s->d_pad, s->sqn);
+            pdl(k_sqnorm<float>, blocks, 256, 0, s)((const float*)s->X, s->n, (int)s->d_pad, s->sqn);
         else
-            k_sqnorm<double><<<blocks, 256, 0, s->stream>>>((const double*)s->X, s->n, (int)s->d_pad, s->sqn); s->launches++;
+            pdl(k_sqnorm<double>, blocks, 256, 0, s)((const double*)s->X, s->n, (int)s->d_pad, s->sqn); s->launches++;
         CU(cudaGetLastError());
         return reset_model(s);
     };
@@ -983,7 +1019,7 @@ int ital_mark_seen(ital_shard* s, int64_t m, const int64_t* global_idx) {
     int rc = ensure_idx(s, (int64_t)loc.size());
     if (rc) return rc;
     CU(cudaMemcpyAsync(s->idx_dev, loc.data(), loc.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream));
-    k_mask_rows<<<grid_for(s, (int64_t)loc.size(), 256), 256, 0, s->stream>>>(s->mask, s->idx_dev, (int64_t)loc.size(), kSeen); s->launches++;
+    pdl(k_mask_rows, grid_for(s, (int64_t)loc.size(), 256), 256, 0, s)(s->mask, s->idx_dev, (int64_t)loc.size(), kSeen); s->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s->stream));
     return ITAL_OK;
@@ -994,12 +1030,12 @@ int ital_restrict_candidates(ital_shard* s, int64_t m, const int64_t* global_idx
     CU(cudaSetDevice(s->device));
     const int blocks = grid_for(s, s->n, 256);
     if (m < 0) {
-        k_mask_all<<<blocks, 256, 0, s->stream>>>(s->mask, s->n, (uint8_t)~kRestricted, 0); s->launches++;
+        pdl(k_mask_all, blocks, 256, 0, s)(s->mask, s->n, (uint8_t)~kRestricted, 0); s->launches++;
         CU(cudaGetLastError());
         return ITAL_OK;
     }
     // everything restricted, then the listed rows released
-    k_mask_all<<<blocks, 256, 0, s->stream>>>(s->mask, s->n, 0xff, kRestricted); s->launches++;
+    pdl(k_mask_all, blocks, 256, 0, s)(s->mask, s->n, 0xff, kRestricted); s->launches++;
     CU(cudaGetLastError());
     std::vector<int64_t> loc;
     for (int64_t k = 0; k < m; ++k) {
@@ -1010,7 +1046,7 @@ int ital_restrict_candidates(ital_shard* s, int64_t m, const int64_t* global_idx
         int rc = ensure_idx(s, (int64_t)loc.size());
         if (rc) return rc;
         CU(cudaMemcpyAsync(s->idx_dev, loc.data(), loc.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream));
-        k_mask_clear_rows<<<grid_for(s, (int64_t)loc.size(), 256), 256, 0, s->stream>>>(s->mask, s->idx_dev,
+        pdl(k_mask_clear_rows, grid_for(s, (int64_t)loc.size(), 256), 256, 0, s)(s->mask, s->idx_dev,
                                                                                        (int64_t)loc.size(), kRestricted); s->launches++;
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(s->stream));
@@ -1131,7 +1167,7 @@ int ital_fetch_end(ital_shard* s) {
     if (!s) return fail(ITAL_EINVAL, "null shard");
     CU(cudaSetDevice(s->device));
     if (s->fetching) {
-        k_mask_all<<<grid_for(s, s->n, 256), 256, 0, s->stream>>>(s->mask, s->n, (uint8_t)~kSelected, 0); s->launches++;
+        pdl(k_mask_all, grid_for(s, s->n, 256), 256, 0, s)(s->mask, s->n, (uint8_t)~kSelected, 0); s->launches++;
         CU(cudaGetLastError());
     }
     s->fetching = false;
@@ -1232,15 +1268,15 @@ int64_t ital_top_results(ital_shard* s, int64_t k, int64_t* out_idx, double* out
     uint64_t* kb[2] = {s->sort_keys, s->sort_keys + np};
     uint32_t* rb[2] = {s->sort_rows, s->sort_rows + np};
     uint32_t* totals = s->sort_hist + (size_t)256 * tiles;
-    k_sort_init<<<grid_for(s, np, 256), 256, 0, s->stream>>>(s->m, np, kb[0], rb[0]); s->launches++;
+    pdl(k_sort_init, grid_for(s, np, 256), 256, 0, s)(s->m, np, kb[0], rb[0]); s->launches++;
     for (int pass = 0; pass < 8; ++pass) {
         const int a = pass & 1, b = a ^ 1;
-        k_sort_hist<<<tiles, kSortThreads, 0, s->stream>>>(kb[a], np, 8 * pass, s->sort_hist);
-        k_sort_scan<<<256, 256, 0, s->stream>>>(s->sort_hist, tiles, totals);
-        k_sort_scatter<<<tiles, kSortThreads, 0, s->stream>>>(kb[a], rb[a], np, 8 * pass, s->sort_hist, totals, kb[b], rb[b]);
+        pdl(k_sort_hist, tiles, kSortThreads, 0, s)(kb[a], np, 8 * pass, s->sort_hist);
+        pdl(k_sort_scan, 256, 256, 0, s)(s->sort_hist, tiles, totals);
+        pdl(k_sort_scatter, tiles, kSortThreads, 0, s)(kb[a], rb[a], np, 8 * pass, s->sort_hist, totals, kb[b], rb[b]);
         s->launches += 3;
     }
-    k_sort_gather<<<grid_for(s, k, 256), 256, 0, s->stream>>>(rb[0], k, s->row_offset, s->m, s->sort_out_idx,
+    pdl(k_sort_gather, grid_for(s, k, 256), 256, 0, s)(rb[0], k, s->row_offset, s->m, s->sort_out_idx,
                                                              s->sort_out_val); s->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out_idx, s->sort_out_idx, (size_t)k * sizeof(int64_t), cudaMemcpyDeviceToHost, s->stream));
@@ -1290,7 +1326,7 @@ int ital_predict(ital_shard* s, const double* Xt, int64_t mrows, double* out_mea
     CU(cudaMemcpyAsync(xt_dev, Xt, (size_t)mrows * s->d * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     const int threads = 128, wpb = threads / 32;
     const size_t smem = (size_t)wpb * nl * sizeof(double);
-    k_predict<<<(unsigned)((mrows + wpb - 1) / wpb), threads, smem, s->stream>>>(
+    pdl(k_predict, (unsigned)((mrows + wpb - 1) / wpb), threads, smem, s)(
         xt_dev, mrows, (int)s->d, s->lab_x_dev, s->lab_sqn_dev, nl, s->w_vec_dev, s->LK_dev, s->var,
         -2.0 * s->ls * s->ls, mean_dev, var_dev); s->launches++;
     CU(cudaGetLastError());

@@ -56,6 +56,15 @@ struct CommitTargets {                   // where a single-shard step commits it
     int enabled = 0;
 };
 
+// Programmatic dependent launch: every kernel lets its successor in the stream start launching at once and then
+// waits until its predecessor has completed and flushed (griddepcontrol.wait is a no-op for a launch without the
+// programmatic-serialization attribute).  The stream order of all memory effects is unchanged; what is saved is the
+// launch latency between the ~30 small dependent kernels of a fetch.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ bool better(double sa, long long ia, double sb, long long ib) {
     // NaN never wins; ties go to the lower index (np.argmax on the ascending candidate list, ital.py:98,130)
     if (ib < 0) return ia >= 0;
@@ -147,6 +156,7 @@ template <> struct Vec<double> {
 template <typename XT>
 __global__ void __launch_bounds__(256) k_sqnorm(const XT* __restrict__ X, int64_t n, int d_pad,
                                                 double* __restrict__ sqn) {
+    pdl_enter();
     constexpr int VN = Vec<XT>::N;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -179,6 +189,7 @@ k_extend(const XT* __restrict__ X, int64_t n, int d, int d_pad, const double* __
          const double* __restrict__ sqn, double* __restrict__ U, int64_t ldu,
          double* __restrict__ m, double* __restrict__ v, int labelled, double y, double noise, double var,
          double neg2ls2, uint8_t* __restrict__ mask, int64_t row_offset, uint8_t mark_bits) {
+    pdl_enter();
     constexpr int VN = Vec<XT>::N;
     constexpr int RB = ITAL_EXTEND_RB;                  // rows in flight per warp
     extern __shared__ double smem[];
@@ -319,6 +330,7 @@ __global__ void __launch_bounds__(256, 2)
 k_extend_multi(const XT* __restrict__ X, int64_t n, int d_pad, const double* __restrict__ ext, int W,
                const double* __restrict__ sqn, double* __restrict__ U, int64_t ldu, double* __restrict__ m,
                double* __restrict__ v, double var, double neg2ls2) {
+    pdl_enter();
     constexpr int VN = Vec<XT>::N;
     extern __shared__ double msm[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarp_blk = blockDim.x >> 5;
@@ -463,6 +475,7 @@ k_extend_bulk(const XT* __restrict__ X, int64_t n, int d, int d_pad, const doubl
               const double* __restrict__ sqn, double* __restrict__ U, int64_t ldu,
               double* __restrict__ m, double* __restrict__ v, int labelled, double y, double noise, double var,
               double neg2ls2) {
+    pdl_enter();
     constexpr int VN = Vec<XT>::N;
     extern __shared__ __align__(128) unsigned char bsm_raw[];
     if (rec[0] < 0.0) return;
@@ -606,6 +619,7 @@ __global__ void __launch_bounds__(kMultiThreads, 1)
 k_extend_bulk_multi(const XT* __restrict__ X, int64_t n, int d_pad, const double* __restrict__ ext, int W,
                     const double* __restrict__ sqn, double* __restrict__ U, int64_t ldu, double* __restrict__ m,
                     double* __restrict__ v, double var, double neg2ls2) {
+    pdl_enter();
     constexpr int VN = Vec<XT>::N;
     constexpr int H = VN / 2;
     constexpr int R = kMultiRows;
@@ -775,6 +789,7 @@ __global__ void __launch_bounds__(256) k_catchup(const int* __restrict__ count, 
                                                  int W, int t, const double* __restrict__ sqn,
                                                  double* __restrict__ U, int64_t ldu, uint8_t* __restrict__ ncol,
                                                  double var, double neg2ls2) {
+    pdl_enter();
     constexpr int VN = Vec<XT>::N;
     extern __shared__ double csm[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarp_blk = blockDim.x >> 5;
@@ -848,6 +863,7 @@ __global__ void __launch_bounds__(256) k_score0(int64_t n, const double* __restr
                                                 double* __restrict__ score, double* __restrict__ gain,
                                                 Best* __restrict__ block_best, double log1p_eps, double scale,
                                                 const double2* __restrict__ phi) {
+    pdl_enter();
     // perfect / mistaken user: scale = 1, log1p_eps = log(1 + eps) (a mistaken user adds a constant later);
     // general model (label_prob < 1): scale = label_prob, log1p_eps = (1-mp) log(1+eps) + mp log(eps)
     double bs = 0.0;
@@ -912,6 +928,7 @@ __global__ void __launch_bounds__(1024) k_argmax_rows(int64_t n, const double* _
                                                       const uint8_t* __restrict__ mask,
                                                       Best* __restrict__ block_best, int* __restrict__ done,
                                                       int* __restrict__ count, int* __restrict__ list) {
+    pdl_enter();
     double bs = 0.0;
     long long bi = -1;
     // four independent (mask, value) loads in flight per thread: the pass is latency-bound, not bandwidth-bound
@@ -971,6 +988,7 @@ __global__ void __launch_bounds__(256) k_argmax_list(const int* __restrict__ cou
                                                      double floor_score = 0.0, double margin = 0.0,
                                                      double* __restrict__ thr_gain = nullptr,
                                                      int* __restrict__ reset_count = nullptr) {
+    pdl_enter();
     const int n = *count;
     double bs = 0.0;
     long long bi = -1;
@@ -1005,6 +1023,7 @@ __global__ void __launch_bounds__(256) k_argmax_list(const int* __restrict__ cou
 // stage 2: one block reduces the per-block results into out[0]
 __global__ void __launch_bounds__(256) k_argmax_final(const Best* __restrict__ block_best, int nblocks,
                                                       Best* __restrict__ out) {
+    pdl_enter();
     double bs = 0.0;
     long long bi = -1;
     for (int k = threadIdx.x; k < nblocks; k += blockDim.x)
@@ -1034,6 +1053,7 @@ __global__ void __launch_bounds__(256) k_worklist(int64_t n, const uint8_t* __re
                                                   const double* __restrict__ gain,
                                                   const double* __restrict__ thr_gain, int exhaustive,
                                                   int* __restrict__ count, int* __restrict__ list) {
+    pdl_enter();
     const double thr = exhaustive ? -1e300 : *thr_gain;
     const int lane = threadIdx.x & 31;
     for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n;
@@ -1110,6 +1130,7 @@ __device__ __forceinline__ double team_sum(double acc, int TPC, double* red) {
 
 template <int T>
 __global__ void __launch_bounds__(256) k_eval(EvalArgs a) {
+    pdl_enter();
     constexpr int NB = 1 << T;
     const int n_items = *a.count;
     const int TPC = eval_team_size(n_items, a.force_block);
@@ -1176,6 +1197,7 @@ __global__ void __launch_bounds__(256) k_eval(EvalArgs a) {
 }
 
 __global__ void __launch_bounds__(256) k_eval_sorted(EvalArgs a) {
+    pdl_enter();
     constexpr int MAXT = 10;
     const int t = a.t;
     const int n_items = *a.count;
@@ -1265,6 +1287,7 @@ struct GeneralArgs {
 };
 
 __global__ void __launch_bounds__(256) k_eval_general(GeneralArgs a) {
+    pdl_enter();
     extern __shared__ double gsm[];
     const int G = a.n_groups, NS = a.n_sets, t = a.t, D = a.t + 1;
     double* A = gsm;                    // [G]
@@ -1392,6 +1415,7 @@ __global__ void __launch_bounds__(256) k_snq_generate(int q, double R, int q_min
                                                       const double* __restrict__ gl_x, const double* __restrict__ gl_w,
                                                       int64_t N, double* __restrict__ eta, double* __restrict__ w,
                                                       int* __restrict__ orth) {
+    pdl_enter();
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= N) return;
     const int two_q = 2 * q;
@@ -1443,6 +1467,7 @@ __global__ void __launch_bounds__(1024) k_snq_finalize(int t, int64_t N, double 
                                                        double* __restrict__ w, int* __restrict__ orth,
                                                        double log1p_eps, double* __restrict__ masses,
                                                        double* __restrict__ h_base, int* __restrict__ n_kept) {
+    pdl_enter();
     __shared__ int warp_tot[32];
     __shared__ double part[32][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -1538,6 +1563,7 @@ __global__ void __launch_bounds__(256) k_pick_winner(const double* __restrict__ 
                                                      double* __restrict__ base_L, double* __restrict__ sel,
                                                      double* __restrict__ rec_hist, uint8_t* __restrict__ mask,
                                                      int64_t row_offset, int64_t n, uint8_t mark_bits) {
+    pdl_enter();
     __shared__ int win_s;
     if (threadIdx.x == 0) {
         int win = -1;
@@ -1578,6 +1604,7 @@ __global__ void __launch_bounds__(256) k_pick_winner(const double* __restrict__ 
 }
 
 __global__ void k_fill(double* __restrict__ p, int64_t n, double value) {
+    pdl_enter();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         p[i] = value;
 }
@@ -1585,17 +1612,20 @@ __global__ void k_fill(double* __restrict__ p, int64_t n, double value) {
 // mask[i] = (mask[i] & ~clear) | set for the listed local rows
 __global__ void k_mask_rows(uint8_t* __restrict__ mask, const int64_t* __restrict__ rows, int64_t m,
                             uint8_t set_bits) {
+    pdl_enter();
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += (int64_t)gridDim.x * blockDim.x)
         mask[rows[k]] |= set_bits;
 }
 
 __global__ void k_mask_all(uint8_t* __restrict__ mask, int64_t n, uint8_t and_bits, uint8_t or_bits) {
+    pdl_enter();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         mask[i] = (mask[i] & and_bits) | or_bits;
 }
 
 __global__ void k_mask_clear_rows(uint8_t* __restrict__ mask, const int64_t* __restrict__ rows, int64_t m,
                                   uint8_t clear_bits) {
+    pdl_enter();
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += (int64_t)gridDim.x * blockDim.x)
         mask[rows[k]] &= (uint8_t)~clear_bits;
 }
@@ -1609,10 +1639,14 @@ __global__ void __launch_bounds__(256) k_record(long long row, const Best* __res
                                                 int64_t ldu, int W_lab, int W_tot, int w_cap,
                                                 const double* __restrict__ gain, double* __restrict__ rec,
                                                 double shift_coef, const double* __restrict__ h_base,
-                                                const int* __restrict__ counters = nullptr,
+                                                int* __restrict__ counters = nullptr,
                                                 int* __restrict__ counters_dst = nullptr,
                                                 CommitTargets ct = CommitTargets()) {
-    if (counters_dst != nullptr && threadIdx.x < 4) counters_dst[threadIdx.x] = counters[threadIdx.x];
+    pdl_enter();
+    if (counters_dst != nullptr && threadIdx.x < 4) {
+        counters_dst[threadIdx.x] = counters[threadIdx.x];
+        if (threadIdx.x < 3) counters[threadIdx.x] = 0;     // ready for the next greedy step (no memset in between)
+    }
     // shift_coef * (total mass): what a user who mislabels with probability mistake_prob adds to every score of
     // the step (DESIGN.md "mistake_prob"); 0 for the perfect user
     double score = 0.0;
@@ -1667,6 +1701,7 @@ __global__ void __launch_bounds__(128) k_predict(const double* __restrict__ Xt, 
                                                  int nl, const double* __restrict__ wvec,
                                                  const double* __restrict__ LK, double var, double neg2ls2,
                                                  double* __restrict__ out_mean, double* __restrict__ out_var) {
+    pdl_enter();
     extern __shared__ double sm[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     double* kbuf = sm + (size_t)wib * nl;
@@ -1721,6 +1756,7 @@ __device__ __forceinline__ uint64_t desc_key(double x) {
 
 __global__ void __launch_bounds__(256) k_sort_init(const double* __restrict__ m, int64_t n, uint64_t* __restrict__ keys,
                                                    uint32_t* __restrict__ rows) {
+    pdl_enter();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         keys[i] = desc_key(m[i]);
         rows[i] = (uint32_t)i;
@@ -1730,6 +1766,7 @@ __global__ void __launch_bounds__(256) k_sort_init(const double* __restrict__ m,
 // item (w, j, lane) of a tile: tile_base + w * (32 * kSortItems) + j * 32 + lane -- the order that defines stability
 __global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint64_t* __restrict__ keys, int64_t n, int shift,
                                                             uint32_t* __restrict__ hist) {
+    pdl_enter();
     __shared__ uint32_t h[256];
     h[threadIdx.x] = 0;
     __syncthreads();
@@ -1745,6 +1782,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint64_t* __re
 
 // One block per digit: exclusive scan of the digit's tile counts in place, digit total to totals[digit].
 __global__ void __launch_bounds__(256) k_sort_scan(uint32_t* __restrict__ hist, int tiles, uint32_t* __restrict__ totals) {
+    pdl_enter();
     __shared__ uint32_t wsum[8];
     uint32_t* h = hist + (size_t)blockIdx.x * tiles;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1779,6 +1817,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint64_t* _
                                                                const uint32_t* __restrict__ totals,
                                                                uint64_t* __restrict__ keys_out,
                                                                uint32_t* __restrict__ rows_out) {
+    pdl_enter();
     constexpr int kWarps = kSortThreads / 32;
     __shared__ uint32_t cnt[kWarps][256];
     __shared__ uint32_t dsum[kWarps];
@@ -1835,6 +1874,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint64_t* _
 __global__ void __launch_bounds__(256) k_sort_gather(const uint32_t* __restrict__ rows, int64_t k, int64_t row_offset,
                                                      const double* __restrict__ m, int64_t* __restrict__ out_idx,
                                                      double* __restrict__ out_val) {
+    pdl_enter();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < k; i += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t r = rows[i];
         out_idx[i] = row_offset + (int64_t)r;
