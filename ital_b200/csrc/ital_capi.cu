@@ -87,6 +87,7 @@ struct ital_shard {
     int* stats_host = nullptr;       // pinned
     int proposals = 0;               // propose calls in the running fetch
     bool lazy_rows = false;          // batch projections only for the rows that get scored (k_catchup)
+    PickSrc pick;                    // where k_record finds the local best of the running step
     bool pdl = true;                 // programmatic dependent launch between the kernels of a stream (ITAL_B200_PDL=0: off)
     bool bulk_stream = true;         // X stream staged by the bulk-copy engine (k_extend_bulk) where it applies
     uint8_t* ncol = nullptr;         // lazy rows: batch columns valid per row
@@ -365,7 +366,7 @@ double step_shift_coef(const ital_shard* s) {
     return (1.0 - c) * (std::log(1e-12) - s->log1p_eps);
 }
 
-int make_record(ital_shard* s, long long local_row, double* dst_dev, bool commit_here = false) {
+int make_record(ital_shard* s, long long local_row, double* dst_dev, bool commit_here = false, PickSrc src = PickSrc()) {
     const double shift = local_row < 0 ? step_shift_coef(s) : 0.0;
     CommitTargets ct;
     if (commit_here) {
@@ -384,12 +385,12 @@ int make_record(ital_shard* s, long long local_row, double* dst_dev, bool commit
         pdl(k_record<float>, 1, 256, 0, s)(local_row, s->best, s->row_offset, (const float*)s->X, (int)s->d,
                                                   (int)s->d_pad, s->sqn, s->m, s->v, s->U, s->ldu, s->W,
                                                   s->W + s->t, s->w_cap, s->gain, dst_dev, shift, s->hbase_dev,
-                                                  s->counters, local_row < 0 ? s->stats_dev + 4 * s->t : nullptr, ct);
+                                                  s->counters, local_row < 0 ? s->stats_dev + 4 * s->t : nullptr, ct, src);
     else
         pdl(k_record<double>, 1, 256, 0, s)(local_row, s->best, s->row_offset, (const double*)s->X,
                                                    (int)s->d, (int)s->d_pad, s->sqn, s->m, s->v, s->U, s->ldu,
                                                    s->W, s->W + s->t, s->w_cap, s->gain, dst_dev, shift, s->hbase_dev,
-                                                   s->counters, local_row < 0 ? s->stats_dev + 4 * s->t : nullptr, ct); s->launches++;
+                                                   s->counters, local_row < 0 ? s->stats_dev + 4 * s->t : nullptr, ct, src); s->launches++;
     CU(cudaGetLastError());
     return ITAL_OK;
 }
@@ -596,7 +597,9 @@ int propose_general(ital_shard* s) {
     pdl(k_eval_general, blocks, 256, smem, s)(a); s->launches++;
     const int lb = std::min(kArgmaxBlocks, grid_for(s, s->n, 256));
     pdl(k_argmax_list, lb, 256, 0, s)(s->counters, s->worklist, s->score, s->block_best, nullptr, 0.0, 0.0, nullptr, nullptr); s->launches++;
-    pdl(k_argmax_final, 1, 256, 0, s)(s->block_best, lb, s->best); s->launches++;
+    s->pick = PickSrc();
+    s->pick.block_best = s->block_best;
+    s->pick.nblocks = lb;
     CU(cudaGetLastError());
     return ITAL_OK;
 }
@@ -606,6 +609,7 @@ int propose_general(ital_shard* s) {
 int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_out, bool commit_here = false) {
     if (s->t >= kMaxBatch) return fail(ITAL_EINVAL, "batches of more than %d samples are not supported", kMaxBatch);
     const int blocks = std::min(kArgmaxBlocks, grid_for(s, s->n, 256));
+    s->pick = PickSrc();
     // counters [0..2] are zero here: k_record re-arms them at the end of every step, ital_fetch_begin before the first
     if (s->t == 0) CU(cudaMemsetAsync(s->counters, 0, 4 * sizeof(int), s->stream));
     if (s->t == 0) {
@@ -613,7 +617,8 @@ int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_o
         const double lc = general ? (1.0 - s->mistake_prob) * s->log1p_eps + s->mistake_prob * std::log(1e-12) : s->log1p_eps;
         pdl(k_score0, blocks, 256, 0, s)(s->n, s->m, s->v, s->mask, s->score, s->gain, s->block_best, lc,
                                                 general ? s->label_prob : 1.0, s->phi_dev); s->launches++;
-        pdl(k_argmax_final, 1, 256, 0, s)(s->block_best, blocks, s->best); s->launches++;
+        s->pick.block_best = s->block_best;     // reduced by k_record
+        s->pick.nblocks = blocks;
         CU(cudaGetLastError());
         s->n_nodes = 1;
     } else if (s->label_prob < 1.0) {
@@ -630,7 +635,8 @@ int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_o
             if (rc) return rc;
             const int lb = std::min(kArgmaxBlocks, grid_for(s, s->n, 256));
             pdl(k_argmax_list, lb, 256, 0, s)(s->counters, s->worklist, s->score, s->block_best, nullptr, 0.0, 0.0, nullptr, nullptr); s->launches++;
-            pdl(k_argmax_final, 1, 256, 0, s)(s->block_best, lb, s->best); s->launches++;
+            s->pick.block_best = s->block_best;
+            s->pick.nblocks = lb;
         } else {
             // stage A: a spread sample of the most promising rows -- the maximum of the bound within each of
             // 2 x #SM strided subsets of the pool -- is scored first, one block per row.  (Taking the global
@@ -651,13 +657,15 @@ int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_o
             CU(cudaGetLastError());
             rc = launch_eval(s, (int64_t)s->num_sms * 24, false);    // 3 resident blocks per SM (80 registers)
             if (rc) return rc;
-            pdl(k_argmax_list, 1, 256, 0, s)(s->counters, s->worklist, s->score, s->best, nullptr, 0.0, 0.0, nullptr, nullptr); s->launches++;
+            s->pick.count = s->counters;            // final argmax over the scored rows: done by k_record
+            s->pick.list = s->worklist;
+            s->pick.score = s->score;
         }
         CU(cudaGetLastError());
     }
     s->step_nodes[s->t] = (double)s->n_nodes;
     s->proposals = s->t + 1;
-    return make_record(s, -1, rec_out, commit_here);
+    return make_record(s, -1, rec_out, commit_here, s->pick);
 }
 
 // np.argmax over `n_records` proposals in device memory + append; with `extend` the streaming pass follows.

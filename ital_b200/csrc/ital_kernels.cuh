@@ -60,6 +60,14 @@ struct CommitTargets {                   // where a single-shard step commits it
 // waits until its predecessor has completed and flushed (griddepcontrol.wait is a no-op for a launch without the
 // programmatic-serialization attribute).  The stream order of all memory effects is unchanged; what is saved is the
 // launch latency between the ~30 small dependent kernels of a fetch.
+struct PickSrc {                         // what k_record reduces to find the step's local best (one of the two, or
+    const Best* block_best = nullptr;    // neither: the row is given or `best` holds it): per-block results ...
+    int nblocks = 0;
+    const int* count = nullptr;          // ... or the scored rows of the final worklist
+    const int* list = nullptr;
+    const double* score = nullptr;
+};
+
 __device__ __forceinline__ void pdl_enter() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -923,7 +931,7 @@ __global__ void __launch_bounds__(256) k_score0(int64_t n, const double* __restr
     }
 }
 
-// argmax of `values` over candidate rows (mask == 0); stage 1 of 2
+// argmax of `values` over candidate rows (mask == 0), per block
 __global__ void __launch_bounds__(1024) k_argmax_rows(int64_t n, const double* __restrict__ values,
                                                       const uint8_t* __restrict__ mask,
                                                       Best* __restrict__ block_best, int* __restrict__ done,
@@ -979,7 +987,7 @@ __global__ void __launch_bounds__(1024) k_argmax_rows(int64_t n, const double* _
     }
 }
 
-// argmax of score[] over the rows listed in the worklist; stage 1 of 2
+// argmax of score[] over the rows listed in the worklist, per block (k_record reduces the per-block results)
 __global__ void __launch_bounds__(256) k_argmax_list(const int* __restrict__ count,
                                                      const int* __restrict__ list,
                                                      const double* __restrict__ score,
@@ -1017,32 +1025,6 @@ __global__ void __launch_bounds__(256) k_argmax_list(const int* __restrict__ cou
             *thr_gain = thr - margin - *h_base;
             *reset_count = 0;           // the worklist is rebuilt next
         }
-    }
-}
-
-// stage 2: one block reduces the per-block results into out[0]
-__global__ void __launch_bounds__(256) k_argmax_final(const Best* __restrict__ block_best, int nblocks,
-                                                      Best* __restrict__ out) {
-    pdl_enter();
-    double bs = 0.0;
-    long long bi = -1;
-    for (int k = threadIdx.x; k < nblocks; k += blockDim.x)
-        if (better(block_best[k].score, block_best[k].idx, bs, bi)) { bs = block_best[k].score; bi = block_best[k].idx; }
-    __shared__ double ss[32];
-    __shared__ long long si[32];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double os = __shfl_xor_sync(0xffffffffu, bs, o);
-        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (better(os, oi, bs, bi)) { bs = os; bi = oi; }
-    }
-    if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = bs; si[threadIdx.x >> 5] = bi; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
-            if (better(ss[w], si[w], bs, bi)) { bs = ss[w]; bi = si[w]; }
-        out->score = bs;
-        out->idx = bi;
     }
 }
 
@@ -1641,8 +1623,45 @@ __global__ void __launch_bounds__(256) k_record(long long row, const Best* __res
                                                 double shift_coef, const double* __restrict__ h_base,
                                                 int* __restrict__ counters = nullptr,
                                                 int* __restrict__ counters_dst = nullptr,
-                                                CommitTargets ct = CommitTargets()) {
+                                                CommitTargets ct = CommitTargets(), PickSrc src = PickSrc()) {
     pdl_enter();
+    __shared__ Best pick_s;
+    if (row < 0 && (src.block_best != nullptr || src.list != nullptr)) {
+        // the argmax that used to be a kernel of its own (k_argmax_final / the last k_argmax_list of a step)
+        double bs = 0.0;
+        long long bi = -1;
+        if (src.block_best != nullptr) {
+            for (int k = threadIdx.x; k < src.nblocks; k += blockDim.x)
+                if (better(src.block_best[k].score, src.block_best[k].idx, bs, bi)) {
+                    bs = src.block_best[k].score;
+                    bi = src.block_best[k].idx;
+                }
+        } else {
+            const int cnt = *src.count;
+            for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+                const long long i = src.list[k];
+                if (better(src.score[i], i, bs, bi)) { bs = src.score[i]; bi = i; }
+            }
+        }
+        __shared__ double pss[8];
+        __shared__ long long psi[8];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+            const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (better(os, oi, bs, bi)) { bs = os; bi = oi; }
+        }
+        if ((threadIdx.x & 31) == 0) { pss[threadIdx.x >> 5] = bs; psi[threadIdx.x >> 5] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+                if (better(pss[w], psi[w], bs, bi)) { bs = pss[w]; bi = psi[w]; }
+            pick_s.score = bs;
+            pick_s.idx = bi;
+        }
+        __syncthreads();
+        best = &pick_s;
+    }
     if (counters_dst != nullptr && threadIdx.x < 4) {
         counters_dst[threadIdx.x] = counters[threadIdx.x];
         if (threadIdx.x < 3) counters[threadIdx.x] = 0;     // ready for the next greedy step (no memset in between)
