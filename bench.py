@@ -389,6 +389,8 @@ def main():
                   'note': 'wall clock; update(%d labels) = one multi-column streaming pass + host bookkeeping; '
                           'top_results(100) = device radix sort of the local means, 100 indices read back' % args.batch}
 
+    used_peer = bool(getattr(learner, '_peer', False))
+    learner.close()
     if rank != 0:
         dist.destroy_process_group()
         return
@@ -401,7 +403,9 @@ def main():
                                % (args.rows, world, args.dim, args.batch, n_lab),
                    'rows_per_gpu': args.rows, 'd': args.dim, 'batch': args.batch, 'labelled': n_lab,
                    'candidates_ranked_per_step': ranked, 'l2': 'inputs (2 GB per GPU) exceed the 126 MB L2; no flush',
-                   'parallelism': 'rows sharded over %d GPU(s); one record all-gather per greedy step' % world,
+                   'parallelism': 'rows sharded over %d GPU(s); per greedy step every shard %s' % (
+                       world, 'stores its proposal into its peers\' memory over NVLink (CUDA IPC; no NCCL in the loop)'
+                       if used_peer else 'contributes one record to an NCCL all-gather'),
                    'batch_selected': [int(i) for i in ret]},
         'e2e': {'value': ranked * args.steps / wall, 'unit': UNIT, 'ms_per_step': wall / args.steps * 1e3,
                 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),

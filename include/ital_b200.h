@@ -107,6 +107,26 @@ int ital_fetch_end(ital_shard* s);
 int ital_fetch(ital_shard* s, int k, double label_prob, double mistake_prob, int exhaustive,
                int64_t* out_idx, double* out_scores);
 
+/* Multi-GPU fetch without NCCL in the loop.  Every shard owns an exchange buffer (one slot per shard and epoch
+ * parity, one flag word per shard) that its peers map through CUDA IPC.  In a greedy step a shard stores its proposal
+ * straight into the slot reserved for it in every peer's buffer (k_peer_put: peer stores over NVLink / NVSwitch,
+ * then a system-scope release of the epoch flag); the kernel that picks the winner (k_pick_winner) waits on the
+ * flags of its own buffer.  This replaces the per-step all-gather of `ital_fetch_propose_dev` /
+ * `ital_fetch_commit_dev` (np.argmax over the Pool's results, ital/ital.py:124-130, across GPUs).
+ *   ital_peer_export:   (re)allocates the local buffer, writes its IPC handle (>= 64 bytes) to handle_out;
+ *   ital_peer_connect:  maps the buffers of all shards; `handles` holds world handles of handle_bytes each, by rank;
+ *   ital_fetch_peer:    the whole greedy loop (as ital_fetch); every shard must call it with the same arguments;
+ *                       fails if a peer does not deliver within 5 s (bounded spin: the GPU is never left hanging);
+ *   ital_peer_disconnect: unmaps the peers' buffers (call on every shard before any shard is destroyed);
+ *   ital_peer_slot_doubles: capacity of a slot in doubles (0 if not connected); records longer than this
+ *                       (more than 2048 projection entries) need the NCCL path. */
+int ital_peer_export(ital_shard* s, int world, int rank, void* handle_out, int64_t handle_bytes);
+int ital_peer_connect(ital_shard* s, const void* handles, int64_t handle_bytes);
+int ital_peer_disconnect(ital_shard* s);
+int64_t ital_peer_slot_doubles(const ital_shard* s);
+int ital_fetch_peer(ital_shard* s, int k, double label_prob, double mistake_prob, int exhaustive, int64_t* out_idx,
+                    double* out_scores);
+
 /* Lazy rows (off by default).  Off: every greedy step streams the whole pool once to extend every row's
  * batch-conditional projection (k_extend; HBM-bound, what predict_cov_batch does for all rows, ital/gp.py:235-261).
  * On: the projection is extended only for the rows that are actually scored, on demand, from the stored records of

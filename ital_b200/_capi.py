@@ -42,6 +42,12 @@ SIGNATURES = {
     'ital_fetch_end': (ctypes.c_int, [_shard_p]),
     'ital_fetch': (ctypes.c_int, [_shard_p, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                   _c_int64_p, _c_double_p]),
+    'ital_peer_export': (ctypes.c_int, [_shard_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64]),
+    'ital_peer_connect': (ctypes.c_int, [_shard_p, ctypes.c_void_p, ctypes.c_int64]),
+    'ital_peer_disconnect': (ctypes.c_int, [_shard_p]),
+    'ital_peer_slot_doubles': (ctypes.c_int64, [_shard_p]),
+    'ital_fetch_peer': (ctypes.c_int, [_shard_p, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int,
+                                       _c_int64_p, _c_double_p]),
     'ital_set_lazy_rows': (ctypes.c_int, [_shard_p, ctypes.c_int]),
     'ital_set_bulk_stream': (ctypes.c_int, [_shard_p, ctypes.c_int]),
     'ital_fetch_stats': (ctypes.c_int, [_shard_p, _c_double_p]),

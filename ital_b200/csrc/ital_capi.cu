@@ -87,6 +87,15 @@ struct ital_shard {
     int* stats_host = nullptr;       // pinned
     int proposals = 0;               // propose calls in the running fetch
     bool lazy_rows = false;          // batch projections only for the rows that get scored (k_catchup)
+    // peer-memory exchange of the per-step proposals (multi-GPU fetch without NCCL in the loop)
+    int xg_world = 0, xg_rank = 0;
+    int64_t xg_slot = 0;                     // doubles per slot
+    unsigned char* xg_local = nullptr;       // this shard's exchange buffer (exported through CUDA IPC)
+    std::vector<unsigned char*> xg_peer;     // mapped buffers of all shards ([rank] = xg_local)
+    unsigned char** xg_peer_dev = nullptr;
+    int* xg_error_dev = nullptr;
+    unsigned long long xg_epoch = 0;
+    bool xg_ready = false;
     PickSrc pick;                    // where k_record finds the local best of the running step
     bool pdl = true;                 // programmatic dependent launch between the kernels of a stream (ITAL_B200_PDL=0: off)
     bool bulk_stream = true;         // X stream staged by the bulk-copy engine (k_extend_bulk) where it applies
@@ -366,7 +375,8 @@ double step_shift_coef(const ital_shard* s) {
     return (1.0 - c) * (std::log(1e-12) - s->log1p_eps);
 }
 
-int make_record(ital_shard* s, long long local_row, double* dst_dev, bool commit_here = false, PickSrc src = PickSrc()) {
+int make_record(ital_shard* s, long long local_row, double* dst_dev, bool commit_here = false, PickSrc src = PickSrc(),
+                PeerPut pp = PeerPut()) {
     const double shift = local_row < 0 ? step_shift_coef(s) : 0.0;
     CommitTargets ct;
     if (commit_here) {
@@ -385,12 +395,12 @@ int make_record(ital_shard* s, long long local_row, double* dst_dev, bool commit
         pdl(k_record<float>, 1, 256, 0, s)(local_row, s->best, s->row_offset, (const float*)s->X, (int)s->d,
                                                   (int)s->d_pad, s->sqn, s->m, s->v, s->U, s->ldu, s->W,
                                                   s->W + s->t, s->w_cap, s->gain, dst_dev, shift, s->hbase_dev,
-                                                  s->counters, local_row < 0 ? s->stats_dev + 4 * s->t : nullptr, ct, src);
+                                                  s->counters, local_row < 0 ? s->stats_dev + 4 * s->t : nullptr, ct, src, pp);
     else
         pdl(k_record<double>, 1, 256, 0, s)(local_row, s->best, s->row_offset, (const double*)s->X,
                                                    (int)s->d, (int)s->d_pad, s->sqn, s->m, s->v, s->U, s->ldu,
                                                    s->W, s->W + s->t, s->w_cap, s->gain, dst_dev, shift, s->hbase_dev,
-                                                   s->counters, local_row < 0 ? s->stats_dev + 4 * s->t : nullptr, ct, src); s->launches++;
+                                                   s->counters, local_row < 0 ? s->stats_dev + 4 * s->t : nullptr, ct, src, pp); s->launches++;
     CU(cudaGetLastError());
     return ITAL_OK;
 }
@@ -606,7 +616,8 @@ int propose_general(ital_shard* s) {
 
 // The local candidates of the current greedy step -> record of the local best in DEVICE memory `rec_out`.
 // Nothing here waits for the GPU (t <= 3).
-int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_out, bool commit_here = false) {
+int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_out, bool commit_here = false,
+                PeerPut pp = PeerPut()) {
     if (s->t >= kMaxBatch) return fail(ITAL_EINVAL, "batches of more than %d samples are not supported", kMaxBatch);
     const int blocks = std::min(kArgmaxBlocks, grid_for(s, s->n, 256));
     s->pick = PickSrc();
@@ -665,16 +676,18 @@ int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_o
     }
     s->step_nodes[s->t] = (double)s->n_nodes;
     s->proposals = s->t + 1;
-    return make_record(s, -1, rec_out, commit_here, s->pick);
+    return make_record(s, -1, rec_out, commit_here, s->pick, pp);
 }
 
 // np.argmax over `n_records` proposals in device memory + append; with `extend` the streaming pass follows.
-int commit_dev(ital_shard* s, const double* recs_dev, int n_records, int extend, bool picked = false) {
+int commit_dev(ital_shard* s, const double* recs_dev, int n_records, int extend, bool picked = false,
+               PeerWait pw = PeerWait(), int64_t rec_stride = 0) {
     if (s->t >= kMaxBatch) return fail(ITAL_EINVAL, "batches of more than %d samples are not supported", kMaxBatch);
     if (!picked) {
-    pdl(k_pick_winner, 1, 256, 0, s)(recs_dev, n_records, record_doubles(s), s->t, s->W, s->rec_in_dev,
+    pdl(k_pick_winner, 1, 256, 0, s)(recs_dev, n_records, rec_stride > 0 ? rec_stride : record_doubles(s),
+                                            record_doubles(s), s->t, s->W, s->rec_in_dev,
                                             s->base_m_dev, s->base_L_dev, s->sel_dev, s->rec_hist, s->mask,
-                                            s->row_offset, s->n, kSelected); s->launches++;
+                                            s->row_offset, s->n, kSelected, pw); s->launches++;
     CU(cudaGetLastError());
     }
     if (extend && !s->lazy_rows) {      // lazy rows: the projection is extended on demand by k_catchup instead
@@ -687,8 +700,19 @@ int commit_dev(ital_shard* s, const double* recs_dev, int n_records, int extend,
     return ITAL_OK;
 }
 
+void peer_close(ital_shard* s) {
+    for (int g = 0; g < (int)s->xg_peer.size(); ++g)
+        if (g != s->xg_rank && s->xg_peer[g]) cudaIpcCloseMemHandle(s->xg_peer[g]);
+    s->xg_peer.clear();
+    s->xg_ready = false;
+}
+
 void free_all(ital_shard* s) {
     cudaSetDevice(s->device);
+    peer_close(s);
+    if (s->xg_local) cudaFree(s->xg_local);
+    if (s->xg_peer_dev) cudaFree(s->xg_peer_dev);
+    if (s->xg_error_dev) cudaFree(s->xg_error_dev);
     void* ptrs[] = {s->X, s->sqn, s->m, s->v, s->U, s->gain, s->score, s->mask, s->worklist, s->counters,
                     s->block_best, s->best, s->thr_dev, s->rec_dev, s->rec_in_dev, s->idx_dev, s->eta_dev,
                     s->w_dev, s->masses_dev, s->group_dev, s->orth_dev, s->eta_raw, s->w_raw, s->orth_raw, s->gl_dev, s->phi_dev, s->base_m_dev, s->base_L_dev, s->sel_dev,
@@ -1181,6 +1205,118 @@ int ital_fetch_end(ital_shard* s) {
     s->fetching = false;
     s->t = 0;
     return ITAL_OK;
+}
+
+int ital_peer_export(ital_shard* s, int world, int rank, void* handle_out, int64_t handle_bytes) {
+    if (!s || world < 2 || world > 32 || rank < 0 || rank >= world || !handle_out ||
+        handle_bytes < (int64_t)sizeof(cudaIpcMemHandle_t))
+        return fail(ITAL_EINVAL, "ital_peer_export: bad arguments");
+    CU(cudaSetDevice(s->device));
+    peer_close(s);
+    if (s->xg_local) { CU(cudaFree(s->xg_local)); s->xg_local = nullptr; }
+    s->xg_world = world;
+    s->xg_rank = rank;
+    s->xg_slot = ITAL_RECORD_HEADER + 2048 + s->d;          // records with up to 2048 projection entries
+    const size_t bytes = 256 + (size_t)2 * world * s->xg_slot * sizeof(double);
+    CU(cudaMalloc(&s->xg_local, bytes));
+    CU(cudaMemset(s->xg_local, 0, bytes));
+    if (!s->xg_error_dev) CU(cudaMalloc(&s->xg_error_dev, sizeof(int)));
+    CU(cudaMemset(s->xg_error_dev, 0, sizeof(int)));
+    CU(cudaDeviceSynchronize());
+    s->xg_epoch = 0;
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s->xg_local));
+    memset(handle_out, 0, (size_t)handle_bytes);
+    memcpy(handle_out, &h, sizeof h);
+    return ITAL_OK;
+}
+
+int ital_peer_connect(ital_shard* s, const void* handles, int64_t handle_bytes) {
+    if (!s || !handles || !s->xg_local || handle_bytes < (int64_t)sizeof(cudaIpcMemHandle_t))
+        return fail(ITAL_EINVAL, "ital_peer_connect: bad arguments (ital_peer_export first)");
+    CU(cudaSetDevice(s->device));
+    peer_close(s);
+    s->xg_peer.assign((size_t)s->xg_world, nullptr);
+    for (int g = 0; g < s->xg_world; ++g) {
+        if (g == s->xg_rank) { s->xg_peer[g] = s->xg_local; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const unsigned char*)handles + (size_t)g * handle_bytes, sizeof h);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            peer_close(s);
+            return fail(ITAL_ECUDA, "ital_peer_connect: cannot map the exchange buffer of shard %d (%s)", g,
+                        cudaGetErrorString(e));
+        }
+        s->xg_peer[g] = (unsigned char*)p;
+    }
+    if (!s->xg_peer_dev) CU(cudaMalloc(&s->xg_peer_dev, 32 * sizeof(unsigned char*)));
+    CU(cudaMemcpy(s->xg_peer_dev, s->xg_peer.data(), (size_t)s->xg_world * sizeof(unsigned char*), cudaMemcpyHostToDevice));
+    s->xg_ready = true;
+    return ITAL_OK;
+}
+
+int ital_peer_disconnect(ital_shard* s) {
+    if (!s) return fail(ITAL_EINVAL, "null shard");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    peer_close(s);
+    return ITAL_OK;
+}
+
+int64_t ital_peer_slot_doubles(const ital_shard* s) { return s && s->xg_ready ? s->xg_slot : 0; }
+
+int ital_fetch_peer(ital_shard* s, int k, double label_prob, double mistake_prob, int exhaustive, int64_t* out_idx,
+                    double* out_scores) {
+    if (!s || k < 0 || (k > 0 && !out_idx)) return fail(ITAL_EINVAL, "ital_fetch_peer: bad arguments");
+    if (!s->xg_ready) return fail(ITAL_ESTATE, "ital_fetch_peer: no peer exchange (ital_peer_export / ital_peer_connect)");
+    if (k > kMaxBatch) return fail(ITAL_EINVAL, "batches of more than %d samples are not supported", kMaxBatch);
+    int rc = ital_fetch_begin(s, label_prob, mistake_prob);
+    if (rc) return rc;
+    const int64_t rl = record_doubles(s);
+    if (rl > s->xg_slot) {
+        ital_fetch_end(s);
+        return fail(ITAL_ESTATE, "ital_fetch_peer: records of %lld doubles exceed the exchange slots", (long long)rl);
+    }
+    const int G = s->xg_world;
+    // every shard enqueues the same k steps; nothing waits for the host, the shards meet in k_pick_winner
+    for (int it = 0; it < k && rc == ITAL_OK; ++it) {
+        const unsigned long long epoch = ++s->xg_epoch;
+        PeerPut pp;
+        pp.peer_base = s->xg_peer_dev;
+        pp.G = G;
+        pp.rank = s->xg_rank;
+        pp.slot_doubles = s->xg_slot;
+        pp.epoch = epoch;
+        rc = propose_dev(s, -std::numeric_limits<double>::infinity(), exhaustive, s->rec_dev, false, pp);
+        if (rc) break;
+        PeerWait pw;
+        pw.flags = reinterpret_cast<const unsigned long long*>(s->xg_local);
+        pw.epoch = epoch;
+        pw.error = s->xg_error_dev;
+        const double* slots = reinterpret_cast<const double*>(s->xg_local + 256) + (int64_t)(epoch & 1) * G * s->xg_slot;
+        // the slots are xg_slot doubles apart, the records in them rl doubles long
+        rc = commit_dev(s, slots, G, it + 1 < k, false, pw, s->xg_slot);
+    }
+    int got = 0;
+    if (rc == ITAL_OK) {
+        got = ital_fetch_result(s, k, out_idx, out_scores);
+        if (got >= 0) {
+            int err = 0;
+            CU(cudaMemcpy(&err, s->xg_error_dev, sizeof err, cudaMemcpyDeviceToHost));
+            if (err) {
+                CU(cudaMemset(s->xg_error_dev, 0, sizeof(int)));
+                rc = fail(ITAL_ECUDA, "ital_fetch_peer: a shard did not deliver its proposal within 5 s");
+            }
+        } else {
+            rc = got;
+        }
+    }
+    int rc2 = ital_fetch_end(s);
+    if (rc) return rc;
+    if (rc2) return rc2;
+    return got;
 }
 
 int ital_fetch(ital_shard* s, int k, double label_prob, double mistake_prob, int exhaustive, int64_t* out_idx,

@@ -1540,20 +1540,50 @@ __global__ void __launch_bounds__(1024) k_snq_finalize(int t, int64_t N, double 
 // np.argmax over the shards' proposals + AppendedMutualInformation.append (ital/ital.py:130-131, 561-568): choose
 // the best of G point records (score desc, global row asc), make it the record k_extend will read, and append it
 // to the batch state kept on the device (mean, Cholesky row of the batch's posterior covariance, selection list).
-__global__ void __launch_bounds__(256) k_pick_winner(const double* __restrict__ recs, int G, int64_t rec_len, int t,
+struct PeerWait {                        // peer-memory exchange (k_peer_put): wait until every shard's record of this
+    const unsigned long long* flags = nullptr;   // epoch has landed in local memory; nullptr = records already there
+    unsigned long long epoch = 0;
+    int* error = nullptr;                // set to 1 if a peer did not deliver within the time limit
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(256) k_pick_winner(const double* recs, int G, int64_t rec_stride, int64_t rec_len, int t,
                                                      int W, double* __restrict__ rec_in, double* __restrict__ base_m,
                                                      double* __restrict__ base_L, double* __restrict__ sel,
                                                      double* __restrict__ rec_hist, uint8_t* __restrict__ mask,
-                                                     int64_t row_offset, int64_t n, uint8_t mark_bits) {
+                                                     int64_t row_offset, int64_t n, uint8_t mark_bits, PeerWait pw) {
     pdl_enter();
     __shared__ int win_s;
+    if (pw.flags != nullptr) {
+        // records were stored into this GPU's memory by the peers (k_peer_put over NVLink): spin on their epoch flags,
+        // bounded (a peer that never delivers must not hang the GPU), and read the records past L1 (__ldcg)
+        if ((int)threadIdx.x < G) {
+            const unsigned long long t0 = global_ns();
+            unsigned spins = 0;
+            while (ld_acquire_sys(pw.flags + threadIdx.x) < pw.epoch) {
+                if ((++spins & 1023u) == 0 && global_ns() - t0 > 5000000000ull) { *pw.error = 1; break; }
+            }
+        }
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
         int win = -1;
         for (int g = 0; g < G; ++g) {
-            const double idx = recs[g * rec_len], sc = recs[g * rec_len + 1];
+            const double idx = __ldcg(recs + g * rec_stride), sc = __ldcg(recs + g * rec_stride + 1);
             if (idx < 0.0 || sc != sc) continue;
-            if (win < 0 || sc > recs[win * rec_len + 1] ||
-                (sc == recs[win * rec_len + 1] && idx < recs[win * rec_len]))
+            if (win < 0 || sc > __ldcg(recs + win * rec_stride + 1) ||
+                (sc == __ldcg(recs + win * rec_stride + 1) && idx < __ldcg(recs + win * rec_stride)))
                 win = g;
         }
         win_s = win;
@@ -1569,19 +1599,49 @@ __global__ void __launch_bounds__(256) k_pick_winner(const double* __restrict__ 
         }
         return;
     }
-    const double* r = recs + (int64_t)win * rec_len;
+    const double* r = recs + (int64_t)win * rec_stride;
     for (int64_t k = threadIdx.x; k < rec_len; k += blockDim.x) {
-        rec_in[k] = r[k];
-        rec_hist[(int64_t)t * rec_len + k] = r[k];      // kept for rows that catch up later (k_catchup)
+        const double val = __ldcg(r + k);
+        rec_in[k] = val;
+        rec_hist[(int64_t)t * rec_len + k] = val;       // kept for rows that catch up later (k_catchup)
     }
     if (threadIdx.x == 0) {
-        const long long loc = (long long)r[0] - row_offset;
+        const long long loc = (long long)__ldcg(r) - row_offset;
         if (loc >= 0 && loc < n) mask[loc] |= mark_bits;    // the chosen row leaves the candidate set
-        base_m[t] = r[2];
-        for (int j = 0; j < t; ++j) base_L[t * kBaseStride + j] = r[8 + W + j];
-        base_L[t * kBaseStride + t] = sqrt(fmax(r[3], 1e-300));
-        sel[2 * t] = r[0];
-        sel[2 * t + 1] = r[1];
+        base_m[t] = __ldcg(r + 2);
+        for (int j = 0; j < t; ++j) base_L[t * kBaseStride + j] = __ldcg(r + 8 + W + j);
+        base_L[t * kBaseStride + t] = sqrt(fmax(__ldcg(r + 3), 1e-300));
+        sel[2 * t] = __ldcg(r);
+        sel[2 * t + 1] = __ldcg(r + 1);
+    }
+}
+
+// The all-gather of a greedy step without NCCL: the kernel that writes a shard's proposal (k_record) also stores it
+// into the slot reserved for this shard in every shard's exchange buffer (peer memory mapped through CUDA IPC; the
+// stores travel over NVLink / NVSwitch), then publishes the epoch in the flag words with system-scope release
+// semantics.  Slots are double-buffered by epoch parity: a shard can run at most one step ahead of a peer that still
+// reads the previous record.
+//   buffer of a shard: [G flag words, padded to 256 bytes][2][G][slot_doubles]
+struct PeerPut {
+    unsigned char* const* peer_base = nullptr;   // device array of G mapped buffers; nullptr = no exchange
+    int G = 0;
+    int rank = 0;
+    int64_t slot_doubles = 0;
+    unsigned long long epoch = 0;
+};
+
+__device__ __forceinline__ void peer_put(const PeerPut& pp, const double* rec, int64_t rec_len) {
+    __syncthreads();                                     // the record is complete (written by this block)
+    for (int g = 0; g < pp.G; ++g) {
+        double* dst = reinterpret_cast<double*>(pp.peer_base[g] + 256) +
+                      ((int64_t)(pp.epoch & 1) * pp.G + pp.rank) * pp.slot_doubles;
+        for (int64_t k = threadIdx.x; k < rec_len; k += blockDim.x) dst[k] = rec[k];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < pp.G) {
+        unsigned long long* flag = reinterpret_cast<unsigned long long*>(pp.peer_base[threadIdx.x]) + pp.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(pp.epoch) : "memory");
     }
 }
 
@@ -1623,7 +1683,8 @@ __global__ void __launch_bounds__(256) k_record(long long row, const Best* __res
                                                 double shift_coef, const double* __restrict__ h_base,
                                                 int* __restrict__ counters = nullptr,
                                                 int* __restrict__ counters_dst = nullptr,
-                                                CommitTargets ct = CommitTargets(), PickSrc src = PickSrc()) {
+                                                CommitTargets ct = CommitTargets(), PickSrc src = PickSrc(),
+                                                PeerPut pp = PeerPut()) {
     pdl_enter();
     __shared__ Best pick_s;
     if (row < 0 && (src.block_best != nullptr || src.list != nullptr)) {
@@ -1680,6 +1741,7 @@ __global__ void __launch_bounds__(256) k_record(long long row, const Best* __res
             ct.sel[2 * ct.t] = -1.0;
             ct.sel[2 * ct.t + 1] = -INFINITY;
         }
+        if (pp.peer_base != nullptr) peer_put(pp, rec, rec_len);
         return;
     }
     for (int j = threadIdx.x; j < w_cap; j += blockDim.x) rec[8 + j] = j < W_tot ? U[(int64_t)j * ldu + row] : 0.0;
@@ -1711,6 +1773,7 @@ __global__ void __launch_bounds__(256) k_record(long long row, const Best* __res
             ct.sel[2 * ct.t + 1] = rec[1];
         }
     }
+    if (pp.peer_base != nullptr) peer_put(pp, rec, rec_len);
 }
 
 // GaussianProcess.predict (ital/gp.py:264-292) for arbitrary rows: one warp per test row.

@@ -57,6 +57,9 @@ class LocalComm(object):
     def gather_rows(self, local, offsets):
         return local
 
+    def barrier(self):
+        pass
+
 
 class TorchComm(object):
     """torch.distributed process group; NCCL moves CUDA tensors, gloo moves CPU tensors."""
@@ -100,6 +103,22 @@ class TorchComm(object):
         out = self._torch.empty(self.world_size * t.numel(), dtype=t.dtype, device=self.device)
         self._dist.all_gather_into_tensor(out, t, group=self.group)
         return out.cpu().numpy().reshape((self.world_size,) + tuple(np.shape(rec)))
+
+    def gather_bytes(self, mine):
+        """All ranks' fixed-size byte strings (numpy uint8), by rank: (world_size, len) array."""
+        t = self._torch.from_numpy(np.ascontiguousarray(mine, dtype=np.uint8)).to(self.device)
+        out = self._torch.empty(self.world_size * t.numel(), dtype=t.dtype, device=self.device)
+        self._dist.all_gather_into_tensor(out, t, group=self.group)
+        return out.cpu().numpy().reshape(self.world_size, -1)
+
+    def all_agree(self, ok):
+        """True iff `ok` is true on every rank."""
+        t = self._torch.tensor([1 if ok else 0], dtype=self._torch.int32, device=self.device)
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.MIN, group=self.group)
+        return bool(int(t.item()))
+
+    def barrier(self):
+        self._dist.barrier(group=self.group)
 
     def gather_rows(self, local, offsets):
         """Concatenate per-shard row vectors (ragged by at most one row) into the global vector."""

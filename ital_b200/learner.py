@@ -105,6 +105,31 @@ class _Shard(object):
                                               int(bool(exhaustive)), _capi.i64ptr(idx), _capi.dptr(scores)))
         return idx[:got], scores[:got]
 
+    def peer_export(self, world, rank, handle_bytes):
+        handle = np.zeros(handle_bytes, dtype=np.uint8)
+        _capi.check(self.lib.ital_peer_export(self.handle, int(world), int(rank),
+                                              handle.ctypes.data_as(ctypes.c_void_p), int(handle_bytes)))
+        return handle
+
+    def peer_connect(self, handles, handle_bytes):
+        """True if the exchange buffers of all shards could be mapped (same node, peer access)."""
+        handles = np.ascontiguousarray(handles, dtype=np.uint8)
+        return self.lib.ital_peer_connect(self.handle, handles.ctypes.data_as(ctypes.c_void_p), int(handle_bytes)) == 0
+
+    def peer_disconnect(self):
+        if self.handle:
+            self.lib.ital_peer_disconnect(self.handle)
+
+    def peer_slot_doubles(self):
+        return int(self.lib.ital_peer_slot_doubles(self.handle))
+
+    def fetch_peer(self, k, label_prob, mistake_prob, exhaustive):
+        idx = np.zeros(max(k, 1), dtype=np.int64)
+        scores = np.zeros(max(k, 1))
+        got = _capi.check(self.lib.ital_fetch_peer(self.handle, int(k), float(label_prob), float(mistake_prob),
+                                                   int(bool(exhaustive)), _capi.i64ptr(idx), _capi.dptr(scores)))
+        return idx[:got], scores[:got]
+
     def stats(self):
         out = np.zeros(8)
         _capi.check(self.lib.ital_fetch_stats(self.handle, _capi.dptr(out)))
@@ -234,6 +259,7 @@ class ITAL(object):
         self._comm = LocalComm() if process_group is None else \
             TorchComm(None if process_group is True else process_group, device)
         self._shard = None
+        self._peer = False
         self.last_fetch_stats = []
         self.fit(data, queries)
 
@@ -261,9 +287,7 @@ class ITAL(object):
     def fit(self, data, queries=[]):                                            # retrieval_base.py:34-45
         self.data = data
         self.queries = queries
-        if self._shard is not None:
-            self._shard.close()
-            self._shard = None
+        self.close()
         if self.data is None:
             self.gp = None
             return
@@ -302,9 +326,40 @@ class ITAL(object):
         self._shard = _Shard(Xl, _capi.ITAL_F32 if storage == 'float32' else _capi.ITAL_F64, lo, self._n,
                              self.length_scale, self.var, self.noise, device)
         self.gp = _GPView(self)
+        self._setup_peer_exchange()
         self.lazy_rows = self._lazy_rows
         self.bulk_stream = self._bulk_stream
         self.reset()
+
+    def _setup_peer_exchange(self):
+        """Multi-GPU on one node: map every shard's exchange buffer into every process (CUDA IPC), so that a greedy
+        step exchanges its proposals by peer stores over NVLink instead of an NCCL all-gather (ital_fetch_peer).
+        Falls back to the NCCL loop, on all ranks alike, if any mapping fails (ITAL_B200_PEER=0 forces that)."""
+        import os
+        self._peer = False
+        comm = self._comm
+        if comm.world_size == 1 or not getattr(comm, 'on_device', False) \
+                or os.environ.get('ITAL_B200_PEER', '1') != '1':
+            return
+        handle_bytes = 128
+        mine = self._shard.peer_export(comm.world_size, comm.rank, handle_bytes)
+        ok = self._shard.peer_connect(comm.gather_bytes(mine), handle_bytes)
+        self._peer = comm.all_agree(ok)
+        if not self._peer:
+            self._shard.peer_disconnect()
+
+    def close(self):
+        """Release the GPU state.  With several GPUs every process must call it (the peers' exchange buffers are
+        unmapped between two barriers, before any of them is freed)."""
+        if getattr(self, '_shard', None) is None:
+            return
+        if getattr(self, '_peer', False):
+            self._comm.barrier()
+            self._shard.peer_disconnect()
+            self._comm.barrier()
+            self._peer = False
+        self._shard.close()
+        self._shard = None
 
     def reset(self):                                                            # retrieval_base.py:48-61
         self.rounds = 0
@@ -466,6 +521,11 @@ class ITAL(object):
                 self.last_fetch_scores = scores
                 return [int(i) for i in idx]
             if getattr(self._comm, 'on_device', False) and not show_progress:
+                if self._peer and 2 * self._shard.record_doubles() <= self._shard.peer_slot_doubles():
+                    # (2 x: room for the batch's projection columns may still double the record in ital_fetch_begin)
+                    idx, scores = self._shard.fetch_peer(k, self.label_prob, self.mistake_prob, self.exhaustive)
+                    self.last_fetch_scores = scores
+                    return [int(i) for i in idx]
                 return self._fetch_device_loop(k)
             return self._fetch_stepwise(k, show_progress)
         finally:

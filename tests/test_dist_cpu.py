@@ -66,6 +66,10 @@ def _worker(rank, world, port, out):
         order = np.lexsort((loc, -means[lo:hi]))
         top_all = merge_top(comm, loc[order], means[lo:hi][order], int(np.max(np.diff(off))), None)
         top4 = merge_top(comm, loc[order][:4], means[lo:hi][order][:4], 4, 4)
+        hb = comm.gather_bytes(np.full(16, rank + 1, dtype=np.uint8))
+        assert hb.shape == (world, 16) and all(np.all(hb[r] == r + 1) for r in range(world))
+        assert comm.all_agree(True) and not comm.all_agree(rank == 0)
+        comm.barrier()
         out.put((rank, summed.tolist(), pick_winner(allrec), rows.tolist(), top_all.tolist(), top4.tolist()))
     finally:
         dist.destroy_process_group()

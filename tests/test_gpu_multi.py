@@ -35,11 +35,12 @@ def _rounds(learner, y, rounds=3):
     return out, np.array(learner.rel_mean), (learner.top_results(), learner.top_results(25))
 
 
-def _worker(rank, world, port, q, local_rows):
+def _worker(rank, world, port, q, local_rows, peer):
     import torch
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
+    os.environ['ITAL_B200_PEER'] = '1' if peer else '0'
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
     try:
@@ -54,13 +55,15 @@ def _worker(rank, world, port, q, local_rows):
         else:
             learner = ITAL(X, length_scale=1.0, device=rank, process_group=True)
         batches, rel_mean, tops = _rounds(learner, y)
-        q.put((rank, batches, rel_mean, tops))
+        q.put((rank, batches, rel_mean, tops, learner._peer))
+        learner.close()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('local_rows', [False, True])
-def test_two_gpus_match_one_gpu_and_oracle(local_rows):
+@pytest.mark.parametrize('local_rows,peer', [(False, True), (True, True), (False, False)])
+def test_two_gpus_match_one_gpu_and_oracle(local_rows, peer):
+    """peer: proposals exchanged by peer stores over NVLink (ital_fetch_peer); otherwise the NCCL all-gather loop."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
@@ -72,7 +75,7 @@ def test_two_gpus_match_one_gpu_and_oracle(local_rows):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, local_rows)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, local_rows, peer)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted((q.get(timeout=300) for _ in procs), key=lambda r: r[0])
@@ -81,7 +84,8 @@ def test_two_gpus_match_one_gpu_and_oracle(local_rows):
         assert p.exitcode == 0
     one_batches, one_mean, one_tops = _rounds(ITAL(X, length_scale=1.0, device=0), y)
     ora_batches, ora_mean, _ = _rounds(OracleITAL(X, length_scale=1.0), y)
-    for rank, batches, rel_mean, tops in res:
+    for rank, batches, rel_mean, tops, used_peer in res:
+        assert used_peer == peer, 'peer exchange %s' % ('not available' if peer else 'not disabled')
         want = np.lexsort((np.arange(len(rel_mean)), -rel_mean))
         assert np.array_equal(tops[0], want) and np.array_equal(tops[1], want[:25])
         assert np.array_equal(one_tops[1], np.lexsort((np.arange(len(one_mean)), -one_mean))[:25])
