@@ -381,12 +381,14 @@ def main():
             learner.top_results(100)
             tops.append(time.perf_counter() - w0)
         tt_top = float(np.median(tops)) * args.rounds
-        rounds = {'rounds': args.rounds, 'fetch_ms': tf / args.rounds * 1e3, 'update_ms': tu / args.rounds * 1e3,
+        rounds = {'rounds': args.rounds, 'fetch_ms': float(np.median(fetch_each)), 'fetch_ms_max': float(np.max(fetch_each)),
+                  'update_ms': tu / args.rounds * 1e3,
                   'top_results_100_ms': tt_top / args.rounds * 1e3,
                   'fetch_ms_each': fetch_each,
                   'update_pass_ms': float(np.median(upd_ms)), 'update_pass_GBs': float(np.median(upd_gbs)),
                   'labelled_after': n_lab + args.rounds * args.batch,
-                  'note': 'wall clock; update(%d labels) = one multi-column streaming pass + host bookkeeping; '
+                  'note': 'wall clock (fetch: median; the maximum contains the one-off growth of the projection matrix when the '
+                          'column capacity doubles); update(%d labels) = one multi-column streaming pass + host bookkeeping; '
                           'top_results(100) = device radix sort of the local means, 100 indices read back' % args.batch}
 
     used_peer = bool(getattr(learner, '_peer', False))

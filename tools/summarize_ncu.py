@@ -48,7 +48,14 @@ def launches(path):
         print('%-34s %6d %12.1f %10.1f %7.3f' % (k[:34], v[0], v[1], v[1] / v[0], v[1] / total))
     starts = [i for i, (n, _) in enumerate(seq) if n.startswith('k_score0')]
     if starts:
-        last = seq[starts[-1]:]
+        # the last fetch of the timed region (the very last one in a bench run is the stepwise fetch that collects
+        # the per-step statistics), up to and including the k_mask_all that ends it
+        first = starts[-2] if len(starts) >= 2 else starts[-1]
+        last = seq[first:]
+        for j, (n, _) in enumerate(last):
+            if n.startswith('k_mask_all'):
+                last = last[:j + 1]
+                break
         tot = sum(v for _, v in last)
         print('\n# the last fetch_unlabelled in the capture, launch by launch (%d launches, %.1f us):' % (len(last), tot))
         for n, v in last:
