@@ -96,6 +96,13 @@ struct ital_shard {
     int* xg_error_dev = nullptr;
     unsigned long long xg_epoch = 0;
     bool xg_ready = false;
+    // work of the NEXT greedy step that does not depend on the streaming pass (quadrature nodes, stage-A bound
+    // argmax) runs on a side stream while the pass runs on all SMs but one (ITAL_B200_OVERLAP=0: off)
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_commit = nullptr, ev_side = nullptr;
+    int nodes_ready_t = -1, stage_a_ready_t = -1;
+    int reserve_sms = 4;                     // SMs the pass leaves to the side stream
+    bool overlap = true, last_exhaustive = false, reserve_sm = false;
     PickSrc pick;                    // where k_record finds the local best of the running step
     bool pdl = true;                 // programmatic dependent launch between the kernels of a stream (ITAL_B200_PDL=0: off)
     bool bulk_stream = true;         // X stream staged by the bulk-copy engine (k_extend_bulk) where it applies
@@ -257,7 +264,8 @@ int launch_extend_t(ital_shard* s, int W_used, int labelled, double y, uint8_t m
         const size_t ring = (size_t)bwarps * kBulkSlots * kBulkRows * s->d_pad * sizeof(XT);
         const size_t bsmem = ring + (size_t)((W_used + 1) & ~1) * sizeof(double) +
                              (size_t)bwarps * kBulkSlots * sizeof(uint64_t);
-        const int bblocks = (int)std::min<int64_t>((units + bwarps - 1) / bwarps, (int64_t)s->num_sms);
+        const int bblocks = (int)std::max<int64_t>(1, std::min<int64_t>((units + bwarps - 1) / bwarps,
+                                                                        (int64_t)s->num_sms - (s->reserve_sm ? s->reserve_sms : 0)));
 #define ITAL_LAUNCH_BULK(NCV)                                                                                     \
     do {                                                                                                          \
         CU(cudaFuncSetAttribute(k_extend_bulk<XT, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem)); \
@@ -474,8 +482,11 @@ int prepare_nodes(ital_shard* s) {
 }
 
 // lazy rows: make the listed rows' batch projections current before they are scored
-int launch_catchup(ital_shard* s, int64_t items_hint) {
-    if (!s->lazy_rows || s->t == 0) return ITAL_OK;
+// `ahead`: streaming mode, side stream -- the listed rows get the column the concurrent streaming pass is writing
+// (same bits, so whichever store lands last is immaterial); the per-row column counts of lazy mode are not involved
+int launch_catchup(ital_shard* s, int64_t items_hint, bool ahead = false) {
+    if ((!s->lazy_rows && !ahead) || s->t == 0) return ITAL_OK;
+    uint8_t* ncol = ahead ? nullptr : s->ncol;
     const int threads = 256, warps = threads / 32;
     const int blocks = grid_for(s, std::max<int64_t>(1, items_hint), warps, 8);
     const size_t smem = (size_t)warps * (32 + s->w_cap) * sizeof(double);
@@ -483,11 +494,11 @@ int launch_catchup(ital_shard* s, int64_t items_hint) {
     if (s->x_dtype == ITAL_F32)
         pdl(k_catchup<float>, blocks, threads, smem, s)(s->counters, s->worklist, (const float*)s->X, (int)s->d,
                                                                (int)s->d_pad, s->rec_hist, record_doubles(s), s->w_cap,
-                                                               s->W, s->t, s->sqn, s->U, s->ldu, s->ncol, s->var, neg2ls2);
+                                                               s->W, s->t, s->sqn, s->U, s->ldu, ncol, s->var, neg2ls2);
     else
         pdl(k_catchup<double>, blocks, threads, smem, s)(s->counters, s->worklist, (const double*)s->X, (int)s->d,
                                                                 (int)s->d_pad, s->rec_hist, record_doubles(s), s->w_cap,
-                                                                s->W, s->t, s->sqn, s->U, s->ldu, s->ncol, s->var, neg2ls2);
+                                                                s->W, s->t, s->sqn, s->U, s->ldu, ncol, s->var, neg2ls2);
     s->launches++;
     CU(cudaGetLastError());
     return ITAL_OK;
@@ -614,6 +625,30 @@ int propose_general(ital_shard* s) {
     return ITAL_OK;
 }
 
+// Stage A of a greedy step (t >= 1, perfect user, pruned): the bound argmax over 2 x #SM strided subsets, the exact
+// scores of those rows, and from the best of them the threshold and the worklist of stage B.  None of it needs the
+// streaming pass of the previous step except the new projection column of the ~300 stage-A rows themselves, which
+// `ahead` computes on demand (k_catchup), so the whole stage can run beside the pass on the side stream.
+int stage_a(ital_shard* s, double floor_score, bool ahead) {
+    const int blocks = std::min(kArgmaxBlocks, grid_for(s, s->n, 256));
+    const int ba = std::min(kArgmaxBlocks, std::min(blocks, 2 * s->num_sms));
+    pdl(k_argmax_rows, ba, 512, 0, s)(s->n, s->gain, s->mask, s->block_best, s->counters + 4, s->counters,
+                                      s->worklist); s->launches++;
+    CU(cudaGetLastError());
+    int rc = ahead ? launch_catchup(s, ba, true) : ITAL_OK;
+    if (rc) return rc;
+    rc = launch_eval(s, ba, true);
+    if (rc) return rc;
+    // best of stage A and, in the same kernel, the threshold of stage B: every row whose bound still
+    // reaches the best exact score found so far
+    pdl(k_argmax_list, 1, 256, 0, s)(s->counters, s->worklist, s->score, s->best + 1, s->hbase_dev,
+                                     floor_score, kPruneMargin, s->thr_dev, s->counters); s->launches++;
+    pdl(k_worklist, grid_for(s, s->n, 256), 256, 0, s)(s->n, s->mask, s->gain, s->thr_dev, 0,
+                                                       s->counters, s->worklist); s->launches++;
+    CU(cudaGetLastError());
+    return ITAL_OK;
+}
+
 // The local candidates of the current greedy step -> record of the local best in DEVICE memory `rec_out`.
 // Nothing here waits for the GPU (t <= 3).
 int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_out, bool commit_here = false,
@@ -636,7 +671,9 @@ int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_o
         int rc = propose_general(s);
         if (rc) return rc;
     } else {
-        int rc = prepare_nodes(s);
+        int rc = ITAL_OK;
+        if (s->nodes_ready_t == s->t) s->n_nodes = snq::capacity_for(s->t);     // generated during the last pass
+        else rc = prepare_nodes(s);
         if (rc) return rc;
         if (exhaustive) {
             pdl(k_worklist, grid_for(s, s->n, 256), 256, 0, s)(s->n, s->mask, s->gain, s->thr_dev, 1,
@@ -653,19 +690,8 @@ int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_o
             // 2 x #SM strided subsets of the pool -- is scored first, one block per row.  (Taking the global
             // top rows by bound instead is worse: they cluster around the previous pick, whose neighbours have
             // just lost their gain; measured 882 vs 399 rows left for stage B at t = 3 on SYN-1M.)
-            const int ba = std::min(kArgmaxBlocks, std::min(blocks, 2 * s->num_sms));
-            pdl(k_argmax_rows, ba, 512, 0, s)(s->n, s->gain, s->mask, s->block_best, s->counters + 4, s->counters,
-                                                      s->worklist); s->launches++;
-            CU(cudaGetLastError());
-            rc = launch_eval(s, ba, true);
+            if (s->stage_a_ready_t != s->t) rc = stage_a(s, floor_score, false);     // else: done during the last pass
             if (rc) return rc;
-            // best of stage A and, in the same kernel, the threshold of stage B: every row whose bound still
-            // reaches the best exact score found so far
-            pdl(k_argmax_list, 1, 256, 0, s)(s->counters, s->worklist, s->score, s->best + 1, s->hbase_dev,
-                                                    floor_score, kPruneMargin, s->thr_dev, s->counters); s->launches++;
-            pdl(k_worklist, grid_for(s, s->n, 256), 256, 0, s)(s->n, s->mask, s->gain, s->thr_dev, 0,
-                                                                        s->counters, s->worklist); s->launches++;
-            CU(cudaGetLastError());
             rc = launch_eval(s, (int64_t)s->num_sms * 24, false);    // 3 resident blocks per SM (80 registers)
             if (rc) return rc;
             s->pick.count = s->counters;            // final argmax over the scored rows: done by k_record
@@ -676,6 +702,8 @@ int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_o
     }
     s->step_nodes[s->t] = (double)s->n_nodes;
     s->proposals = s->t + 1;
+    s->last_exhaustive = exhaustive != 0;
+    s->nodes_ready_t = s->stage_a_ready_t = -1;
     return make_record(s, -1, rec_out, commit_here, s->pick, pp);
 }
 
@@ -692,9 +720,35 @@ int commit_dev(ital_shard* s, const double* recs_dev, int n_records, int extend,
     }
     if (extend && !s->lazy_rows) {      // lazy rows: the projection is extended on demand by k_catchup instead
         const int col = s->W + s->t;
-        int rc = s->x_dtype == ITAL_F32 ? launch_extend_t<float>(s, col, 0, 0.0, 0)
-                                        : launch_extend_t<double>(s, col, 0, 0.0, 0);
+        // the next step's nodes and stage-A list depend on the committed batch only, not on the pass: side stream
+        const bool ahead = s->overlap && s->side && s->label_prob >= 1.0 && s->t + 1 <= 3;
+        int rc = ITAL_OK;
+        if (ahead) {
+            CU(cudaEventRecord(s->ev_commit, s->stream));
+            CU(cudaStreamWaitEvent(s->side, s->ev_commit, 0));
+            cudaStream_t main_stream = s->stream;
+            s->stream = s->side;
+            s->t += 1;
+            rc = prepare_nodes(s);
+            if (rc == ITAL_OK) {
+                s->nodes_ready_t = s->t;
+                if (!s->last_exhaustive) {
+                    rc = stage_a(s, -std::numeric_limits<double>::infinity(), true);
+                    if (rc == ITAL_OK) s->stage_a_ready_t = s->t;
+                }
+            }
+            s->t -= 1;
+            s->stream = main_stream;
+            if (rc) return rc;
+            CU(cudaGetLastError());
+            CU(cudaEventRecord(s->ev_side, s->side));
+        }
+        s->reserve_sm = ahead;
+        rc = s->x_dtype == ITAL_F32 ? launch_extend_t<float>(s, col, 0, 0.0, 0)
+                                    : launch_extend_t<double>(s, col, 0, 0.0, 0);
+        s->reserve_sm = false;
         if (rc) return rc;
+        if (ahead) CU(cudaStreamWaitEvent(s->stream, s->ev_side, 0));
     }
     s->t += 1;
     return ITAL_OK;
@@ -709,6 +763,9 @@ void peer_close(ital_shard* s) {
 
 void free_all(ital_shard* s) {
     cudaSetDevice(s->device);
+    if (s->side) cudaStreamDestroy(s->side);
+    if (s->ev_commit) cudaEventDestroy(s->ev_commit);
+    if (s->ev_side) cudaEventDestroy(s->ev_side);
     peer_close(s);
     if (s->xg_local) cudaFree(s->xg_local);
     if (s->xg_peer_dev) cudaFree(s->xg_peer_dev);
@@ -781,6 +838,8 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
     s->row_offset = row_offset;
     s->n_data = n_data;
     if (const char* env = std::getenv("ITAL_B200_PDL")) s->pdl = env[0] != '0';    // (A/B comparisons)
+    if (const char* env = std::getenv("ITAL_B200_OVERLAP")) s->overlap = env[0] != '0';
+    if (const char* env = std::getenv("ITAL_B200_RESERVE")) s->reserve_sms = std::max(1, std::min(64, atoi(env)));
     s->ldu = (n_local + 31) / 32 * 32;
     s->ls = length_scale;
     s->var = var;
@@ -809,6 +868,9 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
         CU(cudaMalloc(&s->worklist, (size_t)s->n * sizeof(int)));
         CU(cudaMalloc(&s->counters, 8 * sizeof(int)));     // [4] ticket of k_argmax_rows
         CU(cudaMemset(s->counters, 0, 8 * sizeof(int)));
+        CU(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&s->ev_commit, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s->ev_side, cudaEventDisableTiming));
         CU(cudaMalloc(&s->block_best, kArgmaxBlocks * sizeof(Best)));
         CU(cudaMalloc(&s->best, 2 * sizeof(Best)));
         CU(cudaMalloc(&s->thr_dev, sizeof(double)));
@@ -1116,6 +1178,7 @@ int ital_fetch_begin(ital_shard* s, double label_prob, double mistake_prob) {
     CU(cudaMemcpyAsync(s->hbase_dev, s->sel_host + 30, sizeof hb0, cudaMemcpyHostToDevice, s->stream));
     s->fetching = true;
     s->t = 0;
+    s->nodes_ready_t = s->stage_a_ready_t = -1;
     s->proposals = 0;
     s->label_prob = label_prob;
     s->mistake_prob = mistake_prob;
