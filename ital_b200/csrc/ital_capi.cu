@@ -101,7 +101,10 @@ struct ital_shard {
     cudaStream_t side = nullptr;
     cudaEvent_t ev_commit = nullptr, ev_side = nullptr;
     int nodes_ready_t = -1, stage_a_ready_t = -1;
-    int reserve_sms = 4;                     // SMs the pass leaves to the side stream
+    cudaEvent_t ev_win[16] = {}, ev_ext[16] = {};   // pipelined fetch: winner of step t committed / pass t finished
+    const double* ext_rec = nullptr;         // record the streaming pass reads (default: rec_in_dev)
+    bool ahead_cols = false;                 // scoring runs beside the pass that writes the newest column
+    int reserve_sms = 16;                    // SMs the pass leaves to the side stream (tools: ITAL_B200_RESERVE)
     bool overlap = true, last_exhaustive = false, reserve_sm = false;
     PickSrc pick;                    // where k_record finds the local best of the running step
     bool pdl = true;                 // programmatic dependent launch between the kernels of a stream (ITAL_B200_PDL=0: off)
@@ -252,6 +255,7 @@ int launch_extend_t(ital_shard* s, int W_used, int labelled, double y, uint8_t m
     int blocks = (int)std::min<int64_t>((units + warps - 1) / warps, (int64_t)s->num_sms * ITAL_EXTEND_MINB);
     if (blocks < 1) blocks = 1;
     const double neg2ls2 = -2.0 * (s->ls * s->ls);
+    const double* ext_rec = s->ext_rec ? s->ext_rec : s->rec_in_dev;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (s->profiling) {
         CU(cudaEventCreate(&ev0));
@@ -270,7 +274,7 @@ int launch_extend_t(ital_shard* s, int W_used, int labelled, double y, uint8_t m
     do {                                                                                                          \
         CU(cudaFuncSetAttribute(k_extend_bulk<XT, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem)); \
         pdl(k_extend_bulk<XT, NCV>, bblocks, bthreads, bsmem, s)(                                           \
-            (const XT*)s->X, s->n, (int)s->d, (int)s->d_pad, s->rec_in_dev, s->w_cap, W_used, s->sqn, s->U,       \
+            (const XT*)s->X, s->n, (int)s->d, (int)s->d_pad, ext_rec, s->w_cap, W_used, s->sqn, s->U,       \
             s->ldu, s->m, s->v, labelled, y, s->noise, s->var, neg2ls2);                                          \
     } while (0)
         if (nchunks == 4) ITAL_LAUNCH_BULK(4);
@@ -282,7 +286,7 @@ int launch_extend_t(ital_shard* s, int W_used, int labelled, double y, uint8_t m
     do {                                                                                                       \
         CU(cudaFuncSetAttribute(k_extend<XT, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
         pdl(k_extend<XT, NCV>, blocks, threads, smem, s)(                                                \
-            (const XT*)s->X, s->n, (int)s->d, (int)s->d_pad, s->rec_in_dev, s->w_cap, W_used, s->sqn, s->U,     \
+            (const XT*)s->X, s->n, (int)s->d, (int)s->d_pad, ext_rec, s->w_cap, W_used, s->sqn, s->U,     \
             s->ldu, s->m, s->v, labelled, y, s->noise, s->var, neg2ls2, s->mask, s->row_offset, mark_bits);     \
     } while (0)
     if (nchunks == 4) ITAL_LAUNCH_EXT(4);
@@ -690,7 +694,9 @@ int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_o
             // 2 x #SM strided subsets of the pool -- is scored first, one block per row.  (Taking the global
             // top rows by bound instead is worse: they cluster around the previous pick, whose neighbours have
             // just lost their gain; measured 882 vs 399 rows left for stage B at t = 3 on SYN-1M.)
-            if (s->stage_a_ready_t != s->t) rc = stage_a(s, floor_score, false);     // else: done during the last pass
+            if (s->stage_a_ready_t != s->t) rc = stage_a(s, floor_score, s->ahead_cols);  // else: done during the last pass
+            if (rc) return rc;
+            if (s->ahead_cols) rc = launch_catchup(s, (int64_t)s->num_sms * 24, true);
             if (rc) return rc;
             rc = launch_eval(s, (int64_t)s->num_sms * 24, false);    // 3 resident blocks per SM (80 registers)
             if (rc) return rc;
@@ -766,6 +772,10 @@ void free_all(ital_shard* s) {
     if (s->side) cudaStreamDestroy(s->side);
     if (s->ev_commit) cudaEventDestroy(s->ev_commit);
     if (s->ev_side) cudaEventDestroy(s->ev_side);
+    for (int k = 0; k < 16; ++k) {
+        if (s->ev_win[k]) cudaEventDestroy(s->ev_win[k]);
+        if (s->ev_ext[k]) cudaEventDestroy(s->ev_ext[k]);
+    }
     peer_close(s);
     if (s->xg_local) cudaFree(s->xg_local);
     if (s->xg_peer_dev) cudaFree(s->xg_peer_dev);
@@ -871,6 +881,10 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
         CU(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&s->ev_commit, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s->ev_side, cudaEventDisableTiming));
+        for (int k = 0; k < 16; ++k) {
+            CU(cudaEventCreateWithFlags(&s->ev_win[k], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s->ev_ext[k], cudaEventDisableTiming));
+        }
         CU(cudaMalloc(&s->block_best, kArgmaxBlocks * sizeof(Best)));
         CU(cudaMalloc(&s->best, 2 * sizeof(Best)));
         CU(cudaMalloc(&s->thr_dev, sizeof(double)));
@@ -1270,6 +1284,78 @@ int ital_fetch_end(ital_shard* s) {
     return ITAL_OK;
 }
 
+// The greedy loop of ital_fetch / ital_fetch_peer.  Streaming mode, perfect user, pruned: PIPELINED -- the passes
+// E_0, E_1, ... run back to back on the main stream, each on all SMs but `reserve_sms`; the scoring of step t + 1
+// (S_{t+1}: nodes, stage A, stage B, record / winner) runs on the side stream beside E_t.  S_{t+1} needs the batch
+// committed by S_t, the columns written by E_0 .. E_{t-1}, and the newest column only for the few hundred rows it
+// scores, which k_catchup computes on demand with the same bits as the pass; E_{t+1} needs only the record committed
+// by S_{t+1} (read from the per-step record history, which is never overwritten within a fetch).  The critical path
+// of a fetch is then S_0 + E_0 + ... + E_{k-2}: the HBM passes themselves.
+int greedy_loop(ital_shard* s, int k, int exhaustive, bool peer) {
+    const double ninf = -std::numeric_limits<double>::infinity();
+    const bool pipelined = s->overlap && s->side && !s->lazy_rows && s->label_prob >= 1.0 && !exhaustive;
+    const int64_t rl = record_doubles(s);
+    const int G = s->xg_world;
+    cudaStream_t main_stream = s->stream;
+    int rc = ITAL_OK;
+    bool last_on_side = false;
+    for (int it = 0; it < k && rc == ITAL_OK; ++it) {
+        const bool on_side = pipelined && it >= 1 && it <= 3;
+        if (on_side) {
+            CU(cudaStreamWaitEvent(s->side, s->ev_win[it - 1], 0));
+            if (it >= 2) CU(cudaStreamWaitEvent(s->side, s->ev_ext[it - 2], 0));
+            s->stream = s->side;
+            s->ahead_cols = true;
+        }
+        if (peer) {
+            const unsigned long long epoch = ++s->xg_epoch;
+            PeerPut pp;
+            pp.peer_base = s->xg_peer_dev;
+            pp.G = G;
+            pp.rank = s->xg_rank;
+            pp.slot_doubles = s->xg_slot;
+            pp.epoch = epoch;
+            rc = propose_dev(s, ninf, exhaustive, s->rec_dev, false, pp);
+            if (rc == ITAL_OK) {
+                PeerWait pw;
+                pw.flags = reinterpret_cast<const unsigned long long*>(s->xg_local);
+                pw.epoch = epoch;
+                pw.error = s->xg_error_dev;
+                const double* slots = reinterpret_cast<const double*>(s->xg_local + 256) +
+                                      (int64_t)(epoch & 1) * G * s->xg_slot;     // slots xg_slot doubles apart
+                pdl(k_pick_winner, 1, 256, 0, s)(slots, G, s->xg_slot, rl, s->t, s->W, s->rec_in_dev, s->base_m_dev,
+                                                 s->base_L_dev, s->sel_dev, s->rec_hist, s->mask, s->row_offset, s->n,
+                                                 kSelected, pw); s->launches++;
+            }
+        } else {
+            // single shard: the record kernel commits the winner itself (no separate pick)
+            rc = propose_dev(s, ninf, exhaustive, s->rec_dev, true);
+        }
+        cudaError_t e = cudaGetLastError();
+        if (rc == ITAL_OK && e == cudaSuccess && pipelined) e = cudaEventRecord(s->ev_win[it], s->stream);
+        s->stream = main_stream;
+        s->ahead_cols = false;
+        if (rc) break;
+        CU(e);
+        last_on_side = on_side;
+        if (it + 1 < k && !s->lazy_rows) {      // lazy rows: the projection is extended on demand by k_catchup instead
+            if (on_side) CU(cudaStreamWaitEvent(main_stream, s->ev_win[it], 0));
+            s->reserve_sm = pipelined && it + 1 <= 3;           // the next step is scored beside this pass
+            s->ext_rec = pipelined ? s->rec_hist + (int64_t)s->t * rl : nullptr;
+            rc = s->x_dtype == ITAL_F32 ? launch_extend_t<float>(s, s->W + s->t, 0, 0.0, 0)
+                                        : launch_extend_t<double>(s, s->W + s->t, 0, 0.0, 0);
+            s->reserve_sm = false;
+            s->ext_rec = nullptr;
+            if (rc) break;
+            if (pipelined) CU(cudaEventRecord(s->ev_ext[it], main_stream));
+        }
+        s->t += 1;
+    }
+    if (rc == ITAL_OK && last_on_side) CU(cudaStreamWaitEvent(main_stream, s->ev_win[k - 1], 0));
+    if (rc != ITAL_OK && pipelined) cudaStreamSynchronize(s->side);
+    return rc;
+}
+
 int ital_peer_export(ital_shard* s, int world, int rank, void* handle_out, int64_t handle_bytes) {
     if (!s || world < 2 || world > 32 || rank < 0 || rank >= world || !handle_out ||
         handle_bytes < (int64_t)sizeof(cudaIpcMemHandle_t))
@@ -1342,26 +1428,8 @@ int ital_fetch_peer(ital_shard* s, int k, double label_prob, double mistake_prob
         ital_fetch_end(s);
         return fail(ITAL_ESTATE, "ital_fetch_peer: records of %lld doubles exceed the exchange slots", (long long)rl);
     }
-    const int G = s->xg_world;
     // every shard enqueues the same k steps; nothing waits for the host, the shards meet in k_pick_winner
-    for (int it = 0; it < k && rc == ITAL_OK; ++it) {
-        const unsigned long long epoch = ++s->xg_epoch;
-        PeerPut pp;
-        pp.peer_base = s->xg_peer_dev;
-        pp.G = G;
-        pp.rank = s->xg_rank;
-        pp.slot_doubles = s->xg_slot;
-        pp.epoch = epoch;
-        rc = propose_dev(s, -std::numeric_limits<double>::infinity(), exhaustive, s->rec_dev, false, pp);
-        if (rc) break;
-        PeerWait pw;
-        pw.flags = reinterpret_cast<const unsigned long long*>(s->xg_local);
-        pw.epoch = epoch;
-        pw.error = s->xg_error_dev;
-        const double* slots = reinterpret_cast<const double*>(s->xg_local + 256) + (int64_t)(epoch & 1) * G * s->xg_slot;
-        // the slots are xg_slot doubles apart, the records in them rl doubles long
-        rc = commit_dev(s, slots, G, it + 1 < k, false, pw, s->xg_slot);
-    }
+    rc = greedy_loop(s, k, exhaustive, true);
     int got = 0;
     if (rc == ITAL_OK) {
         got = ital_fetch_result(s, k, out_idx, out_scores);
@@ -1389,11 +1457,7 @@ int ital_fetch(ital_shard* s, int k, double label_prob, double mistake_prob, int
     int rc = ital_fetch_begin(s, label_prob, mistake_prob);
     if (rc) return rc;
     // the whole greedy loop is enqueued without waiting for the GPU; one read-back at the end
-    for (int it = 0; it < k && rc == ITAL_OK; ++it) {
-        // single shard: the record kernel commits the winner itself (no separate pick)
-        rc = propose_dev(s, -std::numeric_limits<double>::infinity(), exhaustive, s->rec_dev, true);
-        if (rc == ITAL_OK) rc = commit_dev(s, s->rec_dev, 1, it + 1 < k, true);
-    }
+    rc = greedy_loop(s, k, exhaustive, false);
     int got = 0;
     if (rc == ITAL_OK) {
         got = ital_fetch_result(s, k, out_idx, out_scores);
