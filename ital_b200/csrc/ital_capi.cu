@@ -101,10 +101,10 @@ struct ital_shard {
     cudaStream_t side = nullptr;
     cudaEvent_t ev_commit = nullptr, ev_side = nullptr;
     int nodes_ready_t = -1, stage_a_ready_t = -1;
-    cudaEvent_t ev_win[16] = {}, ev_ext[16] = {};   // pipelined fetch: winner of step t committed / pass t finished
+    cudaEvent_t ev_win[16] = {};             // pipelined fetch: winner of step t committed
     const double* ext_rec = nullptr;         // record the streaming pass reads (default: rec_in_dev)
     bool ahead_cols = false;                 // scoring runs beside the pass that writes the newest column
-    int reserve_sms = 16;                    // SMs the pass leaves to the side stream (tools: ITAL_B200_RESERVE)
+    int reserve_sms = 4;                     // SMs the pass leaves at least to the side stream (tools: ITAL_B200_RESERVE)
     bool overlap = true, last_exhaustive = false, reserve_sm = false;
     PickSrc pick;                    // where k_record finds the local best of the running step
     bool pdl = true;                 // programmatic dependent launch between the kernels of a stream (ITAL_B200_PDL=0: off)
@@ -244,6 +244,24 @@ int ensure_width(ital_shard* s, int cols) {
     return ensure_record_buffers(s, 1);
 }
 
+// CTAs of a persistent streaming kernel whose warps own whole 32-row units in a static round-robin: the count in
+// [lo, hi] that wastes the least of the last round (with 10^6 rows and 16 warps per CTA, 148 CTAs leave 80 % of the
+// warps idle in round 14 of 14, while 140 CTAs fill 13.95 of 14 rounds; the pass is HBM-bound, not SM-bound, so
+// fewer, evenly loaded CTAs are faster).  Ties go to the larger count.
+int balanced_ctas(int64_t units, int warps_per_cta, int lo, int hi) {
+    lo = std::max(1, lo);
+    hi = std::max(lo, hi);
+    int best = hi;
+    double best_eff = -1.0;
+    for (int c = hi; c >= lo; --c) {
+        const int64_t w = (int64_t)c * warps_per_cta;
+        const int64_t rounds = (units + w - 1) / w;
+        const double eff = (double)units / (double)(rounds * w);
+        if (eff > best_eff + 1e-12) { best_eff = eff; best = c; }
+    }
+    return best;
+}
+
 template <typename XT>
 int launch_extend_t(ital_shard* s, int W_used, int labelled, double y, uint8_t mark_bits) {
     constexpr int VN = Vec<XT>::N;
@@ -268,8 +286,9 @@ int launch_extend_t(ital_shard* s, int W_used, int labelled, double y, uint8_t m
         const size_t ring = (size_t)bwarps * kBulkSlots * kBulkRows * s->d_pad * sizeof(XT);
         const size_t bsmem = ring + (size_t)((W_used + 1) & ~1) * sizeof(double) +
                              (size_t)bwarps * kBulkSlots * sizeof(uint64_t);
-        const int bblocks = (int)std::max<int64_t>(1, std::min<int64_t>((units + bwarps - 1) / bwarps,
-                                                                        (int64_t)s->num_sms - (s->reserve_sm ? s->reserve_sms : 0)));
+        const int hi = s->num_sms - (s->reserve_sm ? s->reserve_sms : 0);
+        const int bblocks = (units + bwarps - 1) / bwarps <= hi ? (int)std::max<int64_t>(1, (units + bwarps - 1) / bwarps)
+                                                                : balanced_ctas(units, bwarps, hi - 12, hi);
 #define ITAL_LAUNCH_BULK(NCV)                                                                                     \
     do {                                                                                                          \
         CU(cudaFuncSetAttribute(k_extend_bulk<XT, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem)); \
@@ -342,7 +361,8 @@ int launch_extend_multi(ital_shard* s, int q, int W_used) {
                          (size_t)bwarps * kMultiSlots * sizeof(uint64_t);
     if (s->bulk_stream && s->d_pad * sizeof(XT) == 2048 && s->d_pad / (32 * VN) == 4 && bsmem <= 227 * 1024) {
         // 2 KB rows: the TMA-staged variant, one CTA per SM
-        const int bblocks = (int)std::max<int64_t>(1, std::min<int64_t>((units + bwarps - 1) / bwarps, (int64_t)s->num_sms));
+        const int bblocks = (units + bwarps - 1) / bwarps <= s->num_sms ? (int)std::max<int64_t>(1, (units + bwarps - 1) / bwarps)
+                                                                        : balanced_ctas(units, bwarps, s->num_sms - 12, s->num_sms);
 #define ITAL_LAUNCH_BMULTI(QV)                                                                                        \
     do {                                                                                                              \
         CU(cudaFuncSetAttribute(k_extend_bulk_multi<XT, 4, QV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem)); \
@@ -486,11 +506,12 @@ int prepare_nodes(ital_shard* s) {
 }
 
 // lazy rows: make the listed rows' batch projections current before they are scored
-// `ahead`: streaming mode, side stream -- the listed rows get the column the concurrent streaming pass is writing
-// (same bits, so whichever store lands last is immaterial); the per-row column counts of lazy mode are not involved
+// `ahead`: streaming mode, side stream -- the listed rows get the batch columns they still lack from the stored
+// winner records, exactly as in lazy mode, while the streaming passes write the same columns for every row on the
+// main stream (same bits, so whichever store lands last is immaterial)
 int launch_catchup(ital_shard* s, int64_t items_hint, bool ahead = false) {
     if ((!s->lazy_rows && !ahead) || s->t == 0) return ITAL_OK;
-    uint8_t* ncol = ahead ? nullptr : s->ncol;
+    uint8_t* ncol = s->ncol;
     const int threads = 256, warps = threads / 32;
     const int blocks = grid_for(s, std::max<int64_t>(1, items_hint), warps, 8);
     const size_t smem = (size_t)warps * (32 + s->w_cap) * sizeof(double);
@@ -774,7 +795,6 @@ void free_all(ital_shard* s) {
     if (s->ev_side) cudaEventDestroy(s->ev_side);
     for (int k = 0; k < 16; ++k) {
         if (s->ev_win[k]) cudaEventDestroy(s->ev_win[k]);
-        if (s->ev_ext[k]) cudaEventDestroy(s->ev_ext[k]);
     }
     peer_close(s);
     if (s->xg_local) cudaFree(s->xg_local);
@@ -883,7 +903,6 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
         CU(cudaEventCreateWithFlags(&s->ev_side, cudaEventDisableTiming));
         for (int k = 0; k < 16; ++k) {
             CU(cudaEventCreateWithFlags(&s->ev_win[k], cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&s->ev_ext[k], cudaEventDisableTiming));
         }
         CU(cudaMalloc(&s->block_best, kArgmaxBlocks * sizeof(Best)));
         CU(cudaMalloc(&s->best, 2 * sizeof(Best)));
@@ -1185,7 +1204,7 @@ int ital_fetch_begin(ital_shard* s, double label_prob, double mistake_prob) {
         CU(cudaMalloc(&s->rec_hist, (size_t)hist_need * sizeof(double)));
         s->rec_hist_cap = hist_need;
     }
-    if (s->lazy_rows) CU(cudaMemsetAsync(s->ncol, 0, (size_t)s->n, s->stream));
+    if (s->lazy_rows || s->overlap) CU(cudaMemsetAsync(s->ncol, 0, (size_t)s->n, s->stream));
     CU(cudaMemsetAsync(s->stamp, 0, (size_t)s->n, s->stream));
     const double hb0[2] = {0.0, 1.0};                   // first step: no base, total mass 1
     memcpy(s->sel_host + 30, hb0, sizeof hb0);          // (pinned scratch at the tail of the selection mirror)
@@ -1285,12 +1304,12 @@ int ital_fetch_end(ital_shard* s) {
 }
 
 // The greedy loop of ital_fetch / ital_fetch_peer.  Streaming mode, perfect user, pruned: PIPELINED -- the passes
-// E_0, E_1, ... run back to back on the main stream, each on all SMs but `reserve_sms`; the scoring of step t + 1
-// (S_{t+1}: nodes, stage A, stage B, record / winner) runs on the side stream beside E_t.  S_{t+1} needs the batch
-// committed by S_t, the columns written by E_0 .. E_{t-1}, and the newest column only for the few hundred rows it
-// scores, which k_catchup computes on demand with the same bits as the pass; E_{t+1} needs only the record committed
-// by S_{t+1} (read from the per-step record history, which is never overwritten within a fetch).  The critical path
-// of a fetch is then S_0 + E_0 + ... + E_{k-2}: the HBM passes themselves.
+// E_0, E_1, ... run back to back on the main stream, each on all SMs but `reserve_sms`; the scoring chain
+// S_1, S_2, S_3 (nodes, stage A, stage B, record / winner of each step) runs on the side stream beside them.
+// S_{t+1} needs the batch committed by S_t and the batch columns of the few hundred rows it scores, which k_catchup
+// computes on demand from the winner records with the same bits as the passes; E_t needs only the record committed
+// by S_t (read from the per-step record history, which is never overwritten within a fetch).  The critical path of
+// a fetch is then S_0 + E_0 + ... + E_{k-2}: the HBM passes themselves.
 int greedy_loop(ital_shard* s, int k, int exhaustive, bool peer) {
     const double ninf = -std::numeric_limits<double>::infinity();
     const bool pipelined = s->overlap && s->side && !s->lazy_rows && s->label_prob >= 1.0 && !exhaustive;
@@ -1302,8 +1321,7 @@ int greedy_loop(ital_shard* s, int k, int exhaustive, bool peer) {
     for (int it = 0; it < k && rc == ITAL_OK; ++it) {
         const bool on_side = pipelined && it >= 1 && it <= 3;
         if (on_side) {
-            CU(cudaStreamWaitEvent(s->side, s->ev_win[it - 1], 0));
-            if (it >= 2) CU(cudaStreamWaitEvent(s->side, s->ev_ext[it - 2], 0));
+            if (it == 1) CU(cudaStreamWaitEvent(s->side, s->ev_win[0], 0));     // (later steps follow on the side stream)
             s->stream = s->side;
             s->ahead_cols = true;
         }
@@ -1347,7 +1365,6 @@ int greedy_loop(ital_shard* s, int k, int exhaustive, bool peer) {
             s->reserve_sm = false;
             s->ext_rec = nullptr;
             if (rc) break;
-            if (pipelined) CU(cudaEventRecord(s->ev_ext[it], main_stream));
         }
         s->t += 1;
     }

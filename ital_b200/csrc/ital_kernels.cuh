@@ -808,7 +808,7 @@ __global__ void __launch_bounds__(256) k_catchup(const int* __restrict__ count, 
     const int n_items = *count;
     for (int item = blockIdx.x * nwarp_blk + wib; item < n_items; item += gridDim.x * nwarp_blk) {
         const int64_t i = list[item];
-        const int c0 = ncol != nullptr ? ncol[i] : t - 1;     // nullptr: every row is current except the last column
+        const int c0 = ncol[i];
         if (c0 >= t) continue;
         for (int j = lane; j < W + c0; j += 32) uv[j] = U[(int64_t)j * ldu + i];
         __syncwarp();
@@ -858,7 +858,7 @@ __global__ void __launch_bounds__(256) k_catchup(const int* __restrict__ count, 
             }
             __syncwarp();
         }
-        if (lane == 0 && ncol != nullptr) ncol[i] = (uint8_t)t;
+        if (lane == 0) ncol[i] = (uint8_t)t;
         __syncwarp();
     }
 }
