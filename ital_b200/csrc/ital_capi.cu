@@ -228,7 +228,9 @@ int ensure_idx(ital_shard* s, int64_t m) {
 // grow U to hold at least `cols` projection columns
 int ensure_width(ital_shard* s, int cols) {
     if (cols <= s->w_cap) return ITAL_OK;
-    int new_cap = std::max(32, s->w_cap);
+    // 64 columns to start with: a session of up to ~50 labelled points never reallocates (growing U means a new
+    // allocation of n x cap doubles and a device-to-device copy, 3 to 600 ms at n = 10^6 depending on the allocator)
+    int new_cap = std::max(64, s->w_cap);
     while (new_cap < cols) new_cap *= 2;
     double* nu = nullptr;
     CU(cudaMalloc(&nu, (size_t)new_cap * s->ldu * sizeof(double)));
