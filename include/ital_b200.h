@@ -43,7 +43,10 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
                 int64_t row_offset, int64_t n_data, double length_scale, double var, double noise);
 int ital_destroy(ital_shard* s);
 
-/* Use this CUDA stream (a cudaStream_t) for all work of the shard; NULL = the legacy default stream. */
+/* Use this CUDA stream (a cudaStream_t) for all work of the shard; NULL = the legacy default stream.  A fetch also
+ * uses one internal non-blocking stream (the scoring of the next greedy step runs beside the streaming pass of the
+ * current one); that work is forked from and joined back into this stream with events inside the same call, so the
+ * caller sees ordinary stream order. */
 int ital_set_stream(ital_shard* s, void* cuda_stream);
 
 /* GaussianProcess.reset (ital/gp.py:132-138) + ActiveRetrievalBase.reset (ital/retrieval_base.py:48-61):
@@ -109,7 +112,7 @@ int ital_fetch(ital_shard* s, int k, double label_prob, double mistake_prob, int
 
 /* Multi-GPU fetch without NCCL in the loop.  Every shard owns an exchange buffer (one slot per shard and epoch
  * parity, one flag word per shard) that its peers map through CUDA IPC.  In a greedy step a shard stores its proposal
- * straight into the slot reserved for it in every peer's buffer (k_peer_put: peer stores over NVLink / NVSwitch,
+ * straight into the slot reserved for it in every peer's buffer (k_record: peer stores over NVLink / NVSwitch,
  * then a system-scope release of the epoch flag); the kernel that picks the winner (k_pick_winner) waits on the
  * flags of its own buffer.  This replaces the per-step all-gather of `ital_fetch_propose_dev` /
  * `ital_fetch_commit_dev` (np.argmax over the Pool's results, ital/ital.py:124-130, across GPUs).

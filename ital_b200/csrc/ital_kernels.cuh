@@ -1540,7 +1540,7 @@ __global__ void __launch_bounds__(1024) k_snq_finalize(int t, int64_t N, double 
 // np.argmax over the shards' proposals + AppendedMutualInformation.append (ital/ital.py:130-131, 561-568): choose
 // the best of G point records (score desc, global row asc), make it the record k_extend will read, and append it
 // to the batch state kept on the device (mean, Cholesky row of the batch's posterior covariance, selection list).
-struct PeerWait {                        // peer-memory exchange (k_peer_put): wait until every shard's record of this
+struct PeerWait {                        // peer-memory exchange (peer_put in k_record): wait until every shard's record of this
     const unsigned long long* flags = nullptr;   // epoch has landed in local memory; nullptr = records already there
     unsigned long long epoch = 0;
     int* error = nullptr;                // set to 1 if a peer did not deliver within the time limit
@@ -1566,7 +1566,7 @@ __global__ void __launch_bounds__(256) k_pick_winner(const double* recs, int G, 
     pdl_enter();
     __shared__ int win_s;
     if (pw.flags != nullptr) {
-        // records were stored into this GPU's memory by the peers (k_peer_put over NVLink): spin on their epoch flags,
+        // records were stored into this GPU's memory by the peers (peer_put in their k_record, over NVLink): spin on their epoch flags,
         // bounded (a peer that never delivers must not hang the GPU), and read the records past L1 (__ldcg)
         if ((int)threadIdx.x < G) {
             const unsigned long long t0 = global_ns();
@@ -1688,7 +1688,7 @@ __global__ void __launch_bounds__(256) k_record(long long row, const Best* __res
     pdl_enter();
     __shared__ Best pick_s;
     if (row < 0 && (src.block_best != nullptr || src.list != nullptr)) {
-        // the argmax that used to be a kernel of its own (k_argmax_final / the last k_argmax_list of a step)
+        // the argmax that used to be a kernel of its own (a final one-block reduction after k_score0 / k_argmax_list)
         double bs = 0.0;
         long long bi = -1;
         if (src.block_best != nullptr) {
