@@ -91,3 +91,13 @@ def test_batch_is_invariant_under_pruning_and_lazy_rows(big):
         glob = np.array(top)[tr['candidates']]
         np.testing.assert_allclose(full[t][glob], tr['scores'], rtol=1e-6, atol=1e-12)
         assert tr['argmax'] == pos[base[t]]
+
+
+def test_top_results_is_the_sorted_ranking_at_full_size(big):
+    """top_results() over 10^6 rows (245 tiles of the device radix sort): the permutation np.argsort would give, with
+    exact ties in ascending row order (retrieval_base.py:64-75)."""
+    X, assign, learner, fbs = big
+    rm = np.array(learner.rel_mean)
+    want = np.lexsort((np.arange(len(rm)), -rm))
+    assert np.array_equal(learner.top_results(), want)
+    assert np.array_equal(learner.top_results(100), want[:100])
