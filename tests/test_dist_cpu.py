@@ -94,3 +94,117 @@ def test_record_exchange_over_gloo_world2():
         assert summed[0] == (np.arange(9) + 300).tolist() and summed[1] == (np.arange(9) + 900).tolist()
         assert win == 1
         assert rows == list(range(11))
+
+
+class _StubLib(object):
+    def __getattr__(self, name):
+        return lambda *a: 0
+
+
+class _StubShard(object):
+    """Row-sharded stand-in for learner._Shard (no GPU): scores are a fixed function of the global row, so the batch
+    the sharded learner must return is known in closed form."""
+
+    def __init__(self, X, dtype_code, row_offset, n_data, length_scale, var, noise, device):
+        self.n_local, self.d = X.shape
+        self.lo, self.n_data = int(row_offset), int(n_data)
+        self.lib, self.handle = _StubLib(), 1
+        self.seen, self.selected, self.labelled = set(), set(), []
+
+    @staticmethod
+    def score(i):
+        return ((i * 7919) % 101) / 101.0
+
+    def close(self):
+        pass
+
+    def reset(self):
+        self.seen, self.selected, self.labelled = set(), set(), []
+
+    def record_doubles(self):
+        return 8 + 64 + self.d
+
+    def export_points(self, idx):
+        rec = np.zeros((len(idx), self.record_doubles()))
+        for a, g in enumerate(idx):
+            if self.lo <= g < self.lo + self.n_local:
+                rec[a, 0] = g
+                rec[a, 2] = 100.0 + g                 # non-owners contribute zeros; the sum is the owner's record
+        return rec
+
+    def add_labelled_many(self, records, y):
+        records = np.atleast_2d(records)
+        assert all(r[2] == 100.0 + r[0] for r in records), 'incomplete record after the exchange'
+        self.labelled += [int(r[0]) for r in records]
+        self.seen.update(int(r[0]) for r in records)
+
+    def mark_seen(self, idx):
+        self.seen.update(int(i) for i in idx)
+
+    def fetch_begin(self, label_prob, mistake_prob):
+        self.selected = set()
+
+    def fetch_propose(self, floor_score, exhaustive):
+        rec = np.zeros(self.record_doubles())
+        rec[0], rec[1] = -1.0, -np.inf
+        for g in range(self.lo, min(self.lo + self.n_local, self.n_data)):
+            if g in self.seen or g in self.selected:
+                continue
+            if self.score(g) > rec[1]:
+                rec[0], rec[1] = g, self.score(g)
+        return rec
+
+    def fetch_commit(self, record):
+        self.selected.add(int(record[0]))
+
+    def fetch_end(self):
+        self.selected = set()
+
+    def stats(self):
+        return np.zeros(8)
+
+    def rel_mean(self):
+        return np.arange(self.lo, self.lo + self.n_local, dtype=np.float64)
+
+
+def _learner_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from ital_b200 import learner as learner_mod
+        learner_mod._Shard = _StubShard
+        n = 23
+        X = np.arange(n * 2, dtype=np.float64).reshape(n, 2)
+        L = learner_mod.ITAL(X, length_scale=1.0, process_group=True)
+        L.update({3: 1, 20: -1, 11: 0})                # rows 3 and 20 live on different shards
+        batch = L.fetch_unlabelled(5)
+        out.put((rank, batch, L._shard.labelled, L.rel_mean.tolist(), int(L._shard.n_local), bool(L._peer)))
+        L.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_learner_host_loop_over_gloo_world2():
+    """The learner's multi-shard host logic end to end on CPU: contiguous row blocks, summed point records for the
+    labelled rows, per-step gather of the shards' proposals and the same winner everywhere (ital.py:119-132)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_learner_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(out.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    cand = [i for i in range(23) if i not in (3, 20, 11)]
+    want = sorted(cand, key=lambda i: (-_StubShard.score(i), i))[:5]
+    assert sorted(r[4] for r in res) == [11, 12]
+    for rank, batch, labelled, rel_mean, n_local, peer in res:
+        assert batch == want
+        assert labelled == [3, 20]
+        assert rel_mean == list(map(float, range(23)))
+        assert not peer                                # no CUDA, no peer exchange: the host loop is what ran
