@@ -137,13 +137,22 @@ int ital_fetch_peer(ital_shard* s, int k, double label_prob, double mistake_prob
  * prunes most rows. */
 int ital_set_lazy_rows(ital_shard* s, int on);
 
+/* The fused persistent fetch kernel (on by default; environment ITAL_B200_FUSED=0 turns it off).  With lazy rows on, a
+ * user who labels every sample (label_prob >= 1) and pruning (exhaustive == 0), ital_fetch / ital_fetch_peer run the
+ * first four greedy steps -- scores of the first step, quadrature nodes, stage A, worklist, exact scores, argmax and
+ * commit of every step, with the peer exchange if there is one -- as ONE cooperative kernel with grid-wide barriers
+ * (k_fetch_fused) instead of ~10 dependent launches per step; later steps of a longer batch continue with the
+ * multi-kernel loop.  Same batch and bit-identical scores either way. */
+int ital_set_fused(ital_shard* s, int on);
+
 /* Streaming pass variant (on by default): stage the rows through shared memory with the bulk-copy engine (TMA,
  * cp.async.bulk + mbarrier; k_extend_bulk) where the tuned shape applies (2 KB rows, e.g. d = 512 float32), else
  * coalesced register loads (k_extend).  Same results bit for bit either way. */
 int ital_set_bulk_stream(ital_shard* s, int on);
 
 /* Per-step diagnostics of the last propose: [0] candidates considered, [1] candidates scored exactly,
- * [2] quadrature nodes, [3] H(base), [4] flagged (conditional variance < 100 * noise), [5..7] reserved. */
+ * [2] quadrature nodes, [3] H(base), [4] flagged (conditional variance < 100 * noise), [5] greedy steps the fused
+ * kernel ran in the last ital_fetch / ital_fetch_peer, [6..7] reserved. */
 int ital_fetch_stats(const ital_shard* s, double* out8);
 
 /* Scores of the last propose for all local rows (NaN where not scored this step). */
@@ -173,6 +182,9 @@ int ital_predict(ital_shard* s, const double* Xt, int64_t m, double* out_mean, d
 int ital_profile_enable(ital_shard* s, int on);
 int ital_profile_read(ital_shard* s, double* ms_total, int64_t* launches, double* algorithmic_bytes);
 int64_t ital_launch_count(const ital_shard* s);
+/* Bytes the library has copied host->device / device->host since the shard was created (every copy is counted where
+ * it is issued; peer stores and NCCL traffic between GPUs are not host transfers). */
+int ital_transfer_bytes(const ital_shard* s, int64_t* h2d_bytes, int64_t* d2h_bytes);
 
 /* Host-side pieces exposed for CPU-only tests (no GPU needed) ------------------------------------------- */
 /* Shared quadrature nodes of one greedy step (see oracle/orthant.py for the rule): base mean m[t], lower

@@ -50,6 +50,7 @@ SIGNATURES = {
                                        _c_int64_p, _c_double_p]),
     'ital_set_lazy_rows': (ctypes.c_int, [_shard_p, ctypes.c_int]),
     'ital_set_bulk_stream': (ctypes.c_int, [_shard_p, ctypes.c_int]),
+    'ital_set_fused': (ctypes.c_int, [_shard_p, ctypes.c_int]),
     'ital_fetch_stats': (ctypes.c_int, [_shard_p, _c_double_p]),
     'ital_last_scores': (ctypes.c_int, [_shard_p, _c_double_p]),
     'ital_rel_mean': (ctypes.c_int, [_shard_p, _c_double_p]),
@@ -59,6 +60,7 @@ SIGNATURES = {
     'ital_profile_enable': (ctypes.c_int, [_shard_p, ctypes.c_int]),
     'ital_profile_read': (ctypes.c_int, [_shard_p, _c_double_p, _c_int64_p, _c_double_p]),
     'ital_launch_count': (ctypes.c_int64, [_shard_p]),
+    'ital_transfer_bytes': (ctypes.c_int, [_shard_p, _c_int64_p, _c_int64_p]),
     'ital_snq_nodes': (ctypes.c_int64, [ctypes.c_int, _c_double_p, _c_double_p, _c_double_p, _c_double_p,
                                         _c_int32_p, _c_double_p]),
     'ital_snq_order': (ctypes.c_int, [ctypes.c_int]),

@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libital_b200.so')
 SOURCES = ['ital_capi.cu']
-DEPENDS = ['ital_capi.cu', 'ital_kernels.cuh', 'snq_host.h', os.path.join('..', '..', 'include', 'ital_b200.h')]
+DEPENDS = ['ital_capi.cu', 'ital_kernels.cuh', 'ital_fused.cuh', 'snq_host.h', os.path.join('..', '..', 'include', 'ital_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']
 

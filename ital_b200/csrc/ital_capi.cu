@@ -17,6 +17,7 @@
 
 #include "../../include/ital_b200.h"
 #include "ital_kernels.cuh"
+#include "ital_fused.cuh"
 #include "snq_host.h"
 
 using namespace italk;
@@ -109,8 +110,17 @@ struct ital_shard {
     PickSrc pick;                    // where k_record finds the local best of the running step
     bool pdl = true;                 // programmatic dependent launch between the kernels of a stream (ITAL_B200_PDL=0: off)
     bool bulk_stream = true;         // X stream staged by the bulk-copy engine (k_extend_bulk) where it applies
-    uint8_t* ncol = nullptr;         // lazy rows: batch columns valid per row
-    uint8_t* stamp = nullptr;        // greedy step in which the row was last scored (this fetch)
+    uint32_t* tags = nullptr;        // per row: [fetch epoch | batch columns valid | step of the last exact score]
+    uint32_t epoch = 0;              // epoch of the running fetch (tags of older epochs read as empty)
+    // the fused persistent fetch kernel (k_fetch_fused): scratch, grid barrier, switches
+    Best* f_best = nullptr;
+    int* f_cnt = nullptr;
+    int* f_stage = nullptr;
+    unsigned* f_bar = nullptr;
+    unsigned f_bar_count = 0;        // arrivals on the barrier counter so far (monotone across launches)
+    bool fused = true;               // ITAL_B200_FUSED=0: multi-kernel loop only
+    bool sel_marked = false;         // rows of the running batch carry the kSelected mask bit
+    int fused_steps_last = 0;        // greedy steps the fused kernel ran in the last fetch (diagnostics)
     double* rec_hist = nullptr;      // records of the points selected in the running fetch
     uint64_t* sort_keys = nullptr;   // top_results: two key and two row buffers (ping-pong), tile histograms
     uint32_t* sort_rows = nullptr;
@@ -153,7 +163,25 @@ struct ital_shard {
     double prof_bytes = 0.0;
     int64_t launches = 0;
     double log1p_eps = std::log(1.0 + 1e-12);
+    int64_t h2d_bytes = 0, d2h_bytes = 0;      // host <-> device bytes copied by the library since creation
 };
+
+namespace {
+
+// every host <-> device copy of the library goes through these two, so that the bytes a call moves can be read back
+// (ital_transfer_bytes; bench.py reports them per fetch instead of a hand-kept constant)
+cudaError_t copy_async(ital_shard* s, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st) {
+    if (kind == cudaMemcpyHostToDevice) s->h2d_bytes += (int64_t)bytes;
+    else if (kind == cudaMemcpyDeviceToHost) s->d2h_bytes += (int64_t)bytes;
+    return cudaMemcpyAsync(dst, src, bytes, kind, st);
+}
+cudaError_t copy_sync(ital_shard* s, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+    if (kind == cudaMemcpyHostToDevice) s->h2d_bytes += (int64_t)bytes;
+    else if (kind == cudaMemcpyDeviceToHost) s->d2h_bytes += (int64_t)bytes;
+    return cudaMemcpy(dst, src, bytes, kind);
+}
+
+}  // namespace
 
 namespace {
 
@@ -235,7 +263,7 @@ int ensure_width(ital_shard* s, int cols) {
     double* nu = nullptr;
     CU(cudaMalloc(&nu, (size_t)new_cap * s->ldu * sizeof(double)));
     if (s->U) {
-        CU(cudaMemcpyAsync(nu, s->U, (size_t)s->w_cap * s->ldu * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+        CU(copy_async(s, nu, s->U, (size_t)s->w_cap * s->ldu * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
         CU(cudaStreamSynchronize(s->stream));
         CU(cudaFree(s->U));
     }
@@ -336,7 +364,7 @@ int extend_with_record(ital_shard* s, const double* rec, int col, int labelled, 
     if (rc) return rc;
     const int64_t rl = record_doubles(s);
     memcpy(s->rec_in_host, rec, (size_t)rl * sizeof(double));
-    CU(cudaMemcpyAsync(s->rec_in_dev, s->rec_in_host, (size_t)rl * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, s->rec_in_dev, s->rec_in_host, (size_t)rl * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     const uint8_t mark = mark_selected ? kSelected : (uint8_t)0;
     if (s->x_dtype == ITAL_F32) return launch_extend_t<float>(s, col, labelled, y, mark);
     return launch_extend_t<double>(s, col, labelled, y, mark);
@@ -414,6 +442,7 @@ int make_record(ital_shard* s, long long local_row, double* dst_dev, bool commit
     const double shift = local_row < 0 ? step_shift_coef(s) : 0.0;
     CommitTargets ct;
     if (commit_here) {
+        s->sel_marked = true;
         ct.rec_in = s->rec_in_dev;
         ct.rec_hist_t = s->rec_hist + (int64_t)s->t * record_doubles(s);
         ct.base_m = s->base_m_dev;
@@ -487,8 +516,8 @@ int prepare_nodes(ital_shard* s) {
     }
     // host path
     std::vector<double> bm(16), bL(16 * 16);
-    CU(cudaMemcpyAsync(bm.data(), s->base_m_dev, 16 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(bL.data(), s->base_L_dev, 256 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(copy_async(s, bm.data(), s->base_m_dev, 16 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(copy_async(s, bL.data(), s->base_L_dev, 256 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     std::vector<double> Lb((size_t)t * t, 0.0);
     for (int a = 0; a < t; ++a)
@@ -496,13 +525,13 @@ int prepare_nodes(ital_shard* s) {
     snq::Nodes nd = snq::generate(t, bm.data(), Lb.data());
     const int nb = 1 << t;
     s->n_nodes = nd.n;                      // stride of the dimension-major coordinates
-    CU(cudaMemcpyAsync(s->eta_dev, nd.eta.data(), nd.eta.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    CU(cudaMemcpyAsync(s->w_dev, nd.w.data(), nd.w.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    CU(cudaMemcpyAsync(s->masses_dev, nd.masses.data(), nb * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    CU(cudaMemcpyAsync(s->group_dev, nd.group_begin.data(), (nb + 1) * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, s->eta_dev, nd.eta.data(), nd.eta.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, s->w_dev, nd.w.data(), nd.w.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, s->masses_dev, nd.masses.data(), nb * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, s->group_dev, nd.group_begin.data(), (nb + 1) * sizeof(int), cudaMemcpyHostToDevice, s->stream));
     double hb[2] = {nd.entropy, 0.0};
     for (double mval : nd.masses) hb[1] += mval;
-    CU(cudaMemcpyAsync(s->hbase_dev, hb, sizeof hb, cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, s->hbase_dev, hb, sizeof hb, cudaMemcpyHostToDevice, s->stream));
     CU(cudaStreamSynchronize(s->stream));   // nd lives in pageable host memory
     return ITAL_OK;
 }
@@ -513,19 +542,21 @@ int prepare_nodes(ital_shard* s) {
 // main stream (same bits, so whichever store lands last is immaterial)
 int launch_catchup(ital_shard* s, int64_t items_hint, bool ahead = false) {
     if ((!s->lazy_rows && !ahead) || s->t == 0) return ITAL_OK;
-    uint8_t* ncol = s->ncol;
     const int threads = 256, warps = threads / 32;
     const int blocks = grid_for(s, std::max<int64_t>(1, items_hint), warps, 8);
-    const size_t smem = (size_t)warps * (32 + s->w_cap) * sizeof(double);
+    const size_t smem = (size_t)warps * s->w_cap * sizeof(double);
     const double neg2ls2 = -2.0 * (s->ls * s->ls);
-    if (s->x_dtype == ITAL_F32)
+    if (s->x_dtype == ITAL_F32) {
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_catchup<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         pdl(k_catchup<float>, blocks, threads, smem, s)(s->counters, s->worklist, (const float*)s->X, (int)s->d,
-                                                               (int)s->d_pad, s->rec_hist, record_doubles(s), s->w_cap,
-                                                               s->W, s->t, s->sqn, s->U, s->ldu, ncol, s->var, neg2ls2);
-    else
+                                                        (int)s->d_pad, s->rec_hist, record_doubles(s), s->w_cap,
+                                                        s->W, s->t, s->sqn, s->U, s->ldu, s->tags, s->epoch, s->var, neg2ls2);
+    } else {
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_catchup<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         pdl(k_catchup<double>, blocks, threads, smem, s)(s->counters, s->worklist, (const double*)s->X, (int)s->d,
-                                                                (int)s->d_pad, s->rec_hist, record_doubles(s), s->w_cap,
-                                                                s->W, s->t, s->sqn, s->U, s->ldu, ncol, s->var, neg2ls2);
+                                                         (int)s->d_pad, s->rec_hist, record_doubles(s), s->w_cap,
+                                                         s->W, s->t, s->sqn, s->U, s->ldu, s->tags, s->epoch, s->var, neg2ls2);
+    }
     s->launches++;
     CU(cudaGetLastError());
     return ITAL_OK;
@@ -559,7 +590,8 @@ int launch_eval(ital_shard* s, int64_t items_hint, bool block_per_candidate) {
     a.flag_var = 100.0 * s->noise;
     a.score = s->score;
     a.gain = s->gain;
-    a.stamp = s->stamp;
+    a.tags = s->tags;
+    a.epoch = s->epoch;
     a.n_flagged = s->counters + 1;
     a.n_scored = s->counters + 2;
     a.force_block = block_per_candidate ? 1 : 0;
@@ -579,8 +611,8 @@ int propose_general(ital_shard* s) {
     const int t = s->t;
     if (t > 4) return fail(ITAL_EINVAL, "label_prob < 1 supports batches of at most 5 samples");
     std::vector<double> bm(16), bL(16 * 16);
-    CU(cudaMemcpyAsync(bm.data(), s->base_m_dev, 16 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(bL.data(), s->base_L_dev, 256 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(copy_async(s, bm.data(), s->base_m_dev, 16 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(copy_async(s, bL.data(), s->base_L_dev, 256 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     std::vector<double> Lb((size_t)t * t, 0.0);
     for (int a = 0; a < t; ++a)
@@ -603,12 +635,12 @@ int propose_general(ital_shard* s) {
     if ((rc = grow((void**)&s->g_begin, &cap_b, (size_t)gs.n_groups + 1, sizeof(int)))) return rc;
     if ((rc = grow((void**)&s->g_set0, &s->g_cap_sets, (size_t)gs.n_sets + 1, sizeof(int)))) return rc;
     if ((rc = grow((void**)&s->g_lut, &s->g_cap_lut, gs.lut.size(), sizeof(int)))) return rc;
-    CU(cudaMemcpyAsync(s->g_eta, gs.eta.data(), gs.eta.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    CU(cudaMemcpyAsync(s->g_w, gs.w.data(), gs.w.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    CU(cudaMemcpyAsync(s->g_mass, gs.group_mass.data(), gs.group_mass.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    CU(cudaMemcpyAsync(s->g_begin, gs.group_begin.data(), gs.group_begin.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
-    CU(cudaMemcpyAsync(s->g_set0, gs.set_group0.data(), gs.set_group0.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
-    CU(cudaMemcpyAsync(s->g_lut, gs.lut.data(), gs.lut.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, s->g_eta, gs.eta.data(), gs.eta.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, s->g_w, gs.w.data(), gs.w.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, s->g_mass, gs.group_mass.data(), gs.group_mass.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, s->g_begin, gs.group_begin.data(), gs.group_begin.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, s->g_set0, gs.set_group0.data(), gs.set_group0.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, s->g_lut, gs.lut.data(), gs.lut.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
     CU(cudaStreamSynchronize(s->stream));       // gs lives in pageable host memory
     s->n_nodes = gs.n_nodes;
     pdl(k_worklist, grid_for(s, s->n, 256), 256, 0, s)(s->n, s->mask, s->gain, s->thr_dev, 1, s->counters, s->worklist); s->launches++;
@@ -636,7 +668,8 @@ int propose_general(ital_shard* s) {
     a.phi = s->phi_dev;
     a.score = s->score;
     a.gain = s->gain;
-    a.stamp = s->stamp;
+    a.tags = s->tags;
+    a.epoch = s->epoch;
     a.n_scored = s->counters + 2;
     if ((rc = launch_catchup(s, s->n))) return rc;
     const size_t smem = ((size_t)3 * gs.n_groups + 2 * gs.n_sets + (size_t)gs.n_groups * 24 + 8) * sizeof(double);
@@ -741,6 +774,7 @@ int commit_dev(ital_shard* s, const double* recs_dev, int n_records, int extend,
                PeerWait pw = PeerWait(), int64_t rec_stride = 0) {
     if (s->t >= kMaxBatch) return fail(ITAL_EINVAL, "batches of more than %d samples are not supported", kMaxBatch);
     if (!picked) {
+    s->sel_marked = true;
     pdl(k_pick_winner, 1, 256, 0, s)(recs_dev, n_records, rec_stride > 0 ? rec_stride : record_doubles(s),
                                             record_doubles(s), s->t, s->W, s->rec_in_dev,
                                             s->base_m_dev, s->base_L_dev, s->sel_dev, s->rec_hist, s->mask,
@@ -783,6 +817,119 @@ int commit_dev(ital_shard* s, const double* recs_dev, int n_records, int extend,
     return ITAL_OK;
 }
 
+
+// ---- the fused persistent fetch kernel (ital_fused.cuh) ------------------------------------------------------------
+int fused_chunk_cap(const ital_shard* s) {
+    const int64_t cap = snq::capacity_for(kFusedMaxSteps - 1);
+    int c = (int)((cap + s->num_sms - 1) / s->num_sms);
+    return (c + 1) & ~1;
+}
+
+// Can the running fetch start with k_fetch_fused?  Users who label every sample, pruned, projections on demand, and
+// the shapes the kernel's shared-memory staging covers.
+bool fused_applies(const ital_shard* s, int exhaustive, bool peer) {
+    if (!s->fused || !s->lazy_rows || exhaustive || s->label_prob < 1.0) return false;
+    const int C = fused_chunk_cap(s);
+    if (C > kFusedThreads) return false;
+    const FusedSmem L(record_doubles(s), s->w_cap, C);
+    if (L.total * sizeof(double) > 200 * 1024) return false;
+    if (peer && s->xg_world > kFusedThreads) return false;
+    return true;
+}
+
+// Steps 0 .. steps-1 of the greedy loop in one cooperative launch.  Nothing here waits for the GPU.
+int launch_fused(ital_shard* s, int steps, bool more_follow, bool peer) {
+    int rc = ensure_nodes(s, snq::capacity_for(kFusedMaxSteps - 1));
+    if (rc) return rc;
+    FusedArgs a = {};
+    a.X = s->X;
+    a.n = s->n;
+    a.d = (int)s->d;
+    a.d_pad = (int)s->d_pad;
+    a.row_offset = s->row_offset;
+    a.sqn = s->sqn;
+    a.m = s->m;
+    a.v = s->v;
+    a.U = s->U;
+    a.ldu = s->ldu;
+    a.mask = s->mask;
+    a.mask_rw = more_follow ? s->mask : nullptr;
+    a.sel_bits = kSelected;
+    a.gain = s->gain;
+    a.score = s->score;
+    a.tags = s->tags;
+    a.epoch = s->epoch;
+    a.W = s->W;
+    a.w_cap = s->w_cap;
+    a.k = steps;
+    a.var = s->var;
+    a.neg2ls2 = -2.0 * (s->ls * s->ls);
+    a.log1p_eps = s->log1p_eps;
+    a.flag_var = 100.0 * s->noise;
+    a.margin = kPruneMargin;
+    const int t_saved = s->t;
+    for (int t = 0; t < kFusedMaxSteps; ++t) {
+        s->t = t;
+        a.shift_coef[t] = step_shift_coef(s);
+        a.order[t] = snq::order_for(t);
+        a.node_cap[t] = snq::capacity_for(t);
+    }
+    s->t = t_saved;
+    a.gl_x = s->gl_dev;
+    a.gl_w = s->gl_dev + (snq::kMaxOrder + 1) * 64;
+    a.phi = s->phi_dev;
+    a.R = snq::kR;
+    a.w_min = snq::kWMin;
+    a.q_min = snq::kQMin;
+    a.chunk_cap = fused_chunk_cap(s);
+    a.eta = s->eta_dev;
+    a.w = s->w_dev;
+    a.orth = s->orth_dev;
+    a.masses = s->masses_dev;
+    a.hbase = s->hbase_dev;
+    a.rec_hist = s->rec_hist;
+    a.rec_len = record_doubles(s);
+    a.rec_in = s->rec_in_dev;
+    a.base_m = s->base_m_dev;
+    a.base_L = s->base_L_dev;
+    a.sel = s->sel_dev;
+    a.stats = s->stats_dev;
+    a.counters = s->counters;
+    a.blk_best = s->f_best;
+    a.blk_cnt = s->f_cnt;
+    a.stage_rows = s->f_stage;
+    a.worklist = s->worklist;
+    a.barrier = s->f_bar;
+    a.bar_base = s->f_bar_count;
+    a.want_scores = 0;
+    if (peer) {
+        a.pp.peer_base = s->xg_peer_dev;
+        a.pp.G = s->xg_world;
+        a.pp.rank = s->xg_rank;
+        a.pp.slot_doubles = s->xg_slot;
+        a.pp.epoch = s->xg_epoch + 1;
+        a.flags = reinterpret_cast<const unsigned long long*>(s->xg_local);
+        a.slots = reinterpret_cast<const double*>(s->xg_local + 256);
+        a.peer_error = s->xg_error_dev;
+        s->xg_epoch += (unsigned long long)steps;
+    }
+    const int grid = s->num_sms;
+    const FusedSmem L(a.rec_len, a.w_cap, a.chunk_cap);
+    const size_t smem = L.total * sizeof(double);
+    void* params[] = {&a};
+    const void* fn = s->x_dtype == ITAL_F32 ? (const void*)k_fetch_fused<float> : (const void*)k_fetch_fused<double>;
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kFusedThreads), params, smem, s->stream));
+    s->launches++;
+    s->f_bar_count += (unsigned)grid * (unsigned)(1 + 5 * (steps - 1));
+    if (more_follow) s->sel_marked = true;
+    s->step_nodes[0] = 1.0;
+    for (int t = 1; t < steps; ++t) s->step_nodes[t] = (double)snq::capacity_for(t);
+    s->proposals = steps;
+    s->fused_steps_last = steps;
+    return ITAL_OK;
+}
+
 void peer_close(ital_shard* s) {
     for (int g = 0; g < (int)s->xg_peer.size(); ++g)
         if (g != s->xg_rank && s->xg_peer[g]) cudaIpcCloseMemHandle(s->xg_peer[g]);
@@ -805,7 +952,7 @@ void free_all(ital_shard* s) {
     void* ptrs[] = {s->X, s->sqn, s->m, s->v, s->U, s->gain, s->score, s->mask, s->worklist, s->counters,
                     s->block_best, s->best, s->thr_dev, s->rec_dev, s->rec_in_dev, s->idx_dev, s->eta_dev,
                     s->w_dev, s->masses_dev, s->group_dev, s->orth_dev, s->eta_raw, s->w_raw, s->orth_raw, s->gl_dev, s->phi_dev, s->base_m_dev, s->base_L_dev, s->sel_dev,
-                    s->hbase_dev, s->stats_dev, s->ncol, s->stamp, s->rec_hist, s->mext_dev, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev,
+                    s->hbase_dev, s->stats_dev, s->tags, s->f_best, s->f_cnt, s->f_stage, s->f_bar, s->rec_hist, s->mext_dev, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev,
                     s->sort_keys, s->sort_rows, s->sort_hist, s->sort_out_idx, s->sort_out_val};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -835,7 +982,7 @@ int reset_model(ital_shard* s) {
     std::vector<uint8_t> mk((size_t)s->n, 0);
     for (int64_t i = 0; i < s->n; ++i)
         if (s->row_offset + i >= s->n_data) mk[i] = kNotCandidate;
-    CU(cudaMemcpyAsync(s->mask, mk.data(), (size_t)s->n, cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, s->mask, mk.data(), (size_t)s->n, cudaMemcpyHostToDevice, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     return ITAL_OK;
 }
@@ -871,6 +1018,7 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
     s->n_data = n_data;
     if (const char* env = std::getenv("ITAL_B200_PDL")) s->pdl = env[0] != '0';    // (A/B comparisons)
     if (const char* env = std::getenv("ITAL_B200_OVERLAP")) s->overlap = env[0] != '0';
+    if (const char* env = std::getenv("ITAL_B200_FUSED")) s->fused = env[0] != '0';
     if (const char* env = std::getenv("ITAL_B200_RESERVE")) s->reserve_sms = std::max(1, std::min(64, atoi(env)));
     s->ldu = (n_local + 31) / 32 * 32;
     s->ls = length_scale;
@@ -883,7 +1031,7 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
     auto body = [&]() -> int {
         CU(cudaMalloc(&s->X, (size_t)s->n * s->d_pad * esize));
         if (s->d_pad == d) {
-            CU(cudaMemcpy(s->X, X, (size_t)s->n * d * esize, cudaMemcpyHostToDevice));
+            CU(copy_sync(s, s->X, X, (size_t)s->n * d * esize, cudaMemcpyHostToDevice));
         } else {
             CU(cudaMemset(s->X, 0, (size_t)s->n * s->d_pad * esize));
             CU(cudaMemcpy2D(s->X, (size_t)s->d_pad * esize, X, (size_t)d * esize, (size_t)d * esize, (size_t)s->n,
@@ -895,8 +1043,13 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
         CU(cudaMalloc(&s->gain, (size_t)s->n * sizeof(double)));
         CU(cudaMalloc(&s->score, (size_t)s->n * sizeof(double)));
         CU(cudaMalloc(&s->mask, (size_t)s->n));
-        CU(cudaMalloc(&s->ncol, (size_t)s->n));
-        CU(cudaMalloc(&s->stamp, (size_t)s->n));
+        CU(cudaMalloc(&s->tags, (size_t)s->n * sizeof(uint32_t)));
+        CU(cudaMemset(s->tags, 0, (size_t)s->n * sizeof(uint32_t)));
+        CU(cudaMalloc(&s->f_best, (size_t)s->num_sms * kFusedTeams * sizeof(Best)));
+        CU(cudaMalloc(&s->f_cnt, (size_t)s->num_sms * sizeof(int)));
+        CU(cudaMalloc(&s->f_stage, (size_t)s->num_sms * kFusedTeams * sizeof(int)));
+        CU(cudaMalloc(&s->f_bar, sizeof(unsigned)));
+        CU(cudaMemset(s->f_bar, 0, sizeof(unsigned)));
         CU(cudaMalloc(&s->worklist, (size_t)s->n * sizeof(int)));
         CU(cudaMalloc(&s->counters, 8 * sizeof(int)));     // [4] ticket of k_argmax_rows
         CU(cudaMemset(s->counters, 0, 8 * sizeof(int)));
@@ -927,7 +1080,7 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
                 tab[k].y = std::exp(-0.5 * xk * xk) * 0.39894228040143267794;
             }
             CU(cudaMalloc(&s->phi_dev, tab.size() * sizeof(double2)));
-            CU(cudaMemcpy(s->phi_dev, tab.data(), tab.size() * sizeof(double2), cudaMemcpyHostToDevice));
+            CU(copy_sync(s, s->phi_dev, tab.data(), tab.size() * sizeof(double2), cudaMemcpyHostToDevice));
         }
         {   // Gauss-Legendre tables for every order the panel split can ask for
             const snq::GaussLegendre& G = snq::gl();
@@ -938,7 +1091,7 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
                     tab[(size_t)(snq::kMaxOrder + 1) * 64 + (size_t)nn * 64 + i] = G.w[nn][i];
                 }
             CU(cudaMalloc(&s->gl_dev, tab.size() * sizeof(double)));
-            CU(cudaMemcpy(s->gl_dev, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+            CU(copy_sync(s, s->gl_dev, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
         }
         int r = ensure_width(s, 32);
         if (r) return r;
@@ -1001,7 +1154,7 @@ int ital_export_points(ital_shard* s, int q, const int64_t* global_idx, double* 
         }
     }
     if (any) {
-        CU(cudaMemcpyAsync(s->rec_host, s->rec_dev, (size_t)q * rl * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        CU(copy_async(s, s->rec_host, s->rec_dev, (size_t)q * rl * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
         CU(cudaStreamSynchronize(s->stream));
     }
     for (int a = 0; a < q; ++a) {
@@ -1114,7 +1267,7 @@ int ital_add_labelled_many(ital_shard* s, int q, const double* records, const do
         memcpy(s->mext_host + hdr_d + (size_t)q * s->d_pad + (size_t)a * W, u[a].data(), (size_t)W * sizeof(double));
     }
     memcpy(h->tri, tri, sizeof tri);
-    CU(cudaMemcpyAsync(s->mext_dev, s->mext_host, need * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, s->mext_dev, s->mext_host, need * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     rc = s->x_dtype == ITAL_F32 ? launch_extend_multi<float>(s, q, W) : launch_extend_multi<double>(s, q, W);
     if (rc) return rc;
     // host copy of the model: Cholesky rows, beta, labelled rows (for predict)
@@ -1147,7 +1300,7 @@ int ital_mark_seen(ital_shard* s, int64_t m, const int64_t* global_idx) {
     if (loc.empty()) return ITAL_OK;
     int rc = ensure_idx(s, (int64_t)loc.size());
     if (rc) return rc;
-    CU(cudaMemcpyAsync(s->idx_dev, loc.data(), loc.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, s->idx_dev, loc.data(), loc.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream));
     pdl(k_mask_rows, grid_for(s, (int64_t)loc.size(), 256), 256, 0, s)(s->mask, s->idx_dev, (int64_t)loc.size(), kSeen); s->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s->stream));
@@ -1174,7 +1327,7 @@ int ital_restrict_candidates(ital_shard* s, int64_t m, const int64_t* global_idx
     if (!loc.empty()) {
         int rc = ensure_idx(s, (int64_t)loc.size());
         if (rc) return rc;
-        CU(cudaMemcpyAsync(s->idx_dev, loc.data(), loc.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream));
+        CU(copy_async(s, s->idx_dev, loc.data(), loc.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream));
         pdl(k_mask_clear_rows, grid_for(s, (int64_t)loc.size(), 256), 256, 0, s)(s->mask, s->idx_dev,
                                                                                        (int64_t)loc.size(), kRestricted); s->launches++;
         CU(cudaGetLastError());
@@ -1206,11 +1359,15 @@ int ital_fetch_begin(ital_shard* s, double label_prob, double mistake_prob) {
         CU(cudaMalloc(&s->rec_hist, (size_t)hist_need * sizeof(double)));
         s->rec_hist_cap = hist_need;
     }
-    if (s->lazy_rows || s->overlap) CU(cudaMemsetAsync(s->ncol, 0, (size_t)s->n, s->stream));
-    CU(cudaMemsetAsync(s->stamp, 0, (size_t)s->n, s->stream));
+    // a new epoch empties every row tag (no n-sized memset per fetch); the 24-bit epoch wraps after 16M fetches
+    if (++s->epoch >= (1u << 24)) {
+        CU(cudaMemsetAsync(s->tags, 0, (size_t)s->n * sizeof(uint32_t), s->stream));
+        s->epoch = 1;
+    }
+    s->sel_marked = false;
     const double hb0[2] = {0.0, 1.0};                   // first step: no base, total mass 1
     memcpy(s->sel_host + 30, hb0, sizeof hb0);          // (pinned scratch at the tail of the selection mirror)
-    CU(cudaMemcpyAsync(s->hbase_dev, s->sel_host + 30, sizeof hb0, cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, s->hbase_dev, s->sel_host + 30, sizeof hb0, cudaMemcpyHostToDevice, s->stream));
     s->fetching = true;
     s->t = 0;
     s->nodes_ready_t = s->stage_a_ready_t = -1;
@@ -1242,6 +1399,7 @@ static int read_step_stats(ital_shard* s, int step) {
     s->stats[1] = step == 0 ? -1.0 : (double)c[2];      // rows scored by quadrature (-1: closed form for all)
     s->stats[2] = s->step_nodes[step];
     s->stats[4] = (double)c[1];
+    s->stats[5] = (double)s->fused_steps_last;
     return ITAL_OK;
 }
 
@@ -1254,9 +1412,9 @@ int ital_fetch_propose(ital_shard* s, double floor_score, int exhaustive, double
     if (rc) return rc;
     const int64_t rl = record_doubles(s);
     double hb = 0.0;
-    CU(cudaMemcpyAsync(s->rec_host, s->rec_dev, (size_t)rl * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(s->stats_host, s->stats_dev, 16 * 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(&hb, s->hbase_dev, sizeof(double), cudaMemcpyDeviceToHost, s->stream));   // pageable: synchronous
+    CU(copy_async(s, s->rec_host, s->rec_dev, (size_t)rl * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(copy_async(s, s->stats_host, s->stats_dev, 16 * 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CU(copy_async(s, &hb, s->hbase_dev, sizeof(double), cudaMemcpyDeviceToHost, s->stream));   // pageable: synchronous
     CU(cudaStreamSynchronize(s->stream));
     memcpy(record, s->rec_host, (size_t)rl * sizeof(double));
     read_step_stats(s, step);
@@ -1272,15 +1430,15 @@ int ital_fetch_commit(ital_shard* s, const double* record) {
     // through pinned staging into the device buffer the winner is picked from (a list of one)
     const int64_t rl = record_doubles(s);
     memcpy(s->rec_in_host, record, (size_t)rl * sizeof(double));
-    CU(cudaMemcpyAsync(s->rec_dev, s->rec_in_host, (size_t)rl * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, s->rec_dev, s->rec_in_host, (size_t)rl * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     return commit_dev(s, s->rec_dev, 1, 1);
 }
 
 int ital_fetch_result(ital_shard* s, int max_out, int64_t* out_idx, double* out_scores) {
     if (!s || max_out < 0 || (max_out > 0 && !out_idx)) return fail(ITAL_EINVAL, "ital_fetch_result: bad arguments");
     CU(cudaSetDevice(s->device));
-    CU(cudaMemcpyAsync(s->sel_host, s->sel_dev, 32 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(s->stats_host, s->stats_dev, 16 * 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CU(copy_async(s, s->sel_host, s->sel_dev, 32 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(copy_async(s, s->stats_host, s->stats_dev, 16 * 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     int got = 0;
     for (int k = 0; k < s->t && k < max_out; ++k) {
@@ -1296,10 +1454,11 @@ int ital_fetch_result(ital_shard* s, int max_out, int64_t* out_idx, double* out_
 int ital_fetch_end(ital_shard* s) {
     if (!s) return fail(ITAL_EINVAL, "null shard");
     CU(cudaSetDevice(s->device));
-    if (s->fetching) {
+    if (s->fetching && s->sel_marked) {
         pdl(k_mask_all, grid_for(s, s->n, 256), 256, 0, s)(s->mask, s->n, (uint8_t)~kSelected, 0); s->launches++;
         CU(cudaGetLastError());
     }
+    s->sel_marked = false;
     s->fetching = false;
     s->t = 0;
     return ITAL_OK;
@@ -1320,7 +1479,16 @@ int greedy_loop(ital_shard* s, int k, int exhaustive, bool peer) {
     cudaStream_t main_stream = s->stream;
     int rc = ITAL_OK;
     bool last_on_side = false;
-    for (int it = 0; it < k && rc == ITAL_OK; ++it) {
+    int it0 = 0;
+    s->fused_steps_last = 0;
+    if (k > 0 && fused_applies(s, exhaustive, peer)) {
+        // the first (up to four) greedy steps in one persistent kernel; later steps continue below
+        it0 = std::min(k, kFusedMaxSteps);
+        rc = launch_fused(s, it0, k > it0, peer);
+        if (rc) return rc;
+        s->t = it0;
+    }
+    for (int it = it0; it < k && rc == ITAL_OK; ++it) {
         const bool on_side = pipelined && it >= 1 && it <= 3;
         if (on_side) {
             if (it == 1) CU(cudaStreamWaitEvent(s->side, s->ev_win[0], 0));     // (later steps follow on the side stream)
@@ -1343,6 +1511,7 @@ int greedy_loop(ital_shard* s, int k, int exhaustive, bool peer) {
                 pw.error = s->xg_error_dev;
                 const double* slots = reinterpret_cast<const double*>(s->xg_local + 256) +
                                       (int64_t)(epoch & 1) * G * s->xg_slot;     // slots xg_slot doubles apart
+                s->sel_marked = true;
                 pdl(k_pick_winner, 1, 256, 0, s)(slots, G, s->xg_slot, rl, s->t, s->W, s->rec_in_dev, s->base_m_dev,
                                                  s->base_L_dev, s->sel_dev, s->rec_hist, s->mask, s->row_offset, s->n,
                                                  kSelected, pw); s->launches++;
@@ -1420,7 +1589,7 @@ int ital_peer_connect(ital_shard* s, const void* handles, int64_t handle_bytes) 
         s->xg_peer[g] = (unsigned char*)p;
     }
     if (!s->xg_peer_dev) CU(cudaMalloc(&s->xg_peer_dev, 32 * sizeof(unsigned char*)));
-    CU(cudaMemcpy(s->xg_peer_dev, s->xg_peer.data(), (size_t)s->xg_world * sizeof(unsigned char*), cudaMemcpyHostToDevice));
+    CU(copy_sync(s, s->xg_peer_dev, s->xg_peer.data(), (size_t)s->xg_world * sizeof(unsigned char*), cudaMemcpyHostToDevice));
     s->xg_ready = true;
     return ITAL_OK;
 }
@@ -1454,7 +1623,7 @@ int ital_fetch_peer(ital_shard* s, int k, double label_prob, double mistake_prob
         got = ital_fetch_result(s, k, out_idx, out_scores);
         if (got >= 0) {
             int err = 0;
-            CU(cudaMemcpy(&err, s->xg_error_dev, sizeof err, cudaMemcpyDeviceToHost));
+            CU(copy_sync(s, &err, s->xg_error_dev, sizeof err, cudaMemcpyDeviceToHost));
             if (err) {
                 CU(cudaMemset(s->xg_error_dev, 0, sizeof(int)));
                 rc = fail(ITAL_ECUDA, "ital_fetch_peer: a shard did not deliver its proposal within 5 s");
@@ -1496,7 +1665,7 @@ int ital_fetch_stats(const ital_shard* s, double* out8) {
 
 static int copy_vec(ital_shard* s, const double* dev, double* out) {
     CU(cudaSetDevice(s->device));
-    CU(cudaMemcpyAsync(out, dev, (size_t)s->n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(copy_async(s, out, dev, (size_t)s->n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     return ITAL_OK;
 }
@@ -1506,15 +1675,15 @@ int ital_last_scores(ital_shard* s, double* out) {
     int rc = copy_vec(s, s->score, out);
     if (rc) return rc;
     if (s->proposals > 1) {      // steps after the first: only rows stamped with the step were scored in it
-        std::vector<uint8_t> st((size_t)s->n);
-        CU(cudaMemcpy(st.data(), s->stamp, (size_t)s->n, cudaMemcpyDeviceToHost));
-        const uint8_t want = (uint8_t)(s->proposals - 1);
+        std::vector<uint32_t> st((size_t)s->n);
+        CU(copy_sync(s, st.data(), s->tags, (size_t)s->n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        const uint32_t want = (s->epoch << 8) | (uint32_t)(s->proposals - 1);
         for (int64_t i = 0; i < s->n; ++i)
-            if (st[i] != want) out[i] = std::numeric_limits<double>::quiet_NaN();
+            if ((st[i] & 0xffffff0fu) != want) out[i] = std::numeric_limits<double>::quiet_NaN();
     }
     if (s->mistake_prob > 0.0 && s->proposals > 0) {    // same additive constant as the records carry
         double hb[2];
-        CU(cudaMemcpy(hb, s->hbase_dev, sizeof hb, cudaMemcpyDeviceToHost));
+        CU(copy_sync(s, hb, s->hbase_dev, sizeof hb, cudaMemcpyDeviceToHost));
         const int t_saved = s->t;
         s->t = s->proposals - 1;
         const double shift = step_shift_coef(s) * hb[1];
@@ -1569,9 +1738,9 @@ int64_t ital_top_results(ital_shard* s, int64_t k, int64_t* out_idx, double* out
     pdl(k_sort_gather, grid_for(s, k, 256), 256, 0, s)(rb[0], k, s->row_offset, s->m, s->sort_out_idx,
                                                              s->sort_out_val); s->launches++;
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(out_idx, s->sort_out_idx, (size_t)k * sizeof(int64_t), cudaMemcpyDeviceToHost, s->stream));
+    CU(copy_async(s, out_idx, s->sort_out_idx, (size_t)k * sizeof(int64_t), cudaMemcpyDeviceToHost, s->stream));
     if (out_val)
-        CU(cudaMemcpyAsync(out_val, s->sort_out_val, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        CU(copy_async(s, out_val, s->sort_out_val, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     return k;
 }
@@ -1603,25 +1772,26 @@ int ital_predict(ital_shard* s, const double* Xt, int64_t mrows, double* out_mea
         std::vector<double> LKd((size_t)nl * nl, 0.0);
         for (int a = 0; a < nl; ++a)
             for (int b = 0; b <= a; ++b) LKd[(size_t)a * nl + b] = s->LK[a][b];
-        CU(cudaMemcpy(s->lab_x_dev, s->lab_x.data(), (size_t)nl * s->d * sizeof(double), cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(s->lab_sqn_dev, s->lab_sqn.data(), (size_t)nl * sizeof(double), cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(s->w_vec_dev, w.data(), (size_t)nl * sizeof(double), cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(s->LK_dev, LKd.data(), (size_t)nl * nl * sizeof(double), cudaMemcpyHostToDevice));
+        CU(copy_sync(s, s->lab_x_dev, s->lab_x.data(), (size_t)nl * s->d * sizeof(double), cudaMemcpyHostToDevice));
+        CU(copy_sync(s, s->lab_sqn_dev, s->lab_sqn.data(), (size_t)nl * sizeof(double), cudaMemcpyHostToDevice));
+        CU(copy_sync(s, s->w_vec_dev, w.data(), (size_t)nl * sizeof(double), cudaMemcpyHostToDevice));
+        CU(copy_sync(s, s->LK_dev, LKd.data(), (size_t)nl * nl * sizeof(double), cudaMemcpyHostToDevice));
         s->lab_dev_valid = true;
     }
     double *xt_dev = nullptr, *mean_dev = nullptr, *var_dev = nullptr;
     CU(cudaMalloc(&xt_dev, (size_t)mrows * s->d * sizeof(double)));
     CU(cudaMalloc(&mean_dev, (size_t)mrows * sizeof(double)));
     if (out_var) CU(cudaMalloc(&var_dev, (size_t)mrows * sizeof(double)));
-    CU(cudaMemcpyAsync(xt_dev, Xt, (size_t)mrows * s->d * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, xt_dev, Xt, (size_t)mrows * s->d * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     const int threads = 128, wpb = threads / 32;
     const size_t smem = (size_t)wpb * nl * sizeof(double);
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_predict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pdl(k_predict, (unsigned)((mrows + wpb - 1) / wpb), threads, smem, s)(
         xt_dev, mrows, (int)s->d, s->lab_x_dev, s->lab_sqn_dev, nl, s->w_vec_dev, s->LK_dev, s->var,
         -2.0 * s->ls * s->ls, mean_dev, var_dev); s->launches++;
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(out_mean, mean_dev, (size_t)mrows * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    if (out_var) CU(cudaMemcpyAsync(out_var, var_dev, (size_t)mrows * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(copy_async(s, out_mean, mean_dev, (size_t)mrows * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (out_var) CU(copy_async(s, out_var, var_dev, (size_t)mrows * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaFree(xt_dev));
     CU(cudaFree(mean_dev));
@@ -1633,6 +1803,13 @@ int ital_set_lazy_rows(ital_shard* s, int on) {
     if (!s) return fail(ITAL_EINVAL, "null shard");
     if (s->fetching) return fail(ITAL_ESTATE, "ital_set_lazy_rows during a fetch");
     s->lazy_rows = on != 0;
+    return ITAL_OK;
+}
+
+int ital_set_fused(ital_shard* s, int on) {
+    if (!s) return fail(ITAL_EINVAL, "null shard");
+    if (s->fetching) return fail(ITAL_ESTATE, "ital_set_fused during a fetch");
+    s->fused = on != 0;
     return ITAL_OK;
 }
 
@@ -1669,6 +1846,13 @@ int ital_profile_read(ital_shard* s, double* ms_total, int64_t* launches, double
 }
 
 int64_t ital_launch_count(const ital_shard* s) { return s ? s->launches : 0; }
+
+int ital_transfer_bytes(const ital_shard* s, int64_t* h2d, int64_t* d2h) {
+    if (!s) return fail(ITAL_EINVAL, "null shard");
+    if (h2d) *h2d = s->h2d_bytes;
+    if (d2h) *d2h = s->d2h_bytes;
+    return ITAL_OK;
+}
 
 int64_t ital_snq_nodes(int t, const double* m, const double* L, double* eta, double* w, int32_t* orth, double* masses) {
     if (t < 1 || t > 10 || !m || !L) return fail(ITAL_EINVAL, "ital_snq_nodes: bad arguments");

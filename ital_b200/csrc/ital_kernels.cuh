@@ -84,6 +84,28 @@ __device__ __forceinline__ bool better(double sa, long long ia, double sb, long 
 
 __device__ __forceinline__ double phi_cdf(double x) { return 0.5 * erfc(-x * 0.70710678118654752440); }
 
+// Per-row tag of the running fetch: [fetch epoch : 24 | batch columns valid : 4 | greedy step of the last exact score : 4].
+// A tag written by an earlier fetch reads as "no batch column, not scored", so nothing has to be cleared between
+// fetches (two n-sized memsets per fetch_unlabelled otherwise).  Steps are 1..15 (the first step is closed form and
+// is never stamped), batch columns 0..15.
+__device__ __forceinline__ int tag_ncol(uint32_t tag, uint32_t epoch) {
+    return (tag >> 8) == epoch ? (int)((tag >> 4) & 15u) : 0;
+}
+__device__ __forceinline__ int tag_step(uint32_t tag, uint32_t epoch) {
+    return (tag >> 8) == epoch ? (int)(tag & 15u) : 0;
+}
+__device__ __forceinline__ uint32_t tag_with_ncol(uint32_t tag, uint32_t epoch, int ncol) {
+    return (epoch << 8) | ((uint32_t)ncol << 4) | (uint32_t)tag_step(tag, epoch);
+}
+__device__ __forceinline__ uint32_t tag_with_step(uint32_t tag, uint32_t epoch, int step) {
+    return (epoch << 8) | ((uint32_t)tag_ncol(tag, epoch) << 4) | (uint32_t)step;
+}
+
+// barrier of a team of `n` threads (a multiple of 32) inside a block; id 0 with n = blockDim.x is __syncthreads()
+__device__ __forceinline__ void team_barrier(int id, int n) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
 // Standard normal CDF from a table: (Phi, phi) on the grid x_k = -8.5 + k/32 and a 6th-order Taylor step around the
 // nearest grid point (|delta| <= 1/64; derivatives of Phi are Hermite polynomials times phi).  Absolute error below
 // 1e-15 against erfc, ~30 FP64 instructions instead of ~150; the quadrature sums need absolute, not relative accuracy.
@@ -786,81 +808,107 @@ k_extend_bulk_multi(const XT* __restrict__ X, int64_t n, int d_pad, const double
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Lazy rows: bring the batch-conditional projection of the LISTED rows up to date (columns ncol[i] .. t-1) from
+// Lazy rows: bring the batch-conditional projection of the LISTED rows up to date (columns ncol .. t-1) from
 // the stored records of the points selected so far, instead of streaming the whole pool once per greedy step
 // (k_extend).  One warp per row; the arithmetic (per-lane partial sums, order of the lane sum, fma chains of the
 // projection) is the same as in k_extend, so a row gets bit-identical entries either way.
+//
+// catchup_row: one warp, row i.  `recs` are the records of the selected points (stride rec_len; global or shared
+// memory), `uv` is a warp-private scratch of w_cap doubles.  The row's tag keeps the number of valid batch columns.
+template <typename XT>
+__device__ __forceinline__ void catchup_row(int64_t i, int lane, const XT* __restrict__ X, int d, int d_pad,
+                                            const double* recs, int64_t rec_len, int w_cap, int W, int t,
+                                            const double* __restrict__ sqn, double* U, int64_t ldu, uint32_t* tags,
+                                            uint32_t epoch, double var, double neg2ls2, double* uv) {
+    constexpr int VN = Vec<XT>::N;
+    const uint32_t tag = __ldcg(tags + i);
+    const int c0 = tag_ncol(tag, epoch);
+    if (c0 >= t) return;
+    const int nchunks = d_pad / (32 * VN);
+    const bool fixed = nchunks == 1 || nchunks == 2 || nchunks == 4;    // k_extend<XT, NC> vs k_extend<XT, 0>
+    for (int j = lane; j < W + c0; j += 32) uv[j] = __ldcg(U + (int64_t)j * ldu + i);
+    __syncwarp();
+    const XT* xrow = X + i * (int64_t)d_pad;
+    const double sq = sqn[i];
+    for (int col = c0; col < t; ++col) {
+        const double* rec = recs + (int64_t)col * rec_len;
+        const double* z = rec + 8 + w_cap;
+        double a0 = 0.0, a1 = 0.0;
+        for (int c = 0; c < nchunks; ++c) {
+            Vec<XT> x;
+            x.load(xrow + (c * 32 + lane) * VN);
+#pragma unroll
+            for (int e = 0; e < VN; e += 2) {
+                const int cc = (c * 32 + lane) * VN + e;
+                const double z0 = cc < d ? z[cc] : 0.0, z1 = cc + 1 < d ? z[cc + 1] : 0.0;
+                if (fixed) {
+                    a0 = fma(x.get(e), z0, a0);
+                    a1 = fma(x.get(e + 1), z1, a1);
+                } else {
+                    a0 = fma(x.get(e), z0, a0);
+                    a0 = fma(x.get(e + 1), z1, a0);
+                }
+            }
+        }
+        double dot = fixed ? a0 + a1 : a0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);   // = tree_sum32 order
+        if (lane == 0) {
+            const double kv = var * exp((sq + rec[4] - 2.0 * dot) / neg2ls2);
+            const double* ur = rec + 8;
+            const int Wc = W + col;
+            double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+            int j = 0;
+            for (; j + 4 <= Wc; j += 4) {
+                p0 = fma(uv[j + 0], ur[j + 0], p0);
+                p1 = fma(uv[j + 1], ur[j + 1], p1);
+                p2 = fma(uv[j + 2], ur[j + 2], p2);
+                p3 = fma(uv[j + 3], ur[j + 3], p3);
+            }
+            for (; j < Wc; ++j) p0 = fma(uv[j], ur[j], p0);
+            const double piv = sqrt(fmax(rec[3], 1e-300));
+            const double e_new = (kv - ((p0 + p1) + (p2 + p3))) / piv;
+            uv[Wc] = e_new;
+            U[(int64_t)Wc * ldu + i] = e_new;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) tags[i] = tag_with_ncol(tag, epoch, t);
+    __syncwarp();
+}
+
 template <typename XT>
 __global__ void __launch_bounds__(256) k_catchup(const int* __restrict__ count, const int* __restrict__ list,
                                                  const XT* __restrict__ X, int d, int d_pad,
                                                  const double* __restrict__ rec_hist, int64_t rec_len, int w_cap,
                                                  int W, int t, const double* __restrict__ sqn,
-                                                 double* __restrict__ U, int64_t ldu, uint8_t* __restrict__ ncol,
+                                                 double* U, int64_t ldu, uint32_t* tags, uint32_t epoch,
                                                  double var, double neg2ls2) {
     pdl_enter();
-    constexpr int VN = Vec<XT>::N;
     extern __shared__ double csm[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarp_blk = blockDim.x >> 5;
-    double* part = csm + (size_t)wib * (32 + w_cap);   // [32]
-    double* uv = part + 32;                             // [w_cap] projection entries of the row
-    const int nchunks = d_pad / (32 * VN);
-    const bool fixed = nchunks == 1 || nchunks == 2 || nchunks == 4;    // k_extend<XT, NC> vs k_extend<XT, 0>
+    double* uv = csm + (size_t)wib * w_cap;            // [w_cap] projection entries of the row
     const int n_items = *count;
-    for (int item = blockIdx.x * nwarp_blk + wib; item < n_items; item += gridDim.x * nwarp_blk) {
-        const int64_t i = list[item];
-        const int c0 = ncol[i];
-        if (c0 >= t) continue;
-        for (int j = lane; j < W + c0; j += 32) uv[j] = U[(int64_t)j * ldu + i];
-        __syncwarp();
-        const XT* xrow = X + i * (int64_t)d_pad;
-        const double sq = sqn[i];
-        for (int col = c0; col < t; ++col) {
-            const double* rec = rec_hist + (int64_t)col * rec_len;
-            const double* z = rec + 8 + w_cap;
-            double a0 = 0.0, a1 = 0.0;
-            for (int c = 0; c < nchunks; ++c) {
-                Vec<XT> x;
-                x.load(xrow + (c * 32 + lane) * VN);
-#pragma unroll
-                for (int e = 0; e < VN; e += 2) {
-                    const int cc = (c * 32 + lane) * VN + e;
-                    const double z0 = cc < d ? z[cc] : 0.0, z1 = cc + 1 < d ? z[cc + 1] : 0.0;
-                    if (fixed) {
-                        a0 = fma(x.get(e), z0, a0);
-                        a1 = fma(x.get(e + 1), z1, a1);
-                    } else {
-                        a0 = fma(x.get(e), z0, a0);
-                        a0 = fma(x.get(e + 1), z1, a0);
-                    }
-                }
-            }
-            double dot = fixed ? a0 + a1 : a0;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);   // = tree_sum32 order
-            double e_new = 0.0;
-            if (lane == 0) {
-                const double kv = var * exp((sq + rec[4] - 2.0 * dot) / neg2ls2);
-                const double* ur = rec + 8;
-                const int Wc = W + col;
-                double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
-                int j = 0;
-                for (; j + 4 <= Wc; j += 4) {
-                    p0 = fma(uv[j + 0], ur[j + 0], p0);
-                    p1 = fma(uv[j + 1], ur[j + 1], p1);
-                    p2 = fma(uv[j + 2], ur[j + 2], p2);
-                    p3 = fma(uv[j + 3], ur[j + 3], p3);
-                }
-                for (; j < Wc; ++j) p0 = fma(uv[j], ur[j], p0);
-                const double piv = sqrt(fmax(rec[3], 1e-300));
-                e_new = (kv - ((p0 + p1) + (p2 + p3))) / piv;
-                uv[Wc] = e_new;
-                U[(int64_t)Wc * ldu + i] = e_new;
-            }
-            __syncwarp();
-        }
-        if (lane == 0) ncol[i] = (uint8_t)t;
-        __syncwarp();
+    for (int item = blockIdx.x * nwarp_blk + wib; item < n_items; item += gridDim.x * nwarp_blk)
+        catchup_row<XT>(list[item], lane, X, d, d_pad, rec_hist, rec_len, w_cap, W, t, sqn, U, ldu, tags, epoch, var,
+                        neg2ls2, uv);
+}
+
+// Score of a single sample (first greedy step): MI of one variable in closed form (ital/ital.py:364-369, 183-224).
+__device__ __forceinline__ double score0_value(double mean, double var_raw, double log1p_eps, double scale,
+                                               const double2* __restrict__ phi) {
+    const double var_i = fmax(var_raw, 0.0);             // predict_stored(cov_mode='diag') clamps (gp.py:229)
+    const double sd = sqrt(var_i);
+    double p1, p0;
+    if (sd > 0.0) {
+        const double zz = mean / sd;
+        p1 = phi_tab(phi, zz);
+        p0 = phi_tab(phi, -zz);
+    } else {
+        p1 = mean > 0.0 ? 1.0 : 0.0;
+        p0 = 1.0 - p1;
     }
+    return scale * (mi_term(p0, log1p_eps) + mi_term(p1, log1p_eps));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -894,18 +942,7 @@ __global__ void __launch_bounds__(256) k_score0(int64_t n, const double* __restr
             if (i >= n) break;
             double s = nan("");
             if (mk[u] == 0) {
-                const double var_i = fmax(vv[u], 0.0);   // predict_stored(cov_mode='diag') clamps (gp.py:229)
-                const double sd = sqrt(var_i);
-                double p1, p0;
-                if (sd > 0.0) {
-                    const double zz = mm[u] / sd;
-                    p1 = phi_tab(phi, zz);
-                    p0 = phi_tab(phi, -zz);
-                } else {
-                    p1 = mm[u] > 0.0 ? 1.0 : 0.0;
-                    p0 = 1.0 - p1;
-                }
-                s = scale * (mi_term(p0, log1p_eps) + mi_term(p1, log1p_eps));
+                s = score0_value(mm[u], vv[u], log1p_eps, scale, phi);
                 gain[i] = s;
                 if (better(s, i, bs, bi)) { bs = s; bi = i; }
             }
@@ -1084,7 +1121,8 @@ struct EvalArgs {
     double flag_var;
     double* score;
     double* gain;
-    uint8_t* stamp;             // stamp[i] == t: row i has been scored in this greedy step
+    uint32_t* tags;             // tag_step(tags[i]) == t: row i has been scored in this greedy step
+    uint32_t epoch;
     int* n_flagged;
     int* n_scored;
     int force_block;
@@ -1095,6 +1133,104 @@ __device__ __forceinline__ int eval_team_size(int n_items, int force_block) {
     // a warp per candidate when there are enough candidates to keep every warp busy, otherwise the whole block
     // works on one candidate (the node loop is latency-bound for a lone warp)
     return (force_block || n_items < (int)(gridDim.x * (blockDim.x >> 5))) ? (int)blockDim.x : 32;
+}
+
+// Exact score of candidate i by a team of TPC threads (32, or 256 = eight warps synchronising on barrier `bar_id`)
+// with the nodes of k_snq_generate<T> (generation order, orthant id per node).  Thread `tid_team` takes the nodes
+// tid_team + TPC * (4 j + u); the partial sums are reduced by an xor butterfly inside every warp and then warp by
+// warp in ascending order, so a row's score depends on the team size only.  `red` holds 8 * 2^T doubles per team.
+// masses / h_base may live in shared or global memory.  Returns after the row's score, gain and tag are written.
+template <int T>
+__device__ __forceinline__ void eval_candidate(const EvalArgs& a, int64_t i, int tid_team, int TPC, int bar_id,
+                                               double* red, int64_t N, int64_t NK, const double* masses,
+                                               double h_base) {
+    constexpr int NB = 1 << T;
+    double l[T];
+    double s2 = a.v[i];
+#pragma unroll
+    for (int j = 0; j < T; ++j) {
+        l[j] = __ldcg(a.U + (int64_t)(a.W0 + j) * a.ldu + i);
+        s2 = fma(-l[j], l[j], s2);
+    }
+    const double mi = a.m[i];
+    const double s = s2 > 0.0 ? sqrt(s2) : 0.0;
+    const double inv_s = s > 0.0 ? 1.0 / s : 0.0;
+    double acc[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) acc[b] = 0.0;
+    // four nodes per thread and trip: independent erfc chains hide the FP64 latency
+    for (int64_t q = tid_team; q < NK; q += 4 * TPC) {
+        double num[4], ww[4];
+        int ob[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t qq = q + (int64_t)u * TPC;
+            const bool ok = qq < NK;
+            ww[u] = ok ? a.w[qq] : 0.0;
+            ob[u] = ok ? a.orth[qq] : 0;
+            num[u] = mi;
+#pragma unroll
+            for (int j = 0; j < T; ++j) num[u] = fma(l[j], ok ? a.eta[(int64_t)j * N + qq] : 0.0, num[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double cdf = s > 0.0 ? phi_tab(a.phi, num[u] * inv_s) : (num[u] > 0.0 ? 1.0 : 0.0);
+            const double term = ww[u] * cdf;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) acc[b] += (ob[u] == b) ? term : 0.0;
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], o);
+    }
+    if (TPC > 32) {
+        if ((tid_team & 31) == 0) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) red[b * 8 + (tid_team >> 5)] = acc[b];
+        }
+        team_barrier(bar_id, TPC);
+    }
+    if (tid_team == 0) {
+        double sc = 0.0;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            double p_plus = acc[b];
+            if (TPC > 32) {
+                p_plus = 0.0;
+                for (int k = 0; k < TPC / 32; ++k) p_plus += red[b * 8 + k];
+            }
+            const double p_minus = fmax(masses[b] - p_plus, 0.0);
+            sc += mi_term(p_plus, a.log1p_eps) + mi_term(p_minus, a.log1p_eps);
+        }
+        a.tags[i] = tag_with_step(__ldcg(a.tags + i), a.epoch, a.t);
+        a.score[i] = sc;
+        a.gain[i] = sc - h_base;
+        atomicAdd(a.n_scored, 1);
+        if (s2 < a.flag_var) atomicAdd(a.n_flagged, 1);
+    }
+    if (TPC > 32) team_barrier(bar_id, TPC);            // red and the tag are free again
+}
+
+template <int T>
+__global__ void __launch_bounds__(256) k_eval(EvalArgs a) {
+    pdl_enter();
+    constexpr int NB = 1 << T;
+    const int n_items = *a.count;
+    const int TPC = eval_team_size(n_items, a.force_block);
+    const int tid_team = threadIdx.x % TPC;
+    const int team_global = (blockIdx.x * blockDim.x + threadIdx.x) / TPC;
+    const int teams_total = (gridDim.x * blockDim.x) / TPC;
+    const int64_t N = a.n_nodes;
+    const int64_t NK = *a.n_kept;
+    const double h_base = *a.h_base;
+    __shared__ double red[8 * NB];
+    for (int item = team_global; item < n_items; item += teams_total) {
+        const int64_t i = a.list[item];
+        if (tag_step(a.tags[i], a.epoch) == a.t) continue;  // scored earlier in this step (team-uniform)
+        eval_candidate<T>(a, i, tid_team, TPC, 0, red, N, NK, a.masses, h_base);
+    }
 }
 
 __device__ __forceinline__ double team_sum(double acc, int TPC, double* red) {
@@ -1110,74 +1246,6 @@ __device__ __forceinline__ double team_sum(double acc, int TPC, double* red) {
     return acc;
 }
 
-template <int T>
-__global__ void __launch_bounds__(256) k_eval(EvalArgs a) {
-    pdl_enter();
-    constexpr int NB = 1 << T;
-    const int n_items = *a.count;
-    const int TPC = eval_team_size(n_items, a.force_block);
-    const int tid_team = threadIdx.x % TPC;
-    const int team_global = (blockIdx.x * blockDim.x + threadIdx.x) / TPC;
-    const int teams_total = (gridDim.x * blockDim.x) / TPC;
-    const int64_t N = a.n_nodes;
-    const int64_t NK = *a.n_kept;
-    __shared__ double red[8];
-    for (int item = team_global; item < n_items; item += teams_total) {
-        const int64_t i = a.list[item];
-        if (a.stamp[i] == (uint8_t)a.t) continue;       // scored earlier in this step (team-uniform)
-        double l[T];
-        double s2 = a.v[i];
-#pragma unroll
-        for (int j = 0; j < T; ++j) {
-            l[j] = a.U[(int64_t)(a.W0 + j) * a.ldu + i];
-            s2 = fma(-l[j], l[j], s2);
-        }
-        const double mi = a.m[i];
-        const double s = s2 > 0.0 ? sqrt(s2) : 0.0;
-        const double inv_s = s > 0.0 ? 1.0 / s : 0.0;
-        double acc[NB];
-#pragma unroll
-        for (int b = 0; b < NB; ++b) acc[b] = 0.0;
-        // four nodes per thread and trip: independent erfc chains hide the FP64 latency
-        for (int64_t q = tid_team; q < NK; q += 4 * TPC) {
-            double num[4], ww[4];
-            int ob[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int64_t qq = q + (int64_t)u * TPC;
-                const bool ok = qq < NK;
-                ww[u] = ok ? a.w[qq] : 0.0;
-                ob[u] = ok ? a.orth[qq] : 0;
-                num[u] = mi;
-#pragma unroll
-                for (int j = 0; j < T; ++j) num[u] = fma(l[j], ok ? a.eta[(int64_t)j * N + qq] : 0.0, num[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const double cdf = s > 0.0 ? phi_tab(a.phi, num[u] * inv_s) : (num[u] > 0.0 ? 1.0 : 0.0);
-                const double term = ww[u] * cdf;
-#pragma unroll
-                for (int b = 0; b < NB; ++b) acc[b] += (ob[u] == b) ? term : 0.0;
-            }
-        }
-        double sc = 0.0;
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            const double p_plus = team_sum(acc[b], TPC, red);
-            const double p_minus = fmax(a.masses[b] - p_plus, 0.0);
-            sc += mi_term(p_plus, a.log1p_eps) + mi_term(p_minus, a.log1p_eps);
-        }
-        if (TPC > 32) __syncthreads();                  // every thread has read stamp[i] before it is written
-        if (tid_team == 0) {
-            a.stamp[i] = (uint8_t)a.t;
-            a.score[i] = sc;
-            a.gain[i] = sc - *a.h_base;
-            atomicAdd(a.n_scored, 1);
-            if (s2 < a.flag_var) atomicAdd(a.n_flagged, 1);
-        }
-    }
-}
-
 __global__ void __launch_bounds__(256) k_eval_sorted(EvalArgs a) {
     pdl_enter();
     constexpr int MAXT = 10;
@@ -1191,7 +1259,7 @@ __global__ void __launch_bounds__(256) k_eval_sorted(EvalArgs a) {
     __shared__ double red[8];
     for (int item = team_global; item < n_items; item += teams_total) {
         const int64_t i = a.list[item];
-        if (a.stamp[i] == (uint8_t)a.t) continue;
+        if (tag_step(a.tags[i], a.epoch) == a.t) continue;
         double l[MAXT];
         double s2 = a.v[i];
 #pragma unroll
@@ -1224,7 +1292,7 @@ __global__ void __launch_bounds__(256) k_eval_sorted(EvalArgs a) {
         }
         if (TPC > 32) __syncthreads();
         if (tid_team == 0) {
-            a.stamp[i] = (uint8_t)a.t;
+            a.tags[i] = tag_with_step(a.tags[i], a.epoch, a.t);
             a.score[i] = sc;
             a.gain[i] = sc - *a.h_base;
             atomicAdd(a.n_scored, 1);
@@ -1264,7 +1332,8 @@ struct GeneralArgs {
     const double2* phi;
     double* score;
     double* gain;
-    uint8_t* stamp;
+    uint32_t* tags;
+    uint32_t epoch;
     int* n_scored;
 };
 
@@ -1377,7 +1446,7 @@ __global__ void __launch_bounds__(256) k_eval_general(GeneralArgs a) {
         if (threadIdx.x == 0) {
             double tot = 0.0;
             for (int k = 0; k < 8; ++k) tot += red[k];
-            a.stamp[i] = (uint8_t)a.t;
+            a.tags[i] = tag_with_step(a.tags[i], a.epoch, a.t);
             a.score[i] = tot;
             a.gain[i] = tot;
             atomicAdd(a.n_scored, 1);
@@ -1389,19 +1458,13 @@ __global__ void __launch_bounds__(256) k_eval_general(GeneralArgs a) {
 // ---- shared quadrature nodes on the device (same rule as csrc/snq_host.h / oracle/orthant.py) ----------------
 constexpr int kGlStride = 64;            // Gauss-Legendre tables: rule n at [n * 64 .. n * 64 + n)
 
-// One thread per node; node index = sum_j digit_j (2q)^(t-1-j).  Every thread recomputes the boundary of each
+// Node k of the rule; node index = sum_j digit_j (2q)^(t-1-j).  Every thread recomputes the boundary of each
 // dimension from its own prefix of coordinates (a handful of flops) instead of communicating.
 template <int T>
-__global__ void __launch_bounds__(256) k_snq_generate(int q, double R, int q_min, const double* __restrict__ base_m,
-                                                      const double* __restrict__ base_L,
-                                                      const double* __restrict__ gl_x, const double* __restrict__ gl_w,
-                                                      int64_t N, double* __restrict__ eta, double* __restrict__ w,
-                                                      int* __restrict__ orth) {
-    pdl_enter();
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= N) return;
+__device__ __forceinline__ void snq_node(int64_t k, int64_t N, int q, double R, int q_min, const double* base_m,
+                                         const double* base_L, const double* __restrict__ gl_x,
+                                         const double* __restrict__ gl_w, double* e, double& wt_out, int& orth_out) {
     const int two_q = 2 * q;
-    double e[T];
     double wt = 1.0;
     int ob = 0;
     int64_t rem = k, stride = N;
@@ -1433,10 +1496,68 @@ __global__ void __launch_bounds__(256) k_snq_generate(int q, double R, int q_min
         wg *= exp(-0.5 * x * x) / 2.50662827463100050242;      // standard normal density
         e[j] = x;
         wt *= wg;
-        eta[(int64_t)j * N + k] = x;
     }
+    wt_out = wt;
+    orth_out = ob;
+}
+
+template <int T>
+__global__ void __launch_bounds__(256) k_snq_generate(int q, double R, int q_min, const double* __restrict__ base_m,
+                                                      const double* __restrict__ base_L,
+                                                      const double* __restrict__ gl_x, const double* __restrict__ gl_w,
+                                                      int64_t N, double* __restrict__ eta, double* __restrict__ w,
+                                                      int* __restrict__ orth) {
+    pdl_enter();
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    double e[T];
+    double wt;
+    int ob;
+    snq_node<T>(k, N, q, R, q_min, base_m, base_L, gl_x, gl_w, e, wt, ob);
+#pragma unroll
+    for (int j = 0; j < T; ++j) eta[(int64_t)j * N + k] = e[j];
     w[k] = wt;
     orth[k] = ob;
+}
+
+// Base orthant probabilities P_b = sum of the kept weights per orthant, the score of the base alone and the total
+// mass, in a fixed order: threads 0..255 of the block take the nodes k, k + 256, ...; xor butterfly inside every
+// warp; the eight warp partials are added in ascending order.  Every thread of the block must call it (it contains
+// block barriers); `part` is 8 x 8 doubles of shared memory; thread 0 writes masses[0 .. 2^t), h_out[0] = H(base),
+// h_out[1] = total mass (shared or global memory).  t <= 3.
+__device__ __forceinline__ void snq_masses_block(int t, int kept, const double* w, const int* orth, double log1p_eps,
+                                                 double (*part)[8], double* masses, double* h_out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 256) {
+        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int k = threadIdx.x; k < kept; k += 256) {
+            const int ob = orth[k];
+            const double wk = w[k];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) acc[b] += (ob == b) ? wk : 0.0;
+        }
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], o);
+            if (lane == 0) part[warp][b] = acc[b];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nb = 1 << t;
+        double h = 0.0, tot = 0.0;
+        for (int b = 0; b < nb; ++b) {
+            double p = 0.0;
+            for (int k = 0; k < 8; ++k) p += part[k][b];
+            masses[b] = p;
+            h += mi_term(p, log1p_eps);
+            tot += p;
+        }
+        h_out[0] = h;
+        h_out[1] = tot;                                 // total mass (1 up to quadrature error)
+    }
+    __syncthreads();
 }
 
 // Drops the nodes whose weight is below w_min (stable, out of place: about half of the nodes at t = 3 carry a
@@ -1451,7 +1572,7 @@ __global__ void __launch_bounds__(1024) k_snq_finalize(int t, int64_t N, double 
                                                        double* __restrict__ h_base, int* __restrict__ n_kept) {
     pdl_enter();
     __shared__ int warp_tot[32];
-    __shared__ double part[32][8];
+    __shared__ double part[8][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     // every warp owns a contiguous range of nodes and walks it 32 at a time (coalesced); ballots give the stable
     // order inside the warp, one scan over the warp totals the offsets between warps.  All loads of a pass are
@@ -1508,33 +1629,7 @@ __global__ void __launch_bounds__(1024) k_snq_finalize(int t, int64_t N, double 
     }
     if (threadIdx.x == 0) *n_kept = kept;
     __syncthreads();
-    const int nb = 1 << t;                              // t <= 3 here
-    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int k = threadIdx.x; k < kept; k += blockDim.x) {
-        const int ob = orth[k];
-        const double wk = w[k];
-#pragma unroll
-        for (int b = 0; b < 8; ++b) acc[b] += (ob == b) ? wk : 0.0;
-    }
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], o);
-        if (lane == 0) part[warp][b] = acc[b];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double h = 0.0, tot = 0.0;
-        for (int b = 0; b < nb; ++b) {
-            double p = 0.0;
-            for (int k = 0; k < nwarps; ++k) p += part[k][b];
-            masses[b] = p;
-            h += mi_term(p, log1p_eps);
-            tot += p;
-        }
-        h_base[0] = h;
-        h_base[1] = tot;                                // total mass (1 up to quadrature error)
-    }
+    snq_masses_block(t, kept, w, orth, log1p_eps, part, masses, h_base);     // t <= 3 here
 }
 
 // np.argmax over the shards' proposals + AppendedMutualInformation.append (ital/ital.py:130-131, 561-568): choose

@@ -231,7 +231,8 @@ class ITAL(object):
     `local_rows=(first_row, n_total)` declares that `data` holds only this process's contiguous block of a
     pool of n_total rows (for pools too large to replicate on every host process; no `queries` then);
     `lazy_rows` extends the batch-conditional projections only for the rows that get scored instead of streaming
-    the whole pool once per greedy step (same batch, same scores bit for bit; see include/ital_b200.h);
+    the whole pool once per greedy step (same batch, same scores bit for bit; see include/ital_b200.h); the default
+    (None) does so whenever the lazy-greedy bound prunes, i.e. for users who label every sample unless `exhaustive`;
     `bulk_stream` (default on; environment ITAL_B200_BULK=0 turns it off) stages the streaming pass through shared
     memory with the bulk-copy engine where the tuned shape applies (2 KB rows), else coalesced register loads.
     """
@@ -240,7 +241,7 @@ class ITAL(object):
                  label_prob=1.0, mistake_prob=0.0, top_candidates=None, change_estimation_subset=0,
                  clip_cov=0, label_estimation='mean', monte_carlo_num_rel=None, monte_carlo_num_fb=None,
                  parallelized=True, device=None, storage='auto', process_group=None, exhaustive=False,
-                 local_rows=None, lazy_rows=False, bulk_stream=None):
+                 local_rows=None, lazy_rows=None, bulk_stream=None):
         self.length_scale, self.var, self.noise = length_scale, var, noise
         self.label_prob, self.mistake_prob = label_prob, mistake_prob
         self.top_candidates = top_candidates
@@ -250,9 +251,10 @@ class ITAL(object):
         self.monte_carlo_num_rel, self.monte_carlo_num_fb = monte_carlo_num_rel, monte_carlo_num_fb
         self.parallelized = parallelized            # accepted for compatibility; the GPU is the parallelism
         self.exhaustive = exhaustive
-        self._lazy_rows = bool(lazy_rows)
+        self._lazy_rows = None if lazy_rows is None else bool(lazy_rows)
         import os
         self._bulk_stream = os.environ.get('ITAL_B200_BULK', '1') == '1' if bulk_stream is None else bool(bulk_stream)
+        self._fused = os.environ.get('ITAL_B200_FUSED', '1') == '1'
         self._storage = storage
         self._device = device
         self._local_rows = local_rows
@@ -261,6 +263,7 @@ class ITAL(object):
         self._shard = None
         self._peer = False
         self.last_fetch_stats = []
+        self.last_fused_steps = 0
         self.fit(data, queries)
 
     @property
@@ -269,9 +272,27 @@ class ITAL(object):
 
     @lazy_rows.setter
     def lazy_rows(self, on):
-        self._lazy_rows = bool(on)
+        self._lazy_rows = None if on is None else bool(on)
+
+    def _apply_lazy_rows(self):
+        """None (default) = on demand whenever the lazy-greedy bound prunes (users who label every sample, not
+        `exhaustive`): a greedy step then scores a few hundred rows and a pass over the whole pool per step would feed
+        nothing; otherwise the streaming pass keeps every row's projection current (every row is scored)."""
+        on = self._lazy_rows
+        if on is None:
+            on = self.label_prob >= 1 and not self.exhaustive
+        _capi.check(self._shard.lib.ital_set_lazy_rows(self._shard.handle, int(bool(on))))
+        return bool(on)
+
+    @property
+    def fused(self):
+        return self._fused
+
+    @fused.setter
+    def fused(self, on):
+        self._fused = bool(on)
         if self._shard is not None:
-            _capi.check(self._shard.lib.ital_set_lazy_rows(self._shard.handle, int(self._lazy_rows)))
+            _capi.check(self._shard.lib.ital_set_fused(self._shard.handle, int(self._fused)))
 
     @property
     def bulk_stream(self):
@@ -327,8 +348,8 @@ class ITAL(object):
                              self.length_scale, self.var, self.noise, device)
         self.gp = _GPView(self)
         self._setup_peer_exchange()
-        self.lazy_rows = self._lazy_rows
         self.bulk_stream = self._bulk_stream
+        self.fused = self._fused
         self.reset()
 
     def _setup_peer_exchange(self):
@@ -515,16 +536,19 @@ class ITAL(object):
                 self._shard.restrict_candidates(cand[top_ind])
                 restricted = True
         self.last_fetch_stats = []
+        self._apply_lazy_rows()
         try:
             if self._comm.world_size == 1 and not show_progress:
                 idx, scores = self._shard.fetch(k, self.label_prob, self.mistake_prob, self.exhaustive)
                 self.last_fetch_scores = scores
+                self.last_fused_steps = int(self._shard.stats()[5])
                 return [int(i) for i in idx]
             if getattr(self._comm, 'on_device', False) and not show_progress:
                 if self._peer and 2 * self._shard.record_doubles() <= self._shard.peer_slot_doubles():
                     # (2 x: room for the batch's projection columns may still double the record in ital_fetch_begin)
                     idx, scores = self._shard.fetch_peer(k, self.label_prob, self.mistake_prob, self.exhaustive)
                     self.last_fetch_scores = scores
+                    self.last_fused_steps = int(self._shard.stats()[5])
                     return [int(i) for i in idx]
                 return self._fetch_device_loop(k)
             return self._fetch_stepwise(k, show_progress)
@@ -558,6 +582,7 @@ class ITAL(object):
             from tqdm import trange
             steps = trange(k)
         ret, self.last_fetch_scores, self.last_step_scores = [], [], []
+        self._apply_lazy_rows()
         self._shard.fetch_begin(self.label_prob, self.mistake_prob)
         try:
             for it in steps:

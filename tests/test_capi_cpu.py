@@ -168,5 +168,9 @@ def test_library_is_sm100a_code_with_bulk_copies_and_dependent_launch():
     for f in ring:
         assert 'UBLKCP' in f and 'SYNCS.ARRIVE.TRANS64' in f and 'TRYWAIT' in f
     kernels = re.split(r'\n\s*Function : ', sass)[1:]
-    assert all('ACQBULK' in f and 'PREEXIT' in f for f in kernels), 'a kernel without pdl_enter()'
+    fused = [f for f in kernels if 'k_fetch_fused' in f.split('\n', 1)[0]]
+    assert len(fused) == 2          # the persistent fetch kernel (cooperative launch): grid barrier = acquire + L1 invalidate
+    for f in fused:
+        assert 'LDG.E.STRONG.GPU' in f and 'CCTL.IVALL' in f and 'STRONG.SYS' in f
+    assert all('ACQBULK' in f and 'PREEXIT' in f for f in kernels if f not in fused), 'a kernel without pdl_enter()'
     assert 'STRONG.SYS' in sass and 'MEMBAR.SC.SYS' in sass

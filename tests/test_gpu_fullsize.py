@@ -61,9 +61,13 @@ def test_batch_is_invariant_under_pruning_and_lazy_rows(big):
     base = learner.fetch_unlabelled(4)
     base_scores = np.array(learner.last_fetch_scores)
     assert len(set(base)) == 4 and not (set(base) & {i for fb in fbs for i in fb})
-    learner.lazy_rows = True
-    assert learner.fetch_unlabelled(4) == base
+    learner.lazy_rows = None                      # the default: one persistent kernel per fetch
+    assert learner.fetch_unlabelled(4) == base and learner.last_fused_steps == 4
     assert np.array_equal(np.array(learner.last_fetch_scores), base_scores)
+    learner.lazy_rows, learner.fused = True, False      # the same as separate kernels
+    assert learner.fetch_unlabelled(4) == base and learner.last_fused_steps == 0
+    assert np.array_equal(np.array(learner.last_fetch_scores), base_scores)
+    learner.fused = True
     learner.exhaustive = True
     assert learner._fetch_stepwise(4, keep_scores=True) == base
     np.testing.assert_allclose(learner.last_fetch_scores, base_scores, rtol=1e-12)
@@ -72,6 +76,7 @@ def test_batch_is_invariant_under_pruning_and_lazy_rows(big):
     assert learner.fetch_unlabelled(4) == base
     np.testing.assert_allclose(learner.last_fetch_scores, base_scores, rtol=1e-12)
     learner.exhaustive = False
+    learner.lazy_rows = None
     # every candidate's conditional gain shrinks as the batch grows
     h = [0.0] + [float(s) for s in base_scores]
     gains = [full[t] - h[t] for t in range(4)]

@@ -154,20 +154,32 @@ def test_synthetic_parity_exhaustive_and_pruned(n, d, storage):
     assert kinds == ['identical'] * 4
     assert ret == ora.fetch_unlabelled(4)
     gpu.exhaustive = False
-    assert gpu.fetch_unlabelled(4) == ret
-    stats = gpu._fetch_stepwise(4) and gpu.last_fetch_stats
-    # lazy rows: projections extended on demand for the scored rows only -- same batch, same scores bit for bit
+    # streaming passes (pipelined multi-kernel loop), then the same loop step by step
+    gpu.lazy_rows = False
+    assert gpu.fetch_unlabelled(4) == ret and gpu.last_fused_steps == 0
     stream_scores = np.array(gpu.last_fetch_scores)
-    gpu.lazy_rows = True
-    assert gpu.fetch_unlabelled(4) == ret
+    stats = gpu._fetch_stepwise(4) and gpu.last_fetch_stats
     assert np.array_equal(np.array(gpu.last_fetch_scores), stream_scores)
+    # the default: projections on demand for the scored rows only, the whole fetch in one persistent kernel --
+    # same batch, same scores bit for bit
+    gpu.lazy_rows = None
+    assert gpu.fetch_unlabelled(4) == ret and gpu.last_fused_steps == 4
+    assert np.array_equal(np.array(gpu.last_fetch_scores), stream_scores)
+    assert gpu.fetch_unlabelled(2) == ret[:2] and gpu.last_fused_steps == 2
+    assert gpu.fetch_unlabelled(1) == ret[:1] and gpu.last_fused_steps == 1
+    # ... and as separate kernels (ITAL_B200_FUSED=0)
+    gpu.fused = False
+    assert gpu.fetch_unlabelled(4) == ret and gpu.last_fused_steps == 0
+    assert np.array_equal(np.array(gpu.last_fetch_scores), stream_scores)
+    gpu.fused = True
+    gpu.lazy_rows = True
     gpu.exhaustive = True
     assert gpu._fetch_stepwise(4, keep_scores=True) == ret
     ora.fetch_unlabelled(4, forced=ret)
     for sc, tr in zip(gpu.last_step_scores, ora.trace):
         np.testing.assert_allclose(sc[tr['candidates']], tr['scores'], rtol=SCORE_RTOL, atol=SCORE_ATOL)
     gpu.exhaustive = False
-    gpu.lazy_rows = False
+    gpu.lazy_rows = None
     # [0] rows in the final worklist, [1] rows scored by quadrature (-1: closed form), [2] nodes
     assert stats[0][1] == -1 and all(0 < s[1] <= n + 2 * 148 for s in stats[1:]), stats
     assert [int(s[2]) for s in stats] == [1, 64, 1024, 13824]
@@ -178,7 +190,7 @@ def test_bulk_staged_stream_is_bit_identical():
     X, assign = _syn(20011, 512, seed=4)
     out = {}
     for bulk in (False, True):
-        gpu = _gpu_learner(X, length_scale=1.0, bulk_stream=bulk)
+        gpu = _gpu_learner(X, length_scale=1.0, bulk_stream=bulk, lazy_rows=False)
         _label_syn(gpu, assign)
         out[bulk] = (gpu.fetch_unlabelled(4), np.array(gpu.last_fetch_scores), gpu.rel_mean.copy())
     assert out[False][0] == out[True][0]
@@ -239,7 +251,8 @@ def test_repeated_rounds_track_the_oracle():
     for L in (gpu, ora):
         L.update({0: 1})
     for rnd in range(5):
-        gpu.lazy_rows = bool(rnd % 2)                 # alternate streaming and on-demand projections
+        gpu.lazy_rows = (False, True, None)[rnd % 3]  # streaming passes, on-demand projections, the default (fused)
+        gpu.fused = rnd != 1
         a, b = gpu.fetch_unlabelled(4), ora.fetch_unlabelled(4)
         assert a == b, rnd
         fb = {i: int(y[i]) for i in a}

@@ -61,6 +61,9 @@ class StubShard(object):
         self.calls.append(('fetch', k, label_prob, mistake_prob, bool(exhaustive)))
         return np.array(cand[:k], dtype=np.int64), np.arange(len(cand[:k]), dtype=np.float64)
 
+    def stats(self):
+        return np.zeros(8)
+
     def rel_mean(self):
         return self.mean.copy()
 
