@@ -145,6 +145,12 @@ int ital_set_lazy_rows(ital_shard* s, int on);
  * multi-kernel loop.  Same batch and bit-identical scores either way. */
 int ital_set_fused(ital_shard* s, int on);
 
+/* Diagnostics: with `on`, CTA 0 of k_fetch_fused stamps the GPU's nanosecond timer at every phase boundary; `out`
+ * (may be NULL) receives up to max_out (<= 64) stamps of the last fused launch, in order: start, end of S0's scan,
+ * after its barrier, commit of step 0, then per later step both sides of each of the five barriers (P1..P5) and the
+ * commit.  Returns the number of stamps copied. */
+int64_t ital_fused_trace(ital_shard* s, int on, uint64_t* out, int64_t max_out);
+
 /* Streaming pass variant (on by default): stage the rows through shared memory with the bulk-copy engine (TMA,
  * cp.async.bulk + mbarrier; k_extend_bulk) where the tuned shape applies (2 KB rows, e.g. d = 512 float32), else
  * coalesced register loads (k_extend).  Same results bit for bit either way. */
@@ -195,6 +201,16 @@ int ital_transfer_bytes(const ital_shard* s, int64_t* h2d_bytes, int64_t* d2h_by
 int64_t ital_snq_nodes(int t, const double* m, const double* L, double* eta, double* w, int32_t* orth,
                        double* masses);
 int ital_snq_order(int t);
+/* Table behind the closed-form score of the first greedy step (one sample: ital/ital.py:364-369 + 183-224),
+ *   H(u) = -Phi(u) log(Phi(u) + 1e-12) - Phi(-u) log(Phi(-u) + 1e-12),  u = |mean| / stdev in [0, 8.5]:
+ * 136 intervals of width 1/16, 8 coefficients each (ascending powers of x = 32 (u - (k + 1/2) / 16) in [-1, 1]).
+ * Copies up to max_out doubles, returns the table length (1088). */
+int64_t ital_h_table(double* out, int64_t max_out);
+/* Table behind the standard normal CDF of the scoring kernels (replaces scipy.stats.norm.cdf / the CDF inside mvndst,
+ * ital/ital.py:364-383): (Phi, phi) at the 2177 grid points x_k = -8.5 + k/128; the kernels add a 5th-order Taylor
+ * step from the nearest grid point (phi_tab in csrc/ital_kernels.cuh).  Copies up to max_out doubles, returns the
+ * length (4354). */
+int64_t ital_phi_table(double* out, int64_t max_out);
 /* Conditional node sets of the general feedback model (label_prob < 1; csrc/snq_host.h generate_general).
  * sizes[4] = {n_nodes, n_groups, n_sets, lut entries}; call with eta == NULL to get the sizes only.  eta[t*n_nodes]
  * dimension-major, w[n_nodes], group_begin[n_groups+1], group_mass[n_groups], set_group0[n_sets+1],

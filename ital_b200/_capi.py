@@ -51,6 +51,7 @@ SIGNATURES = {
     'ital_set_lazy_rows': (ctypes.c_int, [_shard_p, ctypes.c_int]),
     'ital_set_bulk_stream': (ctypes.c_int, [_shard_p, ctypes.c_int]),
     'ital_set_fused': (ctypes.c_int, [_shard_p, ctypes.c_int]),
+    'ital_fused_trace': (ctypes.c_int64, [_shard_p, ctypes.c_int, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int64]),
     'ital_fetch_stats': (ctypes.c_int, [_shard_p, _c_double_p]),
     'ital_last_scores': (ctypes.c_int, [_shard_p, _c_double_p]),
     'ital_rel_mean': (ctypes.c_int, [_shard_p, _c_double_p]),
@@ -64,6 +65,8 @@ SIGNATURES = {
     'ital_snq_nodes': (ctypes.c_int64, [ctypes.c_int, _c_double_p, _c_double_p, _c_double_p, _c_double_p,
                                         _c_int32_p, _c_double_p]),
     'ital_snq_order': (ctypes.c_int, [ctypes.c_int]),
+    'ital_h_table': (ctypes.c_int64, [_c_double_p, ctypes.c_int64]),
+    'ital_phi_table': (ctypes.c_int64, [_c_double_p, ctypes.c_int64]),
     'ital_snq_general': (ctypes.c_int, [ctypes.c_int, _c_double_p, _c_double_p, ctypes.c_double, _c_int64_p,
                                         _c_double_p, _c_double_p, _c_int32_p, _c_double_p, _c_int32_p, _c_int32_p]),
 }

@@ -81,6 +81,7 @@ struct ital_shard {
     int64_t n_nodes = 0;
     double* gl_dev = nullptr;        // Gauss-Legendre tables: x[65][64] then w[65][64]
     double2* phi_dev = nullptr;      // (Phi, phi) on the grid of phi_tab
+    double* htab_dev = nullptr;      // polynomial table of h_tab (closed-form score of the first greedy step)
     // batch state on the device: means and Cholesky rows of the selected points, selection list, H(base)
     double *base_m_dev = nullptr, *base_L_dev = nullptr, *sel_dev = nullptr, *hbase_dev = nullptr;
     double* sel_host = nullptr;      // pinned mirror of sel_dev: (global row, score) per step
@@ -116,10 +117,14 @@ struct ital_shard {
     Best* f_best = nullptr;
     int* f_cnt = nullptr;
     int* f_stage = nullptr;
+    double* f_mass = nullptr;
     unsigned* f_bar = nullptr;
     unsigned f_bar_count = 0;        // arrivals on the barrier counter so far (monotone across launches)
     bool fused = true;               // ITAL_B200_FUSED=0: multi-kernel loop only
+    unsigned long long* f_trace = nullptr;   // phase time stamps of the last fused launch (ital_fused_trace)
+    bool f_trace_on = false;
     bool sel_marked = false;         // rows of the running batch carry the kSelected mask bit
+    bool hbase_seeded = false;       // hbase_dev holds {0, 1} for the first greedy step of the running fetch
     int fused_steps_last = 0;        // greedy steps the fused kernel ran in the last fetch (diagnostics)
     double* rec_hist = nullptr;      // records of the points selected in the running fetch
     uint64_t* sort_keys = nullptr;   // top_results: two key and two row buffers (ping-pong), tile histograms
@@ -186,6 +191,54 @@ cudaError_t copy_sync(ital_shard* s, void* dst, const void* src, size_t bytes, c
 namespace {
 
 int64_t record_doubles(const ital_shard* s) { return ITAL_RECORD_HEADER + s->w_cap + s->d; }
+
+// H(u) = -Phi(u) log(Phi(u) + eps) - Phi(-u) log(Phi(-u) + eps) as degree-7 polynomials per interval of width 1/16
+// over [0, 8.5] (h_tab in ital_kernels.cuh): interpolation at the Chebyshev nodes of every interval, in extended
+// precision; coefficients in ascending powers of the position x in [-1, 1] inside the interval.
+// (Phi, phi) on the grid x_k = -8.5 + k/128 of phi_tab, in extended precision
+std::vector<double> build_phi_table() {
+    std::vector<double> tab((size_t)kPhiTableLen * 2);
+    for (int k = 0; k < kPhiTableLen; ++k) {
+        const long double x = -(long double)kPhiXMax + (long double)k / kPhiPerUnit;
+        tab[(size_t)k * 2 + 0] = (double)(0.5L * erfcl(-x * 0.70710678118654752440084436210484903L));
+        tab[(size_t)k * 2 + 1] = (double)(expl(-0.5L * x * x) * 0.39894228040143267793994605993438187L);
+    }
+    return tab;
+}
+
+std::vector<double> build_h_table() {
+    std::vector<double> tab((size_t)kHTabLen * 8);
+    const long double eps = 1e-12L, pi = 3.14159265358979323846264338327950288L;
+    auto H = [&](long double u) {
+        const long double p1 = 0.5L * erfcl(-u * 0.70710678118654752440084436210484903L);
+        const long double p0 = 0.5L * erfcl(u * 0.70710678118654752440084436210484903L);
+        return -(p1 * logl(p1 + eps) + p0 * logl(p0 + eps));
+    };
+    for (int k = 0; k < kHTabLen; ++k) {
+        const long double mid = ((long double)k + 0.5L) / kHTabPerUnit, half = 0.5L / kHTabPerUnit;
+        long double A[8][9];
+        for (int i = 0; i < 8; ++i) {
+            const long double x = cosl(pi * (2 * i + 1) / 16.0L);
+            long double pw = 1.0L;
+            for (int j = 0; j < 8; ++j) { A[i][j] = pw; pw *= x; }
+            A[i][8] = H(mid + half * x);
+        }
+        for (int c = 0; c < 8; ++c) {       // Gauss-Jordan with partial pivoting
+            int piv = c;
+            for (int r = c + 1; r < 8; ++r)
+                if (fabsl(A[r][c]) > fabsl(A[piv][c])) piv = r;
+            for (int j = 0; j < 9; ++j) std::swap(A[c][j], A[piv][j]);
+            for (int r = 0; r < 8; ++r) {
+                if (r == c) continue;
+                const long double f = A[r][c] / A[c][c];
+                for (int j = c; j < 9; ++j) A[r][j] -= f * A[c][j];
+            }
+        }
+        for (int j = 0; j < 8; ++j) tab[(size_t)k * 8 + j] = (double)(A[j][8] / A[j][j]);
+    }
+    return tab;
+}
+
 
 // Kernel launch with programmatic stream serialization (see pdl_enter in ital_kernels.cuh): the kernel may start
 // launching while its predecessor in the stream drains; it waits for the predecessor's completion itself.  All
@@ -471,6 +524,7 @@ int make_record(ital_shard* s, long long local_row, double* dst_dev, bool commit
 constexpr int kMaxBatch = 11;            // greedy steps per fetch (t <= 10 base variables)
 
 int ensure_nodes(ital_shard* s, int64_t n_nodes) {
+    n_nodes += 8 * kNodePad;                            // (every orthant of the packed node list is zero-padded to 256)
     if (n_nodes <= s->nodes_cap) return ITAL_OK;
     CU(cudaStreamSynchronize(s->stream));
     for (void* p : {(void*)s->eta_dev, (void*)s->w_dev, (void*)s->orth_dev, (void*)s->eta_raw, (void*)s->w_raw,
@@ -509,8 +563,10 @@ int prepare_nodes(ital_shard* s) {
         else ITAL_GEN(3);
 #undef ITAL_GEN
         s->launches++;
-        pdl(k_snq_finalize, 1, 1024, 0, s)(t, N, snq::kWMin, s->eta_raw, s->w_raw, s->orth_raw, s->eta_dev, s->w_dev,
-                                                  s->orth_dev, s->log1p_eps, s->masses_dev, s->hbase_dev, s->counters + 3); s->launches++;
+        const size_t fsm = ((size_t)s->num_sms * 8 + 8) * sizeof(double);
+        pdl(k_snq_finalize, 1, 1024, fsm, s)(t, N, snq::kWMin, s->eta_raw, s->w_raw, s->orth_raw, s->eta_dev,
+                                             s->group_dev, s->log1p_eps, s->masses_dev, s->hbase_dev, s->counters + 3,
+                                             s->num_sms); s->launches++;
         CU(cudaGetLastError());
         return ITAL_OK;
     }
@@ -579,6 +635,7 @@ int launch_eval(ital_shard* s, int64_t items_hint, bool block_per_candidate) {
     a.W0 = s->W;
     a.eta = s->eta_dev;
     a.w = s->w_dev;
+    a.nodes4 = s->eta_dev;
     a.orth = s->orth_dev;
     a.phi = s->phi_dev;
     a.group_begin = s->group_dev;
@@ -672,7 +729,8 @@ int propose_general(ital_shard* s) {
     a.epoch = s->epoch;
     a.n_scored = s->counters + 2;
     if ((rc = launch_catchup(s, s->n))) return rc;
-    const size_t smem = ((size_t)3 * gs.n_groups + 2 * gs.n_sets + (size_t)gs.n_groups * 24 + 8) * sizeof(double);
+    const size_t smem = ((size_t)3 * gs.n_groups + 2 * gs.n_sets + (size_t)gs.n_groups * 24 + 8) * sizeof(double) +
+                        (size_t)kPhiTableLen * sizeof(double2);
     CU(cudaFuncSetAttribute(k_eval_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int blocks = grid_for(s, s->n, 1, 8);
     pdl(k_eval_general, blocks, 256, smem, s)(a); s->launches++;
@@ -718,11 +776,17 @@ int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_o
     s->pick = PickSrc();
     // counters [0..2] are zero here: k_record re-arms them at the end of every step, ital_fetch_begin before the first
     if (s->t == 0) CU(cudaMemsetAsync(s->counters, 0, 4 * sizeof(int), s->stream));
+    if (s->t == 0 && !s->hbase_seeded) {
+        const double hb0[2] = {0.0, 1.0};               // first step: no base, total mass 1
+        memcpy(s->sel_host + 30, hb0, sizeof hb0);      // (pinned scratch at the tail of the selection mirror)
+        CU(copy_async(s, s->hbase_dev, s->sel_host + 30, sizeof hb0, cudaMemcpyHostToDevice, s->stream));
+        s->hbase_seeded = true;
+    }
     if (s->t == 0) {
         const bool general = s->label_prob < 1.0;
         const double lc = general ? (1.0 - s->mistake_prob) * s->log1p_eps + s->mistake_prob * std::log(1e-12) : s->log1p_eps;
         pdl(k_score0, blocks, 256, 0, s)(s->n, s->m, s->v, s->mask, s->score, s->gain, s->block_best, lc,
-                                                general ? s->label_prob : 1.0, s->phi_dev); s->launches++;
+                                                general ? s->label_prob : 1.0, s->htab_dev); s->launches++;
         s->pick.block_best = s->block_best;     // reduced by k_record
         s->pick.nblocks = blocks;
         CU(cudaGetLastError());
@@ -831,7 +895,7 @@ bool fused_applies(const ital_shard* s, int exhaustive, bool peer) {
     if (!s->fused || !s->lazy_rows || exhaustive || s->label_prob < 1.0) return false;
     const int C = fused_chunk_cap(s);
     if (C > kFusedThreads) return false;
-    const FusedSmem L(record_doubles(s), s->w_cap, C);
+    const FusedSmem L(record_doubles(s), s->w_cap, C, s->num_sms);
     if (L.total * sizeof(double) > 200 * 1024) return false;
     if (peer && s->xg_world > kFusedThreads) return false;
     return true;
@@ -878,13 +942,13 @@ int launch_fused(ital_shard* s, int steps, bool more_follow, bool peer) {
     a.gl_x = s->gl_dev;
     a.gl_w = s->gl_dev + (snq::kMaxOrder + 1) * 64;
     a.phi = s->phi_dev;
+    a.htab = s->htab_dev;
     a.R = snq::kR;
     a.w_min = snq::kWMin;
     a.q_min = snq::kQMin;
     a.chunk_cap = fused_chunk_cap(s);
-    a.eta = s->eta_dev;
-    a.w = s->w_dev;
-    a.orth = s->orth_dev;
+    a.nodes4 = s->eta_dev;
+    a.group_begin = s->group_dev;
     a.masses = s->masses_dev;
     a.hbase = s->hbase_dev;
     a.rec_hist = s->rec_hist;
@@ -897,11 +961,13 @@ int launch_fused(ital_shard* s, int steps, bool more_follow, bool peer) {
     a.counters = s->counters;
     a.blk_best = s->f_best;
     a.blk_cnt = s->f_cnt;
+    a.blk_mass = s->f_mass;
     a.stage_rows = s->f_stage;
     a.worklist = s->worklist;
     a.barrier = s->f_bar;
     a.bar_base = s->f_bar_count;
     a.want_scores = 0;
+    a.trace = s->f_trace_on ? s->f_trace : nullptr;
     if (peer) {
         a.pp.peer_base = s->xg_peer_dev;
         a.pp.G = s->xg_world;
@@ -914,7 +980,7 @@ int launch_fused(ital_shard* s, int steps, bool more_follow, bool peer) {
         s->xg_epoch += (unsigned long long)steps;
     }
     const int grid = s->num_sms;
-    const FusedSmem L(a.rec_len, a.w_cap, a.chunk_cap);
+    const FusedSmem L(a.rec_len, a.w_cap, a.chunk_cap, grid);
     const size_t smem = L.total * sizeof(double);
     void* params[] = {&a};
     const void* fn = s->x_dtype == ITAL_F32 ? (const void*)k_fetch_fused<float> : (const void*)k_fetch_fused<double>;
@@ -951,8 +1017,8 @@ void free_all(ital_shard* s) {
     if (s->xg_error_dev) cudaFree(s->xg_error_dev);
     void* ptrs[] = {s->X, s->sqn, s->m, s->v, s->U, s->gain, s->score, s->mask, s->worklist, s->counters,
                     s->block_best, s->best, s->thr_dev, s->rec_dev, s->rec_in_dev, s->idx_dev, s->eta_dev,
-                    s->w_dev, s->masses_dev, s->group_dev, s->orth_dev, s->eta_raw, s->w_raw, s->orth_raw, s->gl_dev, s->phi_dev, s->base_m_dev, s->base_L_dev, s->sel_dev,
-                    s->hbase_dev, s->stats_dev, s->tags, s->f_best, s->f_cnt, s->f_stage, s->f_bar, s->rec_hist, s->mext_dev, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev,
+                    s->w_dev, s->masses_dev, s->group_dev, s->orth_dev, s->eta_raw, s->w_raw, s->orth_raw, s->gl_dev, s->phi_dev, s->htab_dev, s->base_m_dev, s->base_L_dev, s->sel_dev,
+                    s->hbase_dev, s->tags, s->f_best, s->f_cnt, s->f_stage, s->f_mass, s->f_bar, s->f_trace, s->rec_hist, s->mext_dev, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev,
                     s->sort_keys, s->sort_rows, s->sort_hist, s->sort_out_idx, s->sort_out_val};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -960,7 +1026,6 @@ void free_all(ital_shard* s) {
     if (s->rec_in_host) cudaFreeHost(s->rec_in_host);
     if (s->sel_host) cudaFreeHost(s->sel_host);
     if (s->mext_host) cudaFreeHost(s->mext_host);
-    if (s->stats_host) cudaFreeHost(s->stats_host);
 }
 
 int reset_model(ital_shard* s) {
@@ -1046,8 +1111,9 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
         CU(cudaMalloc(&s->tags, (size_t)s->n * sizeof(uint32_t)));
         CU(cudaMemset(s->tags, 0, (size_t)s->n * sizeof(uint32_t)));
         CU(cudaMalloc(&s->f_best, (size_t)s->num_sms * kFusedTeams * sizeof(Best)));
-        CU(cudaMalloc(&s->f_cnt, (size_t)s->num_sms * sizeof(int)));
+        CU(cudaMalloc(&s->f_cnt, (size_t)s->num_sms * 8 * sizeof(int)));
         CU(cudaMalloc(&s->f_stage, (size_t)s->num_sms * kFusedTeams * sizeof(int)));
+        CU(cudaMalloc(&s->f_mass, (size_t)s->num_sms * 8 * sizeof(double)));
         CU(cudaMalloc(&s->f_bar, sizeof(unsigned)));
         CU(cudaMemset(s->f_bar, 0, sizeof(unsigned)));
         CU(cudaMalloc(&s->worklist, (size_t)s->n * sizeof(int)));
@@ -1064,23 +1130,23 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
         CU(cudaMalloc(&s->thr_dev, sizeof(double)));
         CU(cudaMalloc(&s->base_m_dev, 16 * sizeof(double)));
         CU(cudaMalloc(&s->base_L_dev, 16 * 16 * sizeof(double)));
-        CU(cudaMalloc(&s->sel_dev, 32 * sizeof(double)));
+        CU(cudaMalloc(&s->sel_dev, 32 * sizeof(double) + 16 * 4 * sizeof(int)));   // selection list, then the step stats
         CU(cudaMalloc(&s->hbase_dev, 2 * sizeof(double)));      // [0] H(base), [1] total quadrature mass
         CU(cudaMemset(s->hbase_dev, 0, 2 * sizeof(double)));
         CU(cudaMalloc(&s->masses_dev, 1024 * sizeof(double)));
         CU(cudaMalloc(&s->group_dev, 1025 * sizeof(int)));
-        CU(cudaMalloc(&s->stats_dev, 16 * 4 * sizeof(int)));
-        CU(cudaMallocHost(&s->sel_host, 32 * sizeof(double)));
-        CU(cudaMallocHost(&s->stats_host, 16 * 4 * sizeof(int)));
-        {   // table of the standard normal CDF / density for phi_tab
-            std::vector<double2> tab(kPhiTableLen);
-            for (int k = 0; k < kPhiTableLen; ++k) {
-                const double xk = -kPhiXMax + (double)k / kPhiPerUnit;
-                tab[k].x = 0.5 * std::erfc(-xk * 0.70710678118654752440);
-                tab[k].y = std::exp(-0.5 * xk * xk) * 0.39894228040143267794;
-            }
-            CU(cudaMalloc(&s->phi_dev, tab.size() * sizeof(double2)));
-            CU(copy_sync(s, s->phi_dev, tab.data(), tab.size() * sizeof(double2), cudaMemcpyHostToDevice));
+        s->stats_dev = reinterpret_cast<int*>(s->sel_dev + 32);
+        CU(cudaMallocHost(&s->sel_host, 32 * sizeof(double) + 16 * 4 * sizeof(int)));
+        s->stats_host = reinterpret_cast<int*>(s->sel_host + 32);
+        {   // Taylor coefficients of the standard normal CDF around the grid points of phi_tab
+            std::vector<double> tab = build_phi_table();
+            CU(cudaMalloc(&s->phi_dev, tab.size() * sizeof(double)));
+            CU(copy_sync(s, s->phi_dev, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
+        {   // polynomial table of the closed-form first step (h_tab)
+            std::vector<double> tab = build_h_table();
+            CU(cudaMalloc(&s->htab_dev, tab.size() * sizeof(double)));
+            CU(copy_sync(s, s->htab_dev, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
         }
         {   // Gauss-Legendre tables for every order the panel split can ask for
             const snq::GaussLegendre& G = snq::gl();
@@ -1365,9 +1431,7 @@ int ital_fetch_begin(ital_shard* s, double label_prob, double mistake_prob) {
         s->epoch = 1;
     }
     s->sel_marked = false;
-    const double hb0[2] = {0.0, 1.0};                   // first step: no base, total mass 1
-    memcpy(s->sel_host + 30, hb0, sizeof hb0);          // (pinned scratch at the tail of the selection mirror)
-    CU(copy_async(s, s->hbase_dev, s->sel_host + 30, sizeof hb0, cudaMemcpyHostToDevice, s->stream));
+    s->hbase_seeded = false;                            // (uploaded by the first multi-kernel step; the fused kernel seeds its own)
     s->fetching = true;
     s->t = 0;
     s->nodes_ready_t = s->stage_a_ready_t = -1;
@@ -1437,8 +1501,8 @@ int ital_fetch_commit(ital_shard* s, const double* record) {
 int ital_fetch_result(ital_shard* s, int max_out, int64_t* out_idx, double* out_scores) {
     if (!s || max_out < 0 || (max_out > 0 && !out_idx)) return fail(ITAL_EINVAL, "ital_fetch_result: bad arguments");
     CU(cudaSetDevice(s->device));
-    CU(copy_async(s, s->sel_host, s->sel_dev, 32 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    CU(copy_async(s, s->stats_host, s->stats_dev, 16 * 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CU(copy_async(s, s->sel_host, s->sel_dev, 32 * sizeof(double) + 16 * 4 * sizeof(int), cudaMemcpyDeviceToHost,
+                  s->stream));                          // selection list and step stats in one copy
     CU(cudaStreamSynchronize(s->stream));
     int got = 0;
     for (int k = 0; k < s->t && k < max_out; ++k) {
@@ -1813,6 +1877,22 @@ int ital_set_fused(ital_shard* s, int on) {
     return ITAL_OK;
 }
 
+int64_t ital_fused_trace(ital_shard* s, int on, uint64_t* out, int64_t max_out) {
+    if (!s) return fail(ITAL_EINVAL, "null shard");
+    CU(cudaSetDevice(s->device));
+    constexpr int kMarks = 64;
+    if (!s->f_trace) {
+        CU(cudaMalloc(&s->f_trace, kMarks * sizeof(unsigned long long)));
+        CU(cudaMemset(s->f_trace, 0, kMarks * sizeof(unsigned long long)));
+    }
+    s->f_trace_on = on != 0;
+    if (!out) return 0;
+    CU(cudaStreamSynchronize(s->stream));
+    const int64_t m = std::min<int64_t>(max_out, kMarks);
+    CU(cudaMemcpy(out, s->f_trace, (size_t)m * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return m;
+}
+
 int ital_set_bulk_stream(ital_shard* s, int on) {
     if (!s) return fail(ITAL_EINVAL, "null shard");
     s->bulk_stream = on != 0;
@@ -1866,6 +1946,18 @@ int64_t ital_snq_nodes(int t, const double* m, const double* L, double* eta, dou
 }
 
 int ital_snq_order(int t) { return snq::order_for(t); }
+
+int64_t ital_phi_table(double* out, int64_t max_out) {
+    const std::vector<double> tab = build_phi_table();
+    if (out) memcpy(out, tab.data(), (size_t)std::min<int64_t>(max_out, (int64_t)tab.size()) * sizeof(double));
+    return (int64_t)tab.size();
+}
+
+int64_t ital_h_table(double* out, int64_t max_out) {
+    const std::vector<double> tab = build_h_table();
+    if (out) memcpy(out, tab.data(), (size_t)std::min<int64_t>(max_out, (int64_t)tab.size()) * sizeof(double));
+    return (int64_t)tab.size();
+}
 
 int ital_snq_general(int t, const double* m, const double* L, double noise, int64_t* sizes, double* eta, double* w,
                      int32_t* group_begin, double* group_mass, int32_t* set_group0, int32_t* lut) {

@@ -16,7 +16,7 @@
 //   P5   the worklist rows: projections caught up by one warp per row, eight rows of a team in flight, then scored
 //   P6   argmax over the teams' bests, the winner's record into every CTA's shared memory, batch state committed
 //
-// The arithmetic is that of the multi-kernel path, function by function (score0_value, snq_node, snq_masses_block,
+// The arithmetic is that of the multi-kernel path, function by function (score0_value, snq_node, chunk_mass_warp + masses_from_chunks,
 // catchup_row, eval_candidate with 256-thread teams), so both paths return the same batch with bit-identical scores.
 // Multi-GPU: in P6 CTA 0 stores the shard's proposal into its peers' exchange buffers (peer_put, NVLink) and every
 // CTA waits for the peers' flags in local memory -- the exchange of ital_fetch_peer without its two extra launches.
@@ -56,14 +56,14 @@ struct FusedArgs {
     const double* gl_x;
     const double* gl_w;
     const double2* phi;
+    const double* htab;             // table of h_tab (closed-form first step)
     double R, w_min;
     int q_min;
     int order[kFusedMaxSteps];
     int64_t node_cap[kFusedMaxSteps];
     int chunk_cap;                  // nodes generated per CTA at most (shared-memory staging)
-    double* eta;
-    double* w;
-    int* orth;
+    double* nodes4;                 // {eta_0, eta_1, eta_2, weight} per kept node, zero-padded to kNodePad
+    int* group_begin;               // [9] orthant offsets (for a multi-kernel continuation)
     double* masses;
     double* hbase;
     // batch state in global memory (written by CTA 0; read by the host and by a multi-kernel continuation)
@@ -77,7 +77,8 @@ struct FusedArgs {
     int* counters;
     // scratch
     Best* blk_best;                 // [gridDim.x * kFusedTeams]
-    int* blk_cnt;                   // [gridDim.x]
+    int* blk_cnt;                   // [gridDim.x][8] kept nodes per orthant in every CTA's chunk
+    double* blk_mass;               // [gridDim.x][8] orthant masses of every CTA's chunk of nodes
     int* stage_rows;                // [gridDim.x * kFusedTeams]
     int* worklist;
     unsigned* barrier;
@@ -88,17 +89,19 @@ struct FusedArgs {
     const unsigned long long* flags;
     const double* slots;            // base of the local slots: [2][G][slot_doubles]
     int* peer_error;
+    unsigned long long* trace;      // != nullptr: CTA 0 stamps %globaltimer at every phase boundary (diagnostics)
 };
 
 // shared-memory carve-up of k_fetch_fused, in doubles (host and device use the same numbers)
 struct FusedSmem {
-    size_t recs, uv, red, part, masses, hb, base_m, base_L, ss, si, nd_eta, nd_w, nd_orth, ism, sel_loc, total;
-    __host__ __device__ FusedSmem(int64_t rec_len, int w_cap, int C) {
+    size_t recs, uv, red, phi, part, masses, hb, base_m, base_L, ss, si, nd_eta, nd_w, nd_orth, ism, sel_loc, total;
+    __host__ __device__ FusedSmem(int64_t rec_len, int w_cap, int C, int n_ctas) {
         size_t o = 0;
         recs = o; o += (size_t)kFusedMaxSteps * rec_len;
         uv = o; o += (size_t)kFusedWarps * w_cap;
         red = o; o += kFusedTeams * 64;
-        part = o; o += 64;
+        phi = o; o += 2 * (size_t)kPhiTableLen;     // table of phi_tab
+        part = o; o += (size_t)n_ctas * 8;          // chunk sums of the base masses
         masses = o; o += 8;
         hb = o; o += 2;
         base_m = o; o += kFusedMaxSteps;
@@ -108,7 +111,7 @@ struct FusedSmem {
         nd_eta = o; o += 3 * (size_t)C;
         nd_w = o; o += C;
         nd_orth = o; o += (C + 1) / 2;
-        ism = o; o += 32;                       // 64 ints
+        ism = o; o += 128;                      // 256 ints (the first 16 also serve as orthant offsets)
         sel_loc = o; o += kFusedMaxSteps;
         total = o;
     }
@@ -136,7 +139,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
 }
 
 // argmax over a group of threads (a team on a named barrier, or the whole CTA on barrier 0); every thread returns it
-__device__ __forceinline__ Best group_argmax(double bs, long long bi, int tid_group, int nthreads, int bar_id,
+__device__ __noinline__ Best group_argmax(double bs, long long bi, int tid_group, int nthreads, int bar_id,
                                              double* ss, long long* si) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -155,6 +158,38 @@ __device__ __forceinline__ Best group_argmax(double bs, long long bi, int tid_gr
     return r;
 }
 
+// One copy of the row-level routines inside the persistent kernel (inlined at every call site they made half a
+// megabyte of SASS, and a kernel that runs every piece of its code once per launch is bound by instruction fetch).
+template <int T>
+__device__ __noinline__ void eval_candidate_call(const EvalArgs& a, int64_t i, int tid_team, int TPC, int bar_id,
+                                                 double* red, const double2* phi, const int* gb, const double* masses,
+                                                 double h_base) {
+    eval_candidate<T>(a, i, tid_team, TPC, bar_id, red, phi, gb, masses, h_base);
+}
+
+__device__ __forceinline__ void eval_dispatch(int tn, const EvalArgs& a, int64_t i, int tid_team, int TPC, int bar_id,
+                                              double* red, const double2* phi, const int* gb, const double* masses,
+                                              double h_base) {
+    if (tn == 1) eval_candidate_call<1>(a, i, tid_team, TPC, bar_id, red, phi, gb, masses, h_base);
+    else if (tn == 2) eval_candidate_call<2>(a, i, tid_team, TPC, bar_id, red, phi, gb, masses, h_base);
+    else eval_candidate_call<3>(a, i, tid_team, TPC, bar_id, red, phi, gb, masses, h_base);
+}
+
+template <typename XT>
+__device__ __noinline__ void catchup_row_call(int64_t i, int lane, const XT* X, int d, int d_pad, const double* recs,
+                                              int64_t rec_len, int w_cap, int W, int t, const double* sqn, double* U,
+                                              int64_t ldu, uint32_t* tags, uint32_t epoch, double var, double neg2ls2,
+                                              double* uv) {
+    catchup_row<XT>(i, lane, X, d, d_pad, recs, rec_len, w_cap, W, t, sqn, U, ldu, tags, epoch, var, neg2ls2, uv);
+}
+
+template <int T>
+__device__ __noinline__ void snq_node_call(int64_t k, int64_t N, int q, double R, int q_min, const double* base_m,
+                                           const double* base_L, const double* gl_x, const double* gl_w, double* e,
+                                           double& wt, int& ob) {
+    snq_node<T>(k, N, q, R, q_min, base_m, base_L, gl_x, gl_w, e, wt, ob);
+}
+
 template <typename XT>
 __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
     extern __shared__ __align__(16) double fsm[];
@@ -165,13 +200,21 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
     const XT* X = (const XT*)a.X;
     const int C = a.chunk_cap;
     unsigned target = a.bar_base;
+    int n_marks = 0;
+#define FUSED_MARK()                                                                     \
+    do {                                                                                 \
+        if (a.trace != nullptr && blockIdx.x == 0 && tid == 0) a.trace[n_marks] = global_ns(); \
+        ++n_marks;                                                                       \
+    } while (0)
+    FUSED_MARK();
 
     // shared memory
-    const FusedSmem L(a.rec_len, a.w_cap, C);
+    const FusedSmem L(a.rec_len, a.w_cap, C, (int)gridDim.x);
     double* recs = fsm + L.recs;                                        // [kFusedMaxSteps][rec_len]
     double* uv = fsm + L.uv + (size_t)warp * a.w_cap;                   // [warps][w_cap]
     double* red = fsm + L.red + team * 64;                              // [teams][64]
-    double(*part)[8] = reinterpret_cast<double(*)[8]>(fsm + L.part);
+    double2* phi_s = reinterpret_cast<double2*>(fsm + L.phi);           // table of phi_tab
+    double* chunk_part = fsm + L.part;                                  // [gridDim.x][8]
     double* masses = fsm + L.masses;                                    // [8]
     double* hb = fsm + L.hb;                                            // [2]
     double* base_m = fsm + L.base_m;                                    // [4]
@@ -181,7 +224,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
     double* nd_eta = fsm + L.nd_eta;                                    // [3][C]
     double* nd_w = fsm + L.nd_w;                                        // [C]
     int* nd_orth = reinterpret_cast<int*>(fsm + L.nd_orth);             // [C]
-    int* ism = reinterpret_cast<int*>(fsm + L.ism);                     // [64] small integers
+    int* ism = reinterpret_cast<int*>(fsm + L.ism);                     // [256] small integers
+    int* gbeg = ism + 16;                                               // [9] orthant offsets of the step's nodes
     long long* sel_loc = reinterpret_cast<long long*>(fsm + L.sel_loc); // [4] local rows selected so far (-1: remote)
 
     if (blockIdx.x == 0 && tid < 4) {
@@ -190,6 +234,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
     }
     if (tid < 2) hb[tid] = (double)tid;                                  // first step: no base, total mass 1
     if (tid < kFusedMaxSteps) sel_loc[tid] = -1;
+    phi_tab_to_shared(phi_s, a.phi);
 
     // ---- S0: closed form for every candidate ------------------------------------------------------------------
     Best win;
@@ -197,23 +242,23 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
         double bs = 0.0;
         long long bi = -1;
         const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-        for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + tid; i0 < a.n; i0 += 4 * stride) {
-            uint8_t mk[4];
-            double mm[4], vv[4];
+        for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + tid; i0 < a.n; i0 += 2 * stride) {
+            uint8_t mk[2];
+            double mm[2], vv[2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 2; ++u) {
                 const int64_t i = i0 + u * stride;
                 mk[u] = i < a.n ? a.mask[i] : (uint8_t)1;
                 mm[u] = i < a.n ? a.m[i] : 0.0;
                 vv[u] = i < a.n ? a.v[i] : 0.0;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 2; ++u) {
                 const int64_t i = i0 + u * stride;
                 if (i >= a.n) break;
                 double s = nan("");
                 if (mk[u] == 0) {
-                    s = score0_value(mm[u], vv[u], a.log1p_eps, 1.0, a.phi);
+                    s = score0_value(mm[u], vv[u], a.log1p_eps, 1.0, a.htab);
                     a.gain[i] = s;
                     if (better(s, i, bs, bi)) { bs = s; bi = i; }
                 }
@@ -222,8 +267,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
         }
         const Best b = group_argmax(bs, bi, tid, kFusedThreads, 0, ss, si);
         if (tid == 0) a.blk_best[blockIdx.x] = b;
+        if (warp == 0 && b.idx >= 0)
+            prefetch_row<XT>(b.idx, lane, X, a.d_pad, a.U, a.ldu, a.W, a.m, a.v, a.sqn, a.gain, a.tags);
     }
+    FUSED_MARK();
     grid_barrier(a.barrier, target);
+    FUSED_MARK();
     {
         double bs = 0.0;
         long long bi = -1;
@@ -338,12 +387,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
             }
         }
         __syncthreads();
+        FUSED_MARK();
         if (t + 1 >= a.k) break;
         const int tn = t + 1;                                           // the step scored next: tn base variables
         const int64_t N = a.node_cap[tn];
 
         // ---- P1: nodes of the step (one chunk per CTA) and stage A -------------------------------------------------
-        int my_cnt = 0;
+        bool my_keep = false;
+        int my_rank = 0, my_ob = 0;
         if (!dead) {
             const int64_t per = (N + gridDim.x - 1) / gridDim.x;        // <= C
             const int64_t k = (int64_t)blockIdx.x * per + tid;
@@ -352,32 +403,45 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
             double wt = 0.0;
             int ob = 0;
             if (have) {
-                if (tn == 1) snq_node<1>(k, N, a.order[1], a.R, a.q_min, base_m, base_L, a.gl_x, a.gl_w, e, wt, ob);
-                else if (tn == 2) snq_node<2>(k, N, a.order[2], a.R, a.q_min, base_m, base_L, a.gl_x, a.gl_w, e, wt, ob);
-                else snq_node<3>(k, N, a.order[3], a.R, a.q_min, base_m, base_L, a.gl_x, a.gl_w, e, wt, ob);
+                if (tn == 1) snq_node_call<1>(k, N, a.order[1], a.R, a.q_min, base_m, base_L, a.gl_x, a.gl_w, e, wt, ob);
+                else if (tn == 2) snq_node_call<2>(k, N, a.order[2], a.R, a.q_min, base_m, base_L, a.gl_x, a.gl_w, e, wt, ob);
+                else snq_node_call<3>(k, N, a.order[3], a.R, a.q_min, base_m, base_L, a.gl_x, a.gl_w, e, wt, ob);
             }
             const bool keep = have && wt >= a.w_min;
-            const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0) ism[warp] = __popc(bal);
-            __syncthreads();
-            int off = 0;
-            for (int ww = 0; ww < kFusedWarps; ++ww) {
-                if (ww < warp) off += ism[ww];
-                my_cnt += ism[ww];
+            // staged in generation order; rank of every kept node among the kept nodes of its orthant in this chunk
+            if (tid < C) {
+                nd_eta[tid] = e[0];
+                nd_eta[C + tid] = e[1];
+                nd_eta[2 * C + tid] = e[2];
+                nd_w[tid] = keep ? wt : 0.0;
+                nd_orth[tid] = ob;
             }
-            if (keep) {
-                const int dst = off + __popc(bal & ((1u << lane) - 1u));
-                nd_eta[dst] = e[0];
-                nd_eta[C + dst] = e[1];
-                nd_eta[2 * C + dst] = e[2];
-                nd_w[dst] = wt;
-                nd_orth[dst] = ob;
-            }
-            if (tid == 0) a.blk_cnt[blockIdx.x] = my_cnt;
-        }
-        long long selr[kFusedMaxSteps];                                 // rows selected so far never compete again
+            int rank_w = 0;
 #pragma unroll
-        for (int c = 0; c < kFusedMaxSteps; ++c) selr[c] = c <= t ? sel_loc[c] : -1;
+            for (int o = 0; o < 8; ++o) {
+                const unsigned bal = __ballot_sync(0xffffffffu, keep && ob == o);
+                if (ob == o) rank_w = __popc(bal & ((1u << lane) - 1u));
+                if (lane == 0) ism[64 + warp * 8 + o] = __popc(bal);
+            }
+            __syncthreads();
+            if (keep) {
+                int r = rank_w;
+                for (int ww = 0; ww < warp; ++ww) r += ism[64 + ww * 8 + ob];
+                my_rank = r;
+            }
+            if (tid < 8) {
+                int c = 0;
+                for (int ww = 0; ww < kFusedWarps; ++ww) c += ism[64 + ww * 8 + tid];
+                a.blk_cnt[blockIdx.x * 8 + tid] = c;
+            }
+            if (warp == 1) chunk_mass_warp(nd_w, nd_orth, (int)min((int64_t)per, max((int64_t)0, N - (int64_t)blockIdx.x * per)),
+                                           lane, 0.0, a.blk_mass + (size_t)blockIdx.x * 8);
+            my_keep = keep;
+            my_ob = ob;
+        }
+        int selr[kFusedMaxSteps];                                       // rows selected so far never compete again
+#pragma unroll
+        for (int c = 0; c < kFusedMaxSteps; ++c) selr[c] = c <= t ? (int)sel_loc[c] : -1;
         long long a_row = -1;                                           // the team's stage-A row
         if (!dead) {
             double bs = 0.0;
@@ -395,28 +459,32 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int64_t i = i0 + u * stride;
-                    bool ok = mk[u] == 0;
-#pragma unroll
-                    for (int c = 0; c < kFusedMaxSteps; ++c) ok = ok && selr[c] != i;
-                    if (ok && better(val[u], i, bs, bi)) { bs = val[u]; bi = i; }
+                    const int ii = (int)i;
+                    const bool ok = mk[u] == 0 && ii != selr[0] && ii != selr[1] && ii != selr[2] && ii != selr[3];
+                    // (score desc, row asc; a NaN bound never wins) -- rows come in ascending order per thread
+                    if (ok && (bi < 0 ? val[u] == val[u] : val[u] > bs)) { bs = val[u]; bi = i; }
                 }
             }
             const Best b = group_argmax(bs, bi, tid_team, kFusedTeam, team_bar, ss + team * 16, si + team * 16);
             a_row = b.idx;
+            if (a_row >= 0 && warp_team == 1 && lane < 2) prefetch_l2(lane == 0 ? a.m + a_row : a.v + a_row);
             if (a_row >= 0 && warp_team == 0)
-                catchup_row<XT>(a_row, lane, X, a.d, a.d_pad, recs, a.rec_len, a.w_cap, a.W, tn, a.sqn, a.U, a.ldu,
+                catchup_row_call<XT>(a_row, lane, X, a.d, a.d_pad, recs, a.rec_len, a.w_cap, a.W, tn, a.sqn, a.U, a.ldu,
                                 a.tags, a.epoch, a.var, a.neg2ls2, uv);
             if (tid_team == 0) a.stage_rows[gt] = (int)a_row;
         }
+        FUSED_MARK();
         grid_barrier(a.barrier, target);
+        FUSED_MARK();
 
         // ---- P2: compaction of the kept nodes (generation order) ---------------------------------------------------
         int NK = 0;
         if (!dead) {
-            if (warp == 0) {
+            // per orthant: kept nodes in the chunks before this one, and in all chunks (warp o counts orthant o)
+            if (warp < 8) {
                 int before = 0, all = 0;
                 for (int k = lane; k < (int)gridDim.x; k += 32) {
-                    const int c = __ldcg(a.blk_cnt + k);
+                    const int c = __ldcg(a.blk_cnt + k * 8 + warp);
                     all += c;
                     if (k < (int)blockIdx.x) before += c;
                 }
@@ -425,20 +493,40 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
                     before += __shfl_xor_sync(0xffffffffu, before, o);
                     all += __shfl_xor_sync(0xffffffffu, all, o);
                 }
-                if (lane == 0) { ism[40] = before; ism[41] = all; }
+                if (lane == 0) { ism[32 + warp] = before; ism[40 + warp] = all; }
             }
             __syncthreads();
-            const int off = ism[40];
-            NK = ism[41];
-            if (tid < my_cnt) {
-                a.eta[off + tid] = nd_eta[tid];
-                if (tn >= 2) a.eta[N + off + tid] = nd_eta[C + tid];
-                if (tn >= 3) a.eta[2 * N + off + tid] = nd_eta[2 * C + tid];
-                a.w[off + tid] = nd_w[tid];
-                a.orth[off + tid] = nd_orth[tid];
+            if (tid == 0) {
+                int g = 0, kept = 0;
+                for (int o = 0; o < (1 << tn); ++o) {
+                    gbeg[o] = g;
+                    g += pad_nodes(ism[40 + o]);
+                    kept += ism[40 + o];
+                }
+                gbeg[1 << tn] = g;
+                ism[48] = kept;
             }
+            __syncthreads();
+            NK = ism[48];
+            if (my_keep) {
+                double* nd = a.nodes4 + 4 * (size_t)(gbeg[my_ob] + ism[32 + my_ob] + my_rank);
+                nd[0] = nd_eta[tid];
+                nd[1] = tn >= 2 ? nd_eta[C + tid] : 0.0;
+                nd[2] = tn >= 3 ? nd_eta[2 * C + tid] : 0.0;
+                nd[3] = nd_w[tid];
+            }
+            if ((int)blockIdx.x < (1 << tn)) {          // zero-weight tail of orthant blockIdx.x
+                const int o = blockIdx.x;
+                for (int k = gbeg[o] + ism[40 + o] + tid; k < gbeg[o + 1]; k += blockDim.x) {
+                    double* nd = a.nodes4 + 4 * (size_t)k;
+                    nd[0] = nd[1] = nd[2] = nd[3] = 0.0;
+                }
+            }
+            if (blockIdx.x == 0 && tid <= (1 << tn)) a.group_begin[tid] = gbeg[tid];
         }
+        FUSED_MARK();
         grid_barrier(a.barrier, target);
+        FUSED_MARK();
 
         // ---- P3: base masses and H(base); exact score of the stage-A rows ------------------------------------------
         EvalArgs ea;
@@ -449,10 +537,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
         ea.U = a.U;
         ea.ldu = a.ldu;
         ea.W0 = a.W;
-        ea.eta = a.eta;
-        ea.w = a.w;
+        ea.eta = nullptr;
+        ea.w = nullptr;
+        ea.nodes4 = a.nodes4;
         ea.phi = a.phi;
-        ea.orth = a.orth;
+        ea.orth = nullptr;
         ea.group_begin = nullptr;
         ea.n_nodes = N;
         ea.n_kept = nullptr;
@@ -469,19 +558,22 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
         ea.force_block = 1;
         ea.t = tn;
         if (!dead) {
-            snq_masses_block(tn, NK, a.w, a.orth, a.log1p_eps, part, masses, hb);
+            for (int k = tid; k < (int)gridDim.x * 8; k += blockDim.x) chunk_part[k] = __ldcg(a.blk_mass + k);
+            __syncthreads();
+            masses_from_chunks(tn, (int)gridDim.x, chunk_part, a.log1p_eps, masses, hb);
+            FUSED_MARK();
             if (blockIdx.x == 0 && tid < 8) {
                 if (tid < (1 << tn)) a.masses[tid] = masses[tid];
                 if (tid < 2) a.hbase[tid] = hb[tid];
                 if (tid == 2) a.counters[3] = NK;
             }
             if (a_row >= 0 && tag_step(__ldcg(a.tags + a_row), a.epoch) != tn) {
-                if (tn == 1) eval_candidate<1>(ea, a_row, tid_team, kFusedTeam, team_bar, red, N, NK, masses, hb[0]);
-                else if (tn == 2) eval_candidate<2>(ea, a_row, tid_team, kFusedTeam, team_bar, red, N, NK, masses, hb[0]);
-                else eval_candidate<3>(ea, a_row, tid_team, kFusedTeam, team_bar, red, N, NK, masses, hb[0]);
+                eval_dispatch(tn, ea, a_row, tid_team, kFusedTeam, team_bar, red, phi_s, gbeg, masses, hb[0]);
             }
         }
+        FUSED_MARK();
         grid_barrier(a.barrier, target);
+        FUSED_MARK();
 
         // ---- P4: threshold of the lazy-greedy bound, worklist ------------------------------------------------------
         if (!dead) {
@@ -497,23 +589,41 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
             double thr = -INFINITY;
             if (b.idx >= 0 && b.score == b.score) thr = b.score;
             thr = thr - a.margin - hb[0];
-            for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + (tid & ~31); i0 < a.n; i0 += (int64_t)gridDim.x * blockDim.x) {
-                const int64_t i = i0 + lane;
-                const uint8_t mk = i < a.n ? a.mask[i] : (uint8_t)1;
-                const double gv = i < a.n ? __ldcg(a.gain + i) : 0.0;
-                bool take = mk == 0 && gv >= thr;
+            const int64_t wstride = (int64_t)gridDim.x * blockDim.x;
+            for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + (tid & ~31); i0 < a.n; i0 += 2 * wstride) {
+                uint8_t mk[2];
+                double gv[2];
 #pragma unroll
-                for (int c = 0; c < kFusedMaxSteps; ++c) take = take && selr[c] != i;
-                const unsigned ballot = __ballot_sync(0xffffffffu, take);
-                if (ballot != 0) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(a.counters, __popc(ballot));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (take) a.worklist[base + __popc(ballot & ((1u << lane) - 1u))] = (int)i;
+                for (int u = 0; u < 2; ++u) {
+                    const int64_t i = i0 + u * wstride + lane;
+                    mk[u] = i < a.n ? a.mask[i] : (uint8_t)1;
+                    gv[u] = i < a.n ? __ldcg(a.gain + i) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int64_t i = i0 + u * wstride + lane;
+                    const int ii = (int)i;
+                    const bool take = mk[u] == 0 && gv[u] >= thr && ii != selr[0] && ii != selr[1] && ii != selr[2] &&
+                                      ii != selr[3];
+                    unsigned ballot = __ballot_sync(0xffffffffu, take);
+                    if (ballot != 0) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(a.counters, __popc(ballot));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (take) a.worklist[base + __popc(ballot & ((1u << lane) - 1u))] = ii;
+                        while (ballot != 0) {                           // what P5 will read of these rows, into L2
+                            const int src = __ffs(ballot) - 1;
+                            ballot &= ballot - 1;
+                            const int64_t r = __shfl_sync(0xffffffffu, ii, src);
+                            prefetch_row<XT>(r, lane, X, a.d_pad, a.U, a.ldu, a.W + tn - 1, a.m, a.v, a.sqn, a.gain, a.tags);
+                        }
+                    }
                 }
             }
         }
+        FUSED_MARK();
         grid_barrier(a.barrier, target);
+        FUSED_MARK();
 
         // ---- P5: exact scores of the worklist ----------------------------------------------------------------------
         {
@@ -528,7 +638,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
                         const int64_t item_w = gt + (int64_t)(r0 + warp_team) * n_teams;
                         if (item_w < n_items) {
                             const int64_t i = __ldcg(a.worklist + item_w);
-                            catchup_row<XT>(i, lane, X, a.d, a.d_pad, recs, a.rec_len, a.w_cap, a.W, tn, a.sqn, a.U,
+                            catchup_row_call<XT>(i, lane, X, a.d, a.d_pad, recs, a.rec_len, a.w_cap, a.W, tn, a.sqn, a.U,
                                             a.ldu, a.tags, a.epoch, a.var, a.neg2ls2, uv);
                         }
                         team_barrier(team_bar, kFusedTeam);
@@ -537,9 +647,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
                             if (item >= n_items) break;
                             const int64_t i = __ldcg(a.worklist + item);
                             if (tag_step(__ldcg(a.tags + i), a.epoch) != tn) {
-                                if (tn == 1) eval_candidate<1>(ea, i, tid_team, kFusedTeam, team_bar, red, N, NK, masses, hb[0]);
-                                else if (tn == 2) eval_candidate<2>(ea, i, tid_team, kFusedTeam, team_bar, red, N, NK, masses, hb[0]);
-                                else eval_candidate<3>(ea, i, tid_team, kFusedTeam, team_bar, red, N, NK, masses, hb[0]);
+                                eval_dispatch(tn, ea, i, tid_team, kFusedTeam, team_bar, red, phi_s, gbeg, masses, hb[0]);
                             }
                             if (tid_team == 0) {
                                 const double s = __ldcg(a.score + i);
@@ -553,11 +661,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
                          item += (int64_t)gridDim.x * kFusedWarps) {
                         const int64_t i = __ldcg(a.worklist + item);
                         if (tag_step(__ldcg(a.tags + i), a.epoch) != tn) {
-                            catchup_row<XT>(i, lane, X, a.d, a.d_pad, recs, a.rec_len, a.w_cap, a.W, tn, a.sqn, a.U,
+                            catchup_row_call<XT>(i, lane, X, a.d, a.d_pad, recs, a.rec_len, a.w_cap, a.W, tn, a.sqn, a.U,
                                             a.ldu, a.tags, a.epoch, a.var, a.neg2ls2, uv);
-                            if (tn == 1) eval_candidate<1>(ea, i, lane, 32, 0, red, N, NK, masses, hb[0]);
-                            else if (tn == 2) eval_candidate<2>(ea, i, lane, 32, 0, red, N, NK, masses, hb[0]);
-                            else eval_candidate<3>(ea, i, lane, 32, 0, red, N, NK, masses, hb[0]);
+                            eval_dispatch(tn, ea, i, lane, 32, 0, red, phi_s, gbeg, masses, hb[0]);
                         }
                         __syncwarp();
                         const double s = __ldcg(a.score + i);
@@ -567,8 +673,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
             }
             const Best b = group_argmax(bs, bi, tid_team, kFusedTeam, team_bar, ss + team * 16, si + team * 16);
             if (tid_team == 0) a.blk_best[gt] = b;
+            if (warp_team == 0 && b.idx >= 0)
+                prefetch_row<XT>(b.idx, lane, X, a.d_pad, a.U, a.ldu, a.W + tn, a.m, a.v, a.sqn, a.gain, a.tags);
         }
+        FUSED_MARK();
         grid_barrier(a.barrier, target);
+        FUSED_MARK();
 
         // ---- P6: the step's winner ---------------------------------------------------------------------------------
         {
@@ -585,7 +695,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
                 if (tid < 3) a.counters[tid] = 0;                       // ready for the next greedy step
             }
         }
+        FUSED_MARK();
     }
+#undef FUSED_MARK
 }
 
 }  // namespace italk

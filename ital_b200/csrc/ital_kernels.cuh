@@ -106,28 +106,33 @@ __device__ __forceinline__ void team_barrier(int id, int n) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
 
-// Standard normal CDF from a table: (Phi, phi) on the grid x_k = -8.5 + k/32 and a 6th-order Taylor step around the
-// nearest grid point (|delta| <= 1/64; derivatives of Phi are Hermite polynomials times phi).  Absolute error below
-// 1e-15 against erfc, ~30 FP64 instructions instead of ~150; the quadrature sums need absolute, not relative accuracy.
+// Standard normal CDF from a table: (Phi, phi) on the grid x_k = -8.5 + k/128 and a 5th-order Taylor step around the
+// nearest grid point (|delta| <= 1/256; derivatives of Phi are Hermite polynomials times phi).  Absolute error below
+// 1e-16 against erfc, ~25 FP64 instructions and one 16-byte load instead of ~150 instructions; the quadrature sums
+// need absolute, not relative accuracy.  The scoring kernels keep the table (35 KB) in shared memory: the lanes of a
+// warp look up unrelated entries, which the L1 serves one cache line per cycle.
 constexpr double kPhiXMax = 8.5;
-constexpr int kPhiPerUnit = 32;
-constexpr int kPhiTableLen = 2 * 17 * kPhiPerUnit / 2 + 1;     // 545 grid points on [-8.5, 8.5]
+constexpr int kPhiPerUnit = 128;
+constexpr int kPhiTableLen = 17 * kPhiPerUnit + 1;             // 2177 grid points on [-8.5, 8.5]
 
-__device__ __forceinline__ double phi_tab(const double2* __restrict__ tab, double x) {
-    if (!(x > -kPhiXMax)) return 0.0;
-    if (!(x < kPhiXMax)) return 1.0;
+__device__ __forceinline__ double phi_tab(const double2* tab, double x) {
+    x = fmin(fmax(x, -kPhiXMax), kPhiXMax);                     // Phi(-8.5) = 1e-17, Phi(8.5) = 1 in double; NaN -> 0
     const int k = __double2int_rn((x + kPhiXMax) * kPhiPerUnit);
-    const double xk = -kPhiXMax + (double)k * (1.0 / kPhiPerUnit);
+    const double xk = fma((double)k, 1.0 / kPhiPerUnit, -kPhiXMax);
     const double dl = x - xk;
-    const double2 t = __ldg(tab + k);
+    const double2 t = tab[k];
     const double x2 = xk * xk;
     const double c2 = -0.5 * xk;
     const double c3 = (x2 - 1.0) * (1.0 / 6.0);
     const double c4 = -xk * (x2 - 3.0) * (1.0 / 24.0);
     const double c5 = (x2 * (x2 - 6.0) + 3.0) * (1.0 / 120.0);
-    const double c6 = -xk * (x2 * (x2 - 10.0) + 15.0) * (1.0 / 720.0);
-    const double poly = fma(dl, fma(dl, fma(dl, fma(dl, fma(dl, c6, c5), c4), c3), c2), 1.0);
+    const double poly = fma(dl, fma(dl, fma(dl, fma(dl, c5, c4), c3), c2), 1.0);
     return fma(t.y * dl, poly, t.x);
+}
+
+// copy of the table into shared memory (every thread of the block; followed by a block barrier at the caller)
+__device__ __forceinline__ void phi_tab_to_shared(double2* dst, const double2* __restrict__ src) {
+    for (int k = threadIdx.x; k < kPhiTableLen; k += blockDim.x) dst[k] = __ldg(src + k);
 }
 
 __device__ __forceinline__ double mi_term(double p, double log1p_eps) {
@@ -815,36 +820,76 @@ k_extend_bulk_multi(const XT* __restrict__ X, int64_t n, int d_pad, const double
 //
 // catchup_row: one warp, row i.  `recs` are the records of the selected points (stride rec_len; global or shared
 // memory), `uv` is a warp-private scratch of w_cap doubles.  The row's tag keeps the number of valid batch columns.
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// Everything the catch-up, the scoring and the record of row i will read, into L2 (fire and forget): the row of X, its
+// projection entries, moments and tag.  Called by a whole warp for one row.
+template <typename XT>
+__device__ __forceinline__ void prefetch_row(int64_t i, int lane, const XT* X, int d_pad, const double* U, int64_t ldu,
+                                             int n_cols, const double* m, const double* v, const double* sqn,
+                                             const double* gain, const uint32_t* tags) {
+    const char* xr = reinterpret_cast<const char*>(X + i * (int64_t)d_pad);
+    const int lines = (int)((d_pad * sizeof(XT) + 127) / 128);
+    for (int l = lane; l < lines; l += 32) prefetch_l2(xr + l * 128);
+    for (int j = lane; j < n_cols; j += 32) prefetch_l2(U + (int64_t)j * ldu + i);
+    if (lane == 0) prefetch_l2(m + i);
+    if (lane == 1) prefetch_l2(v + i);
+    if (lane == 2) prefetch_l2(sqn + i);
+    if (lane == 3) prefetch_l2(gain + i);
+    if (lane == 4) prefetch_l2(tags + i);
+}
+
 template <typename XT>
 __device__ __forceinline__ void catchup_row(int64_t i, int lane, const XT* __restrict__ X, int d, int d_pad,
                                             const double* recs, int64_t rec_len, int w_cap, int W, int t,
                                             const double* __restrict__ sqn, double* U, int64_t ldu, uint32_t* tags,
                                             uint32_t epoch, double var, double neg2ls2, double* uv) {
     constexpr int VN = Vec<XT>::N;
-    const uint32_t tag = __ldcg(tags + i);
-    const int c0 = tag_ncol(tag, epoch);
-    if (c0 >= t) return;
     const int nchunks = d_pad / (32 * VN);
     const bool fixed = nchunks == 1 || nchunks == 2 || nchunks == 4;    // k_extend<XT, NC> vs k_extend<XT, 0>
-    for (int j = lane; j < W + c0; j += 32) uv[j] = __ldcg(U + (int64_t)j * ldu + i);
-    __syncwarp();
+    // every load the row needs is issued before the first one is used: the tag, the row of X (kept in registers for
+    // the fixed shapes) and the projection entries up to the last column that can be valid (entries past the valid
+    // ones are overwritten below before they are read)
+    const uint32_t tag = __ldcg(tags + i);
     const XT* xrow = X + i * (int64_t)d_pad;
+    Vec<XT> xr[4];
+    if (fixed) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (c < nchunks) xr[c].load(xrow + (c * 32 + lane) * VN);
+    }
     const double sq = sqn[i];
+    for (int j = lane; j < W + t - 1; j += 32) uv[j] = __ldcg(U + (int64_t)j * ldu + i);
+    const int c0 = tag_ncol(tag, epoch);
+    if (c0 >= t) return;
+    __syncwarp();
     for (int col = c0; col < t; ++col) {
         const double* rec = recs + (int64_t)col * rec_len;
         const double* z = rec + 8 + w_cap;
         double a0 = 0.0, a1 = 0.0;
-        for (int c = 0; c < nchunks; ++c) {
-            Vec<XT> x;
-            x.load(xrow + (c * 32 + lane) * VN);
+        if (fixed) {
 #pragma unroll
-            for (int e = 0; e < VN; e += 2) {
-                const int cc = (c * 32 + lane) * VN + e;
-                const double z0 = cc < d ? z[cc] : 0.0, z1 = cc + 1 < d ? z[cc + 1] : 0.0;
-                if (fixed) {
-                    a0 = fma(x.get(e), z0, a0);
-                    a1 = fma(x.get(e + 1), z1, a1);
-                } else {
+            for (int c = 0; c < 4; ++c) {
+                if (c < nchunks) {
+#pragma unroll
+                    for (int e = 0; e < VN; e += 2) {
+                        const int cc = (c * 32 + lane) * VN + e;
+                        const double z0 = cc < d ? z[cc] : 0.0, z1 = cc + 1 < d ? z[cc + 1] : 0.0;
+                        a0 = fma(xr[c].get(e), z0, a0);
+                        a1 = fma(xr[c].get(e + 1), z1, a1);
+                    }
+                }
+            }
+        } else {
+            for (int c = 0; c < nchunks; ++c) {
+                Vec<XT> x;
+                x.load(xrow + (c * 32 + lane) * VN);
+#pragma unroll
+                for (int e = 0; e < VN; e += 2) {
+                    const int cc = (c * 32 + lane) * VN + e;
+                    const double z0 = cc < d ? z[cc] : 0.0, z1 = cc + 1 < d ? z[cc + 1] : 0.0;
                     a0 = fma(x.get(e), z0, a0);
                     a0 = fma(x.get(e + 1), z1, a0);
                 }
@@ -894,21 +939,31 @@ __global__ void __launch_bounds__(256) k_catchup(const int* __restrict__ count, 
                         neg2ls2, uv);
 }
 
-// Score of a single sample (first greedy step): MI of one variable in closed form (ital/ital.py:364-369, 183-224).
-__device__ __forceinline__ double score0_value(double mean, double var_raw, double log1p_eps, double scale,
-                                               const double2* __restrict__ phi) {
+// Score of a single sample (first greedy step): MI of one variable in closed form (ital/ital.py:364-369, 183-224),
+//   sum_r p_r (lc - log(p_r + eps)) = lc + H(u),  H(u) = -Phi(u) log(Phi(u) + eps) - Phi(-u) log(Phi(-u) + eps),
+// u = |m| / sqrt(v) (H is even; p_0 + p_1 = 1).  H comes from a table of degree-7 polynomials on intervals of width
+// 1/16 over [0, 8.5] (built on the host in extended precision, absolute error 1e-16 against erfc / log): ~40 FP64
+// instructions per row instead of ~250, which is what a pass over 10^6 candidates is bound by.
+constexpr int kHTabPerUnit = 16;
+constexpr double kHTabMax = 8.5;
+constexpr int kHTabLen = 136;                            // intervals; 8 coefficients each (ascending powers)
+
+__device__ __forceinline__ double h_tab(const double* __restrict__ tab, double u) {
+    u = fmin(u, kHTabMax);
+    const int k = min((int)(u * kHTabPerUnit), kHTabLen - 1);
+    const double x = fma(u, 2.0 * kHTabPerUnit, -(2.0 * k + 1.0));         // position in the interval, [-1, 1]
+    const double2* c = reinterpret_cast<const double2*>(tab + 8 * k);
+    const double2 c01 = __ldg(c), c23 = __ldg(c + 1), c45 = __ldg(c + 2), c67 = __ldg(c + 3);
+    return fma(x, fma(x, fma(x, fma(x, fma(x, fma(x, fma(x, c67.y, c67.x), c45.y), c45.x), c23.y), c23.x), c01.y), c01.x);
+}
+
+__device__ __forceinline__ double score0_value(double mean, double var_raw, double lc, double scale,
+                                               const double* __restrict__ htab) {
     const double var_i = fmax(var_raw, 0.0);             // predict_stored(cov_mode='diag') clamps (gp.py:229)
     const double sd = sqrt(var_i);
-    double p1, p0;
-    if (sd > 0.0) {
-        const double zz = mean / sd;
-        p1 = phi_tab(phi, zz);
-        p0 = phi_tab(phi, -zz);
-    } else {
-        p1 = mean > 0.0 ? 1.0 : 0.0;
-        p0 = 1.0 - p1;
-    }
-    return scale * (mi_term(p0, log1p_eps) + mi_term(p1, log1p_eps));
+    const double u = sd > 0.0 ? fabs(mean) / sd : kHTabMax;
+    if (u != u) return u;                                // a NaN mean stays NaN (and never wins)
+    return scale * (lc + h_tab(htab, u));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -918,7 +973,7 @@ __global__ void __launch_bounds__(256) k_score0(int64_t n, const double* __restr
                                                 const double* __restrict__ v, const uint8_t* __restrict__ mask,
                                                 double* __restrict__ score, double* __restrict__ gain,
                                                 Best* __restrict__ block_best, double log1p_eps, double scale,
-                                                const double2* __restrict__ phi) {
+                                                const double* __restrict__ htab) {
     pdl_enter();
     // perfect / mistaken user: scale = 1, log1p_eps = log(1 + eps) (a mistaken user adds a constant later);
     // general model (label_prob < 1): scale = label_prob, log1p_eps = (1-mp) log(1+eps) + mp log(eps)
@@ -942,7 +997,7 @@ __global__ void __launch_bounds__(256) k_score0(int64_t n, const double* __restr
             if (i >= n) break;
             double s = nan("");
             if (mk[u] == 0) {
-                s = score0_value(mm[u], vv[u], log1p_eps, scale, phi);
+                s = score0_value(mm[u], vv[u], log1p_eps, scale, htab);
                 gain[i] = s;
                 if (better(s, i, bs, bi)) { bs = s; bi = i; }
             }
@@ -1108,11 +1163,13 @@ struct EvalArgs {
     const double* U;
     int64_t ldu;
     int W0;
-    const double* eta;          // [t][n_nodes]
-    const double* w;
+    const double* eta;          // k_eval_sorted: [t][n_nodes]
+    const double* w;            // k_eval_sorted
+    const double* nodes4;       // k_eval<T>: {eta_0, eta_1, eta_2, weight} per node, sorted by orthant, every orthant
+                                // zero-padded to a multiple of kNodePad nodes; group_begin[2^T + 1] = offsets
     const double2* phi;         // table of phi_tab
-    const int* orth;            // k_eval<T>: orthant id per node
-    const int* group_begin;     // k_eval_sorted: 2^t + 1 offsets
+    const int* orth;            // (orthant id per generated node: k_snq_generate -> k_snq_finalize)
+    const int* group_begin;     // 2^t + 1 offsets of the orthants in the node list
     int64_t n_nodes;            // stride of eta (nodes generated)
     const int* n_kept;          // nodes kept after dropping negligible weights (device; k_eval<T>)
     const double* masses;       // 2^t base orthant probabilities (device)
@@ -1135,17 +1192,24 @@ __device__ __forceinline__ int eval_team_size(int n_items, int force_block) {
     return (force_block || n_items < (int)(gridDim.x * (blockDim.x >> 5))) ? (int)blockDim.x : 32;
 }
 
+constexpr int kNodePad = 256;            // every orthant's nodes are zero-padded to a multiple of this (one node per thread of a team)
+
+__host__ __device__ __forceinline__ int pad_nodes(int cnt) { return (cnt + kNodePad - 1) / kNodePad * kNodePad; }
+
 // Exact score of candidate i by a team of TPC threads (32, or 256 = eight warps synchronising on barrier `bar_id`)
-// with the nodes of k_snq_generate<T> (generation order, orthant id per node).  Thread `tid_team` takes the nodes
-// tid_team + TPC * (4 j + u); the partial sums are reduced by an xor butterfly inside every warp and then warp by
-// warp in ascending order, so a row's score depends on the team size only.  `red` holds 8 * 2^T doubles per team.
-// masses / h_base may live in shared or global memory.  Returns after the row's score, gain and tag are written.
+// with the nodes of the step: {eta, weight} packed per node, sorted by orthant in generation order, every orthant
+// padded with zero-weight nodes to a multiple of 256 (no tail, no orthant id per node, one accumulator per thread).
+// Thread `tid_team` takes the nodes g0 + tid_team + TPC j of an orthant in that order; the partial sums are reduced
+// by an xor butterfly inside every warp and then warp by warp in ascending order, so a row's score depends on the
+// team size only.  `red` holds 8 * 2^T doubles per team; `phi` is the table of phi_tab (shared memory); `gb` the
+// orthant offsets and `masses` the base orthant masses (shared or global memory).  Returns after the row's score,
+// gain and tag are written.
 template <int T>
 __device__ __forceinline__ void eval_candidate(const EvalArgs& a, int64_t i, int tid_team, int TPC, int bar_id,
-                                               double* red, int64_t N, int64_t NK, const double* masses,
+                                               double* red, const double2* phi, const int* gb, const double* masses,
                                                double h_base) {
     constexpr int NB = 1 << T;
-    double l[T];
+    double l[3] = {0.0, 0.0, 0.0};
     double s2 = a.v[i];
 #pragma unroll
     for (int j = 0; j < T; ++j) {
@@ -1155,35 +1219,33 @@ __device__ __forceinline__ void eval_candidate(const EvalArgs& a, int64_t i, int
     const double mi = a.m[i];
     const double s = s2 > 0.0 ? sqrt(s2) : 0.0;
     const double inv_s = s > 0.0 ? 1.0 / s : 0.0;
+    const double2* nd = reinterpret_cast<const double2*>(a.nodes4);
     double acc[NB];
 #pragma unroll
-    for (int b = 0; b < NB; ++b) acc[b] = 0.0;
-    // four nodes per thread and trip: independent erfc chains hide the FP64 latency
-    for (int64_t q = tid_team; q < NK; q += 4 * TPC) {
-        double num[4], ww[4];
-        int ob[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int64_t qq = q + (int64_t)u * TPC;
-            const bool ok = qq < NK;
-            ww[u] = ok ? a.w[qq] : 0.0;
-            ob[u] = ok ? a.orth[qq] : 0;
-            num[u] = mi;
-#pragma unroll
-            for (int j = 0; j < T; ++j) num[u] = fma(l[j], ok ? a.eta[(int64_t)j * N + qq] : 0.0, num[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const double cdf = s > 0.0 ? phi_tab(a.phi, num[u] * inv_s) : (num[u] > 0.0 ? 1.0 : 0.0);
-            const double term = ww[u] * cdf;
-#pragma unroll
-            for (int b = 0; b < NB; ++b) acc[b] += (ob[u] == b) ? term : 0.0;
-        }
-    }
-#pragma unroll
     for (int b = 0; b < NB; ++b) {
+        const int g0 = gb[b], g1 = gb[b + 1];
+        double ac = 0.0;
+        if (s > 0.0) {
+#pragma unroll 4
+            for (int q = g0 + tid_team; q < g1; q += TPC) {
+                const double2 n01 = nd[2 * q], n23 = nd[2 * q + 1];
+                double num = fma(l[0], n01.x, mi);
+                if (T >= 2) num = fma(l[1], n01.y, num);
+                if (T >= 3) num = fma(l[2], n23.x, num);
+                ac = fma(n23.y, phi_tab(phi, num * inv_s), ac);
+            }
+        } else {                                        // no conditional variance left: Phi is a step
+            for (int q = g0 + tid_team; q < g1; q += TPC) {
+                const double2 n01 = nd[2 * q], n23 = nd[2 * q + 1];
+                double num = fma(l[0], n01.x, mi);
+                if (T >= 2) num = fma(l[1], n01.y, num);
+                if (T >= 3) num = fma(l[2], n23.x, num);
+                ac = fma(n23.y, num > 0.0 ? 1.0 : 0.0, ac);
+            }
+        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], o);
+        for (int o = 16; o > 0; o >>= 1) ac += __shfl_xor_sync(0xffffffffu, ac, o);
+        acc[b] = ac;
     }
     if (TPC > 32) {
         if ((tid_team & 31) == 0) {
@@ -1192,23 +1254,32 @@ __device__ __forceinline__ void eval_candidate(const EvalArgs& a, int64_t i, int
         }
         team_barrier(bar_id, TPC);
     }
-    if (tid_team == 0) {
+    if (tid_team < 32) {
+        // lane b of the team's first warp finishes orthant b (its two logarithms); lane 0 adds the terms in
+        // ascending order of b
+        double p_plus = 0.0;
+        if (TPC > 32) {
+            if (tid_team < NB)
+                for (int k = 0; k < TPC / 32; ++k) p_plus += red[tid_team * 8 + k];
+        } else {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) p_plus = (tid_team == b) ? acc[b] : p_plus;
+        }
+        double term = 0.0;
+        if (tid_team < NB) {
+            const double p_minus = fmax(masses[tid_team] - p_plus, 0.0);
+            term = mi_term(p_plus, a.log1p_eps) + mi_term(p_minus, a.log1p_eps);
+        }
         double sc = 0.0;
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            double p_plus = acc[b];
-            if (TPC > 32) {
-                p_plus = 0.0;
-                for (int k = 0; k < TPC / 32; ++k) p_plus += red[b * 8 + k];
-            }
-            const double p_minus = fmax(masses[b] - p_plus, 0.0);
-            sc += mi_term(p_plus, a.log1p_eps) + mi_term(p_minus, a.log1p_eps);
+        for (int b = 0; b < NB; ++b) sc += __shfl_sync(0xffffffffu, term, b);
+        if (tid_team == 0) {
+            a.tags[i] = tag_with_step(__ldcg(a.tags + i), a.epoch, a.t);
+            a.score[i] = sc;
+            a.gain[i] = sc - h_base;
+            atomicAdd(a.n_scored, 1);
+            if (s2 < a.flag_var) atomicAdd(a.n_flagged, 1);
         }
-        a.tags[i] = tag_with_step(__ldcg(a.tags + i), a.epoch, a.t);
-        a.score[i] = sc;
-        a.gain[i] = sc - h_base;
-        atomicAdd(a.n_scored, 1);
-        if (s2 < a.flag_var) atomicAdd(a.n_flagged, 1);
     }
     if (TPC > 32) team_barrier(bar_id, TPC);            // red and the tag are free again
 }
@@ -1222,14 +1293,18 @@ __global__ void __launch_bounds__(256) k_eval(EvalArgs a) {
     const int tid_team = threadIdx.x % TPC;
     const int team_global = (blockIdx.x * blockDim.x + threadIdx.x) / TPC;
     const int teams_total = (gridDim.x * blockDim.x) / TPC;
-    const int64_t N = a.n_nodes;
-    const int64_t NK = *a.n_kept;
     const double h_base = *a.h_base;
     __shared__ double red[8 * NB];
+    __shared__ int gb[NB + 1];
+    __shared__ double2 phi_s[kPhiTableLen];
+    if (blockIdx.x * (blockDim.x / TPC) >= n_items) return;     // no item for this block
+    phi_tab_to_shared(phi_s, a.phi);
+    if (threadIdx.x <= NB) gb[threadIdx.x] = a.group_begin[threadIdx.x];
+    __syncthreads();
     for (int item = team_global; item < n_items; item += teams_total) {
         const int64_t i = a.list[item];
         if (tag_step(a.tags[i], a.epoch) == a.t) continue;  // scored earlier in this step (team-uniform)
-        eval_candidate<T>(a, i, tid_team, TPC, 0, red, N, NK, a.masses, h_base);
+        eval_candidate<T>(a, i, tid_team, TPC, 0, red, phi_s, gb, a.masses, h_base);
     }
 }
 
@@ -1257,6 +1332,9 @@ __global__ void __launch_bounds__(256) k_eval_sorted(EvalArgs a) {
     const int teams_total = (gridDim.x * blockDim.x) / TPC;
     const int64_t N = a.n_nodes;
     __shared__ double red[8];
+    __shared__ double2 phi_s[kPhiTableLen];
+    phi_tab_to_shared(phi_s, a.phi);
+    __syncthreads();
     for (int item = team_global; item < n_items; item += teams_total) {
         const int64_t i = a.list[item];
         if (tag_step(a.tags[i], a.epoch) == a.t) continue;
@@ -1283,7 +1361,7 @@ __global__ void __launch_bounds__(256) k_eval_sorted(EvalArgs a) {
 #pragma unroll
                 for (int j = 0; j < MAXT; ++j)
                     if (j < t) num = fma(l[j], a.eta[(int64_t)j * N + q], num);
-                const double cdf = s > 0.0 ? phi_tab(a.phi, num * inv_s) : (num > 0.0 ? 1.0 : 0.0);
+                const double cdf = s > 0.0 ? phi_tab(phi_s, num * inv_s) : (num > 0.0 ? 1.0 : 0.0);
                 acc = fma(a.w[q], cdf, acc);
             }
             const double p_plus = team_sum(acc, TPC, red);
@@ -1347,6 +1425,9 @@ __global__ void __launch_bounds__(256) k_eval_general(GeneralArgs a) {
     double* sBp = Bm + G;               // [NS]
     double* sBm = sBp + NS;             // [NS]
     double* red = sBm + NS;             // [G][8][3] per-warp partials, later [8] for the final sum
+    double2* phi_s = reinterpret_cast<double2*>(red + (size_t)G * 24 + 8);      // table of phi_tab
+    phi_tab_to_shared(phi_s, a.phi);
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_items = *a.count;
     const int64_t N = a.n_nodes;
@@ -1375,7 +1456,7 @@ __global__ void __launch_bounds__(256) k_eval_general(GeneralArgs a) {
                 for (int j = 0; j < 4; ++j)
                     if (j < t) num = fma(l[j], a.eta[(int64_t)j * N + q], num);
                 const double wq = a.w[q];
-                const double cdf = s > 0.0 ? phi_tab(a.phi, num * inv_s) : (num > 0.0 ? 1.0 : 0.0);
+                const double cdf = s > 0.0 ? phi_tab(phi_s, num * inv_s) : (num > 0.0 ? 1.0 : 0.0);
                 const double dp = (1.0 - num) * inv_st, dm = (-1.0 - num) * inv_st;
                 xa = fma(wq, cdf, xa);
                 xp = fma(wq, exp(-0.5 * dp * dp), xp);
@@ -1521,36 +1602,45 @@ __global__ void __launch_bounds__(256) k_snq_generate(int q, double R, int q_min
 }
 
 // Base orthant probabilities P_b = sum of the kept weights per orthant, the score of the base alone and the total
-// mass, in a fixed order: threads 0..255 of the block take the nodes k, k + 256, ...; xor butterfly inside every
-// warp; the eight warp partials are added in ascending order.  Every thread of the block must call it (it contains
-// block barriers); `part` is 8 x 8 doubles of shared memory; thread 0 writes masses[0 .. 2^t), h_out[0] = H(base),
-// h_out[1] = total mass (shared or global memory).  t <= 3.
-__device__ __forceinline__ void snq_masses_block(int t, int kept, const double* w, const int* orth, double log1p_eps,
-                                                 double (*part)[8], double* masses, double* h_out) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x < 256) {
-        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int k = threadIdx.x; k < kept; k += 256) {
-            const int ob = orth[k];
-            const double wk = w[k];
+// mass, in a fixed two-level order shared by the one-CTA finalize kernel and the persistent fetch kernel (where every
+// CTA generates one chunk of the nodes): the nodes are cut into `n_chunks` chunks of ceil(N / n_chunks) consecutive
+// generated nodes; inside a chunk lane l of a warp adds the kept nodes among the generated nodes l, l + 32, ... of the
+// chunk and the lanes are combined by an xor butterfly (chunk_mass_warp); the chunk sums are then added in ascending chunk order
+// (masses_from_chunks).  t <= 3.
+__device__ __forceinline__ void chunk_mass_warp(const double* w, const int* orth, int cnt, int lane, double w_min,
+                                                double* out8) {
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = lane; k < cnt; k += 32) {
+        const int ob = orth[k];
+        const double wk = w[k];
+        if (wk >= w_min) {
 #pragma unroll
             for (int b = 0; b < 8; ++b) acc[b] += (ob == b) ? wk : 0.0;
         }
+    }
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
+    for (int b = 0; b < 8; ++b) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], o);
-            if (lane == 0) part[warp][b] = acc[b];
-        }
+        for (int o = 16; o > 0; o >>= 1) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], o);
+        if (lane == 0) out8[b] = acc[b];
+    }
+}
+
+// chunk_part: [n_chunks][8] in shared memory.  Every thread of the CTA must call it (block barriers inside); thread b < 8
+// adds orthant b over the chunks, thread 0 writes h_out[0] = H(base), h_out[1] = total mass.
+__device__ __forceinline__ void masses_from_chunks(int t, int n_chunks, const double* chunk_part, double log1p_eps,
+                                                   double* masses, double* h_out) {
+    if (threadIdx.x < 8) {
+        double p = 0.0;
+        for (int c = 0; c < n_chunks; ++c) p += chunk_part[c * 8 + threadIdx.x];
+        masses[threadIdx.x] = p;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         const int nb = 1 << t;
         double h = 0.0, tot = 0.0;
         for (int b = 0; b < nb; ++b) {
-            double p = 0.0;
-            for (int k = 0; k < 8; ++k) p += part[k][b];
-            masses[b] = p;
+            const double p = masses[b];
             h += mi_term(p, log1p_eps);
             tot += p;
         }
@@ -1560,76 +1650,114 @@ __device__ __forceinline__ void snq_masses_block(int t, int kept, const double* 
     __syncthreads();
 }
 
-// Drops the nodes whose weight is below w_min (stable, out of place: about half of the nodes at t = 3 carry a
-// total mass of ~1e-11), then sums the base orthant probabilities P_b = sum of the kept weights per orthant and
-// the score of the base alone.  One block; every thread owns a contiguous range of nodes, one block-wide scan of
-// the kept counts gives the output offsets; fixed order throughout.
+// Drops the nodes whose weight is below w_min (about half of the nodes at t = 3 carry a total mass of ~1e-11), sorts
+// the kept ones by orthant (stable: generation order inside an orthant) and packs them as {eta_0, eta_1, eta_2,
+// weight} records, every orthant zero-padded to a multiple of kNodePad nodes (group_begin[2^t + 1] = offsets); then
+// sums the base orthant probabilities and the score of the base alone (chunk_mass_warp / masses_from_chunks).  One
+// block; every warp owns a contiguous range of generated nodes and walks it 32 at a time (coalesced); ballots per
+// orthant give the stable ranks inside the warp, the warp totals the offsets between warps.
+// N <= 13824 = 32 warps x kIt x 32 nodes.
 __global__ void __launch_bounds__(1024) k_snq_finalize(int t, int64_t N, double w_min,
                                                        const double* __restrict__ eta_in, const double* __restrict__ w_in,
-                                                       const int* __restrict__ orth_in, double* __restrict__ eta,
-                                                       double* __restrict__ w, int* __restrict__ orth,
+                                                       const int* __restrict__ orth_in, double* __restrict__ nodes4,
+                                                       int* __restrict__ group_begin,
                                                        double log1p_eps, double* __restrict__ masses,
-                                                       double* __restrict__ h_base, int* __restrict__ n_kept) {
+                                                       double* __restrict__ h_base, int* __restrict__ n_kept,
+                                                       int n_chunks) {
     pdl_enter();
-    __shared__ int warp_tot[32];
-    __shared__ double part[8][8];
+    extern __shared__ double fin_sm[];                  // [n_chunks][8] chunk sums, [8] masses
+    __shared__ int warp_tot[32][8];
+    __shared__ int gb[9];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    // every warp owns a contiguous range of nodes and walks it 32 at a time (coalesced); ballots give the stable
-    // order inside the warp, one scan over the warp totals the offsets between warps.  All loads of a pass are
-    // issued before any is used (N <= 13824 = 32 warps x kIt x 32 nodes).
+    const int nb = 1 << t;
     constexpr int kIt = 14;
     const int64_t per = ((N + nwarps - 1) / nwarps + 31) / 32 * 32;
     const int64_t k0 = min(N, (int64_t)warp * per), k1 = min(N, k0 + per);
+    const unsigned lt = (1u << lane) - 1u;
     double wv[kIt];
+    int ov[kIt], rk[kIt];                               // orthant and rank inside (warp, orthant); -1 = dropped
+    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int it = 0; it < kIt; ++it) {
         const int64_t k = k0 + it * 32 + lane;
         wv[it] = k < k1 ? w_in[k] : 0.0;
+        ov[it] = k < k1 ? orth_in[k] : 0;
     }
-    int dst[kIt];                                       // position inside the warp's output, -1 = dropped
-    int cnt = 0;
 #pragma unroll
     for (int it = 0; it < kIt; ++it) {
         const bool keep = wv[it] >= w_min && k0 + it * 32 + lane < k1;
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        dst[it] = keep ? cnt + __popc(bal & ((1u << lane) - 1)) : -1;
-        cnt += __popc(bal);
-    }
-    if (lane == 0) warp_tot[warp] = cnt;
-    __syncthreads();
-    int off = 0, kept = 0;
-    for (int ww = 0; ww < nwarps; ++ww) {
-        if (ww < warp) off += warp_tot[ww];
-        kept += warp_tot[ww];
-    }
+        rk[it] = -1;
 #pragma unroll
-    for (int it = 0; it < kIt; ++it)
-        if (dst[it] >= 0) w[off + dst[it]] = wv[it];
-    {
-        int ov[kIt];
-#pragma unroll
-        for (int it = 0; it < kIt; ++it) {
-            const int64_t k = k0 + it * 32 + lane;
-            ov[it] = k < k1 ? orth_in[k] : 0;
+        for (int o = 0; o < 8; ++o) {
+            const unsigned bal = __ballot_sync(0xffffffffu, keep && ov[it] == o);
+            if (keep && ov[it] == o) rk[it] = cnt[o] + __popc(bal & lt);
+            cnt[o] += __popc(bal);
         }
-#pragma unroll
-        for (int it = 0; it < kIt; ++it)
-            if (dst[it] >= 0) orth[off + dst[it]] = ov[it];
     }
-    for (int j = 0; j < t; ++j) {
-        double ev[kIt];
+    if (lane < 8) {
+        int c = 0;
 #pragma unroll
-        for (int it = 0; it < kIt; ++it) {
-            const int64_t k = k0 + it * 32 + lane;
-            ev[it] = k < k1 ? eta_in[(int64_t)j * N + k] : 0.0;
-        }
-#pragma unroll
-        for (int it = 0; it < kIt; ++it)
-            if (dst[it] >= 0) eta[(int64_t)j * N + off + dst[it]] = ev[it];
+        for (int o = 0; o < 8; ++o) c = (lane == o) ? cnt[o] : c;
+        warp_tot[warp][lane] = c;
     }
-    if (threadIdx.x == 0) *n_kept = kept;
     __syncthreads();
-    snq_masses_block(t, kept, w, orth, log1p_eps, part, masses, h_base);     // t <= 3 here
+    if (threadIdx.x == 0) {
+        int g = 0, kept = 0;
+        for (int o = 0; o < nb; ++o) {
+            int all = 0;
+            for (int ww = 0; ww < nwarps; ++ww) all += warp_tot[ww][o];
+            gb[o] = g;
+            g += pad_nodes(all);
+            kept += all;
+        }
+        gb[nb] = g;
+        *n_kept = kept;
+    }
+    __syncthreads();
+    if (threadIdx.x <= nb) group_begin[threadIdx.x] = gb[threadIdx.x];
+    int off[8];                                         // where this warp's nodes of every orthant start
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+        int before = 0, all = 0;
+        for (int ww = 0; ww < nwarps; ++ww) {
+            const int c = warp_tot[ww][o];
+            if (ww < warp) before += c;
+            all += c;
+        }
+        off[o] = (o < nb ? gb[o] : 0) + before;
+        // zero-weight tail of the orthant (all .. padded), written by the warp with the same number
+        if (o < nb && warp == o)
+            for (int k = gb[o] + all + lane; k < gb[o + 1]; k += 32) {
+                nodes4[4 * (size_t)k + 0] = 0.0;
+                nodes4[4 * (size_t)k + 1] = 0.0;
+                nodes4[4 * (size_t)k + 2] = 0.0;
+                nodes4[4 * (size_t)k + 3] = 0.0;
+            }
+    }
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+        if (rk[it] < 0) continue;
+        int base = 0;
+#pragma unroll
+        for (int o = 0; o < 8; ++o) base = (ov[it] == o) ? off[o] : base;
+        const size_t pos = (size_t)(base + rk[it]);
+        const int64_t k = k0 + it * 32 + lane;
+        nodes4[4 * pos + 0] = eta_in[k];
+        nodes4[4 * pos + 1] = t >= 2 ? eta_in[N + k] : 0.0;
+        nodes4[4 * pos + 2] = t >= 3 ? eta_in[2 * N + k] : 0.0;
+        nodes4[4 * pos + 3] = wv[it];
+    }
+    // masses in the two-level order of the persistent fetch kernel: chunk c = generated nodes [c per, (c + 1) per)
+    double* chunk_part = fin_sm;
+    double* sm_masses = fin_sm + (size_t)n_chunks * 8;
+    const int64_t per_chunk = (N + n_chunks - 1) / n_chunks;
+    for (int c = warp; c < n_chunks; c += nwarps) {
+        const int64_t c0 = min(N, (int64_t)c * per_chunk), c1 = min(N, c0 + per_chunk);
+        chunk_mass_warp(w_in + c0, orth_in + c0, (int)(c1 - c0), lane, w_min, chunk_part + c * 8);
+    }
+    __syncthreads();
+    masses_from_chunks(t, n_chunks, chunk_part, log1p_eps, sm_masses, h_base);      // t <= 3 here
+    if (threadIdx.x < nb) masses[threadIdx.x] = sm_masses[threadIdx.x];
 }
 
 // np.argmax over the shards' proposals + AppendedMutualInformation.append (ital/ital.py:130-131, 561-568): choose

@@ -174,3 +174,49 @@ def test_library_is_sm100a_code_with_bulk_copies_and_dependent_launch():
         assert 'LDG.E.STRONG.GPU' in f and 'CCTL.IVALL' in f and 'STRONG.SYS' in f
     assert all('ACQBULK' in f and 'PREEXIT' in f for f in kernels if f not in fused), 'a kernel without pdl_enter()'
     assert 'STRONG.SYS' in sass and 'MEMBAR.SC.SYS' in sass
+
+
+def test_first_step_table_matches_the_closed_form():
+    """h_tab (csrc/ital_kernels.cuh): the polynomial table of H(u) = -sum_r p_r log(p_r + eps), p = Phi(+-u), against
+    scipy's erfc / log at random and at interval-boundary arguments; what the reference computes with norm.cdf for a
+    single sample (ital/ital.py:364-369, 205-219)."""
+    from scipy.special import ndtr
+    lib = _capi.load()
+    n = int(lib.ital_h_table(None, 0))
+    tab = np.zeros(n)
+    assert lib.ital_h_table(_capi.dptr(tab), n) == n == 136 * 8
+    rng = np.random.default_rng(5)
+    u = np.concatenate((rng.uniform(0, 8.5, 20000), np.arange(0, 137) / 16.0, np.arange(1, 137) / 16.0 - 1e-13, [8.5]))
+    u = np.minimum(u, 8.5)
+    k = np.minimum((u * 16).astype(np.int64), 135)
+    x = u * 32.0 - (2.0 * k + 1.0)
+    c = tab.reshape(136, 8)[k]
+    got = np.zeros_like(u)
+    for j in range(7, -1, -1):
+        got = got * x + c[:, j]
+    eps = 1e-12
+    p1, p0 = ndtr(u), ndtr(-u)
+    want = -(p1 * np.log(p1 + eps) + p0 * np.log(p0 + eps))
+    np.testing.assert_allclose(got, want, rtol=0, atol=3e-16)
+
+
+def test_normal_cdf_table_matches_erfc():
+    """phi_tab (csrc/ital_kernels.cuh): (Phi, phi) on the grid x_k = -8.5 + k/128 plus a 5th-order Taylor step from the
+    nearest grid point, evaluated as the kernels do, against scipy's ndtr."""
+    from scipy.special import ndtr
+    lib = _capi.load()
+    n = int(lib.ital_phi_table(None, 0))
+    tab = np.zeros(n)
+    assert lib.ital_phi_table(_capi.dptr(tab), n) == n == 2177 * 2
+    rng = np.random.default_rng(6)
+    x = np.concatenate((rng.uniform(-8.5, 8.5, 50000), -8.5 + (np.arange(2177) + 0.5) / 128.0 - 1e-12, [-8.5, 8.5, 0.0]))
+    x = np.clip(x, -8.5, 8.5)
+    k = np.rint((x + 8.5) * 128).astype(np.int64)
+    xk = k / 128.0 - 8.5
+    dl = x - xk
+    t = tab.reshape(2177, 2)[k]
+    x2 = xk * xk
+    c2, c3, c4, c5 = -0.5 * xk, (x2 - 1) / 6, -xk * (x2 - 3) / 24, (x2 * (x2 - 6) + 3) / 120
+    poly = 1 + dl * (c2 + dl * (c3 + dl * (c4 + dl * c5)))
+    got = t[:, 0] + t[:, 1] * dl * poly
+    np.testing.assert_allclose(got, ndtr(x), rtol=0, atol=3e-16)
