@@ -522,6 +522,7 @@ int make_record(ital_shard* s, long long local_row, double* dst_dev, bool commit
 }
 
 constexpr int kMaxBatch = 11;            // greedy steps per fetch (t <= 10 base variables)
+constexpr int kMaxBatchGeneral = 5;      // ... with label_prob < 1 (conditional node sets up to 4 base variables)
 
 int ensure_nodes(ital_shard* s, int64_t n_nodes) {
     n_nodes += 8 * kNodePad;                            // (every orthant of the packed node list is zero-padded to 256)
@@ -666,7 +667,7 @@ int launch_eval(ital_shard* s, int64_t items_hint, bool block_per_candidate) {
 // who label every sample); the conditional node sets come from the host, which costs one round trip per step.
 int propose_general(ital_shard* s) {
     const int t = s->t;
-    if (t > 4) return fail(ITAL_EINVAL, "label_prob < 1 supports batches of at most 5 samples");
+    if (t >= kMaxBatchGeneral) return fail(ITAL_EINVAL, "label_prob < 1 supports batches of at most %d samples", kMaxBatchGeneral);
     std::vector<double> bm(16), bL(16 * 16);
     CU(copy_async(s, bm.data(), s->base_m_dev, 16 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CU(copy_async(s, bL.data(), s->base_L_dev, 256 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
@@ -1673,6 +1674,8 @@ int ital_fetch_peer(ital_shard* s, int k, double label_prob, double mistake_prob
     if (!s || k < 0 || (k > 0 && !out_idx)) return fail(ITAL_EINVAL, "ital_fetch_peer: bad arguments");
     if (!s->xg_ready) return fail(ITAL_ESTATE, "ital_fetch_peer: no peer exchange (ital_peer_export / ital_peer_connect)");
     if (k > kMaxBatch) return fail(ITAL_EINVAL, "batches of more than %d samples are not supported", kMaxBatch);
+    if (label_prob < 1.0 && k > kMaxBatchGeneral)
+        return fail(ITAL_EINVAL, "label_prob < 1 supports batches of at most %d samples", kMaxBatchGeneral);
     int rc = ital_fetch_begin(s, label_prob, mistake_prob);
     if (rc) return rc;
     const int64_t rl = record_doubles(s);
@@ -1706,6 +1709,8 @@ int ital_fetch(ital_shard* s, int k, double label_prob, double mistake_prob, int
                double* out_scores) {
     if (!s || k < 0 || (k > 0 && !out_idx)) return fail(ITAL_EINVAL, "ital_fetch: bad arguments");
     if (k > kMaxBatch) return fail(ITAL_EINVAL, "batches of more than %d samples are not supported", kMaxBatch);
+    if (label_prob < 1.0 && k > kMaxBatchGeneral)
+        return fail(ITAL_EINVAL, "label_prob < 1 supports batches of at most %d samples", kMaxBatchGeneral);
     int rc = ital_fetch_begin(s, label_prob, mistake_prob);
     if (rc) return rc;
     // the whole greedy loop is enqueued without waiting for the GPU; one read-back at the end

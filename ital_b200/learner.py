@@ -363,8 +363,12 @@ class ITAL(object):
                 or os.environ.get('ITAL_B200_PEER', '1') != '1':
             return
         handle_bytes = 128
-        mine = self._shard.peer_export(comm.world_size, comm.rank, handle_bytes)
-        ok = self._shard.peer_connect(comm.gather_bytes(mine), handle_bytes)
+        try:                        # (more than 32 shards, no IPC support, ...: every rank falls back together)
+            mine, ok = self._shard.peer_export(comm.world_size, comm.rank, handle_bytes), True
+        except _capi.ItalError:
+            mine, ok = np.zeros(handle_bytes, dtype=np.uint8), False
+        handles = comm.gather_bytes(mine)
+        ok = comm.all_agree(ok) and self._shard.peer_connect(handles, handle_bytes)
         self._peer = comm.all_agree(ok)
         if not self._peer:
             self._shard.peer_disconnect()
@@ -381,6 +385,26 @@ class ITAL(object):
             self._peer = False
         self._shard.close()
         self._shard = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        """Last resort (prefer close() / a with-block): non-collective release, no barrier -- a learner that is
+        garbage-collected on one rank cannot take part in a collective fetch any more anyway.  The peers' mappings of
+        this shard's exchange buffer are theirs to close."""
+        shard = getattr(self, '_shard', None)
+        if shard is not None:
+            try:
+                if getattr(self, '_peer', False):
+                    shard.peer_disconnect()
+                shard.close()
+            except Exception:
+                pass
+            self._shard = None
 
     def reset(self):                                                            # retrieval_base.py:48-61
         self.rounds = 0
@@ -447,6 +471,7 @@ class ITAL(object):
 
     def _add_labelled(self, idx, y):
         """gp.fit / gp.update (ital/gp.py:141-200): up to four labelled points per pass over the pool."""
+        self._check_rows(idx, with_queries=True)
         idx, y = [int(i) for i in idx], [float(v) for v in y]
         for lo in range(0, len(idx), 4):
             chunk = idx[lo:lo + 4]
@@ -456,7 +481,16 @@ class ITAL(object):
             self._labelled_y.extend(y[lo:lo + 4])
         self._rel_mean = None
 
+    def _check_rows(self, idx, with_queries=False):
+        """The reference indexes numpy arrays with these (IndexError when out of range); a row no shard owns would
+        otherwise enter the model as an all-zero record."""
+        hi = self._n + (len(self.queries) if with_queries else 0)
+        for i in idx:
+            if not (0 <= int(i) < hi) or int(i) != i:
+                raise IndexError('sample index %r is out of range for a pool of %d rows' % (i, self._n))
+
     def update(self, feedback):                                                 # retrieval_base.py:105-126
+        self._check_rows(feedback.keys())
         rel, irr, unnameable = self.partition_feedback(feedback)
         if len(rel) + len(irr) > 0:
             self._add_labelled(rel + irr, [1.0] * len(rel) + [-1.0] * len(irr))
@@ -470,6 +504,7 @@ class ITAL(object):
     def _posterior_block(self, rows):
         """Posterior means and full covariance of a small set of rows from their point records (one k_record launch
         per row): c_ij = k(x_i, x_j) - u_i . u_j with u the projections on the labelled set's Cholesky factor."""
+        self._check_rows(rows, with_queries=True)
         rows = [int(i) for i in rows]
         recs = []
         for lo in range(0, len(rows), 64):
@@ -491,6 +526,7 @@ class ITAL(object):
         which equals the reference's extended inverse (extend_inv, gp.py:40-87)."""
         if cov_mode not in (None, 'diag', 'full'):
             raise ValueError('cov_mode must be None, "diag" or "full"')
+        self._check_rows(feedback.keys())
         rel, irr, _ = self.partition_feedback(feedback)
         test_ind = [int(i) for i in test_ind]
         obs = sorted(rel) + sorted(irr)
@@ -509,7 +545,14 @@ class ITAL(object):
         return mean_t
 
     # ---- ITAL ------------------------------------------------------------------------------------------
-    def _check_supported(self):
+    MAX_BATCH = 11                  # greedy steps per fetch (10 base variables)
+    MAX_BATCH_GENERAL = 5           # with label_prob < 1 (conditional node sets up to 4 base variables)
+
+    def _check_supported(self, k=0):
+        limit = self.MAX_BATCH_GENERAL if self.label_prob < 1 else self.MAX_BATCH
+        if k > limit:               # before any work (and before any collective) -- not in the middle of the greedy loop
+            raise NotImplementedError('batches of more than %d samples are not supported%s' % (
+                limit, ' with label_prob < 1' if self.label_prob < 1 else ''))
         if self.label_estimation != 'mean':
             raise NotImplementedError("label_estimation must be 'mean' on the GPU path")
         if self.change_estimation_subset != 0 or (self.clip_cov and 0 < self.clip_cov < 1) \
@@ -519,12 +562,12 @@ class ITAL(object):
 
     def fetch_unlabelled(self, k, show_progress=False):                         # ital.py:84-134
         """Greedy batch of k unlabelled samples maximising mutual information; list of row indices."""
-        self._check_supported()
         if len(self._labelled_idx) == 0:
             raise RuntimeError('fetch_unlabelled() needs at least one query or labelled sample '
                                '(the reference fails here with gp.K_inv = None)')
         n_unseen = self._n - len(self.relevant_ids | self.irrelevant_ids | self.unnameable_ids)
         k = min(int(k), n_unseen)                                               # ital.py:99-100
+        self._check_supported(k)
         restricted = False
         if self.top_candidates is not None:                                     # ital.py:111-117
             top = self.top_candidates

@@ -196,13 +196,14 @@ class OracleITAL(object):
     def __init__(self, data=None, queries=[], length_scale=0.1, var=1.0, noise=1e-6,
                  label_prob=1.0, mistake_prob=0.0, top_candidates=None, change_estimation_subset=0,
                  clip_cov=0, label_estimation='mean', monte_carlo_num_rel=None, monte_carlo_num_fb=None,
-                 parallelized=True, force_general=False):
+                 parallelized=True, force_general=False, general_sets=False):
         self.length_scale, self.var, self.noise = length_scale, var, noise
         self.label_prob, self.mistake_prob = label_prob, mistake_prob
         self.top_candidates = top_candidates
         self.label_estimation = label_estimation
         self.parallelized = parallelized
         self.force_general = force_general
+        self.general_sets = general_sets      # general feedback model through shared conditional node sets (oracle/general_sets.py)
         if change_estimation_subset != 0 or clip_cov != 0 or monte_carlo_num_rel is not None \
                 or monte_carlo_num_fb is not None:
             raise NotImplementedError('oracle restates the enumeration path only (see module docstring)')
@@ -308,6 +309,15 @@ class OracleITAL(object):
                 scores, p_plus, p_base, s = mi_perfect_user(
                     m_base, cov_base, self.rel_mean[cand], var_test[cand], cov_base_test[:, cand], pool=pool)
                 extra = dict(p_plus=p_plus, p_base=p_base, s=s)
+            elif self.general_sets and self.label_estimation == 'mean':
+                from .general_sets import mi_general_shared
+                L = safe_cholesky(cov_base) if len(ret) else np.zeros((0, 0))
+                l = scipy.linalg.solve_triangular(L, cov_base_test[:, cand], lower=True).T if len(ret) \
+                    else np.zeros((len(cand), 0))
+                s = np.sqrt(np.maximum(var_test[cand] - (l * l).sum(axis=1), 0.0))
+                scores = mi_general_shared(m_base, L, self.rel_mean[cand], l, s, self.label_prob, self.mistake_prob,
+                                           self.noise)
+                extra = dict(s=s)
             else:
                 scores = np.array([self._mi_general(ret + [int(i)], m_base, cov_base, self.rel_mean[i],
                                                     var_test[i], cov_base_test[:, i]) for i in cand])

@@ -158,3 +158,35 @@ def test_reset_and_unsupported_modes(make):
             B.fetch_unlabelled(1)
     with pytest.raises(ValueError):
         make(storage='float16')
+
+
+def test_bad_sample_indices_raise_index_error(make):
+    """The reference indexes numpy arrays with the feedback keys (IndexError when out of range); here a row that no
+    shard owns would otherwise enter the model as an all-zero record."""
+    L = make(n=10)
+    for bad in (10, -1, 250):
+        with pytest.raises(IndexError):
+            L.update({bad: 1})
+    with pytest.raises(IndexError):
+        L.update({3: 1, 12: 0})
+    assert L.rounds == 0 and not [c for c in L._shard.calls if c[0] == 'add']     # nothing reached the model
+    L.update({3: 1})
+    with pytest.raises(IndexError):
+        L.updated_prediction({11: 1}, [0, 1])
+
+
+def test_batch_size_is_validated_before_any_work(make):
+    """Batches beyond what the node sets cover are refused up front, as NotImplementedError (configs/toy-mistakes.conf
+    ships batch_size = 6 with label_prob = 0.75), not in the middle of the greedy loop."""
+    L = make(n=40, label_prob=0.75, mistake_prob=0.2)
+    L.update({0: 1})
+    n_calls = len(L._shard.calls)
+    with pytest.raises(NotImplementedError, match='label_prob < 1'):
+        L.fetch_unlabelled(6)
+    assert len(L._shard.calls) == n_calls
+    assert len(L.fetch_unlabelled(5)) == 5
+    P = make(n=40)
+    P.update({0: 1})
+    with pytest.raises(NotImplementedError):
+        P.fetch_unlabelled(12)
+    assert len(P.fetch_unlabelled(11)) == 11

@@ -10,7 +10,7 @@ import numpy as np
 
 import pytest
 
-from conftest import drive, load_updpred, updpred_names
+from conftest import drive, load_golden, load_updpred, updpred_names
 from oracle.ital_oracle import OracleITAL
 
 
@@ -39,6 +39,13 @@ def test_oracle_reproduces_reference(golden):
     general = not (float(g['label_prob']) >= 1 and float(g['mistake_prob']) <= 0)
     for t, (tr, st) in enumerate(zip(ora.trace, g['steps'])):
         assert tr['candidates'].tolist() == st['candidates'].tolist()
+        # the per-candidate covariance of ret + [i] the reference scored with (predict_cov_batch, gp.py:235-261;
+        # step 0: the clamped 'diag' variance, ital.py:557-558)
+        cov = np.empty((len(tr['candidates']), t + 1, t + 1))
+        cov[:, :t, :t] = tr['cov_base']
+        cov[:, :t, t] = cov[:, t, :t] = tr['cov_base_test'].T
+        cov[:, t, t] = tr['var']
+        np.testing.assert_allclose(cov, st['rel_covs'], rtol=1e-6, atol=1e-9 * float(g['var']))
         rtol, atol = _tol(t)
         atol = np.full(len(st['mi']), atol)
         if general:
@@ -61,6 +68,26 @@ def test_oracle_reproduces_reference(golden):
         if not (general and str(g['label_estimation']) != 'mean'):
             check_choice(tr['scores'], tr['candidates'], st['chosen'],
                          rtol=1e-4 if general else 1e-9)
+
+
+@pytest.mark.parametrize('name', ['toy_mistakes_k3', 'butterflies_conservative_k3', 'butterflies_aggressive_k3'])
+def test_general_model_shared_node_sets_equal_the_literal_enumeration(name):
+    """oracle/general_sets.py (one conditional node set per annotated subset of the base, shared by all candidates --
+    the form the CUDA kernel evaluates) against the literal double loop over relevance and feedback configurations
+    (ital.py:183-224) and against the reference's own record: same quantity, different node placement."""
+    g = load_golden(name)
+    kw = dict(g['learner_kw'])
+    lit = drive(OracleITAL(g['X'], **kw), g)
+    sets = drive(OracleITAL(g['X'], general_sets=True, **kw), g)
+    ret = g['ret'].tolist()
+    lit.fetch_unlabelled(int(g['k']), forced=ret)
+    sets.fetch_unlabelled(int(g['k']), forced=ret)
+    for t, (a, b, st) in enumerate(zip(lit.trace, sets.trace, g['steps'])):
+        np.testing.assert_allclose(b['scores'], a['scores'], rtol=1e-5, atol=1e-9, err_msg='step %d' % t)
+        np.testing.assert_allclose(b['scores'], st['mi'], rtol=1e-4, atol=1e-6, err_msg='step %d' % t)
+        # (near the maximum the two evaluations can order near-ties differently: within the 1e-5 they agree to)
+        pos = int(np.nonzero(b['candidates'] == a['argmax'])[0][0])
+        assert b['scores'][pos] >= b['scores'].max() - 1e-5 * abs(b['scores'].max())
 
 
 def test_perfect_user_shortcut_equals_general_formula():
