@@ -13,9 +13,10 @@ modes of the same call: `exhaustive` (every candidate scored by quadrature each 
 `streaming` (one HBM pass over the pool per greedy step, the round-1 default) and `multi_kernel` (the fused
 kernel's phases as separate launches).  `e2e` is wall clock through the public `ITAL.fetch_unlabelled` (host
 arguments in, host list out, every host<->device copy of the call inside the timed region, bytes counted by the
-library).  `roofline` rates the HBM-bound pass that is consumed every active-learning round -- the multi-column
-labelled pass of `update` -- by its algorithmic bytes over its own CUDA-event time; `roofline_streaming` does the
-same for the single-column pass of the streaming fetch.  `cpu_baseline` / `--impl reference` time the float64 oracle
+library).  `roofline` rates the HBM-bound streaming pass where its output is consumed -- the single-column pass of
+the exhaustive fetch, whose new projection entries every candidate's score reads -- by its algorithmic bytes over its
+own CUDA-event time; `roofline_update` does the same for the multi-column labelled pass of `update` (consumed every
+active-learning round) and `roofline_streaming` for the pass inside the pipelined streaming fetch.  `cpu_baseline` / `--impl reference` time the float64 oracle
 (the port of the reference's algorithm; the reference itself cannot allocate its n-by-n kernel matrix at this size
 and is Python that does not travel to the GPU box) on a bounded sample.
 """
@@ -340,7 +341,9 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--exhaustive-steps', type=int, default=1)
     ap.add_argument('--secondary-steps', type=int, default=30, help='timed fetches of the streaming / multi-kernel rows')
-    ap.add_argument('--rounds', type=int, default=5, help='full fetch+update rounds timed at the end')
+    ap.add_argument('--rounds', type=int, default=8, help='full fetch+update rounds timed at the end (8 rounds of 4: |L| = 41)')
+    ap.add_argument('--model-steps', type=int, default=20, help='timed fetches with mistake_prob = 0.5')
+    ap.add_argument('--general-steps', type=int, default=1, help='timed fetches with label_prob = 0.25 (slow: every candidate scored)')
     ap.add_argument('--no-strong', action='store_true', help='skip the strong-scaling sub-run at N > 1')
     args = ap.parse_args()
 
@@ -437,14 +440,50 @@ def main():
                        'achieved': s_ach, 'peak': peak, 'unit': 'GB/s', 'frac': s_ach / peak, 'traffic': s_traffic,
                        'traffic_source': s_src, 'launches': int(snl), 'avg_launch_ms': sms / max(1, snl),
                        'algorithmic_bytes_per_launch': snb / max(1, snl), 'share_of_step': sms / 1e3 / sdev}
+    roof_consumed = None
     if args.exhaustive_steps > 0:
         H.set_mode(exhaustive=True)
+        lib.ital_profile_enable(shard.handle, 1)
+        H.profile_read()
         edev, ewall, eret = H.timed(args.exhaustive_steps)
+        ems, enl, enb = H.profile_read()
+        lib.ital_profile_enable(shard.handle, 0)
         exh = row(edev, ewall, args.exhaustive_steps, eret,
                   'every candidate scored by quadrature at every greedy step (no lazy-greedy bound): the like-for-like '
-                  'count against the CPU arms')
+                  'count against the CPU arms; one streaming pass per step keeps all projections current')
         checks['exhaustive_same_batch'] = eret == ret
+        e_ach = (enb / 1e9) / (ems / 1e3) if ems > 0 else 0.0
+        e_traffic, e_src = ncu_traffic('r*_k_extend_bulk_full.txt')
+        roof_consumed = {'bound': 'hbm',
+                         'kernel': 'k_extend_bulk<float,4> -- the single-column streaming pass, measured where its output is '
+                                   'consumed: exhaustive scoring reads every row\'s new projection entry in the next step '
+                                   '(so does the general feedback model, label_prob < 1)',
+                         'achieved': e_ach, 'peak': peak, 'unit': 'GB/s', 'frac': e_ach / peak, 'traffic': e_traffic,
+                         'traffic_source': e_src, 'peak_source': peak_src, 'launches': int(enl),
+                         'avg_launch_ms': ems / max(1, enl), 'algorithmic_bytes_per_launch': enb / max(1, enl),
+                         'timed_region': 'the %d exhaustive fetch(es) of this run (CUDA events inside the library)' % args.exhaustive_steps,
+                         'share_of_step': ems / 1e3 / edev}
     H.set_mode()
+
+    # ---- other feedback models on the same pool (SURVEY.md 8d secondary rows) ---------------------------------------
+    models = {}
+    if args.model_steps > 0:
+        learner.mistake_prob = 0.5                      # configs/butterflies-aggressive.conf: labels wrong half of the time
+        H.timed(2)
+        mdev2, mwall2, mret2 = H.timed(args.model_steps)
+        models['mistake_prob_0.5'] = row(mdev2, mwall2, args.model_steps, mret2,
+                                         'label_prob=1, mistake_prob=0.5: perfect-user scores + a per-step constant (same '
+                                         'argmax), persistent kernel')
+        learner.mistake_prob = 0.0
+    if args.general_steps > 0:
+        learner.label_prob = 0.25                       # configs/butterflies-conservative.conf: every candidate is scored
+        gdev, gwall, gret = H.timed(args.general_steps, batch=min(args.batch, 4), flush=False)
+        models['label_prob_0.25'] = row(gdev, gwall, args.general_steps, gret,
+                                        'label_prob=0.25 (general feedback model): conditional node sets (~20.7k nodes at '
+                                        'the 4th step), every candidate scored at every step, streaming passes')
+        models['label_prob_0.25']['same_batch'] = None
+        models['label_prob_0.25']['batch'] = [int(i) for i in gret]
+        learner.label_prob = 1.0
 
     # ---- a few full active-learning rounds (fetch 4, label them, update): the update is the consumer of the
     # streaming pass (one multi-column pass per <= 4 labels); this changes the model, so it runs last ----------------
@@ -500,20 +539,29 @@ def main():
                           'one-off growth of the projection matrix when the column capacity doubles); update(%d labels) = '
                           'one multi-column streaming pass + bookkeeping; top_results(100) = device radix sort of the '
                           'local means, 100 indices read back' % args.batch}
+        H.set_mode()
+        H.timed(2)
+        ldev, lwall, lret = H.timed(min(args.steps, 50))
+        r41 = candidates_ranked(n_total, n_lab + args.rounds * args.batch, args.batch)
+        rounds['fetch_after_rounds'] = {'labelled': n_lab + args.rounds * args.batch,
+                                        'value': r41 * min(args.steps, 50) / ldev, 'unit': UNIT,
+                                        'ms_per_step': ldev / min(args.steps, 50) * 1e3,
+                                        'e2e_ms_per_step': lwall / min(args.steps, 50) * 1e3,
+                                        'batch': [int(i) for i in lret],
+                                        'note': 'the headline measurement repeated on the model after the rounds (|L| = %d)'
+                                                % (n_lab + args.rounds * args.batch)}
         u_ach = (tot_bytes / 1e9) / (tot_ms / 1e3) if tot_ms > 0 else 0.0
         u_traffic, u_src = ncu_traffic('r*_k_extend_bulk_multi_full.txt')
         roof = {'bound': 'hbm',
-                'kernel': 'k_extend_bulk_multi<float,4,%d> -- the labelled pass of update(): the HBM-bound pass that is '
-                          'consumed every active-learning round (the default fetch is one latency-bound persistent '
-                          'kernel that reads ~80 MB of per-row vectors; its streaming variant is rated in '
-                          'roofline_streaming)' % args.batch,
+                'kernel': 'k_extend_bulk_multi<float,4,%d> -- the labelled pass of update(): the multi-column HBM pass that '
+                          'is consumed every active-learning round' % args.batch,
                 'achieved': u_ach, 'peak': peak, 'unit': 'GB/s', 'frac': u_ach / peak, 'traffic': u_traffic,
                 'traffic_source': u_src, 'peak_source': peak_src, 'launches': int(tot_launch),
                 'avg_launch_ms': tot_ms / max(1, tot_launch),
                 'algorithmic_bytes_per_launch': tot_bytes / max(1, tot_launch),
                 'timed_region': 'the %d update() calls of al_rounds in this run (CUDA events inside the library)' % args.rounds}
-    if roof is None:
-        roof = roof_stream
+    roof_update = roof
+    roof = roof_consumed or roof_update or roof_stream
 
     used_peer = bool(getattr(learner, '_peer', False))
     t_fit, t_gen, t_update, x_bytes = H.t_fit, H.t_gen, H.t_update, H.X.nbytes
@@ -572,10 +620,12 @@ def main():
         'clocks': clocks,
         'checks': checks,
         'roofline': roof,
+        'roofline_update': roof_update,
         'roofline_streaming': roof_stream,
         'exhaustive': exh,
         'streaming': streaming,
         'multi_kernel': multi,
+        'feedback_models': models,
         'al_rounds': rounds,
         'strong_scaling': strong_row,
         'fetch_stats_per_step': stats,

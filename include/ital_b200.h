@@ -73,6 +73,13 @@ int ital_add_labelled(ital_shard* s, const double* record, double y);
  * before any of them is added. */
 int ital_add_labelled_many(ital_shard* s, int q, const double* records, const double* y);
 
+/* The same without the host in the loop, for a learner whose rows all live on this shard (one GPU): q <= 4 labelled
+ * pool rows (global indices, targets y) enter the model with one small kernel that gathers their records, computes
+ * the triangle of the block Cholesky extension among them and appends the model rows on the device
+ * (k_prepare_labelled), followed by ONE pass over the pool.  Asynchronous: nothing waits for the GPU, nothing is read
+ * back.  Marks the points as seen.  (ActiveRetrievalBase.update, ital/retrieval_base.py:105-126.) */
+int ital_update_labelled(ital_shard* s, int q, const int64_t* global_idx, const double* y);
+
 /* ActiveRetrievalBase.update's unnameable_ids / get_unseen (ital/retrieval_base.py:78-87,126):
  * mark rows as seen (never candidates again until reset).  Non-local indices are ignored. */
 int ital_mark_seen(ital_shard* s, int64_t m, const int64_t* global_idx);

@@ -31,6 +31,7 @@ SIGNATURES = {
     'ital_export_points': (ctypes.c_int, [_shard_p, ctypes.c_int, _c_int64_p, _c_double_p]),
     'ital_add_labelled': (ctypes.c_int, [_shard_p, _c_double_p, ctypes.c_double]),
     'ital_add_labelled_many': (ctypes.c_int, [_shard_p, ctypes.c_int, _c_double_p, _c_double_p]),
+    'ital_update_labelled': (ctypes.c_int, [_shard_p, ctypes.c_int, _c_int64_p, _c_double_p]),
     'ital_mark_seen': (ctypes.c_int, [_shard_p, ctypes.c_int64, _c_int64_p]),
     'ital_restrict_candidates': (ctypes.c_int, [_shard_p, ctypes.c_int64, _c_int64_p]),
     'ital_fetch_propose_dev': (ctypes.c_int, [_shard_p, ctypes.c_double, ctypes.c_int, ctypes.c_void_p]),

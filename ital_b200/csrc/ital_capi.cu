@@ -148,17 +148,14 @@ struct ital_shard {
     bool fetching = false;
     double label_prob = 1.0, mistake_prob = 0.0;
 
-    // host copy of the small model
-    std::vector<std::vector<double>> LK;     // row a of the Cholesky factor of K_LL + noise I (a+1 entries)
-    std::vector<double> beta;                // L_K^-1 y
-    std::vector<double> lab_x;               // labelled rows, W x d doubles
-    std::vector<double> lab_sqn, lab_y;
-    std::vector<int64_t> lab_idx;
-
-    // predict() scratch
-    double *lab_x_dev = nullptr, *lab_sqn_dev = nullptr, *w_vec_dev = nullptr, *LK_dev = nullptr;
-    int lab_dev_cap = 0;
-    bool lab_dev_valid = false;
+    // the small model lives on the device (appended by k_prepare_labelled / k_append_model): Cholesky factor of
+    // K_LL + noise I (row-major lower triangle, leading dimension model_cap), beta = L_K^-1 y, the labelled rows as
+    // float64 and their squared norms; w = K^-1 y is derived on demand (k_model_w) for predict()
+    double *lab_x_dev = nullptr, *lab_sqn_dev = nullptr, *w_vec_dev = nullptr, *LK_dev = nullptr, *beta_dev = nullptr;
+    int model_cap = 0;
+    bool w_valid = false;
+    int64_t* upd_idx_dev = nullptr;          // parameters of ital_update_labelled: rows and targets of the new points
+    double* upd_y_dev = nullptr;
 
     double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double step_nodes[16] = {0};
@@ -421,6 +418,63 @@ int extend_with_record(ital_shard* s, const double* rec, int col, int labelled, 
     const uint8_t mark = mark_selected ? kSelected : (uint8_t)0;
     if (s->x_dtype == ITAL_F32) return launch_extend_t<float>(s, col, labelled, y, mark);
     return launch_extend_t<double>(s, col, labelled, y, mark);
+}
+
+
+// room for `rows` labelled points in the device-resident model (grows by doubling; the old rows are copied over)
+int ensure_model(ital_shard* s, int rows) {
+    if (rows <= s->model_cap) return ITAL_OK;
+    int cap = std::max(64, s->model_cap);
+    while (cap < rows) cap *= 2;
+    double *nx = nullptr, *nq = nullptr, *nw = nullptr, *nl = nullptr, *nb = nullptr;
+    CU(cudaMalloc(&nx, (size_t)cap * s->d * sizeof(double)));
+    CU(cudaMalloc(&nq, (size_t)cap * sizeof(double)));
+    CU(cudaMalloc(&nw, (size_t)cap * sizeof(double)));
+    CU(cudaMalloc(&nl, (size_t)cap * cap * sizeof(double)));
+    CU(cudaMalloc(&nb, (size_t)cap * sizeof(double)));
+    if (s->W > 0 && s->model_cap > 0) {
+        CU(cudaMemcpyAsync(nx, s->lab_x_dev, (size_t)s->W * s->d * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+        CU(cudaMemcpyAsync(nq, s->lab_sqn_dev, (size_t)s->W * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+        CU(cudaMemcpyAsync(nb, s->beta_dev, (size_t)s->W * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+        CU(cudaMemcpy2DAsync(nl, (size_t)cap * sizeof(double), s->LK_dev, (size_t)s->model_cap * sizeof(double),
+                             (size_t)s->W * sizeof(double), (size_t)s->W, cudaMemcpyDeviceToDevice, s->stream));
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    for (double* p : {s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev, s->beta_dev})
+        if (p) CU(cudaFree(p));
+    s->lab_x_dev = nx;
+    s->lab_sqn_dev = nq;
+    s->w_vec_dev = nw;
+    s->LK_dev = nl;
+    s->beta_dev = nb;
+    s->model_cap = cap;
+    s->w_valid = false;
+    return ITAL_OK;
+}
+
+ModelRefs model_refs(const ital_shard* s) {
+    ModelRefs M;
+    M.LK = s->LK_dev;
+    M.ldk = s->model_cap;
+    M.beta = s->beta_dev;
+    M.lab_x = s->lab_x_dev;
+    M.lab_sqn = s->lab_sqn_dev;
+    return M;
+}
+
+// device + pinned block of the multi-column labelled extension: MultiExt header, z[q][d_pad], ur[q][W]
+int ensure_mext(ital_shard* s, int q, int W) {
+    const size_t need = sizeof(MultiExt) / sizeof(double) + (size_t)q * s->d_pad + (size_t)q * W;
+    if (need <= s->mext_cap) return ITAL_OK;
+    CU(cudaStreamSynchronize(s->stream));
+    if (s->mext_dev) CU(cudaFree(s->mext_dev));
+    if (s->mext_host) CU(cudaFreeHost(s->mext_host));
+    s->mext_dev = s->mext_host = nullptr;
+    const size_t cap = need * 2;
+    CU(cudaMalloc(&s->mext_dev, cap * sizeof(double)));
+    CU(cudaMallocHost(&s->mext_host, cap * sizeof(double)));
+    s->mext_cap = cap;
+    return ITAL_OK;
 }
 
 template <typename XT>
@@ -1019,7 +1073,7 @@ void free_all(ital_shard* s) {
     void* ptrs[] = {s->X, s->sqn, s->m, s->v, s->U, s->gain, s->score, s->mask, s->worklist, s->counters,
                     s->block_best, s->best, s->thr_dev, s->rec_dev, s->rec_in_dev, s->idx_dev, s->eta_dev,
                     s->w_dev, s->masses_dev, s->group_dev, s->orth_dev, s->eta_raw, s->w_raw, s->orth_raw, s->gl_dev, s->phi_dev, s->htab_dev, s->base_m_dev, s->base_L_dev, s->sel_dev,
-                    s->hbase_dev, s->tags, s->f_best, s->f_cnt, s->f_stage, s->f_mass, s->f_bar, s->f_trace, s->rec_hist, s->mext_dev, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev,
+                    s->hbase_dev, s->tags, s->f_best, s->f_cnt, s->f_stage, s->f_mass, s->f_bar, s->f_trace, s->rec_hist, s->mext_dev, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev, s->beta_dev, s->upd_idx_dev, s->upd_y_dev,
                     s->sort_keys, s->sort_rows, s->sort_hist, s->sort_out_idx, s->sort_out_val};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -1033,13 +1087,7 @@ int reset_model(ital_shard* s) {
     s->W = 0;
     s->t = 0;
     s->fetching = false;
-    s->LK.clear();
-    s->beta.clear();
-    s->lab_x.clear();
-    s->lab_sqn.clear();
-    s->lab_y.clear();
-    s->lab_idx.clear();
-    s->lab_dev_valid = false;
+    s->w_valid = false;
     const int blocks = grid_for(s, s->n, 256);
     pdl(k_fill, blocks, 256, 0, s)(s->m, s->n, 0.0); s->launches++;
     pdl(k_fill, blocks, 256, 0, s)(s->v, s->n, s->var); s->launches++;
@@ -1234,48 +1282,16 @@ int ital_export_points(ital_shard* s, int q, const int64_t* global_idx, double* 
 
 int ital_add_labelled(ital_shard* s, const double* record, double y) {
     if (!s || !record) return fail(ITAL_EINVAL, "ital_add_labelled: bad arguments");
-    if (s->fetching) return fail(ITAL_ESTATE, "ital_add_labelled: a fetch is in progress");
-    CU(cudaSetDevice(s->device));
-    // the capacity (and with it the record layout) may have to grow first: copy the record out
-    const int64_t old_cap = s->w_cap;
-    std::vector<double> u(record + ITAL_RECORD_HEADER, record + ITAL_RECORD_HEADER + s->W);
-    std::vector<double> x(record + ITAL_RECORD_HEADER + old_cap, record + ITAL_RECORD_HEADER + old_cap + s->d);
-    double hdr[ITAL_RECORD_HEADER];
-    memcpy(hdr, record, sizeof hdr);
-    int rc = ensure_width(s, s->W + 1);
-    if (rc) return rc;
-    std::vector<double> rec((size_t)record_doubles(s), 0.0);
-    memcpy(rec.data(), hdr, sizeof hdr);
-    std::copy(u.begin(), u.end(), rec.begin() + ITAL_RECORD_HEADER);
-    std::copy(x.begin(), x.end(), rec.begin() + ITAL_RECORD_HEADER + s->w_cap);
-    // rank-1 extension of the Cholesky factor of K_LL + noise I (replaces the full re-inversion of gp.py:194)
-    // (the kernel derives the same pivot and beta from the record header)
-    const double v_r = hdr[5];
-    const double piv = std::sqrt(std::max(v_r + s->noise, 2.3e-308));
-    const double beta = (y - hdr[2]) / piv;
-    rc = extend_with_record(s, rec.data(), s->W, 1, y, false);
-    if (rc) return rc;
-    std::vector<double> row(u);
-    row.push_back(piv);
-    s->LK.push_back(row);
-    s->beta.push_back(beta);
-    s->lab_x.insert(s->lab_x.end(), x.begin(), x.end());
-    s->lab_sqn.push_back(hdr[4]);
-    s->lab_y.push_back(y);
-    s->lab_idx.push_back((int64_t)hdr[0]);
-    s->lab_dev_valid = false;
-    s->W += 1;
-    int64_t g = (int64_t)hdr[0];
-    return ital_mark_seen(s, 1, &g);
+    return ital_add_labelled_many(s, 1, record, &y);
 }
 
 // GaussianProcess.update with several samples (ital/gp.py:164-200): q <= 4 labelled points, whose records were all
 // exported in the CURRENT state of the model, enter with ONE pass over the pool.  The q x q triangle of the block
-// Cholesky extension among the new points is computed here on the host from the records.
+// Cholesky extension among the new points is computed here on the host from the records (the multi-GPU path: the
+// records have been summed over the shards on the host anyway; a single shard uses ital_update_labelled).
 int ital_add_labelled_many(ital_shard* s, int q, const double* records, const double* y) {
     if (!s || q < 1 || !records || !y) return fail(ITAL_EINVAL, "ital_add_labelled_many: bad arguments");
     if (s->fetching) return fail(ITAL_ESTATE, "ital_add_labelled_many: a fetch is in progress");
-    if (q == 1) return ital_add_labelled(s, records, y[0]);
     if (q > 4) return fail(ITAL_EINVAL, "ital_add_labelled_many: at most 4 points per pass");
     CU(cudaSetDevice(s->device));
     const int W = s->W;
@@ -1291,6 +1307,7 @@ int ital_add_labelled_many(ital_shard* s, int q, const double* records, const do
     }
     int rc = ensure_width(s, W + q);
     if (rc) return rc;
+    if ((rc = ensure_model(s, W + q))) return rc;
     // block Cholesky extension among the new points
     const double neg2ls2 = -2.0 * (s->ls * s->ls);
     double tri[16] = {0}, piv[4] = {0}, beta[4] = {0};
@@ -1313,16 +1330,7 @@ int ital_add_labelled_many(ital_shard* s, int q, const double* records, const do
     // device block: MultiExt header, z[q][d_pad] (zero padded), ur[q][W]
     const size_t hdr_d = sizeof(MultiExt) / sizeof(double);
     const size_t need = hdr_d + (size_t)q * s->d_pad + (size_t)q * W;
-    if (need > s->mext_cap) {
-        CU(cudaStreamSynchronize(s->stream));
-        if (s->mext_dev) CU(cudaFree(s->mext_dev));
-        if (s->mext_host) CU(cudaFreeHost(s->mext_host));
-        s->mext_dev = s->mext_host = nullptr;
-        const size_t cap = need * 2;
-        CU(cudaMalloc(&s->mext_dev, cap * sizeof(double)));
-        CU(cudaMallocHost(&s->mext_host, cap * sizeof(double)));
-        s->mext_cap = cap;
-    }
+    if ((rc = ensure_mext(s, q, W))) return rc;
     CU(cudaStreamSynchronize(s->stream));               // the pinned block may still feed the previous pass
     MultiExt* h = reinterpret_cast<MultiExt*>(s->mext_host);
     memset(s->mext_host, 0, need * sizeof(double));
@@ -1335,25 +1343,76 @@ int ital_add_labelled_many(ital_shard* s, int q, const double* records, const do
     }
     memcpy(h->tri, tri, sizeof tri);
     CU(copy_async(s, s->mext_dev, s->mext_host, need * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    rc = s->x_dtype == ITAL_F32 ? launch_extend_multi<float>(s, q, W) : launch_extend_multi<double>(s, q, W);
-    if (rc) return rc;
-    // host copy of the model: Cholesky rows, beta, labelled rows (for predict)
-    std::vector<int64_t> gidx(q);
-    for (int a = 0; a < q; ++a) {
-        std::vector<double> row(u[a]);
-        for (int b = 0; b < a; ++b) row.push_back(tri[a * 4 + b]);
-        row.push_back(piv[a]);
-        s->LK.push_back(row);
-        s->beta.push_back(beta[a]);
-        s->lab_x.insert(s->lab_x.end(), x[a].begin(), x[a].end());
-        s->lab_sqn.push_back(hsq[a]);
-        s->lab_y.push_back(y[a]);
-        s->lab_idx.push_back((int64_t)hidx[a]);
-        gidx[a] = (int64_t)hidx[a];
+    pdl(k_append_model, 1, 256, 0, s)(model_refs(s), q, W, (int)s->d, (int)s->d_pad, s->mext_dev); s->launches++;
+    CU(cudaGetLastError());
+    if (q == 1) {
+        // one point: the single-column pass, fed by the point record in the current layout
+        std::vector<double> rec((size_t)record_doubles(s), 0.0);
+        memcpy(rec.data(), records, ITAL_RECORD_HEADER * sizeof(double));
+        std::copy(u[0].begin(), u[0].end(), rec.begin() + ITAL_RECORD_HEADER);
+        std::copy(x[0].begin(), x[0].end(), rec.begin() + ITAL_RECORD_HEADER + s->w_cap);
+        rc = extend_with_record(s, rec.data(), W, 1, y[0], false);
+    } else {
+        rc = s->x_dtype == ITAL_F32 ? launch_extend_multi<float>(s, q, W) : launch_extend_multi<double>(s, q, W);
     }
-    s->lab_dev_valid = false;
+    if (rc) return rc;
+    std::vector<int64_t> gidx(q);
+    for (int a = 0; a < q; ++a) gidx[a] = (int64_t)hidx[a];
+    s->w_valid = false;
     s->W += q;
     return ital_mark_seen(s, q, gidx.data());
+}
+
+// ActiveRetrievalBase.update -> GaussianProcess.update (ital/retrieval_base.py:105-126, ital/gp.py:164-200) for a
+// learner whose rows all live on this shard: q <= 4 labelled pool rows enter the model with one small kernel (records,
+// triangle among the new points, model rows -- k_prepare_labelled) and ONE pass over the pool.  Nothing here waits
+// for the GPU and nothing comes back to the host.
+int ital_update_labelled(ital_shard* s, int q, const int64_t* global_idx, const double* y) {
+    if (!s || q < 1 || q > 4 || !global_idx || !y) return fail(ITAL_EINVAL, "ital_update_labelled: bad arguments (1 <= q <= 4)");
+    if (s->fetching) return fail(ITAL_ESTATE, "ital_update_labelled: a fetch is in progress");
+    for (int a = 0; a < q; ++a) {
+        const int64_t loc = global_idx[a] - s->row_offset;
+        if (loc < 0 || loc >= s->n) return fail(ITAL_EINVAL, "ital_update_labelled: row %lld is not on this shard", (long long)global_idx[a]);
+        for (int b = 0; b < a; ++b)
+            if (global_idx[a] == global_idx[b]) return fail(ITAL_EINVAL, "ital_update_labelled: row %lld given twice", (long long)global_idx[a]);
+    }
+    CU(cudaSetDevice(s->device));
+    const int W = s->W;
+    int rc = ensure_width(s, W + q);
+    if (rc) return rc;
+    if ((rc = ensure_model(s, W + q))) return rc;
+    if ((rc = ensure_mext(s, q, W))) return rc;
+    if ((rc = ensure_record_buffers(s, 1))) return rc;
+    if (!s->upd_idx_dev) {
+        CU(cudaMalloc(&s->upd_idx_dev, 8 * sizeof(int64_t)));
+        CU(cudaMalloc(&s->upd_y_dev, 8 * sizeof(double)));
+    }
+    // (pageable sources: the runtime stages these few bytes before returning, no wait for the GPU)
+    CU(copy_async(s, s->upd_idx_dev, global_idx, (size_t)q * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, s->upd_y_dev, y, (size_t)q * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    const double neg2ls2 = -2.0 * (s->ls * s->ls);
+    if (s->x_dtype == ITAL_F32)
+        pdl(k_prepare_labelled<float>, 1, 256, 0, s)(q, s->upd_idx_dev, s->upd_y_dev, s->row_offset, s->n, (const float*)s->X,
+                                                     (int)s->d, (int)s->d_pad, s->sqn, s->m, s->v, s->U, s->ldu, W, s->w_cap,
+                                                     s->var, neg2ls2, s->noise, s->mext_dev, s->rec_in_dev, model_refs(s),
+                                                     s->mask, kSeen);
+    else
+        pdl(k_prepare_labelled<double>, 1, 256, 0, s)(q, s->upd_idx_dev, s->upd_y_dev, s->row_offset, s->n, (const double*)s->X,
+                                                      (int)s->d, (int)s->d_pad, s->sqn, s->m, s->v, s->U, s->ldu, W, s->w_cap,
+                                                      s->var, neg2ls2, s->noise, s->mext_dev, s->rec_in_dev, model_refs(s),
+                                                      s->mask, kSeen);
+    s->launches++;
+    CU(cudaGetLastError());
+    if (q == 1) {
+        s->ext_rec = nullptr;       // k_extend reads rec_in_dev, written by the kernel above
+        rc = s->x_dtype == ITAL_F32 ? launch_extend_t<float>(s, W, 1, y[0], 0) : launch_extend_t<double>(s, W, 1, y[0], 0);
+    } else {
+        rc = s->x_dtype == ITAL_F32 ? launch_extend_multi<float>(s, q, W) : launch_extend_multi<double>(s, q, W);
+    }
+    if (rc) return rc;
+    s->w_valid = false;
+    s->W += q;
+    return ITAL_OK;
 }
 
 int ital_mark_seen(ital_shard* s, int64_t m, const int64_t* global_idx) {
@@ -1370,7 +1429,7 @@ int ital_mark_seen(ital_shard* s, int64_t m, const int64_t* global_idx) {
     CU(copy_async(s, s->idx_dev, loc.data(), loc.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream));
     pdl(k_mask_rows, grid_for(s, (int64_t)loc.size(), 256), 256, 0, s)(s->mask, s->idx_dev, (int64_t)loc.size(), kSeen); s->launches++;
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(s->stream));
+    if (loc.size() * sizeof(int64_t) > 32 * 1024) CU(cudaStreamSynchronize(s->stream));   // (small pageable copies are staged)
     return ITAL_OK;
 }
 
@@ -1820,32 +1879,12 @@ int ital_predict(ital_shard* s, const double* Xt, int64_t mrows, double* out_mea
     if (mrows == 0) return ITAL_OK;
     CU(cudaSetDevice(s->device));
     const int nl = s->W;
-    if (!s->lab_dev_valid) {
-        if (nl > s->lab_dev_cap) {
-            for (double** p : {&s->lab_x_dev, &s->lab_sqn_dev, &s->w_vec_dev, &s->LK_dev})
-                if (*p) { CU(cudaFree(*p)); *p = nullptr; }
-            const int cap = std::max(64, 2 * nl);
-            CU(cudaMalloc(&s->lab_x_dev, (size_t)cap * s->d * sizeof(double)));
-            CU(cudaMalloc(&s->lab_sqn_dev, (size_t)cap * sizeof(double)));
-            CU(cudaMalloc(&s->w_vec_dev, (size_t)cap * sizeof(double)));
-            CU(cudaMalloc(&s->LK_dev, (size_t)cap * cap * sizeof(double)));
-            s->lab_dev_cap = cap;
-        }
-        // w = K^-1 y = L^-T (L^-1 y)  (gp.py:158,196)
-        std::vector<double> w(s->beta);
-        for (int a = nl - 1; a >= 0; --a) {
-            double acc = w[a];
-            for (int b = a + 1; b < nl; ++b) acc -= s->LK[b][a] * w[b];
-            w[a] = acc / s->LK[a][a];
-        }
-        std::vector<double> LKd((size_t)nl * nl, 0.0);
-        for (int a = 0; a < nl; ++a)
-            for (int b = 0; b <= a; ++b) LKd[(size_t)a * nl + b] = s->LK[a][b];
-        CU(copy_sync(s, s->lab_x_dev, s->lab_x.data(), (size_t)nl * s->d * sizeof(double), cudaMemcpyHostToDevice));
-        CU(copy_sync(s, s->lab_sqn_dev, s->lab_sqn.data(), (size_t)nl * sizeof(double), cudaMemcpyHostToDevice));
-        CU(copy_sync(s, s->w_vec_dev, w.data(), (size_t)nl * sizeof(double), cudaMemcpyHostToDevice));
-        CU(copy_sync(s, s->LK_dev, LKd.data(), (size_t)nl * nl * sizeof(double), cudaMemcpyHostToDevice));
-        s->lab_dev_valid = true;
+    if (!s->w_valid) {              // w = K^-1 y = L^-T (L^-1 y)  (gp.py:158,196), from the device-resident factor
+        const size_t wsm = (size_t)nl * sizeof(double);
+        if (wsm > 48 * 1024) CU(cudaFuncSetAttribute(k_model_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm));
+        pdl(k_model_w, 1, 1024, wsm, s)(model_refs(s), nl, s->w_vec_dev); s->launches++;
+        CU(cudaGetLastError());
+        s->w_valid = true;
     }
     double *xt_dev = nullptr, *mean_dev = nullptr, *var_dev = nullptr;
     CU(cudaMalloc(&xt_dev, (size_t)mrows * s->d * sizeof(double)));
@@ -1856,7 +1895,7 @@ int ital_predict(ital_shard* s, const double* Xt, int64_t mrows, double* out_mea
     const size_t smem = (size_t)wpb * nl * sizeof(double);
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_predict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pdl(k_predict, (unsigned)((mrows + wpb - 1) / wpb), threads, smem, s)(
-        xt_dev, mrows, (int)s->d, s->lab_x_dev, s->lab_sqn_dev, nl, s->w_vec_dev, s->LK_dev, s->var,
+        xt_dev, mrows, (int)s->d, s->lab_x_dev, s->lab_sqn_dev, nl, s->w_vec_dev, s->LK_dev, (int64_t)s->model_cap, s->var,
         -2.0 * s->ls * s->ls, mean_dev, var_dev); s->launches++;
     CU(cudaGetLastError());
     CU(copy_async(s, out_mean, mean_dev, (size_t)mrows * sizeof(double), cudaMemcpyDeviceToHost, s->stream));

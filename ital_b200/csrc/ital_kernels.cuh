@@ -1999,12 +1999,161 @@ __global__ void __launch_bounds__(256) k_record(long long row, const Best* __res
     if (pp.peer_base != nullptr) peer_put(pp, rec, rec_len);
 }
 
+// ---- GaussianProcess.update without the host (ital/gp.py:164-200): the model lives on the device ----------------
+// The Cholesky factor of K_LL + noise I (row-major, leading dimension ldk), beta = L_K^-1 y and the labelled rows
+// (as float64) are appended on the device, so that update() needs no device-to-host round trip.
+//
+// k_prepare_labelled: one block.  For the q <= 4 new points (local rows idx[a], targets y[a]) it gathers what the
+// labelled pass needs from the pool -- the rows as float64, their projections on the current factor, posterior mean
+// and variance -- computes the q x q triangle of the block Cholesky extension among them
+//   T[a][b] = (k(x_a, x_b) - u_a . u_b - sum_{c<b} T[a][c] T[b][c]) / piv_b,  piv_a^2 = v_a - sum_b T[a][b]^2 + noise,
+// writes the MultiExt block (and, for q = 1, the point record k_extend reads), appends the model rows and marks the
+// points as seen.  Dot products are reduced in a fixed order (thread-strided partial sums, xor butterfly, warps in
+// ascending order).
+__device__ __forceinline__ double block_sum_256(double v, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += red[k];
+    return t;
+}
+
+struct ModelRefs {                // device-resident model
+    double* LK;                   // [cap][ldk] lower triangle
+    int64_t ldk;
+    double* beta;
+    double* lab_x;                // [cap][d]
+    double* lab_sqn;
+};
+
+// append rows W .. W+q-1 of the model from a MultiExt block (header, z[q][d_pad], ur[q][W]); every thread of one block
+__device__ __forceinline__ void append_model_rows(const ModelRefs& M, int q, int W, int d, int d_pad, const double* ext) {
+    const MultiExt* h = reinterpret_cast<const MultiExt*>(ext);
+    const double* z = ext + sizeof(MultiExt) / sizeof(double);
+    const double* ur = z + (size_t)q * d_pad;
+    for (int a = 0; a < q; ++a) {
+        double* row = M.LK + (int64_t)(W + a) * M.ldk;
+        for (int j = threadIdx.x; j < W; j += blockDim.x) row[j] = ur[(size_t)a * W + j];
+        for (int j = threadIdx.x; j < d; j += blockDim.x) M.lab_x[(int64_t)(W + a) * d + j] = z[(size_t)a * d_pad + j];
+        if (threadIdx.x == 0) {
+            for (int b = 0; b < a; ++b) row[W + b] = h->tri[a * 4 + b];
+            row[W + a] = h->piv[a];
+            M.beta[W + a] = h->beta[a];
+            M.lab_sqn[W + a] = h->zn[a];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_append_model(ModelRefs M, int q, int W, int d, int d_pad,
+                                                      const double* __restrict__ ext) {
+    pdl_enter();
+    append_model_rows(M, q, W, d, d_pad, ext);
+}
+
+template <typename XT>
+__global__ void __launch_bounds__(256) k_prepare_labelled(int q, const int64_t* __restrict__ idx,
+                                                          const double* __restrict__ yv, int64_t row_offset, int64_t n,
+                                                          const XT* __restrict__ X, int d, int d_pad,
+                                                          const double* __restrict__ sqn, const double* __restrict__ m,
+                                                          const double* __restrict__ v, const double* __restrict__ U,
+                                                          int64_t ldu, int W, int w_cap, double var, double neg2ls2,
+                                                          double noise, double* __restrict__ ext,
+                                                          double* __restrict__ rec1, ModelRefs M,
+                                                          uint8_t* __restrict__ mask, uint8_t seen_bits) {
+    pdl_enter();
+    __shared__ double red[8];
+    __shared__ double hm[4], hv[4], tri[16], piv[4], beta[4];
+    MultiExt* h = reinterpret_cast<MultiExt*>(ext);
+    double* z = ext + sizeof(MultiExt) / sizeof(double);
+    double* ur = z + (size_t)q * d_pad;
+    for (int a = 0; a < q; ++a) {
+        const int64_t row = idx[a] - row_offset;
+        for (int j = threadIdx.x; j < d_pad; j += blockDim.x)
+            z[(size_t)a * d_pad + j] = j < d ? (double)X[row * (int64_t)d_pad + j] : 0.0;
+        for (int j = threadIdx.x; j < W; j += blockDim.x) ur[(size_t)a * W + j] = U[(int64_t)j * ldu + row];
+        if (threadIdx.x == 0) {
+            hm[a] = m[row];
+            hv[a] = v[row];
+            h->zn[a] = sqn[row];
+            mask[row] |= seen_bits;
+        }
+    }
+    if (threadIdx.x < 16) tri[threadIdx.x] = 0.0;
+    __syncthreads();
+    for (int a = 0; a < q; ++a) {
+        double cv = hv[a], ma = hm[a];
+        for (int b = 0; b < a; ++b) {
+            double pd = 0.0, pu = 0.0;
+            for (int j = threadIdx.x; j < d; j += blockDim.x) pd = fma(z[(size_t)a * d_pad + j], z[(size_t)b * d_pad + j], pd);
+            for (int j = threadIdx.x; j < W; j += blockDim.x) pu = fma(ur[(size_t)a * W + j], ur[(size_t)b * W + j], pu);
+            const double dot = block_sum_256(pd, red);
+            const double proj = block_sum_256(pu, red);
+            double num = var * exp((h->zn[a] + h->zn[b] - 2.0 * dot) / neg2ls2) - proj;
+            for (int c = 0; c < b; ++c) num -= tri[a * 4 + c] * tri[b * 4 + c];
+            const double e = num / piv[b];
+            __syncthreads();
+            if (threadIdx.x == 0) tri[a * 4 + b] = e;
+            cv -= e * e;
+            ma += e * beta[b];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            piv[a] = sqrt(fmax(cv + noise, 2.3e-308));
+            beta[a] = (yv[a] - ma) / piv[a];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 16) h->tri[threadIdx.x] = tri[threadIdx.x];
+    if (threadIdx.x < 4) {
+        h->piv[threadIdx.x] = threadIdx.x < q ? piv[threadIdx.x] : 0.0;
+        h->beta[threadIdx.x] = threadIdx.x < q ? beta[threadIdx.x] : 0.0;
+        if ((int)threadIdx.x >= q) h->zn[threadIdx.x] = 0.0;
+    }
+    if (q == 1 && rec1 != nullptr) {                    // the single-column pass reads a point record (k_extend)
+        for (int j = threadIdx.x; j < w_cap; j += blockDim.x) rec1[8 + j] = j < W ? ur[j] : 0.0;
+        for (int j = threadIdx.x; j < d; j += blockDim.x) rec1[8 + w_cap + j] = z[j];
+        if (threadIdx.x == 0) {
+            rec1[0] = (double)idx[0];
+            rec1[1] = 0.0;
+            rec1[2] = hm[0];
+            rec1[3] = hv[0];
+            rec1[4] = h->zn[0];
+            rec1[5] = hv[0];
+            rec1[6] = 0.0;
+            rec1[7] = 0.0;
+        }
+    }
+    __syncthreads();
+    append_model_rows(M, q, W, d, d_pad, ext);
+}
+
+// w = K^-1 y = L_K^-T beta (gp.py:158,196) by back substitution in one block: column sweep, the row of L_K that is
+// eliminated is contiguous.
+__global__ void __launch_bounds__(1024) k_model_w(ModelRefs M, int W, double* __restrict__ w) {
+    pdl_enter();
+    extern __shared__ double wsm[];
+    for (int j = threadIdx.x; j < W; j += blockDim.x) wsm[j] = M.beta[j];
+    __syncthreads();
+    for (int a = W - 1; a >= 0; --a) {
+        const double* row = M.LK + (int64_t)a * M.ldk;
+        const double wa = wsm[a] / row[a];
+        __syncthreads();
+        for (int b = threadIdx.x; b < a; b += blockDim.x) wsm[b] = fma(-row[b], wa, wsm[b]);
+        if (threadIdx.x == 0) wsm[a] = wa;
+        __syncthreads();
+    }
+    for (int j = threadIdx.x; j < W; j += blockDim.x) w[j] = wsm[j];
+}
+
 // GaussianProcess.predict (ital/gp.py:264-292) for arbitrary rows: one warp per test row.
 //   k_l = var * exp((|x|^2 + |x_l|^2 - 2 x . x_l) / s);  mean = w . k;  var = max(0, var - |L_K^-1 k|^2)
 __global__ void __launch_bounds__(128) k_predict(const double* __restrict__ Xt, int64_t mrows, int d,
                                                  const double* __restrict__ Xl, const double* __restrict__ sqn_l,
                                                  int nl, const double* __restrict__ wvec,
-                                                 const double* __restrict__ LK, double var, double neg2ls2,
+                                                 const double* __restrict__ LK, int64_t ldk, double var, double neg2ls2,
                                                  double* __restrict__ out_mean, double* __restrict__ out_var) {
     pdl_enter();
     extern __shared__ double sm[];
@@ -2034,8 +2183,8 @@ __global__ void __launch_bounds__(128) k_predict(const double* __restrict__ Xt, 
             double q = 0.0;
             for (int a = 0; a < nl; ++a) {               // forward substitution with the Cholesky factor
                 double u = kbuf[a];
-                for (int b = 0; b < a; ++b) u = fma(-LK[(int64_t)a * nl + b], kbuf[b], u);
-                u /= LK[(int64_t)a * nl + a];
+                for (int b = 0; b < a; ++b) u = fma(-LK[(int64_t)a * ldk + b], kbuf[b], u);
+                u /= LK[(int64_t)a * ldk + a];
                 kbuf[a] = u;
                 q = fma(u, u, q);
             }

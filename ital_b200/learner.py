@@ -56,6 +56,10 @@ class _Shard(object):
         records, y = _capi.as_f64(records), _capi.as_f64(y)
         _capi.check(self.lib.ital_add_labelled_many(self.handle, len(y), _capi.dptr(records), _capi.dptr(y)))
 
+    def update_labelled(self, idx, y):
+        idx, y = _capi.as_i64(idx), _capi.as_f64(y)
+        _capi.check(self.lib.ital_update_labelled(self.handle, len(idx), _capi.i64ptr(idx), _capi.dptr(y)))
+
     def mark_seen(self, idx):
         idx = _capi.as_i64(idx)
         if len(idx):
@@ -475,8 +479,11 @@ class ITAL(object):
         idx, y = [int(i) for i in idx], [float(v) for v in y]
         for lo in range(0, len(idx), 4):
             chunk = idx[lo:lo + 4]
-            recs = self._comm.sum_records(self._shard.export_points(chunk))     # all in the current state
-            self._shard.add_labelled_many(recs, y[lo:lo + 4])
+            if self._comm.world_size == 1:
+                self._shard.update_labelled(chunk, y[lo:lo + 4])                # all on the device, nothing waits
+            else:
+                recs = self._comm.sum_records(self._shard.export_points(chunk))     # all in the current state
+                self._shard.add_labelled_many(recs, y[lo:lo + 4])
             self._labelled_idx.extend(chunk)
             self._labelled_y.extend(y[lo:lo + 4])
         self._rel_mean = None

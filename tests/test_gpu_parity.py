@@ -171,7 +171,9 @@ def test_general_feedback_model_golden_and_oracle(name):
     lit.fetch_unlabelled(int(g['k']), forced=ret)
     for t, (sc, tr, tl) in enumerate(zip(gpu.last_step_scores, ora.trace, lit.trace)):
         np.testing.assert_allclose(sc[tr['candidates']], tr['scores'], rtol=SCORE_RTOL, atol=1e-9, err_msg='step %d' % t)
-        assert tr['argmax'] == ret[t] or tr['scores'][list(tr['candidates']).index(ret[t])] >= tr['scores'].max() * (1 - 1e-12)
+        # (the same candidate, or one the oracle scores within round-off of its maximum: symmetric rows of the toy set)
+        assert tr['argmax'] == ret[t] or tr['scores'][list(tr['candidates']).index(ret[t])] >= \
+            tr['scores'].max() - 1e-9 * abs(tr['scores'].max())
         np.testing.assert_allclose(sc[tl['candidates']], tl['scores'], rtol=1e-5, atol=1e-9, err_msg='step %d' % t)
     for t, st in enumerate(g['steps']):          # the reference's own record, as far as the paths coincide
         if ret[t] != st['chosen']:

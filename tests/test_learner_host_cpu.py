@@ -47,6 +47,12 @@ class StubShard(object):
         self.labelled += idx
         self.seen.update(idx)
 
+    def update_labelled(self, idx, y):
+        idx = [int(i) for i in idx]
+        self.calls.append(('add', idx, [float(v) for v in y]))
+        self.labelled += idx
+        self.seen.update(idx)
+
     def mark_seen(self, idx):
         self.calls.append(('seen', [int(i) for i in idx]))
         self.seen.update(int(i) for i in idx)
