@@ -113,6 +113,14 @@ int ital_fetch_result(ital_shard* s, int max_out, int64_t* out_idx, double* out_
 int ital_fetch_begin(ital_shard* s, double label_prob, double mistake_prob);
 int ital_fetch_propose(ital_shard* s, double floor_score, int exhaustive, double* record);
 int ital_fetch_commit(ital_shard* s, const double* record);
+/* VarianceSampling.fetch_unlabelled (ital/baseline_methods.py:124-155) on the same batch state: inside a fetch
+ * (ital_fetch_begin ... ital_fetch_end) score every local candidate by the change of "sum of variances minus sum of
+ * covariances" of the batch when it is appended -- v_i - sum_a cov(r_a, i), from the incremental Cholesky rows the
+ * streaming pass of ital_fetch_commit maintains (lazy rows must be off) -- or, with use_correlations == 0, by its
+ * posterior variance alone, and write the record of the local best (score desc, row asc).  The reference's first pick
+ * with use_correlations does not exclude unnameable rows (baseline_methods.py:133): first_pick_takes_unnameable != 0
+ * mirrors that. */
+int ital_variance_propose(ital_shard* s, int use_correlations, int first_pick_takes_unnameable, double* record);
 int ital_fetch_end(ital_shard* s);
 int ital_fetch(ital_shard* s, int k, double label_prob, double mistake_prob, int exhaustive,
                int64_t* out_idx, double* out_scores);

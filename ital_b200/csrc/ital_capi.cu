@@ -43,7 +43,7 @@ int fail(int code, const char* fmt, ...) {
             return fail(ITAL_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-constexpr uint8_t kSeen = 1, kSelected = 2, kNotCandidate = 4, kRestricted = 8;
+constexpr uint8_t kSeen = 1, kSelected = 2, kNotCandidate = 4, kRestricted = 8, kUnnameable = 16;
 constexpr double kPruneMargin = 1e-6;   // slack of the lazy-greedy bound against quadrature round-off
 constexpr int kArgmaxBlocks = 592;      // 4 x 148 SMs
 
@@ -1427,7 +1427,7 @@ int ital_mark_seen(ital_shard* s, int64_t m, const int64_t* global_idx) {
     int rc = ensure_idx(s, (int64_t)loc.size());
     if (rc) return rc;
     CU(copy_async(s, s->idx_dev, loc.data(), loc.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream));
-    pdl(k_mask_rows, grid_for(s, (int64_t)loc.size(), 256), 256, 0, s)(s->mask, s->idx_dev, (int64_t)loc.size(), kSeen); s->launches++;
+    pdl(k_mask_rows, grid_for(s, (int64_t)loc.size(), 256), 256, 0, s)(s->mask, s->idx_dev, (int64_t)loc.size(), (uint8_t)(kSeen | kUnnameable)); s->launches++;
     CU(cudaGetLastError());
     if (loc.size() * sizeof(int64_t) > 32 * 1024) CU(cudaStreamSynchronize(s->stream));   // (small pageable copies are staged)
     return ITAL_OK;
@@ -1543,6 +1543,30 @@ int ital_fetch_propose(ital_shard* s, double floor_score, int exhaustive, double
     memcpy(record, s->rec_host, (size_t)rl * sizeof(double));
     read_step_stats(s, step);
     s->stats[3] = step == 0 ? 0.0 : hb;
+    return ITAL_OK;
+}
+
+int ital_variance_propose(ital_shard* s, int use_correlations, int first_pick_takes_unnameable, double* record) {
+    if (!s || !record) return fail(ITAL_EINVAL, "ital_variance_propose: bad arguments");
+    if (!s->fetching) return fail(ITAL_ESTATE, "ital_variance_propose outside a fetch");
+    if (s->t >= kMaxBatch) return fail(ITAL_EINVAL, "batches of more than %d samples are not supported", kMaxBatch);
+    CU(cudaSetDevice(s->device));
+    const int blocks = std::min(kArgmaxBlocks, grid_for(s, s->n, 256));
+    const int t = use_correlations ? s->t : 0;
+    const uint8_t allow = (first_pick_takes_unnameable && s->t == 0) ? (uint8_t)(kSeen | kUnnameable) : (uint8_t)0;
+    pdl(k_var_score, blocks, 256, 0, s)(s->n, s->v, s->U, s->ldu, s->W, t, s->base_L_dev, s->mask, allow, s->score,
+                                        s->block_best); s->launches++;
+    CU(cudaGetLastError());
+    PickSrc pick;
+    pick.block_best = s->block_best;
+    pick.nblocks = blocks;
+    s->proposals = s->t + 1;
+    int rc = make_record(s, -1, s->rec_dev, false, pick);
+    if (rc) return rc;
+    const int64_t rl = record_doubles(s);
+    CU(copy_async(s, s->rec_host, s->rec_dev, (size_t)rl * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    memcpy(record, s->rec_host, (size_t)rl * sizeof(double));
     return ITAL_OK;
 }
 

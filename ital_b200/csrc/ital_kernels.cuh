@@ -1023,6 +1023,53 @@ __global__ void __launch_bounds__(256) k_score0(int64_t n, const double* __restr
     }
 }
 
+// VarianceSampling (ital/baseline_methods.py:110-155): score of appending row i to the running batch,
+//   sum of the variances minus sum of the covariances of ret + [i]  =  const(ret) + v_i - sum_a c(r_a, i),
+// with c(r_a, i) = L_b[a] . l_i from the incremental Cholesky rows, i.e. v_i - g . l_i with g the column sums of L_b.
+// t = 0 (and use_correlations = False): the posterior variance itself, clamped at 0 as predict_stored('diag') does.
+// `allow_mask`: mask value that is admitted besides 0 (the reference's first pick does not exclude unnameable rows).
+__global__ void __launch_bounds__(256) k_var_score(int64_t n, const double* __restrict__ v, const double* __restrict__ U,
+                                                   int64_t ldu, int W0, int t, const double* __restrict__ base_L,
+                                                   const uint8_t* __restrict__ mask, uint8_t allow_mask,
+                                                   double* __restrict__ score, Best* __restrict__ block_best) {
+    pdl_enter();
+    __shared__ double g[16];
+    if (threadIdx.x < 16) {
+        double acc = 0.0;
+        for (int a = threadIdx.x; a < t; ++a) acc += base_L[a * kBaseStride + threadIdx.x];
+        g[threadIdx.x] = (int)threadIdx.x < t ? acc : 0.0;
+    }
+    __syncthreads();
+    double bs = 0.0;
+    long long bi = -1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint8_t mk = mask[i];
+        double s = nan("");
+        if (mk == 0 || (allow_mask != 0 && mk == allow_mask)) {
+            s = t == 0 ? fmax(v[i], 0.0) : v[i];
+            for (int j = 0; j < t; ++j) s = fma(-g[j], U[(int64_t)(W0 + j) * ldu + i], s);
+            if (better(s, i, bs, bi)) { bs = s; bi = i; }
+        }
+        score[i] = s;
+    }
+    __shared__ double ss[8];
+    __shared__ long long si[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(os, oi, bs, bi)) { bs = os; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = bs; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            if (better(ss[w], si[w], bs, bi)) { bs = ss[w]; bi = si[w]; }
+        block_best[blockIdx.x].score = bs;
+        block_best[blockIdx.x].idx = bi;
+    }
+}
+
 // argmax of `values` over candidate rows (mask == 0), per block
 __global__ void __launch_bounds__(1024) k_argmax_rows(int64_t n, const double* __restrict__ values,
                                                       const uint8_t* __restrict__ mask,

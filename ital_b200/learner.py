@@ -81,6 +81,12 @@ class _Shard(object):
                                                 _capi.dptr(rec)))
         return rec
 
+    def variance_propose(self, use_correlations, first_pick_takes_unnameable):
+        rec = np.zeros(self.record_doubles())
+        _capi.check(self.lib.ital_variance_propose(self.handle, int(bool(use_correlations)),
+                                                   int(bool(first_pick_takes_unnameable)), _capi.dptr(rec)))
+        return rec
+
     def fetch_commit(self, record):
         record = _capi.as_f64(record)
         _capi.check(self.lib.ital_fetch_commit(self.handle, _capi.dptr(record)))
@@ -664,3 +670,44 @@ class EntropySampling(ITAL):
         for name in ('label_prob', 'mistake_prob', 'label_estimation'):
             kwargs.pop(name, None)
         ITAL.__init__(self, data, queries, length_scale, var, noise, label_prob=1.0, mistake_prob=0.0, **kwargs)
+
+
+class VarianceSampling(ITAL):
+    """Maximum predictive variance; drop-in for `ital.baseline_methods.VarianceSampling`
+    (ital/baseline_methods.py:110-155).  With `use_correlations` a batch is scored by the sum of its variances minus
+    the sum of its covariances and built greedily: the change when row i joins is v_i - sum_a cov(r_a, i), read off the
+    incremental Cholesky rows that ITAL's streaming pass maintains for every row (predict_cov_batch is never formed).
+    Like the reference, the first pick of that mode does not exclude unnameable samples (baseline_methods.py:133)."""
+
+    def __init__(self, data=None, queries=[], length_scale=0.1, var=1.0, noise=1e-6, use_correlations=False, **kwargs):
+        self.use_correlations = use_correlations
+        for name in ('label_prob', 'mistake_prob', 'label_estimation', 'lazy_rows'):
+            kwargs.pop(name, None)
+        ITAL.__init__(self, data, queries, length_scale, var, noise, **kwargs)
+
+    def fetch_unlabelled(self, k, show_progress=False):
+        if len(self._labelled_idx) == 0:
+            raise RuntimeError('fetch_unlabelled() needs at least one query or labelled sample')
+        k = int(k)
+        if k > self.MAX_BATCH:
+            raise NotImplementedError('batches of more than %d samples are not supported' % self.MAX_BATCH)
+        corr = bool(self.use_correlations)
+        # the streaming pass keeps every row's batch columns current (all rows are scored); without correlations
+        # nothing of the batch enters the score, so no pass is needed at all
+        _capi.check(self._shard.lib.ital_set_lazy_rows(self._shard.handle, int(not corr)))
+        ret, self.last_fetch_scores = [], []
+        self._shard.fetch_begin(1.0, 0.0)
+        try:
+            for it in range(k):
+                rec = self._shard.variance_propose(corr, corr)
+                allrec = self._comm.gather_records(rec)
+                win = pick_winner(allrec)
+                if win < 0:
+                    break
+                ret.append(int(allrec[win][0]))
+                self.last_fetch_scores.append(float(allrec[win][1]))
+                if it + 1 < k:
+                    self._shard.fetch_commit(allrec[win])
+        finally:
+            self._shard.fetch_end()
+        return ret

@@ -22,12 +22,30 @@ def _npz_names():
 
 def golden_names():
     """Fetch goldens (every greedy step of a fetch_unlabelled of the reference)."""
-    return [n for n in _npz_names() if not n.startswith('updpred_')]
+    return [n for n in _npz_names() if not n.startswith(('updpred_', 'experiment_', 'baseline_'))]
 
 
 def updpred_names():
     """updated_prediction goldens (make_golden.py run_updated_prediction)."""
     return [n for n in _npz_names() if n.startswith('updpred_')]
+
+
+def baseline_names():
+    """Goldens of EntropySampling / VarianceSampling (make_baseline_golden.py)."""
+    return [n for n in _npz_names() if n.startswith('baseline_')]
+
+
+def load_baseline(name):
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + '.npz'), allow_pickle=False))
+    g['updates'] = [dict(zip(g['upd%d_idx' % u].tolist(), g['upd%d_val' % u].tolist()))
+                    for u in range(int(g['n_updates']))]
+    g['entropy_steps'] = []
+    t = 0
+    while 'entropy_step%d_entropy' % t in g:
+        g['entropy_steps'].append(dict(candidates=g['entropy_step%d_candidates' % t], entropy=g['entropy_step%d_entropy' % t]))
+        t += 1
+    g['learner_kw'] = dict(length_scale=float(g['length_scale']), var=float(g['var']), noise=float(g['noise']))
+    return g
 
 
 def load_updpred(name):

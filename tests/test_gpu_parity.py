@@ -8,7 +8,7 @@ oracle (absolute floor 1e-9 for moments, 1e-12 = the reference's eps for scores)
 import numpy as np
 import pytest
 
-from conftest import drive, golden_names, load_golden, load_updpred, updpred_names
+from conftest import baseline_names, drive, golden_names, load_baseline, load_golden, load_updpred, updpred_names
 
 pytestmark = pytest.mark.gpu
 
@@ -300,6 +300,39 @@ def test_entropy_sampling_shares_the_kernels():
         _label_syn(L, assign)
     assert a.fetch_unlabelled(4) == b.fetch_unlabelled(4)
     assert np.array_equal(a.last_fetch_scores, b.last_fetch_scores)
+
+
+@pytest.mark.parametrize('name', baseline_names())
+def test_entropy_sampling_matches_the_reference(name):
+    """EntropySampling.fetch_unlabelled of the UNMODIFIED reference (ital/baseline_methods.py:241-287: single_entropy
+    for the first sample, batch_entropy = -sum p log p over the joint sign patterns afterwards): same batch, and every
+    candidate's entropy of every greedy step within 1e-6 (the reference clips single probabilities to [1e-8, 1 - 1e-8]
+    and drops terms below 1e-12; ITAL's summand is p (log(1 + 1e-12) - log(p + 1e-12)): differences below 1e-10)."""
+    from ital_b200 import EntropySampling
+    g = load_baseline(name)
+    gpu = drive(EntropySampling(g['X'], exhaustive=True, **g['learner_kw']), g)
+    ret = gpu._fetch_stepwise(int(g['k']), keep_scores=True)
+    assert ret == g['entropy_ret'].tolist()
+    for t, (sc, st) in enumerate(zip(gpu.last_step_scores, g['entropy_steps'])):
+        np.testing.assert_allclose(sc[st['candidates']], st['entropy'], rtol=1e-6, atol=2e-6 if t >= 2 else 1e-9,
+                                   err_msg='%s step %d' % (name, t))
+    gpu.exhaustive = False
+    assert gpu.fetch_unlabelled(int(g['k'])) == ret
+
+
+@pytest.mark.parametrize('name', baseline_names())
+def test_variance_sampling_matches_the_reference(name):
+    """VarianceSampling.fetch_unlabelled of the UNMODIFIED reference (ital/baseline_methods.py:110-155), without and with
+    use_correlations (greedy on sum of variances - sum of covariances, from predict_cov_batch there, from the
+    incremental Cholesky rows here)."""
+    from ital_b200 import VarianceSampling
+    g = load_baseline(name)
+    plain = drive(VarianceSampling(g['X'], **g['learner_kw']), g)
+    np.testing.assert_allclose(np.maximum(plain.gp.predict_stored(cov_mode='diag')[1], 0), g['var_diag'], rtol=1e-6, atol=1e-9)
+    assert plain.fetch_unlabelled(int(g['k'])) == g['variance_ret'].tolist()
+    corr = drive(VarianceSampling(g['X'], use_correlations=True, **g['learner_kw']), g)
+    assert corr.fetch_unlabelled(int(g['k'])) == g['variance_corr_ret'].tolist()
+    assert corr.fetch_unlabelled(2) == g['variance_corr_ret'].tolist()[:2]          # (nothing of a fetch persists)
 
 
 def test_repeated_rounds_track_the_oracle():
