@@ -314,8 +314,9 @@ def test_entropy_sampling_matches_the_reference(name):
     ret = gpu._fetch_stepwise(int(g['k']), keep_scores=True)
     assert ret == g['entropy_ret'].tolist()
     for t, (sc, st) in enumerate(zip(gpu.last_step_scores, g['entropy_steps'])):
-        np.testing.assert_allclose(sc[st['candidates']], st['entropy'], rtol=1e-6, atol=2e-6 if t >= 2 else 1e-9,
-                                   err_msg='%s step %d' % (name, t))
+        # step 0: the reference's clip of p to [1e-8, 1 - 1e-8] lifts the entropy of decided samples to 1.9e-7
+        atol = 2.5e-7 if t == 0 else (2e-6 if t >= 2 else 1e-9)
+        np.testing.assert_allclose(sc[st['candidates']], st['entropy'], rtol=1e-6, atol=atol, err_msg='%s step %d' % (name, t))
     gpu.exhaustive = False
     assert gpu.fetch_unlabelled(int(g['k'])) == ret
 
