@@ -44,7 +44,12 @@ int fail(int code, const char* fmt, ...) {
     } while (0)
 
 constexpr uint8_t kSeen = 1, kSelected = 2, kNotCandidate = 4, kRestricted = 8, kUnnameable = 16;
-constexpr double kPruneMargin = 1e-6;   // slack of the lazy-greedy bound against quadrature round-off
+// Slack of the lazy-greedy bound: a row is pruned only if its bound (a gain evaluated exactly at an EARLIER step) stays
+// below the best exact score of this step by more than this, so it has to cover the quadrature error of both steps'
+// node sets (measured against converged rules, tests/test_orthant_vs_scipy.py: scores to 1e-7 for up to 4 base
+// variables, 4e-6 for 5, 1e-4 for the lattice from 6 on).
+constexpr double kPruneMargin = 1e-6;
+inline double prune_margin(int t) { return t <= 3 ? kPruneMargin : (t == 4 ? 2e-6 : (t == 5 ? 2e-5 : 1e-3)); }
 constexpr int kArgmaxBlocks = 592;      // 4 x 148 SMs
 
 }  // namespace
@@ -815,7 +820,7 @@ int stage_a(ital_shard* s, double floor_score, bool ahead) {
     // best of stage A and, in the same kernel, the threshold of stage B: every row whose bound still
     // reaches the best exact score found so far
     pdl(k_argmax_list, 1, 256, 0, s)(s->counters, s->worklist, s->score, s->best + 1, s->hbase_dev,
-                                     floor_score, kPruneMargin, s->thr_dev, s->counters); s->launches++;
+                                     floor_score, prune_margin(s->t), s->thr_dev, s->counters); s->launches++;
     pdl(k_worklist, grid_for(s, s->n, 256), 256, 0, s)(s->n, s->mask, s->gain, s->thr_dev, 0,
                                                        s->counters, s->worklist); s->launches++;
     CU(cudaGetLastError());

@@ -21,8 +21,8 @@ split at the orthant boundary ``a_j(eta_<j) = -(m_j + sum_{i<j} L_ji eta_i) / L_
 shared out between the panels in proportion to their widths (``snq_split``; at least ``SNQ_QMIN`` each) and the
 weights are multiplied by the standard normal density.  The node set depends only on the base variables, so one set
 serves every candidate of a greedy step.  ``R = SNQ_R`` and ``Q = snq_order(t)`` for
-t <= 3 base variables; from t = 4 on (batches of more than 4 samples) the tensor rule is replaced by a fixed
-quasi-Monte-Carlo node set (``qmc_nodes``).
+t <= 5 base variables; from t = 6 on (batches of more than 6 samples) the tensor rule is replaced by a
+sequential-conditioning lattice inside every base orthant (``sc_nodes``).
 
 Nothing here is imported by the product path (ital_b200/); only tests/, bench.py's cpu_baseline /
 ``--impl reference`` legs and ``__graft_entry__.smoke()`` use it, as the checker.
@@ -38,46 +38,80 @@ _SQRT_2PI = np.sqrt(2.0 * np.pi)
 _GL_CACHE = {}
 
 
-SNQ_QMC_FROM = 4       # bases of this many variables or more use the quasi-Monte-Carlo node set
-SNQ_QMC_N = 65536
-_PRIMES = (2, 3, 5, 7, 11, 13, 17, 19, 23, 29)
+SNQ_SC_FROM = 6        # bases of this many variables or more use the sequential-conditioning lattice
+SNQ_SC_N = 262144      # ... with about this many nodes over all orthants
+SNQ_SC_PILOT = 256     # nodes per orthant of the pilot pass that estimates the orthant masses
+SNQ_SC_MIN = 64        # nodes per orthant at least
+SNQ_SC_PMIN = 1e-13    # orthants lighter than this are left out
+_PRIMES = (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37)
 
 
 def snq_order(t):
-    """Gauss-Legendre nodes per panel for a base of ``t`` <= 3 variables (0: quasi-Monte-Carlo nodes instead)."""
+    """Gauss-Legendre nodes per panel for a base of ``t`` <= 5 variables (0: sequential-conditioning lattice instead).
+
+    Accuracy of the orthant probabilities / of the scores against converged rules (tests/test_orthant_vs_scipy.py,
+    DESIGN.md): t = 1: 1e-11, t = 2: 1e-9, t = 3: 1e-7, t = 4: 1e-8 / 1e-7, t = 5: ~2e-6 / ~2e-5."""
     if t <= 1:
         return 32
     if t == 2:
         return 16
-    if t == 3:
+    if t in (3, 4):
         return 12
+    if t == 5:
+        return 10
     return 0
 
 
-def qmc_nodes(m_base, L_base, n=SNQ_QMC_N):
-    """Node set for t >= 4 base variables (batches of more than 4 samples), where a tensor rule explodes.
+def sc_nodes(m_base, L_base, n_total=SNQ_SC_N):
+    """Node set for t >= 6 base variables (batches of more than 6 samples), where a tensor rule explodes.
 
-    Kronecker sequence u_kj = frac((k + 1/2) sqrt(p_j)), p_j the j-th prime, folded by the tent map
-    1 - |2u - 1| and mapped through the inverse normal CDF; equal weights; the orthant of a node is the sign
-    pattern of m + L eta.  Absolute error of the orthant probabilities ~1e-3 at n = 65536 -- the accuracy class of
-    the reference's own ``mvndst(maxpts=100*dim, abseps=1e-4)`` (ital/ital.py:380-381) for these dimensions.
+    For every orthant b of the base a Kronecker sequence u_kj = frac((k + 1/2) sqrt(p_j)), p_j the j-th prime, folded by
+    the tent map 1 - |2u - 1|, is pushed through Genz's sequential conditioning INSIDE that orthant: eta_j is drawn
+    from the standard normal truncated to the half-line on the orthant's side of the boundary
+    a_j = -(m_j + sum_{i<j} L_ji eta_i) / L_jj and the node weight collects the half-line masses, so the integrand the
+    candidates add (Phi of an affine function of eta) stays smooth on every node set.  A pilot pass of SNQ_SC_PILOT
+    nodes per orthant estimates the orthant masses; ``n_total`` nodes are then shared out in proportion to them (at
+    least SNQ_SC_MIN each; orthants below SNQ_SC_PMIN are left out) and the weights are scaled so that the orthant masses
+    add up to one.  Nodes come out sorted by orthant.  Accuracy: 1e-4 class in the orthant probabilities
+    (tests/test_orthant_vs_scipy.py) -- the reference's own ``mvndst(maxpts=100*dim, abseps=1e-4)``
+    (ital/ital.py:380-381) is no better for these dimensions.
     """
     from scipy.special import ndtri
     m_base = np.asarray(m_base, dtype=np.float64)
     L_base = np.asarray(L_base, dtype=np.float64)
     t = len(m_base)
-    k = np.arange(n, dtype=np.float64) + 0.5
-    eta = np.empty((n, t))
-    for j in range(t):
-        a = np.sqrt(float(_PRIMES[j]))
-        a -= np.floor(a)
-        u = k * a
+    alpha = np.array([np.sqrt(float(p)) - np.floor(np.sqrt(float(p))) for p in _PRIMES[:t]])
+
+    def gen(b, N):
+        k = np.arange(N, dtype=np.float64) + 0.5
+        u = k[:, None] * alpha[None, :]
         u -= np.floor(u)
         u = 1.0 - np.abs(2.0 * u - 1.0)
-        eta[:, j] = ndtri(np.clip(u, 1e-16, 1.0 - 1e-16))
-    z = m_base[None, :] + eta @ L_base.T
-    orth = ((z > 0).astype(np.int64) << np.arange(t)[None, :]).sum(axis=1)
-    return eta, np.full(n, 1.0 / n), orth
+        eta = np.zeros((N, t))
+        w = np.full(N, 1.0 / N)
+        for j in range(t):
+            a = -(m_base[j] + eta[:, :j] @ L_base[j, :j]) / L_base[j, j]
+            if (b >> j) & 1:
+                q = ndtr(-a)
+                eta[:, j] = -ndtri(np.maximum(u[:, j] * q, 1e-300))
+            else:
+                q = ndtr(a)
+                eta[:, j] = ndtri(np.maximum(u[:, j] * q, 1e-300))
+            w = w * q
+        return eta, w
+
+    P = np.array([gen(b, SNQ_SC_PILOT)[1].sum() for b in range(1 << t)])
+    etas, ws, orth = [], [], []
+    for b in range(1 << t):
+        if P[b] < SNQ_SC_PMIN:
+            continue
+        nb = max(SNQ_SC_MIN, int(np.floor(n_total * P[b] / P.sum() + 0.5)))
+        e, w = gen(b, nb)
+        etas.append(e)
+        ws.append(w)
+        orth.append(np.full(nb, b, dtype=np.int64))
+    w = np.concatenate(ws)
+    return np.concatenate(etas), w / w.sum(), np.concatenate(orth)      # (the orthant masses must add up to one)
 
 
 def gauss_legendre(q):
@@ -112,8 +146,8 @@ def snq_nodes(m_base, L_base, q=None, R=SNQ_R, w_min=SNQ_WMIN):
     L_base = np.asarray(L_base, dtype=np.float64)
     t = len(m_base)
     if q is None:
-        if t >= SNQ_QMC_FROM:
-            return qmc_nodes(m_base, L_base)
+        if t >= SNQ_SC_FROM:
+            return sc_nodes(m_base, L_base)
         q = snq_order(t)
     eta = np.zeros((1, 0))
     w = np.ones(1)

@@ -259,18 +259,25 @@ def test_bulk_staged_stream_is_bit_identical():
 
 
 def test_batches_beyond_four_track_the_oracle():
-    """Greedy steps with 4 and more base variables switch from the tensor rule to 65 536 quasi-Monte-Carlo nodes
-    (oracle/orthant.py qmc_nodes, csrc/snq_host.h); same nodes on both sides, so scores agree to round-off."""
+    """Greedy steps with 4 and 5 base variables use the tensor rule at 12 / 10 nodes per panel (81k / 400k nodes, generated
+    on the host), from 6 base variables on the sequential-conditioning lattice (oracle/orthant.py sc_nodes,
+    csrc/snq_host.h generate_sc); same nodes on both sides, so scores agree to round-off.  The persistent kernel runs the
+    first four steps and hands over to the multi-kernel loop; the lazy-greedy margin grows with the step's quadrature
+    error (prune_margin)."""
     from oracle.ital_oracle import OracleITAL
     X, assign = _syn(500, 48, seed=21, centres=8)
     gpu = _gpu_learner(X, length_scale=1.0, exhaustive=True)
     ora = OracleITAL(X, length_scale=1.0)
     _label_syn(gpu, assign)
     _label_syn(ora, assign)
-    ret, kinds = _compare_steps(gpu, ora, 7)
-    assert len(ret) == 7 and len(set(ret)) == 7
+    ret, kinds = _compare_steps(gpu, ora, 8)
+    assert len(ret) == 8 and len(set(ret)) == 8
     gpu.exhaustive = False
-    assert gpu.fetch_unlabelled(7) == ret
+    assert gpu.fetch_unlabelled(8) == ret and gpu.last_fused_steps == 4
+    gpu.lazy_rows = False
+    assert gpu.fetch_unlabelled(8) == ret and gpu.last_fused_steps == 0
+    with pytest.raises(NotImplementedError):
+        gpu.fetch_unlabelled(12)
 
 
 @pytest.mark.parametrize('var,noise,ls', [(2.5, 1e-4, 0.7), (0.3, 1e-6, 2.0), (1.0, 1e-2, 1.0)])
