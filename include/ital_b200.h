@@ -87,6 +87,11 @@ int ital_mark_seen(ital_shard* s, int64_t m, const int64_t* global_idx);
 /* ITAL.fetch_unlabelled's top_candidates restriction (ital/ital.py:111-117): candidates are the unseen rows
  * whose global index is in `global_idx` (m entries; m < 0 lifts the restriction). */
 int ital_restrict_candidates(ital_shard* s, int64_t m, const int64_t* global_idx);
+/* The same restriction computed on the device for a learner on one shard: the `top` unseen pool rows with the largest
+ * posterior mean stay candidates (np.argpartition(rel_mean[candidates], -top)[-top:], ital/ital.py:116; exact ties at
+ * the cut go to the lower row).  A masked radix sort of the means; no n-sized copy to the host.  Lift with
+ * ital_restrict_candidates(s, -1, NULL). */
+int ital_restrict_top(ital_shard* s, int64_t top);
 
 /* ---- greedy batch construction (ITAL.fetch_unlabelled, ital/ital.py:119-134) ---------------------------
  * ital_fetch_begin:   AppendedMutualInformation.__init__/set_ret([]) (ital/ital.py:491-558).
@@ -152,6 +157,12 @@ int ital_fetch_peer(ital_shard* s, int k, double label_prob, double mistake_prob
  * prunes most rows. */
 int ital_set_lazy_rows(ital_shard* s, int on);
 
+/* ITAL(label_estimation=...) (ital/ital.py:62-67, 210-219): 0 'mean' (default: expectation over the relevance
+ * configurations), 1 'optimistic' / 2 'pessimistic' (the largest / the "first or smaller" single term of the
+ * enumeration, kept in the reference's order).  Other than 'mean' there is no lazy-greedy bound: every candidate is
+ * scored at every step by the general-model kernel, batches of at most 5 samples. */
+int ital_set_label_estimation(ital_shard* s, int mode);
+
 /* The fused persistent fetch kernel (on by default; environment ITAL_B200_FUSED=0 turns it off).  With lazy rows on, a
  * user who labels every sample (label_prob >= 1) and pruning (exhaustive == 0), ital_fetch / ital_fetch_peer run the
  * first four greedy steps -- scores of the first step, quadrature nodes, stage A, worklist, exact scores, argmax and
@@ -195,6 +206,9 @@ int64_t ital_top_results(ital_shard* s, int64_t k, int64_t* out_idx, double* out
  * 0) for m arbitrary rows of float64 features.  Uses the labelled rows held by this shard's model, so it is
  * valid on any shard (the labelled points are replicated). */
 int ital_predict(ital_shard* s, const double* Xt, int64_t m, double* out_mean, double* out_var);
+/* The same with the projections u = L_K^-1 k(X_L, x) of the m rows (out_proj[m][ital_width()], row-major), from which
+ * the caller forms the 'full' covariance k(Xt, Xt) - U U^T of GaussianProcess.predict (ital/gp.py:285-287). */
+int ital_predict_proj(ital_shard* s, const double* Xt, int64_t m, double* out_mean, double* out_proj);
 
 /* Measurement hooks (bench.py): with profiling on, every launch of the streaming kernel (k_extend) is bracketed
  * by CUDA events on the shard's stream.  ital_profile_read synchronises, returns the accumulated kernel time in

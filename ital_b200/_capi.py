@@ -34,6 +34,7 @@ SIGNATURES = {
     'ital_update_labelled': (ctypes.c_int, [_shard_p, ctypes.c_int, _c_int64_p, _c_double_p]),
     'ital_mark_seen': (ctypes.c_int, [_shard_p, ctypes.c_int64, _c_int64_p]),
     'ital_restrict_candidates': (ctypes.c_int, [_shard_p, ctypes.c_int64, _c_int64_p]),
+    'ital_restrict_top': (ctypes.c_int, [_shard_p, ctypes.c_int64]),
     'ital_fetch_propose_dev': (ctypes.c_int, [_shard_p, ctypes.c_double, ctypes.c_int, ctypes.c_void_p]),
     'ital_fetch_commit_dev': (ctypes.c_int, [_shard_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     'ital_fetch_result': (ctypes.c_int, [_shard_p, ctypes.c_int, _c_int64_p, _c_double_p]),
@@ -52,6 +53,7 @@ SIGNATURES = {
                                        _c_int64_p, _c_double_p]),
     'ital_set_lazy_rows': (ctypes.c_int, [_shard_p, ctypes.c_int]),
     'ital_set_bulk_stream': (ctypes.c_int, [_shard_p, ctypes.c_int]),
+    'ital_set_label_estimation': (ctypes.c_int, [_shard_p, ctypes.c_int]),
     'ital_set_fused': (ctypes.c_int, [_shard_p, ctypes.c_int]),
     'ital_fused_trace': (ctypes.c_int64, [_shard_p, ctypes.c_int, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int64]),
     'ital_fetch_stats': (ctypes.c_int, [_shard_p, _c_double_p]),
@@ -60,6 +62,7 @@ SIGNATURES = {
     'ital_rel_var': (ctypes.c_int, [_shard_p, _c_double_p]),
     'ital_top_results': (ctypes.c_int64, [_shard_p, ctypes.c_int64, _c_int64_p, _c_double_p]),
     'ital_predict': (ctypes.c_int, [_shard_p, _c_double_p, ctypes.c_int64, _c_double_p, _c_double_p]),
+    'ital_predict_proj': (ctypes.c_int, [_shard_p, _c_double_p, ctypes.c_int64, _c_double_p, _c_double_p]),
     'ital_profile_enable': (ctypes.c_int, [_shard_p, ctypes.c_int]),
     'ital_profile_read': (ctypes.c_int, [_shard_p, _c_double_p, _c_int64_p, _c_double_p]),
     'ital_launch_count': (ctypes.c_int64, [_shard_p]),

@@ -152,6 +152,7 @@ struct ital_shard {
     int t = 0;                       // points selected in the running fetch
     bool fetching = false;
     double label_prob = 1.0, mistake_prob = 0.0;
+    int estimation = 0;              // label_estimation: 0 'mean', 1 'optimistic', 2 'pessimistic' (ital/ital.py:210-219)
 
     // the small model lives on the device (appended by k_prepare_labelled / k_append_model): Cholesky factor of
     // K_LL + noise I (row-major lower triangle, leading dimension model_cap), beta = L_K^-1 y, the labelled rows as
@@ -544,7 +545,7 @@ int launch_extend_multi(ital_shard* s, int q, int W_used) {
 // (1 - mp)^(t+1) and gets log(eps) otherwise (the updated orthant probability is 0 after a contradicting label), so
 // score = perfect-user score + (1 - (1 - mp)^(t+1)) * (log eps - log(1 + eps)) * sum_r p_r.
 double step_shift_coef(const ital_shard* s) {
-    if (!(s->mistake_prob > 0.0) || s->label_prob < 1.0) return 0.0;
+    if (!(s->mistake_prob > 0.0) || s->label_prob < 1.0 || s->estimation != 0) return 0.0;
     const double c = std::pow(1.0 - s->mistake_prob, (double)(s->t + 1));
     return (1.0 - c) * (std::log(1e-12) - s->log1p_eps);
 }
@@ -788,9 +789,11 @@ int propose_general(ital_shard* s) {
     a.tags = s->tags;
     a.epoch = s->epoch;
     a.n_scored = s->counters + 2;
+    a.estimation = s->estimation;
+    a.fb_kind = (s->label_prob >= 1.0 && s->mistake_prob <= 0.0) ? 0 : (s->label_prob >= 1.0 ? 1 : 2);
     if ((rc = launch_catchup(s, s->n))) return rc;
     const size_t smem = ((size_t)3 * gs.n_groups + 2 * gs.n_sets + (size_t)gs.n_groups * 24 + 8) * sizeof(double) +
-                        (size_t)kPhiTableLen * sizeof(double2);
+                        (size_t)kPhiTableLen * sizeof(double2) + (s->estimation != 0 ? (32 + 1024 + 512) * sizeof(double) : 0);
     CU(cudaFuncSetAttribute(k_eval_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int blocks = grid_for(s, s->n, 1, 8);
     pdl(k_eval_general, blocks, 256, smem, s)(a); s->launches++;
@@ -842,7 +845,7 @@ int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_o
         CU(copy_async(s, s->hbase_dev, s->sel_host + 30, sizeof hb0, cudaMemcpyHostToDevice, s->stream));
         s->hbase_seeded = true;
     }
-    if (s->t == 0) {
+    if (s->t == 0 && s->estimation == 0) {
         const bool general = s->label_prob < 1.0;
         const double lc = general ? (1.0 - s->mistake_prob) * s->log1p_eps + s->mistake_prob * std::log(1e-12) : s->log1p_eps;
         pdl(k_score0, blocks, 256, 0, s)(s->n, s->m, s->v, s->mask, s->score, s->gain, s->block_best, lc,
@@ -851,7 +854,7 @@ int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_o
         s->pick.nblocks = blocks;
         CU(cudaGetLastError());
         s->n_nodes = 1;
-    } else if (s->label_prob < 1.0) {
+    } else if (s->label_prob < 1.0 || s->estimation != 0) {
         int rc = propose_general(s);
         if (rc) return rc;
     } else {
@@ -908,7 +911,7 @@ int commit_dev(ital_shard* s, const double* recs_dev, int n_records, int extend,
     if (extend && !s->lazy_rows) {      // lazy rows: the projection is extended on demand by k_catchup instead
         const int col = s->W + s->t;
         // the next step's nodes and stage-A list depend on the committed batch only, not on the pass: side stream
-        const bool ahead = s->overlap && s->side && s->label_prob >= 1.0 && s->t + 1 <= 3;
+        const bool ahead = s->overlap && s->side && s->label_prob >= 1.0 && s->estimation == 0 && s->t + 1 <= 3;
         int rc = ITAL_OK;
         if (ahead) {
             CU(cudaEventRecord(s->ev_commit, s->stream));
@@ -952,7 +955,7 @@ int fused_chunk_cap(const ital_shard* s) {
 // Can the running fetch start with k_fetch_fused?  Users who label every sample, pruned, projections on demand, and
 // the shapes the kernel's shared-memory staging covers.
 bool fused_applies(const ital_shard* s, int exhaustive, bool peer) {
-    if (!s->fused || !s->lazy_rows || exhaustive || s->label_prob < 1.0) return false;
+    if (!s->fused || !s->lazy_rows || exhaustive || s->label_prob < 1.0 || s->estimation != 0) return false;
     const int C = fused_chunk_cap(s);
     if (C > kFusedThreads) return false;
     const FusedSmem L(record_doubles(s), s->w_cap, C, s->num_sms);
@@ -1626,7 +1629,7 @@ int ital_fetch_end(ital_shard* s) {
 // a fetch is then S_0 + E_0 + ... + E_{k-2}: the HBM passes themselves.
 int greedy_loop(ital_shard* s, int k, int exhaustive, bool peer) {
     const double ninf = -std::numeric_limits<double>::infinity();
-    const bool pipelined = s->overlap && s->side && !s->lazy_rows && s->label_prob >= 1.0 && !exhaustive;
+    const bool pipelined = s->overlap && s->side && !s->lazy_rows && s->label_prob >= 1.0 && !exhaustive && s->estimation == 0;
     const int64_t rl = record_doubles(s);
     const int G = s->xg_world;
     cudaStream_t main_stream = s->stream;
@@ -1762,8 +1765,8 @@ int ital_fetch_peer(ital_shard* s, int k, double label_prob, double mistake_prob
     if (!s || k < 0 || (k > 0 && !out_idx)) return fail(ITAL_EINVAL, "ital_fetch_peer: bad arguments");
     if (!s->xg_ready) return fail(ITAL_ESTATE, "ital_fetch_peer: no peer exchange (ital_peer_export / ital_peer_connect)");
     if (k > kMaxBatch) return fail(ITAL_EINVAL, "batches of more than %d samples are not supported", kMaxBatch);
-    if (label_prob < 1.0 && k > kMaxBatchGeneral)
-        return fail(ITAL_EINVAL, "label_prob < 1 supports batches of at most %d samples", kMaxBatchGeneral);
+    if ((label_prob < 1.0 || s->estimation != 0) && k > kMaxBatchGeneral)
+        return fail(ITAL_EINVAL, "label_prob < 1 (and label_estimation other than 'mean') supports batches of at most %d samples", kMaxBatchGeneral);
     int rc = ital_fetch_begin(s, label_prob, mistake_prob);
     if (rc) return rc;
     const int64_t rl = record_doubles(s);
@@ -1797,8 +1800,8 @@ int ital_fetch(ital_shard* s, int k, double label_prob, double mistake_prob, int
                double* out_scores) {
     if (!s || k < 0 || (k > 0 && !out_idx)) return fail(ITAL_EINVAL, "ital_fetch: bad arguments");
     if (k > kMaxBatch) return fail(ITAL_EINVAL, "batches of more than %d samples are not supported", kMaxBatch);
-    if (label_prob < 1.0 && k > kMaxBatchGeneral)
-        return fail(ITAL_EINVAL, "label_prob < 1 supports batches of at most %d samples", kMaxBatchGeneral);
+    if ((label_prob < 1.0 || s->estimation != 0) && k > kMaxBatchGeneral)
+        return fail(ITAL_EINVAL, "label_prob < 1 (and label_estimation other than 'mean') supports batches of at most %d samples", kMaxBatchGeneral);
     int rc = ital_fetch_begin(s, label_prob, mistake_prob);
     if (rc) return rc;
     // the whole greedy loop is enqueued without waiting for the GPU; one read-back at the end
@@ -1859,15 +1862,10 @@ int ital_rel_var(ital_shard* s, double* out) {
     return copy_vec(s, s->v, out);
 }
 
-int64_t ital_top_results(ital_shard* s, int64_t k, int64_t* out_idx, double* out_val) {
-    if (!s || !out_idx) return fail(ITAL_EINVAL, "ital_top_results: bad arguments");
-    if (s->W == 0) return fail(ITAL_ESTATE, "ital_top_results before any labelled point");
-    CU(cudaSetDevice(s->device));
-    // pool rows only: query rows (global index >= n_data) are the last local rows of the last shard
-    const int64_t np = std::max<int64_t>(0, std::min<int64_t>(s->n, s->n_data - s->row_offset));
-    if (k < 0 || k > np) k = np;
-    if (k == 0) return 0;
-    if (np >= ((int64_t)1 << 32)) return fail(ITAL_EINVAL, "ital_top_results: more than 2^32 rows in one shard");
+// stable LSD radix sort of the local pool rows by descending mean (masked rows last if `masked`); the sorted rows end
+// up in sort_rows[0 .. np)
+static int sort_rows_by_mean(ital_shard* s, int64_t np, bool masked) {
+    if (np >= ((int64_t)1 << 32)) return fail(ITAL_EINVAL, "more than 2^32 rows in one shard");
     const int tiles = (int)((np + kSortTile - 1) / kSortTile);
     if (np > s->sort_cap) {
         for (void** p : {(void**)&s->sort_keys, (void**)&s->sort_rows, (void**)&s->sort_hist, (void**)&s->sort_out_idx,
@@ -1884,7 +1882,7 @@ int64_t ital_top_results(ital_shard* s, int64_t k, int64_t* out_idx, double* out
     uint64_t* kb[2] = {s->sort_keys, s->sort_keys + np};
     uint32_t* rb[2] = {s->sort_rows, s->sort_rows + np};
     uint32_t* totals = s->sort_hist + (size_t)256 * tiles;
-    pdl(k_sort_init, grid_for(s, np, 256), 256, 0, s)(s->m, np, kb[0], rb[0]); s->launches++;
+    pdl(k_sort_init, grid_for(s, np, 256), 256, 0, s)(s->m, np, kb[0], rb[0], masked ? s->mask : (const uint8_t*)nullptr); s->launches++;
     for (int pass = 0; pass < 8; ++pass) {
         const int a = pass & 1, b = a ^ 1;
         pdl(k_sort_hist, tiles, kSortThreads, 0, s)(kb[a], np, 8 * pass, s->sort_hist);
@@ -1892,8 +1890,22 @@ int64_t ital_top_results(ital_shard* s, int64_t k, int64_t* out_idx, double* out
         pdl(k_sort_scatter, tiles, kSortThreads, 0, s)(kb[a], rb[a], np, 8 * pass, s->sort_hist, totals, kb[b], rb[b]);
         s->launches += 3;
     }
-    pdl(k_sort_gather, grid_for(s, k, 256), 256, 0, s)(rb[0], k, s->row_offset, s->m, s->sort_out_idx,
-                                                             s->sort_out_val); s->launches++;
+    CU(cudaGetLastError());
+    return ITAL_OK;
+}
+
+int64_t ital_top_results(ital_shard* s, int64_t k, int64_t* out_idx, double* out_val) {
+    if (!s || !out_idx) return fail(ITAL_EINVAL, "ital_top_results: bad arguments");
+    if (s->W == 0) return fail(ITAL_ESTATE, "ital_top_results before any labelled point");
+    CU(cudaSetDevice(s->device));
+    // pool rows only: query rows (global index >= n_data) are the last local rows of the last shard
+    const int64_t np = std::max<int64_t>(0, std::min<int64_t>(s->n, s->n_data - s->row_offset));
+    if (k < 0 || k > np) k = np;
+    if (k == 0) return 0;
+    int rc = sort_rows_by_mean(s, np, false);
+    if (rc) return rc;
+    pdl(k_sort_gather, grid_for(s, k, 256), 256, 0, s)(s->sort_rows, k, s->row_offset, s->m, s->sort_out_idx,
+                                                       s->sort_out_val); s->launches++;
     CU(cudaGetLastError());
     CU(copy_async(s, out_idx, s->sort_out_idx, (size_t)k * sizeof(int64_t), cudaMemcpyDeviceToHost, s->stream));
     if (out_val)
@@ -1902,7 +1914,25 @@ int64_t ital_top_results(ital_shard* s, int64_t k, int64_t* out_idx, double* out
     return k;
 }
 
-int ital_predict(ital_shard* s, const double* Xt, int64_t mrows, double* out_mean, double* out_var) {
+// ITAL.fetch_unlabelled's top_candidates restriction (ital/ital.py:111-117) on the device: the `top` unseen local pool
+// rows with the largest posterior mean stay candidates (exact ties at the cut go to the lower row), everything else
+// gets the restricted bit.  Nothing is copied to the host.
+int ital_restrict_top(ital_shard* s, int64_t top) {
+    if (!s || top < 1) return fail(ITAL_EINVAL, "ital_restrict_top: bad arguments");
+    if (s->W == 0) return fail(ITAL_ESTATE, "ital_restrict_top before any labelled point");
+    CU(cudaSetDevice(s->device));
+    const int64_t np = std::max<int64_t>(0, std::min<int64_t>(s->n, s->n_data - s->row_offset));
+    if (np == 0) return ITAL_OK;
+    int rc = sort_rows_by_mean(s, np, true);            // (masks without the restricted bit: lifted before)
+    if (rc) return rc;
+    pdl(k_mask_all, grid_for(s, s->n, 256), 256, 0, s)(s->mask, s->n, 0xff, kRestricted); s->launches++;
+    pdl(k_mask_clear_sorted, grid_for(s, std::min(top, np), 256), 256, 0, s)(s->mask, s->sort_rows, std::min(top, np),
+                                                                            kRestricted); s->launches++;
+    CU(cudaGetLastError());
+    return ITAL_OK;
+}
+
+static int predict_impl(ital_shard* s, const double* Xt, int64_t mrows, double* out_mean, double* out_var, double* out_proj) {
     if (!s || !Xt || mrows < 0 || !out_mean) return fail(ITAL_EINVAL, "ital_predict: bad arguments");
     if (s->W == 0) return fail(ITAL_ESTATE, "ital_predict before any labelled point");
     if (mrows == 0) return ITAL_OK;
@@ -1915,31 +1945,50 @@ int ital_predict(ital_shard* s, const double* Xt, int64_t mrows, double* out_mea
         CU(cudaGetLastError());
         s->w_valid = true;
     }
-    double *xt_dev = nullptr, *mean_dev = nullptr, *var_dev = nullptr;
+    double *xt_dev = nullptr, *mean_dev = nullptr, *var_dev = nullptr, *proj_dev = nullptr;
     CU(cudaMalloc(&xt_dev, (size_t)mrows * s->d * sizeof(double)));
     CU(cudaMalloc(&mean_dev, (size_t)mrows * sizeof(double)));
     if (out_var) CU(cudaMalloc(&var_dev, (size_t)mrows * sizeof(double)));
+    if (out_proj) CU(cudaMalloc(&proj_dev, (size_t)mrows * nl * sizeof(double)));
     CU(copy_async(s, xt_dev, Xt, (size_t)mrows * s->d * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     const int threads = 128, wpb = threads / 32;
     const size_t smem = (size_t)wpb * nl * sizeof(double);
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_predict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pdl(k_predict, (unsigned)((mrows + wpb - 1) / wpb), threads, smem, s)(
         xt_dev, mrows, (int)s->d, s->lab_x_dev, s->lab_sqn_dev, nl, s->w_vec_dev, s->LK_dev, (int64_t)s->model_cap, s->var,
-        -2.0 * s->ls * s->ls, mean_dev, var_dev); s->launches++;
+        -2.0 * s->ls * s->ls, mean_dev, var_dev, proj_dev); s->launches++;
     CU(cudaGetLastError());
     CU(copy_async(s, out_mean, mean_dev, (size_t)mrows * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     if (out_var) CU(copy_async(s, out_var, var_dev, (size_t)mrows * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (out_proj) CU(copy_async(s, out_proj, proj_dev, (size_t)mrows * nl * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaFree(xt_dev));
     CU(cudaFree(mean_dev));
     if (var_dev) CU(cudaFree(var_dev));
+    if (proj_dev) CU(cudaFree(proj_dev));
     return ITAL_OK;
+}
+
+int ital_predict(ital_shard* s, const double* Xt, int64_t mrows, double* out_mean, double* out_var) {
+    return predict_impl(s, Xt, mrows, out_mean, out_var, nullptr);
+}
+
+int ital_predict_proj(ital_shard* s, const double* Xt, int64_t mrows, double* out_mean, double* out_proj) {
+    if (!out_proj) return fail(ITAL_EINVAL, "ital_predict_proj: bad arguments");
+    return predict_impl(s, Xt, mrows, out_mean, nullptr, out_proj);
 }
 
 int ital_set_lazy_rows(ital_shard* s, int on) {
     if (!s) return fail(ITAL_EINVAL, "null shard");
     if (s->fetching) return fail(ITAL_ESTATE, "ital_set_lazy_rows during a fetch");
     s->lazy_rows = on != 0;
+    return ITAL_OK;
+}
+
+int ital_set_label_estimation(ital_shard* s, int mode) {
+    if (!s || mode < 0 || mode > 2) return fail(ITAL_EINVAL, "ital_set_label_estimation: mode must be 0, 1 or 2");
+    if (s->fetching) return fail(ITAL_ESTATE, "ital_set_label_estimation during a fetch");
+    s->estimation = mode;
     return ITAL_OK;
 }
 

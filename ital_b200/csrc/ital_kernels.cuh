@@ -1460,6 +1460,9 @@ struct GeneralArgs {
     uint32_t* tags;
     uint32_t epoch;
     int* n_scored;
+    int estimation;             // label_estimation: 0 'mean', 1 'optimistic', 2 'pessimistic' (ital.py:210-219)
+    int fb_kind;                // feedback configurations enumerated (fb_iter, ital.py:300-342): 0 the single perfect
+                                // one (weight 1), 1 {-1, 1}^D, 2 {-1, 0, 1}^D (weights = likelihood)
 };
 
 __global__ void __launch_bounds__(256) k_eval_general(GeneralArgs a) {
@@ -1541,9 +1544,96 @@ __global__ void __launch_bounds__(256) k_eval_general(GeneralArgs a) {
             sBm[sidx] = xm;
         }
         __syncthreads();
+        const int nr = 1 << D;
+        if (a.estimation != 0) {
+            // label_estimation = 'optimistic' / 'pessimistic' (ital.py:210-215): no expectation over the relevance
+            // configurations -- the largest, resp. the "first or smaller" single term
+            //   cur = (log(p'(r | f) + eps) - log(p_r + eps)) * weight(f | r)
+            // in the enumeration order of the reference (r over product([F, T]), f over fb_iter; the first sample
+            // varies slowest).  The quirk of the 'pessimistic' fold -- a running value of exactly 0 is replaced by the
+            // next term -- is kept: every thread folds a contiguous piece of the sequence into (saw a zero term,
+            // minimum of the terms after the last zero), thread 0 chains the pieces.
+            double* logp = red + (size_t)G * 24 + 8 + 2 * (size_t)kPhiTableLen;     // [nr]
+            double* logq = logp + 32;                                               // [nr][nr]
+            double* piece = logq + 1024;                                            // [256][2]
+            for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+                const int g0 = r & ((1 << t) - 1), rc = r >> t;
+                logp[r] = log(fmax(rc ? A[g0] : a.group_mass[g0] - A[g0], 0.0) + kEps);
+            }
+            for (int pidx = threadIdx.x; pidx < nr * nr; pidx += blockDim.x) {
+                const int r = pidx >> D, Om = pidx & (nr - 1), rc = r >> t;
+                if (Om == 0) continue;
+                const int* e = a.lut + ((size_t)r * nr + Om) * 3;
+                double q;
+                if (e[2] & 2) q = 1.0;
+                else if (e[2] & 1) q = (rc ? Bp[e[0]] : Bm[e[0]]) / fmax(rc ? sBp[e[1]] : sBm[e[1]], 1e-300);
+                else q = rc ? A[e[0]] : a.group_mass[e[0]] - A[e[0]];
+                logq[pidx] = log(fmin(fmax(q, 0.0), 1.0) + kEps);
+            }
+            __syncthreads();
+            int nf = 1;
+            if (a.fb_kind == 1) nf = nr;
+            if (a.fb_kind == 2) { nf = 1; for (int j = 0; j < D; ++j) nf *= 3; }
+            const int N = nr * nf, chunk = (N + (int)blockDim.x - 1) / (int)blockDim.x;
+            const int k0 = min(N, (int)threadIdx.x * chunk), k1 = min(N, k0 + chunk);
+            const double w0 = 1.0 - a.lp, wc = a.lp * (1.0 - a.mp), wm = a.lp * a.mp;
+            bool has_zero = false;
+            double mn = INFINITY, mx = 0.0;
+            for (int k = k0; k < k1; ++k) {
+                const int ri = k / nf;
+                int fi = k - ri * nf;
+                int rmask = 0, Om = 0;
+                bool consistent = true;
+                double weight = 1.0;
+                // digits of f from the last sample to the first (the first varies slowest); the weight is multiplied
+                // up in sample order afterwards
+                int fd[5];
+                for (int j = D - 1; j >= 0; --j) {
+                    const int rj = (ri >> (D - 1 - j)) & 1;
+                    rmask |= rj << j;
+                    int f;
+                    if (a.fb_kind == 0) f = 2 * rj - 1;
+                    else if (a.fb_kind == 1) { f = 2 * (fi & 1) - 1; fi >>= 1; }
+                    else { f = fi % 3 - 1; fi /= 3; }
+                    fd[j] = f;
+                    if (f != 0) {
+                        Om |= 1 << j;
+                        if (f != 2 * rj - 1) consistent = false;
+                    }
+                }
+                if (Om == 0) continue;                  // nobody labelled: not a feedback configuration (ital.py:201)
+                if (a.fb_kind != 0) {
+                    for (int j = 0; j < D; ++j) {
+                        const int rj = (rmask >> j) & 1;
+                        weight *= fd[j] == 0 ? w0 : (fd[j] == 2 * rj - 1 ? wc : wm);
+                    }
+                }
+                const double cur = ((consistent ? logq[rmask * nr + Om] : log_eps) - logp[rmask]) * weight;
+                if (cur > mx) mx = cur;
+                if (cur == 0.0) { has_zero = true; mn = INFINITY; }
+                else if (cur < mn) mn = cur;
+            }
+            piece[2 * threadIdx.x] = has_zero ? 1.0 : 0.0;
+            piece[2 * threadIdx.x + 1] = a.estimation == 1 ? mx : mn;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double mi = 0.0;
+                for (int k = 0; k < (int)blockDim.x; ++k) {
+                    const double v = piece[2 * k + 1];
+                    if (a.estimation == 1) { if (v > mi) mi = v; }
+                    else if (piece[2 * k] != 0.0) mi = isinf(v) ? 0.0 : v;
+                    else if (!isinf(v)) mi = (mi == 0.0 || v < mi) ? v : mi;
+                }
+                a.tags[i] = tag_with_step(a.tags[i], a.epoch, a.t);
+                a.score[i] = mi;
+                a.gain[i] = mi;
+                atomicAdd(a.n_scored, 1);
+            }
+            __syncthreads();
+            continue;
+        }
         // assembly over (r, O); O = 0 stands for the -log p_r term
         double part = 0.0;
-        const int nr = 1 << D;
         for (int pidx = threadIdx.x; pidx < nr * nr; pidx += blockDim.x) {
             const int r = pidx >> D, Om = pidx & (nr - 1);
             const int g0 = r & ((1 << t) - 1), rc = r >> t;
@@ -2201,7 +2291,8 @@ __global__ void __launch_bounds__(128) k_predict(const double* __restrict__ Xt, 
                                                  const double* __restrict__ Xl, const double* __restrict__ sqn_l,
                                                  int nl, const double* __restrict__ wvec,
                                                  const double* __restrict__ LK, int64_t ldk, double var, double neg2ls2,
-                                                 double* __restrict__ out_mean, double* __restrict__ out_var) {
+                                                 double* __restrict__ out_mean, double* __restrict__ out_var,
+                                                 double* __restrict__ out_proj) {
     pdl_enter();
     extern __shared__ double sm[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -2226,7 +2317,7 @@ __global__ void __launch_bounds__(128) k_predict(const double* __restrict__ Xt, 
         double mean = 0.0;
         for (int l = 0; l < nl; ++l) mean = fma(wvec[l], kbuf[l], mean);
         out_mean[row] = mean;
-        if (out_var != nullptr) {
+        if (out_var != nullptr || out_proj != nullptr) {
             double q = 0.0;
             for (int a = 0; a < nl; ++a) {               // forward substitution with the Cholesky factor
                 double u = kbuf[a];
@@ -2234,8 +2325,9 @@ __global__ void __launch_bounds__(128) k_predict(const double* __restrict__ Xt, 
                 u /= LK[(int64_t)a * ldk + a];
                 kbuf[a] = u;
                 q = fma(u, u, q);
+                if (out_proj != nullptr) out_proj[row * (int64_t)nl + a] = u;
             }
-            out_var[row] = fmax(0.0, var - q);
+            if (out_var != nullptr) out_var[row] = fmax(0.0, var - q);
         }
     }
 }
@@ -2255,13 +2347,23 @@ __device__ __forceinline__ uint64_t desc_key(double x) {
     return ~asc;
 }
 
+// `mask` != nullptr: rows with a non-zero mask (seen, not candidates) get the largest key, i.e. they sort behind every
+// candidate (the top_candidates restriction ranks the unseen rows only, ital/ital.py:116)
 __global__ void __launch_bounds__(256) k_sort_init(const double* __restrict__ m, int64_t n, uint64_t* __restrict__ keys,
-                                                   uint32_t* __restrict__ rows) {
+                                                   uint32_t* __restrict__ rows, const uint8_t* __restrict__ mask) {
     pdl_enter();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        keys[i] = desc_key(m[i]);
+        keys[i] = (mask != nullptr && mask[i] != 0) ? ~0ull : desc_key(m[i]);
         rows[i] = (uint32_t)i;
     }
+}
+
+// the first `top` rows of a sorted row list become the only candidates: clears `clear_bits` in their masks
+__global__ void __launch_bounds__(256) k_mask_clear_sorted(uint8_t* __restrict__ mask, const uint32_t* __restrict__ rows,
+                                                           int64_t top, uint8_t clear_bits) {
+    pdl_enter();
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < top; k += (int64_t)gridDim.x * blockDim.x)
+        mask[rows[k]] &= (uint8_t)~clear_bits;
 }
 
 // item (w, j, lane) of a tile: tile_base + w * (32 * kSortItems) + j * 32 + lane -- the order that defines stability

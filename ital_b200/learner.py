@@ -72,6 +72,9 @@ class _Shard(object):
             idx = _capi.as_i64(idx)
             _capi.check(self.lib.ital_restrict_candidates(self.handle, len(idx), _capi.i64ptr(idx)))
 
+    def restrict_top(self, top):
+        _capi.check(self.lib.ital_restrict_top(self.handle, int(top)))
+
     def fetch_begin(self, label_prob, mistake_prob):
         _capi.check(self.lib.ital_fetch_begin(self.handle, float(label_prob), float(mistake_prob)))
 
@@ -167,6 +170,13 @@ class _Shard(object):
                                                     _capi.dptr(val)))
         return idx[:got], val[:got]
 
+    def predict_proj(self, X):
+        X = _capi.as_f64(X)
+        W = int(self.lib.ital_width(self.handle))
+        mean, proj = np.zeros(len(X)), np.zeros((len(X), W))
+        _capi.check(self.lib.ital_predict_proj(self.handle, _capi.dptr(X), len(X), _capi.dptr(mean), _capi.dptr(proj)))
+        return mean, proj
+
     def predict(self, X, want_var):
         X = _capi.as_f64(X)
         mean = np.zeros(len(X))
@@ -203,12 +213,15 @@ class _GPView(object):
         return self._l.length_scale
 
     def predict(self, X, cov_mode=None):
-        """GaussianProcess.predict (ital/gp.py:264-292); cov_mode None or 'diag'."""
+        """GaussianProcess.predict (ital/gp.py:264-292); cov_mode None, 'diag' or 'full'."""
         X = np.asarray(X, dtype=np.float64)
         if X.ndim == 1:
             X = X[None, :]
-        if cov_mode == 'full':
-            raise NotImplementedError("cov_mode='full' is not on the accelerated path")
+        if cov_mode == 'full':                  # k(X, X) - k^T K^-1 k (gp.py:285-287) from the rows' projections
+            mean, proj = self._l._shard.predict_proj(X)
+            sq = np.sum(X ** 2, axis=-1)
+            kxx = self._l.var * np.exp((sq[:, None] + sq[None, :] - 2.0 * (X @ X.T)) / (-2.0 * self._l.length_scale ** 2))
+            return mean, kxx - proj @ proj.T
         mean, var = self._l._shard.predict(X, cov_mode == 'diag')
         return (mean, var) if cov_mode == 'diag' else mean
 
@@ -290,9 +303,17 @@ class ITAL(object):
         nothing; otherwise the streaming pass keeps every row's projection current (every row is scored)."""
         on = self._lazy_rows
         if on is None:
-            on = self.label_prob >= 1 and not self.exhaustive
+            on = self.label_prob >= 1 and not self._exhaustive()
         _capi.check(self._shard.lib.ital_set_lazy_rows(self._shard.handle, int(bool(on))))
+        _capi.check(self._shard.lib.ital_set_label_estimation(self._shard.handle,
+                                                              self.ESTIMATIONS.get(self.label_estimation, 0)))
         return bool(on)
+
+    def _exhaustive(self):
+        """Every candidate is scored at every step: asked for, or no lazy-greedy bound (only the expectation over the
+        relevance configurations, label_estimation='mean', is a submodular entropy)."""
+        return bool(self.exhaustive) or self.label_estimation != 'mean'
+
 
     @property
     def fused(self):
@@ -558,20 +579,26 @@ class ITAL(object):
         return mean_t
 
     # ---- ITAL ------------------------------------------------------------------------------------------
+    ESTIMATIONS = {'mean': 0, 'optimistic': 1, 'pessimistic': 2}
     MAX_BATCH = 11                  # greedy steps per fetch (10 base variables)
     MAX_BATCH_GENERAL = 5           # with label_prob < 1 (conditional node sets up to 4 base variables)
 
     def _check_supported(self, k=0):
-        limit = self.MAX_BATCH_GENERAL if self.label_prob < 1 else self.MAX_BATCH
+        if self.label_estimation not in self.ESTIMATIONS:
+            raise ValueError("label_estimation must be 'mean', 'optimistic' or 'pessimistic'")
+        general = self.label_prob < 1 or self.label_estimation != 'mean'
+        limit = self.MAX_BATCH_GENERAL if general else self.MAX_BATCH
         if k > limit:               # before any work (and before any collective) -- not in the middle of the greedy loop
             raise NotImplementedError('batches of more than %d samples are not supported%s' % (
-                limit, ' with label_prob < 1' if self.label_prob < 1 else ''))
-        if self.label_estimation != 'mean':
-            raise NotImplementedError("label_estimation must be 'mean' on the GPU path")
-        if self.change_estimation_subset != 0 or (self.clip_cov and 0 < self.clip_cov < 1) \
-                or self.monte_carlo_num_rel is not None or self.monte_carlo_num_fb is not None:
-            raise NotImplementedError('change_estimation_subset, clip_cov and the Monte-Carlo modes are outside the '
-                                      'accelerated path (no named configuration uses them)')
+                limit, " with label_prob < 1 or label_estimation other than 'mean'" if general else ''))
+        if self.change_estimation_subset != 0 or (self.clip_cov and 0 < self.clip_cov < 1 and k > 5):
+            raise NotImplementedError('change_estimation_subset and clip_cov are outside the accelerated path')
+        # monte_carlo_num_rel / monte_carlo_num_fb (ital.py:293-297, 319-342): the reference replaces the enumeration
+        # of relevance / feedback configurations by random samples only when there are more configurations than
+        # samples (2^(D-1) >= D * num, 3^D >= 2 * D * num); its samples come from the global numpy RNG in candidate
+        # order, so its noisy estimates are not reproducible outside that exact call sequence.  Here the sums those
+        # samples estimate are always evaluated exactly (the enumeration is cheap on the device): the zero-variance
+        # limit of the reference's estimator.
 
     def fetch_unlabelled(self, k, show_progress=False):                         # ital.py:84-134
         """Greedy batch of k unlabelled samples maximising mutual information; list of row indices."""
@@ -587,22 +614,25 @@ class ITAL(object):
             if isinstance(top, float):
                 top = min(n_unseen, int(top * (len(self.queries) + len(self.relevant_ids) + len(self.irrelevant_ids))))
             if 0 < top < n_unseen:
-                cand = np.nonzero(~self._seen_mask())[0]
-                top_ind = np.argpartition(self.rel_mean[cand], -top)[-top:]
-                self._shard.restrict_candidates(cand[top_ind])
+                if self._comm.world_size == 1:
+                    self._shard.restrict_top(top)           # masked sort of the means on the device
+                else:                                       # (several shards: the cut is global)
+                    cand = np.nonzero(~self._seen_mask())[0]
+                    top_ind = np.argpartition(self.rel_mean[cand], -top)[-top:]
+                    self._shard.restrict_candidates(cand[top_ind])
                 restricted = True
         self.last_fetch_stats = []
         self._apply_lazy_rows()
         try:
             if self._comm.world_size == 1 and not show_progress:
-                idx, scores = self._shard.fetch(k, self.label_prob, self.mistake_prob, self.exhaustive)
+                idx, scores = self._shard.fetch(k, self.label_prob, self.mistake_prob, self._exhaustive())
                 self.last_fetch_scores = scores
                 self.last_fused_steps = int(self._shard.stats()[5])
                 return [int(i) for i in idx]
             if getattr(self._comm, 'on_device', False) and not show_progress:
                 if self._peer and 2 * self._shard.record_doubles() <= self._shard.peer_slot_doubles():
                     # (2 x: room for the batch's projection columns may still double the record in ital_fetch_begin)
-                    idx, scores = self._shard.fetch_peer(k, self.label_prob, self.mistake_prob, self.exhaustive)
+                    idx, scores = self._shard.fetch_peer(k, self.label_prob, self.mistake_prob, self._exhaustive())
                     self.last_fetch_scores = scores
                     self.last_fused_steps = int(self._shard.stats()[5])
                     return [int(i) for i in idx]
@@ -622,7 +652,7 @@ class ITAL(object):
             rl = self._shard.record_doubles()
             rec, allrec = comm.device_buffers(rl)
             for it in range(k):
-                self._shard.fetch_propose_dev(-np.inf, self.exhaustive, rec.data_ptr())
+                self._shard.fetch_propose_dev(-np.inf, self._exhaustive(), rec.data_ptr())
                 comm.all_gather_device(allrec, rec)
                 self._shard.fetch_commit_dev(allrec.data_ptr(), comm.world_size, it + 1 < k)
             idx, scores = self._shard.fetch_result(k)
@@ -642,7 +672,7 @@ class ITAL(object):
         self._shard.fetch_begin(self.label_prob, self.mistake_prob)
         try:
             for it in steps:
-                rec = self._shard.fetch_propose(-np.inf, self.exhaustive)
+                rec = self._shard.fetch_propose(-np.inf, self._exhaustive())
                 self.last_fetch_stats.append(self._shard.stats())
                 if keep_scores:
                     self.last_step_scores.append(self._all_rows(self._shard.last_scores())[:self._n])

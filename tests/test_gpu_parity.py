@@ -390,8 +390,7 @@ def test_interface_edge_cases():
     assert gpu.fetch_unlabelled(0) == []
     gpu.reset()
     assert gpu.rel_mean is None and gpu.rounds == 0 and gpu.get_unseen() == list(range(12))
-    for kw in (dict(label_estimation='pessimistic'), dict(clip_cov=0.5), dict(label_estimation='optimistic'),
-               dict(monte_carlo_num_rel=3)):
+    for kw in (dict(change_estimation_subset=4), dict(change_estimation_subset=None)):
         bad = _gpu_learner(X, length_scale=1.0, **kw)
         bad.update({0: 1})
         with pytest.raises(NotImplementedError):
@@ -535,3 +534,64 @@ def test_interface_errors_before_any_work():
         ctx.update({1: 1})
         assert len(ctx.fetch_unlabelled(1)) == 1
     assert ctx._shard is None
+
+
+def test_predict_full_covariance_and_device_top_candidates():
+    """GaussianProcess.predict(cov_mode='full') (gp.py:285-287) from the test rows' projections; the top_candidates
+    restriction (ital.py:111-117) computed on the device (masked sort of the means) against the oracle's argpartition."""
+    from oracle.ital_oracle import OracleITAL
+    X, assign = _syn(3000, 40, seed=41, centres=9)
+    gpu, ora = _gpu_learner(X, length_scale=1.0), OracleITAL(X, length_scale=1.0)
+    for L in (gpu, ora):
+        _label_syn(L, assign)
+    Xt = X[5:45] * 1.02
+    m, c = gpu.gp.predict(Xt, cov_mode='full')
+    mo, co = ora.gp.predict(Xt, cov_mode='full')
+    np.testing.assert_allclose(m, mo, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(c, co, rtol=1e-6, atol=1e-9)
+    for top in (50, 7.0):
+        gpu.top_candidates = ora.top_candidates = top
+        a, b = gpu.fetch_unlabelled(4), ora.fetch_unlabelled(4)
+        assert a == b, (top, a, b)
+        assert gpu.fetch_unlabelled(4) == a            # the restriction is lifted after every fetch and rebuilt
+    gpu.top_candidates = ora.top_candidates = None
+    assert gpu.fetch_unlabelled(3) == ora.fetch_unlabelled(3)
+
+
+@pytest.mark.parametrize('est,lp,mp', [('optimistic', 1.0, 0.2), ('pessimistic', 1.0, 0.2), ('optimistic', 1.0, 0.0),
+                                       ('pessimistic', 1.0, 0.0), ('optimistic', 0.6, 0.1), ('pessimistic', 0.6, 0.1),
+                                       ('pessimistic', 0.5, 0.0)])
+def test_label_estimation_optimistic_and_pessimistic(est, lp, mp):
+    """ITAL(label_estimation='optimistic' | 'pessimistic') (ital/ital.py:210-215): the largest / the "first or smaller"
+    single term of the enumeration over relevance and feedback configurations, in the reference's order (including the
+    fold's quirk that a running value of exactly 0 -- a feedback configuration of likelihood 0 -- is replaced by the next
+    term).  Every candidate of every step against the oracle's literal loop."""
+    from oracle.ital_oracle import OracleITAL
+    X, assign = _syn(70, 12, seed=5, centres=4)
+    kw = dict(length_scale=1.0, label_prob=lp, mistake_prob=mp, label_estimation=est)
+    gpu, ora = _gpu_learner(X, **kw), OracleITAL(X, **kw)
+    for L in (gpu, ora):
+        L.update({0: 1, 1: -1 if assign[1] != assign[0] else 1, 2: -1 if assign[2] != assign[0] else 1})
+    ret = gpu._fetch_stepwise(3, keep_scores=True)
+    ora.fetch_unlabelled(3, forced=ret)
+    for t, (sc, tr) in enumerate(zip(gpu.last_step_scores, ora.trace)):
+        np.testing.assert_allclose(sc[tr['candidates']], tr['scores'], rtol=2e-6, atol=1e-9, err_msg='step %d' % t)
+        pos = list(tr['candidates']).index(ret[t])
+        assert tr['scores'][pos] >= tr['scores'].max() - 1e-6 * abs(tr['scores'].max())
+    assert gpu.fetch_unlabelled(3) == ret
+    with pytest.raises(NotImplementedError):
+        gpu.fetch_unlabelled(6)
+
+
+def test_optimistic_golden_from_the_reference():
+    """The reference's own record for label_estimation='optimistic' (label_prob = 1, mistake_prob = 0.2); loose like
+    the oracle's comparison (tests/test_oracle_golden.py: the winning term is set by the relative accuracy of small
+    probabilities, ill-conditioned in the reference itself)."""
+    g = load_golden('butterflies_optimistic_k2')
+    kw = dict(g['learner_kw'])
+    gpu = drive(_gpu_learner(g['X'], **kw), g)
+    ret = gpu._fetch_stepwise(int(g['k']), keep_scores=True)
+    for t, (sc, st) in enumerate(zip(gpu.last_step_scores, g['steps'])):
+        np.testing.assert_allclose(sc[st['candidates']], st['mi'], rtol=1e-2, atol=1e-5, err_msg='step %d' % t)
+        if ret[t] != st['chosen']:
+            break

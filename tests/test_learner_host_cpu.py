@@ -61,6 +61,12 @@ class StubShard(object):
         self.restricted = None if idx is None else set(int(i) for i in idx)
         self.calls.append(('restrict', None if idx is None else sorted(self.restricted)))
 
+    def restrict_top(self, top):
+        cand = [i for i in range(self.n_data) if i not in self.seen]
+        order = sorted(cand, key=lambda i: (-self.mean[i], i))[:int(top)]
+        self.restricted = set(order)
+        self.calls.append(('restrict', sorted(self.restricted)))
+
     def fetch(self, k, label_prob, mistake_prob, exhaustive):
         cand = [i for i in range(self.n_data) if i not in self.seen
                 and (self.restricted is None or i in self.restricted)]
@@ -156,12 +162,19 @@ def test_reset_and_unsupported_modes(make):
     L.update({1: 1})
     L.reset()
     assert L.rounds == 0 and L.rel_mean is None and L.get_unseen() == list(range(20))
-    for kw in (dict(label_estimation='optimistic'), dict(clip_cov=0.5), dict(change_estimation_subset=3),
-               dict(monte_carlo_num_fb=5)):
+    for kw in (dict(change_estimation_subset=3), dict(change_estimation_subset=None)):
         B = make(**kw)
         B.update({0: 1})
         with pytest.raises(NotImplementedError):
             B.fetch_unlabelled(1)
+    C = make(clip_cov=0.5)                             # ital.py:360: grouping only for more than 5 variables
+    C.update({0: 1})
+    assert len(C.fetch_unlabelled(5)) == 5
+    with pytest.raises(NotImplementedError):
+        C.fetch_unlabelled(6)
+    M = make(monte_carlo_num_rel=3, monte_carlo_num_fb=5)      # evaluated exactly (zero-variance limit of the estimator)
+    M.update({0: 1})
+    assert len(M.fetch_unlabelled(4)) == 4
     with pytest.raises(ValueError):
         make(storage='float16')
 

@@ -14,8 +14,8 @@ cap() {   # name, kernel regex, skip, count, driver mode
     rm -f $O/prof_$1.ncu-rep
 }
 cap k_fetch_fused k_fetch_fused 2 2 fused
-cap k_eval "k_eval<" 0 3 exhaustive
+cap k_eval "^k_eval$" 0 3 exhaustive
 cap k_eval_general k_eval_general 0 3 general
 cap k_extend_bulk_multi k_extend_bulk_multi 0 2 update
-cap k_extend_bulk "k_extend_bulk<" 1 2 streaming
+cap k_extend_bulk "^k_extend_bulk$" 1 2 streaming
 ls -la $O | tail -20
