@@ -792,8 +792,8 @@ int propose_general(ital_shard* s) {
     a.estimation = s->estimation;
     a.fb_kind = (s->label_prob >= 1.0 && s->mistake_prob <= 0.0) ? 0 : (s->label_prob >= 1.0 ? 1 : 2);
     if ((rc = launch_catchup(s, s->n))) return rc;
-    const size_t smem = ((size_t)3 * gs.n_groups + 2 * gs.n_sets + (size_t)gs.n_groups * 24 + 8) * sizeof(double) +
-                        (size_t)kPhiTableLen * sizeof(double2) + (s->estimation != 0 ? (32 + 1024 + 512) * sizeof(double) : 0);
+    const size_t smem = ((((size_t)3 * gs.n_groups + 2 * gs.n_sets + 1) & ~(size_t)1) + (size_t)gs.n_groups * 24 + 8) * sizeof(double) +
+                        (size_t)kPhiTableLen * sizeof(double2) + (s->estimation != 0 ? (32 + 1024 + 7776) * sizeof(double) : 0);      // logp, logq, the 2^5 * 3^5 terms
     CU(cudaFuncSetAttribute(k_eval_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int blocks = grid_for(s, s->n, 1, 8);
     pdl(k_eval_general, blocks, 256, smem, s)(a); s->launches++;

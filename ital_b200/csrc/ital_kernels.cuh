@@ -1474,7 +1474,7 @@ __global__ void __launch_bounds__(256) k_eval_general(GeneralArgs a) {
     double* Bm = Bp + G;                // [G]
     double* sBp = Bm + G;               // [NS]
     double* sBm = sBp + NS;             // [NS]
-    double* red = sBm + NS;             // [G][8][3] per-warp partials, later [8] for the final sum
+    double* red = gsm + ((3 * G + 2 * NS + 1) & ~1);    // [G][8][3] per-warp partials, later [8] (16-byte aligned: the table follows)
     double2* phi_s = reinterpret_cast<double2*>(red + (size_t)G * 24 + 8);      // table of phi_tab
     phi_tab_to_shared(phi_s, a.phi);
     __syncthreads();
@@ -1550,12 +1550,11 @@ __global__ void __launch_bounds__(256) k_eval_general(GeneralArgs a) {
             // configurations -- the largest, resp. the "first or smaller" single term
             //   cur = (log(p'(r | f) + eps) - log(p_r + eps)) * weight(f | r)
             // in the enumeration order of the reference (r over product([F, T]), f over fb_iter; the first sample
-            // varies slowest).  The quirk of the 'pessimistic' fold -- a running value of exactly 0 is replaced by the
-            // next term -- is kept: every thread folds a contiguous piece of the sequence into (saw a zero term,
-            // minimum of the terms after the last zero), thread 0 chains the pieces.
+            // varies slowest).  The terms are formed in parallel and folded in order by one thread, so that the quirk
+            // of the 'pessimistic' fold -- a running value of exactly 0 is replaced by the next term -- is kept.
             double* logp = red + (size_t)G * 24 + 8 + 2 * (size_t)kPhiTableLen;     // [nr]
             double* logq = logp + 32;                                               // [nr][nr]
-            double* piece = logq + 1024;                                            // [256][2]
+            double* piece = logq + 1024;                                            // [2^D * |feedback configurations|]
             for (int r = threadIdx.x; r < nr; r += blockDim.x) {
                 const int g0 = r & ((1 << t) - 1), rc = r >> t;
                 logp[r] = log(fmax(rc ? A[g0] : a.group_mass[g0] - A[g0], 0.0) + kEps);
@@ -1574,12 +1573,9 @@ __global__ void __launch_bounds__(256) k_eval_general(GeneralArgs a) {
             int nf = 1;
             if (a.fb_kind == 1) nf = nr;
             if (a.fb_kind == 2) { nf = 1; for (int j = 0; j < D; ++j) nf *= 3; }
-            const int N = nr * nf, chunk = (N + (int)blockDim.x - 1) / (int)blockDim.x;
-            const int k0 = min(N, (int)threadIdx.x * chunk), k1 = min(N, k0 + chunk);
+            const int N = nr * nf;
             const double w0 = 1.0 - a.lp, wc = a.lp * (1.0 - a.mp), wm = a.lp * a.mp;
-            bool has_zero = false;
-            double mn = INFINITY, mx = 0.0;
-            for (int k = k0; k < k1; ++k) {
+            for (int k = threadIdx.x; k < N; k += blockDim.x) {     // every term of the sequence, in parallel
                 const int ri = k / nf;
                 int fi = k - ri * nf;
                 int rmask = 0, Om = 0;
@@ -1601,28 +1597,25 @@ __global__ void __launch_bounds__(256) k_eval_general(GeneralArgs a) {
                         if (f != 2 * rj - 1) consistent = false;
                     }
                 }
-                if (Om == 0) continue;                  // nobody labelled: not a feedback configuration (ital.py:201)
                 if (a.fb_kind != 0) {
                     for (int j = 0; j < D; ++j) {
                         const int rj = (rmask >> j) & 1;
                         weight *= fd[j] == 0 ? w0 : (fd[j] == 2 * rj - 1 ? wc : wm);
                     }
                 }
-                const double cur = ((consistent ? logq[rmask * nr + Om] : log_eps) - logp[rmask]) * weight;
-                if (cur > mx) mx = cur;
-                if (cur == 0.0) { has_zero = true; mn = INFINITY; }
-                else if (cur < mn) mn = cur;
+                // nobody labelled: not a feedback configuration (ital.py:201) -- marked NaN and skipped by the fold
+                piece[k] = Om == 0 ? nan("") : ((consistent ? logq[rmask * nr + Om] : log_eps) - logp[rmask]) * weight;
             }
-            piece[2 * threadIdx.x] = has_zero ? 1.0 : 0.0;
-            piece[2 * threadIdx.x + 1] = a.estimation == 1 ? mx : mn;
             __syncthreads();
             if (threadIdx.x == 0) {
+                // the fold of ital.py:210-215, literally and in order: 'optimistic' keeps the largest term (from 0),
+                // 'pessimistic' replaces a running value of exactly 0 by the next term and otherwise keeps the smaller
                 double mi = 0.0;
-                for (int k = 0; k < (int)blockDim.x; ++k) {
-                    const double v = piece[2 * k + 1];
-                    if (a.estimation == 1) { if (v > mi) mi = v; }
-                    else if (piece[2 * k] != 0.0) mi = isinf(v) ? 0.0 : v;
-                    else if (!isinf(v)) mi = (mi == 0.0 || v < mi) ? v : mi;
+                for (int k = 0; k < N; ++k) {
+                    const double c = piece[k];
+                    if (c != c) continue;
+                    if (a.estimation == 1) { if (c > mi) mi = c; }
+                    else if (mi == 0.0 || c < mi) mi = c;
                 }
                 a.tags[i] = tag_with_step(a.tags[i], a.epoch, a.t);
                 a.score[i] = mi;
