@@ -392,7 +392,7 @@ def main():
     stats = None
     if world == 1:
         learner._fetch_stepwise(args.batch)
-        stats = [[float(x) for x in s[:5]] for s in learner.last_fetch_stats]
+        stats = [[float(x) for x in s[:7]] for s in learner.last_fetch_stats]
 
     # ---- correctness carried by the line ---------------------------------------------------------------------------
     checks = {}
@@ -452,6 +452,19 @@ def main():
                   'every candidate scored by quadrature at every greedy step (no lazy-greedy bound): the like-for-like '
                   'count against the CPU arms; one streaming pass per step keeps all projections current')
         checks['exhaustive_same_batch'] = eret == ret
+        if stats is not None:
+            # FP64-pipe roofline of the scorer (the MI arithmetic is the secondary, compute bound): node
+            # evaluations per second x FP64-pipe instructions per node (25, counted in the SASS of k_eval<3>:
+            # 3 DFMA for the argument, 1 DMUL, ~20 for the table-based normal CDF, 1 DFMA accumulate) against the DFMA
+            # issue rate measured on this GPU (tools/probe/dmma_bench.cu: 0.55 cycles per warp instruction and SM)
+            node_evals = sum((n_total - n_lab - t) * pad for t, pad in enumerate([0] + [s[6] for s in stats[1:]]))
+            clk = (clocks or {}).get('sm_mhz') or 1965.0
+            peak_fp64 = 148 * 32 / 0.55 * clk * 1e6
+            ach = node_evals * 25 * args.exhaustive_steps / edev
+            exh['fp64_roofline'] = {'bound': 'fp64 pipe', 'node_evaluations_per_fetch': node_evals,
+                                    'fp64_instructions_per_node': 25, 'achieved': ach, 'peak': peak_fp64,
+                                    'unit': 'FP64 lane-instructions/s', 'frac': ach / peak_fp64,
+                                    'ncu': 'profiles/r02_k_eval_full.txt: sm__pipe_fp64_cycles_active 51 %, issue slots 49 %, XU 16 %'}
         e_ach = (enb / 1e9) / (ems / 1e3) if ems > 0 else 0.0
         e_traffic, e_src = ncu_traffic('r*_k_extend_bulk_full.txt')
         roof_consumed = {'bound': 'hbm',

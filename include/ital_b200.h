@@ -184,7 +184,8 @@ int ital_set_bulk_stream(ital_shard* s, int on);
 
 /* Per-step diagnostics of the last propose: [0] candidates considered, [1] candidates scored exactly,
  * [2] quadrature nodes, [3] H(base), [4] flagged (conditional variance < 100 * noise), [5] greedy steps the fused
- * kernel ran in the last ital_fetch / ital_fetch_peer, [6..7] reserved. */
+ * kernel ran in the last ital_fetch / ital_fetch_peer, [6] quadrature nodes kept (device-generated rules drop the
+ * nodes lighter than 1e-13), [7] reserved. */
 int ital_fetch_stats(const ital_shard* s, double* out8);
 
 /* Scores of the last propose for all local rows (NaN where not scored this step). */

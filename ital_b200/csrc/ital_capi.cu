@@ -1532,6 +1532,7 @@ static int read_step_stats(ital_shard* s, int step) {
     s->stats[2] = s->step_nodes[step];
     s->stats[4] = (double)c[1];
     s->stats[5] = (double)s->fused_steps_last;
+    s->stats[6] = step == 0 ? 1.0 : (double)c[3];      // nodes kept (t <= 3: after the light ones are dropped)
     return ITAL_OK;
 }
 
