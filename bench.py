@@ -343,6 +343,7 @@ def main():
     ap.add_argument('--secondary-steps', type=int, default=30, help='timed fetches of the streaming / multi-kernel rows')
     ap.add_argument('--rounds', type=int, default=8, help='full fetch+update rounds timed at the end (8 rounds of 4: |L| = 41)')
     ap.add_argument('--model-steps', type=int, default=20, help='timed fetches with mistake_prob = 0.5')
+    ap.add_argument('--batch10-steps', type=int, default=1, help='timed fetches of a batch of 10')
     ap.add_argument('--general-steps', type=int, default=1, help='timed fetches with label_prob = 0.25 (slow: every candidate scored)')
     ap.add_argument('--no-strong', action='store_true', help='skip the strong-scaling sub-run at N > 1')
     args = ap.parse_args()
@@ -488,6 +489,17 @@ def main():
                                          'label_prob=1, mistake_prob=0.5: perfect-user scores + a per-step constant (same '
                                          'argmax), persistent kernel')
         learner.mistake_prob = 0.0
+    if args.batch10_steps > 0:
+        r10 = candidates_ranked(n_total, n_lab, 10)
+        H.timed(1, batch=10, flush=False)
+        bdev, bwall, bret = H.timed(args.batch10_steps, batch=10)
+        models['batch_10'] = {'value': r10 * args.batch10_steps / bdev, 'unit': UNIT, 'ms_per_step': bdev / args.batch10_steps * 1e3,
+                              'e2e_ms_per_step': bwall / args.batch10_steps * 1e3, 'steps': args.batch10_steps,
+                              'batch': [int(i) for i in bret], 'first_four_match': [int(i) for i in bret[:4]] == [int(i) for i in ret],
+                              'note': 'fetch_unlabelled(10) (BASELINE.json config 5): the persistent kernel runs the first four '
+                                      'steps; steps 5-10 use host-generated nodes (tensor rule with 81k / 400k nodes for 4 / 5 '
+                                      'base variables, sequential-conditioning lattice with 2^18 nodes from 6 on) and the '
+                                      'multi-kernel loop -- the time is dominated by generating and uploading those nodes'}
     if args.general_steps > 0:
         learner.label_prob = 0.25                       # configs/butterflies-conservative.conf: every candidate is scored
         gdev, gwall, gret = H.timed(args.general_steps, batch=min(args.batch, 4), flush=False)

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(LIB_DIR, 'libital_b200.so')
 SOURCES = ['ital_capi.cu']
 DEPENDS = ['ital_capi.cu', 'ital_kernels.cuh', 'ital_fused.cuh', 'snq_host.h', os.path.join('..', '..', 'include', 'ital_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '-Xcompiler', '-fPIC', '-shared']
+              '-Xcompiler', '-fPIC', '-Xcompiler', '-pthread', '-shared']
 
 
 def _nvcc():

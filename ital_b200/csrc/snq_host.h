@@ -8,11 +8,32 @@
 //   [-R, c] and [c, R]; the 2q Gauss-Legendre nodes of the dimension are shared out between the two panels in
 //   proportion to their widths (at least SNQ_QMIN each); weights carry the standard normal density.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <thread>
 #include <vector>
 
 namespace snq {
+
+// Host node generation for long batches is millions of independent nodes: spread index ranges over the host cores.
+template <typename F>
+inline void parallel_for(int64_t n, int64_t grain, F&& body) {
+    const int64_t max_threads = std::max<int64_t>(1, std::min<int64_t>(std::thread::hardware_concurrency(), 32));
+    const int64_t threads = std::max<int64_t>(1, std::min<int64_t>(max_threads, n / std::max<int64_t>(1, grain)));
+    if (threads <= 1) {
+        body((int64_t)0, n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    const int64_t per = (n + threads - 1) / threads;
+    for (int64_t th = 0; th < threads; ++th) {
+        const int64_t lo = th * per, hi = std::min(n, lo + per);
+        if (lo >= hi) break;
+        pool.emplace_back([&body, lo, hi]() { body(lo, hi); });
+    }
+    for (auto& th : pool) th.join();
+}
 
 constexpr double kR = 7.0;
 constexpr int kQMin = 2;
@@ -135,7 +156,6 @@ inline Nodes generate_sc(int t, const double* m, const double* L) {
     auto cdf = [](double x) { return 0.5 * std::erfc(-x * 0.70710678118654752440); };
     // nodes of orthant b: eta (dimension-major, stride N) and weights; returns the mass
     auto gen = [&](int b, int64_t N, double* eta, int64_t stride, double* w) {
-        double mass = 0.0;
         std::vector<double> e(t);
         for (int64_t k = 0; k < N; ++k) {
             double wk = 1.0 / (double)N;
@@ -159,24 +179,29 @@ inline Nodes generate_sc(int t, const double* m, const double* L) {
                 }
                 if (eta) eta[(size_t)j * stride + k] = e[j];
             }
-            if (w) w[k] = wk;
-            mass += wk;
+            w[k] = wk;
         }
-        return mass;
     };
+    // (orthants are independent: the pilot pass and the final pass run over the host cores, one orthant at a time per
+    // thread; masses are summed per orthant in node order, so the result does not depend on the thread count)
     std::vector<double> P(nb);
+    parallel_for(nb, 1, [&](int64_t b_lo, int64_t b_hi) {
+        std::vector<double> wp(kScPilot);
+        for (int64_t b = b_lo; b < b_hi; ++b) {
+            gen((int)b, kScPilot, nullptr, 0, wp.data());
+            double s = 0.0;
+            for (int k = 0; k < kScPilot; ++k) s += wp[k];
+            P[b] = s;
+        }
+    });
     double total = 0.0;
+    for (int b = 0; b < nb; ++b) total += P[b];
+    std::vector<int64_t> cnt(nb, 0), start(nb + 1, 0);
     for (int b = 0; b < nb; ++b) {
-        P[b] = gen(b, kScPilot, nullptr, 0, nullptr);
-        total += P[b];
+        if (P[b] >= kScPMin) cnt[b] = std::max<int64_t>(kScMin, (int64_t)std::floor((double)kScN * P[b] / total + 0.5));
+        start[b + 1] = start[b] + cnt[b];
     }
-    std::vector<int64_t> cnt(nb, 0);
-    int64_t n = 0;
-    for (int b = 0; b < nb; ++b) {
-        if (P[b] < kScPMin) continue;
-        cnt[b] = std::max<int64_t>(kScMin, (int64_t)std::floor((double)kScN * P[b] / total + 0.5));
-        n += cnt[b];
-    }
+    const int64_t n = start[nb];
     Nodes out;
     out.t = t;
     out.n = n;
@@ -185,21 +210,20 @@ inline Nodes generate_sc(int t, const double* m, const double* L) {
     out.orth.assign(n, 0);
     out.group_begin.assign(nb + 1, 0);
     out.masses.assign(nb, 0.0);
-    int64_t pos = 0;
-    for (int b = 0; b < nb; ++b) {
-        out.group_begin[b] = (int32_t)pos;
-        if (cnt[b] > 0) {
-            gen(b, cnt[b], out.eta.data() + pos, n, out.w.data() + pos);
+    for (int b = 0; b <= nb; ++b) out.group_begin[b] = (int32_t)start[b];
+    parallel_for(nb, 1, [&](int64_t b_lo, int64_t b_hi) {
+        for (int64_t b = b_lo; b < b_hi; ++b) {
+            if (cnt[b] == 0) continue;
+            const int64_t pos = start[b];
+            gen((int)b, cnt[b], out.eta.data() + pos, n, out.w.data() + pos);
             double s = 0.0;
             for (int64_t k = 0; k < cnt[b]; ++k) {
                 s += out.w[pos + k];
-                out.orth[pos + k] = b;
+                out.orth[pos + k] = (int32_t)b;
             }
             out.masses[b] = s;
-            pos += cnt[b];
         }
-    }
-    out.group_begin[nb] = (int32_t)pos;
+    });
     // the orthant masses must add up to one: scaling the weights accordingly removes the error all node sets share
     double tot = 0.0;
     for (int b = 0; b < nb; ++b) tot += out.masses[b];
@@ -227,7 +251,8 @@ inline Nodes generate(int t, const double* m, const double* L, int q = 0, double
         const int64_t n_new = n * two_q;
         std::vector<double> eta_new((size_t)(j + 1) * n_new), w_new(n_new);
         std::vector<int32_t> orth_new(n_new);
-        for (int64_t k = 0; k < n; ++k) {
+        parallel_for(n, 4096, [&](int64_t k_lo, int64_t k_hi) {
+        for (int64_t k = k_lo; k < k_hi; ++k) {
             double acc = m[j];
             for (int i = 0; i < j; ++i) acc += eta[(size_t)i * n + k] * L[j * t + i];
             const double a = -acc / L[j * t + j];
@@ -256,6 +281,7 @@ inline Nodes generate(int t, const double* m, const double* L, int q = 0, double
                 orth_new[kk] = orth[k] | (bit << j);
             }
         }
+        });
         eta.swap(eta_new);
         w.swap(w_new);
         orth.swap(orth_new);
