@@ -126,6 +126,17 @@ int ital_fetch_commit(ital_shard* s, const double* record);
  * with use_correlations does not exclude unnameable rows (baseline_methods.py:133): first_pick_takes_unnameable != 0
  * mirrors that. */
 int ital_variance_propose(ital_shard* s, int use_correlations, int first_pick_takes_unnameable, double* record);
+/* ITAL(change_estimation_subset = c > 0) (ital/ital.py:102-108, AppendedMutualInformation.__call__ ital.py:514-527,
+ * MutualInformation._call_iter_sub ital.py:227-275): the change of the model output is estimated on a random subset S
+ * of the unseen samples kept at the signs of its means, while the relevance of the batch and the candidate is
+ * integrated over.  Protocol (the host draws S with the reference's own np.random.choice call): ital_set_sub_mode(1),
+ * lazy rows off; per evaluation ital_fetch_begin, ital_fetch_commit of the records of ext = [the n_batch samples picked
+ * so far, then the members of S outside the batch] (every commit is one streaming pass, so each row holds its
+ * projection on ext), then ital_fetch_propose_sub writes the record of the best local candidate outside ext -- or of
+ * the single row only_row >= 0 (a member of S is scored with itself moved out of the subset) -- then ital_fetch_end.
+ * Users who label every sample without mistakes, label_estimation 'mean', at most 7 batch samples and 11 columns. */
+int ital_set_sub_mode(ital_shard* s, int on);
+int ital_fetch_propose_sub(ital_shard* s, int n_batch, int64_t only_row, double* record);
 int ital_fetch_end(ital_shard* s);
 int ital_fetch(ital_shard* s, int k, double label_prob, double mistake_prob, int exhaustive,
                int64_t* out_idx, double* out_scores);
@@ -241,6 +252,13 @@ int64_t ital_h_table(double* out, int64_t max_out);
  * step from the nearest grid point (phi_tab in csrc/ital_kernels.cuh).  Copies up to max_out doubles, returns the
  * length (4354). */
 int64_t ital_phi_table(double* out, int64_t max_out);
+/* Node sets and conditional moments of ital_fetch_propose_sub (change_estimation_subset; csrc/snq_host.h
+ * generate_sub) for ext = [n_batch batch samples, n_cols - n_batch subset members] with means m[n_cols] and row-major
+ * Cholesky factor L[n_cols^2].  sizes[4] = {n_nodes, n_groups = 2 * 2^n_batch, s* (sign bits of the subset's means),
+ * doubles in `tables`}; call with eta == NULL to get the sizes only.  eta[n_cols * n_nodes] dimension-major,
+ * w[n_nodes], group_begin[n_groups + 1]; tables = mass[2 G] | mu[G D] | Sig[D D] | mU[G u] | CU[u u] | BS[u D]. */
+int ital_snq_sub(int n_batch, int n_cols, const double* m, const double* L, double noise, int64_t* sizes, double* eta,
+                 double* w, int32_t* group_begin, double* tables);
 /* Conditional node sets of the general feedback model (label_prob < 1; csrc/snq_host.h generate_general).
  * sizes[4] = {n_nodes, n_groups, n_sets, lut entries}; call with eta == NULL to get the sizes only.  eta[t*n_nodes]
  * dimension-major, w[n_nodes], group_begin[n_groups+1], group_mass[n_groups], set_group0[n_sets+1],

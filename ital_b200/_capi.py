@@ -42,6 +42,8 @@ SIGNATURES = {
     'ital_fetch_propose': (ctypes.c_int, [_shard_p, ctypes.c_double, ctypes.c_int, _c_double_p]),
     'ital_fetch_commit': (ctypes.c_int, [_shard_p, _c_double_p]),
     'ital_variance_propose': (ctypes.c_int, [_shard_p, ctypes.c_int, ctypes.c_int, _c_double_p]),
+    'ital_set_sub_mode': (ctypes.c_int, [_shard_p, ctypes.c_int]),
+    'ital_fetch_propose_sub': (ctypes.c_int, [_shard_p, ctypes.c_int, ctypes.c_int64, _c_double_p]),
     'ital_fetch_end': (ctypes.c_int, [_shard_p]),
     'ital_fetch': (ctypes.c_int, [_shard_p, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                   _c_int64_p, _c_double_p]),
@@ -72,6 +74,8 @@ SIGNATURES = {
     'ital_snq_order': (ctypes.c_int, [ctypes.c_int]),
     'ital_h_table': (ctypes.c_int64, [_c_double_p, ctypes.c_int64]),
     'ital_phi_table': (ctypes.c_int64, [_c_double_p, ctypes.c_int64]),
+    'ital_snq_sub': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _c_double_p, _c_double_p, ctypes.c_double, _c_int64_p,
+                                    _c_double_p, _c_double_p, _c_int32_p, _c_double_p]),
     'ital_snq_general': (ctypes.c_int, [ctypes.c_int, _c_double_p, _c_double_p, ctypes.c_double, _c_int64_p,
                                         _c_double_p, _c_double_p, _c_int32_p, _c_double_p, _c_int32_p, _c_int32_p]),
 }

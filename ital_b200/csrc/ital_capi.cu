@@ -146,6 +146,11 @@ struct ital_shard {
     double *g_eta = nullptr, *g_w = nullptr, *g_mass = nullptr;
     int *g_begin = nullptr, *g_set0 = nullptr, *g_lut = nullptr;
     size_t g_cap_nodes = 0, g_cap_groups = 0, g_cap_sets = 0, g_cap_lut = 0;
+    // change_estimation_subset: node sets of ital_fetch_propose_sub
+    double *sb_eta = nullptr, *sb_w = nullptr, *sb_small = nullptr;
+    int* sb_begin = nullptr;
+    size_t sb_cap_eta = 0, sb_cap_w = 0, sb_cap_small = 0, sb_cap_begin = 0;
+    bool sub_mode = false;           // the batch columns hold ext = [batch, subset]: no look-ahead for a next greedy step
 
     int w_cap = 0;                   // allocated projection columns
     int W = 0;                       // labelled points in the model
@@ -806,6 +811,112 @@ int propose_general(ital_shard* s) {
     return ITAL_OK;
 }
 
+// change_estimation_subset: score the local candidates against ext = the D batch columns of the running fetch, the
+// first tB of which are the samples picked so far (k_eval_sub, snq::generate_sub).  only_local >= 0: that row alone.
+int propose_sub(ital_shard* s, int tB, int64_t only_local, bool any_local) {
+    const int D = s->t;
+    std::vector<double> bm(16), bL(16 * 16);
+    CU(copy_async(s, bm.data(), s->base_m_dev, 16 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(copy_async(s, bL.data(), s->base_L_dev, 256 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    std::vector<double> Lb((size_t)D * D, 0.0);
+    for (int a = 0; a < D; ++a)
+        for (int b = 0; b <= a; ++b) Lb[(size_t)a * D + b] = bL[(size_t)a * kBaseStride + b];
+    snq::SubSets ss = snq::generate_sub(tB, D, bm.data(), Lb.data(), s->noise);
+    const int G = 1 << tB;
+    auto grow = [&](void** p, size_t* cap, size_t need, size_t esize) -> int {
+        if (need <= *cap) return ITAL_OK;
+        CU(cudaStreamSynchronize(s->stream));
+        if (*p) CU(cudaFree(*p));
+        *p = nullptr;
+        CU(cudaMalloc(p, need * esize));
+        *cap = need;
+        return ITAL_OK;
+    };
+    int rc;
+    // small tables in one buffer: mass [2G] | mu [G D] | Sig [D D] | mU [G u] | CU [u u] | BS [u D]
+    const int u = D - tB;
+    if (u > kSubMaxU) return fail(ITAL_EINVAL, "change_estimation_subset: at most %d subset members outside the batch", kSubMaxU);
+    std::vector<double> small_tab;
+    small_tab.insert(small_tab.end(), ss.mass.begin(), ss.mass.end());
+    small_tab.insert(small_tab.end(), ss.mu.begin(), ss.mu.end());
+    small_tab.insert(small_tab.end(), ss.Sig.begin(), ss.Sig.end());
+    const size_t off_mU = small_tab.size();
+    small_tab.insert(small_tab.end(), ss.mU.begin(), ss.mU.end());
+    const size_t off_CU = small_tab.size();
+    small_tab.insert(small_tab.end(), ss.CU.begin(), ss.CU.end());
+    const size_t off_BS = small_tab.size();
+    small_tab.insert(small_tab.end(), ss.BS.begin(), ss.BS.end());
+    small_tab.push_back(0.0);
+    if ((rc = grow((void**)&s->sb_eta, &s->sb_cap_eta, ss.eta.size() + 1, sizeof(double)))) return rc;
+    if ((rc = grow((void**)&s->sb_w, &s->sb_cap_w, ss.w.size() + 1, sizeof(double)))) return rc;
+    if ((rc = grow((void**)&s->sb_small, &s->sb_cap_small, small_tab.size(), sizeof(double)))) return rc;
+    if ((rc = grow((void**)&s->sb_begin, &s->sb_cap_begin, ss.group_begin.size(), sizeof(int)))) return rc;
+    CU(copy_async(s, s->sb_eta, ss.eta.data(), ss.eta.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, s->sb_w, ss.w.data(), ss.w.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, s->sb_small, small_tab.data(), small_tab.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, s->sb_begin, ss.group_begin.data(), ss.group_begin.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));       // ss lives in pageable host memory
+    s->n_nodes = ss.n_nodes;
+    CU(cudaMemsetAsync(s->counters, 0, 4 * sizeof(int), s->stream));
+    if (only_local >= 0 || !any_local) {
+        // a single row (if this shard owns it and it is a candidate), or nothing at all on this shard
+        const int one[2] = {(int)only_local, 0};
+        memcpy(s->sel_host + 30, one, sizeof one);      // (pinned scratch at the tail of the selection mirror)
+        if (only_local >= 0) {
+            CU(copy_async(s, s->worklist, s->sel_host + 30, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+            pdl(k_worklist_one, 1, 32, 0, s)(s->mask, s->worklist, s->counters); s->launches++;
+        }
+    } else {
+        pdl(k_worklist, grid_for(s, s->n, 256), 256, 0, s)(s->n, s->mask, s->gain, s->thr_dev, 1, s->counters, s->worklist); s->launches++;
+    }
+    SubArgs a;
+    a.count = s->counters;
+    a.list = s->worklist;
+    a.m = s->m;
+    a.v = s->v;
+    a.U = s->U;
+    a.ldu = s->ldu;
+    a.W0 = s->W;
+    a.tB = tB;
+    a.D = D;
+    a.eta = s->sb_eta;
+    a.w = s->sb_w;
+    a.n_nodes = ss.n_nodes;
+    a.group_begin = s->sb_begin;
+    a.mass = s->sb_small;
+    a.mu = s->sb_small + 2 * G;
+    a.Sig = s->sb_small + 2 * G + (size_t)G * D;
+    a.mU = s->sb_small + off_mU;
+    a.CU = s->sb_small + off_CU;
+    a.BS = s->sb_small + off_BS;
+    a.sub_bits = ss.sub_bits;
+    a.q_last = u >= 2 ? snq::order_for(u - 1) : 1;
+    a.R = snq::kR;
+    a.q_min = snq::kQMin;
+    a.gl_x = s->gl_dev;
+    a.gl_w = s->gl_dev + (snq::kMaxOrder + 1) * 64;
+    a.noise = s->noise;
+    a.phi = s->phi_dev;
+    a.score = s->score;
+    a.gain = s->gain;
+    a.tags = s->tags;
+    a.epoch = s->epoch;
+    a.n_scored = s->counters + 2;
+    const size_t smem = (size_t)((4 * G + 16 + 5 * kBaseStride + 1) & ~1) * sizeof(double) + (size_t)kPhiTableLen * sizeof(double2);
+    CU(cudaFuncSetAttribute(k_eval_sub, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int blocks = only_local >= 0 ? 1 : grid_for(s, s->n, 1, 8);
+    pdl(k_eval_sub, blocks, 256, smem, s)(a); s->launches++;
+    const int lb = std::min(kArgmaxBlocks, grid_for(s, s->n, 256));
+    pdl(k_argmax_list, lb, 256, 0, s)(s->counters, s->worklist, s->score, s->block_best, nullptr, 0.0, 0.0, nullptr, nullptr); s->launches++;
+    s->pick = PickSrc();
+    s->pick.block_best = s->block_best;
+    s->pick.nblocks = lb;
+    CU(cudaGetLastError());
+    s->step_nodes[std::min(s->t, 15)] = (double)ss.n_nodes;
+    return make_record(s, -1, s->rec_dev, false, s->pick);
+}
+
 // Stage A of a greedy step (t >= 1, perfect user, pruned): the bound argmax over 2 x #SM strided subsets, the exact
 // scores of those rows, and from the best of them the threshold and the worklist of stage B.  None of it needs the
 // streaming pass of the previous step except the new projection column of the ~300 stage-A rows themselves, which
@@ -911,7 +1022,7 @@ int commit_dev(ital_shard* s, const double* recs_dev, int n_records, int extend,
     if (extend && !s->lazy_rows) {      // lazy rows: the projection is extended on demand by k_catchup instead
         const int col = s->W + s->t;
         // the next step's nodes and stage-A list depend on the committed batch only, not on the pass: side stream
-        const bool ahead = s->overlap && s->side && s->label_prob >= 1.0 && s->estimation == 0 && s->t + 1 <= 3;
+        const bool ahead = s->overlap && s->side && s->label_prob >= 1.0 && s->estimation == 0 && s->t + 1 <= 3 && !s->sub_mode;
         int rc = ITAL_OK;
         if (ahead) {
             CU(cudaEventRecord(s->ev_commit, s->stream));
@@ -1081,7 +1192,7 @@ void free_all(ital_shard* s) {
     void* ptrs[] = {s->X, s->sqn, s->m, s->v, s->U, s->gain, s->score, s->mask, s->worklist, s->counters,
                     s->block_best, s->best, s->thr_dev, s->rec_dev, s->rec_in_dev, s->idx_dev, s->eta_dev,
                     s->w_dev, s->masses_dev, s->group_dev, s->orth_dev, s->eta_raw, s->w_raw, s->orth_raw, s->gl_dev, s->phi_dev, s->htab_dev, s->base_m_dev, s->base_L_dev, s->sel_dev,
-                    s->hbase_dev, s->tags, s->f_best, s->f_cnt, s->f_stage, s->f_mass, s->f_bar, s->f_trace, s->rec_hist, s->mext_dev, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev, s->beta_dev, s->upd_idx_dev, s->upd_y_dev,
+                    s->hbase_dev, s->tags, s->f_best, s->f_cnt, s->f_stage, s->f_mass, s->f_bar, s->f_trace, s->rec_hist, s->mext_dev, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->sb_eta, s->sb_w, s->sb_small, s->sb_begin, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev, s->beta_dev, s->upd_idx_dev, s->upd_y_dev,
                     s->sort_keys, s->sort_rows, s->sort_hist, s->sort_out_idx, s->sort_out_val};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -1576,6 +1687,41 @@ int ital_variance_propose(ital_shard* s, int use_correlations, int first_pick_ta
     CU(copy_async(s, s->rec_host, s->rec_dev, (size_t)rl * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     memcpy(record, s->rec_host, (size_t)rl * sizeof(double));
+    return ITAL_OK;
+}
+
+int ital_set_sub_mode(ital_shard* s, int on) {
+    if (!s) return fail(ITAL_EINVAL, "null shard");
+    if (s->fetching) return fail(ITAL_ESTATE, "ital_set_sub_mode during a fetch");
+    s->sub_mode = on != 0;
+    return ITAL_OK;
+}
+
+int ital_fetch_propose_sub(ital_shard* s, int n_batch, int64_t only_row, double* record) {
+    if (!s || !record) return fail(ITAL_EINVAL, "ital_fetch_propose_sub: bad arguments");
+    if (!s->fetching || !s->sub_mode) return fail(ITAL_ESTATE, "ital_fetch_propose_sub outside a fetch in subset mode");
+    if (s->lazy_rows) return fail(ITAL_ESTATE, "ital_fetch_propose_sub needs the streaming pass (lazy rows off)");
+    if (!(s->label_prob >= 1.0 && s->mistake_prob <= 0.0) || s->estimation != 0)
+        return fail(ITAL_EINVAL, "change_estimation_subset is built for users who label every sample without mistakes and label_estimation 'mean'");
+    if (n_batch < 0 || n_batch > s->t || n_batch > 7 || s->t > kSubMaxCols)
+        return fail(ITAL_EINVAL, "ital_fetch_propose_sub: %d batch samples of %d columns (at most 7 of %d)", n_batch, s->t, kSubMaxCols);
+    CU(cudaSetDevice(s->device));
+    int64_t only_local = -1;
+    bool any_local = true;
+    if (only_row >= 0) {
+        only_local = only_row - s->row_offset;
+        if (only_local < 0 || only_local >= s->n) { only_local = -1; any_local = false; }
+    }
+    const int step = std::min(s->t, 15);
+    int rc = propose_sub(s, n_batch, only_local, any_local);
+    if (rc) return rc;
+    const int64_t rl = record_doubles(s);
+    CU(copy_async(s, s->rec_host, s->rec_dev, (size_t)rl * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(copy_async(s, s->stats_host, s->stats_dev, 16 * 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    memcpy(record, s->rec_host, (size_t)rl * sizeof(double));
+    s->proposals = step + 1;
+    read_step_stats(s, step);
     return ITAL_OK;
 }
 
@@ -2080,6 +2226,35 @@ int64_t ital_h_table(double* out, int64_t max_out) {
     const std::vector<double> tab = build_h_table();
     if (out) memcpy(out, tab.data(), (size_t)std::min<int64_t>(max_out, (int64_t)tab.size()) * sizeof(double));
     return (int64_t)tab.size();
+}
+
+int ital_snq_sub(int n_batch, int n_cols, const double* m, const double* L, double noise, int64_t* sizes, double* eta,
+                 double* w, int32_t* group_begin, double* tables) {
+    if (n_batch < 0 || n_batch > 7 || n_cols < n_batch || n_cols > kSubMaxCols || n_cols - n_batch > kSubMaxU ||
+        !m || !L || !sizes)
+        return fail(ITAL_EINVAL, "ital_snq_sub: bad arguments");
+    snq::SubSets ss = snq::generate_sub(n_batch, n_cols, m, L, noise);
+    const int G = 1 << n_batch, D = n_cols, u = n_cols - n_batch;
+    sizes[0] = ss.n_nodes;
+    sizes[1] = ss.n_groups;
+    sizes[2] = ss.sub_bits;
+    sizes[3] = 2 * G + (int64_t)G * D + D * D + (int64_t)G * u + u * u + u * D;
+    if (!eta) return ITAL_OK;
+    memcpy(eta, ss.eta.data(), ss.eta.size() * sizeof(double));
+    memcpy(w, ss.w.data(), ss.w.size() * sizeof(double));
+    memcpy(group_begin, ss.group_begin.data(), ss.group_begin.size() * sizeof(int32_t));
+    double* p = tables;
+    auto put = [&](const std::vector<double>& v, size_t count) {
+        if (count) memcpy(p, v.data(), count * sizeof(double));
+        p += count;
+    };
+    put(ss.mass, 2 * G);
+    put(ss.mu, (size_t)G * D);
+    put(ss.Sig, (size_t)D * D);
+    put(ss.mU, (size_t)G * u);
+    put(ss.CU, (size_t)u * u);
+    put(ss.BS, (size_t)u * D);
+    return ITAL_OK;
 }
 
 int ital_snq_general(int t, const double* m, const double* L, double noise, int64_t* sizes, double* eta, double* w,

@@ -1193,6 +1193,12 @@ __global__ void __launch_bounds__(256) k_worklist(int64_t n, const uint8_t* __re
     }
 }
 
+// Worklist of ONE given row (already stored in list[0]) if it is a candidate.
+__global__ void k_worklist_one(const uint8_t* __restrict__ mask, const int* __restrict__ list, int* __restrict__ count) {
+    pdl_enter();
+    if (threadIdx.x == 0) count[0] = mask[list[0]] == 0 ? 1 : 0;
+}
+
 // Exact MI of one candidate per team of threads (a warp, or the whole 256-thread block when few candidates are
 // left and latency matters) with the shared nodes of the step (t >= 1 base variables):
 //   P(r_base, +) = sum_{q in orthant r_base} w_q * Phi((m_i + l_i . eta_q) / s_i),  P(r_base, -) = P(r_base) - P(+)
@@ -1710,6 +1716,220 @@ __device__ __forceinline__ void snq_node(int64_t k, int64_t N, int q, double R, 
     }
     wt_out = wt;
     orth_out = ob;
+}
+
+// ---- change_estimation_subset (ital.py:227-275, AppendedMutualInformation.__call__ ital.py:514-527) --------------
+// The batch columns of the running fetch hold ext = [B (tB samples picked so far), S' (the change-estimation subset
+// without the members of B)], D = tB + u columns.  The reference integrates over the relevance of B and the candidate
+// only and keeps the subset at the signs s* of its means:
+//     MI = sum_{r over B + candidate} p_r [ log(P(s*, r | labels of B and the candidate as in r) + eps)
+//                                           - log(P(s*, r) + eps) ],     p_r = P(r) with the subset marginalised.
+//   p_r and P(s*, r): sums over node sets that depend on ext only (csrc/snq_host.h generate_sub) --
+//     part 1, groups [0, G): nodes over B (coordinates of S' zero), candidate variance conditional on B only;
+//     part 2, groups [G, 2G): nodes of the prior of ext inside the orthant (r_B, s*).
+//   P(s*, r | labels): a labelled sample keeps the sign of its label (variances >> label noise, as in the general
+//     feedback model), so this is P(S' keeps s* | labels).  Given the labels of B, S' ~ N(mU_g, CU) and the
+//     candidate's label y ~ N(mean_c, tau^2) with covariance c = (Bm Sig) l_i to S': conditioning on y is a rank-one
+//     update, S' ~ N(mU_g + c (y - mean_c) / tau^2, CU - c c^T / tau^2), different for every candidate, and its
+//     orthant probability is evaluated here with the shared-node rule itself (nodes of the first u - 1 variables
+//     generated on the fly by snq_node, the last variable analytic) -- the importance-weighted shortcut over shared
+//     nodes (label density times prior nodes) under-resolves candidates that correlate strongly with the subset.
+struct SubArgs {
+    const int* count;
+    const int* list;
+    const double* m;
+    const double* v;
+    const double* U;
+    int64_t ldu;
+    int W0;
+    int tB, D;
+    const double* eta;          // dimension-major [D][n_nodes]
+    const double* w;
+    int64_t n_nodes;
+    const int* group_begin;     // 2 G + 1
+    const double* mass;         // [2][G]: parts 1 and 2
+    const double* mu;           // [G][D]: mean of eta given the labels r_B
+    const double* Sig;          // [D][D]: covariance of eta given labels on B
+    const double* mU;           // [G][u]: mean of S' given the labels r_B
+    const double* CU;           // [u][u]: covariance of S' given labels on B
+    const double* BS;           // [u][D]: Bm Sig (covariance of S' with eta)
+    int sub_bits;               // s*
+    int q_last;                 // Gauss-Legendre nodes per panel of the per-candidate rule (u - 1 variables)
+    double R;
+    int q_min;
+    const double* gl_x;
+    const double* gl_w;
+    double noise;
+    const double2* phi;
+    double* score;
+    double* gain;
+    uint32_t* tags;
+    uint32_t epoch;
+    int* n_scored;
+};
+
+constexpr int kSubMaxCols = 11;          // = kMaxBatch columns of ext
+constexpr int kSubMaxU = 5;              // subset members outside the batch
+
+template <int T>
+__device__ __forceinline__ double sub_orthant_sum(int64_t N, const SubArgs& a, const double* bm, const double* bL,
+                                                  int want, double sgn_last, const double2* phi_s) {
+    // sum over the nodes of the first T variables inside orthant `want` of Phi(+-(m_T + L_T. eta) / L_TT)
+    double acc = 0.0;
+    const double sd = bL[T * kBaseStride + T];
+    const double inv_sd = sd > 0.0 ? 1.0 / sd : 0.0;
+    for (int64_t k = threadIdx.x; k < N; k += blockDim.x) {
+        double e[T > 0 ? T : 1];
+        double wt;
+        int ob;
+        snq_node<T>(k, N, a.q_last, a.R, a.q_min, bm, bL, a.gl_x, a.gl_w, e, wt, ob);
+        if (ob != want || wt < 1e-13) continue;         // (the host rule drops the same light nodes)
+        double num = bm[T];
+#pragma unroll
+        for (int j = 0; j < T; ++j) num = fma(bL[T * kBaseStride + j], e[j], num);
+        num *= sgn_last;
+        const double cdf = sd > 0.0 ? phi_tab(phi_s, num * inv_sd) : (num > 0.0 ? 1.0 : 0.0);
+        acc = fma(wt, cdf, acc);
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(256) k_eval_sub(SubArgs a) {
+    pdl_enter();
+    extern __shared__ double ssm[];
+    const int G = 1 << a.tB, D = a.D, tB = a.tB, u = a.D - a.tB;
+    double* acc = ssm;                                  // [2G]: sums of the groups of parts 1 and 2
+    double* qv = ssm + 2 * G;                           // [2G]: P(S' keeps s* | labels), by (g, rc)
+    double* red = qv + 2 * G;                           // [8] per-warp partials
+    double* bm = red + 8;                               // [8]: mean of S' given all labels
+    double* bL = bm + 8;                                // [5][kBaseStride]: Cholesky factor of its covariance
+    double2* phi_s = reinterpret_cast<double2*>(ssm + ((4 * G + 16 + 5 * kBaseStride + 1) & ~1));
+    phi_tab_to_shared(phi_s, a.phi);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_items = *a.count;
+    const int64_t N = a.n_nodes;
+    int64_t n_last = 1;
+    for (int j = 0; j + 1 < u; ++j) n_last *= 2 * a.q_last;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int64_t i = a.list[item];
+        double l[kSubMaxCols];
+        double s2B = a.v[i], s2F;
+#pragma unroll
+        for (int j = 0; j < kSubMaxCols; ++j) l[j] = j < D ? a.U[(int64_t)(a.W0 + j) * a.ldu + i] : 0.0;
+        s2F = s2B;
+#pragma unroll
+        for (int j = 0; j < kSubMaxCols; ++j) {
+            if (j < tB) s2B = fma(-l[j], l[j], s2B);
+            s2F = fma(-l[j], l[j], s2F);
+        }
+        const double mi = a.m[i];
+        const double sB = s2B > 0.0 ? sqrt(s2B) : 0.0, sF = s2F > 0.0 ? sqrt(s2F) : 0.0;
+        const double st2 = fmax(s2F, 0.0) + a.noise;
+        // parts 1 and 2: shared nodes
+        for (int g = 0; g < 2 * G; ++g) {
+            const double sd = g < G ? sB : sF;
+            const double inv_sd = sd > 0.0 ? 1.0 / sd : 0.0;
+            double x0 = 0.0;
+            for (int q = a.group_begin[g] + threadIdx.x; q < a.group_begin[g + 1]; q += blockDim.x) {
+                double num = mi;
+#pragma unroll
+                for (int j = 0; j < kSubMaxCols; ++j)
+                    if (j < D) num = fma(l[j], a.eta[(int64_t)j * N + q], num);
+                const double cdf = sd > 0.0 ? phi_tab(phi_s, num * inv_sd) : (num > 0.0 ? 1.0 : 0.0);
+                x0 = fma(a.w[q], cdf, x0);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x0 += __shfl_xor_sync(0xffffffffu, x0, o);
+            if (lane == 0) red[warp] = x0;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double tot = 0.0;
+                for (int k = 0; k < 8; ++k) tot += red[k];
+                acc[g] = tot;
+            }
+            __syncthreads();
+        }
+        // part 3: the subset given the labels of B and of the candidate, one rank-one update per (g, label)
+        for (int gr = 0; gr < 2 * G; ++gr) {
+            const int g = gr & (G - 1), rc = gr >> tB;
+            if (u == 0) {
+                if (threadIdx.x == 0) qv[gr] = 1.0;
+                continue;
+            }
+            if (threadIdx.x == 0) {
+                double lSl = 0.0, mean_c = mi;
+                for (int r = 0; r < D; ++r) {
+                    double row = 0.0;
+                    for (int c = 0; c < D; ++c) row = fma(a.Sig[r * D + c], l[c], row);
+                    lSl = fma(l[r], row, lSl);
+                    mean_c = fma(l[r], a.mu[g * D + r], mean_c);
+                }
+                const double tau2 = st2 + fmax(lSl, 0.0);
+                const double dy = ((rc ? 1.0 : -1.0) - mean_c) / tau2;
+                double cv[kSubMaxU];
+                for (int x = 0; x < u; ++x) {
+                    double c = 0.0;
+                    for (int r = 0; r < D; ++r) c = fma(a.BS[x * D + r], l[r], c);
+                    cv[x] = c;
+                    bm[x] = fma(c, dy, a.mU[g * u + x]);
+                }
+                // Cholesky factor of CU - c c^T / tau^2 (pivots floored like the host's)
+                for (int x = 0; x < u; ++x)
+                    for (int y = 0; y <= x; ++y) {
+                        double val = a.CU[x * u + y] - cv[x] * cv[y] / tau2;
+                        for (int k = 0; k < y; ++k) val -= bL[x * kBaseStride + k] * bL[y * kBaseStride + k];
+                        if (x == y) bL[x * kBaseStride + x] = sqrt(val > 1e-300 ? val : 1e-300);
+                        else bL[x * kBaseStride + y] = val / bL[y * kBaseStride + y];
+                    }
+            }
+            __syncthreads();
+            const int T = u - 1;
+            const int want = a.sub_bits & ((1 << T) - 1);
+            const double sgn_last = ((a.sub_bits >> T) & 1) ? 1.0 : -1.0;
+            double x0;
+            switch (T) {
+                case 0: x0 = sub_orthant_sum<0>(n_last, a, bm, bL, want, sgn_last, phi_s); break;
+                case 1: x0 = sub_orthant_sum<1>(n_last, a, bm, bL, want, sgn_last, phi_s); break;
+                case 2: x0 = sub_orthant_sum<2>(n_last, a, bm, bL, want, sgn_last, phi_s); break;
+                case 3: x0 = sub_orthant_sum<3>(n_last, a, bm, bL, want, sgn_last, phi_s); break;
+                default: x0 = sub_orthant_sum<4>(n_last, a, bm, bL, want, sgn_last, phi_s); break;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x0 += __shfl_xor_sync(0xffffffffu, x0, o);
+            if (lane == 0) red[warp] = x0;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double tot = 0.0;
+                for (int k = 0; k < 8; ++k) tot += red[k];
+                qv[gr] = tot;
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+        // assembly over the 2 G relevance configurations of B + candidate
+        double term = 0.0;
+        if (threadIdx.x < 2 * G) {
+            const int g = threadIdx.x & (G - 1), rc = threadIdx.x >> tB;
+            const double p_r = fmax(rc ? acc[g] : a.mass[g] - acc[g], 0.0);
+            const double P = fmax(rc ? acc[G + g] : a.mass[G + g] - acc[G + g], 0.0);
+            const double q = fmin(fmax(qv[threadIdx.x], 0.0), 1.0);
+            term = p_r * (log(q + kEps) - log(P + kEps));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) term += __shfl_xor_sync(0xffffffffu, term, o);
+        if (lane == 0) red[warp] = term;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+            for (int k = 0; k < 8; ++k) tot += red[k];
+            a.tags[i] = tag_with_step(a.tags[i], a.epoch, a.D);
+            a.score[i] = tot;
+            a.gain[i] = tot;
+            atomicAdd(a.n_scored, 1);
+        }
+        __syncthreads();
+    }
 }
 
 template <int T>

@@ -145,43 +145,46 @@ struct Nodes {
 // nodes per orthant estimates the orthant masses; the kScN nodes are then shared out in proportion to them (at least
 // kScMin each; orthants below kScPMin are left out) and the weights scaled so that the orthant masses add up to one.
 // Nodes come out sorted by orthant.  Accuracy: 1e-4 class in the orthant probabilities (tests/test_orthant_vs_scipy.py).
-inline Nodes generate_sc(int t, const double* m, const double* L) {
+// Nodes of ONE orthant b (bit j set: z_j > 0): eta dimension-major with stride `stride` (nullptr: weights only).
+inline void sc_orthant(int t, const double* m, const double* L, int b, int64_t N, double* eta, int64_t stride, double* w) {
     static const int primes[12] = {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37};
     double alpha[12];
     for (int j = 0; j < t; ++j) {
         alpha[j] = std::sqrt((double)primes[j]);
         alpha[j] -= std::floor(alpha[j]);
     }
-    const int nb = 1 << t;
     auto cdf = [](double x) { return 0.5 * std::erfc(-x * 0.70710678118654752440); };
-    // nodes of orthant b: eta (dimension-major, stride N) and weights; returns the mass
-    auto gen = [&](int b, int64_t N, double* eta, int64_t stride, double* w) {
-        std::vector<double> e(t);
-        for (int64_t k = 0; k < N; ++k) {
-            double wk = 1.0 / (double)N;
-            for (int j = 0; j < t; ++j) {
-                double u = ((double)k + 0.5) * alpha[j];
-                u -= std::floor(u);
-                u = 1.0 - std::fabs(2.0 * u - 1.0);
-                double acc = m[j];
-                for (int i = 0; i < j; ++i) acc += L[j * t + i] * e[i];
-                const double a = -acc / L[j * t + j];
-                if ((b >> j) & 1) {                     // z_j > 0: eta_j above a
-                    const double q = cdf(-a);
-                    const double p = u * q;
-                    e[j] = -ndtri(p < 1e-300 ? 1e-300 : p);
-                    wk *= q;
-                } else {
-                    const double q = cdf(a);
-                    const double p = u * q;
-                    e[j] = ndtri(p < 1e-300 ? 1e-300 : p);
-                    wk *= q;
-                }
-                if (eta) eta[(size_t)j * stride + k] = e[j];
+    std::vector<double> e(t);
+    for (int64_t k = 0; k < N; ++k) {
+        double wk = 1.0 / (double)N;
+        for (int j = 0; j < t; ++j) {
+            double u = ((double)k + 0.5) * alpha[j];
+            u -= std::floor(u);
+            u = 1.0 - std::fabs(2.0 * u - 1.0);
+            double acc = m[j];
+            for (int i = 0; i < j; ++i) acc += L[j * t + i] * e[i];
+            const double a = -acc / L[j * t + j];
+            if ((b >> j) & 1) {                     // z_j > 0: eta_j above a
+                const double q = cdf(-a);
+                const double p = u * q;
+                e[j] = -ndtri(p < 1e-300 ? 1e-300 : p);
+                wk *= q;
+            } else {
+                const double q = cdf(a);
+                const double p = u * q;
+                e[j] = ndtri(p < 1e-300 ? 1e-300 : p);
+                wk *= q;
             }
-            w[k] = wk;
+            if (eta) eta[(size_t)j * stride + k] = e[j];
         }
-    };
+        w[k] = wk;
+    }
+}
+
+inline Nodes generate_sc(int t, const double* m, const double* L) {
+    const int nb = 1 << t;
+    // nodes of orthant b: eta (dimension-major, stride N) and weights
+    auto gen = [&](int b, int64_t N, double* eta, int64_t stride, double* w) { sc_orthant(t, m, L, b, N, eta, stride, w); };
     // (orthants are independent: the pilot pass and the final pass run over the host cores, one orthant at a time per
     // thread; masses are summed per orthant in node order, so the result does not depend on the thread count)
     std::vector<double> P(nb);
@@ -538,6 +541,190 @@ inline GeneralSets generate_general(int t, const double* m, const double* L, dou
             e[1] = s;
             e[2] = (c_in ? 1 : 0) | (Om == (1 << D) - 1 ? 2 : 0);
         }
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Node sets of the change-estimation subset (MutualInformation._call_iter_sub, /root/reference/ital/ital.py:227-275):
+// the variables are ext = [B (tB samples of the batch), S' (subset members outside the batch)], D of them, with means
+// m and Cholesky factor L (row-major D x D) of their posterior covariance.  Two families of 2^tB groups each, in the
+// whitened coordinates eta of ext (consumed by k_eval_sub, which documents what each part is for):
+//   part 1: the unconditional nodes of B alone (coordinates of S' zero);
+//   part 2: nodes of the prior inside the orthant (r_B, s*), s* = signs of the means of S';
+// and the moments of S' conditional on the labels r_B of B (labels +-1 with noise sigma^2) from which the kernel
+// conditions on every candidate's own label.
+// Orthants of up to 5 variables are cut out of the tensor rule, larger ones get kSubN lattice nodes each.
+constexpr int64_t kSubN = 16384;
+
+struct SubSets {
+    int tB = 0, D = 0, n_groups = 0, sub_bits = 0;
+    int64_t n_nodes = 0;
+    std::vector<double> eta;            // dimension-major [D][n_nodes]
+    std::vector<double> w;
+    std::vector<int32_t> group_begin;   // 2 * 2^tB + 1
+    std::vector<double> mass;           // [2][2^tB]: group masses of parts 1 and 2
+    std::vector<double> mu;             // [2^tB][D]: mean of eta given the labels r_B
+    std::vector<double> Sig;            // [D][D]: covariance of eta given labels on B
+    std::vector<double> mU;             // [2^tB][u]: mean of S' given the labels r_B
+    std::vector<double> CU;             // [u][u]: covariance of S' given labels on B
+    std::vector<double> BS;             // [u][D]: Bm Sig, covariance of S' with eta given labels on B
+};
+
+// nodes of N(m, L L^T) (u variables) inside orthant b, coordinates whitened by L: appended to eta (node-major, u per
+// node) and w
+inline void orthant_nodes(int u, const double* m, const double* L, int b, std::vector<double>& eta, std::vector<double>& w) {
+    if (u == 0) {
+        w.push_back(1.0);
+        return;
+    }
+    if (u < kScFrom) {
+        Nodes nd = generate(u, m, L);
+        for (int32_t q = nd.group_begin[b]; q < nd.group_begin[b + 1]; ++q) {
+            for (int a = 0; a < u; ++a) eta.push_back(nd.eta[(size_t)a * nd.n + q]);
+            w.push_back(nd.w[q]);
+        }
+        return;
+    }
+    std::vector<double> e((size_t)u * kSubN), ww(kSubN);
+    // (one orthant: spread the nodes over the cores by running the lattice in slices would change nothing in the
+    // result, but 16384 nodes take about a millisecond)
+    sc_orthant(u, m, L, b, kSubN, e.data(), kSubN, ww.data());
+    for (int64_t q = 0; q < kSubN; ++q) {
+        for (int a = 0; a < u; ++a) eta.push_back(e[(size_t)a * kSubN + q]);
+        w.push_back(ww[q]);
+    }
+}
+
+inline SubSets generate_sub(int tB, int D, const double* m, const double* L, double noise) {
+    SubSets out;
+    out.tB = tB;
+    out.D = D;
+    const int u = D - tB, G = 1 << tB;
+    out.n_groups = 2 * G;
+    for (int a = 0; a < u; ++a)
+        if (m[tB + a] > 0.0) out.sub_bits |= 1 << a;
+    std::vector<std::vector<double>> g_eta(2 * G), g_w(2 * G);      // node-major, D coordinates per node
+    out.mass.assign(2 * G, 0.0);
+    // part 1: B alone
+    if (tB == 0) {
+        g_eta[0].assign(D, 0.0);
+        g_w[0].assign(1, 1.0);
+        out.mass[0] = 1.0;
+    } else {
+        std::vector<double> LB((size_t)tB * tB);
+        for (int a = 0; a < tB; ++a)
+            for (int c = 0; c < tB; ++c) LB[a * tB + c] = L[a * D + c];
+        Nodes nd = generate(tB, m, LB.data());
+        for (int g = 0; g < G; ++g) {
+            for (int32_t q = nd.group_begin[g]; q < nd.group_begin[g + 1]; ++q) {
+                for (int c = 0; c < D; ++c) g_eta[g].push_back(c < tB ? nd.eta[(size_t)c * nd.n + q] : 0.0);
+                g_w[g].push_back(nd.w[q]);
+            }
+            out.mass[g] = nd.masses[g];
+        }
+    }
+    // the pieces of the conditioning on B that do not depend on the labels: X = (A A^T + noise I)^-1 A, A = L[B, :],
+    // Sig = I - A^T X; S' = m_U + Bm eta, CU = Bm Sig Bm^T
+    std::vector<double> X((size_t)tB * D, 0.0), Sig((size_t)D * D, 0.0);
+    if (tB > 0) {
+        std::vector<double> S((size_t)tB * tB);
+        for (int a = 0; a < tB; ++a)
+            for (int b = 0; b < tB; ++b) {
+                double acc = (a == b) ? noise : 0.0;
+                for (int c = 0; c < D; ++c) acc += L[a * D + c] * L[b * D + c];
+                S[a * tB + b] = acc;
+            }
+        chol_inplace(S, tB);
+        for (int c = 0; c < D; ++c) {
+            std::vector<double> y(tB);
+            for (int a = 0; a < tB; ++a) {
+                double v = L[a * D + c];
+                for (int b = 0; b < a; ++b) v -= S[a * tB + b] * y[b];
+                y[a] = v / S[a * tB + a];
+            }
+            for (int a = tB - 1; a >= 0; --a) {
+                double v = y[a];
+                for (int b = a + 1; b < tB; ++b) v -= S[b * tB + a] * X[b * D + c];
+                X[a * D + c] = v / S[a * tB + a];
+            }
+        }
+    }
+    for (int r = 0; r < D; ++r)
+        for (int c = 0; c < D; ++c) {
+            double acc = (r == c) ? 1.0 : 0.0;
+            for (int a = 0; a < tB; ++a) acc -= L[a * D + r] * X[a * D + c];
+            Sig[r * D + c] = acc;
+        }
+    out.Sig = Sig;
+    std::vector<double> SB((size_t)D * std::max(u, 1)), CU((size_t)u * u);
+    for (int r = 0; r < D; ++r)
+        for (int a = 0; a < u; ++a) {
+            double acc = 0.0;
+            for (int c = 0; c < D; ++c) acc += Sig[r * D + c] * L[(tB + a) * D + c];
+            SB[r * u + a] = acc;
+        }
+    for (int a = 0; a < u; ++a)
+        for (int b = 0; b < u; ++b) {
+            double acc = 0.0;
+            for (int c = 0; c < D; ++c) acc += L[(tB + a) * D + c] * SB[c * u + b];
+            CU[a * u + b] = acc;
+        }
+    out.CU = CU;
+    out.BS.assign((size_t)u * D, 0.0);
+    for (int a = 0; a < u; ++a)
+        for (int r = 0; r < D; ++r) out.BS[a * D + r] = SB[r * u + a];
+    out.mU.assign((size_t)G * std::max(u, 1), 0.0);
+    out.mu.assign((size_t)G * D, 0.0);
+    Nodes prior;                        // the tensor rule of ext serves every group of part 2
+    if (D < kScFrom) prior = generate(D, m, L);
+    // part 2 and the conditional moments, one group per relevance configuration of B (independent: over the host cores)
+    parallel_for(G, 1, [&](int64_t g_lo, int64_t g_hi) {
+        for (int64_t g = g_lo; g < g_hi; ++g) {
+            // part 2: prior of ext inside (r_B = g, s*)
+            {
+                std::vector<double> e, w;
+                const int b = (int)g | (out.sub_bits << tB);
+                if (D < kScFrom) {
+                    for (int32_t q = prior.group_begin[b]; q < prior.group_begin[b + 1]; ++q) {
+                        for (int a = 0; a < D; ++a) e.push_back(prior.eta[(size_t)a * prior.n + q]);
+                        w.push_back(prior.w[q]);
+                    }
+                } else {
+                    orthant_nodes(D, m, L, b, e, w);
+                }
+                double acc = 0.0;
+                for (double wk : w) acc += wk;
+                out.mass[G + g] = acc;
+                g_eta[G + g].swap(e);
+                g_w[G + g].swap(w);
+            }
+            // moments conditional on the labels of B
+            double* mu = out.mu.data() + (size_t)g * D;
+            for (int c = 0; c < D; ++c) {
+                double acc = 0.0;
+                for (int a = 0; a < tB; ++a) acc += X[a * D + c] * ((((g >> a) & 1) ? 1.0 : -1.0) - m[a]);
+                mu[c] = acc;
+            }
+            for (int a = 0; a < u; ++a) {
+                double acc = m[tB + a];
+                for (int c = 0; c < D; ++c) acc += L[(tB + a) * D + c] * mu[c];
+                out.mU[(size_t)g * u + a] = acc;
+            }
+        }
+    });
+    // flatten, dimension-major
+    out.group_begin.assign(2 * G + 1, 0);
+    for (int g = 0; g < 2 * G; ++g) out.group_begin[g + 1] = out.group_begin[g] + (int32_t)g_w[g].size();
+    out.n_nodes = out.group_begin[2 * G];
+    out.eta.assign((size_t)D * out.n_nodes, 0.0);
+    out.w.resize(out.n_nodes);
+    for (int g = 0; g < 2 * G; ++g) {
+        const int64_t pos = out.group_begin[g];
+        for (size_t q = 0; q < g_w[g].size(); ++q) {
+            out.w[pos + q] = g_w[g][q];
+            for (int c = 0; c < D; ++c) out.eta[(size_t)c * out.n_nodes + pos + q] = g_eta[g][q * D + c];
+        }
+    }
     return out;
 }
 

@@ -90,6 +90,14 @@ class _Shard(object):
                                                    int(bool(first_pick_takes_unnameable)), _capi.dptr(rec)))
         return rec
 
+    def set_sub_mode(self, on):
+        _capi.check(self.lib.ital_set_sub_mode(self.handle, int(bool(on))))
+
+    def fetch_propose_sub(self, n_batch, only_row):
+        rec = np.zeros(self.record_doubles())
+        _capi.check(self.lib.ital_fetch_propose_sub(self.handle, int(n_batch), int(only_row), _capi.dptr(rec)))
+        return rec
+
     def fetch_commit(self, record):
         record = _capi.as_f64(record)
         _capi.check(self.lib.ital_fetch_commit(self.handle, _capi.dptr(record)))
@@ -582,6 +590,8 @@ class ITAL(object):
     ESTIMATIONS = {'mean': 0, 'optimistic': 1, 'pessimistic': 2}
     MAX_BATCH = 11                  # greedy steps per fetch (10 base variables)
     MAX_BATCH_GENERAL = 5           # with label_prob < 1 (conditional node sets up to 4 base variables)
+    MAX_BATCH_SUBSET = 7            # with change_estimation_subset > 0 ...
+    MAX_COLS_SUBSET = 11            # ... and batch - 1 + subset columns at most
 
     def _check_supported(self, k=0):
         if self.label_estimation not in self.ESTIMATIONS:
@@ -591,8 +601,18 @@ class ITAL(object):
         if k > limit:               # before any work (and before any collective) -- not in the middle of the greedy loop
             raise NotImplementedError('batches of more than %d samples are not supported%s' % (
                 limit, " with label_prob < 1 or label_estimation other than 'mean'" if general else ''))
-        if self.change_estimation_subset != 0 or (self.clip_cov and 0 < self.clip_cov < 1 and k > 5):
-            raise NotImplementedError('change_estimation_subset and clip_cov are outside the accelerated path')
+        if self.clip_cov and 0 < self.clip_cov < 1 and k > 5:
+            raise NotImplementedError('clip_cov (grouped orthant probabilities of more than 5 variables) is not built')
+        ce = self.change_estimation_subset
+        if ce is None:              # every unseen sample in the subset: orthant probabilities in n dimensions
+            raise NotImplementedError('change_estimation_subset=None (all unseen samples) is not built')
+        if ce > 0:
+            if general or self.mistake_prob > 0:
+                raise NotImplementedError('change_estimation_subset is built for label_prob=1, mistake_prob=0, '
+                                          "label_estimation='mean'")
+            if k > self.MAX_BATCH_SUBSET or k - 1 + ce > self.MAX_COLS_SUBSET:
+                raise NotImplementedError('change_estimation_subset: at most %d samples per batch and batch + subset '
+                                          '<= %d' % (self.MAX_BATCH_SUBSET, self.MAX_COLS_SUBSET + 1))
         # monte_carlo_num_rel / monte_carlo_num_fb (ital.py:293-297, 319-342): the reference replaces the enumeration
         # of relevance / feedback configurations by random samples only when there are more configurations than
         # samples (2^(D-1) >= D * num, 3^D >= 2 * D * num); its samples come from the global numpy RNG in candidate
@@ -624,6 +644,8 @@ class ITAL(object):
         self.last_fetch_stats = []
         self._apply_lazy_rows()
         try:
+            if self.change_estimation_subset:
+                return self._fetch_change_subset(k)
             if self._comm.world_size == 1 and not show_progress:
                 idx, scores = self._shard.fetch(k, self.label_prob, self.mistake_prob, self._exhaustive())
                 self.last_fetch_scores = scores
@@ -641,6 +663,52 @@ class ITAL(object):
         finally:
             if restricted:
                 self._shard.restrict_candidates(None)
+
+    def _fetch_change_subset(self, k, keep_scores=False):                       # ital.py:102-108, 227-275, 514-584
+        """Greedy loop with change_estimation_subset > 0: the reference's own draw of the subset (same call on the
+        global numpy RNG), then per step one evaluation of all candidates outside ext = batch + subset and one per
+        subset member that is still a candidate (scored with itself moved out of the subset)."""
+        sh, comm = self._shard, self._comm
+        candidates = self.get_unseen()
+        S = sorted(np.random.choice(candidates, min(len(candidates), self.change_estimation_subset), replace=False))
+        S = [int(i) for i in S]
+        _capi.check(sh.lib.ital_set_lazy_rows(sh.handle, 0))    # every row needs its projection on ext
+        sh.set_sub_mode(True)
+        ret, self.last_fetch_scores, self.last_subset, self.last_step_scores = [], [], list(S), []
+
+        def evaluate(batch, sub, only):
+            sh.fetch_begin(1.0, 0.0)
+            try:
+                for e in batch + sub:
+                    sh.fetch_commit(comm.sum_records(sh.export_points([e]))[0])
+                allrec = comm.gather_records(sh.fetch_propose_sub(len(batch), only))
+                self.last_fetch_stats.append(sh.stats())
+                if keep_scores:
+                    sc = self._all_rows(sh.last_scores())[:self._n]
+                    seen = ~np.isnan(sc)
+                    self.last_step_scores[-1][seen] = sc[seen]
+            finally:
+                sh.fetch_end()
+            win = pick_winner(allrec)
+            return None if win < 0 else (float(allrec[win][1]), int(allrec[win][0]))
+
+        try:
+            for it in range(k):
+                sub = [i for i in S if i not in ret]
+                if keep_scores:
+                    self.last_step_scores.append(np.full(self._n, np.nan))
+                best = evaluate(ret, sub, -1)
+                for i in sub:
+                    cur = evaluate(ret, [j for j in sub if j != i], i)
+                    if cur is not None and (best is None or cur[0] > best[0] or (cur[0] == best[0] and cur[1] < best[1])):
+                        best = cur
+                if best is None:
+                    break
+                ret.append(best[1])
+                self.last_fetch_scores.append(best[0])
+        finally:
+            sh.set_sub_mode(False)
+        return ret
 
     def _fetch_device_loop(self, k):
         """Multi-GPU greedy loop with the records staying on the GPUs: per step one enqueue of the local

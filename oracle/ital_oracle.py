@@ -204,7 +204,8 @@ class OracleITAL(object):
         self.parallelized = parallelized
         self.force_general = force_general
         self.general_sets = general_sets      # general feedback model through shared conditional node sets (oracle/general_sets.py)
-        if change_estimation_subset != 0 or clip_cov != 0 or monte_carlo_num_rel is not None \
+        self.change_estimation_subset = change_estimation_subset
+        if change_estimation_subset is None or clip_cov != 0 or monte_carlo_num_rel is not None \
                 or monte_carlo_num_fb is not None:
             raise NotImplementedError('oracle restates the enumeration path only (see module docstring)')
         self.fit(data, queries)
@@ -286,6 +287,10 @@ class OracleITAL(object):
         candidates = self.get_unseen()
         if len(candidates) < k:
             k = len(candidates)
+        subset = None
+        if self.change_estimation_subset:                                       # ital.py:105-106 (same draw, same RNG)
+            subset = [int(i) for i in sorted(np.random.choice(
+                candidates, min(len(candidates), self.change_estimation_subset), replace=False))]
         if self.top_candidates is not None:                                     # ital.py:111-117
             top = self.top_candidates
             if isinstance(top, float):
@@ -294,6 +299,8 @@ class OracleITAL(object):
             if (top > 0) and (top < len(candidates)):
                 top_ind = np.argpartition(self.rel_mean[candidates], -top)[-top:]
                 candidates = [candidates[i] for i in top_ind]
+        if subset is not None:
+            return self._fetch_change_subset(k, candidates, subset, forced)
         n = len(self.data)
         ret = []
         self.trace = []          # per greedy step: dict(candidates, scores, ...) for the parity tests
@@ -329,6 +336,47 @@ class OracleITAL(object):
                                    var=var_test[cand].copy(), cov_base=cov_base.copy(),
                                    cov_base_test=cov_base_test[:, cand].copy(), chosen=int(cand[max_ind]),
                                    argmax=int(cand[int(np.argmax(scores))]), **extra))
+            ret.append(int(cand[max_ind]))
+            del candidates[max_ind]
+        return ret
+
+    # change_estimation_subset > 0 (ital.py:227-275, 514-584), scores in the shared-node form of oracle/ce_subset.py
+    def _sub_scores(self, batch, sub, rows):
+        """Scores of ``rows`` (outside ext) against ext = batch + sub."""
+        from .ce_subset import mi_sub_shared
+        ext = list(batch) + list(sub)
+        rows = np.asarray(rows, dtype=np.int64)
+        var0 = self.gp.predict_stored(cov_mode='diag')[1]
+        if len(ext) == 0:
+            L, l = np.zeros((0, 0)), np.zeros((len(rows), 0))
+        else:
+            cov_ext, _, cov_ext_test = self.gp.predict_cov_parts(ext)
+            L = safe_cholesky(cov_ext)
+            l = scipy.linalg.solve_triangular(L, cov_ext_test[:, rows], lower=True).T
+        m_ext = self.rel_mean[ext] if len(ext) else np.zeros(0)
+        return mi_sub_shared(len(batch), m_ext, L, self.rel_mean[rows], l, var0[rows], self.noise)
+
+    def _fetch_change_subset(self, k, candidates, subset, forced=None):
+        if not (self._perfect_user() and self.label_estimation == 'mean'):
+            raise NotImplementedError('change_estimation_subset is restated for users who label everything correctly')
+        ret = []
+        self.trace = []
+        self.subset = list(subset)
+        for it in range(k):
+            sub = [i for i in subset if i not in ret]
+            cand = np.asarray(candidates, dtype=np.int64)
+            scores = np.empty(len(cand))
+            outside = np.array([int(i) not in sub for i in cand], dtype=bool)
+            if outside.any():
+                scores[outside] = self._sub_scores(ret, sub, cand[outside])
+            for pos in np.nonzero(~outside)[0]:         # a subset member: scored with itself moved out of the subset
+                i = int(cand[pos])
+                scores[pos] = self._sub_scores(ret, [j for j in sub if j != i], [i])[0]
+            max_ind = int(np.argmax(scores))
+            if forced is not None:
+                max_ind = candidates.index(int(forced[it]))
+            self.trace.append(dict(candidates=cand, scores=scores, chosen=int(cand[max_ind]),
+                                   argmax=int(cand[int(np.argmax(scores))]), subset=list(subset)))
             ret.append(int(cand[max_ind]))
             del candidates[max_ind]
         return ret

@@ -62,6 +62,32 @@ def snq_order(t):
     return 0
 
 
+def sc_orthant(m_base, L_base, b, N):
+    """N lattice nodes of N(m, L L^T) inside ONE orthant b (bit j set: variable j positive), whitened coordinates:
+    (eta (N, t), w (N,)); sum(w) estimates the orthant probability.  See sc_nodes."""
+    from scipy.special import ndtri
+    m_base = np.asarray(m_base, dtype=np.float64)
+    L_base = np.asarray(L_base, dtype=np.float64)
+    t = len(m_base)
+    alpha = np.array([np.sqrt(float(p)) - np.floor(np.sqrt(float(p))) for p in _PRIMES[:t]])
+    k = np.arange(N, dtype=np.float64) + 0.5
+    u = k[:, None] * alpha[None, :]
+    u -= np.floor(u)
+    u = 1.0 - np.abs(2.0 * u - 1.0)
+    eta = np.zeros((N, t))
+    w = np.full(N, 1.0 / N)
+    for j in range(t):
+        a = -(m_base[j] + eta[:, :j] @ L_base[j, :j]) / L_base[j, j]
+        if (b >> j) & 1:
+            q = ndtr(-a)
+            eta[:, j] = -ndtri(np.maximum(u[:, j] * q, 1e-300))
+        else:
+            q = ndtr(a)
+            eta[:, j] = ndtri(np.maximum(u[:, j] * q, 1e-300))
+        w = w * q
+    return eta, w
+
+
 def sc_nodes(m_base, L_base, n_total=SNQ_SC_N):
     """Node set for t >= 6 base variables (batches of more than 6 samples), where a tensor rule explodes.
 
@@ -76,29 +102,12 @@ def sc_nodes(m_base, L_base, n_total=SNQ_SC_N):
     (tests/test_orthant_vs_scipy.py) -- the reference's own ``mvndst(maxpts=100*dim, abseps=1e-4)``
     (ital/ital.py:380-381) is no better for these dimensions.
     """
-    from scipy.special import ndtri
     m_base = np.asarray(m_base, dtype=np.float64)
     L_base = np.asarray(L_base, dtype=np.float64)
     t = len(m_base)
-    alpha = np.array([np.sqrt(float(p)) - np.floor(np.sqrt(float(p))) for p in _PRIMES[:t]])
 
     def gen(b, N):
-        k = np.arange(N, dtype=np.float64) + 0.5
-        u = k[:, None] * alpha[None, :]
-        u -= np.floor(u)
-        u = 1.0 - np.abs(2.0 * u - 1.0)
-        eta = np.zeros((N, t))
-        w = np.full(N, 1.0 / N)
-        for j in range(t):
-            a = -(m_base[j] + eta[:, :j] @ L_base[j, :j]) / L_base[j, j]
-            if (b >> j) & 1:
-                q = ndtr(-a)
-                eta[:, j] = -ndtri(np.maximum(u[:, j] * q, 1e-300))
-            else:
-                q = ndtr(a)
-                eta[:, j] = ndtri(np.maximum(u[:, j] * q, 1e-300))
-            w = w * q
-        return eta, w
+        return sc_orthant(m_base, L_base, b, N)
 
     P = np.array([gen(b, SNQ_SC_PILOT)[1].sum() for b in range(1 << t)])
     etas, ws, orth = [], [], []

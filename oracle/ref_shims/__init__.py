@@ -16,7 +16,7 @@ import numpy as np
 REFERENCE_ROOT = '/root/reference'
 # Gauss-Legendre nodes per panel of the stand-in, by number of variables (the oracle itself uses 32/16/12
 # for 2/3/4 variables); two variables go to scipy's own translation of Genz's BVU instead.
-STANDIN_Q = {3: 48, 4: 28, 5: 14, 6: 8}
+STANDIN_Q = {3: 48, 4: 28, 5: 14, 6: 12}
 STANDIN_R = 8.5
 
 

@@ -22,12 +22,26 @@ def _npz_names():
 
 def golden_names():
     """Fetch goldens (every greedy step of a fetch_unlabelled of the reference)."""
-    return [n for n in _npz_names() if not n.startswith(('updpred_', 'experiment_', 'baseline_'))]
+    return [n for n in _npz_names() if not n.startswith(('updpred_', 'experiment_', 'baseline_', 'subset_'))]
 
 
 def updpred_names():
     """updated_prediction goldens (make_golden.py run_updated_prediction)."""
     return [n for n in _npz_names() if n.startswith('updpred_')]
+
+
+def subset_names():
+    """Goldens of ITAL(change_estimation_subset = c) (make_subset_golden.py)."""
+    return [n for n in _npz_names() if n.startswith('subset_')]
+
+
+def load_subset(name):
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + '.npz'), allow_pickle=False))
+    g['updates'] = [dict(zip(g['upd%d_idx' % u].tolist(), g['upd%d_val' % u].tolist()))
+                    for u in range(int(g['n_updates']))]
+    g['steps'] = [dict(candidates=g['step%d_candidates' % t], mi=g['step%d_mi' % t], chosen=int(g['step%d_chosen' % t]))
+                  for t in range(len(g['ret']))]
+    return g
 
 
 def baseline_names():

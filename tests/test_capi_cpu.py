@@ -223,3 +223,70 @@ def test_normal_cdf_table_matches_erfc():
     poly = 1 + dl * (c2 + dl * (c3 + dl * (c4 + dl * c5)))
     got = t[:, 0] + t[:, 1] * dl * poly
     np.testing.assert_allclose(got, ndtr(x), rtol=0, atol=3e-16)
+
+
+@pytest.mark.parametrize('tB,u', [(0, 3), (2, 2), (1, 4), (3, 5), (2, 0)])
+def test_subset_node_sets_match_the_oracle(tB, u):
+    """csrc/snq_host.h generate_sub (change_estimation_subset) against oracle/ce_subset.py sub_sets: node sets of the
+    batch alone and of the prior inside (r_B, s*), conditional moments of the subset given the labels of the batch."""
+    from oracle import ce_subset
+    lib = _capi.load()
+    rng = np.random.RandomState(10 * tB + u)
+    D = tB + u
+    A = rng.randn(D, D + 2)
+    C = A @ A.T / (D + 2) + 0.05 * np.eye(D)
+    L = np.ascontiguousarray(np.linalg.cholesky(C))
+    m = rng.randn(D) * 0.7
+    noise = 1e-4
+    sizes = np.zeros(4, dtype=np.int64)
+    i32 = ctypes.POINTER(ctypes.c_int32)
+    assert lib.ital_snq_sub(tB, D, _capi.dptr(m), _capi.dptr(L), noise, _capi.i64ptr(sizes), None, None, None, None) == 0
+    N, NG, bits, nt = [int(x) for x in sizes]
+    G = 1 << tB
+    assert NG == 2 * G
+    eta, w, gb, tab = np.zeros((D, N)), np.zeros(N), np.zeros(NG + 1, dtype=np.int32), np.zeros(max(nt, 1))
+    assert lib.ital_snq_sub(tB, D, _capi.dptr(m), _capi.dptr(L), noise, _capi.i64ptr(sizes), _capi.dptr(eta),
+                            _capi.dptr(w), gb.ctypes.data_as(i32), _capi.dptr(tab)) == 0
+    S = ce_subset.sub_sets(tB, m, L, noise)
+    assert bits == S['sub_bits']
+    for g in range(G):
+        for part, key in ((0, 'part1'), (1, 'part2')):
+            e, ww = S[key][g]
+            lo, hi = gb[part * G + g], gb[part * G + g + 1]
+            assert hi - lo == len(ww)
+            np.testing.assert_allclose(w[lo:hi], ww, rtol=1e-9, atol=1e-300)
+            np.testing.assert_allclose(eta[:, lo:hi].T, e, rtol=0, atol=1e-9)
+    off = 0
+    for key, count in (('mass1', G), ('mass2', G), ('mu', G * D), ('Sig', D * D), ('mU', G * u), ('CU', u * u),
+                       ('BS', u * D)):
+        np.testing.assert_allclose(tab[off:off + count], np.asarray(S[key]).reshape(-1), rtol=1e-9, atol=1e-12,
+                                   err_msg=key)
+        off += count
+    assert off == nt
+
+
+def test_subset_oracle_forms_agree():
+    """oracle/ce_subset.py: the shared-node form (what k_eval_sub computes) against the literal restatement of
+    MutualInformation._call_iter_sub (three orthant probabilities per relevance configuration, updated_prediction)."""
+    from oracle.ce_subset import mi_sub_literal
+    from oracle.ital_oracle import OracleITAL
+    rng = np.random.RandomState(0)
+    X = rng.randn(40, 2)
+    L = OracleITAL(X, length_scale=1.0, noise=1e-6, change_estimation_subset=3)
+    L.update({0: 1, 5: -1, 9: 1})
+    np.random.seed(7)
+    ret = L.fetch_unlabelled(2)
+    B = []
+    for it, tr in enumerate(L.trace):
+        ext = L.subset + [b for b in B if b not in L.subset]
+        members = [int(np.nonzero(tr['candidates'] == s)[0][0]) for s in L.subset if s in tr['candidates']]
+        for pos in list(range(0, len(tr['candidates']), 9)) + members:
+            i = int(tr['candidates'][pos])
+            if i in ext:
+                r, rel_it = ext, [ext.index(b) for b in B] + [ext.index(i)]
+            else:
+                r, rel_it = ext + [i], [ext.index(b) for b in B] + [len(ext)]
+            lit = mi_sub_literal(L, r, rel_it)
+            assert abs(lit - tr['scores'][pos]) <= 2e-5 * max(1.0, abs(lit)), (it, i, lit, tr['scores'][pos])
+        B.append(tr['chosen'])
+    assert ret == B

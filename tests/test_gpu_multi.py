@@ -92,3 +92,58 @@ def test_two_gpus_match_one_gpu_and_oracle(local_rows, peer):
         assert batches == one_batches == ora_batches
         np.testing.assert_allclose(rel_mean, one_mean, rtol=1e-9, atol=1e-12)
         np.testing.assert_allclose(rel_mean, ora_mean, rtol=1e-6, atol=1e-9)
+
+
+def _subset_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        from ital_b200 import ITAL
+        X, fb = _subset_problem()
+        learner = ITAL(X, length_scale=1.0, device=rank, process_group=True, change_estimation_subset=3)
+        learner.update(fb)
+        np.random.seed(21)                              # every rank draws the same subset
+        ret = learner.fetch_unlabelled(3)
+        q.put((rank, ret, learner.last_subset, list(learner.last_fetch_scores)))
+        learner.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def _subset_problem(n=61, seed=2):
+    rng = np.random.RandomState(seed)
+    X = rng.randn(n, 2)
+    y = np.where(X[:, 0] - 0.4 * X[:, 1] > 0, 1, -1)
+    return X, {1: int(y[1]), 6: int(y[6]), 20: int(y[20]), 40: int(y[40])}
+
+
+def test_change_estimation_subset_on_two_gpus():
+    """The stepwise protocol of the subset mode over two shards (records of batch + subset summed over the ranks, the
+    shards' best records gathered): same subset, batch and scores as one GPU."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    from ital_b200 import ITAL
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_subset_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=300) for _ in procs), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    X, fb = _subset_problem()
+    one = ITAL(X, length_scale=1.0, device=0, change_estimation_subset=3)
+    one.update(fb)
+    np.random.seed(21)
+    want = one.fetch_unlabelled(3)
+    for rank, ret, subset, scores in res:
+        assert subset == one.last_subset and ret == want
+        np.testing.assert_allclose(scores, one.last_fetch_scores, rtol=1e-9, atol=1e-12)

@@ -8,7 +8,8 @@ oracle (absolute floor 1e-9 for moments, 1e-12 = the reference's eps for scores)
 import numpy as np
 import pytest
 
-from conftest import baseline_names, drive, golden_names, load_baseline, load_golden, load_updpred, updpred_names
+from conftest import (baseline_names, drive, golden_names, load_baseline, load_golden, load_subset, load_updpred,
+                      subset_names, updpred_names)
 
 pytestmark = pytest.mark.gpu
 
@@ -597,3 +598,59 @@ def test_optimistic_golden_from_the_reference():
         np.testing.assert_allclose(sc[st['candidates']], st['mi'], rtol=1e-2, atol=1e-5, err_msg='step %d' % t)
         if ret[t] != st['chosen']:
             break
+
+
+def _subset_problem(n=60, seed=0):
+    rng = np.random.RandomState(seed)
+    X = rng.randn(n, 2)
+    y = np.where(X[:, 0] + 0.3 * X[:, 1] > 0, 1, -1)
+    return X, {0: int(y[0]), 5: int(y[5]), 9: int(y[9]), 14: int(y[14])}
+
+
+@pytest.mark.parametrize('ce,k,noise', [(3, 3, 1e-6), (5, 4, 1e-6), (2, 4, 1e-3), (4, 2, 1e-6)])
+def test_change_estimation_subset_matches_the_oracle(ce, k, noise):
+    """ITAL(change_estimation_subset = c) (ital.py:102-108, 227-275): the subset comes from the reference's own draw
+    on the global numpy RNG; every candidate's score of every step within 1e-6 of the oracle's restatement of the
+    kernel's form (oracle/ce_subset.py mi_sub_shared; up to six variables -- beyond that the lattice of the prior
+    differs in its 1e-15 inverse-CDF round-off only), same batch."""
+    from oracle.ital_oracle import OracleITAL
+    X, fb = _subset_problem()
+    kw = dict(length_scale=1.0, noise=noise, change_estimation_subset=ce)
+    gpu, ora = _gpu_learner(X, **kw), OracleITAL(X, **kw)
+    gpu.update(fb)
+    ora.update(fb)
+    np.random.seed(123)
+    state = np.random.get_state()
+    ret = gpu._fetch_change_subset(k, keep_scores=True)
+    np.random.set_state(state)
+    want = ora.fetch_unlabelled(k, forced=ret)
+    assert gpu.last_subset == ora.subset and want == ret
+    for t, tr in enumerate(ora.trace):
+        got = gpu.last_step_scores[t][tr['candidates']]
+        assert not np.any(np.isnan(got)), 'step %d: unscored candidates' % t
+        np.testing.assert_allclose(got, tr['scores'], rtol=2e-6, atol=1e-9, err_msg='step %d' % t)
+        best = float(np.max(tr['scores']))
+        assert tr['scores'][list(tr['candidates']).index(ret[t])] >= best - 1e-9 * max(1.0, abs(best))
+    # the public call draws the same subset and returns the same batch
+    np.random.set_state(state)
+    assert gpu.fetch_unlabelled(k) == ret
+    gpu.close()
+
+
+@pytest.mark.parametrize('name', subset_names())
+def test_change_estimation_subset_matches_the_reference(name):
+    """The goldens of the unmodified reference with change_estimation_subset (make_subset_golden.py): same subset,
+    same batch, every candidate's score of every step within 1e-4 (see test_oracle_golden.py for the tolerance)."""
+    g = load_subset(name)
+    gpu = _gpu_learner(g['X'], length_scale=float(g['length_scale']), var=float(g['var']), noise=float(g['noise']),
+                       change_estimation_subset=int(g['change_estimation_subset']))
+    for fb in g['updates']:
+        gpu.update({int(k): v for k, v in fb.items()})
+    np.random.seed(int(g['seed']))
+    ret = gpu._fetch_change_subset(int(g['k']), keep_scores=True)
+    assert gpu.last_subset == [int(i) for i in g['subset']]
+    assert ret == [int(i) for i in g['ret']]
+    for t, st in enumerate(g['steps']):
+        got = gpu.last_step_scores[t][st['candidates']]
+        np.testing.assert_allclose(got, st['mi'], rtol=1e-4, atol=1e-4, err_msg='step %d' % t)
+    gpu.close()

@@ -67,6 +67,37 @@ class StubShard(object):
         self.restricted = set(order)
         self.calls.append(('restrict', sorted(self.restricted)))
 
+    # -- stepwise protocol (change_estimation_subset) --
+    def set_sub_mode(self, on):
+        self.calls.append(('sub_mode', bool(on)))
+
+    def fetch_begin(self, label_prob, mistake_prob):
+        self.committed = []
+
+    def fetch_commit(self, record):
+        self.committed.append(int(record[0]))
+
+    def fetch_end(self):
+        pass
+
+    def fetch_propose_sub(self, n_batch, only_row):
+        self.calls.append(('propose_sub', n_batch, list(self.committed), int(only_row)))
+        rec = np.zeros(self.record_doubles())
+        cand = [i for i in range(self.n_data) if i not in self.seen and i not in self.committed
+                and (self.restricted is None or i in self.restricted)]
+        if only_row >= 0:
+            cand = [i for i in cand if i == only_row]
+        if not cand:
+            rec[0] = -1
+            return rec
+        score = {i: -abs(i - 10.2) for i in cand}           # peaks at row 10, then 11, 9, 12, ...
+        best = max(cand, key=lambda i: (score[i], -i))
+        rec[0], rec[1] = best, score[best]
+        return rec
+
+    def last_scores(self):
+        return np.full(self.n_local, np.nan)
+
     def fetch(self, k, label_prob, mistake_prob, exhaustive):
         cand = [i for i in range(self.n_data) if i not in self.seen
                 and (self.restricted is None or i in self.restricted)]
@@ -162,7 +193,8 @@ def test_reset_and_unsupported_modes(make):
     L.update({1: 1})
     L.reset()
     assert L.rounds == 0 and L.rel_mean is None and L.get_unseen() == list(range(20))
-    for kw in (dict(change_estimation_subset=3), dict(change_estimation_subset=None)):
+    for kw in (dict(change_estimation_subset=None), dict(change_estimation_subset=3, label_prob=0.5),
+               dict(change_estimation_subset=3, mistake_prob=0.1), dict(change_estimation_subset=12)):
         B = make(**kw)
         B.update({0: 1})
         with pytest.raises(NotImplementedError):
@@ -209,3 +241,26 @@ def test_batch_size_is_validated_before_any_work(make):
     with pytest.raises(NotImplementedError):
         P.fetch_unlabelled(12)
     assert len(P.fetch_unlabelled(11)) == 11
+
+
+def test_change_estimation_subset_draws_like_the_reference_and_scores_members_separately(make):
+    """ital.py:105-106: the subset is np.random.choice(candidates, c, replace=False), sorted, from the global RNG;
+    per greedy step all candidates outside batch + subset are scored in one evaluation, every subset member that is
+    still a candidate in one of its own with itself moved out of the subset (ital.py:516-519)."""
+    L = make(n=20, change_estimation_subset=3)
+    L.update({0: 1, 1: -1})
+    np.random.seed(4)
+    want_subset = sorted(int(i) for i in np.random.choice(list(range(2, 20)), 3, replace=False))
+    np.random.seed(4)
+    ret = L.fetch_unlabelled(2)
+    assert L.last_subset == want_subset
+    assert ret == [10, 11]                                  # the stub's scores peak at row 10, then 11
+    props = [c for c in L._shard.calls if c[0] == 'propose_sub']
+    S = want_subset
+    first = [('propose_sub', 0, S, -1)] + [('propose_sub', 0, [j for j in S if j != i], i) for i in S]
+    assert props[:4] == first
+    sub2 = [i for i in S if i != 10]
+    second = [('propose_sub', 1, [10] + sub2, -1)] + [('propose_sub', 1, [10] + [j for j in sub2 if j != i], i)
+                                                      for i in sub2]
+    assert props[4:] == second
+    assert [c for c in L._shard.calls if c[0] == 'sub_mode'] == [('sub_mode', True), ('sub_mode', False)]

@@ -10,7 +10,7 @@ import numpy as np
 
 import pytest
 
-from conftest import drive, load_golden, load_updpred, updpred_names
+from conftest import drive, load_golden, load_subset, load_updpred, subset_names, updpred_names
 from oracle.ital_oracle import OracleITAL
 
 
@@ -119,3 +119,27 @@ def test_oracle_updated_prediction_matches_reference(name):
         m, c = ora.updated_prediction(pr['feedback'], pr['test'], cov_mode='full')
         np.testing.assert_allclose(m, pr['mean'], rtol=1e-6, atol=1e-9)
         np.testing.assert_allclose(c, pr['cov'], rtol=1e-6, atol=1e-9)
+
+
+SUBSET_ATOL, SUBSET_RTOL = 1e-4, 1e-4
+
+
+@pytest.mark.parametrize('name', subset_names())
+def test_oracle_change_estimation_subset_matches_reference(name):
+    """ITAL(change_estimation_subset = c) of the unmodified reference (tests/golden/make_subset_golden.py): same
+    subset from the same RNG call, same batch, every candidate's score of every step within 1e-4 -- the scores contain
+    logarithms of orthant probabilities down to 1e-3, which magnify the 1e-7 quadrature error of the oracle's rule
+    (the reference's own mvndst(abseps=1e-4) is far noisier there)."""
+    g = load_subset(name)
+    ora = OracleITAL(g['X'], length_scale=float(g['length_scale']), var=float(g['var']), noise=float(g['noise']),
+                     change_estimation_subset=int(g['change_estimation_subset']))
+    for fb in g['updates']:
+        ora.update({int(k): v for k, v in fb.items()})
+    np.testing.assert_allclose(ora.rel_mean, g['rel_mean'], rtol=1e-9, atol=1e-12)
+    np.random.seed(int(g['seed']))
+    ret = ora.fetch_unlabelled(int(g['k']))
+    assert ora.subset == [int(i) for i in g['subset']]
+    assert ret == [int(i) for i in g['ret']]
+    for t, (tr, st) in enumerate(zip(ora.trace, g['steps'])):
+        assert tr['candidates'].tolist() == st['candidates'].tolist()
+        np.testing.assert_allclose(tr['scores'], st['mi'], rtol=SUBSET_RTOL, atol=SUBSET_ATOL, err_msg='step %d' % t)
