@@ -1070,7 +1070,7 @@ bool fused_applies(const ital_shard* s, int exhaustive, bool peer) {
     const int C = fused_chunk_cap(s);
     if (C > kFusedThreads) return false;
     const FusedSmem L(record_doubles(s), s->w_cap, C, s->num_sms);
-    if (L.total * sizeof(double) > 220 * 1024) return false;
+    if (L.total * sizeof(double) > 200 * 1024) return false;
     if (peer && s->xg_world > kFusedThreads) return false;
     return true;
 }

@@ -30,7 +30,6 @@ constexpr int kFusedTeam = 256;
 constexpr int kFusedTeams = kFusedThreads / kFusedTeam;
 constexpr int kFusedWarps = kFusedThreads / 32;
 constexpr int kFusedMaxSteps = 4;               // greedy steps with at most 3 base variables (tensor rule on the device)
-constexpr int kStreamStages = 14;               // node stream of the scoring phases: 8 KB stages in shared memory
 
 struct FusedArgs {
     // pool
@@ -95,7 +94,7 @@ struct FusedArgs {
 
 // shared-memory carve-up of k_fetch_fused, in doubles (host and device use the same numbers)
 struct FusedSmem {
-    size_t recs, uv, red, phi, part, masses, hb, base_m, base_L, ss, si, nd_eta, nd_w, nd_orth, ism, sel_loc, ring, bars, total;
+    size_t recs, uv, red, phi, part, masses, hb, base_m, base_L, ss, si, nd_eta, nd_w, nd_orth, ism, sel_loc, total;
     __host__ __device__ FusedSmem(int64_t rec_len, int w_cap, int C, int n_ctas) {
         size_t o = 0;
         recs = o; o += (size_t)kFusedMaxSteps * rec_len;
@@ -114,9 +113,6 @@ struct FusedSmem {
         nd_orth = o; o += (C + 1) / 2;
         ism = o; o += 128;                      // 256 ints (the first 16 also serve as orthant offsets)
         sel_loc = o; o += kFusedMaxSteps;
-        o = (o + 1) & ~(size_t)1;               // (16-byte aligned: destination of bulk copies)
-        ring = o; o += (size_t)kStreamStages * kNodePad * 4;     // node stream: stages of kNodePad {eta, w} records
-        bars = o; o += 2 * kStreamStages;       // full / empty mbarriers of the stages
         total = o;
     }
 };
@@ -160,160 +156,6 @@ __device__ __noinline__ Best group_argmax(double bs, long long bi, int tid_group
         if (better(ss[w], si[w], r.score, r.idx)) { r.score = ss[w]; r.idx = si[w]; }
     team_barrier(bar_id, nthreads);
     return r;
-}
-
-// ---- node stream ------------------------------------------------------------------------------------------------
-// The node list of a step (up to 256 KB at three base variables) does not fit beside the rest in shared memory, and
-// read with plain loads every candidate pays the L2 latency once per 256 nodes.  Instead the CTA streams it through a
-// ring of kStreamStages 8 KB stages with the bulk-copy engine (cp.async.bulk + mbarrier, as the HBM passes do): chunk
-// c of the endless sequence [list, list, ...] lands in stage c % kStreamStages, thread 0 keeps the ring
-// kStreamStages - 2 chunks ahead, and BOTH teams score their current row against the same chunk, so a pass over the
-// list serves two candidates.  Every warp of the CTA consumes every chunk (a team without a row just releases it).  A
-// thread reads node (chunk * 256 + tid_team): the same nodes in the same order as eval_candidate, so the scores are
-// bit-identical to the multi-kernel path.
-struct NodeStream {
-    double* ring;
-    uint64_t* full;
-    uint64_t* empty;
-    const double* src;      // node list of the step
-    uint32_t n_chunks;      // its length in chunks of kNodePad nodes
-    uint32_t cons;          // chunks consumed so far (every thread counts)
-    uint32_t prod;          // chunks issued so far (thread 0)
-    uint32_t base;          // chunk number at which the running node list started
-};
-
-__device__ __forceinline__ void stream_fill(NodeStream& ns) {         // thread 0 only
-    while (ns.prod + 2 < ns.cons + kStreamStages) {
-        const uint32_t c = ns.prod;
-        const int st = (int)(c % kStreamStages);
-        if (c >= kStreamStages) bar_wait(ns.empty + st, ((c / kStreamStages) - 1) & 1);
-        bulk_issue(ns.ring + (size_t)st * kNodePad * 4, ns.src + (size_t)((c - ns.base) % ns.n_chunks) * kNodePad * 4,
-                   kNodePad * 4 * sizeof(double), ns.full + st);
-        ns.prod = c + 1;
-    }
-}
-
-__device__ __forceinline__ const double2* stream_acquire(NodeStream& ns) {
-    if (threadIdx.x == 0) stream_fill(ns);
-    const int st = (int)(ns.cons % kStreamStages);
-    bar_wait(ns.full + st, (ns.cons / kStreamStages) & 1);
-    return reinterpret_cast<const double2*>(ns.ring + (size_t)st * kNodePad * 4);
-}
-
-__device__ __forceinline__ void stream_release(NodeStream& ns) {
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0)
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(ns.empty + ns.cons % kStreamStages)) : "memory");
-    ns.cons += 1;
-}
-
-// A new node list (written by all CTAs before the last grid barrier): whatever is still in flight of the old one is
-// consumed unused, the sequence restarts at chunk 0 of the new list.
-__device__ __forceinline__ void stream_drain(NodeStream& ns, uint32_t* scratch) {
-    if (threadIdx.x == 0) *scratch = ns.prod;
-    __syncthreads();
-    const uint32_t issued = *scratch;
-    while (ns.cons < issued) {
-        const int st = (int)(ns.cons % kStreamStages);
-        bar_wait(ns.full + st, (ns.cons / kStreamStages) & 1);
-        stream_release(ns);
-    }
-    __syncthreads();
-}
-
-__device__ __forceinline__ void stream_restart(NodeStream& ns, const double* src, uint32_t n_chunks, uint32_t* scratch) {
-    stream_drain(ns, scratch);
-    ns.src = src;
-    ns.n_chunks = n_chunks;
-    ns.base = ns.cons;
-    if (threadIdx.x == 0) {
-        ns.prod = ns.cons;
-        asm volatile("fence.proxy.async;" ::: "memory");              // the list was written with ordinary stores
-    }
-}
-
-// eval_candidate over one pass of the stream; i < 0: this team has no row in this pass and only releases the chunks.
-// Up to four chunks of an orthant are taken at a time, so that a thread has four independent Phi evaluations in flight
-// (the accumulation itself stays one fma chain in node order, as in eval_candidate).
-template <int T>
-__device__ __noinline__ void eval_candidate_stream(const EvalArgs& a, int64_t i, int tid_team, int bar_id, double* red,
-                                                   const double2* phi, const int* gb, const double* masses,
-                                                   double h_base, NodeStream& ns_ref) {
-    constexpr int NB = 1 << T;
-    NodeStream ns = ns_ref;                             // (in registers while the pass runs)
-    double l[3] = {0.0, 0.0, 0.0};
-    double s2 = 0.0, mi = 0.0;
-    if (i >= 0) {
-        s2 = a.v[i];
-#pragma unroll
-        for (int j = 0; j < T; ++j) {
-            l[j] = __ldcg(a.U + (int64_t)(a.W0 + j) * a.ldu + i);
-            s2 = fma(-l[j], l[j], s2);
-        }
-        mi = a.m[i];
-    }
-    const double s = s2 > 0.0 ? sqrt(s2) : 0.0;
-    const double inv_s = s > 0.0 ? 1.0 / s : 0.0;
-    double acc[NB];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-        const int nch = (gb[b + 1] - gb[b]) / kNodePad;
-        double ac = 0.0;
-        for (int c = 0; c < nch; c += 4) {
-            const int g = nch - c < 4 ? nch - c : 4;
-            if (threadIdx.x == 0) stream_fill(ns);
-            const double2* nd[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                nd[u] = nullptr;
-                if (u < g) {
-                    const uint32_t cc = ns.cons + u;
-                    const int st = (int)(cc % kStreamStages);
-                    bar_wait(ns.full + st, (cc / kStreamStages) & 1);
-                    nd[u] = reinterpret_cast<const double2*>(ns.ring + (size_t)st * kNodePad * 4);
-                }
-            }
-            if (i >= 0) {
-                double val[4], wq[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    val[u] = wq[u] = 0.0;
-                    if (u < g) {
-                        const double2 n01 = nd[u][2 * tid_team], n23 = nd[u][2 * tid_team + 1];
-                        double num = fma(l[0], n01.x, mi);
-                        if (T >= 2) num = fma(l[1], n01.y, num);
-                        if (T >= 3) num = fma(l[2], n23.x, num);
-                        val[u] = s > 0.0 ? phi_tab(phi, num * inv_s) : (num > 0.0 ? 1.0 : 0.0);
-                        wq[u] = n23.y;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (u < g) ac = fma(wq[u], val[u], ac);
-            }
-            __syncwarp();
-            if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (u < g)
-                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(ns.empty + (ns.cons + u) % kStreamStages)) : "memory");
-            }
-            ns.cons += g;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ac += __shfl_xor_sync(0xffffffffu, ac, o);
-        acc[b] = ac;
-    }
-    ns_ref = ns;
-    if (i >= 0) eval_epilogue<T>(a, i, tid_team, kFusedTeam, bar_id, red, masses, h_base, acc, s2);
-}
-
-__device__ __forceinline__ void eval_stream_dispatch(int tn, const EvalArgs& a, int64_t i, int tid_team, int bar_id,
-                                                     double* red, const double2* phi, const int* gb,
-                                                     const double* masses, double h_base, NodeStream& ns) {
-    if (tn == 1) eval_candidate_stream<1>(a, i, tid_team, bar_id, red, phi, gb, masses, h_base, ns);
-    else if (tn == 2) eval_candidate_stream<2>(a, i, tid_team, bar_id, red, phi, gb, masses, h_base, ns);
-    else eval_candidate_stream<3>(a, i, tid_team, bar_id, red, phi, gb, masses, h_base, ns);
 }
 
 // One copy of the row-level routines inside the persistent kernel (inlined at every call site they made half a
@@ -385,22 +227,6 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
     int* ism = reinterpret_cast<int*>(fsm + L.ism);                     // [256] small integers
     int* gbeg = ism + 16;                                               // [9] orthant offsets of the step's nodes
     long long* sel_loc = reinterpret_cast<long long*>(fsm + L.sel_loc); // [4] local rows selected so far (-1: remote)
-    NodeStream ns;
-    ns.ring = fsm + L.ring;
-    ns.full = reinterpret_cast<uint64_t*>(fsm + L.bars);
-    ns.empty = ns.full + kStreamStages;
-    ns.src = a.nodes4;
-    ns.n_chunks = 1;
-    ns.cons = ns.prod = ns.base = 0;
-    uint32_t* stream_scratch = reinterpret_cast<uint32_t*>(ism + 56);
-    if (tid == 0) {
-        for (int k = 0; k < kStreamStages; ++k) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(ns.full + k)) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(ns.empty + k)), "r"(kFusedWarps) : "memory");
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
 
     if (blockIdx.x == 0 && tid < 4) {
         a.counters[tid] = 0;
@@ -697,7 +523,6 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
                 }
             }
             if (blockIdx.x == 0 && tid <= (1 << tn)) a.group_begin[tid] = gbeg[tid];
-            asm volatile("fence.proxy.async;" ::: "memory");          // the node list is read back by bulk copies
         }
         FUSED_MARK();
         grid_barrier(a.barrier, target);
@@ -742,13 +567,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
                 if (tid < 2) a.hbase[tid] = hb[tid];
                 if (tid == 2) a.counters[3] = NK;
             }
-            stream_restart(ns, a.nodes4, (uint32_t)(gbeg[1 << tn] / kNodePad), stream_scratch);
-            {
-                const bool need = a_row >= 0 && tag_step(__ldcg(a.tags + a_row), a.epoch) != tn;
-                if (tid_team == 0) ism[52 + team] = need;
-                __syncthreads();
-                if (ism[52] | ism[53])      // one pass over the node list serves the rows of both teams
-                    eval_stream_dispatch(tn, ea, need ? a_row : -1, tid_team, team_bar, red, phi_s, gbeg, masses, hb[0], ns);
+            if (a_row >= 0 && tag_step(__ldcg(a.tags + a_row), a.epoch) != tn) {
+                eval_dispatch(tn, ea, a_row, tid_team, kFusedTeam, team_bar, red, phi_s, gbeg, masses, hb[0]);
             }
         }
         FUSED_MARK();
@@ -814,27 +634,22 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
                 if (n_items < 24 * (int)gridDim.x) {
                     // few rows: a 256-thread team per row; the projections of eight rows of a team are brought up to date
                     // by its eight warps at once (all their loads in flight), then the rows are scored one after the other
-                    const int gt0 = blockIdx.x * kFusedTeams;
-                    for (int r0 = 0; gt0 + (int64_t)r0 * n_teams < n_items; r0 += 8) {
+                    for (int r0 = 0; gt + (int64_t)r0 * n_teams < n_items; r0 += 8) {
                         const int64_t item_w = gt + (int64_t)(r0 + warp_team) * n_teams;
                         if (item_w < n_items) {
                             const int64_t i = __ldcg(a.worklist + item_w);
                             catchup_row_call<XT>(i, lane, X, a.d, a.d_pad, recs, a.rec_len, a.w_cap, a.W, tn, a.sqn, a.U,
                                             a.ldu, a.tags, a.epoch, a.var, a.neg2ls2, uv);
                         }
-                        __syncthreads();
+                        team_barrier(team_bar, kFusedTeam);
                         for (int rr = 0; rr < 8; ++rr) {
-                            if (gt0 + (int64_t)(r0 + rr) * n_teams >= n_items) break;      // (the same for both teams)
                             const int64_t item = gt + (int64_t)(r0 + rr) * n_teams;
-                            const int64_t i = item < n_items ? __ldcg(a.worklist + item) : -1;
-                            const bool need = i >= 0 && tag_step(__ldcg(a.tags + i), a.epoch) != tn;
-                            int* fl = ism + 52 + 2 * (rr & 1);
-                            if (tid_team == 0) fl[team] = need;
-                            __syncthreads();
-                            if (fl[0] | fl[1])  // one pass over the node list serves the rows of both teams
-                                eval_stream_dispatch(tn, ea, need ? i : -1, tid_team, team_bar, red, phi_s, gbeg, masses,
-                                                     hb[0], ns);
-                            if (tid_team == 0 && i >= 0) {
+                            if (item >= n_items) break;
+                            const int64_t i = __ldcg(a.worklist + item);
+                            if (tag_step(__ldcg(a.tags + i), a.epoch) != tn) {
+                                eval_dispatch(tn, ea, i, tid_team, kFusedTeam, team_bar, red, phi_s, gbeg, masses, hb[0]);
+                            }
+                            if (tid_team == 0) {
                                 const double s = __ldcg(a.score + i);
                                 if (better(s, i, bs, bi)) { bs = s; bi = i; }
                             }
@@ -882,7 +697,6 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
         }
         FUSED_MARK();
     }
-    stream_drain(ns, stream_scratch);                                  // no bulk copy may be in flight at exit
 #undef FUSED_MARK
 }
 

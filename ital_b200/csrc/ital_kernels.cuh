@@ -1257,49 +1257,6 @@ __host__ __device__ __forceinline__ int pad_nodes(int cnt) { return (cnt + kNode
 // team size only.  `red` holds 8 * 2^T doubles per team; `phi` is the table of phi_tab (shared memory); `gb` the
 // orthant offsets and `masses` the base orthant masses (shared or global memory).  Returns after the row's score,
 // gain and tag are written.
-// The tail of a candidate's score: the per-warp orthant sums `acc` are added over the team in a fixed order, lane b
-// finishes orthant b, lane 0 adds the terms in ascending order of b and writes score, gain and tag.
-template <int T>
-__device__ __forceinline__ void eval_epilogue(const EvalArgs& a, int64_t i, int tid_team, int TPC, int bar_id, double* red,
-                                              const double* masses, double h_base, const double* acc, double s2) {
-    constexpr int NB = 1 << T;
-    if (TPC > 32) {
-        if ((tid_team & 31) == 0) {
-#pragma unroll
-            for (int b = 0; b < NB; ++b) red[b * 8 + (tid_team >> 5)] = acc[b];
-        }
-        team_barrier(bar_id, TPC);
-    }
-    if (tid_team < 32) {
-        // lane b of the team's first warp finishes orthant b (its two logarithms); lane 0 adds the terms in
-        // ascending order of b
-        double p_plus = 0.0;
-        if (TPC > 32) {
-            if (tid_team < NB)
-                for (int k = 0; k < TPC / 32; ++k) p_plus += red[tid_team * 8 + k];
-        } else {
-#pragma unroll
-            for (int b = 0; b < NB; ++b) p_plus = (tid_team == b) ? acc[b] : p_plus;
-        }
-        double term = 0.0;
-        if (tid_team < NB) {
-            const double p_minus = fmax(masses[tid_team] - p_plus, 0.0);
-            term = mi_term(p_plus, a.log1p_eps) + mi_term(p_minus, a.log1p_eps);
-        }
-        double sc = 0.0;
-#pragma unroll
-        for (int b = 0; b < NB; ++b) sc += __shfl_sync(0xffffffffu, term, b);
-        if (tid_team == 0) {
-            a.tags[i] = tag_with_step(__ldcg(a.tags + i), a.epoch, a.t);
-            a.score[i] = sc;
-            a.gain[i] = sc - h_base;
-            atomicAdd(a.n_scored, 1);
-            if (s2 < a.flag_var) atomicAdd(a.n_flagged, 1);
-        }
-    }
-    if (TPC > 32) team_barrier(bar_id, TPC);            // red and the tag are free again
-}
-
 template <int T>
 __device__ __forceinline__ void eval_candidate(const EvalArgs& a, int64_t i, int tid_team, int TPC, int bar_id,
                                                double* red, const double2* phi, const int* gb, const double* masses,
@@ -1343,7 +1300,41 @@ __device__ __forceinline__ void eval_candidate(const EvalArgs& a, int64_t i, int
         for (int o = 16; o > 0; o >>= 1) ac += __shfl_xor_sync(0xffffffffu, ac, o);
         acc[b] = ac;
     }
-    eval_epilogue<T>(a, i, tid_team, TPC, bar_id, red, masses, h_base, acc, s2);
+    if (TPC > 32) {
+        if ((tid_team & 31) == 0) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) red[b * 8 + (tid_team >> 5)] = acc[b];
+        }
+        team_barrier(bar_id, TPC);
+    }
+    if (tid_team < 32) {
+        // lane b of the team's first warp finishes orthant b (its two logarithms); lane 0 adds the terms in
+        // ascending order of b
+        double p_plus = 0.0;
+        if (TPC > 32) {
+            if (tid_team < NB)
+                for (int k = 0; k < TPC / 32; ++k) p_plus += red[tid_team * 8 + k];
+        } else {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) p_plus = (tid_team == b) ? acc[b] : p_plus;
+        }
+        double term = 0.0;
+        if (tid_team < NB) {
+            const double p_minus = fmax(masses[tid_team] - p_plus, 0.0);
+            term = mi_term(p_plus, a.log1p_eps) + mi_term(p_minus, a.log1p_eps);
+        }
+        double sc = 0.0;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) sc += __shfl_sync(0xffffffffu, term, b);
+        if (tid_team == 0) {
+            a.tags[i] = tag_with_step(__ldcg(a.tags + i), a.epoch, a.t);
+            a.score[i] = sc;
+            a.gain[i] = sc - h_base;
+            atomicAdd(a.n_scored, 1);
+            if (s2 < a.flag_var) atomicAdd(a.n_flagged, 1);
+        }
+    }
+    if (TPC > 32) team_barrier(bar_id, TPC);            // red and the tag are free again
 }
 
 template <int T>
