@@ -1257,6 +1257,49 @@ __host__ __device__ __forceinline__ int pad_nodes(int cnt) { return (cnt + kNode
 // team size only.  `red` holds 8 * 2^T doubles per team; `phi` is the table of phi_tab (shared memory); `gb` the
 // orthant offsets and `masses` the base orthant masses (shared or global memory).  Returns after the row's score,
 // gain and tag are written.
+// The tail of a candidate's score: the per-warp orthant sums `acc` are added over the team in a fixed order, lane b
+// finishes orthant b, lane 0 adds the terms in ascending order of b and writes score, gain and tag.
+template <int T>
+__device__ __forceinline__ void eval_epilogue(const EvalArgs& a, int64_t i, int tid_team, int TPC, int bar_id, double* red,
+                                              const double* masses, double h_base, const double* acc, double s2) {
+    constexpr int NB = 1 << T;
+    if (TPC > 32) {
+        if ((tid_team & 31) == 0) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) red[b * 8 + (tid_team >> 5)] = acc[b];
+        }
+        team_barrier(bar_id, TPC);
+    }
+    if (tid_team < 32) {
+        // lane b of the team's first warp finishes orthant b (its two logarithms); lane 0 adds the terms in
+        // ascending order of b
+        double p_plus = 0.0;
+        if (TPC > 32) {
+            if (tid_team < NB)
+                for (int k = 0; k < TPC / 32; ++k) p_plus += red[tid_team * 8 + k];
+        } else {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) p_plus = (tid_team == b) ? acc[b] : p_plus;
+        }
+        double term = 0.0;
+        if (tid_team < NB) {
+            const double p_minus = fmax(masses[tid_team] - p_plus, 0.0);
+            term = mi_term(p_plus, a.log1p_eps) + mi_term(p_minus, a.log1p_eps);
+        }
+        double sc = 0.0;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) sc += __shfl_sync(0xffffffffu, term, b);
+        if (tid_team == 0) {
+            a.tags[i] = tag_with_step(__ldcg(a.tags + i), a.epoch, a.t);
+            a.score[i] = sc;
+            a.gain[i] = sc - h_base;
+            atomicAdd(a.n_scored, 1);
+            if (s2 < a.flag_var) atomicAdd(a.n_flagged, 1);
+        }
+    }
+    if (TPC > 32) team_barrier(bar_id, TPC);            // red and the tag are free again
+}
+
 template <int T>
 __device__ __forceinline__ void eval_candidate(const EvalArgs& a, int64_t i, int tid_team, int TPC, int bar_id,
                                                double* red, const double2* phi, const int* gb, const double* masses,
@@ -1300,41 +1343,56 @@ __device__ __forceinline__ void eval_candidate(const EvalArgs& a, int64_t i, int
         for (int o = 16; o > 0; o >>= 1) ac += __shfl_xor_sync(0xffffffffu, ac, o);
         acc[b] = ac;
     }
-    if (TPC > 32) {
-        if ((tid_team & 31) == 0) {
+    eval_epilogue<T>(a, i, tid_team, TPC, bar_id, red, masses, h_base, acc, s2);
+}
+
+// Two candidates per warp against ONE pass over the node list (exhaustive scoring, where there are far more candidates
+// than warps): every node is loaded once and feeds two independent Phi evaluations, which halves the L2 traffic of the
+// node list (262 KB per pass at three base variables, more than the L1 keeps) and doubles the work in flight per
+// load.  Each candidate's sums are formed in the same order as in eval_candidate: bit-identical scores.
+template <int T>
+__device__ __forceinline__ void eval_candidate_pair(const EvalArgs& a, int64_t i0, int64_t i1, int lane, const double2* phi,
+                                                    const int* gb, const double* masses, double h_base) {
+    constexpr int NB = 1 << T;
+    double l0[3] = {0.0, 0.0, 0.0}, l1[3] = {0.0, 0.0, 0.0};
+    double s20 = a.v[i0], s21 = a.v[i1];
 #pragma unroll
-            for (int b = 0; b < NB; ++b) red[b * 8 + (tid_team >> 5)] = acc[b];
-        }
-        team_barrier(bar_id, TPC);
+    for (int j = 0; j < T; ++j) {
+        l0[j] = __ldcg(a.U + (int64_t)(a.W0 + j) * a.ldu + i0);
+        l1[j] = __ldcg(a.U + (int64_t)(a.W0 + j) * a.ldu + i1);
+        s20 = fma(-l0[j], l0[j], s20);
+        s21 = fma(-l1[j], l1[j], s21);
     }
-    if (tid_team < 32) {
-        // lane b of the team's first warp finishes orthant b (its two logarithms); lane 0 adds the terms in
-        // ascending order of b
-        double p_plus = 0.0;
-        if (TPC > 32) {
-            if (tid_team < NB)
-                for (int k = 0; k < TPC / 32; ++k) p_plus += red[tid_team * 8 + k];
-        } else {
+    const double m0 = a.m[i0], m1 = a.m[i1];
+    const double s0 = s20 > 0.0 ? sqrt(s20) : 0.0, s1 = s21 > 0.0 ? sqrt(s21) : 0.0;
+    const double inv0 = s0 > 0.0 ? 1.0 / s0 : 0.0, inv1 = s1 > 0.0 ? 1.0 / s1 : 0.0;
+    const double2* nd = reinterpret_cast<const double2*>(a.nodes4);
+    double acc0[NB], acc1[NB];
 #pragma unroll
-            for (int b = 0; b < NB; ++b) p_plus = (tid_team == b) ? acc[b] : p_plus;
+    for (int b = 0; b < NB; ++b) {
+        const int g0 = gb[b], g1 = gb[b + 1];
+        double ac0 = 0.0, ac1 = 0.0;
+#pragma unroll 2
+        for (int q = g0 + lane; q < g1; q += 32) {
+            const double2 n01 = nd[2 * q], n23 = nd[2 * q + 1];
+            double num0 = fma(l0[0], n01.x, m0), num1 = fma(l1[0], n01.x, m1);
+            if (T >= 2) { num0 = fma(l0[1], n01.y, num0); num1 = fma(l1[1], n01.y, num1); }
+            if (T >= 3) { num0 = fma(l0[2], n23.x, num0); num1 = fma(l1[2], n23.x, num1); }
+            const double c0 = s0 > 0.0 ? phi_tab(phi, num0 * inv0) : (num0 > 0.0 ? 1.0 : 0.0);
+            const double c1 = s1 > 0.0 ? phi_tab(phi, num1 * inv1) : (num1 > 0.0 ? 1.0 : 0.0);
+            ac0 = fma(n23.y, c0, ac0);
+            ac1 = fma(n23.y, c1, ac1);
         }
-        double term = 0.0;
-        if (tid_team < NB) {
-            const double p_minus = fmax(masses[tid_team] - p_plus, 0.0);
-            term = mi_term(p_plus, a.log1p_eps) + mi_term(p_minus, a.log1p_eps);
-        }
-        double sc = 0.0;
 #pragma unroll
-        for (int b = 0; b < NB; ++b) sc += __shfl_sync(0xffffffffu, term, b);
-        if (tid_team == 0) {
-            a.tags[i] = tag_with_step(__ldcg(a.tags + i), a.epoch, a.t);
-            a.score[i] = sc;
-            a.gain[i] = sc - h_base;
-            atomicAdd(a.n_scored, 1);
-            if (s2 < a.flag_var) atomicAdd(a.n_flagged, 1);
+        for (int o = 16; o > 0; o >>= 1) {
+            ac0 += __shfl_xor_sync(0xffffffffu, ac0, o);
+            ac1 += __shfl_xor_sync(0xffffffffu, ac1, o);
         }
+        acc0[b] = ac0;
+        acc1[b] = ac1;
     }
-    if (TPC > 32) team_barrier(bar_id, TPC);            // red and the tag are free again
+    eval_epilogue<T>(a, i0, lane, 32, 0, nullptr, masses, h_base, acc0, s20);
+    eval_epilogue<T>(a, i1, lane, 32, 0, nullptr, masses, h_base, acc1, s21);
 }
 
 template <int T>
@@ -1354,6 +1412,19 @@ __global__ void __launch_bounds__(256) k_eval(EvalArgs a) {
     phi_tab_to_shared(phi_s, a.phi);
     if (threadIdx.x <= NB) gb[threadIdx.x] = a.group_begin[threadIdx.x];
     __syncthreads();
+    if (TPC == 32 && n_items >= 2 * teams_total) {
+        // far more candidates than warps: two per warp and pass over the node list
+        for (int p = team_global; 2 * p < n_items; p += teams_total) {
+            const int64_t i0 = a.list[2 * p];
+            const int64_t i1 = 2 * p + 1 < n_items ? a.list[2 * p + 1] : -1;
+            const bool do0 = tag_step(a.tags[i0], a.epoch) != a.t;
+            const bool do1 = i1 >= 0 && tag_step(a.tags[i1], a.epoch) != a.t;
+            if (do0 && do1) eval_candidate_pair<T>(a, i0, i1, tid_team, phi_s, gb, a.masses, h_base);
+            else if (do0) eval_candidate<T>(a, i0, tid_team, TPC, 0, red, phi_s, gb, a.masses, h_base);
+            else if (do1) eval_candidate<T>(a, i1, tid_team, TPC, 0, red, phi_s, gb, a.masses, h_base);
+        }
+        return;
+    }
     for (int item = team_global; item < n_items; item += teams_total) {
         const int64_t i = a.list[item];
         if (tag_step(a.tags[i], a.epoch) == a.t) continue;  // scored earlier in this step (team-uniform)
