@@ -150,6 +150,10 @@ struct ital_shard {
     double *sb_eta = nullptr, *sb_w = nullptr, *sb_small = nullptr;
     int* sb_begin = nullptr;
     size_t sb_cap_eta = 0, sb_cap_w = 0, sb_cap_small = 0, sb_cap_begin = 0;
+    // sequential-conditioning lattice generated on the device (t >= 6): scratch
+    double* sc_dbl = nullptr;        // P[1024] | chunk_sum[4096]
+    int* sc_int = nullptr;           // cnt[1024] | chunk_orth[4096] | chunk_off[4096] | n_chunks
+    bool device_lattice = true;      // (ITAL_B200_DEVICE_LATTICE=0: host generation, for A/B comparisons)
     bool sub_mode = false;           // the batch columns hold ext = [batch, subset]: no look-ahead for a next greedy step
 
     int w_cap = 0;                   // allocated projection columns
@@ -633,6 +637,47 @@ int prepare_nodes(ital_shard* s) {
         pdl(k_snq_finalize, 1, 1024, fsm, s)(t, N, snq::kWMin, s->eta_raw, s->w_raw, s->orth_raw, s->eta_dev,
                                              s->group_dev, s->log1p_eps, s->masses_dev, s->hbase_dev, s->counters + 3,
                                              s->num_sms); s->launches++;
+        CU(cudaGetLastError());
+        return ITAL_OK;
+    }
+    if (t >= snq::kScFrom && s->device_lattice) {
+        // the lattice inside every base orthant, generated where the batch state lives: nothing waits for the host
+        if (!s->sc_dbl) {
+            CU(cudaMalloc(&s->sc_dbl, (1024 + 4096) * sizeof(double)));
+            CU(cudaMalloc(&s->sc_int, (1024 + 2 * 4096 + 1) * sizeof(int)));
+        }
+        static const int primes[12] = {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37};
+        ScArgs a;
+        a.t = t;
+        for (int j = 0; j < 12; ++j) {
+            const double r = std::sqrt((double)primes[j]);
+            a.alpha[j] = r - std::floor(r);
+        }
+        a.base_m = s->base_m_dev;
+        a.base_L = s->base_L_dev;
+        a.n_total = snq::kScN;
+        a.pilot = snq::kScPilot;
+        a.n_min = snq::kScMin;
+        a.p_min = snq::kScPMin;
+        a.stride = N;
+        a.P = s->sc_dbl;
+        a.chunk_sum = s->sc_dbl + 1024;
+        a.cnt = s->sc_int;
+        a.chunk_orth = s->sc_int + 1024;
+        a.chunk_off = s->sc_int + 1024 + 4096;
+        a.n_chunks = s->sc_int + 1024 + 2 * 4096;
+        a.group_begin = s->group_dev;
+        a.eta = s->eta_dev;
+        a.w = s->w_dev;
+        a.masses = s->masses_dev;
+        a.hbase = s->hbase_dev;
+        a.log1p_eps = s->log1p_eps;
+        const int nb = 1 << t;
+        pdl(k_sc_pilot, nb, 256, 0, s)(a); s->launches++;
+        pdl(k_sc_alloc, 1, 1024, 0, s)(a); s->launches++;
+        pdl(k_sc_generate, std::min(4096, 8 * s->num_sms), 256, 0, s)(a); s->launches++;
+        pdl(k_sc_masses, 1, 1024, 0, s)(a); s->launches++;
+        pdl(k_sc_scale, 2 * s->num_sms, 256, 0, s)(a); s->launches++;
         CU(cudaGetLastError());
         return ITAL_OK;
     }
@@ -1192,7 +1237,7 @@ void free_all(ital_shard* s) {
     void* ptrs[] = {s->X, s->sqn, s->m, s->v, s->U, s->gain, s->score, s->mask, s->worklist, s->counters,
                     s->block_best, s->best, s->thr_dev, s->rec_dev, s->rec_in_dev, s->idx_dev, s->eta_dev,
                     s->w_dev, s->masses_dev, s->group_dev, s->orth_dev, s->eta_raw, s->w_raw, s->orth_raw, s->gl_dev, s->phi_dev, s->htab_dev, s->base_m_dev, s->base_L_dev, s->sel_dev,
-                    s->hbase_dev, s->tags, s->f_best, s->f_cnt, s->f_stage, s->f_mass, s->f_bar, s->f_trace, s->rec_hist, s->mext_dev, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->sb_eta, s->sb_w, s->sb_small, s->sb_begin, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev, s->beta_dev, s->upd_idx_dev, s->upd_y_dev,
+                    s->hbase_dev, s->tags, s->f_best, s->f_cnt, s->f_stage, s->f_mass, s->f_bar, s->f_trace, s->rec_hist, s->mext_dev, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->sb_eta, s->sb_w, s->sb_small, s->sb_begin, s->sc_dbl, s->sc_int, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev, s->beta_dev, s->upd_idx_dev, s->upd_y_dev,
                     s->sort_keys, s->sort_rows, s->sort_hist, s->sort_out_idx, s->sort_out_val};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -1252,6 +1297,7 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
     if (const char* env = std::getenv("ITAL_B200_PDL")) s->pdl = env[0] != '0';    // (A/B comparisons)
     if (const char* env = std::getenv("ITAL_B200_OVERLAP")) s->overlap = env[0] != '0';
     if (const char* env = std::getenv("ITAL_B200_FUSED")) s->fused = env[0] != '0';
+    if (const char* env = std::getenv("ITAL_B200_DEVICE_LATTICE")) s->device_lattice = env[0] != '0';
     if (const char* env = std::getenv("ITAL_B200_RESERVE")) s->reserve_sms = std::max(1, std::min(64, atoi(env)));
     s->ldu = (n_local + 31) / 32 * 32;
     s->ls = length_scale;

@@ -2003,6 +2003,210 @@ __global__ void __launch_bounds__(256) k_eval_sub(SubArgs a) {
     }
 }
 
+// ---- sequential-conditioning lattice on the device (t >= 6 base variables; same rule as snq_host.h generate_sc) ----
+// inverse of the standard normal CDF: Abramowitz-Stegun 26.2.23 start, Halley steps on 0.5 erfc(-x / sqrt 2)
+__device__ __forceinline__ double ndtri_dev(double p) {
+    const bool lower = p < 0.5;
+    const double pp = lower ? p : 1.0 - p;
+    const double tt = sqrt(-2.0 * log(pp));
+    double x = tt - (2.515517 + 0.802853 * tt + 0.010328 * tt * tt) /
+                        (1.0 + 1.432788 * tt + 0.189269 * tt * tt + 0.001308 * tt * tt * tt);
+    x = lower ? -x : x;
+    for (int it = 0; it < 6; ++it) {
+        const double cdf = 0.5 * erfc(-x * 0.70710678118654752440);
+        const double pdf = exp(-0.5 * x * x) * 0.39894228040143267794;
+        const double f = cdf - p;
+        const double dx = f / (pdf + 0.5 * x * f);
+        x -= dx;
+        if (fabs(dx) < 1e-15 * (1.0 + fabs(x))) break;
+    }
+    return x;
+}
+
+struct ScArgs {
+    int t;
+    double alpha[12];               // fractional parts of the square roots of the first primes (Kronecker sequence)
+    const double* base_m;
+    const double* base_L;           // [t][kBaseStride]
+    int64_t n_total;                // node budget over all orthants (kScN)
+    int pilot, n_min;               // kScPilot, kScMin
+    double p_min;                   // kScPMin
+    int64_t stride;                 // of the dimension-major coordinates (capacity)
+    double* P;                      // [2^t] pilot masses
+    int* cnt;                       // [2^t]
+    int* group_begin;               // [2^t + 1]
+    int* chunk_orth;                // per chunk of up to 256 nodes: orthant, offset within the orthant
+    int* chunk_off;
+    int* n_chunks;
+    double* chunk_sum;
+    double* eta;
+    double* w;
+    double* masses;
+    double* hbase;                  // {H(base), total mass}
+    double log1p_eps;
+};
+
+// node k of N inside orthant b: coordinates into e[], returns the weight
+__device__ __forceinline__ double sc_node(const ScArgs& a, const double* bm, const double* bL, int b, int64_t k,
+                                          int64_t N, double* e) {
+    double wk = 1.0 / (double)N;
+    for (int j = 0; j < a.t; ++j) {
+        double u = ((double)k + 0.5) * a.alpha[j];
+        u -= floor(u);
+        u = 1.0 - fabs(2.0 * u - 1.0);
+        double acc = bm[j];
+        for (int i = 0; i < j; ++i) acc += bL[j * kBaseStride + i] * e[i];
+        const double av = -acc / bL[j * kBaseStride + j];
+        if ((b >> j) & 1) {                             // z_j > 0: eta_j above the boundary
+            const double q = 0.5 * erfc(av * 0.70710678118654752440);
+            const double p = u * q;
+            e[j] = -ndtri_dev(p < 1e-300 ? 1e-300 : p);
+            wk *= q;
+        } else {
+            const double q = 0.5 * erfc(-av * 0.70710678118654752440);
+            const double p = u * q;
+            e[j] = ndtri_dev(p < 1e-300 ? 1e-300 : p);
+            wk *= q;
+        }
+    }
+    return wk;
+}
+
+__device__ __forceinline__ double block_sum_fixed(double x, double* red) {     // 256 threads, fixed order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;
+    __syncthreads();
+    double tot = 0.0;
+    for (int k = 0; k < 8; ++k) tot += red[k];
+    return tot;
+}
+
+// pilot pass: one block per orthant, one pilot node per thread
+__global__ void __launch_bounds__(256) k_sc_pilot(ScArgs a) {
+    pdl_enter();
+    __shared__ double red[8];
+    __shared__ double bm[16], bL[16 * kBaseStride];
+    for (int k = threadIdx.x; k < 16 * kBaseStride; k += 256) bL[k] = a.base_L[k];
+    if (threadIdx.x < 16) bm[threadIdx.x] = a.base_m[threadIdx.x];
+    __syncthreads();
+    double e[12];
+    const double wk = (int)threadIdx.x < a.pilot ? sc_node(a, bm, bL, blockIdx.x, threadIdx.x, a.pilot, e) : 0.0;
+    const double tot = block_sum_fixed(wk, red);
+    if (threadIdx.x == 0) a.P[blockIdx.x] = tot;
+}
+
+// node counts per orthant in proportion to the pilot masses, offsets, list of chunks (one block)
+__global__ void __launch_bounds__(1024) k_sc_alloc(ScArgs a) {
+    pdl_enter();
+    __shared__ double s_total;
+    __shared__ int s_cnt[1024];
+    const int nb = 1 << a.t;
+    if (threadIdx.x == 0) {
+        double total = 0.0;
+        for (int b = 0; b < nb; ++b) total += a.P[b];
+        s_total = total;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nb) {
+        const double Pb = a.P[threadIdx.x];
+        int c = 0;
+        if (Pb >= a.p_min) {
+            c = (int)floor((double)a.n_total * Pb / s_total + 0.5);
+            if (c < a.n_min) c = a.n_min;
+        }
+        s_cnt[threadIdx.x] = c;
+        a.cnt[threadIdx.x] = c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int pos = 0, nc = 0;
+        for (int b = 0; b < nb; ++b) {
+            a.group_begin[b] = pos;
+            for (int off = 0; off < s_cnt[b]; off += 256) {
+                a.chunk_orth[nc] = b;
+                a.chunk_off[nc] = off;
+                ++nc;
+            }
+            pos += s_cnt[b];
+        }
+        a.group_begin[nb] = pos;
+        *a.n_chunks = nc;
+    }
+}
+
+// the nodes: one block per chunk of up to 256 nodes of one orthant
+__global__ void __launch_bounds__(256) k_sc_generate(ScArgs a) {
+    pdl_enter();
+    __shared__ double red[8];
+    __shared__ double bm[16], bL[16 * kBaseStride];
+    for (int k = threadIdx.x; k < 16 * kBaseStride; k += 256) bL[k] = a.base_L[k];
+    if (threadIdx.x < 16) bm[threadIdx.x] = a.base_m[threadIdx.x];
+    __syncthreads();
+    const int nc = *a.n_chunks;
+    for (int c = blockIdx.x; c < nc; c += gridDim.x) {
+        const int b = a.chunk_orth[c], off = a.chunk_off[c];
+        const int N = a.cnt[b];
+        const int k = off + threadIdx.x;
+        double wk = 0.0;
+        if (k < N) {
+            double e[12];
+            wk = sc_node(a, bm, bL, b, k, N, e);
+            const int64_t pos = a.group_begin[b] + k;
+            for (int j = 0; j < a.t; ++j) a.eta[(int64_t)j * a.stride + pos] = e[j];
+            a.w[pos] = wk;
+        }
+        const double tot = block_sum_fixed(wk, red);
+        if (threadIdx.x == 0) a.chunk_sum[c] = tot;
+    }
+}
+
+// orthant masses from the chunk sums (chunk order), total, H(base) of the normalised masses (one block)
+__global__ void __launch_bounds__(1024) k_sc_masses(ScArgs a) {
+    pdl_enter();
+    __shared__ double s_m[1024];
+    __shared__ double s_tot;
+    const int nb = 1 << a.t, nc = *a.n_chunks;
+    if ((int)threadIdx.x < nb) {
+        // the chunks of an orthant are consecutive in the chunk list: find the first by the offsets
+        double sum = 0.0;
+        for (int c = 0; c < nc; ++c)
+            if (a.chunk_orth[c] == (int)threadIdx.x) sum += a.chunk_sum[c];
+        s_m[threadIdx.x] = sum;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int b = 0; b < nb; ++b) tot += s_m[b];
+        s_tot = tot;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nb) {
+        s_m[threadIdx.x] /= s_tot;
+        a.masses[threadIdx.x] = s_m[threadIdx.x];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double h = 0.0, tot = 0.0;
+        for (int b = 0; b < nb; ++b) {
+            h += s_m[b] * (a.log1p_eps - log(s_m[b] + kEps));
+            tot += s_m[b];
+        }
+        a.hbase[0] = h;
+        a.hbase[1] = tot;
+        a.P[0] = s_tot;                                 // (the scale of the weights, for k_sc_scale)
+    }
+}
+
+// the orthant masses must add up to one: scaling the weights accordingly removes the error all node sets share
+__global__ void __launch_bounds__(256) k_sc_scale(ScArgs a) {
+    pdl_enter();
+    const int n = a.group_begin[1 << a.t];
+    const double inv = a.P[0];
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) a.w[k] /= inv;
+}
+
 template <int T>
 __global__ void __launch_bounds__(256) k_snq_generate(int q, double R, int q_min, const double* __restrict__ base_m,
                                                       const double* __restrict__ base_L,

@@ -238,98 +238,119 @@ inline Nodes generate_sc(int t, const double* m, const double* L) {
     return out;
 }
 
-// m[t], L[t*t] row-major lower triangular.
+// m[t], L[t*t] row-major lower triangular.  Node k = sum_j g_j (2q)^(t-1-j) (the digit of the first dimension varies
+// slowest); contiguous index ranges are generated independently over the host cores, each walking its range like an
+// odometer (a dimension is recomputed only when its digit or one before it changes), the kept nodes (weight >= kWMin)
+// are then scattered to their place in the orthant-sorted list, in index order within an orthant.
 inline Nodes generate(int t, const double* m, const double* L, int q = 0, double R = kR) {
     if (q <= 0 && t >= kScFrom) return generate_sc(t, m, L);
     Nodes out;
     out.t = t;
-    const bool qmc = false;
     if (q <= 0) q = order_for(t);
     const int two_q = 2 * q;
-    int64_t n = 1;
-    std::vector<double> eta(0), w(1, 1.0);
-    std::vector<int32_t> orth(1, 0);
+    const int nb = 1 << t;
+    int64_t N = 1;
+    for (int j = 0; j < t; ++j) N *= two_q;
     const GaussLegendre& G = gl();
-    for (int j = 0; j < (qmc ? 0 : t); ++j) {
-        const int64_t n_new = n * two_q;
-        std::vector<double> eta_new((size_t)(j + 1) * n_new), w_new(n_new);
-        std::vector<int32_t> orth_new(n_new);
-        parallel_for(n, 4096, [&](int64_t k_lo, int64_t k_hi) {
-        for (int64_t k = k_lo; k < k_hi; ++k) {
-            double acc = m[j];
-            for (int i = 0; i < j; ++i) acc += eta[(size_t)i * n + k] * L[j * t + i];
-            const double a = -acc / L[j * t + j];
-            const double c = a < -R ? -R : (a > R ? R : a);
-            int n_lo = (int)std::floor(two_q * (c + R) / (2.0 * R) + 0.5);
-            if (n_lo < kQMin) n_lo = kQMin;
-            if (n_lo > two_q - kQMin) n_lo = two_q - kQMin;
-            const int n_hi = two_q - n_lo;
-            const double half_lo = 0.5 * (c + R), half_hi = 0.5 * (R - c);
-            for (int g = 0; g < two_q; ++g) {
-                const int64_t kk = k * two_q + g;
-                double xg, wg;
-                int bit;
-                if (g < n_lo) {
-                    xg = -R + half_lo * (1.0 + G.x[n_lo][g]);
-                    wg = half_lo * G.w[n_lo][g] * phi(xg);
-                    bit = 0;
-                } else {
-                    xg = c + half_hi * (1.0 + G.x[n_hi][g - n_lo]);
-                    wg = half_hi * G.w[n_hi][g - n_lo] * phi(xg);
-                    bit = 1;
+    // chunks of consecutive indices; per chunk the kept nodes in generation order
+    const int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>(1024, N / 2048));
+    struct Chunk {
+        std::vector<double> eta;      // node-major, t per node
+        std::vector<double> w;
+        std::vector<int32_t> orth;
+        std::vector<int32_t> cnt;     // kept per orthant
+    };
+    std::vector<Chunk> chunks(n_chunks);
+    parallel_for(n_chunks, 1, [&](int64_t c_lo, int64_t c_hi) {
+        for (int64_t c = c_lo; c < c_hi; ++c) {
+            Chunk& ch = chunks[c];
+            ch.cnt.assign(nb, 0);
+            const int64_t k_lo = N * c / n_chunks, k_hi = N * (c + 1) / n_chunks;
+            int dig[16], bit[16];
+            double e[16], wpre[17];
+            wpre[0] = 1.0;
+            int from = 0;                                // first dimension whose state is stale
+            for (int64_t k = k_lo; k < k_hi; ++k) {
+                if (k == k_lo) {
+                    int64_t rem = k;
+                    for (int j = t - 1; j >= 0; --j) { dig[j] = (int)(rem % two_q); rem /= two_q; }
+                    from = 0;
                 }
-                for (int i = 0; i < j; ++i) eta_new[(size_t)i * n_new + kk] = eta[(size_t)i * n + k];
-                eta_new[(size_t)j * n_new + kk] = xg;
-                w_new[kk] = w[k] * wg;
-                orth_new[kk] = orth[k] | (bit << j);
+                for (int j = from; j < t; ++j) {
+                    double acc = m[j];
+                    for (int i = 0; i < j; ++i) acc += e[i] * L[j * t + i];
+                    const double a = -acc / L[j * t + j];
+                    const double cc = a < -R ? -R : (a > R ? R : a);
+                    int n_lo = (int)std::floor(two_q * (cc + R) / (2.0 * R) + 0.5);
+                    if (n_lo < kQMin) n_lo = kQMin;
+                    if (n_lo > two_q - kQMin) n_lo = two_q - kQMin;
+                    const int n_hi = two_q - n_lo;
+                    const double half_lo = 0.5 * (cc + R), half_hi = 0.5 * (R - cc);
+                    const int g = dig[j];
+                    double xg, wg;
+                    if (g < n_lo) {
+                        xg = -R + half_lo * (1.0 + G.x[n_lo][g]);
+                        wg = half_lo * G.w[n_lo][g] * phi(xg);
+                        bit[j] = 0;
+                    } else {
+                        xg = cc + half_hi * (1.0 + G.x[n_hi][g - n_lo]);
+                        wg = half_hi * G.w[n_hi][g - n_lo] * phi(xg);
+                        bit[j] = 1;
+                    }
+                    e[j] = xg;
+                    wpre[j + 1] = wpre[j] * wg;
+                }
+                const double wk = wpre[t];
+                if (t == 0 || wk >= kWMin) {
+                    int ob = 0;
+                    for (int j = 0; j < t; ++j) ob |= bit[j] << j;
+                    for (int j = 0; j < t; ++j) ch.eta.push_back(e[j]);
+                    ch.w.push_back(wk);
+                    ch.orth.push_back(ob);
+                    ch.cnt[ob]++;
+                }
+                // odometer: advance the digits, remember the first dimension that changed
+                int j = t - 1;
+                while (j >= 0 && dig[j] == two_q - 1) { dig[j] = 0; --j; }
+                if (j >= 0) dig[j]++;
+                from = j < 0 ? 0 : j;
             }
         }
-        });
-        eta.swap(eta_new);
-        w.swap(w_new);
-        orth.swap(orth_new);
-        n = n_new;
-    }
-    // drop the nodes whose weight is negligible (keeps the generation order)
-    if (t > 0 && !qmc) {
-        int64_t kept = 0;
-        for (int64_t k = 0; k < n; ++k) {
-            if (w[k] < kWMin) continue;
-            for (int i = 0; i < t; ++i) eta[(size_t)i * n + kept] = eta[(size_t)i * n + k];
-            w[kept] = w[k];
-            orth[kept] = orth[k];
-            ++kept;
-        }
-        // re-pack the dimension-major coordinates to the new stride
-        std::vector<double> eta2((size_t)t * kept);
-        for (int i = 0; i < t; ++i)
-            for (int64_t k = 0; k < kept; ++k) eta2[(size_t)i * kept + k] = eta[(size_t)i * n + k];
-        eta.swap(eta2);
-        w.resize(kept);
-        orth.resize(kept);
-        n = kept;
-    }
-    // stable counting sort by orthant
-    const int nb = 1 << t;
-    out.n = n;
+    });
+    // offsets: orthant-major, chunk-minor
     out.group_begin.assign(nb + 1, 0);
-    for (int64_t k = 0; k < n; ++k) out.group_begin[orth[k] + 1]++;
-    for (int b = 0; b < nb; ++b) out.group_begin[b + 1] += out.group_begin[b];
-    std::vector<int32_t> cursor(out.group_begin.begin(), out.group_begin.end() - 1);
-    out.eta.resize((size_t)t * n);
-    out.w.resize(n);
-    out.orth.resize(n);
-    for (int64_t k = 0; k < n; ++k) {
-        const int32_t pos = cursor[orth[k]]++;
-        for (int i = 0; i < t; ++i) out.eta[(size_t)i * n + pos] = eta[(size_t)i * n + k];
-        out.w[pos] = w[k];
-        out.orth[pos] = orth[k];
+    std::vector<int64_t> pos((size_t)n_chunks * nb);
+    int64_t total = 0;
+    for (int b = 0; b < nb; ++b) {
+        out.group_begin[b] = (int32_t)total;
+        for (int64_t c = 0; c < n_chunks; ++c) {
+            pos[(size_t)c * nb + b] = total;
+            total += chunks[c].cnt[b];
+        }
     }
+    out.group_begin[nb] = (int32_t)total;
+    const int64_t n = total;
+    out.n = n;
+    out.eta.assign((size_t)t * n, 0.0);
+    out.w.assign(n, 0.0);
+    out.orth.assign(n, 0);
+    parallel_for(n_chunks, 1, [&](int64_t c_lo, int64_t c_hi) {
+        for (int64_t c = c_lo; c < c_hi; ++c) {
+            const Chunk& ch = chunks[c];
+            std::vector<int64_t> cur(pos.begin() + (size_t)c * nb, pos.begin() + (size_t)(c + 1) * nb);
+            for (size_t k = 0; k < ch.w.size(); ++k) {
+                const int64_t p = cur[ch.orth[k]]++;
+                for (int i = 0; i < t; ++i) out.eta[(size_t)i * n + p] = ch.eta[k * t + i];
+                out.w[p] = ch.w[k];
+                out.orth[p] = ch.orth[k];
+            }
+        }
+    });
     out.masses.assign(nb, 0.0);
     for (int b = 0; b < nb; ++b) {
-        double s = 0.0;
-        for (int32_t k = out.group_begin[b]; k < out.group_begin[b + 1]; ++k) s += out.w[k];
-        out.masses[b] = s;
+        double sum = 0.0;
+        for (int32_t k = out.group_begin[b]; k < out.group_begin[b + 1]; ++k) sum += out.w[k];
+        out.masses[b] = sum;
     }
     // same summand as the candidate scores (ital.py:207-219 with p' = 1), so that gain = score - entropy
     out.entropy = 0.0;
