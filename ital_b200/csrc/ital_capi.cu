@@ -153,6 +153,8 @@ struct ital_shard {
     // sequential-conditioning lattice generated on the device (t >= 6): scratch
     double* sc_dbl = nullptr;        // P[1024] | chunk_sum[4096]
     int* sc_int = nullptr;           // cnt[1024] | chunk_orth[4096] | chunk_off[4096] | n_chunks
+    int* tn_int = nullptr;           // tensor rule on the device (t = 4, 5): kept nodes per block and orthant, their scan
+    size_t tn_cap = 0;
     bool device_lattice = true;      // (ITAL_B200_DEVICE_LATTICE=0: host generation, for A/B comparisons)
     bool sub_mode = false;           // the batch columns hold ext = [batch, subset]: no look-ahead for a next greedy step
 
@@ -637,6 +639,43 @@ int prepare_nodes(ital_shard* s) {
         pdl(k_snq_finalize, 1, 1024, fsm, s)(t, N, snq::kWMin, s->eta_raw, s->w_raw, s->orth_raw, s->eta_dev,
                                              s->group_dev, s->log1p_eps, s->masses_dev, s->hbase_dev, s->counters + 3,
                                              s->num_sms); s->launches++;
+        CU(cudaGetLastError());
+        return ITAL_OK;
+    }
+    if (t < snq::kScFrom && s->device_lattice) {
+        // 4 or 5 base variables: the tensor rule, counted and scattered on the device
+        const int nb = 1 << t;
+        const int n_blocks = (int)((N + 255) / 256);
+        if ((size_t)n_blocks * nb > s->tn_cap) {
+            CU(cudaStreamSynchronize(s->stream));
+            if (s->tn_int) CU(cudaFree(s->tn_int));
+            s->tn_int = nullptr;
+            CU(cudaMalloc(&s->tn_int, (size_t)n_blocks * nb * 2 * sizeof(int)));
+            s->tn_cap = (size_t)n_blocks * nb;
+        }
+        int* blk_cnt = s->tn_int;
+        int* blk_off = s->tn_int + (size_t)n_blocks * nb;
+        const double* glx = s->gl_dev;
+        const double* glw = s->gl_dev + (snq::kMaxOrder + 1) * 64;
+        if (t == 4) {
+            pdl(k_tn_count<4>, n_blocks, 256, 0, s)(q, snq::kR, snq::kQMin, s->base_m_dev, s->base_L_dev, glx, glw, N,
+                                                    snq::kWMin, blk_cnt);
+        } else {
+            pdl(k_tn_count<5>, n_blocks, 256, 0, s)(q, snq::kR, snq::kQMin, s->base_m_dev, s->base_L_dev, glx, glw, N,
+                                                    snq::kWMin, blk_cnt);
+        }
+        s->launches++;
+        pdl(k_tn_scan, 1, 1024, 0, s)(nb, n_blocks, blk_cnt, blk_off, s->group_dev, s->counters + 3); s->launches++;
+        if (t == 4) {
+            pdl(k_tn_scatter<4>, n_blocks, 256, 0, s)(q, snq::kR, snq::kQMin, s->base_m_dev, s->base_L_dev, glx, glw, N,
+                                                      snq::kWMin, blk_off, s->group_dev, N, s->eta_dev, s->w_dev);
+        } else {
+            pdl(k_tn_scatter<5>, n_blocks, 256, 0, s)(q, snq::kR, snq::kQMin, s->base_m_dev, s->base_L_dev, glx, glw, N,
+                                                      snq::kWMin, blk_off, s->group_dev, N, s->eta_dev, s->w_dev);
+        }
+        s->launches++;
+        pdl(k_tn_masses, nb, 256, 0, s)(s->group_dev, s->w_dev, s->masses_dev); s->launches++;
+        pdl(k_tn_hbase, 1, 32, 0, s)(nb, s->masses_dev, s->log1p_eps, s->hbase_dev); s->launches++;
         CU(cudaGetLastError());
         return ITAL_OK;
     }
@@ -1237,7 +1276,7 @@ void free_all(ital_shard* s) {
     void* ptrs[] = {s->X, s->sqn, s->m, s->v, s->U, s->gain, s->score, s->mask, s->worklist, s->counters,
                     s->block_best, s->best, s->thr_dev, s->rec_dev, s->rec_in_dev, s->idx_dev, s->eta_dev,
                     s->w_dev, s->masses_dev, s->group_dev, s->orth_dev, s->eta_raw, s->w_raw, s->orth_raw, s->gl_dev, s->phi_dev, s->htab_dev, s->base_m_dev, s->base_L_dev, s->sel_dev,
-                    s->hbase_dev, s->tags, s->f_best, s->f_cnt, s->f_stage, s->f_mass, s->f_bar, s->f_trace, s->rec_hist, s->mext_dev, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->sb_eta, s->sb_w, s->sb_small, s->sb_begin, s->sc_dbl, s->sc_int, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev, s->beta_dev, s->upd_idx_dev, s->upd_y_dev,
+                    s->hbase_dev, s->tags, s->f_best, s->f_cnt, s->f_stage, s->f_mass, s->f_bar, s->f_trace, s->rec_hist, s->mext_dev, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->sb_eta, s->sb_w, s->sb_small, s->sb_begin, s->sc_dbl, s->sc_int, s->tn_int, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev, s->beta_dev, s->upd_idx_dev, s->upd_y_dev,
                     s->sort_keys, s->sort_rows, s->sort_hist, s->sort_out_idx, s->sort_out_val};
     for (void* p : ptrs)
         if (p) cudaFree(p);

@@ -2003,6 +2003,134 @@ __global__ void __launch_bounds__(256) k_eval_sub(SubArgs a) {
     }
 }
 
+// ---- tensor rule for 4 and 5 base variables on the device ------------------------------------------------------------
+// 331 776 / 3.2 million nodes are generated twice (a node costs a few hundred flops, storing them all would cost more):
+// once to count the kept nodes per orthant and block, once to scatter them to their place in the orthant-sorted,
+// dimension-major list -- generation order within an orthant, like snq_host.h generate().
+template <int T>
+__global__ void __launch_bounds__(256) k_tn_count(int q, double R, int q_min, const double* __restrict__ base_m,
+                                                  const double* __restrict__ base_L, const double* __restrict__ gl_x,
+                                                  const double* __restrict__ gl_w, int64_t N, double w_min,
+                                                  int* __restrict__ blk_cnt) {
+    pdl_enter();
+    constexpr int NB = 1 << T;
+    __shared__ int cnt_s[NB];
+    if (threadIdx.x < NB) cnt_s[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (k < N) {
+        double e[T], wt;
+        int ob;
+        snq_node<T>(k, N, q, R, q_min, base_m, base_L, gl_x, gl_w, e, wt, ob);
+        if (wt >= w_min) atomicAdd(&cnt_s[ob], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < NB) blk_cnt[(int64_t)blockIdx.x * NB + threadIdx.x] = cnt_s[threadIdx.x];
+}
+
+// exclusive scan of the block counts per orthant (a warp per orthant), orthant offsets
+__global__ void __launch_bounds__(1024) k_tn_scan(int nb, int n_blocks, const int* __restrict__ blk_cnt,
+                                                  int* __restrict__ blk_off, int* __restrict__ group_begin,
+                                                  int* __restrict__ n_kept) {
+    pdl_enter();
+    __shared__ int tot[32];
+    const int lane = threadIdx.x & 31, o = threadIdx.x >> 5;
+    if (o < nb) {
+        int run = 0;
+        for (int b0 = 0; b0 < n_blocks; b0 += 32) {
+            const int b = b0 + lane;
+            const int c = b < n_blocks ? blk_cnt[(int64_t)b * nb + o] : 0;
+            int inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += v;
+            }
+            if (b < n_blocks) blk_off[(int64_t)b * nb + o] = run + inc - c;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) tot[o] = run;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int pos = 0;
+        for (int b = 0; b < nb; ++b) { group_begin[b] = pos; pos += tot[b]; }
+        group_begin[nb] = pos;
+        *n_kept = pos;
+    }
+}
+
+template <int T>
+__global__ void __launch_bounds__(256) k_tn_scatter(int q, double R, int q_min, const double* __restrict__ base_m,
+                                                    const double* __restrict__ base_L, const double* __restrict__ gl_x,
+                                                    const double* __restrict__ gl_w, int64_t N, double w_min,
+                                                    const int* __restrict__ blk_off, const int* __restrict__ group_begin,
+                                                    int64_t stride, double* __restrict__ eta, double* __restrict__ w) {
+    pdl_enter();
+    constexpr int NB = 1 << T;
+    __shared__ int warp_cnt[8][NB];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = threadIdx.x; k < 8 * NB; k += 256) (&warp_cnt[0][0])[k] = 0;
+    __syncthreads();
+    const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    double e[T], wt = 0.0;
+    int ob = 0;
+    bool keep = false;
+    if (k < N) {
+        snq_node<T>(k, N, q, R, q_min, base_m, base_L, gl_x, gl_w, e, wt, ob);
+        keep = wt >= w_min;
+    }
+    // rank among the kept nodes of the same orthant with a lower index: within the warp, then over the warps before
+    const unsigned kept_mask = __ballot_sync(0xffffffffu, keep);
+    int rank = 0;
+    if (keep) {
+        const unsigned same = __match_any_sync(kept_mask, ob);
+        rank = __popc(same & ((1u << lane) - 1u));
+        if (rank == 0) warp_cnt[warp][ob] = __popc(same);
+    }
+    __syncthreads();
+    if (keep) {
+        int before = 0;
+        for (int ww = 0; ww < warp; ++ww) before += warp_cnt[ww][ob];
+        const int64_t pos = (int64_t)group_begin[ob] + blk_off[(int64_t)blockIdx.x * NB + ob] + before + rank;
+#pragma unroll
+        for (int j = 0; j < T; ++j) eta[(int64_t)j * stride + pos] = e[j];
+        w[pos] = wt;
+    }
+}
+
+// orthant masses (one block per orthant: fixed strided partial sums, fixed tree), then H(base) and the total mass
+__global__ void __launch_bounds__(256) k_tn_masses(const int* __restrict__ group_begin, const double* __restrict__ w,
+                                                   double* __restrict__ masses) {
+    pdl_enter();
+    __shared__ double red[8];
+    const int g0 = group_begin[blockIdx.x], g1 = group_begin[blockIdx.x + 1];
+    double sum = 0.0;
+    for (int k = g0 + threadIdx.x; k < g1; k += 256) sum += w[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int k = 0; k < 8; ++k) tot += red[k];
+        masses[blockIdx.x] = tot;
+    }
+}
+
+__global__ void k_tn_hbase(int nb, const double* __restrict__ masses, double log1p_eps, double* __restrict__ hbase) {
+    pdl_enter();
+    if (threadIdx.x == 0) {
+        double h = 0.0, tot = 0.0;
+        for (int b = 0; b < nb; ++b) {
+            h += masses[b] * (log1p_eps - log(masses[b] + kEps));
+            tot += masses[b];
+        }
+        hbase[0] = h;
+        hbase[1] = tot;
+    }
+}
+
 // ---- sequential-conditioning lattice on the device (t >= 6 base variables; same rule as snq_host.h generate_sc) ----
 // inverse of the standard normal CDF: Abramowitz-Stegun 26.2.23 start, Halley steps on 0.5 erfc(-x / sqrt 2)
 __device__ __forceinline__ double ndtri_dev(double p) {
