@@ -806,7 +806,10 @@ int launch_eval(ital_shard* s, int64_t items_hint, bool block_per_candidate) {
     if (s->t == 1) pdl(k_eval<1>, blocks, threads, 0, s)(a);
     else if (s->t == 2) pdl(k_eval<2>, blocks, threads, 0, s)(a);
     else if (s->t == 3) pdl(k_eval<3>, blocks, threads, 0, s)(a);
-    else pdl(k_eval_sorted, blocks, threads, 0, s)(a);
+    else {
+        pdl(k_eval_sorted, blocks, threads, 0, s)(a);
+        pdl(k_eval_sorted_pair, blocks, threads, 0, s)(a); s->launches++;      // (one of the two returns at once)
+    }
     s->launches++;
     CU(cudaGetLastError());
     return ITAL_OK;

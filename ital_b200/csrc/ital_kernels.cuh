@@ -1445,6 +1445,93 @@ __device__ __forceinline__ double team_sum(double acc, int TPC, double* red) {
     return acc;
 }
 
+// More candidates than teams (the wide pruning margins of the long-batch rules let thousands of rows through): two
+// candidates per team and pass over the node list.  The list (up to 30 MB) streams from L2 once per pass, which is what
+// bounds the scoring of long batches; each candidate's sums are formed in the same order as in k_eval_sorted.  A
+// kernel of its own so that the extra registers do not cost k_eval_sorted its occupancy.
+__global__ void __launch_bounds__(256) k_eval_sorted_pair(EvalArgs a) {
+    pdl_enter();
+    constexpr int MAXT = 10;
+    const int t = a.t;
+    const int n_items = *a.count;
+    const int TPC = eval_team_size(n_items, a.force_block);
+    const int tid_team = threadIdx.x % TPC;
+    const int team_global = (blockIdx.x * blockDim.x + threadIdx.x) / TPC;
+    const int teams_total = (gridDim.x * blockDim.x) / TPC;
+    const int64_t N = a.n_nodes;
+    __shared__ double red[8];
+    __shared__ double2 phi_s[kPhiTableLen];
+    phi_tab_to_shared(phi_s, a.phi);
+    __syncthreads();
+    if (n_items <= teams_total) return;                // k_eval_sorted takes these
+    {
+        for (int p = team_global; 2 * p < n_items; p += teams_total) {
+            int64_t ii[2] = {a.list[2 * p], 2 * p + 1 < n_items ? a.list[2 * p + 1] : -1};
+            bool todo[2];
+            double l[2][MAXT], s2[2], mi[2], inv_s[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                todo[c] = ii[c] >= 0 && tag_step(a.tags[ii[c]], a.epoch) != a.t;
+                const int64_t i = todo[c] ? ii[c] : a.list[2 * p];
+                s2[c] = a.v[i];
+#pragma unroll
+                for (int j = 0; j < MAXT; ++j) {
+                    l[c][j] = 0.0;
+                    if (j < t) {
+                        l[c][j] = a.U[(int64_t)(a.W0 + j) * a.ldu + i];
+                        s2[c] = fma(-l[c][j], l[c][j], s2[c]);
+                    }
+                }
+                mi[c] = a.m[i];
+                const double sd = s2[c] > 0.0 ? sqrt(s2[c]) : 0.0;
+                inv_s[c] = sd > 0.0 ? 1.0 / sd : 0.0;
+            }
+            if (!todo[0] && !todo[1]) continue;
+            double sc[2] = {0.0, 0.0};
+            const int nb = 1 << t;
+            for (int b = 0; b < nb; ++b) {
+                const int g0 = a.group_begin[b], g1 = a.group_begin[b + 1];
+                double acc[2] = {0.0, 0.0};
+                for (int q = g0 + tid_team; q < g1; q += TPC) {
+                    double num[2] = {mi[0], mi[1]};
+#pragma unroll
+                    for (int j = 0; j < MAXT; ++j)
+                        if (j < t) {
+                            const double ej = a.eta[(int64_t)j * N + q];
+                            num[0] = fma(l[0][j], ej, num[0]);
+                            num[1] = fma(l[1][j], ej, num[1]);
+                        }
+                    const double wq = a.w[q];
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const double cdf = inv_s[c] > 0.0 ? phi_tab(phi_s, num[c] * inv_s[c]) : (num[c] > 0.0 ? 1.0 : 0.0);
+                        acc[c] = fma(wq, cdf, acc[c]);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const double p_plus = team_sum(acc[c], TPC, red);
+                    const double p_minus = fmax(a.masses[b] - p_plus, 0.0);
+                    sc[c] += mi_term(p_plus, a.log1p_eps) + mi_term(p_minus, a.log1p_eps);
+                }
+            }
+            if (TPC > 32) __syncthreads();
+            if (tid_team == 0) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                    if (todo[c]) {
+                        const int64_t i = ii[c];
+                        a.tags[i] = tag_with_step(a.tags[i], a.epoch, a.t);
+                        a.score[i] = sc[c];
+                        a.gain[i] = sc[c] - *a.h_base;
+                        atomicAdd(a.n_scored, 1);
+                        if (s2[c] < a.flag_var) atomicAdd(a.n_flagged, 1);
+                    }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_eval_sorted(EvalArgs a) {
     pdl_enter();
     constexpr int MAXT = 10;
@@ -1459,6 +1546,7 @@ __global__ void __launch_bounds__(256) k_eval_sorted(EvalArgs a) {
     __shared__ double2 phi_s[kPhiTableLen];
     phi_tab_to_shared(phi_s, a.phi);
     __syncthreads();
+    if (n_items > teams_total) return;                 // k_eval_sorted_pair takes these
     for (int item = team_global; item < n_items; item += teams_total) {
         const int64_t i = a.list[item];
         if (tag_step(a.tags[i], a.epoch) == a.t) continue;
