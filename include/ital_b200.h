@@ -136,6 +136,13 @@ int ital_variance_propose(ital_shard* s, int use_correlations, int first_pick_ta
  * the single row only_row >= 0 (a member of S is scored with itself moved out of the subset) -- then ital_fetch_end.
  * Users who label every sample without mistakes, label_estimation 'mean', at most 7 batch samples and 11 columns. */
 int ital_set_sub_mode(ital_shard* s, int on);
+/* ITAL(clip_cov = th) (ital/ital.py:360-362, MutualInformation._grouped_prob_rel ital.py:386-429, group_cov
+ * ital.py:590-616): from the sixth sample of a batch on, correlations of at most th are dropped and the orthant
+ * probability factorises over the resulting groups.  For users who label every sample without mistakes the score of a
+ * candidate is then the entropy of the batch's groups it is not connected to plus the entropy of the group it forms
+ * with the ones it is; every candidate is scored at those steps (no lazy-greedy bound for the clipped model).
+ * th outside (0, 1) turns it off. */
+int ital_set_clip_cov(ital_shard* s, double clip_cov);
 int ital_fetch_propose_sub(ital_shard* s, int n_batch, int64_t only_row, double* record);
 int ital_fetch_end(ital_shard* s);
 int ital_fetch(ital_shard* s, int k, double label_prob, double mistake_prob, int exhaustive,

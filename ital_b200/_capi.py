@@ -43,6 +43,7 @@ SIGNATURES = {
     'ital_fetch_commit': (ctypes.c_int, [_shard_p, _c_double_p]),
     'ital_variance_propose': (ctypes.c_int, [_shard_p, ctypes.c_int, ctypes.c_int, _c_double_p]),
     'ital_set_sub_mode': (ctypes.c_int, [_shard_p, ctypes.c_int]),
+    'ital_set_clip_cov': (ctypes.c_int, [_shard_p, ctypes.c_double]),
     'ital_fetch_propose_sub': (ctypes.c_int, [_shard_p, ctypes.c_int, ctypes.c_int64, _c_double_p]),
     'ital_fetch_end': (ctypes.c_int, [_shard_p]),
     'ital_fetch': (ctypes.c_int, [_shard_p, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int,

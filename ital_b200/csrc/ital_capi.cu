@@ -156,6 +156,15 @@ struct ital_shard {
     int* tn_int = nullptr;           // tensor rule on the device (t = 4, 5): kept nodes per block and orthant, their scan
     size_t tn_cap = 0;
     bool device_lattice = true;      // (ITAL_B200_DEVICE_LATTICE=0: host generation, for A/B comparisons)
+    // clip_cov (grouped orthant probabilities from the sixth sample of a batch on)
+    double clip_cov = 0.0;
+    unsigned short* clip_sub = nullptr;  // [n] union of the batch's groups a candidate is connected to
+    int* clip_int = nullptr;             // present[32] | count2 | comp_mask[16] | gb (grown)
+    double* clip_dbl = nullptr;          // sd_b[16] | mass | T (grown)
+    int* clip_list2 = nullptr;           // [n]
+    void* clip_desc = nullptr;           // ClipDesc[1024]
+    double *clip_eta = nullptr, *clip_w = nullptr;
+    size_t clip_cap_int = 0, clip_cap_dbl = 0, clip_cap_eta = 0, clip_cap_w = 0;
     bool sub_mode = false;           // the batch columns hold ext = [batch, subset]: no look-ahead for a next greedy step
 
     int w_cap = 0;                   // allocated projection columns
@@ -898,6 +907,192 @@ int propose_general(ital_shard* s) {
     return ITAL_OK;
 }
 
+// clip_cov, steps with more than 5 samples (t >= 5 base variables), users who label everything: every candidate is
+// scored (the lazy-greedy bound is not proven for the clipped model), see k_clip_adj / k_eval_clip.
+int propose_clip(ital_shard* s) {
+    const int t = s->t;
+    if (t > 10) return fail(ITAL_EINVAL, "clip_cov: batches of more than 11 samples are not supported");
+    std::vector<double> bm(16), bL(16 * 16);
+    CU(copy_async(s, bm.data(), s->base_m_dev, 16 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(copy_async(s, bL.data(), s->base_L_dev, 256 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    // covariance of the batch, its groups (connected components of |corr| > clip_cov)
+    std::vector<double> C((size_t)t * t, 0.0), sd(16, 1.0);
+    for (int a = 0; a < t; ++a)
+        for (int b = 0; b <= a; ++b) {
+            double acc = 0.0;
+            for (int j = 0; j <= b; ++j) acc += bL[a * kBaseStride + j] * bL[b * kBaseStride + j];
+            C[a * t + b] = C[b * t + a] = acc;
+        }
+    for (int a = 0; a < t; ++a) sd[a] = std::sqrt(std::max(C[a * t + a], 1e-300));
+    std::vector<int> comp(t);
+    for (int a = 0; a < t; ++a) comp[a] = a;
+    auto find = [&](int a) { while (comp[a] != a) a = comp[a] = comp[comp[a]]; return a; };
+    for (int a = 0; a < t; ++a)
+        for (int b = 0; b < a; ++b)
+            if (std::fabs(C[a * t + b] / (sd[a] * sd[b])) > s->clip_cov) comp[find(a)] = find(b);
+    std::vector<int> comp_mask(16, 0);
+    for (int a = 0; a < t; ++a)
+        for (int b = 0; b < t; ++b)
+            if (find(a) == find(b)) comp_mask[a] |= 1 << b;
+    // node set of a subset of the batch (members in batch order): marginal means and Cholesky factor
+    auto subset_nodes = [&](int mask, std::vector<int>& mem, std::vector<double>& Ls) {
+        mem.clear();
+        for (int a = 0; a < t; ++a)
+            if ((mask >> a) & 1) mem.push_back(a);
+        const int u = (int)mem.size();
+        std::vector<double> ms(u);
+        Ls.assign((size_t)u * u, 0.0);
+        for (int a = 0; a < u; ++a) {
+            ms[a] = bm[mem[a]];
+            for (int b = 0; b < u; ++b) Ls[a * u + b] = C[mem[a] * t + mem[b]];
+        }
+        snq::chol_inplace(Ls, u);
+        return snq::generate(u, ms.data(), Ls.data());
+    };
+    // entropy of every group
+    double h_all = 0.0;
+    std::vector<double> h_comp(t, 0.0);
+    std::vector<int> mem;
+    std::vector<double> Ls;
+    for (int a = 0; a < t; ++a) {
+        const int lowest = __builtin_ctz(comp_mask[a]);         // (one evaluation per group: at its lowest member)
+        if (lowest != a) continue;
+        snq::Nodes nd = subset_nodes(comp_mask[a], mem, Ls);
+        h_comp[a] = nd.entropy;
+        h_all += nd.entropy;
+    }
+    // pass 1: the groups every candidate is connected to
+    auto grow = [&](void** p, size_t* cap, size_t need, size_t esize) -> int {
+        if (need <= *cap) return ITAL_OK;
+        CU(cudaStreamSynchronize(s->stream));
+        if (*p) CU(cudaFree(*p));
+        *p = nullptr;
+        CU(cudaMalloc(p, need * esize));
+        *cap = need;
+        return ITAL_OK;
+    };
+    if (!s->clip_sub) {
+        CU(cudaMalloc(&s->clip_sub, (size_t)s->n * sizeof(unsigned short)));
+        CU(cudaMalloc(&s->clip_list2, (size_t)s->n * sizeof(int)));
+        CU(cudaMalloc(&s->clip_desc, 1024 * sizeof(ClipDesc)));
+    }
+    int rc;
+    if ((rc = grow((void**)&s->clip_int, &s->clip_cap_int, 64, sizeof(int)))) return rc;
+    if ((rc = grow((void**)&s->clip_dbl, &s->clip_cap_dbl, 64, sizeof(double)))) return rc;
+    std::vector<int> head(64, 0);
+    for (int a = 0; a < 16; ++a) head[33 + a] = comp_mask[a];
+    CU(copy_async(s, s->clip_int, head.data(), 64 * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, s->clip_dbl, sd.data(), 16 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaMemsetAsync(s->counters, 0, 4 * sizeof(int), s->stream));
+    pdl(k_worklist, grid_for(s, s->n, 256), 256, 0, s)(s->n, s->mask, s->gain, s->thr_dev, 1, s->counters, s->worklist); s->launches++;
+    int rcu = launch_catchup(s, s->n);
+    if (rcu) return rcu;
+    ClipArgs a = {};
+    a.count = s->counters;
+    a.list = s->worklist;
+    a.count2 = s->clip_int + 32;
+    a.list2 = s->clip_list2;
+    a.m = s->m;
+    a.v = s->v;
+    a.U = s->U;
+    a.ldu = s->ldu;
+    a.W0 = s->W;
+    a.t = t;
+    a.base_L = s->base_L_dev;
+    a.sd_b = s->clip_dbl;
+    a.comp_mask = s->clip_int + 33;
+    a.th = s->clip_cov;
+    a.h_all = h_all;
+    a.sub = s->clip_sub;
+    a.present = (unsigned*)s->clip_int;
+    a.phi = s->phi_dev;
+    a.log1p_eps = s->log1p_eps;
+    a.score = s->score;
+    a.gain = s->gain;
+    a.tags = s->tags;
+    a.epoch = s->epoch;
+    a.n_scored = s->counters + 2;
+    pdl(k_clip_adj, grid_for(s, s->n, 256), 256, 0, s)(a); s->launches++;
+    std::vector<unsigned> present(33);
+    CU(copy_async(s, present.data(), s->clip_int, 33 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    // pass 2: node sets of the unions that occur
+    std::vector<ClipDesc> desc(1024);
+    std::vector<double> eta, w, dbl(16, 0.0);
+    std::vector<int> ints(64, 0);
+    for (int a2 = 0; a2 < 16; ++a2) dbl[a2] = sd[a2];
+    int64_t total_nodes = 0;
+    for (int S = 1; S < (1 << t); ++S) {
+        if (!((present[S >> 5] >> (S & 31)) & 1u)) continue;
+        snq::Nodes nd = subset_nodes(S, mem, Ls);
+        const int u = (int)mem.size();
+        total_nodes += nd.n;
+        if (total_nodes > (int64_t)48 << 20)
+            return fail(ITAL_EINVAL, "clip_cov: the candidates connect %d and more different unions of groups (over 48M quadrature nodes)", S);
+        ClipDesc& d = desc[S];
+        d.eta_off = (long long)eta.size();
+        d.n = (int)nd.n;
+        d.dims = u;
+        d.gb_off = (int)ints.size() - 64;
+        d.mass_off = (int)dbl.size() - 16;
+        ints.insert(ints.end(), nd.group_begin.begin(), nd.group_begin.end());
+        dbl.insert(dbl.end(), nd.masses.begin(), nd.masses.end());
+        d.T_off = (int)dbl.size() - 16;
+        // T = Ls^-1 L_b[S, :]  (u x t): a candidate's projection on the set's own factor from its batch columns
+        for (int r = 0; r < u; ++r)
+            for (int c = 0; c < t; ++c) dbl.push_back(0.0);
+        double* T = dbl.data() + 16 + d.T_off;
+        for (int c = 0; c < t; ++c)
+            for (int r = 0; r < u; ++r) {
+                double val = c <= mem[r] ? bL[mem[r] * kBaseStride + c] : 0.0;
+                for (int k = 0; k < r; ++k) val -= Ls[r * u + k] * T[k * t + c];
+                T[r * t + c] = val / Ls[r * u + r];
+            }
+        d.h_rest = 0.0;
+        for (int b = 0; b < t; ++b)
+            if (__builtin_ctz(comp_mask[b]) == b && !(S & comp_mask[b])) d.h_rest += h_comp[b];
+        // eta of the set dimension-major, its weights at eta_off / dims
+        // (weights of all sets are kept in their own array at the same node offsets)
+        eta.insert(eta.end(), nd.eta.begin(), nd.eta.end());
+        // pad w so that w offset = eta_off / dims holds: keep a parallel list of offsets instead
+        d.pad = (int)w.size();
+        w.insert(w.end(), nd.w.begin(), nd.w.end());
+    }
+    if ((rc = grow((void**)&s->clip_eta, &s->clip_cap_eta, eta.size() + 1, sizeof(double)))) return rc;
+    if ((rc = grow((void**)&s->clip_w, &s->clip_cap_w, w.size() + 1, sizeof(double)))) return rc;
+    // (the small tables are re-uploaded whole: head of 64 ints / 16 doubles, then the per-set pieces)
+    for (int k2 = 0; k2 < 64; ++k2) ints[k2] = k2 < 33 ? (int)present[k2] : head[k2];
+    if ((rc = grow((void**)&s->clip_int, &s->clip_cap_int, ints.size(), sizeof(int)))) return rc;
+    if ((rc = grow((void**)&s->clip_dbl, &s->clip_cap_dbl, dbl.size(), sizeof(double)))) return rc;
+    CU(copy_async(s, s->clip_int, ints.data(), ints.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, s->clip_dbl, dbl.data(), dbl.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    if (!eta.empty()) CU(copy_async(s, s->clip_eta, eta.data(), eta.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    if (!w.empty()) CU(copy_async(s, s->clip_w, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(copy_async(s, s->clip_desc, desc.data(), desc.size() * sizeof(ClipDesc), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    a.count2 = s->clip_int + 32;
+    a.comp_mask = s->clip_int + 33;
+    a.present = (unsigned*)s->clip_int;
+    a.sd_b = s->clip_dbl;
+    a.desc = (const ClipDesc*)s->clip_desc;
+    a.eta = s->clip_eta;
+    a.w = s->clip_w;
+    a.gb = s->clip_int + 64;
+    a.mass = s->clip_dbl + 16;
+    a.T = s->clip_dbl + 16;
+    pdl(k_eval_clip, grid_for(s, s->n, 1, 8), 256, 0, s)(a); s->launches++;
+    const int lb = std::min(kArgmaxBlocks, grid_for(s, s->n, 256));
+    pdl(k_argmax_list, lb, 256, 0, s)(s->counters, s->worklist, s->score, s->block_best, nullptr, 0.0, 0.0, nullptr, nullptr); s->launches++;
+    s->pick = PickSrc();
+    s->pick.block_best = s->block_best;
+    s->pick.nblocks = lb;
+    s->n_nodes = total_nodes;
+    CU(cudaGetLastError());
+    return ITAL_OK;
+}
+
 // change_estimation_subset: score the local candidates against ext = the D batch columns of the running fetch, the
 // first tB of which are the samples picked so far (k_eval_sub, snq::generate_sub).  only_local >= 0: that row alone.
 int propose_sub(ital_shard* s, int tB, int64_t only_local, bool any_local) {
@@ -1054,6 +1249,9 @@ int propose_dev(ital_shard* s, double floor_score, int exhaustive, double* rec_o
         s->n_nodes = 1;
     } else if (s->label_prob < 1.0 || s->estimation != 0) {
         int rc = propose_general(s);
+        if (rc) return rc;
+    } else if (s->clip_cov > 0.0 && s->clip_cov < 1.0 && s->t + 1 > 5) {
+        int rc = propose_clip(s);                       // ital.py:360: grouped probabilities for more than 5 samples
         if (rc) return rc;
     } else {
         int rc = ITAL_OK;
@@ -1279,7 +1477,7 @@ void free_all(ital_shard* s) {
     void* ptrs[] = {s->X, s->sqn, s->m, s->v, s->U, s->gain, s->score, s->mask, s->worklist, s->counters,
                     s->block_best, s->best, s->thr_dev, s->rec_dev, s->rec_in_dev, s->idx_dev, s->eta_dev,
                     s->w_dev, s->masses_dev, s->group_dev, s->orth_dev, s->eta_raw, s->w_raw, s->orth_raw, s->gl_dev, s->phi_dev, s->htab_dev, s->base_m_dev, s->base_L_dev, s->sel_dev,
-                    s->hbase_dev, s->tags, s->f_best, s->f_cnt, s->f_stage, s->f_mass, s->f_bar, s->f_trace, s->rec_hist, s->mext_dev, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->sb_eta, s->sb_w, s->sb_small, s->sb_begin, s->sc_dbl, s->sc_int, s->tn_int, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev, s->beta_dev, s->upd_idx_dev, s->upd_y_dev,
+                    s->hbase_dev, s->tags, s->f_best, s->f_cnt, s->f_stage, s->f_mass, s->f_bar, s->f_trace, s->rec_hist, s->mext_dev, s->g_eta, s->g_w, s->g_mass, s->g_begin, s->g_set0, s->g_lut, s->sb_eta, s->sb_w, s->sb_small, s->sb_begin, s->sc_dbl, s->sc_int, s->tn_int, s->clip_sub, s->clip_int, s->clip_dbl, s->clip_list2, s->clip_desc, s->clip_eta, s->clip_w, s->lab_x_dev, s->lab_sqn_dev, s->w_vec_dev, s->LK_dev, s->beta_dev, s->upd_idx_dev, s->upd_y_dev,
                     s->sort_keys, s->sort_rows, s->sort_hist, s->sort_out_idx, s->sort_out_val};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -1775,6 +1973,13 @@ int ital_variance_propose(ital_shard* s, int use_correlations, int first_pick_ta
     CU(copy_async(s, s->rec_host, s->rec_dev, (size_t)rl * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     memcpy(record, s->rec_host, (size_t)rl * sizeof(double));
+    return ITAL_OK;
+}
+
+int ital_set_clip_cov(ital_shard* s, double clip_cov) {
+    if (!s) return fail(ITAL_EINVAL, "null shard");
+    if (s->fetching) return fail(ITAL_ESTATE, "ital_set_clip_cov during a fetch");
+    s->clip_cov = clip_cov;
     return ITAL_OK;
 }
 

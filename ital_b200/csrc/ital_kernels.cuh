@@ -2091,6 +2091,152 @@ __global__ void __launch_bounds__(256) k_eval_sub(SubArgs a) {
     }
 }
 
+// ---- clip_cov: grouped orthant probabilities for more than 5 samples (ital.py:360-362, 386-429, 590-616) -----------
+// From the sixth sample of a batch on, the reference drops correlations below clip_cov and multiplies the orthant
+// probabilities of the resulting independent groups.  For users who label everything the score is the entropy of the
+// sign pattern, which is additive over independent groups: score(i) = sum over the groups of the batch that candidate i
+// is not connected to of H(group) + H({i} + the groups it connects).  k_clip_adj finds, per candidate, the union S of
+// the batch's groups it is connected to (|corr| > clip_cov with any member); candidates with S empty are finished in
+// closed form, the others are listed for k_eval_clip, which scores them with the node set of S (generated on the host
+// for every S that occurs, csrc/ital_capi.cu propose_clip).
+struct ClipDesc {
+    long long eta_off;          // node coordinates of the set, dimension-major [dims][n]
+    int n, dims;
+    int gb_off;                 // 2^dims + 1 orthant offsets (relative to the set)
+    int mass_off;               // 2^dims orthant masses
+    int T_off;                  // [dims][t]: projection of a candidate on the set's own Cholesky factor
+    int pad;                    // offset of the set's weights
+    double h_rest;              // entropy of the groups outside S
+};
+
+struct ClipArgs {
+    const int* count;           // candidates (k_worklist, all of them)
+    const int* list;
+    int* count2;                // candidates connected to the batch
+    int* list2;
+    const double* m;
+    const double* v;
+    const double* U;
+    int64_t ldu;
+    int W0, t;
+    const double* base_L;       // [t][kBaseStride]
+    const double* sd_b;         // [t] standard deviations of the batch members
+    const int* comp_mask;       // [t] members of the group of batch member b, as a bit mask
+    double th, h_all;           // clip_cov; entropy of all groups of the batch
+    unsigned short* sub;        // [n] S per candidate
+    unsigned* present;          // [32] which S occur
+    const ClipDesc* desc;       // [1024] by S
+    const double* eta;
+    const double* w;
+    const int* gb;
+    const double* mass;
+    const double* T;
+    const double2* phi;
+    double log1p_eps;
+    double* score;
+    double* gain;
+    uint32_t* tags;
+    uint32_t epoch;
+    int* n_scored;
+};
+
+__global__ void __launch_bounds__(256) k_clip_adj(ClipArgs a) {
+    pdl_enter();
+    const int n_items = *a.count;
+    for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += gridDim.x * blockDim.x) {
+        const int64_t i = a.list[item];
+        const double vi = a.v[i];
+        double l[10];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) l[j] = j < a.t ? a.U[(int64_t)(a.W0 + j) * a.ldu + i] : 0.0;
+        int S = 0;
+        if (vi > 0.0) {
+            const double sdi = sqrt(vi);
+            for (int b = 0; b < a.t; ++b) {
+                double cov = 0.0;
+                for (int j = 0; j <= b; ++j) cov = fma(a.base_L[b * kBaseStride + j], l[j], cov);
+                if (fabs(cov / (a.sd_b[b] * sdi)) > a.th) S |= a.comp_mask[b];
+            }
+        }
+        a.sub[i] = (unsigned short)S;
+        if (S == 0) {
+            // on its own: two-sided entropy of its sign, plus the groups of the batch
+            const double sd = vi > 0.0 ? sqrt(vi) : 0.0;
+            const double mi = a.m[i];
+            const double p1 = sd > 0.0 ? 0.5 * erfc(-mi / sd * 0.70710678118654752440) : (mi > 0.0 ? 1.0 : 0.0);
+            const double sc = mi_term(p1, a.log1p_eps) + mi_term(1.0 - p1, a.log1p_eps) + a.h_all;
+            a.tags[i] = tag_with_step(a.tags[i], a.epoch, a.t);
+            a.score[i] = sc;
+            a.gain[i] = sc;
+            atomicAdd(a.n_scored, 1);
+        } else {
+            atomicOr(a.present + (S >> 5), 1u << (S & 31));
+            a.list2[atomicAdd(a.count2, 1)] = (int)i;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_eval_clip(ClipArgs a) {
+    pdl_enter();
+    __shared__ double red[8];
+    __shared__ double xs[10];
+    __shared__ double2 phi_s[kPhiTableLen];
+    phi_tab_to_shared(phi_s, a.phi);
+    __syncthreads();
+    const int n_items = *a.count2;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int64_t i = a.list2[item];
+        const ClipDesc dsc = a.desc[a.sub[i]];
+        const int dims = dsc.dims;
+        __syncthreads();
+        if ((int)threadIdx.x < dims) {                  // projection on the set's own factor: x = T l_i
+            double acc = 0.0;
+            for (int c = 0; c < a.t; ++c)
+                acc = fma(a.T[dsc.T_off + threadIdx.x * a.t + c], a.U[(int64_t)(a.W0 + c) * a.ldu + i], acc);
+            xs[threadIdx.x] = acc;
+        }
+        __syncthreads();
+        double x[10];
+        double s2 = a.v[i];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+            x[j] = j < dims ? xs[j] : 0.0;
+            s2 = fma(-x[j], x[j], s2);
+        }
+        const double mi = a.m[i];
+        const double sd = s2 > 0.0 ? sqrt(s2) : 0.0;
+        const double inv_s = sd > 0.0 ? 1.0 / sd : 0.0;
+        const double* eta = a.eta + dsc.eta_off;
+        const double* w = a.w + dsc.pad;
+        const int* gb = a.gb + dsc.gb_off;
+        const double* mass = a.mass + dsc.mass_off;
+        const int64_t N = dsc.n;
+        double sc = 0.0;
+        const int nb = 1 << dims;
+        for (int b = 0; b < nb; ++b) {
+            double acc = 0.0;
+            for (int q = gb[b] + threadIdx.x; q < gb[b + 1]; q += 256) {
+                double num = mi;
+#pragma unroll
+                for (int j = 0; j < 10; ++j)
+                    if (j < dims) num = fma(x[j], eta[(int64_t)j * N + q], num);
+                const double cdf = sd > 0.0 ? phi_tab(phi_s, num * inv_s) : (num > 0.0 ? 1.0 : 0.0);
+                acc = fma(w[q], cdf, acc);
+            }
+            const double p_plus = team_sum(acc, 256, red);
+            const double p_minus = fmax(mass[b] - p_plus, 0.0);
+            sc += mi_term(p_plus, a.log1p_eps) + mi_term(p_minus, a.log1p_eps);
+        }
+        if (threadIdx.x == 0) {
+            sc += dsc.h_rest;
+            a.tags[i] = tag_with_step(a.tags[i], a.epoch, a.t);
+            a.score[i] = sc;
+            a.gain[i] = sc;
+            atomicAdd(a.n_scored, 1);
+        }
+    }
+}
+
 // ---- tensor rule for 4 and 5 base variables on the device ------------------------------------------------------------
 // 331 776 / 3.2 million nodes are generated twice (a node costs a few hundred flops, storing them all would cost more):
 // once to count the kept nodes per orthant and block, once to scatter them to their place in the orthant-sorted,

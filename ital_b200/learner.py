@@ -317,6 +317,10 @@ class ITAL(object):
                                                               self.ESTIMATIONS.get(self.label_estimation, 0)))
         return bool(on)
 
+    def _apply_clip_cov(self):
+        clip = float(self.clip_cov) if self.clip_cov and 0 < self.clip_cov < 1 else 0.0     # ital.py:360
+        _capi.check(self._shard.lib.ital_set_clip_cov(self._shard.handle, clip))
+
     def _exhaustive(self):
         """Every candidate is scored at every step: asked for, or no lazy-greedy bound (only the expectation over the
         relevance configurations, label_estimation='mean', is a submodular entropy)."""
@@ -601,8 +605,9 @@ class ITAL(object):
         if k > limit:               # before any work (and before any collective) -- not in the middle of the greedy loop
             raise NotImplementedError('batches of more than %d samples are not supported%s' % (
                 limit, " with label_prob < 1 or label_estimation other than 'mean'" if general else ''))
-        if self.clip_cov and 0 < self.clip_cov < 1 and k > 5:
-            raise NotImplementedError('clip_cov (grouped orthant probabilities of more than 5 variables) is not built')
+        if self.clip_cov and 0 < self.clip_cov < 1 and k > 5 and (general or self.mistake_prob > 0):
+            raise NotImplementedError('clip_cov with more than 5 samples is built for label_prob=1, mistake_prob=0, '
+                                      "label_estimation='mean'")
         ce = self.change_estimation_subset
         if ce is None:              # every unseen sample in the subset: orthant probabilities in n dimensions
             raise NotImplementedError('change_estimation_subset=None (all unseen samples) is not built')
@@ -643,6 +648,7 @@ class ITAL(object):
                 restricted = True
         self.last_fetch_stats = []
         self._apply_lazy_rows()
+        self._apply_clip_cov()
         try:
             if self.change_estimation_subset:
                 return self._fetch_change_subset(k)
@@ -737,6 +743,7 @@ class ITAL(object):
             steps = trange(k)
         ret, self.last_fetch_scores, self.last_step_scores = [], [], []
         self._apply_lazy_rows()
+        self._apply_clip_cov()
         self._shard.fetch_begin(self.label_prob, self.mistake_prob)
         try:
             for it in steps:

@@ -190,6 +190,64 @@ def mi_perfect_user(m_base, cov_base, m_c, var_c, cov_base_c, q=None, pool=None)
     return scores, p_plus, p_base, s
 
 
+def _joint_cov(cov_base, var_c, cov_base_c):
+    D = len(cov_base) + 1
+    cov = np.empty((D, D))
+    cov[:D - 1, :D - 1] = cov_base
+    cov[:D - 1, D - 1] = cov[D - 1, :D - 1] = cov_base_c
+    cov[D - 1, D - 1] = var_c
+    return cov
+
+
+def group_cov(corr, th):
+    """Connected components of the graph |corr| > th (group_cov, ital.py:590-616), in the reference's order: groups by
+    their smallest unassigned member, members in order of discovery."""
+    clipped = np.abs(corr) > th
+    unassigned = list(range(len(corr)))
+    groups = []
+    while unassigned:
+        group, frontier = [], [j for j in np.nonzero(clipped[unassigned[0]])[0]]
+        while frontier:
+            group += [j for j in frontier if j not in group]
+            unassigned = [j for j in unassigned if j not in frontier]
+            reach = np.nonzero(clipped[group].max(axis=0))[0]
+            frontier = [j for j in reach if j in unassigned]
+        groups.append(group)
+    return groups
+
+
+def mi_grouped(mean, cov, th, eps=EPS):
+    """MI of more than 5 samples with clip_cov = th under the perfect-user model (prob_rel -> _grouped_prob_rel,
+    ital.py:360-429): correlations below th are dropped, the probability of a relevance configuration is the product
+    over the independent groups, and the sum over all 2^D configurations is taken literally (ital.py:193-219)."""
+    sd = np.sqrt(np.diag(cov))
+    corr = cov / np.outer(sd, sd)
+    groups = group_cov(corr, th)
+    D = len(mean)
+    tables = []
+    groups = [sorted(g) for g in groups]        # (batch order, the candidate last: the variable integrated analytically)
+    for g in groups:
+        if len(g) == 1:
+            j = g[0]
+            p0 = float(ndtr_scalar(-mean[j] / sd[j]))
+            tables.append(np.array([p0, 1.0 - p0]))
+        else:
+            tables.append(orthant_prob_all(mean[g], cov[np.ix_(g, g)], snq_order(len(g) - 1) or None))
+    p = np.ones(1 << D)
+    r = np.arange(1 << D)
+    for g, tab in zip(groups, tables):
+        idx = np.zeros(1 << D, dtype=np.int64)
+        for k, j in enumerate(g):
+            idx |= ((r >> j) & 1) << k
+        p = p * tab[idx]
+    return float(np.sum(entropy_terms(p, 1.0, eps)))
+
+
+def ndtr_scalar(x):
+    from scipy.special import ndtr
+    return ndtr(x)
+
+
 class OracleITAL(object):
     """ITAL + ActiveRetrievalBase (ital.py:12-134, retrieval_base.py:7-194) over OracleGP."""
 
@@ -205,8 +263,8 @@ class OracleITAL(object):
         self.force_general = force_general
         self.general_sets = general_sets      # general feedback model through shared conditional node sets (oracle/general_sets.py)
         self.change_estimation_subset = change_estimation_subset
-        if change_estimation_subset is None or clip_cov != 0 or monte_carlo_num_rel is not None \
-                or monte_carlo_num_fb is not None:
+        self.clip_cov = clip_cov
+        if change_estimation_subset is None or monte_carlo_num_rel is not None or monte_carlo_num_fb is not None:
             raise NotImplementedError('oracle restates the enumeration path only (see module docstring)')
         self.fit(data, queries)
 
@@ -312,7 +370,14 @@ class OracleITAL(object):
             else:
                 cov_base, var_test, cov_base_test = self.gp.predict_cov_parts(ret)   # ital.py:586
             m_base = self.rel_mean[ret] if len(ret) else np.zeros(0)
-            if self._perfect_user() and self.label_estimation == 'mean' and not self.force_general:
+            if 0 < self.clip_cov < 1 and len(ret) + 1 > 5:                      # ital.py:360-362
+                if not (self._perfect_user() and self.label_estimation == 'mean'):
+                    raise NotImplementedError('clip_cov is restated for users who label everything correctly')
+                scores = np.array([mi_grouped(np.concatenate((m_base, [self.rel_mean[i]])),
+                                              _joint_cov(cov_base, var_test[i], cov_base_test[:, i]), self.clip_cov)
+                                   for i in cand])
+                extra = {}
+            elif self._perfect_user() and self.label_estimation == 'mean' and not self.force_general:
                 scores, p_plus, p_base, s = mi_perfect_user(
                     m_base, cov_base, self.rel_mean[cand], var_test[cand], cov_base_test[:, cand], pool=pool)
                 extra = dict(p_plus=p_plus, p_base=p_base, s=s)

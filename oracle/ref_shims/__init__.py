@@ -41,6 +41,11 @@ def mvndst_standin(lower, upper, infin, correl, maxpts=None, abseps=None, releps
     pivot = np.where(infin == 1, lower, upper)
     if not np.all(np.isfinite(pivot)) or not np.all(np.isfinite(corr)):
         return 0.0, float('nan'), 0
+    if np.all(np.abs(pivot) > 12.0):
+        # every variable is more than 12 standard deviations from its limit: the probability is 0 or 1 to 1e-30 whatever
+        # the correlations (the updated distributions of a user who labels everything, ital.py:432-450)
+        inside = np.where(infin == 1, pivot < 0, pivot > 0)
+        return 1e-30, float(np.all(inside)), 0
     if D == 2:
         from scipy.stats._qmvnt import _bvnu        # Genz BVU: P(x > h, y > k) for correlation r
         sgn = np.where(infin == 1, 1.0, -1.0)       # flip the variables bounded from above

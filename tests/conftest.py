@@ -22,7 +22,7 @@ def _npz_names():
 
 def golden_names():
     """Fetch goldens (every greedy step of a fetch_unlabelled of the reference)."""
-    return [n for n in _npz_names() if not n.startswith(('updpred_', 'experiment_', 'baseline_', 'subset_'))]
+    return [n for n in _npz_names() if not n.startswith(('updpred_', 'experiment_', 'baseline_', 'subset_', 'clip_'))]
 
 
 def updpred_names():
@@ -36,6 +36,20 @@ def subset_names():
 
 
 def load_subset(name):
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + '.npz'), allow_pickle=False))
+    g['updates'] = [dict(zip(g['upd%d_idx' % u].tolist(), g['upd%d_val' % u].tolist()))
+                    for u in range(int(g['n_updates']))]
+    g['steps'] = [dict(candidates=g['step%d_candidates' % t], mi=g['step%d_mi' % t], chosen=int(g['step%d_chosen' % t]))
+                  for t in range(len(g['ret']))]
+    return g
+
+
+def clip_names():
+    """Goldens of ITAL(clip_cov = th) with more than 5 samples per batch (make_clip_golden.py)."""
+    return [n for n in _npz_names() if n.startswith('clip_')]
+
+
+def load_clip(name):
     g = dict(np.load(os.path.join(GOLDEN_DIR, name + '.npz'), allow_pickle=False))
     g['updates'] = [dict(zip(g['upd%d_idx' % u].tolist(), g['upd%d_val' % u].tolist()))
                     for u in range(int(g['n_updates']))]

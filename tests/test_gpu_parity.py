@@ -8,8 +8,8 @@ oracle (absolute floor 1e-9 for moments, 1e-12 = the reference's eps for scores)
 import numpy as np
 import pytest
 
-from conftest import (baseline_names, drive, golden_names, load_baseline, load_golden, load_subset, load_updpred,
-                      subset_names, updpred_names)
+from conftest import (baseline_names, clip_names, drive, golden_names, load_baseline, load_clip, load_golden,
+                      load_subset, load_updpred, subset_names, updpred_names)
 
 pytestmark = pytest.mark.gpu
 
@@ -655,4 +655,46 @@ def test_change_estimation_subset_matches_the_reference(name):
         six = len(g['subset']) + t + 1 >= 6              # (five base variables at Q = 10: see test_oracle_golden.py)
         np.testing.assert_allclose(got, st['mi'], rtol=1e-4, atol=1e-3 if six else 1e-4, err_msg='step %d' % t)
         assert np.sum(np.abs(got - st['mi']) > 1e-4 + 1e-4 * np.abs(st['mi'])) <= 2
+    gpu.close()
+
+
+@pytest.mark.parametrize('name', clip_names())
+def test_clip_cov_matches_the_reference(name):
+    """ITAL(clip_cov = th) with 6 samples per batch against the goldens of the unmodified reference: same batch, the
+    scores of the grouped step (more than 5 samples, ital.py:360-362) within 1e-6."""
+    g = load_clip(name)
+    gpu = _gpu_learner(g['X'], length_scale=float(g['length_scale']), var=float(g['var']), noise=float(g['noise']),
+                       clip_cov=float(g['clip_cov']))
+    for fb in g['updates']:
+        gpu.update({int(k): v for k, v in fb.items()})
+    assert gpu.fetch_unlabelled(int(g['k'])) == [int(i) for i in g['ret']]
+    ret = gpu._fetch_stepwise(int(g['k']), keep_scores=True)
+    assert ret == [int(i) for i in g['ret']]
+    st = g['steps'][5]
+    got = gpu.last_step_scores[5][st['candidates']]
+    np.testing.assert_allclose(got, st['mi'], rtol=1e-6, atol=1e-6)
+    gpu.close()
+
+
+@pytest.mark.parametrize('th,ls,k', [(0.3, 1.0, 8), (0.15, 0.7, 7), (0.6, 1.5, 6)])
+def test_clip_cov_tracks_the_oracle(th, ls, k):
+    """Longer batches with clip_cov: every candidate's score of every grouped step within 1e-6 of the oracle's literal
+    product over the groups (oracle/ital_oracle.py mi_grouped), same batch."""
+    from oracle.ital_oracle import OracleITAL
+    rng = np.random.RandomState(11)
+    X = rng.randn(80, 2) * 1.5
+    y = np.where(X[:, 0] - 0.3 * X[:, 1] > 0, 1, -1)
+    fb = {i: int(y[i]) for i in (0, 7, 19, 33, 50)}
+    gpu, ora = _gpu_learner(X, length_scale=ls, clip_cov=th), OracleITAL(X, length_scale=ls, clip_cov=th)
+    gpu.update(fb)
+    ora.update(fb)
+    ret = gpu._fetch_stepwise(k, keep_scores=True)
+    ora.fetch_unlabelled(k, forced=ret)
+    for t in range(5, k):
+        tr = ora.trace[t]
+        got = gpu.last_step_scores[t][tr['candidates']]
+        np.testing.assert_allclose(got, tr['scores'], rtol=1e-6, atol=1e-9, err_msg='step %d' % t)
+        best = float(np.max(tr['scores']))
+        assert tr['scores'][list(tr['candidates']).index(ret[t])] >= best - 1e-9 * max(1.0, abs(best))
+    assert gpu.fetch_unlabelled(k) == ret
     gpu.close()

@@ -202,8 +202,12 @@ def test_reset_and_unsupported_modes(make):
     C = make(clip_cov=0.5)                             # ital.py:360: grouping only for more than 5 variables
     C.update({0: 1})
     assert len(C.fetch_unlabelled(5)) == 5
+    assert len(C.fetch_unlabelled(6)) == 6
+    G = make(clip_cov=0.5, mistake_prob=0.1)           # ... built for users who label everything correctly
+    G.update({0: 1})
+    assert len(G.fetch_unlabelled(5)) == 5
     with pytest.raises(NotImplementedError):
-        C.fetch_unlabelled(6)
+        G.fetch_unlabelled(6)
     M = make(monte_carlo_num_rel=3, monte_carlo_num_fb=5)      # evaluated exactly (zero-variance limit of the estimator)
     M.update({0: 1})
     assert len(M.fetch_unlabelled(4)) == 4

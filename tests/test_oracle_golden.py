@@ -10,7 +10,7 @@ import numpy as np
 
 import pytest
 
-from conftest import drive, load_golden, load_subset, load_updpred, subset_names, updpred_names
+from conftest import clip_names, drive, load_clip, load_golden, load_subset, load_updpred, subset_names, updpred_names
 from oracle.ital_oracle import OracleITAL
 
 
@@ -149,3 +149,21 @@ def test_oracle_change_estimation_subset_matches_reference(name):
         np.testing.assert_allclose(tr['scores'], st['mi'], rtol=SUBSET_RTOL, atol=1e-3 if six else SUBSET_ATOL,
                                    err_msg='step %d' % t)
         assert np.sum(np.abs(tr['scores'] - st['mi']) > SUBSET_ATOL + SUBSET_RTOL * np.abs(st['mi'])) <= 2
+
+
+@pytest.mark.parametrize('name', clip_names())
+def test_oracle_clip_cov_matches_reference(name):
+    """ITAL(clip_cov = th), batches of 6 (tests/golden/make_clip_golden.py): the step with more than 5 samples uses the
+    grouped orthant probabilities (ital.py:360-362, 386-429); same batch as the unmodified reference, the scores of that
+    step within 1e-6 (the earlier steps of these strongly correlated pools within 1e-4: the rule's accuracy there)."""
+    g = load_clip(name)
+    ora = OracleITAL(g['X'], length_scale=float(g['length_scale']), var=float(g['var']), noise=float(g['noise']),
+                     clip_cov=float(g['clip_cov']))
+    for fb in g['updates']:
+        ora.update({int(k): v for k, v in fb.items()})
+    ret = ora.fetch_unlabelled(int(g['k']))
+    assert ret == [int(i) for i in g['ret']]
+    for t, (tr, st) in enumerate(zip(ora.trace, g['steps'])):
+        assert tr['candidates'].tolist() == st['candidates'].tolist()
+        tol = 1e-6 if t >= 5 else 1e-4
+        np.testing.assert_allclose(tr['scores'], st['mi'], rtol=tol, atol=tol, err_msg='step %d' % t)
