@@ -134,7 +134,8 @@ int ital_variance_propose(ital_shard* s, int use_correlations, int first_pick_ta
  * so far, then the members of S outside the batch] (every commit is one streaming pass, so each row holds its
  * projection on ext), then ital_fetch_propose_sub writes the record of the best local candidate outside ext -- or of
  * the single row only_row >= 0 (a member of S is scored with itself moved out of the subset) -- then ital_fetch_end.
- * Users who label every sample without mistakes, label_estimation 'mean', at most 7 batch samples and 11 columns. */
+ * Users who label every sample (label_prob = 1; mistake_prob of the fetch is honoured), label_estimation 'mean', at
+ * most 7 batch samples and 11 columns. */
 int ital_set_sub_mode(ital_shard* s, int on);
 /* ITAL(clip_cov = th) (ital/ital.py:360-362, MutualInformation._grouped_prob_rel ital.py:386-429, group_cov
  * ital.py:590-616): from the sixth sample of a batch on, correlations of at most th are dropped and the orthant

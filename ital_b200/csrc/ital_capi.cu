@@ -572,7 +572,7 @@ double step_shift_coef(const ital_shard* s) {
 
 int make_record(ital_shard* s, long long local_row, double* dst_dev, bool commit_here = false, PickSrc src = PickSrc(),
                 PeerPut pp = PeerPut()) {
-    const double shift = local_row < 0 ? step_shift_coef(s) : 0.0;
+    const double shift = (local_row < 0 && !s->sub_mode) ? step_shift_coef(s) : 0.0;     // (k_eval_sub scores in full)
     CommitTargets ct;
     if (commit_here) {
         s->sel_marked = true;
@@ -1083,6 +1083,11 @@ int propose_clip(ital_shard* s) {
     a.mass = s->clip_dbl + 16;
     a.T = s->clip_dbl + 16;
     pdl(k_eval_clip, grid_for(s, s->n, 1, 8), 256, 0, s)(a); s->launches++;
+    {   // {H(batch), total mass}: the mistaken user's additive constant is per unit of total mass (make_record)
+        const double hb2[2] = {h_all, 1.0};
+        memcpy(s->sel_host + 30, hb2, sizeof hb2);      // (pinned scratch at the tail of the selection mirror)
+        CU(copy_async(s, s->hbase_dev, s->sel_host + 30, sizeof hb2, cudaMemcpyHostToDevice, s->stream));
+    }
     const int lb = std::min(kArgmaxBlocks, grid_for(s, s->n, 256));
     pdl(k_argmax_list, lb, 256, 0, s)(s->counters, s->worklist, s->score, s->block_best, nullptr, 0.0, 0.0, nullptr, nullptr); s->launches++;
     s->pick = PickSrc();
@@ -1173,6 +1178,7 @@ int propose_sub(ital_shard* s, int tB, int64_t only_local, bool any_local) {
     a.CU = s->sb_small + off_CU;
     a.BS = s->sb_small + off_BS;
     a.sub_bits = ss.sub_bits;
+    a.c1 = std::pow(1.0 - s->mistake_prob, (double)(tB + 1));
     a.q_last = u >= 2 ? snq::order_for(u - 1) : 1;
     a.R = snq::kR;
     a.q_min = snq::kQMin;
@@ -1994,8 +2000,8 @@ int ital_fetch_propose_sub(ital_shard* s, int n_batch, int64_t only_row, double*
     if (!s || !record) return fail(ITAL_EINVAL, "ital_fetch_propose_sub: bad arguments");
     if (!s->fetching || !s->sub_mode) return fail(ITAL_ESTATE, "ital_fetch_propose_sub outside a fetch in subset mode");
     if (s->lazy_rows) return fail(ITAL_ESTATE, "ital_fetch_propose_sub needs the streaming pass (lazy rows off)");
-    if (!(s->label_prob >= 1.0 && s->mistake_prob <= 0.0) || s->estimation != 0)
-        return fail(ITAL_EINVAL, "change_estimation_subset is built for users who label every sample without mistakes and label_estimation 'mean'");
+    if (!(s->label_prob >= 1.0) || s->estimation != 0)
+        return fail(ITAL_EINVAL, "change_estimation_subset is built for users who label every sample (label_prob = 1) and label_estimation 'mean'");
     if (n_batch < 0 || n_batch > s->t || n_batch > 7 || s->t > kSubMaxCols)
         return fail(ITAL_EINVAL, "ital_fetch_propose_sub: %d batch samples of %d columns (at most 7 of %d)", n_batch, s->t, kSubMaxCols);
     CU(cudaSetDevice(s->device));

@@ -1913,6 +1913,7 @@ struct SubArgs {
     const double* CU;           // [u][u]: covariance of S' given labels on B
     const double* BS;           // [u][D]: Bm Sig (covariance of S' with eta)
     int sub_bits;               // s*
+    double c1;                  // (1 - mistake_prob)^(tB + 1): probability that no label of the batch + candidate is wrong
     int q_last;                 // Gauss-Legendre nodes per panel of the per-candidate rule (u - 1 variables)
     double R;
     int q_min;
@@ -2073,7 +2074,8 @@ __global__ void __launch_bounds__(256) k_eval_sub(SubArgs a) {
             const double p_r = fmax(rc ? acc[g] : a.mass[g] - acc[g], 0.0);
             const double P = fmax(rc ? acc[G + g] : a.mass[G + g] - acc[G + g], 0.0);
             const double q = fmin(fmax(qv[threadIdx.x], 0.0), 1.0);
-            term = p_r * (log(q + kEps) - log(P + kEps));
+            // a user who mislabels (ital.py:317-328): any wrong label contradicts r and leaves probability ~0 for it
+            term = p_r * (a.c1 * log(q + kEps) + (1.0 - a.c1) * log(kEps) - log(P + kEps));
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) term += __shfl_xor_sync(0xffffffffu, term, o);

@@ -605,16 +605,14 @@ class ITAL(object):
         if k > limit:               # before any work (and before any collective) -- not in the middle of the greedy loop
             raise NotImplementedError('batches of more than %d samples are not supported%s' % (
                 limit, " with label_prob < 1 or label_estimation other than 'mean'" if general else ''))
-        if self.clip_cov and 0 < self.clip_cov < 1 and k > 5 and (general or self.mistake_prob > 0):
-            raise NotImplementedError('clip_cov with more than 5 samples is built for label_prob=1, mistake_prob=0, '
-                                      "label_estimation='mean'")
+        # clip_cov only matters from the sixth sample on (ital.py:360), i.e. only for label_prob = 1 and 'mean' (the other
+        # models stop at 5 samples above); a user who mislabels adds the same per-step constant as without clipping
         ce = self.change_estimation_subset
         if ce is None:              # every unseen sample in the subset: orthant probabilities in n dimensions
             raise NotImplementedError('change_estimation_subset=None (all unseen samples) is not built')
         if ce > 0:
-            if general or self.mistake_prob > 0:
-                raise NotImplementedError('change_estimation_subset is built for label_prob=1, mistake_prob=0, '
-                                          "label_estimation='mean'")
+            if general:
+                raise NotImplementedError("change_estimation_subset is built for label_prob=1, label_estimation='mean'")
             if k > self.MAX_BATCH_SUBSET or k - 1 + ce > self.MAX_COLS_SUBSET:
                 raise NotImplementedError('change_estimation_subset: at most %d samples per batch and batch + subset '
                                           '<= %d' % (self.MAX_BATCH_SUBSET, self.MAX_COLS_SUBSET + 1))
@@ -683,7 +681,7 @@ class ITAL(object):
         ret, self.last_fetch_scores, self.last_subset, self.last_step_scores = [], [], list(S), []
 
         def evaluate(batch, sub, only):
-            sh.fetch_begin(1.0, 0.0)
+            sh.fetch_begin(1.0, self.mistake_prob)
             try:
                 for e in batch + sub:
                     sh.fetch_commit(comm.sum_records(sh.export_points([e]))[0])

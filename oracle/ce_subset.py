@@ -95,7 +95,7 @@ def sub_sets(tB, m, L, noise):
                 mU=mU_all, CU=CU, BS=BS)
 
 
-def mi_sub_shared(tB, m_ext, L_ext, m_c, l_c, v_c, noise):
+def mi_sub_shared(tB, m_ext, L_ext, m_c, l_c, v_c, noise, mistake_prob=0.0):
     """Scores of many candidates: m_c (n,), l_c (n, D) projections on L_ext, v_c (n,) posterior variances -> (n,)."""
     m_c = np.asarray(m_c, dtype=np.float64)
     l_c = np.asarray(l_c, dtype=np.float64).reshape(len(m_c), -1)
@@ -120,6 +120,7 @@ def mi_sub_shared(tB, m_ext, L_ext, m_c, l_c, v_c, noise):
     sstar = [(S['sub_bits'] >> a) & 1 for a in range(u)]
     cv = l_c @ S['BS'].T                                   # (n, u): covariance of S' with the candidate's label
     mi = np.zeros(len(m_c))
+    c1 = (1.0 - mistake_prob) ** (tB + 1)
     for g in range(G):
         A1 = cdf_sum(S['part1'][g], sB)
         A2 = cdf_sum(S['part2'][g], sF)
@@ -137,7 +138,8 @@ def mi_sub_shared(tB, m_ext, L_ext, m_c, l_c, v_c, noise):
                     cov_u = S['CU'] - np.outer(cv[c], cv[c]) / tau2[c]
                     q[c] = orthant_prob(sstar, mean_u, cov_u, snq_order(u - 1) if u > 1 else None)
             q = np.clip(q, 0.0, 1.0)
-            mi += p_r * (np.log(q + EPS) - np.log(P + EPS))
+            # a user who mislabels (fb_iter / likelihood, ital.py:317-328, 453-481): any wrong label contradicts r
+            mi += p_r * (c1 * np.log(q + EPS) + (1.0 - c1) * np.log(EPS) - np.log(P + EPS))
     return mi
 
 
@@ -164,23 +166,34 @@ def orthant_prob_any(rel, mean, cov, n_lattice=65536):
     return float(w @ ((num > 0) == rel[t]))
 
 
-def mi_sub_literal(learner, ret, rel_it, n_lattice=65536):
+def mi_sub_literal(learner, ret, rel_it, n_lattice=65536, mistake_prob=0.0):
     """MutualInformation._call_iter_sub (ital.py:227-275) for one candidate, call by call.  ``learner``: OracleITAL
-    (rel_mean, gp.predict_stored, updated_prediction); ret: sample indices; rel_it: positions in ret to integrate over."""
+    (rel_mean, gp.predict_stored, updated_prediction); ret: sample indices; rel_it: positions in ret to integrate over.
+    mistake_prob > 0: the feedback configurations of a user who labels everything but errs (fb_iter ital.py:317-328,
+    likelihood ital.py:453-481)."""
     ret = [int(i) for i in ret]
     mean = learner.rel_mean[ret]
     cov = learner.gp.predict_stored(ret, cov_mode='full')[1]
     mean_it, cov_it = mean[rel_it], cov[np.ix_(rel_it, rel_it)]
     rel_vec = mean > 0
+    order = sorted(range(len(ret)), key=lambda a: ret[a])                       # updated_prob_rel sorts by index
     mi = 0.0
     for reli in itertools.product([False, True], repeat=len(rel_it)):
         rv = rel_vec.copy()
         rv[rel_it] = reli
         pr = orthant_prob_any(reli, mean_it, cov_it, n_lattice)
         log_pr = np.log(orthant_prob_any(rv, mean, cov, n_lattice) + EPS)
-        feedback = {ret[i]: (1 if r else -1) for i, r in zip(rel_it, reli)}
-        order = sorted(range(len(ret)), key=lambda a: ret[a])                   # updated_prob_rel sorts by index
-        mean_u, cov_u = learner.updated_prediction(feedback, [ret[a] for a in order])
-        pr_updated = orthant_prob_any(rv[order], mean_u, cov_u, n_lattice)
-        mi += pr * (np.log(pr_updated + EPS) - log_pr)
+        if mistake_prob > 0:
+            fbs = list(itertools.product([-1, 1], repeat=len(rel_it)))
+        else:
+            fbs = [tuple(1 if r else -1 for r in reli)]
+        for fbi in fbs:
+            like = 1.0
+            if mistake_prob > 0:
+                for r, f in zip(reli, fbi):
+                    like *= (1.0 - mistake_prob) if (f > 0) == bool(r) else mistake_prob
+            feedback = {ret[i]: f for i, f in zip(rel_it, fbi)}
+            mean_u, cov_u = learner.updated_prediction(feedback, [ret[a] for a in order])
+            pr_updated = orthant_prob_any(rv[order], mean_u, cov_u, n_lattice)
+            mi += pr * like * (np.log(pr_updated + EPS) - log_pr)
     return mi

@@ -419,11 +419,11 @@ class OracleITAL(object):
             L = safe_cholesky(cov_ext)
             l = scipy.linalg.solve_triangular(L, cov_ext_test[:, rows], lower=True).T
         m_ext = self.rel_mean[ext] if len(ext) else np.zeros(0)
-        return mi_sub_shared(len(batch), m_ext, L, self.rel_mean[rows], l, var0[rows], self.noise)
+        return mi_sub_shared(len(batch), m_ext, L, self.rel_mean[rows], l, var0[rows], self.noise, self.mistake_prob)
 
     def _fetch_change_subset(self, k, candidates, subset, forced=None):
-        if not (self._perfect_user() and self.label_estimation == 'mean'):
-            raise NotImplementedError('change_estimation_subset is restated for users who label everything correctly')
+        if not (self.label_prob >= 1 and self.label_estimation == 'mean'):
+            raise NotImplementedError('change_estimation_subset is restated for users who label everything')
         ret = []
         self.trace = []
         self.subset = list(subset)

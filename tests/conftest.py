@@ -41,6 +41,7 @@ def load_subset(name):
                     for u in range(int(g['n_updates']))]
     g['steps'] = [dict(candidates=g['step%d_candidates' % t], mi=g['step%d_mi' % t], chosen=int(g['step%d_chosen' % t]))
                   for t in range(len(g['ret']))]
+    g.setdefault('mistake_prob', 0.0)
     return g
 
 

@@ -54,7 +54,8 @@ def run_case(name, X, updates, k, seed, kw):
     assert learner.fetch_unlabelled(k) == ret, 'replay differs from ITAL.fetch_unlabelled'
     out = dict(X=X, k=k, seed=seed, ret=np.array(ret, dtype=np.int64), subset=np.array(subset, dtype=np.int64),
                rel_mean=np.array(learner.rel_mean), n_updates=len(updates),
-               change_estimation_subset=int(kw['change_estimation_subset']))
+               change_estimation_subset=int(kw['change_estimation_subset']),
+               mistake_prob=float(kw.get('mistake_prob', 0.0)))
     for key in ('length_scale', 'var', 'noise'):
         out[key] = float(kw.get(key, dict(length_scale=0.1, var=1.0, noise=1e-6)[key]))
     for u, fb in enumerate(updates):
@@ -79,6 +80,8 @@ if __name__ == '__main__':
     upd_b = mg.labelled_rounds(yb[sub], int(yb[sub][0]), rng, 1)
     for name, args in (('toy_c3_k3', (X, upd, 3, 11, dict(length_scale=0.1, change_estimation_subset=3))),
                        ('toy_c2_k4', (X, upd, 4, 5, dict(length_scale=0.1, change_estimation_subset=2))),
-                       ('butterflies_c3_k2', (Xb[sub], upd_b, 2, 3, dict(length_scale=2.5, change_estimation_subset=3)))):
+                       ('butterflies_c3_k2', (Xb[sub], upd_b, 2, 3, dict(length_scale=2.5, change_estimation_subset=3))),
+                       ('toy_c2_k3_mp02', (X, upd, 3, 9, dict(length_scale=0.1, change_estimation_subset=2,
+                                                              label_prob=1.0, mistake_prob=0.2)))):
         if not want or name in want:
             run_case(name, *args)

@@ -194,7 +194,7 @@ def test_reset_and_unsupported_modes(make):
     L.reset()
     assert L.rounds == 0 and L.rel_mean is None and L.get_unseen() == list(range(20))
     for kw in (dict(change_estimation_subset=None), dict(change_estimation_subset=3, label_prob=0.5),
-               dict(change_estimation_subset=3, mistake_prob=0.1), dict(change_estimation_subset=12)):
+               dict(change_estimation_subset=12)):
         B = make(**kw)
         B.update({0: 1})
         with pytest.raises(NotImplementedError):
@@ -203,7 +203,7 @@ def test_reset_and_unsupported_modes(make):
     C.update({0: 1})
     assert len(C.fetch_unlabelled(5)) == 5
     assert len(C.fetch_unlabelled(6)) == 6
-    G = make(clip_cov=0.5, mistake_prob=0.1)           # ... built for users who label everything correctly
+    G = make(clip_cov=0.5, label_prob=0.5)             # ... the general model stops at 5 samples with or without it
     G.update({0: 1})
     assert len(G.fetch_unlabelled(5)) == 5
     with pytest.raises(NotImplementedError):

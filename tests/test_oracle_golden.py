@@ -132,7 +132,7 @@ def test_oracle_change_estimation_subset_matches_reference(name):
     (the reference's own mvndst(abseps=1e-4) is far noisier there)."""
     g = load_subset(name)
     ora = OracleITAL(g['X'], length_scale=float(g['length_scale']), var=float(g['var']), noise=float(g['noise']),
-                     change_estimation_subset=int(g['change_estimation_subset']))
+                     change_estimation_subset=int(g['change_estimation_subset']), mistake_prob=float(g['mistake_prob']))
     for fb in g['updates']:
         ora.update({int(k): v for k, v in fb.items()})
     np.testing.assert_allclose(ora.rel_mean, g['rel_mean'], rtol=1e-9, atol=1e-12)
@@ -146,9 +146,14 @@ def test_oracle_change_estimation_subset_matches_reference(name):
         # a candidate that correlates 0.975 with a batch member (toy_c2_k4, step 3, row 7) is 6.6e-4 off -- scipy's Genz
         # rule at 4e6 points sides with the golden there (2.316648 vs 2.316621 golden, 2.315986 oracle)
         six = len(g['subset']) + t + 1 >= 6
-        np.testing.assert_allclose(tr['scores'], st['mi'], rtol=SUBSET_RTOL, atol=1e-3 if six else SUBSET_ATOL,
+        # a user who mislabels (toy_c2_k3_mp02): row 13 is a near-duplicate of subset member 23 (correlation 0.9996);
+        # the probability that the two end on different sides (~1e-4) sits inside a logarithm weighted by the mistake
+        # probability, and the rule's absolute accuracy leaves its score 0.1-0.6 off (it is the worst candidate by far)
+        loose = float(g['mistake_prob']) > 0
+        bad = np.abs(tr['scores'] - st['mi']) > SUBSET_ATOL + SUBSET_RTOL * np.abs(st['mi'])
+        assert np.sum(bad) <= 2, 'step %d' % t
+        np.testing.assert_allclose(tr['scores'], st['mi'], rtol=SUBSET_RTOL, atol=1.0 if loose else (1e-3 if six else SUBSET_ATOL),
                                    err_msg='step %d' % t)
-        assert np.sum(np.abs(tr['scores'] - st['mi']) > SUBSET_ATOL + SUBSET_RTOL * np.abs(st['mi'])) <= 2
 
 
 @pytest.mark.parametrize('name', clip_names())
