@@ -284,8 +284,39 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
         win = group_argmax(bs, bi, tid, kFusedThreads, 0, ss, si);
     }
 
+    // stage A of a step: every team takes the maximum of the bound (gain) in its strided subset of the pool, leaving
+    // out the rows in excl[] (selected so far)
+    auto stage_a_scan = [&](const int* excl) -> Best {
+        double bs = 0.0;
+        long long bi = -1;
+        const int64_t stride = (int64_t)n_teams * kFusedTeam;
+        for (int64_t i0 = (int64_t)gt * kFusedTeam + tid_team; i0 < a.n; i0 += 4 * stride) {
+            uint8_t mk[4];
+            double val[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t i = i0 + u * stride;
+                mk[u] = i < a.n ? a.mask[i] : (uint8_t)1;
+                val[u] = i < a.n ? __ldcg(a.gain + i) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t i = i0 + u * stride;
+                const int ii = (int)i;
+                const bool ok = mk[u] == 0 && ii != excl[0] && ii != excl[1] && ii != excl[2] && ii != excl[3];
+                // (score desc, row asc; a NaN bound never wins) -- rows come in ascending order per thread
+                if (ok && (bi < 0 ? val[u] == val[u] : val[u] > bs)) { bs = val[u]; bi = i; }
+            }
+        }
+        return group_argmax(bs, bi, tid_team, kFusedTeam, team_bar, ss + team * 16, si + team * 16);
+    };
     bool dead = false;
     for (int t = 0; t < a.k; ++t) {
+        bool have_early = false;
+        Best early_b;
+        early_b.score = 0.0;
+        early_b.idx = -1;
+        long long early_prop = -1;
         // ---- commit the winner of step t (np.argmax + AppendedMutualInformation.append, ital.py:130-131) ----------
         // every CTA builds the winner's record in its own shared memory; CTA 0 also writes the global batch state
         double* rec = recs + (size_t)t * a.rec_len;
@@ -327,6 +358,18 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
             PeerPut pp = a.pp;
             pp.epoch = a.pp.epoch + (unsigned long long)t;
             if (blockIdx.x == 0) peer_put(pp, rec, a.rec_len);
+            if (t + 1 < a.k && row >= 0) {
+                // while the proposals travel: stage A of the next step needs the gains only, not the winner
+                int excl[kFusedMaxSteps];
+#pragma unroll
+                for (int c = 0; c < kFusedMaxSteps; ++c) excl[c] = c < t ? (int)sel_loc[c] : -1;
+                excl[t] = (int)row;                                     // (t < kFusedMaxSteps - 1 here)
+                // CTA 0 is busy with the exchange itself (record, stores, system fence): its two teams sit this
+                // stage A out -- the sample only sets the pruning threshold, 2 of 296 subsets less do not matter
+                if (blockIdx.x != 0) early_b = stage_a_scan(excl);
+                early_prop = row;
+                have_early = true;
+            }
             if (tid < pp.G) {
                 const unsigned long long t0 = global_ns();
                 unsigned spins = 0;
@@ -444,28 +487,20 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fetch_fused(FusedArgs a) {
         for (int c = 0; c < kFusedMaxSteps; ++c) selr[c] = c <= t ? (int)sel_loc[c] : -1;
         long long a_row = -1;                                           // the team's stage-A row
         if (!dead) {
-            double bs = 0.0;
-            long long bi = -1;
-            const int64_t stride = (int64_t)n_teams * kFusedTeam;
-            for (int64_t i0 = (int64_t)gt * kFusedTeam + tid_team; i0 < a.n; i0 += 4 * stride) {
-                uint8_t mk[4];
-                double val[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int64_t i = i0 + u * stride;
-                    mk[u] = i < a.n ? a.mask[i] : (uint8_t)1;
-                    val[u] = i < a.n ? __ldcg(a.gain + i) : 0.0;
+            Best b;
+            if (have_early) {
+                // the scan ran while the proposals were on their way (in the exchange above, several GPUs): it left out this shard's own
+                // proposal, which is still a candidate if another shard's won -- the team that owns it adds it back
+                b = early_b;
+                int owner = (int)((early_prop / kFusedTeam) % n_teams);
+                if (owner < kFusedTeams && n_teams > 2 * kFusedTeams) owner += kFusedTeams;     // (not a team of CTA 0)
+                if (early_prop >= 0 && early_prop != sel_loc[t] && owner == gt) {
+                    const double gv = __ldcg(a.gain + early_prop);
+                    if (gv == gv && (b.idx < 0 || better(gv, early_prop, b.score, b.idx))) { b.score = gv; b.idx = early_prop; }
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int64_t i = i0 + u * stride;
-                    const int ii = (int)i;
-                    const bool ok = mk[u] == 0 && ii != selr[0] && ii != selr[1] && ii != selr[2] && ii != selr[3];
-                    // (score desc, row asc; a NaN bound never wins) -- rows come in ascending order per thread
-                    if (ok && (bi < 0 ? val[u] == val[u] : val[u] > bs)) { bs = val[u]; bi = i; }
-                }
+            } else {
+                b = stage_a_scan(selr);
             }
-            const Best b = group_argmax(bs, bi, tid_team, kFusedTeam, team_bar, ss + team * 16, si + team * 16);
             a_row = b.idx;
             if (a_row >= 0 && warp_team == 1 && lane < 2) prefetch_l2(lane == 0 ? a.m + a_row : a.v + a_row);
             if (a_row >= 0 && warp_team == 0)
