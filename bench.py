@@ -633,7 +633,8 @@ def main():
                            % (fused_steps, args.batch),
                    'parallelism': 'rows sharded over %d GPU(s); per greedy step every shard %s' % (
                        world, 'stores its proposal into its peers\' memory over NVLink from inside the persistent kernel '
-                              '(CUDA IPC; no NCCL in the loop)' if used_peer else 'contributes one record to an NCCL all-gather'),
+                              '(CUDA IPC; no NCCL in the loop)' if used_peer else
+                       ('needs no exchange (one shard)' if world == 1 else 'contributes one record to an NCCL all-gather')),
                    'batch_selected': [int(i) for i in ret], 'batch_scores': scores},
         'e2e': {'value': ranked * args.steps / wall, 'unit': UNIT, 'ms_per_step': wall / args.steps * 1e3,
                 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),

@@ -199,6 +199,9 @@ def cases():
     yield 'syn2000_k2', (Xs, upd_s, 2, dict(length_scale=1.0)), {}
     yield 'syn200_k4', (Xs[:200].copy(), [{0: 1}, {3: -1, 9: -1, 11: 1 if ys[11] else -1, 20: -1}], 4,
                         dict(length_scale=1.0)), {}
+    # configs/toy.conf ships batch_size = 6: the fifth and sixth pick use five and six variables (tensor rule on the
+    # device for 4 and 5 base variables); the stand-in takes ~1 s per six-variable probability, ~15 min for this case
+    yield 'toy_perfect_k6', (Xt, upd_t, 6, dict(length_scale=0.1)), {}
 
 
 def updated_prediction_cases():
