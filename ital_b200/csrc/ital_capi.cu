@@ -1053,10 +1053,9 @@ int propose_clip(ital_shard* s) {
         d.h_rest = 0.0;
         for (int b = 0; b < t; ++b)
             if (__builtin_ctz(comp_mask[b]) == b && !(S & comp_mask[b])) d.h_rest += h_comp[b];
-        // eta of the set dimension-major, its weights at eta_off / dims
-        // (weights of all sets are kept in their own array at the same node offsets)
+        // coordinates of the set (dimension-major, stride = its own node count) and its weights, each in one array
+        // shared by all sets: offsets eta_off / pad
         eta.insert(eta.end(), nd.eta.begin(), nd.eta.end());
-        // pad w so that w offset = eta_off / dims holds: keep a parallel list of offsets instead
         d.pad = (int)w.size();
         w.insert(w.end(), nd.w.begin(), nd.w.end());
     }

@@ -94,7 +94,12 @@ def test_two_gpus_match_one_gpu_and_oracle(local_rows, peer):
         np.testing.assert_allclose(rel_mean, ora_mean, rtol=1e-6, atol=1e-9)
 
 
-def _subset_worker(rank, world, port, q):
+MODES = {'subset': (dict(length_scale=1.0, change_estimation_subset=3), 3),
+         'subset_mistakes': (dict(length_scale=1.0, change_estimation_subset=2, mistake_prob=0.2), 3),
+         'clip_cov': (dict(length_scale=1.0, clip_cov=0.3), 7)}
+
+
+def _mode_worker(rank, world, port, q, mode):
     import torch
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'
@@ -103,27 +108,30 @@ def _subset_worker(rank, world, port, q):
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
     try:
         from ital_b200 import ITAL
-        X, fb = _subset_problem()
-        learner = ITAL(X, length_scale=1.0, device=rank, process_group=True, change_estimation_subset=3)
+        X, fb = _mode_problem()
+        kw, k = MODES[mode]
+        learner = ITAL(X, device=rank, process_group=True, **kw)
         learner.update(fb)
         np.random.seed(21)                              # every rank draws the same subset
-        ret = learner.fetch_unlabelled(3)
-        q.put((rank, ret, learner.last_subset, list(learner.last_fetch_scores)))
+        ret = learner.fetch_unlabelled(k)
+        q.put((rank, ret, getattr(learner, 'last_subset', None), list(learner.last_fetch_scores)))
         learner.close()
     finally:
         dist.destroy_process_group()
 
 
-def _subset_problem(n=61, seed=2):
+def _mode_problem(n=61, seed=2):
     rng = np.random.RandomState(seed)
-    X = rng.randn(n, 2)
+    X = rng.randn(n, 2) * 1.3
     y = np.where(X[:, 0] - 0.4 * X[:, 1] > 0, 1, -1)
     return X, {1: int(y[1]), 6: int(y[6]), 20: int(y[20]), 40: int(y[40])}
 
 
-def test_change_estimation_subset_on_two_gpus():
-    """The stepwise protocol of the subset mode over two shards (records of batch + subset summed over the ranks, the
-    shards' best records gathered): same subset, batch and scores as one GPU."""
+@pytest.mark.parametrize('mode', sorted(MODES))
+def test_subset_and_clip_modes_on_two_gpus(mode):
+    """change_estimation_subset (stepwise protocol: records of batch + subset summed over the ranks, the shards' best
+    records gathered) and clip_cov (per-shard adjacency pass and node sets) over two shards: same subset, batch and
+    scores as one GPU."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
@@ -132,18 +140,19 @@ def test_change_estimation_subset_on_two_gpus():
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_subset_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_mode_worker, args=(r, 2, port, q, mode)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted((q.get(timeout=300) for _ in procs), key=lambda r: r[0])
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    X, fb = _subset_problem()
-    one = ITAL(X, length_scale=1.0, device=0, change_estimation_subset=3)
+    X, fb = _mode_problem()
+    kw, k = MODES[mode]
+    one = ITAL(X, device=0, **kw)
     one.update(fb)
     np.random.seed(21)
-    want = one.fetch_unlabelled(3)
+    want = one.fetch_unlabelled(k)
     for rank, ret, subset, scores in res:
-        assert subset == one.last_subset and ret == want
+        assert subset == getattr(one, 'last_subset', None) and ret == want
         np.testing.assert_allclose(scores, one.last_fetch_scores, rtol=1e-9, atol=1e-12)
