@@ -1566,6 +1566,8 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
         CU(cudaMalloc(&s->v, (size_t)s->n * sizeof(double)));
         CU(cudaMalloc(&s->gain, (size_t)s->n * sizeof(double)));
         CU(cudaMalloc(&s->score, (size_t)s->n * sizeof(double)));
+        CU(cudaMemset(s->gain, 0, (size_t)s->n * sizeof(double)));      // (read by the worklist scans before the first score)
+        CU(cudaMemset(s->score, 0, (size_t)s->n * sizeof(double)));
         CU(cudaMalloc(&s->mask, (size_t)s->n));
         CU(cudaMalloc(&s->tags, (size_t)s->n * sizeof(uint32_t)));
         CU(cudaMemset(s->tags, 0, (size_t)s->n * sizeof(uint32_t)));

@@ -1182,7 +1182,8 @@ __global__ void __launch_bounds__(256) k_worklist(int64_t n, const uint8_t* __re
         const int64_t i = i0 + lane;
         const uint8_t mk = i < n ? __ldg(mask + i) : (uint8_t)1;      // both loads issued before either is used
         const double gv = i < n ? __ldg(gain + i) : 0.0;
-        const bool take = mk == 0 && gv >= thr;
+        // (exhaustive: the gain is not looked at -- it may never have been written, and a NaN would drop the row)
+        const bool take = mk == 0 && (exhaustive != 0 || gv >= thr);
         const unsigned ballot = __ballot_sync(0xffffffffu, take);
         if (ballot != 0) {
             int base = 0;
