@@ -155,7 +155,26 @@ class _StubShard(object):
         return rec
 
     def fetch_commit(self, record):
+        assert record[0] >= 0 and (record[2] == 100.0 + record[0] or record[2] == 0.0), 'incomplete record'
         self.selected.add(int(record[0]))
+
+    # -- change_estimation_subset: batch + subset are committed as batch columns, then one proposal per evaluation --
+    def set_sub_mode(self, on):
+        self.sub_mode = bool(on)
+
+    def fetch_propose_sub(self, n_batch, only_row):
+        rec = np.zeros(self.record_doubles())
+        rec[0], rec[1] = -1.0, -np.inf
+        for g in range(self.lo, min(self.lo + self.n_local, self.n_data)):
+            if g in self.seen or g in self.selected or (only_row >= 0 and g != only_row):
+                continue
+            sc = self.score(g) - 0.001 * n_batch
+            if sc > rec[1]:
+                rec[0], rec[1] = g, sc
+        return rec
+
+    def last_scores(self):
+        return np.full(self.n_local, np.nan)
 
     def fetch_end(self):
         self.selected = set()
@@ -180,7 +199,15 @@ def _learner_worker(rank, world, port, out):
         L = learner_mod.ITAL(X, length_scale=1.0, process_group=True)
         L.update({3: 1, 20: -1, 11: 0})                # rows 3 and 20 live on different shards
         batch = L.fetch_unlabelled(5)
-        out.put((rank, batch, L._shard.labelled, L.rel_mean.tolist(), int(L._shard.n_local), bool(L._peer)))
+        # change_estimation_subset over the same two shards: every rank draws the same subset (same seed), the records
+        # of batch + subset are completed over the ranks before they are committed, proposals are gathered per evaluation
+        S = learner_mod.ITAL(X, length_scale=1.0, process_group=True, change_estimation_subset=3)
+        S.update({3: 1, 20: -1, 11: 0})
+        np.random.seed(5)
+        sub_batch = S.fetch_unlabelled(3)
+        out.put((rank, batch, L._shard.labelled, L.rel_mean.tolist(), int(L._shard.n_local), bool(L._peer),
+                 sub_batch, list(S.last_subset)))
+        S.close()
         L.close()
     finally:
         dist.destroy_process_group()
@@ -203,7 +230,11 @@ def test_sharded_learner_host_loop_over_gloo_world2():
     cand = [i for i in range(23) if i not in (3, 20, 11)]
     want = sorted(cand, key=lambda i: (-_StubShard.score(i), i))[:5]
     assert sorted(r[4] for r in res) == [11, 12]
-    for rank, batch, labelled, rel_mean, n_local, peer in res:
+    np.random.seed(5)
+    want_subset = sorted(int(i) for i in np.random.choice(cand, 3, replace=False))
+    for rank, batch, labelled, rel_mean, n_local, peer, sub_batch, subset in res:
+        assert subset == want_subset
+        assert sub_batch == want[:3]                   # (the stub's scores do not depend on the subset)
         assert batch == want
         assert labelled == [3, 20]
         assert rel_mean == list(map(float, range(23)))
