@@ -84,3 +84,23 @@ def test_rules_of_longer_batches_match_scipy_genz(D, tol):
     got = orthant_prob_all(mean, cov, snq_order(D - 1) or None)
     assert abs(got.sum() - 1.0) < 1e-5
     assert np.max(np.abs(got - want)) <= tol, (D, np.max(np.abs(got - want)))
+
+
+@pytest.mark.parametrize('D', [6, 8])
+def test_single_orthant_lattice_matches_scipy_genz(D):
+    """change_estimation_subset: the probability that batch + subset (+ candidate) land in ONE orthant of 6 to 9
+    variables comes from 16 384 lattice nodes inside that orthant (oracle/orthant.py sc_orthant = csrc/snq_host.h
+    sc_orthant) with the last variable analytic (oracle/ce_subset.py orthant_prob_any).  Against scipy's Genz rule at
+    2 * 10^6 points: 1e-4 relative for orthants that carry at least a percent of the mass -- the accuracy class stated
+    for this mode (the reference's own mvndst(maxpts = 100 * dim) is 1e-3 there)."""
+    from oracle.ce_subset import SUB_N, orthant_prob_any
+    rng = np.random.default_rng(300 + D)
+    for trial in range(2):
+        mean, cov = _random_block(rng, D, strength=(0.3, 1.0)[trial])
+        rel = mean > 0                                   # the most likely orthant
+        sgn = np.where(rel, -1.0, 1.0)
+        want = multivariate_normal(mean=sgn * mean, cov=cov * np.outer(sgn, sgn), allow_singular=True,
+                                   maxpts=2000000, abseps=1e-10, releps=1e-10, seed=trial).cdf(np.zeros(D))
+        got = orthant_prob_any(rel, mean, cov, n_lattice=SUB_N)
+        assert want > 1e-2
+        assert abs(got - want) <= 1e-4 * want, (D, trial, got, want)
