@@ -1591,6 +1591,8 @@ int ital_create(ital_shard** out, int device, const void* X, int x_dtype, int64_
         CU(cudaMalloc(&s->thr_dev, sizeof(double)));
         CU(cudaMalloc(&s->base_m_dev, 16 * sizeof(double)));
         CU(cudaMalloc(&s->base_L_dev, 16 * 16 * sizeof(double)));
+        CU(cudaMemset(s->base_m_dev, 0, 16 * sizeof(double)));             // (copied whole to the host by the paths that
+        CU(cudaMemset(s->base_L_dev, 0, 16 * 16 * sizeof(double)));        //  build node sets there)
         CU(cudaMalloc(&s->sel_dev, 32 * sizeof(double) + 16 * 4 * sizeof(int)));   // selection list, then the step stats
         CU(cudaMalloc(&s->hbase_dev, 2 * sizeof(double)));      // [0] H(base), [1] total quadrature mass
         CU(cudaMemset(s->hbase_dev, 0, 2 * sizeof(double)));
